@@ -1,0 +1,150 @@
+/*
+ * tornadox_b200 -- C ABI of the B200-native tornadox filter step.
+ *
+ * The reference (pnkraemer/tornadox) is pure Python on JAX and has no FFI of its own.  The seam this
+ * library replaces is the abstract-method pair of ``ODEFilter`` (tornadox/odefilter.py:346-352)
+ *
+ *     initialize(self, f, t0, tmax, y0, df, df_diagonal)          -> ODEFilterState
+ *     attempt_step(self, state, dt, f, t0, tmax, y0, df, df_diagonal) -> (ODEFilterState, info)
+ *
+ * as implemented by ``ek1.DiagonalEK1`` (tornadox/ek1.py:228-369) and ``ek0.KroneckerEK0``
+ * (tornadox/ek0.py:152-193), plus the d-wide reduction of ``AdaptiveSteps.scale_error_estimate``
+ * (tornadox/step.py:93-104) and the vector fields ``ivp.vanderpol / brusselator / lorenz96 / fhn_2d``
+ * (tornadox/ivp.py:28-49, 219-265, 268-294, 409-505), which are evaluated inside the step kernels.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; every array pointer is a DEVICE pointer owned by the caller;
+ *  - every call enqueues work on ``stream`` (a cudaStream_t passed as void*) and returns without
+ *    synchronising; scalars that the host loop needs are written to device scalars the caller reads;
+ *  - return value 0 = OK, otherwise a TDX_ERR_* code; ``tdx_last_error()`` has the message;
+ *  - in/out state buffers are distinct, so a rejected attempt leaves the input state untouched
+ *    (odefilter.py:186-219 re-attempts from the same state);
+ *  - layouts are the reference's: mean (n, d) C-order, DiagonalEK1 factors (d, n, n) C-order,
+ *    KroneckerEK0 factor (n, n) C-order; n = nu + 1; dtype is f64 (default) or f32.
+ *  - multi-GPU: one context per process/GPU owning a shard (rows of the fhn grid, or a range of the
+ *    1-d chain) of BOTH fields; the caller exchanges the halo buffers and all-reduces the scalars.
+ */
+#ifndef TORNADOX_B200_H_
+#define TORNADOX_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TDX_ABI_VERSION 1
+
+/* error codes */
+#define TDX_OK 0
+#define TDX_ERR_INVALID 1   /* bad argument (ValueError on the Python side)              */
+#define TDX_ERR_UNSUPPORTED 2 /* no kernel instantiated for this (kind, nu, dtype)       */
+#define TDX_ERR_CUDA 3      /* a CUDA runtime call failed                                */
+
+/* dtypes */
+#define TDX_F64 0
+#define TDX_F32 1
+
+/* vector fields evaluated in-kernel (tornadox/ivp.py) */
+#define TDX_IVP_VANDERPOL 0   /* params: [mu]                        ivp.py:28-49   */
+#define TDX_IVP_LORENZ96 1    /* params: [forcing]                   ivp.py:268-294 */
+#define TDX_IVP_BRUSSELATOR 2 /* params: [] (c derived from N)       ivp.py:219-265 */
+#define TDX_IVP_FHN2D 3       /* params: [dx, a, b, k, tau]          ivp.py:409-505 */
+
+typedef struct tdx_ctx tdx_ctx;
+
+/* Problem + shard geometry.  State layout is y = [field0(points); field1(points)] (ivp.py:229,438).
+ * fhn_2d: points = grid_rows x grid_cols row-major, shard = rows [shard_begin, shard_end).
+ * 1-d problems (lorenz96, brusselator): grid_rows = 1, grid_cols = N, shard = points
+ * [shard_begin, shard_end).  vanderpol: grid_rows = grid_cols = 1, one point with two fields. */
+typedef struct {
+    int32_t kind;          /* TDX_IVP_*                                                 */
+    int32_t nu;            /* num_derivatives (odefilter.py:34); n = nu + 1             */
+    int64_t grid_rows;     /* global                                                     */
+    int64_t grid_cols;     /* global                                                     */
+    int64_t shard_begin;   /* first owned row (fhn) / point (1-d)                        */
+    int64_t shard_end;     /* one past the last owned row / point                        */
+    int32_t n_params;
+    double params[8];
+} tdx_problem_desc;
+
+/* Per-attempt scalars of AdaptiveSteps (step.py:55-104); for ConstantSteps pass abstol=reltol=0
+ * and ignore the norm output. */
+typedef struct {
+    double t;       /* state.t (the kernels evaluate f at t + dt; all in-scope fields are autonomous) */
+    double dt;
+    double abstol;
+    double reltol;
+    uint32_t flags; /* TDX_STEP_* */
+    uint32_t reserved;
+} tdx_step_args;
+
+/* DiagonalEK0 (ek0.py:196-280): run the DiagonalEK1 kernel with the Jacobian diagonal forced to zero */
+#define TDX_STEP_ZERO_JACOBIAN 1u
+
+const char* tdx_last_error(void);
+int tdx_abi_version(void);
+
+/* context: one per device/shard.  ``device`` is the CUDA ordinal. */
+int tdx_create(tdx_ctx** out, int device, int dtype);
+int tdx_destroy(tdx_ctx* ctx);
+int tdx_set_problem(tdx_ctx* ctx, const tdx_problem_desc* desc);
+/* local state dimension d of this shard (n_fields * owned points) */
+int64_t tdx_local_dim(const tdx_ctx* ctx);
+/* number of halo scalars per side: lo = values needed from the lower neighbour, hi = from the upper;
+ * the same counts (swapped) are what tdx_pack_halo produces for the neighbours. */
+int tdx_halo_sizes(const tdx_ctx* ctx, int64_t* lo, int64_t* hi);
+
+/* Prior constants A (n,n) and Ql (n,n) the kernels use (iwp.py:19-37), written to HOST buffers. */
+int tdx_prior(int nu, double* A_out, double* Ql_out);
+/* Nordsieck preconditioner vectors (iwp.py:65-73), HOST buffers of n doubles each. */
+int tdx_nordsieck(int nu, double dt, double* p_out, double* p_inv_out);
+
+/* f(t, y) and optionally diag(df)(t, y) of the context's vector field on the local shard
+ * (replaces the Python callables ivp.f / ivp.df_diagonal; used for first_dt step.py:111-115,
+ * initialisation and tests).  halo_lo/halo_hi: neighbour values of y itself, or NULL. */
+int tdx_eval_f(tdx_ctx* ctx, double t, const void* y, void* fy, void* jdiag_or_null,
+               const void* halo_lo, const void* halo_hi, void* stream);
+
+/* Predicted state E0 P A P^-1 m (the point where f is evaluated, ek1.py:304-306 / ek0.py:146-147)
+ * at the shard's first / last rows or points, for the neighbours' halos.
+ * edge_first has halo_hi-of-lower-neighbour layout, edge_last has halo_lo-of-upper-neighbour layout. */
+int tdx_pack_halo(tdx_ctx* ctx, double dt, const void* mean_in, void* edge_first, void* edge_last,
+                  void* stream);
+
+/* DiagonalEK1.attempt_step (ek1.py:228-260 + 274-369), fused with
+ * sum_i (dt * err_i / (abstol + reltol * ref_i))^2 over the local shard (step.py:101-104),
+ * which is written to the device scalar ``sq_norm_sum`` (double).  err_out / ref_out may be NULL. */
+int tdx_dek1_attempt_step(tdx_ctx* ctx, const tdx_step_args* args, const void* mean_in,
+                          const void* sc_in, void* mean_out, void* sc_out, void* err_out,
+                          void* ref_out, const void* halo_lo, const void* halo_hi,
+                          double* sq_norm_sum, void* stream);
+
+/* KroneckerEK0.attempt_step (ek0.py:152-193) in three phases, so that a multi-GPU caller can
+ * all-reduce the device scalar between them:
+ *  sweep_a : predict + measure, writes sum_i z_i^2 over the local shard to ``z_sq_sum`` (double);
+ *  mid     : calibration, the single 2n x n QR, gain (ek0.py:123-140, 175); needs the GLOBAL
+ *            z_sq_sum and the global dimension; writes Cl_out (n,n), err_out (scalar, dtype) and the
+ *            gain into the context;
+ *  sweep_b : m_new = P (mp - K z), reference_state = |m_new[0]| (ref_out may be NULL) and
+ *            sum_i 1 / (abstol + reltol * ref_i)^2 -> ``inv_tol_sq_sum`` (double).
+ * The scaled error norm is then dt * err * sqrt(inv_tol_sq_sum / d_global) (step.py:101-104). */
+int tdx_ek0_sweep_a(tdx_ctx* ctx, const tdx_step_args* args, const void* mean_in,
+                    const void* halo_lo, const void* halo_hi, double* z_sq_sum, void* stream);
+int tdx_ek0_mid(tdx_ctx* ctx, const tdx_step_args* args, const void* Cl_in, const double* z_sq_sum,
+                int64_t d_global, void* Cl_out, void* err_out, void* stream);
+int tdx_ek0_sweep_b(tdx_ctx* ctx, const tdx_step_args* args, const void* mean_in, void* mean_out,
+                    void* ref_out, const void* halo_lo, const void* halo_hi,
+                    double* inv_tol_sq_sum, void* stream);
+/* single-GPU convenience: the three phases back to back on ``stream``. */
+int tdx_ek0_attempt_step(tdx_ctx* ctx, const tdx_step_args* args, const void* mean_in,
+                         const void* Cl_in, void* mean_out, void* Cl_out, void* err_out,
+                         void* ref_out, double* z_sq_sum, double* inv_tol_sq_sum, void* stream);
+
+/* kernels launched by this context since creation (bench.py's gpu_launches counter) */
+int64_t tdx_launch_count(const tdx_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TORNADOX_B200_H_ */

@@ -1,0 +1,65 @@
+"""Shared test helpers: build matching (oracle problem, product ivp) pairs and compare states."""
+
+import numpy as np
+
+from oracle.ref_np import driver as odriver
+from oracle.ref_np import problems as oproblems
+
+FP64_RTOL = 1e-10   # north_star: means and Cholesky factors within 1e-10 (fp64) / 1e-5 (fp32)
+FP32_RTOL = 1e-5
+
+
+def make_pair(kind, size, **kw):
+    """Return (oracle Problem, product InitialValueProblem, series_f) for a vector field at a given size."""
+    from tornadox_b200 import ivp as pivp
+
+    if kind == "vanderpol":
+        mu = kw.get("mu", 1.0)
+        o = oproblems.vanderpol(t0=0.0, tmax=kw.get("tmax", 1.0), stiffness_constant=mu)
+        p = pivp.vanderpol(t0=0.0, tmax=kw.get("tmax", 1.0), stiffness_constant=mu)
+        return o, p, odriver.series_vanderpol(mu)
+    if kind == "lorenz96":
+        o = oproblems.lorenz96(num_variables=size)
+        p = pivp.lorenz96(num_variables=size)
+        return o, p, odriver.series_lorenz96(8.0)
+    if kind == "brusselator":
+        o = oproblems.brusselator(N=size)
+        p = pivp.brusselator(N=size)
+        return o, p, odriver.series_brusselator(size)
+    if kind == "fhn_2d":
+        dx = 1.0 / size
+        y0 = np.random.default_rng(2).uniform(size=(2 * size * size,))
+        o = oproblems.fhn_2d(dx=dx, y0=y0)
+        p = pivp.fhn_2d(dx=dx, y0=y0)
+        nx, ny = oproblems.fhn_grid_size(None, dx)
+        assert nx == size, (nx, size)
+        return o, p, odriver.series_fhn_2d(nx, ny, dx)
+    raise KeyError(kind)
+
+
+def random_state(rng, n, d, cov="dense", mean_scale=1.0):
+    """A mid-solve looking state: O(1) mean rows and small factor blocks."""
+    mean = mean_scale * rng.standard_normal((n, d))
+    if cov == "zero":
+        sc = np.zeros((d, n, n))
+    elif cov == "dense":
+        sc = 1e-2 * rng.standard_normal((d, n, n))
+    elif cov == "lower":
+        sc = np.tril(1e-2 * rng.standard_normal((d, n, n)))
+    else:
+        raise KeyError(cov)
+    return mean, sc
+
+
+def rel_err(a, b):
+    """max |a - b| relative to the max-norm of the reference array b."""
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    assert a.shape == b.shape, (a.shape, b.shape)
+    scale = np.max(np.abs(b)) if b.size else 0.0
+    diff = np.max(np.abs(a - b)) if b.size else 0.0
+    return diff / scale if scale > 0 else diff
+
+
+def assert_close(a, b, rtol, what):
+    e = rel_err(a, b)
+    assert e <= rtol, f"{what}: relative error {e:.3e} > {rtol:.1e}"

@@ -1,0 +1,136 @@
+"""ctypes binding of ``libtornadox_b200.so`` (C ABI: include/tornadox_b200.h).
+
+There is NO fallback: if the shared library is missing or no CUDA device is present, every entry
+point that needs compute raises.  torch is used only for device buffers and streams.
+"""
+
+import ctypes
+import os
+import pathlib
+
+import numpy as np
+
+_PKG = pathlib.Path(__file__).resolve().parent
+LIB_PATH = _PKG / "lib" / "libtornadox_b200.so"
+
+TDX_F64, TDX_F32 = 0, 1
+TDX_STEP_ZERO_JACOBIAN = 1
+TDX_IVP_VANDERPOL, TDX_IVP_LORENZ96, TDX_IVP_BRUSSELATOR, TDX_IVP_FHN2D = 0, 1, 2, 3
+
+EXPORTED_SYMBOLS = (
+    "tdx_last_error", "tdx_abi_version", "tdx_create", "tdx_destroy", "tdx_set_problem", "tdx_local_dim",
+    "tdx_halo_sizes", "tdx_prior", "tdx_nordsieck", "tdx_eval_f", "tdx_pack_halo", "tdx_dek1_attempt_step",
+    "tdx_ek0_sweep_a", "tdx_ek0_mid", "tdx_ek0_sweep_b", "tdx_ek0_attempt_step", "tdx_launch_count",
+)
+
+
+class ProblemDesc(ctypes.Structure):
+    _fields_ = [
+        ("kind", ctypes.c_int32),
+        ("nu", ctypes.c_int32),
+        ("grid_rows", ctypes.c_int64),
+        ("grid_cols", ctypes.c_int64),
+        ("shard_begin", ctypes.c_int64),
+        ("shard_end", ctypes.c_int64),
+        ("n_params", ctypes.c_int32),
+        ("params", ctypes.c_double * 8),
+    ]
+
+
+class StepArgs(ctypes.Structure):
+    _fields_ = [
+        ("t", ctypes.c_double),
+        ("dt", ctypes.c_double),
+        ("abstol", ctypes.c_double),
+        ("reltol", ctypes.c_double),
+        ("flags", ctypes.c_uint32),
+        ("reserved", ctypes.c_uint32),
+    ]
+
+
+class TornadoxB200Error(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load():
+    """Load the shared library (building is the job of ``tornadox_b200.build`` / ``__graft_entry__.build``)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise TornadoxB200Error(
+            f"{LIB_PATH} not found: build it with `python -m tornadox_b200.build` "
+            "(tornadox_b200 has no CPU fallback and cannot run without its CUDA library)"
+        )
+    lib = ctypes.CDLL(str(LIB_PATH))
+    vp, i64, dbl, cint = ctypes.c_void_p, ctypes.c_int64, ctypes.c_double, ctypes.c_int
+    pd = ctypes.POINTER(ctypes.c_double)
+    lib.tdx_last_error.restype = ctypes.c_char_p
+    lib.tdx_last_error.argtypes = []
+    lib.tdx_abi_version.restype = cint
+    lib.tdx_create.argtypes = [ctypes.POINTER(vp), cint, cint]
+    lib.tdx_destroy.argtypes = [vp]
+    lib.tdx_set_problem.argtypes = [vp, ctypes.POINTER(ProblemDesc)]
+    lib.tdx_local_dim.restype = i64
+    lib.tdx_local_dim.argtypes = [vp]
+    lib.tdx_halo_sizes.argtypes = [vp, ctypes.POINTER(i64), ctypes.POINTER(i64)]
+    lib.tdx_prior.argtypes = [cint, pd, pd]
+    lib.tdx_nordsieck.argtypes = [cint, dbl, pd, pd]
+    lib.tdx_eval_f.argtypes = [vp, dbl, vp, vp, vp, vp, vp, vp]
+    lib.tdx_pack_halo.argtypes = [vp, dbl, vp, vp, vp, vp]
+    lib.tdx_dek1_attempt_step.argtypes = [vp, ctypes.POINTER(StepArgs)] + [vp] * 10
+    lib.tdx_ek0_sweep_a.argtypes = [vp, ctypes.POINTER(StepArgs), vp, vp, vp, vp, vp]
+    lib.tdx_ek0_mid.argtypes = [vp, ctypes.POINTER(StepArgs), vp, vp, i64, vp, vp, vp]
+    lib.tdx_ek0_sweep_b.argtypes = [vp, ctypes.POINTER(StepArgs), vp, vp, vp, vp, vp, vp, vp]
+    lib.tdx_ek0_attempt_step.argtypes = [vp, ctypes.POINTER(StepArgs)] + [vp] * 9
+    lib.tdx_launch_count.restype = i64
+    lib.tdx_launch_count.argtypes = [vp]
+    for name in EXPORTED_SYMBOLS:
+        fn = getattr(lib, name)
+        if fn.restype is ctypes.c_int and name not in ("tdx_abi_version",):
+            fn.restype = cint
+    _lib = lib
+    return lib
+
+
+def check(rc, exc=None):
+    """Map a non-zero status to a Python exception (TDX_ERR_INVALID -> ValueError, like the reference)."""
+    if rc == 0:
+        return
+    msg = load().tdx_last_error().decode()
+    if rc == 1:
+        raise (exc or ValueError)(msg)
+    if rc == 2:
+        raise NotImplementedError(msg)
+    raise TornadoxB200Error(msg)
+
+
+def prior(nu):
+    """(A, Ql) of the preconditioned IWP(nu) prior as the kernels use them (reference: iwp.py:19-37)."""
+    n = nu + 1
+    A = np.zeros((n, n))
+    Ql = np.zeros((n, n))
+    pd = ctypes.POINTER(ctypes.c_double)
+    check(load().tdx_prior(nu, A.ctypes.data_as(pd), Ql.ctypes.data_as(pd)))
+    return A, Ql
+
+
+def nordsieck(nu, dt):
+    """(p, p_inv) Nordsieck preconditioner vectors (reference: iwp.py:65-73)."""
+    n = nu + 1
+    p = np.zeros(n)
+    pinv = np.zeros(n)
+    pd = ctypes.POINTER(ctypes.c_double)
+    check(load().tdx_nordsieck(nu, float(dt), p.ctypes.data_as(pd), pinv.ctypes.data_as(pd)))
+    return p, pinv
+
+
+def library_is_loaded():
+    """True if libtornadox_b200.so is mapped into this process (used by tests / smoke)."""
+    if not os.path.exists("/proc/self/maps"):
+        return _lib is not None
+    with open("/proc/self/maps") as fh:
+        return "libtornadox_b200.so" in fh.read()

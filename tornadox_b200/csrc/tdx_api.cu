@@ -1,0 +1,472 @@
+// tornadox_b200 C ABI (include/tornadox_b200.h): context, argument validation, dispatch to the kernels.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+#include "../../include/tornadox_b200.h"
+#include "tdx_ops.cuh"
+
+namespace tdx {
+
+// per-instantiation launch tables (tdx_inst_*.cu)
+#define TDX_DECL(NAME) const Ops* ops_##NAME();
+TDX_DECL(f64_2) TDX_DECL(f64_3) TDX_DECL(f64_4) TDX_DECL(f64_5) TDX_DECL(f64_6)
+TDX_DECL(f32_2) TDX_DECL(f32_3) TDX_DECL(f32_4) TDX_DECL(f32_5) TDX_DECL(f32_6)
+#undef TDX_DECL
+const EvalOps* eval_ops_f64();
+const EvalOps* eval_ops_f32();
+
+const Ops* find_ops(int dtype, int n) {
+    if (dtype == TDX_F64) {
+        switch (n) {
+            case 2: return ops_f64_2();
+            case 3: return ops_f64_3();
+            case 4: return ops_f64_4();
+            case 5: return ops_f64_5();
+            case 6: return ops_f64_6();
+        }
+    } else if (dtype == TDX_F32) {
+        switch (n) {
+            case 2: return ops_f32_2();
+            case 3: return ops_f32_3();
+            case 4: return ops_f32_4();
+            case 5: return ops_f32_5();
+            case 6: return ops_f32_6();
+        }
+    }
+    return nullptr;
+}
+
+const EvalOps* find_eval_ops(int dtype) {
+    if (dtype == TDX_F64) return eval_ops_f64();
+    if (dtype == TDX_F32) return eval_ops_f32();
+    return nullptr;
+}
+
+long long grid_for(const Geo& g) {
+    switch (g.kind) {
+        case IVP_VDP: return num_tiles<VanderPol<double>::Shape>(g.rows, g.cols);
+        case IVP_LORENZ96: return num_tiles<Lorenz96<double>::Shape>(g.rows, g.cols);
+        case IVP_BRUSS: return num_tiles<Brusselator<double>::Shape>(g.rows, g.cols);
+        case IVP_FHN2D: return num_tiles<Fhn2d<double>::Shape>(g.rows, g.cols);
+    }
+    return 0;
+}
+
+// ---- prior constants on the host (iwp.py:19-37, 65-73) -------------------------------------------
+
+// Ql = chol(Q), Q[i][j] = 1 / (2 nu + 1 - i - j).  Computed in long double and rounded, so the result is
+// the correctly rounded factor up to ~1 ulp (LAPACK dpotrf in the reference agrees to cond(Q) * eps).
+static void prior_host(int nu, double* A, double* Ql) {
+    const int n = nu + 1;
+    long double L[kMaxN][kMaxN] = {};
+    for (int j = 0; j < n; ++j) {
+        long double s = 1.0L / (long double)(2 * nu + 1 - 2 * j);
+        for (int k = 0; k < j; ++k) s -= L[j][k] * L[j][k];
+        L[j][j] = sqrtl(s);
+        for (int i = j + 1; i < n; ++i) {
+            long double t = 1.0L / (long double)(2 * nu + 1 - i - j);
+            for (int k = 0; k < j; ++k) t -= L[i][k] * L[j][k];
+            L[i][j] = t / L[j][j];
+        }
+    }
+    for (int i = 0; i < n; ++i)
+        for (int j = 0; j < n; ++j) {
+            if (A) A[i * n + j] = (j >= i) ? binom(nu - i, nu - j) : 0.0;
+            if (Ql) Ql[i * n + j] = (j <= i) ? (double)L[i][j] : 0.0;
+        }
+}
+
+static void nordsieck_host(int nu, double dt, double* p, double* pinv) {
+    // p[k] = |dt|^(nu-k+1/2) / (nu-k)!   (iwp.py:65-73)
+    const double adt = std::fabs(dt);
+    for (int k = 0; k <= nu; ++k) {
+        const int q = nu - k;
+        double fact = 1.0;
+        for (int i = 2; i <= q; ++i) fact *= (double)i;
+        const double e = (double)q + 0.5;
+        if (p) p[k] = std::pow(adt, e) / fact;
+        if (pinv) pinv[k] = std::pow(adt, -e) * fact;
+    }
+}
+
+}  // namespace tdx
+
+using namespace tdx;
+
+static thread_local std::string g_last_error;
+
+static int fail(int code, const std::string& msg) {
+    g_last_error = msg;
+    return code;
+}
+
+static int cuda_fail(int cuda_code, const char* where) {
+    if (cuda_code == 0) return TDX_OK;
+    if (cuda_code < 0) return fail(TDX_ERR_INVALID, std::string(where) + ": unknown vector field kind");
+    g_last_error = std::string(where) + ": " + cudaGetErrorString((cudaError_t)cuda_code);
+    return TDX_ERR_CUDA;
+}
+
+struct tdx_ctx {
+    int device = 0;
+    int dtype = TDX_F64;
+    bool has_problem = false;
+    tdx_problem_desc desc{};
+    Geo geo{};
+    int n = 0;
+    const Ops* ops = nullptr;
+    const EvalOps* eval_ops = nullptr;
+    double ql_packed[kMaxN * (kMaxN + 1) / 2] = {};
+    // workspace
+    double* partials = nullptr;
+    long long partials_cap = 0;
+    unsigned int* ticket = nullptr;
+    void* mid = nullptr;
+    long long halo_lo = 0, halo_hi = 0;
+    int64_t launches = 0;
+};
+
+static size_t esize(int dtype) { return dtype == TDX_F64 ? 8 : 4; }
+
+extern "C" {
+
+const char* tdx_last_error(void) { return g_last_error.c_str(); }
+int tdx_abi_version(void) { return TDX_ABI_VERSION; }
+
+int tdx_prior(int nu, double* A_out, double* Ql_out) {
+    if (nu < 1 || nu + 1 > kMaxN) return fail(TDX_ERR_INVALID, "tdx_prior: nu out of range");
+    prior_host(nu, A_out, Ql_out);
+    return TDX_OK;
+}
+
+int tdx_nordsieck(int nu, double dt, double* p_out, double* p_inv_out) {
+    if (nu < 0 || nu + 1 > kMaxN) return fail(TDX_ERR_INVALID, "tdx_nordsieck: nu out of range");
+    nordsieck_host(nu, dt, p_out, p_inv_out);
+    return TDX_OK;
+}
+
+int tdx_create(tdx_ctx** out, int device, int dtype) {
+    if (!out) return fail(TDX_ERR_INVALID, "tdx_create: null output pointer");
+    if (dtype != TDX_F64 && dtype != TDX_F32) return fail(TDX_ERR_INVALID, "tdx_create: dtype must be TDX_F64 or TDX_F32");
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(TDX_ERR_CUDA, std::string("tdx_create: no CUDA device available (") + cudaGetErrorString(e) +
+                                      "); tornadox_b200 has no CPU fallback");
+    if (device < 0 || device >= count) return fail(TDX_ERR_INVALID, "tdx_create: device ordinal out of range");
+    tdx_ctx* ctx = new tdx_ctx();
+    ctx->device = device;
+    ctx->dtype = dtype;
+    ctx->eval_ops = find_eval_ops(dtype);
+    int prev = 0;
+    cudaGetDevice(&prev);
+    cudaSetDevice(device);
+    e = cudaMalloc(&ctx->ticket, sizeof(unsigned int));
+    if (e == cudaSuccess) e = cudaMemset(ctx->ticket, 0, sizeof(unsigned int));
+    if (e == cudaSuccess) e = cudaMalloc(&ctx->mid, 256);
+    if (e == cudaSuccess) e = cudaMemset(ctx->mid, 0, 256);
+    cudaSetDevice(prev);
+    if (e != cudaSuccess) {
+        delete ctx;
+        return cuda_fail((int)e, "tdx_create");
+    }
+    *out = ctx;
+    return TDX_OK;
+}
+
+int tdx_destroy(tdx_ctx* ctx) {
+    if (!ctx) return TDX_OK;
+    int prev = 0;
+    cudaGetDevice(&prev);
+    cudaSetDevice(ctx->device);
+    cudaFree(ctx->partials);
+    cudaFree(ctx->ticket);
+    cudaFree(ctx->mid);
+    cudaSetDevice(prev);
+    delete ctx;
+    return TDX_OK;
+}
+
+int tdx_set_problem(tdx_ctx* ctx, const tdx_problem_desc* d) {
+    if (!ctx || !d) return fail(TDX_ERR_INVALID, "tdx_set_problem: null argument");
+    if (d->nu < 1 || d->nu + 1 > kMaxN) return fail(TDX_ERR_INVALID, "tdx_set_problem: num_derivatives must be in [1, 6]");
+    const Ops* ops = find_ops(ctx->dtype, d->nu + 1);
+    if (!ops) return fail(TDX_ERR_UNSUPPORTED, "tdx_set_problem: no kernel instantiated for this (num_derivatives, dtype)");
+    if (d->grid_rows < 1 || d->grid_cols < 1) return fail(TDX_ERR_INVALID, "tdx_set_problem: empty grid");
+    if (d->shard_begin < 0 || d->shard_end <= d->shard_begin)
+        return fail(TDX_ERR_INVALID, "tdx_set_problem: empty or negative shard range");
+    Geo g{};
+    g.kind = d->kind;
+    g.grows = d->grid_rows;
+    g.gcols = d->grid_cols;
+    for (int i = 0; i < 8; ++i) g.prm[i] = 0.0;
+    switch (d->kind) {
+        case TDX_IVP_VANDERPOL:
+            if (d->grid_rows != 1 || d->grid_cols != 1 || d->shard_begin != 0 || d->shard_end != 1)
+                return fail(TDX_ERR_INVALID, "tdx_set_problem: vanderpol is a single point (d = 2) and does not shard");
+            if (d->n_params < 1) return fail(TDX_ERR_INVALID, "tdx_set_problem: vanderpol needs params = [mu]");
+            g.nf = 2;
+            g.rows = 1; g.cols = 1; g.grow0 = 0; g.gcol0 = 0;
+            g.prm[0] = d->params[0];
+            break;
+        case TDX_IVP_LORENZ96:
+            if (d->grid_rows != 1) return fail(TDX_ERR_INVALID, "tdx_set_problem: lorenz96 is one-dimensional (grid_rows = 1)");
+            if (d->shard_end > d->grid_cols) return fail(TDX_ERR_INVALID, "tdx_set_problem: shard exceeds the chain");
+            if (d->n_params < 1) return fail(TDX_ERR_INVALID, "tdx_set_problem: lorenz96 needs params = [forcing]");
+            if ((d->shard_end - d->shard_begin) != d->grid_cols && (d->shard_end - d->shard_begin) < 2)
+                return fail(TDX_ERR_INVALID, "tdx_set_problem: a lorenz96 shard needs at least 2 points");
+            g.nf = 1;
+            g.rows = 1; g.cols = (int)(d->shard_end - d->shard_begin); g.grow0 = 0; g.gcol0 = d->shard_begin;
+            g.prm[0] = d->params[0];
+            break;
+        case TDX_IVP_BRUSSELATOR:
+            if (d->grid_rows != 1) return fail(TDX_ERR_INVALID, "tdx_set_problem: brusselator is one-dimensional (grid_rows = 1)");
+            if (d->shard_end > d->grid_cols) return fail(TDX_ERR_INVALID, "tdx_set_problem: shard exceeds the chain");
+            g.nf = 2;
+            g.rows = 1; g.cols = (int)(d->shard_end - d->shard_begin); g.grow0 = 0; g.gcol0 = d->shard_begin;
+            {   // ivp.py:223-224  const = alpha * (N + 1) ** 2, alpha = 1/50
+                const double alpha = 1.0 / 50.0;
+                const double np1 = (double)(d->grid_cols + 1);
+                g.prm[0] = alpha * (np1 * np1);
+            }
+            break;
+        case TDX_IVP_FHN2D:
+            if (d->grid_rows != d->grid_cols)
+                return fail(TDX_ERR_INVALID,
+                            "The diagonal Jacobian only works for quadratic spatial grids.");   // ivp.py:427-430
+            if (d->grid_rows < 2) return fail(TDX_ERR_INVALID, "tdx_set_problem: fhn_2d needs at least a 2 x 2 grid");
+            if (d->shard_end > d->grid_rows) return fail(TDX_ERR_INVALID, "tdx_set_problem: shard exceeds the grid");
+            if (d->n_params < 5) return fail(TDX_ERR_INVALID, "tdx_set_problem: fhn_2d needs params = [dx, a, b, k, tau]");
+            g.nf = 2;
+            g.rows = (int)(d->shard_end - d->shard_begin); g.cols = (int)d->grid_cols;
+            g.grow0 = d->shard_begin; g.gcol0 = 0;
+            {
+                const double dx = d->params[0];
+                g.prm[0] = 1.0 / (dx * dx);   // ivp.py:493-494
+                g.prm[1] = d->params[1]; g.prm[2] = d->params[2]; g.prm[3] = d->params[3]; g.prm[4] = d->params[4];
+            }
+            break;
+        default:
+            return fail(TDX_ERR_UNSUPPORTED,
+                        "tdx_set_problem: unknown vector field kind; only vanderpol, lorenz96, brusselator and fhn_2d "
+                        "are evaluated in-kernel (there is no CPU fallback)");
+    }
+    g.npts = (long long)g.rows * g.cols;
+    g.d = (long long)g.nf * g.npts;
+
+    long long lo = 0, hi = 0;
+    switch (g.kind) {
+        case IVP_VDP: VanderPol<double>::halo_sizes(g, lo, hi); break;
+        case IVP_LORENZ96: Lorenz96<double>::halo_sizes(g, lo, hi); break;
+        case IVP_BRUSS: Brusselator<double>::halo_sizes(g, lo, hi); break;
+        case IVP_FHN2D: Fhn2d<double>::halo_sizes(g, lo, hi); break;
+    }
+
+    const long long grid = grid_for(g);
+    if (grid > 2147483647LL) return fail(TDX_ERR_INVALID, "tdx_set_problem: shard too large for one launch");
+    int prev = 0;
+    cudaGetDevice(&prev);
+    cudaSetDevice(ctx->device);
+    cudaError_t e = cudaSuccess;
+    if (grid > ctx->partials_cap) {
+        cudaFree(ctx->partials);
+        ctx->partials = nullptr;
+        e = cudaMalloc(&ctx->partials, sizeof(double) * (size_t)grid);
+        ctx->partials_cap = (e == cudaSuccess) ? grid : 0;
+    }
+    cudaSetDevice(prev);
+    if (e != cudaSuccess) return cuda_fail((int)e, "tdx_set_problem");
+
+    ctx->desc = *d;
+    ctx->geo = g;
+    ctx->n = d->nu + 1;
+    ctx->ops = ops;
+    ctx->halo_lo = lo;
+    ctx->halo_hi = hi;
+    double Ql[kMaxN * kMaxN];
+    prior_host(d->nu, nullptr, Ql);
+    for (int i = 0; i < ctx->n; ++i)
+        for (int j = 0; j <= i; ++j) ctx->ql_packed[i * (i + 1) / 2 + j] = Ql[i * ctx->n + j];
+    ctx->has_problem = true;
+    return TDX_OK;
+}
+
+int64_t tdx_local_dim(const tdx_ctx* ctx) { return (ctx && ctx->has_problem) ? (int64_t)ctx->geo.d : -1; }
+
+int tdx_halo_sizes(const tdx_ctx* ctx, int64_t* lo, int64_t* hi) {
+    if (!ctx || !ctx->has_problem) return fail(TDX_ERR_INVALID, "tdx_halo_sizes: no problem set");
+    if (lo) *lo = ctx->halo_lo;
+    if (hi) *hi = ctx->halo_hi;
+    return TDX_OK;
+}
+
+int64_t tdx_launch_count(const tdx_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+}  // extern "C"
+
+// ---- helpers ---------------------------------------------------------------------------------------
+
+static int check_ready(const tdx_ctx* ctx, const char* where) {
+    if (!ctx) return fail(TDX_ERR_INVALID, std::string(where) + ": null context");
+    if (!ctx->has_problem) return fail(TDX_ERR_INVALID, std::string(where) + ": tdx_set_problem has not been called");
+    return TDX_OK;
+}
+
+static int check_halos(const tdx_ctx* ctx, const void* lo, const void* hi, const char* where) {
+    if (ctx->halo_lo > 0 && !lo) return fail(TDX_ERR_INVALID, std::string(where) + ": this shard needs halo_lo");
+    if (ctx->halo_hi > 0 && !hi) return fail(TDX_ERR_INVALID, std::string(where) + ": this shard needs halo_hi");
+    return TDX_OK;
+}
+
+static StepHost make_step(const tdx_ctx* ctx, const tdx_step_args* a) {
+    StepHost h{};
+    nordsieck_host(ctx->n - 1, a->dt, h.p, h.pinv);
+    std::memcpy(h.ql, ctx->ql_packed, sizeof(h.ql));
+    h.dt = a->dt;
+    h.abstol = a->abstol;
+    h.reltol = a->reltol;
+    h.want_norm = (a->abstol != 0.0 || a->reltol != 0.0) ? 1 : 0;
+    h.flags = a->flags;
+    return h;
+}
+
+static Workspace make_ws(const tdx_ctx* ctx) { return Workspace{ctx->partials, ctx->ticket, ctx->mid}; }
+
+static int check_dt(const tdx_step_args* a, const char* where) {
+    if (!a) return fail(TDX_ERR_INVALID, std::string(where) + ": null step arguments");
+    if (!(a->dt > 0.0) || !std::isfinite(a->dt))
+        return fail(TDX_ERR_INVALID, std::string(where) + ": Invalid step size: dt must be positive and finite");   // odefilter.py:221
+    return TDX_OK;
+}
+
+struct DeviceGuard {
+    int prev = 0;
+    explicit DeviceGuard(int dev) {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+        else prev = -1;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+extern "C" {
+
+int tdx_eval_f(tdx_ctx* ctx, double t, const void* y, void* fy, void* jdiag, const void* halo_lo, const void* halo_hi,
+               void* stream) {
+    (void)t;
+    int rc = check_ready(ctx, "tdx_eval_f");
+    if (rc) return rc;
+    if (!y || !fy) return fail(TDX_ERR_INVALID, "tdx_eval_f: null buffer");
+    if ((rc = check_halos(ctx, halo_lo, halo_hi, "tdx_eval_f"))) return rc;
+    DeviceGuard guard(ctx->device);
+    ctx->launches += 1;
+    return cuda_fail(ctx->eval_ops->eval_f(ctx->geo, y, fy, jdiag, halo_lo, halo_hi, (cudaStream_t)stream), "tdx_eval_f");
+}
+
+int tdx_pack_halo(tdx_ctx* ctx, double dt, const void* mean_in, void* edge_first, void* edge_last, void* stream) {
+    int rc = check_ready(ctx, "tdx_pack_halo");
+    if (rc) return rc;
+    tdx_step_args a{0.0, dt, 0.0, 0.0, 0u, 0u};
+    if ((rc = check_dt(&a, "tdx_pack_halo"))) return rc;
+    if (!mean_in) return fail(TDX_ERR_INVALID, "tdx_pack_halo: null buffer");
+    // what the neighbours need from us: the lower neighbour's hi-halo is our first row/points, the upper
+    // neighbour's lo-halo is our last row/points.
+    int n_first = 0, n_last = 0;
+    const Geo& g = ctx->geo;
+    switch (g.kind) {
+        case IVP_FHN2D: n_first = n_last = g.cols; break;
+        case IVP_BRUSS: n_first = n_last = 1; break;
+        case IVP_LORENZ96: n_first = 1; n_last = 2; break;
+        default: break;
+    }
+    if (!edge_first) n_first = 0;
+    if (!edge_last) n_last = 0;
+    if (n_first + n_last == 0) return TDX_OK;
+    StepHost h = make_step(ctx, &a);
+    DeviceGuard guard(ctx->device);
+    ctx->launches += 1;
+    return cuda_fail(ctx->ops->pack(g, h, mean_in, edge_first, edge_last, n_first, n_last, (cudaStream_t)stream),
+                     "tdx_pack_halo");
+}
+
+int tdx_dek1_attempt_step(tdx_ctx* ctx, const tdx_step_args* args, const void* mean_in, const void* sc_in,
+                          void* mean_out, void* sc_out, void* err_out, void* ref_out, const void* halo_lo,
+                          const void* halo_hi, double* sq_norm_sum, void* stream) {
+    int rc = check_ready(ctx, "tdx_dek1_attempt_step");
+    if (rc) return rc;
+    if ((rc = check_dt(args, "tdx_dek1_attempt_step"))) return rc;
+    if (!mean_in || !sc_in || !mean_out || !sc_out) return fail(TDX_ERR_INVALID, "tdx_dek1_attempt_step: null state buffer");
+    if (mean_in == mean_out || sc_in == sc_out)
+        return fail(TDX_ERR_INVALID, "tdx_dek1_attempt_step: in and out buffers must be distinct (a rejected attempt keeps the input state)");
+    if ((rc = check_halos(ctx, halo_lo, halo_hi, "tdx_dek1_attempt_step"))) return rc;
+    StepHost h = make_step(ctx, args);
+    if (h.want_norm && !sq_norm_sum) return fail(TDX_ERR_INVALID, "tdx_dek1_attempt_step: sq_norm_sum is required with tolerances");
+    DeviceGuard guard(ctx->device);
+    ctx->launches += 1;
+    return cuda_fail(ctx->ops->dek1(ctx->geo, h, mean_in, sc_in, mean_out, sc_out, err_out, ref_out, halo_lo, halo_hi,
+                                    make_ws(ctx), sq_norm_sum, (cudaStream_t)stream),
+                     "tdx_dek1_attempt_step");
+}
+
+int tdx_ek0_sweep_a(tdx_ctx* ctx, const tdx_step_args* args, const void* mean_in, const void* halo_lo,
+                    const void* halo_hi, double* z_sq_sum, void* stream) {
+    int rc = check_ready(ctx, "tdx_ek0_sweep_a");
+    if (rc) return rc;
+    if ((rc = check_dt(args, "tdx_ek0_sweep_a"))) return rc;
+    if (!mean_in || !z_sq_sum) return fail(TDX_ERR_INVALID, "tdx_ek0_sweep_a: null buffer");
+    if ((rc = check_halos(ctx, halo_lo, halo_hi, "tdx_ek0_sweep_a"))) return rc;
+    StepHost h = make_step(ctx, args);
+    DeviceGuard guard(ctx->device);
+    ctx->launches += 1;
+    return cuda_fail(ctx->ops->ek0_a(ctx->geo, h, mean_in, halo_lo, halo_hi, make_ws(ctx), z_sq_sum, (cudaStream_t)stream),
+                     "tdx_ek0_sweep_a");
+}
+
+int tdx_ek0_mid(tdx_ctx* ctx, const tdx_step_args* args, const void* Cl_in, const double* z_sq_sum, int64_t d_global,
+                void* Cl_out, void* err_out, void* stream) {
+    int rc = check_ready(ctx, "tdx_ek0_mid");
+    if (rc) return rc;
+    if ((rc = check_dt(args, "tdx_ek0_mid"))) return rc;
+    if (!Cl_in || !z_sq_sum || !Cl_out || !err_out) return fail(TDX_ERR_INVALID, "tdx_ek0_mid: null buffer");
+    if (d_global < 1) return fail(TDX_ERR_INVALID, "tdx_ek0_mid: d_global must be positive");
+    StepHost h = make_step(ctx, args);
+    DeviceGuard guard(ctx->device);
+    ctx->launches += 1;
+    return cuda_fail(ctx->ops->ek0_mid(h, Cl_in, z_sq_sum, (double)d_global, Cl_out, err_out, make_ws(ctx), (cudaStream_t)stream),
+                     "tdx_ek0_mid");
+}
+
+int tdx_ek0_sweep_b(tdx_ctx* ctx, const tdx_step_args* args, const void* mean_in, void* mean_out, void* ref_out,
+                    const void* halo_lo, const void* halo_hi, double* inv_tol_sq_sum, void* stream) {
+    int rc = check_ready(ctx, "tdx_ek0_sweep_b");
+    if (rc) return rc;
+    if ((rc = check_dt(args, "tdx_ek0_sweep_b"))) return rc;
+    if (!mean_in || !mean_out) return fail(TDX_ERR_INVALID, "tdx_ek0_sweep_b: null buffer");
+    if (mean_in == mean_out) return fail(TDX_ERR_INVALID, "tdx_ek0_sweep_b: in and out buffers must be distinct");
+    if ((rc = check_halos(ctx, halo_lo, halo_hi, "tdx_ek0_sweep_b"))) return rc;
+    StepHost h = make_step(ctx, args);
+    if (h.want_norm && !inv_tol_sq_sum) return fail(TDX_ERR_INVALID, "tdx_ek0_sweep_b: inv_tol_sq_sum is required with tolerances");
+    DeviceGuard guard(ctx->device);
+    ctx->launches += 1;
+    return cuda_fail(ctx->ops->ek0_b(ctx->geo, h, mean_in, mean_out, ref_out, halo_lo, halo_hi, make_ws(ctx), inv_tol_sq_sum,
+                                     (cudaStream_t)stream),
+                     "tdx_ek0_sweep_b");
+}
+
+int tdx_ek0_attempt_step(tdx_ctx* ctx, const tdx_step_args* args, const void* mean_in, const void* Cl_in,
+                         void* mean_out, void* Cl_out, void* err_out, void* ref_out, double* z_sq_sum,
+                         double* inv_tol_sq_sum, void* stream) {
+    int rc = check_ready(ctx, "tdx_ek0_attempt_step");
+    if (rc) return rc;
+    if (ctx->halo_lo > 0 || ctx->halo_hi > 0)
+        return fail(TDX_ERR_INVALID, "tdx_ek0_attempt_step: sharded contexts must call the three phases and all-reduce in between");
+    if ((rc = tdx_ek0_sweep_a(ctx, args, mean_in, nullptr, nullptr, z_sq_sum, stream))) return rc;
+    if ((rc = tdx_ek0_mid(ctx, args, Cl_in, z_sq_sum, (int64_t)ctx->geo.d, Cl_out, err_out, stream))) return rc;
+    return tdx_ek0_sweep_b(ctx, args, mean_in, mean_out, ref_out, nullptr, nullptr, inv_tol_sq_sum, stream);
+}
+
+}  // extern "C"

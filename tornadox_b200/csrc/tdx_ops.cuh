@@ -1,0 +1,200 @@
+// Host-side launch table: one Ops entry per (dtype, n), defined in the per-instantiation translation units.
+#pragma once
+
+#include "tdx_kernels.cuh"
+
+namespace tdx {
+
+struct StepHost {
+    double p[kMaxN], pinv[kMaxN];
+    double ql[kMaxN * (kMaxN + 1) / 2];   // packed for the actual n
+    double dt, abstol, reltol;
+    int want_norm;
+    unsigned int flags;
+};
+
+struct Workspace {
+    double* partials;        // >= grid doubles
+    unsigned int* ticket;
+    void* mid;               // Ek0Mid<T, N>
+};
+
+struct Ops {
+    int (*dek1)(const Geo&, const StepHost&, const void* mean_in, const void* sc_in, void* mean_out, void* sc_out,
+                void* err_out, void* ref_out, const void* halo_lo, const void* halo_hi, const Workspace&,
+                double* out_sum, cudaStream_t);
+    int (*ek0_a)(const Geo&, const StepHost&, const void* mean_in, const void* halo_lo, const void* halo_hi,
+                 const Workspace&, double* out_sum, cudaStream_t);
+    int (*ek0_mid)(const StepHost&, const void* Cl_in, const double* z_sq_sum, double d_global, void* Cl_out,
+                   void* err_out, const Workspace&, cudaStream_t);
+    int (*ek0_b)(const Geo&, const StepHost&, const void* mean_in, void* mean_out, void* ref_out, const void* halo_lo,
+                 const void* halo_hi, const Workspace&, double* out_sum, cudaStream_t);
+    int (*pack)(const Geo&, const StepHost&, const void* mean_in, void* edge_first, void* edge_last, int n_first,
+                int n_last, cudaStream_t);
+};
+
+struct EvalOps {
+    int (*eval_f)(const Geo&, const void* y, void* fy, void* jd, const void* halo_lo, const void* halo_hi,
+                  cudaStream_t);
+};
+
+const Ops* find_ops(int dtype, int n);         // nullptr if not instantiated
+const EvalOps* find_eval_ops(int dtype);
+long long grid_for(const Geo& g);              // CTAs a step kernel launches for this shard
+
+template <typename T, int N>
+inline Consts<T, N> make_consts(const StepHost& h) {
+    Consts<T, N> c;
+    for (int k = 0; k < N; ++k) {
+        c.p[k] = (T)h.p[k];
+        c.pinv[k] = (T)h.pinv[k];
+    }
+    for (int k = 0; k < N * (N + 1) / 2; ++k) c.ql[k] = (T)h.ql[k];
+    c.dt = (T)h.dt;
+    c.abstol = (T)h.abstol;
+    c.reltol = (T)h.reltol;
+    c.want_norm = h.want_norm;
+    c.flags = h.flags;
+    return c;
+}
+
+#define TDX_CUDA_TRY(expr)                        \
+    do {                                          \
+        cudaError_t e__ = (expr);                 \
+        if (e__ != cudaSuccess) return (int)e__;  \
+    } while (0)
+
+// dispatch a templated launch body over the vector field
+#define TDX_SWITCH_IVP(kind, T, ...)                                             \
+    switch (kind) {                                                              \
+        case IVP_VDP: { using IVP = VanderPol<T>; __VA_ARGS__ } break;           \
+        case IVP_LORENZ96: { using IVP = Lorenz96<T>; __VA_ARGS__ } break;       \
+        case IVP_BRUSS: { using IVP = Brusselator<T>; __VA_ARGS__ } break;       \
+        case IVP_FHN2D: { using IVP = Fhn2d<T>; __VA_ARGS__ } break;             \
+        default: return -1;                                                      \
+    }
+
+template <typename T, int N>
+struct Launch {
+    using L = SmemLayout<T, N>;
+
+    static int dek1(const Geo& g, const StepHost& h, const void* mean_in, const void* sc_in, void* mean_out,
+                    void* sc_out, void* err_out, void* ref_out, const void* halo_lo, const void* halo_hi,
+                    const Workspace& ws, double* out_sum, cudaStream_t st) {
+        DekArgs<T, N> a;
+        a.g = g;
+        a.c = make_consts<T, N>(h);
+        a.mean_in = (const T*)mean_in;
+        a.sc_in = (const T*)sc_in;
+        a.mean_out = (T*)mean_out;
+        a.sc_out = (T*)sc_out;
+        a.err_out = (T*)err_out;
+        a.ref_out = (T*)ref_out;
+        a.halo_lo = (const T*)halo_lo;
+        a.halo_hi = (const T*)halo_hi;
+        a.partials = ws.partials;
+        a.ticket = ws.ticket;
+        a.out_sum = out_sum;
+        TDX_SWITCH_IVP(g.kind, T, {
+            using Shape = typename IVP::Shape;
+            const size_t smem = L::total(Shape::AT_ELEMS, true);
+            auto kern = dek1_kernel<IVP, T, N>;
+            TDX_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            const long long grid = num_tiles<Shape>(g.rows, g.cols);
+            kern<<<(unsigned)grid, kThreads, smem, st>>>(a);
+        })
+        return (int)cudaGetLastError();
+    }
+
+    static Ek0Args<T, N> ek0_args(const Geo& g, const StepHost& h, const void* mean_in, void* mean_out, void* ref_out,
+                                  const void* halo_lo, const void* halo_hi, const Workspace& ws, double* out_sum) {
+        Ek0Args<T, N> a;
+        a.g = g;
+        a.c = make_consts<T, N>(h);
+        a.mean_in = (const T*)mean_in;
+        a.mean_out = (T*)mean_out;
+        a.ref_out = (T*)ref_out;
+        a.halo_lo = (const T*)halo_lo;
+        a.halo_hi = (const T*)halo_hi;
+        a.mid = (const Ek0Mid<T, N>*)ws.mid;
+        a.partials = ws.partials;
+        a.ticket = ws.ticket;
+        a.out_sum = out_sum;
+        return a;
+    }
+
+    static int ek0_a(const Geo& g, const StepHost& h, const void* mean_in, const void* halo_lo, const void* halo_hi,
+                     const Workspace& ws, double* out_sum, cudaStream_t st) {
+        Ek0Args<T, N> a = ek0_args(g, h, mean_in, nullptr, nullptr, halo_lo, halo_hi, ws, out_sum);
+        TDX_SWITCH_IVP(g.kind, T, {
+            using Shape = typename IVP::Shape;
+            const size_t smem = L::total(Shape::AT_ELEMS, false);
+            const long long grid = num_tiles<Shape>(g.rows, g.cols);
+            ek0_sweep_a_kernel<IVP, T, N><<<(unsigned)grid, kThreads, smem, st>>>(a);
+        })
+        return (int)cudaGetLastError();
+    }
+
+    static int ek0_b(const Geo& g, const StepHost& h, const void* mean_in, void* mean_out, void* ref_out,
+                     const void* halo_lo, const void* halo_hi, const Workspace& ws, double* out_sum, cudaStream_t st) {
+        Ek0Args<T, N> a = ek0_args(g, h, mean_in, mean_out, ref_out, halo_lo, halo_hi, ws, out_sum);
+        TDX_SWITCH_IVP(g.kind, T, {
+            using Shape = typename IVP::Shape;
+            const size_t smem = L::total(Shape::AT_ELEMS, false);
+            const long long grid = num_tiles<Shape>(g.rows, g.cols);
+            ek0_sweep_b_kernel<IVP, T, N><<<(unsigned)grid, kThreads, smem, st>>>(a);
+        })
+        return (int)cudaGetLastError();
+    }
+
+    static int ek0_mid(const StepHost& h, const void* Cl_in, const double* z_sq_sum, double d_global, void* Cl_out,
+                       void* err_out, const Workspace& ws, cudaStream_t st) {
+        Ek0MidArgs<T, N> a;
+        a.c = make_consts<double, N>(h);
+        a.Cl_in = (const T*)Cl_in;
+        a.z_sq_sum = z_sq_sum;
+        a.d_global = d_global;
+        a.Cl_out = (T*)Cl_out;
+        a.err_out = (T*)err_out;
+        a.mid = (Ek0Mid<T, N>*)ws.mid;
+        ek0_mid_kernel<T, N><<<1, 32, 0, st>>>(a);
+        return (int)cudaGetLastError();
+    }
+
+    static int pack(const Geo& g, const StepHost& h, const void* mean_in, void* edge_first, void* edge_last,
+                    int n_first, int n_last, cudaStream_t st) {
+        PackArgs<T, N> a;
+        a.g = g;
+        a.c = make_consts<T, N>(h);
+        a.mean_in = (const T*)mean_in;
+        a.edge_first = (T*)edge_first;
+        a.edge_last = (T*)edge_last;
+        a.n_first = n_first;
+        a.n_last = n_last;
+        const int total = g.nf * (n_first + n_last);
+        if (total <= 0) return 0;
+        const int blocks = (total + 255) / 256;
+        pack_halo_kernel<T, N><<<blocks, 256, 0, st>>>(a);
+        return (int)cudaGetLastError();
+    }
+
+    static Ops ops() {
+        Ops o{};
+        o.dek1 = &dek1;
+        o.ek0_a = &ek0_a;
+        o.ek0_mid = &ek0_mid;
+        o.ek0_b = &ek0_b;
+        o.pack = &pack;
+        return o;
+    }
+};
+
+}  // namespace tdx
+
+#define TDX_DEFINE_OPS(T, N, NAME)                 \
+    namespace tdx {                                \
+    const Ops* ops_##NAME() {                      \
+        static const Ops o = Launch<T, N>::ops();  \
+        return &o;                                 \
+    }                                              \
+    }

@@ -1,0 +1,65 @@
+"""EK0 solvers on the fused CUDA step.  Mirrors tornadox/ek0.py: ``KroneckerEK0`` (:85-193) and
+``DiagonalEK0`` (:196-280, = the DiagonalEK1 kernel with the Jacobian diagonal forced to zero).
+
+KroneckerEK0 keeps ONE (n, n) factor for all coordinates; an attempt is two d-wide sweeps over the mean
+with the global calibration scalar in between (``tdx_ek0_sweep_a`` -> ``tdx_ek0_mid`` -> ``tdx_ek0_sweep_b``).
+The dense ``ReferenceEK0`` (:13-82) is O(d^3) and out of scope.
+"""
+
+import torch
+
+from . import _lib, odefilter, rv
+from .ek1 import BatchedEK1
+from .init import _spec_of
+from .ivp import as_device_tensor
+
+
+class KroneckerEK0(odefilter.ODEFilter):
+    def __init__(self, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        self.A = None
+        self.Ql = None
+        self.engine = None
+
+    #: when False, reference_state = |mean[0]| is not written by the kernel (it is implied by the mean)
+    materialize_reference_state = True
+
+    def initialize(self, f, t0, tmax, y0, df, df_diagonal):
+        """ek0.py:94-121: single (n, n) factor, scalar NaN error estimate."""
+        y0 = as_device_tensor(y0, dtype=self.dtype)
+        self.engine = BatchedEK1._make_engine(self, f, y0.device)
+        A, Ql = _lib.prior(self.num_derivatives)
+        self.A = torch.as_tensor(A, dtype=self.dtype, device=y0.device)
+        self.Ql = torch.as_tensor(Ql, dtype=self.dtype, device=y0.device)
+        extended_dy0, cov_sqrtm = self.init(f=f, df=df, y0=y0, t0=t0, num_derivatives=self.num_derivatives)
+        mean = BatchedEK1._own_slice(self, extended_dy0.to(self.dtype))
+        d = mean.shape[1]
+        y = rv.LeftIsotropicMatrixNormal(mean=mean, d=d, cov_sqrtm_2=cov_sqrtm.to(self.dtype).contiguous())
+        nan = torch.full((d,), float("nan"), dtype=self.dtype, device=mean.device)
+        return odefilter.ODEFilterState(t=t0, error_estimate=float("nan"), reference_state=nan, y=y)
+
+    def attempt_step(self, state, dt, f, t0, tmax, y0, df, df_diagonal):
+        """ek0.py:152-193 as three launches."""
+        if self.engine is None:
+            raise RuntimeError("call initialize() first")
+        abstol, reltol = self.steprule.kernel_tolerances
+        mean, Cl, err, ref, itol = self.engine.ek0_attempt(
+            state.t, dt, state.y.mean, state.y.cov_sqrtm_2, abstol=abstol, reltol=reltol,
+            want_ref=self.materialize_reference_state)
+        new_state = odefilter.ODEFilterState(
+            t=state.t + dt,
+            error_estimate=err,
+            reference_state=ref,
+            y=rv.LeftIsotropicMatrixNormal(mean, state.y.d, Cl),
+        )
+        if abstol != 0.0 or reltol != 0.0:
+            # || dt err / (abstol + reltol ref) ||^2 = (dt err)^2 * sum 1 / tol_i^2   (step.py:101-104)
+            new_state.scaled_error_norm_sq_sum = (dt * err.double()) ** 2 * itol[0]
+            new_state.scaled_error_norm_dim = self.engine.d_global
+        return new_state, dict(num_f_evaluations=1)
+
+
+class DiagonalEK0(BatchedEK1):
+    """ek0.py:196-280: block-diagonal EK0 = DiagonalEK1 with a zero Jacobian diagonal."""
+
+    _uses_jacobian = False

@@ -1,0 +1,103 @@
+"""EK1 solvers on the fused CUDA step.  Mirrors tornadox/ek1.py: ``BatchedEK1`` (:181-270) and
+``DiagonalEK1`` (:273-369).
+
+The whole reference chain -- precondition, predict_mean, evaluate_ode (f and df_diagonal), estimate_error,
+predict_cov_sqrtm (batched QR), observe_cov_sqrtm, correct_cov_sqrtm, correct_mean, un-precondition,
+reference_state -- is ONE kernel launch per attempt (``tdx_dek1_attempt_step``), which also reduces the
+scaled error norm of ``AdaptiveSteps.scale_error_estimate`` (step.py:93-104).
+The dense ``ReferenceEK1`` family (:11-178) is O(d^3) and out of scope.
+"""
+
+import torch
+
+from . import _lib, odefilter, rv
+from .engine import StepEngine
+from .init import _spec_of
+from .ivp import as_device_tensor
+
+
+class BatchedEK1(odefilter.ODEFilter):
+    """Common functionality for EK1 variations that act on batched multivariate normals (ek1.py:181-270)."""
+
+    #: when False the per-coordinate error_estimate / reference_state vectors are not written to HBM
+    #: (the scaled error norm is fused regardless); state.error_estimate / reference_state are then None
+    materialize_error_vectors = True
+
+    def __init__(self, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        self.phi_1d = None
+        self.sq_1d = None
+        self.engine = None
+
+    def _make_engine(self, f, device):
+        spec = _spec_of(f)
+        group = self.process_group
+        rank = world = None
+        if group is not None:
+            import torch.distributed as dist
+
+            rank, world = dist.get_rank(group), dist.get_world_size(group)
+        return StepEngine(spec, self.num_derivatives, dtype=self.dtype, device=device, group=group,
+                          rank=rank or 0, world=world or 1)
+
+    def initialize(self, f, t0, tmax, y0, df, df_diagonal):
+        """ek1.py:190-205.  ``y0`` is the GLOBAL initial value; a sharded solver keeps its own slice."""
+        y0 = as_device_tensor(y0, dtype=self.dtype)
+        self.engine = self._make_engine(f, y0.device)
+        A, Ql = _lib.prior(self.num_derivatives)
+        self.phi_1d = torch.as_tensor(A, dtype=self.dtype, device=y0.device)
+        self.sq_1d = torch.as_tensor(Ql, dtype=self.dtype, device=y0.device)
+        extended_dy0, cov_sqrtm = self.init(f=f, df=df, y0=y0, t0=t0, num_derivatives=self.num_derivatives)
+        extended_dy0 = self._own_slice(extended_dy0.to(self.dtype))
+        return BatchedEK1.y0_to_initial_state(extended_dy0, cov_sqrtm.to(self.dtype), d=extended_dy0.shape[1], t0=t0)
+
+    def _own_slice(self, mean_global):
+        eng = self.engine
+        if eng.world == 1:
+            return mean_global.contiguous()
+        from .engine import local_slices
+
+        parts = [mean_global[:, s] for s in local_slices(eng.spec, eng.begin, eng.end)]
+        return torch.cat(parts, dim=1).contiguous()
+
+    @staticmethod
+    def y0_to_initial_state(extended_dy0, cov_sqrtm, d, t0):
+        """ek1.py:216-226: the (n, n) factor repeated d times, NaN error / reference."""
+        blocks = cov_sqrtm.unsqueeze(0).expand(d, -1, -1).contiguous()
+        nan = torch.full((d,), float("nan"), dtype=extended_dy0.dtype, device=extended_dy0.device)
+        return odefilter.ODEFilterState(
+            t=t0,
+            y=rv.BatchedMultivariateNormal(extended_dy0, blocks),
+            error_estimate=nan,
+            reference_state=nan.clone(),
+        )
+
+    def attempt_step(self, state, dt, f, t0, tmax, y0, df, df_diagonal):
+        """One fused launch (ek1.py:228-260)."""
+        if self.engine is None:
+            raise RuntimeError("call initialize() first")
+        abstol, reltol = self.steprule.kernel_tolerances
+        mean, sc, err, ref, sq = self.engine.dek1_attempt(
+            state.t, dt, state.y.mean, state.y.cov_sqrtm, abstol=abstol, reltol=reltol,
+            want_err_ref=self.materialize_error_vectors, jacobian=self._uses_jacobian)
+        new_state = odefilter.ODEFilterState(
+            t=state.t + dt,
+            y=rv.BatchedMultivariateNormal(mean, sc),
+            error_estimate=err,
+            reference_state=ref,
+        )
+        if abstol != 0.0 or reltol != 0.0:
+            new_state.scaled_error_norm_sq_sum = sq
+            new_state.scaled_error_norm_dim = self.engine.d_global
+        info = dict(num_f_evaluations=1)
+        if self._uses_jacobian:
+            info["num_df_diagonal_evaluations"] = 1
+        return new_state, info
+
+    _uses_jacobian = True
+
+
+class DiagonalEK1(BatchedEK1):
+    """EK1 with the Jacobian truncated to its diagonal (ek1.py:273-369)."""
+
+    _uses_jacobian = True

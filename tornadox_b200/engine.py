@@ -1,0 +1,264 @@
+"""Step engine: owns one ``tdx_ctx`` (one GPU, one shard) and launches the fused kernels on torch buffers.
+
+Multi-GPU: one process per GPU; the state dimension is sharded by grid rows (fhn_2d) or chain ranges
+(lorenz96, brusselator) of BOTH fields.  Per attempt the only communication is the stencil halo
+(``HaloExchanger``: NCCL send/recv over NVLink) and the all-reduce of one or two fp64 scalars, so every
+rank takes the identical accept/reject decision (reference: no counterpart, single device).
+"""
+
+import ctypes
+from collections import namedtuple
+
+import numpy as np
+import torch
+
+from . import _lib
+
+KernelSpec = namedtuple("KernelSpec", "kind params grid_rows grid_cols n_fields name")
+"""Which in-kernel vector field an ``InitialValueProblem`` maps to (global geometry)."""
+
+
+def shard_range(spec, rank, world):
+    """Contiguous balanced split of the sharded axis (grid rows for fhn_2d, points for 1-d chains)."""
+    extent = spec.grid_rows if spec.kind == _lib.TDX_IVP_FHN2D else spec.grid_cols
+    if world == 1:
+        return 0, extent
+    if spec.kind == _lib.TDX_IVP_VANDERPOL:
+        raise ValueError("vanderpol (d = 2) cannot be sharded across GPUs")
+    if extent < 2 * world:
+        raise ValueError(f"cannot shard an axis of {extent} across {world} ranks")
+    base, rem = divmod(extent, world)
+    begin = rank * base + min(rank, rem)
+    return begin, begin + base + (1 if rank < rem else 0)
+
+
+def local_slices(spec, begin, end):
+    """Index ranges of the global flat state y = [field0; field1] owned by a shard (one per field)."""
+    if spec.kind == _lib.TDX_IVP_FHN2D:
+        npts = spec.grid_rows * spec.grid_cols
+        lo, hi = begin * spec.grid_cols, end * spec.grid_cols
+    else:
+        npts = spec.grid_rows * spec.grid_cols
+        lo, hi = begin, end
+    return [slice(f * npts + lo, f * npts + hi) for f in range(spec.n_fields)]
+
+
+class HaloExchanger:
+    """Neighbour exchange of the shard-edge values (works on any torch backend: nccl on GPUs, gloo in tests).
+
+    ``exchange(edge_first, edge_last)`` sends ``edge_first`` to the lower neighbour (it becomes its
+    upper halo) and ``edge_last`` to the upper neighbour (its lower halo) and returns
+    ``(halo_lo, halo_hi)``.  Non-cyclic problems have no neighbour beyond the global ends.
+    """
+
+    def __init__(self, group, rank, world, cyclic, lo_count, hi_count, dtype, device):
+        import torch.distributed as dist
+
+        self.dist = dist
+        self.group, self.rank, self.world, self.cyclic = group, rank, world, cyclic
+        self.lower = (rank - 1) % world if (cyclic or rank > 0) else None
+        self.upper = (rank + 1) % world if (cyclic or rank < world - 1) else None
+        self.halo_lo = torch.empty(lo_count, dtype=dtype, device=device) if self.lower is not None else None
+        self.halo_hi = torch.empty(hi_count, dtype=dtype, device=device) if self.upper is not None else None
+
+    def exchange(self, edge_first, edge_last):
+        dist = self.dist
+        ops = []
+        if self.lower is not None:
+            ops.append(dist.P2POp(dist.isend, edge_first, self._global(self.lower), self.group))
+            ops.append(dist.P2POp(dist.irecv, self.halo_lo, self._global(self.lower), self.group))
+        if self.upper is not None:
+            ops.append(dist.P2POp(dist.isend, edge_last, self._global(self.upper), self.group))
+            ops.append(dist.P2POp(dist.irecv, self.halo_hi, self._global(self.upper), self.group))
+        if self.world == 2 and self.cyclic:
+            # both neighbours are the same peer: order the four transfers consistently on both ranks
+            ops = self._two_rank_cyclic(edge_first, edge_last)
+        if ops:
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+        return self.halo_lo, self.halo_hi
+
+    def _global(self, r):
+        return self.dist.get_global_rank(self.group, r) if self.group is not None else r
+
+    def _two_rank_cyclic(self, edge_first, edge_last):
+        dist, peer = self.dist, self._global(1 - self.rank)
+        if self.rank == 0:
+            return [
+                dist.P2POp(dist.isend, edge_first, peer, self.group),
+                dist.P2POp(dist.isend, edge_last, peer, self.group),
+                dist.P2POp(dist.irecv, self.halo_hi, peer, self.group),
+                dist.P2POp(dist.irecv, self.halo_lo, peer, self.group),
+            ]
+        return [
+            dist.P2POp(dist.irecv, self.halo_hi, peer, self.group),
+            dist.P2POp(dist.irecv, self.halo_lo, peer, self.group),
+            dist.P2POp(dist.isend, edge_first, peer, self.group),
+            dist.P2POp(dist.isend, edge_last, peer, self.group),
+        ]
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+class StepEngine:
+    """One GPU's share of the filter step for a given (vector field, nu, dtype)."""
+
+    def __init__(self, spec, nu, dtype=torch.float64, device=None, group=None, rank=0, world=1):
+        if not torch.cuda.is_available():
+            raise _lib.TornadoxB200Error(
+                "tornadox_b200 needs a CUDA device (sm_100a); there is no CPU fallback for the filter step"
+            )
+        self.lib = _lib.load()
+        self.spec, self.nu, self.n = spec, int(nu), int(nu) + 1
+        self.dtype = dtype
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        self.group, self.rank, self.world = group, rank, world
+        self.begin, self.end = shard_range(spec, rank, world)
+        self.d_global = spec.n_fields * spec.grid_rows * spec.grid_cols
+
+        handle = ctypes.c_void_p()
+        tdx_dtype = {torch.float64: _lib.TDX_F64, torch.float32: _lib.TDX_F32}[dtype]
+        _lib.check(self.lib.tdx_create(ctypes.byref(handle), self.device.index or 0, tdx_dtype), _lib.TornadoxB200Error)
+        self.handle = handle
+        desc = _lib.ProblemDesc()
+        desc.kind, desc.nu = spec.kind, self.nu
+        desc.grid_rows, desc.grid_cols = spec.grid_rows, spec.grid_cols
+        desc.shard_begin, desc.shard_end = self.begin, self.end
+        desc.n_params = len(spec.params)
+        for i, v in enumerate(spec.params):
+            desc.params[i] = float(v)
+        _lib.check(self.lib.tdx_set_problem(self.handle, ctypes.byref(desc)))
+        self.d_local = int(self.lib.tdx_local_dim(self.handle))
+        lo, hi = ctypes.c_int64(), ctypes.c_int64()
+        _lib.check(self.lib.tdx_halo_sizes(self.handle, ctypes.byref(lo), ctypes.byref(hi)))
+        self.halo_lo_n, self.halo_hi_n = lo.value, hi.value
+
+        self._scalars = torch.zeros(4, dtype=torch.float64, device=self.device)   # [sq_norm, z_sq, inv_tol_sq, spare]
+        self.exchanger = None
+        if world > 1:
+            cyclic = spec.kind == _lib.TDX_IVP_LORENZ96
+            # what we send: first edge has the size of the lower neighbour's hi halo, etc.
+            self._edge_first = torch.empty(self._edge_sizes()[0], dtype=dtype, device=self.device)
+            self._edge_last = torch.empty(self._edge_sizes()[1], dtype=dtype, device=self.device)
+            self.exchanger = HaloExchanger(group, rank, world, cyclic, self.halo_lo_n, self.halo_hi_n, dtype, self.device)
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                self.lib.tdx_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+    # ---- helpers ------------------------------------------------------------------------------
+    def _edge_sizes(self):
+        k = self.spec.kind
+        if k == _lib.TDX_IVP_FHN2D:
+            return 2 * self.spec.grid_cols, 2 * self.spec.grid_cols
+        if k == _lib.TDX_IVP_BRUSSELATOR:
+            return 2, 2
+        if k == _lib.TDX_IVP_LORENZ96:
+            return 1, 2
+        return 0, 0
+
+    def _stream(self):
+        return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _args(self, t, dt, abstol, reltol, flags=0):
+        return _lib.StepArgs(float(t), float(dt), float(abstol), float(reltol), int(flags), 0)
+
+    def _check(self, x, shape, name):
+        if not isinstance(x, torch.Tensor) or x.device != self.device or x.dtype != self.dtype:
+            raise ValueError(f"{name} must be a {self.dtype} tensor on {self.device}")
+        if tuple(x.shape) != tuple(shape):
+            raise ValueError(f"{name} has shape {tuple(x.shape)}, expected {tuple(shape)}")
+        if not x.is_contiguous():
+            raise ValueError(f"{name} must be C-contiguous")
+
+    def launch_count(self):
+        return int(self.lib.tdx_launch_count(self.handle))
+
+    def all_reduce_(self, scalar):
+        if self.world > 1:
+            self.exchanger.dist.all_reduce(scalar, group=self.group)
+        return scalar
+
+    def _halos_for_mean(self, dt, mean):
+        """Predicted-state halos for a step from ``mean`` (multi-GPU only)."""
+        if self.world == 1:
+            return None, None
+        _lib.check(self.lib.tdx_pack_halo(self.handle, float(dt), _ptr(mean), _ptr(self._edge_first),
+                                          _ptr(self._edge_last), self._stream()))
+        return self.exchanger.exchange(self._edge_first, self._edge_last)
+
+    # ---- vector field ---------------------------------------------------------------------------
+    def eval_f(self, t, y, want_jac=False):
+        """f(t, y) (and diag df) on the local shard -- replaces ivp.f / ivp.df_diagonal."""
+        self._check(y, (self.d_local,), "y")
+        halo_lo = halo_hi = None
+        if self.world > 1:
+            k = self.spec.kind
+            npts = self.d_local // self.spec.n_fields
+            yf = y.view(self.spec.n_fields, npts)
+            nf_, nl_ = {_lib.TDX_IVP_FHN2D: (self.spec.grid_cols,) * 2, _lib.TDX_IVP_BRUSSELATOR: (1, 1),
+                        _lib.TDX_IVP_LORENZ96: (1, 2)}[k]
+            self._edge_first.copy_(yf[:, :nf_].reshape(-1))
+            self._edge_last.copy_(yf[:, npts - nl_:].reshape(-1))
+            halo_lo, halo_hi = self.exchanger.exchange(self._edge_first, self._edge_last)
+        fy = torch.empty_like(y)
+        jd = torch.empty_like(y) if want_jac else None
+        _lib.check(self.lib.tdx_eval_f(self.handle, float(t), _ptr(y), _ptr(fy), _ptr(jd), _ptr(halo_lo),
+                                       _ptr(halo_hi), self._stream()))
+        return (fy, jd) if want_jac else fy
+
+    # ---- DiagonalEK1 ------------------------------------------------------------------------------
+    def dek1_attempt(self, t, dt, mean, sc, abstol=0.0, reltol=0.0, mean_out=None, sc_out=None, want_err_ref=True,
+                     jacobian=True):
+        """One DiagonalEK1 attempt (``jacobian=False``: DiagonalEK0).  Returns (mean_out, sc_out, err, ref, sq_norm_sum[device scalar])."""
+        n, d = self.n, self.d_local
+        self._check(mean, (n, d), "mean")
+        self._check(sc, (d, n, n), "cov_sqrtm")
+        mean_out = torch.empty_like(mean) if mean_out is None else mean_out
+        sc_out = torch.empty_like(sc) if sc_out is None else sc_out
+        err = torch.empty(d, dtype=self.dtype, device=self.device) if want_err_ref else None
+        ref = torch.empty(d, dtype=self.dtype, device=self.device) if want_err_ref else None
+        halo_lo, halo_hi = self._halos_for_mean(dt, mean)
+        args = self._args(t, dt, abstol, reltol, 0 if jacobian else _lib.TDX_STEP_ZERO_JACOBIAN)
+        sq = self._scalars[0:1]
+        _lib.check(self.lib.tdx_dek1_attempt_step(
+            self.handle, ctypes.byref(args), _ptr(mean), _ptr(sc), _ptr(mean_out), _ptr(sc_out), _ptr(err), _ptr(ref),
+            _ptr(halo_lo), _ptr(halo_hi), _ptr(sq), self._stream()))
+        if abstol != 0.0 or reltol != 0.0:
+            self.all_reduce_(sq)
+        return mean_out, sc_out, err, ref, sq
+
+    # ---- KroneckerEK0 -----------------------------------------------------------------------------
+    def ek0_attempt(self, t, dt, mean, Cl, abstol=0.0, reltol=0.0, mean_out=None, want_ref=True):
+        """One KroneckerEK0 attempt.  Returns (mean_out, Cl_out, err[device scalar], ref, inv_tol_sq_sum)."""
+        n, d = self.n, self.d_local
+        self._check(mean, (n, d), "mean")
+        self._check(Cl, (n, n), "cov_sqrtm_2")
+        mean_out = torch.empty_like(mean) if mean_out is None else mean_out
+        Cl_out = torch.empty_like(Cl)
+        err = torch.empty((), dtype=self.dtype, device=self.device)
+        ref = torch.empty(d, dtype=self.dtype, device=self.device) if want_ref else None
+        halo_lo, halo_hi = self._halos_for_mean(dt, mean)
+        args = self._args(t, dt, abstol, reltol)
+        zsq, itol = self._scalars[1:2], self._scalars[2:3]
+        st = self._stream()
+        _lib.check(self.lib.tdx_ek0_sweep_a(self.handle, ctypes.byref(args), _ptr(mean), _ptr(halo_lo), _ptr(halo_hi),
+                                            _ptr(zsq), st))
+        self.all_reduce_(zsq)
+        _lib.check(self.lib.tdx_ek0_mid(self.handle, ctypes.byref(args), _ptr(Cl), _ptr(zsq), self.d_global,
+                                        _ptr(Cl_out), _ptr(err), st))
+        _lib.check(self.lib.tdx_ek0_sweep_b(self.handle, ctypes.byref(args), _ptr(mean), _ptr(mean_out), _ptr(ref),
+                                            _ptr(halo_lo), _ptr(halo_hi), _ptr(itol), st))
+        if abstol != 0.0 or reltol != 0.0:
+            self.all_reduce_(itol)
+        return mean_out, Cl_out, err, ref, itol
+
+
+def to_numpy(x):
+    return x.detach().cpu().numpy() if isinstance(x, torch.Tensor) else np.asarray(x)
