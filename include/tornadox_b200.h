@@ -127,19 +127,19 @@ int tdx_dek1_attempt_step(tdx_ctx* ctx, const tdx_step_args* args, const void* m
  *            z_sq_sum and the global dimension; writes Cl_out (n,n), err_out (scalar, dtype) and the
  *            gain into the context;
  *  sweep_b : m_new = P (mp - K z), reference_state = |m_new[0]| (ref_out may be NULL) and
- *            sum_i 1 / (abstol + reltol * ref_i)^2 -> ``inv_tol_sq_sum`` (double).
- * The scaled error norm is then dt * err * sqrt(inv_tol_sq_sum / d_global) (step.py:101-104). */
+ *            sum_i (dt * err / (abstol + reltol * ref_i))^2 over the local shard -> ``sq_norm_sum`` (double).
+ * The scaled error norm is then sqrt(sq_norm_sum / d_global) (step.py:101-104), as for DiagonalEK1. */
 int tdx_ek0_sweep_a(tdx_ctx* ctx, const tdx_step_args* args, const void* mean_in,
                     const void* halo_lo, const void* halo_hi, double* z_sq_sum, void* stream);
 int tdx_ek0_mid(tdx_ctx* ctx, const tdx_step_args* args, const void* Cl_in, const double* z_sq_sum,
                 int64_t d_global, void* Cl_out, void* err_out, void* stream);
 int tdx_ek0_sweep_b(tdx_ctx* ctx, const tdx_step_args* args, const void* mean_in, void* mean_out,
                     void* ref_out, const void* halo_lo, const void* halo_hi,
-                    double* inv_tol_sq_sum, void* stream);
+                    double* sq_norm_sum, void* stream);
 /* single-GPU convenience: the three phases back to back on ``stream``. */
 int tdx_ek0_attempt_step(tdx_ctx* ctx, const tdx_step_args* args, const void* mean_in,
                          const void* Cl_in, void* mean_out, void* Cl_out, void* err_out,
-                         void* ref_out, double* z_sq_sum, double* inv_tol_sq_sum, void* stream);
+                         void* ref_out, double* z_sq_sum, double* sq_norm_sum, void* stream);
 
 /* kernels launched by this context since creation (bench.py's gpu_launches counter) */
 int64_t tdx_launch_count(const tdx_ctx* ctx);

@@ -1,0 +1,30 @@
+"""Short run of the step kernels at a given size for ncu (development aid)."""
+import sys
+import numpy as np
+import torch
+sys.path.insert(0, ".")
+from tornadox_b200 import ivp
+from tornadox_b200.engine import StepEngine
+
+size = int(sys.argv[1]) if len(sys.argv) > 1 else 2048
+which = sys.argv[2] if len(sys.argv) > 2 else "both"
+iters = int(sys.argv[3]) if len(sys.argv) > 3 else 3
+dtype = {"f64": torch.float64, "f32": torch.float32}[sys.argv[4] if len(sys.argv) > 4 else "f64"]
+nu = 4; n = nu + 1
+prob = ivp.fhn_2d(dx=1.0/size, y0=np.zeros(2))
+d = 2*size*size
+g = torch.Generator(device="cuda").manual_seed(0)
+eng = StepEngine(prob.spec, nu, dtype=dtype, device="cuda:0")
+mean = torch.rand((n, d), generator=g, device="cuda", dtype=dtype)
+mo = torch.empty_like(mean)
+if which in ("both", "dek1"):
+    sc = 1e-3*torch.randn((d, n, n), generator=g, device="cuda", dtype=dtype)
+    so = torch.empty_like(sc)
+    for _ in range(iters):
+        eng.dek1_attempt(0.0, 1e-4, mean, sc, 1e-4, 1e-2, mean_out=mo, sc_out=so, want_err_ref=True)
+if which in ("both", "ek0"):
+    Cl = 1e-3*torch.randn((n, n), generator=g, device="cuda", dtype=dtype)
+    for _ in range(iters):
+        eng.ek0_attempt(0.0, 1e-4, mean, Cl, 1e-4, 1e-2, mean_out=mo, want_ref=True)
+torch.cuda.synchronize()
+print("ok")

@@ -99,7 +99,7 @@ def test_ek0_attempt_matches_oracle(cuda_device, kind, size, nu, cov):
     assert_close(C.cpu().numpy(), ref_state.cov_sqrtm, FP64_RTOL, "cov_sqrtm_2")
     assert_close(float(err), ref_state.error_estimate, FP64_RTOL, "error_estimate")
     assert_close(ref.cpu().numpy(), ref_state.reference_state, FP64_RTOL, "reference_state")
-    norm = dt * float(err) * math.sqrt(float(itol) / d)
+    norm = math.sqrt(float(itol) / d)
     assert abs(norm - ref_norm) <= FP64_RTOL * abs(ref_norm), (norm, ref_norm)
 
 

@@ -441,7 +441,7 @@ int tdx_ek0_mid(tdx_ctx* ctx, const tdx_step_args* args, const void* Cl_in, cons
 }
 
 int tdx_ek0_sweep_b(tdx_ctx* ctx, const tdx_step_args* args, const void* mean_in, void* mean_out, void* ref_out,
-                    const void* halo_lo, const void* halo_hi, double* inv_tol_sq_sum, void* stream) {
+                    const void* halo_lo, const void* halo_hi, double* sq_norm_sum, void* stream) {
     int rc = check_ready(ctx, "tdx_ek0_sweep_b");
     if (rc) return rc;
     if ((rc = check_dt(args, "tdx_ek0_sweep_b"))) return rc;
@@ -449,24 +449,24 @@ int tdx_ek0_sweep_b(tdx_ctx* ctx, const tdx_step_args* args, const void* mean_in
     if (mean_in == mean_out) return fail(TDX_ERR_INVALID, "tdx_ek0_sweep_b: in and out buffers must be distinct");
     if ((rc = check_halos(ctx, halo_lo, halo_hi, "tdx_ek0_sweep_b"))) return rc;
     StepHost h = make_step(ctx, args);
-    if (h.want_norm && !inv_tol_sq_sum) return fail(TDX_ERR_INVALID, "tdx_ek0_sweep_b: inv_tol_sq_sum is required with tolerances");
+    if (h.want_norm && !sq_norm_sum) return fail(TDX_ERR_INVALID, "tdx_ek0_sweep_b: sq_norm_sum is required with tolerances");
     DeviceGuard guard(ctx->device);
     ctx->launches += 1;
-    return cuda_fail(ctx->ops->ek0_b(ctx->geo, h, mean_in, mean_out, ref_out, halo_lo, halo_hi, make_ws(ctx), inv_tol_sq_sum,
+    return cuda_fail(ctx->ops->ek0_b(ctx->geo, h, mean_in, mean_out, ref_out, halo_lo, halo_hi, make_ws(ctx), sq_norm_sum,
                                      (cudaStream_t)stream),
                      "tdx_ek0_sweep_b");
 }
 
 int tdx_ek0_attempt_step(tdx_ctx* ctx, const tdx_step_args* args, const void* mean_in, const void* Cl_in,
                          void* mean_out, void* Cl_out, void* err_out, void* ref_out, double* z_sq_sum,
-                         double* inv_tol_sq_sum, void* stream) {
+                         double* sq_norm_sum, void* stream) {
     int rc = check_ready(ctx, "tdx_ek0_attempt_step");
     if (rc) return rc;
     if (ctx->halo_lo > 0 || ctx->halo_hi > 0)
         return fail(TDX_ERR_INVALID, "tdx_ek0_attempt_step: sharded contexts must call the three phases and all-reduce in between");
     if ((rc = tdx_ek0_sweep_a(ctx, args, mean_in, nullptr, nullptr, z_sq_sum, stream))) return rc;
     if ((rc = tdx_ek0_mid(ctx, args, Cl_in, z_sq_sum, (int64_t)ctx->geo.d, Cl_out, err_out, stream))) return rc;
-    return tdx_ek0_sweep_b(ctx, args, mean_in, mean_out, ref_out, nullptr, nullptr, inv_tol_sq_sum, stream);
+    return tdx_ek0_sweep_b(ctx, args, mean_in, mean_out, ref_out, nullptr, nullptr, sq_norm_sum, stream);
 }
 
 }  // extern "C"

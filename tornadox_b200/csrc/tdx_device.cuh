@@ -445,8 +445,9 @@ __device__ __forceinline__ double warp_sum(double v) {
     return v;
 }
 
+// The final value is sum * mult * (*mult_sqrt_ptr)^2 (the last two default to 1).
 __device__ __forceinline__ void grid_sum(double v, double* s_red, double* partials, unsigned int* ticket,
-                                         double* out) {
+                                         double* out, double mult = 1.0, const double* mult_sqrt_ptr = nullptr) {
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     v = warp_sum(v);
     if (lane == 0) s_red[w] = v;
@@ -473,7 +474,11 @@ __device__ __forceinline__ void grid_sum(double v, double* s_red, double* partia
             double b = 0.0;
 #pragma unroll
             for (int i = 0; i < kWarps; ++i) b += s_red[i];
-            *out = b;
+            if (mult_sqrt_ptr) {
+                const double r = *mult_sqrt_ptr;
+                b *= r * r;
+            }
+            *out = b * mult;
             *ticket = 0u;
         }
     }

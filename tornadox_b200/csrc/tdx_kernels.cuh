@@ -223,6 +223,7 @@ __global__ void __launch_bounds__(kThreads, TDX_MIN_BLOCKS) dek1_kernel(const __
 template <typename T, int N>
 struct Ek0Mid {          // written by ek0_mid_kernel, read by sweep B
     T K[kMaxN];          // gain  ek0.py:136
+    double err;          // calibrated scalar error estimate  ek0.py:129
 };
 
 template <typename T, int N>
@@ -287,7 +288,9 @@ __global__ void __launch_bounds__(kThreads) ek0_sweep_b_kernel(const __grid_cons
             acc = 1.0 / (tol * tol);
         }
     }
-    if (a.c.want_norm) grid_sum(acc, s_red, a.partials, a.ticket, a.out_sum);
+    // sum_i (dt err / tol_i)^2 = (dt err)^2 sum_i 1 / tol_i^2     step.py:101-104 with a scalar error estimate
+    if (a.c.want_norm)
+        grid_sum(acc, s_red, a.partials, a.ticket, a.out_sum, (double)a.c.dt * (double)a.c.dt, &a.mid->err);
 }
 
 // mid: calibration, ONE stacked QR, gain, factor update; a single thread in fp64.   ek0.py:123-140,175,182
@@ -335,6 +338,7 @@ __global__ void ek0_mid_kernel(const __grid_constant__ Ek0MidArgs<T, N> a) {
         for (int cc = 2; cc < N; ++cc) a.Cl_out[r * N + cc] = (r >= cc) ? (T)(pr * B[r][cc]) : (T)0;
     }
     *a.err_out = (T)err;
+    a.mid->err = err;
 }
 
 // ---------------------------------------------------------------------------------------------

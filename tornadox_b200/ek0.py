@@ -53,8 +53,7 @@ class KroneckerEK0(odefilter.ODEFilter):
             y=rv.LeftIsotropicMatrixNormal(mean, state.y.d, Cl),
         )
         if abstol != 0.0 or reltol != 0.0:
-            # || dt err / (abstol + reltol ref) ||^2 = (dt err)^2 * sum 1 / tol_i^2   (step.py:101-104)
-            new_state.scaled_error_norm_sq_sum = (dt * err.double()) ** 2 * itol[0]
+            new_state.scaled_error_norm_sq_sum = itol   # sum_i (dt err / tol_i)^2, reduced by sweep B
             new_state.scaled_error_norm_dim = self.engine.d_global
         return new_state, dict(num_f_evaluations=1)
 

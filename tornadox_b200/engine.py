@@ -236,7 +236,7 @@ class StepEngine:
 
     # ---- KroneckerEK0 -----------------------------------------------------------------------------
     def ek0_attempt(self, t, dt, mean, Cl, abstol=0.0, reltol=0.0, mean_out=None, want_ref=True):
-        """One KroneckerEK0 attempt.  Returns (mean_out, Cl_out, err[device scalar], ref, inv_tol_sq_sum)."""
+        """One KroneckerEK0 attempt.  Returns (mean_out, Cl_out, err[device scalar], ref, sq_norm_sum)."""
         n, d = self.n, self.d_local
         self._check(mean, (n, d), "mean")
         self._check(Cl, (n, n), "cov_sqrtm_2")
