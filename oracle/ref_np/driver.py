@@ -106,7 +106,8 @@ class Series:
     def _lift(self, other):
         if isinstance(other, Series):
             return other
-        c = np.zeros((self.order,) + np.shape(other))
+        shape = np.shape(other) if np.ndim(other) > 0 else (1,) * (self.c.ndim - 1)
+        c = np.zeros((self.order,) + shape)
         c[0] = other
         return Series(c)
 

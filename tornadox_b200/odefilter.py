@@ -125,6 +125,9 @@ class ODEFilter(ABC):
                 step_info[key] += attempt_info.get(key, 0)
 
             error_norm = self._scaled_error_norm(proposed, dt)
+            if error_norm is not None and math.isnan(error_norm):
+                # the reference would spin forever here (NaN < 1 is False, odefilter.py:179-219)
+                raise FloatingPointError(f"error estimate is NaN at t={state.t}, dt={dt}")
             accepted = self.steprule.is_accepted(error_norm)
             suggested = self.steprule.suggest(dt, error_norm, local_convergence_rate=rate)
             remaining = tmax - (proposed.t if accepted else state.t)
