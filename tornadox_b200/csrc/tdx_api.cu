@@ -246,6 +246,7 @@ int tdx_set_problem(tdx_ctx* ctx, const tdx_problem_desc* d) {
                 const double dx = d->params[0];
                 g.prm[0] = 1.0 / (dx * dx);   // ivp.py:493-494
                 g.prm[1] = d->params[1]; g.prm[2] = d->params[2]; g.prm[3] = d->params[3]; g.prm[4] = d->params[4];
+                g.prm[5] = 1.0 / d->params[4];   // 1 / tau (multiplied, not divided, in-kernel)
             }
             break;
         default:

@@ -117,18 +117,23 @@ struct Coord {
 };
 
 template <class Shape>
-__device__ __forceinline__ Coord tile_coord(const Geo& g) {
+__host__ __device__ inline long long num_tiles(int rows, int cols) {
+    return (long long)((cols + Shape::TC - 1) / Shape::TC) * ((rows + Shape::TR - 1) / Shape::TR);
+}
+
+// coordinates of this thread in tile number ``tile`` (tiles are numbered row-major over the shard)
+template <class Shape>
+__device__ __forceinline__ Coord tile_coord(const Geo& g, unsigned tile, unsigned tiles_x) {
     Coord c;
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int tiles_x = (g.cols + Shape::TC - 1) / Shape::TC;
-    const int tile_y = blockIdx.x / tiles_x, tile_x = blockIdx.x - tile_y * tiles_x;
+    const unsigned tile_y = tile / tiles_x, tile_x = tile - tile_y * tiles_x;
     c.field = w / (Shape::TR * Shape::SEGS);
     const int rem = w - c.field * (Shape::TR * Shape::SEGS);
     c.tr = rem / Shape::SEGS;
     const int seg = rem - c.tr * Shape::SEGS;
     c.tcol = seg * 32 + lane;
-    c.row = tile_y * Shape::TR + c.tr;
-    const int col0 = tile_x * Shape::TC + seg * 32;
+    c.row = (int)tile_y * Shape::TR + c.tr;
+    const int col0 = (int)tile_x * Shape::TC + seg * 32;
     c.col = col0 + lane;
     const bool row_ok = c.row < g.rows;
     c.valid = row_ok && (c.col < g.cols);
@@ -141,47 +146,69 @@ __device__ __forceinline__ Coord tile_coord(const Geo& g) {
 }
 
 template <class Shape>
-__host__ __device__ inline long long num_tiles(int rows, int cols) {
-    return (long long)((cols + Shape::TC - 1) / Shape::TC) * ((rows + Shape::TR - 1) / Shape::TR);
-}
-
-template <class Shape>
 __device__ __forceinline__ int at_index(int field, int tr, int tcol) {
     return (field * Shape::TR + tr) * Shape::TC + tcol;
 }
 
 // ---------------------------------------------------------------------------------------------
-// Vector fields.  Each provides
-//   Shape                       tile shape
-//   prefetch(...)  -> Ext       out-of-tile neighbour values, fetched BEFORE the tile barrier
-//   eval(...)                   f_i and (df/dy)_ii from the shared tile + Ext, AFTER the barrier
-// halo_lo / halo_hi hold the predicted state of the neighbouring shards (or nullptr: single shard).
+// Vector fields.  The stencil reads the predicted state of neighbouring points.  Neighbours inside the
+// CTA's tile come from shared memory; the few that are not are described by a Plan (at most NEXT
+// "external" values per thread) and fetched BEFORE the tile barrier: recomputed from the mean in
+// global/L2 (SRC_MEAN), read from the exchanged shard halos (SRC_LO / SRC_HI), or a boundary constant.
+//   plan(g, c)                    -> Plan   (where does every stencil neighbour of this thread come from)
+//   eval(g, c, s_at, own, ext, plan, fx, jac)   f_i and (df/dy)_ii, AFTER the barrier
 // ---------------------------------------------------------------------------------------------
-template <typename T>
-struct Ext {
-    T a, b, c, e;
+enum : int { SRC_NONE = 0, SRC_MEAN = 1, SRC_LO = 2, SRC_HI = 3, SRC_CONST = 4 };
+enum : unsigned { NB_TILE = 0u, NB_SELF = 1u, NB_EXT = 2u };   // 2-bit codes, NB_EXT + slot
+
+template <typename T, int NEXT_>
+struct Plan {
+    static constexpr int NEXT = NEXT_;
+    long long idx[NEXT_ > 0 ? NEXT_ : 1];
+    int src[NEXT_ > 0 ? NEXT_ : 1];
+    T cval[NEXT_ > 0 ? NEXT_ : 1];
+    unsigned code;   // per-field-kind encoding, 2 bits per stencil neighbour
 };
+
+template <typename T, int NEXT, class At>
+__device__ __forceinline__ void fetch_ext(const Plan<T, NEXT>& pl, const At& at, const T* __restrict__ halo_lo,
+                                          const T* __restrict__ halo_hi, T (&ext)[NEXT > 0 ? NEXT : 1]) {
+#pragma unroll
+    for (int s = 0; s < NEXT; ++s) {
+        T v = (T)0;
+        const int src = pl.src[s];
+        if (src == SRC_MEAN) v = at(pl.idx[s]);
+        else if (src == SRC_LO) v = __ldg(halo_lo + pl.idx[s]);
+        else if (src == SRC_HI) v = __ldg(halo_hi + pl.idx[s]);
+        else if (src == SRC_CONST) v = pl.cval[s];
+        ext[s] = v;
+    }
+}
 
 // --- vanderpol: ivp.py:28-49.  One point, two fields (y1, y2). ---------------------------------
 template <typename T>
 struct VanderPol {
     using Shape = TileShape<2, 1, 4>;
+    static constexpr int NEXT = 0;
     static __host__ void halo_sizes(const Geo&, long long& lo, long long& hi) { lo = hi = 0; }
-    template <class At>
-    __device__ static __forceinline__ Ext<T> prefetch(const Geo&, const Coord&, const At&, const T*, const T*) {
-        return Ext<T>{};
+    __device__ static __forceinline__ Plan<T, NEXT> plan(const Geo&, const Coord&) {
+        Plan<T, NEXT> pl;
+        pl.src[0] = SRC_NONE;
+        pl.code = 0u;
+        return pl;
     }
-    __device__ static __forceinline__ void eval(const Geo& g, const Coord& c, const T* s_at, const Ext<T>&, T own,
-                                                T& fx, T& jac) {
+    __device__ static __forceinline__ void eval(const Geo& g, const Coord& c, const T* s_at, T own, const T (&)[1],
+                                                const Plan<T, NEXT>&, T& fx, T& jac) {
         const T mu = (T)g.prm[0];
         const T y1 = s_at[at_index<Shape>(0, 0, c.tcol)];
         const T y2 = s_at[at_index<Shape>(1, 0, c.tcol)];
+        const T damp = mu * ((T)1 - y1 * y1);
         if (c.field == 0) {
             fx = y2;
             jac = (T)0;
         } else {
-            fx = mu * ((T)1 - y1 * y1) * y2 - y1;
-            jac = mu * ((T)1 - y1 * y1);
+            fx = damp * y2 - y1;
+            jac = damp;
         }
         (void)own;
     }
@@ -191,44 +218,48 @@ struct VanderPol {
 template <typename T>
 struct Lorenz96 {
     using Shape = TileShape<1, 1, 8>;
+    static constexpr int NEXT = 3;   // slots: i-2, i-1, i+1
     // lower halo = points (i0-2, i0-1), upper halo = point i0+cols (all cyclic)
     static __host__ void halo_sizes(const Geo& g, long long& lo, long long& hi) {
         const bool sharded = g.cols != g.gcols;
         lo = sharded ? 2 : 0;
         hi = sharded ? 1 : 0;
     }
-    template <class At>
-    __device__ static __forceinline__ T outside(const Geo& g, const Coord& c, const At& at, const T* halo_lo,
-                                                const T* halo_hi, int off) {
+    __device__ static __forceinline__ void outside(const Geo& g, const Coord& c, int off, Plan<T, NEXT>& pl, int s) {
         // cyclic neighbour col + off that is not inside the tile
         long long gi = g.gcol0 + c.col + off;
         if (gi < 0) gi += g.gcols;
         if (gi >= g.gcols) gi -= g.gcols;
+        if (gi < 0) gi += g.gcols;          // chains shorter than the stencil reach
         const long long li = gi - g.gcol0;
-        if (li >= 0 && li < g.cols) return at(li);
-        // not owned: one of the exchanged halo values
-        if (off < 0) {
-            const long long k = (long long)c.col + off;  // -2 or -1
-            return halo_lo[2 + k];
+        if (li >= 0 && li < g.cols) {
+            pl.src[s] = SRC_MEAN;
+            pl.idx[s] = li;
+        } else if (off < 0) {
+            pl.src[s] = SRC_LO;
+            pl.idx[s] = 2 + ((long long)c.col + off);   // halo_lo = [i0-2, i0-1]
+        } else {
+            pl.src[s] = SRC_HI;
+            pl.idx[s] = 0;
         }
-        return halo_hi[0];
     }
-    template <class At>
-    __device__ static __forceinline__ Ext<T> prefetch(const Geo& g, const Coord& c, const At& at, const T* halo_lo,
-                                                      const T* halo_hi) {
-        Ext<T> e{};
-        if (!c.valid) return e;
-        if (c.tcol - 2 < 0) e.a = outside(g, c, at, halo_lo, halo_hi, -2);
-        if (c.tcol - 1 < 0) e.b = outside(g, c, at, halo_lo, halo_hi, -1);
-        if (c.tcol + 1 >= Shape::TC || c.col + 1 >= g.cols) e.c = outside(g, c, at, halo_lo, halo_hi, +1);
-        return e;
+    __device__ static __forceinline__ Plan<T, NEXT> plan(const Geo& g, const Coord& c) {
+        Plan<T, NEXT> pl;
+        pl.code = 0u;
+#pragma unroll
+        for (int s = 0; s < NEXT; ++s) pl.src[s] = SRC_NONE;
+        if (!c.valid) return pl;
+        if (c.tcol - 2 < 0) { outside(g, c, -2, pl, 0); pl.code |= 1u; }
+        if (c.tcol - 1 < 0) { outside(g, c, -1, pl, 1); pl.code |= 2u; }
+        if (c.tcol + 1 >= Shape::TC || c.col + 1 >= g.cols) { outside(g, c, +1, pl, 2); pl.code |= 4u; }
+        return pl;
     }
-    __device__ static __forceinline__ void eval(const Geo& g, const Coord& c, const T* s_at, const Ext<T>& e, T own,
-                                                T& fx, T& jac) {
+    __device__ static __forceinline__ void eval(const Geo& g, const Coord& c, const T* s_at, T own, const T (&ext)[NEXT],
+                                                const Plan<T, NEXT>& pl, T& fx, T& jac) {
         const T F = (T)g.prm[0];
-        const T ym2 = (c.tcol - 2 < 0) ? e.a : s_at[c.tcol - 2];
-        const T ym1 = (c.tcol - 1 < 0) ? e.b : s_at[c.tcol - 1];
-        const T yp1 = (c.tcol + 1 >= Shape::TC || c.col + 1 >= g.cols) ? e.c : s_at[c.tcol + 1];
+        const T ym2 = (pl.code & 1u) ? ext[0] : s_at[c.tcol - 2];
+        const T ym1 = (pl.code & 2u) ? ext[1] : s_at[c.tcol - 1];
+        const T yp1 = (pl.code & 4u) ? ext[2] : s_at[c.tcol + 1];
         fx = (yp1 - ym2) * ym1 - own + F;
         jac = (T)-1;
     }
@@ -238,41 +269,47 @@ struct Lorenz96 {
 template <typename T>
 struct Brusselator {
     using Shape = TileShape<2, 1, 4>;
+    static constexpr int NEXT = 2;   // slots: left, right
     static __host__ void halo_sizes(const Geo& g, long long& lo, long long& hi) {
         lo = (g.gcol0 > 0) ? 2 : 0;                  // (u, v) of point i0-1
         hi = (g.gcol0 + g.cols < g.gcols) ? 2 : 0;   // (u, v) of point i0+cols
     }
-    template <class At>
-    __device__ static __forceinline__ Ext<T> prefetch(const Geo& g, const Coord& c, const At& at, const T* halo_lo,
-                                                      const T* halo_hi) {
-        Ext<T> e{};
-        if (!c.valid) return e;
+    __device__ static __forceinline__ Plan<T, NEXT> plan(const Geo& g, const Coord& c) {
+        Plan<T, NEXT> pl;
+        pl.code = 0u;
+        pl.src[0] = pl.src[1] = SRC_NONE;
+        if (!c.valid) return pl;
         const T pad = (c.field == 0) ? (T)1 : (T)3;
         const long long gi = g.gcol0 + c.col;
-        if (gi == 0) e.a = pad;
-        else if (c.tcol == 0) e.a = (c.col > 0) ? at(c.flat - 1) : halo_lo[c.field];
-        if (gi == g.gcols - 1) e.b = pad;
-        else if (c.tcol + 1 >= Shape::TC || c.col + 1 >= g.cols)
-            e.b = (c.col + 1 < g.cols) ? at(c.flat + 1) : halo_hi[c.field];
-        return e;
+        if (gi == 0) { pl.src[0] = SRC_CONST; pl.cval[0] = pad; pl.code |= 1u; }
+        else if (c.tcol == 0) {
+            pl.code |= 1u;
+            if (c.col > 0) { pl.src[0] = SRC_MEAN; pl.idx[0] = c.flat - 1; }
+            else { pl.src[0] = SRC_LO; pl.idx[0] = c.field; }
+        }
+        if (gi == g.gcols - 1) { pl.src[1] = SRC_CONST; pl.cval[1] = pad; pl.code |= 2u; }
+        else if (c.tcol + 1 >= Shape::TC || c.col + 1 >= g.cols) {
+            pl.code |= 2u;
+            if (c.col + 1 < g.cols) { pl.src[1] = SRC_MEAN; pl.idx[1] = c.flat + 1; }
+            else { pl.src[1] = SRC_HI; pl.idx[1] = c.field; }
+        }
+        return pl;
     }
-    __device__ static __forceinline__ void eval(const Geo& g, const Coord& c, const T* s_at, const Ext<T>& e, T own,
-                                                T& fx, T& jac) {
+    __device__ static __forceinline__ void eval(const Geo& g, const Coord& c, const T* s_at, T own, const T (&ext)[NEXT],
+                                                const Plan<T, NEXT>& pl, T& fx, T& jac) {
         const T cc = (T)g.prm[0];
-        const long long gi = g.gcol0 + c.col;
-        const bool ext_l = (gi == 0) || (c.tcol == 0);
-        const bool ext_r = (gi == g.gcols - 1) || (c.tcol + 1 >= Shape::TC) || (c.col + 1 >= g.cols);
-        const T left = ext_l ? e.a : s_at[at_index<Shape>(c.field, 0, c.tcol - 1)];
-        const T right = ext_r ? e.b : s_at[at_index<Shape>(c.field, 0, c.tcol + 1)];
+        const T left = (pl.code & 1u) ? ext[0] : s_at[at_index<Shape>(c.field, 0, c.tcol - 1)];
+        const T right = (pl.code & 2u) ? ext[1] : s_at[at_index<Shape>(c.field, 0, c.tcol + 1)];
         const T u = s_at[at_index<Shape>(0, 0, c.tcol)];
         const T v = s_at[at_index<Shape>(1, 0, c.tcol)];
         const T conv = (left - (T)2 * own) + right;
+        const T uu = u * u;
         if (c.field == 0) {
-            fx = (T)1 + u * u * v - (T)4 * u + cc * conv;
+            fx = (T)1 + uu * v - (T)4 * u + cc * conv;
             jac = (T)2 * u * v - (T)4 - (T)2 * cc;
         } else {
-            fx = (T)3 * u - u * u * v + cc * conv;
-            jac = -(u * u) - (T)2 * cc;
+            fx = (T)3 * u - uu * v + cc * conv;
+            jac = -uu - (T)2 * cc;
         }
     }
 };
@@ -282,49 +319,55 @@ struct Brusselator {
 template <typename T>
 struct Fhn2d {
     using Shape = TileShape<2, 4, 1>;
+    static constexpr int NEXT = 3;   // slots: up, down, horizontal (left for tcol == 0, right for the last column)
     static __host__ void halo_sizes(const Geo& g, long long& lo, long long& hi) {
         lo = (g.grow0 > 0) ? 2LL * g.cols : 0;                 // row above, both fields
         hi = (g.grow0 + g.rows < g.grows) ? 2LL * g.cols : 0;  // row below
     }
-    struct Where {
-        bool up_rep, dn_rep, lf_rep, rt_rep;   // replicate own value (domain boundary)
-        bool up_ext, dn_ext, lf_ext, rt_ext;   // value comes from outside the tile
-    };
-    __device__ static __forceinline__ Where where(const Geo& g, const Coord& c) {
-        Where w;
+    // code: bits [1:0] up, [3:2] down, [5:4] left, [7:6] right, each NB_TILE / NB_SELF / NB_EXT
+    __device__ static __forceinline__ Plan<T, NEXT> plan(const Geo& g, const Coord& c) {
+        Plan<T, NEXT> pl;
+        pl.code = 0u;
+#pragma unroll
+        for (int s = 0; s < NEXT; ++s) pl.src[s] = SRC_NONE;
+        if (!c.valid) return pl;
         const long long gr = g.grow0 + c.row;
-        w.up_rep = (gr == 0);
-        w.dn_rep = (gr == g.grows - 1);
-        w.lf_rep = (c.col == 0);
-        w.rt_rep = (c.col == g.cols - 1);
-        w.up_ext = !w.up_rep && (c.tr == 0);
-        w.dn_ext = !w.dn_rep && (c.tr + 1 >= Shape::TR || c.row + 1 >= g.rows);
-        w.lf_ext = !w.lf_rep && (c.tcol == 0);
-        w.rt_ext = !w.rt_rep && (c.tcol + 1 >= Shape::TC);
-        return w;
+        const long long halo_idx = (long long)c.field * g.cols + c.col;
+        // up
+        if (gr == 0) pl.code |= NB_SELF;
+        else if (c.tr == 0) {
+            pl.code |= NB_EXT;
+            if (c.row > 0) { pl.src[0] = SRC_MEAN; pl.idx[0] = c.flat - g.cols; }
+            else { pl.src[0] = SRC_LO; pl.idx[0] = halo_idx; }
+        }
+        // down
+        if (gr == g.grows - 1) pl.code |= NB_SELF << 2;
+        else if (c.tr + 1 >= Shape::TR || c.row + 1 >= g.rows) {
+            pl.code |= NB_EXT << 2;
+            if (c.row + 1 < g.rows) { pl.src[1] = SRC_MEAN; pl.idx[1] = c.flat + g.cols; }
+            else { pl.src[1] = SRC_HI; pl.idx[1] = halo_idx; }
+        }
+        // left / right share slot 2 (a thread is never both the first and the last column of a 32-wide tile)
+        if (c.col == 0) pl.code |= NB_SELF << 4;
+        else if (c.tcol == 0) { pl.code |= NB_EXT << 4; pl.src[2] = SRC_MEAN; pl.idx[2] = c.flat - 1; }
+        if (c.col == g.cols - 1) pl.code |= NB_SELF << 6;
+        else if (c.tcol + 1 >= Shape::TC) { pl.code |= NB_EXT << 6; pl.src[2] = SRC_MEAN; pl.idx[2] = c.flat + 1; }
+        return pl;
     }
-    template <class At>
-    __device__ static __forceinline__ Ext<T> prefetch(const Geo& g, const Coord& c, const At& at, const T* halo_lo,
-                                                      const T* halo_hi) {
-        Ext<T> e{};
-        if (!c.valid) return e;
-        const Where w = where(g, c);
-        if (w.up_ext) e.a = (c.row > 0) ? at(c.flat - g.cols) : halo_lo[(long long)c.field * g.cols + c.col];
-        if (w.dn_ext) e.b = (c.row + 1 < g.rows) ? at(c.flat + g.cols) : halo_hi[(long long)c.field * g.cols + c.col];
-        if (w.lf_ext) e.c = at(c.flat - 1);
-        if (w.rt_ext) e.e = at(c.flat + 1);
-        return e;
+    __device__ static __forceinline__ T pick(unsigned code, T own, T extv, const T* s_at, int idx) {
+        return code == NB_TILE ? s_at[idx] : (code == NB_SELF ? own : extv);
     }
-    __device__ static __forceinline__ void eval(const Geo& g, const Coord& c, const T* s_at, const Ext<T>& e, T own,
-                                                T& fx, T& jac) {
-        const T inv_dx2 = (T)g.prm[0], a = (T)g.prm[1], b = (T)g.prm[2], k = (T)g.prm[3], tau = (T)g.prm[4];
-        const Where w = where(g, c);
-        const T up = w.up_rep ? own : (w.up_ext ? e.a : s_at[at_index<Shape>(c.field, c.tr - 1, c.tcol)]);
-        const T dn = w.dn_rep ? own : (w.dn_ext ? e.b : s_at[at_index<Shape>(c.field, c.tr + 1, c.tcol)]);
-        const T lf = w.lf_rep ? own : (w.lf_ext ? e.c : s_at[at_index<Shape>(c.field, c.tr, c.tcol - 1)]);
-        const T rt = w.rt_rep ? own : (w.rt_ext ? e.e : s_at[at_index<Shape>(c.field, c.tr, c.tcol + 1)]);
+    __device__ static __forceinline__ void eval(const Geo& g, const Coord& c, const T* s_at, T own, const T (&ext)[NEXT],
+                                                const Plan<T, NEXT>& pl, T& fx, T& jac) {
+        const T inv_dx2 = (T)g.prm[0], a = (T)g.prm[1], b = (T)g.prm[2], k = (T)g.prm[3], inv_tau = (T)g.prm[5];
+        const unsigned cu = pl.code & 3u, cd = (pl.code >> 2) & 3u, cl = (pl.code >> 4) & 3u, cr = (pl.code >> 6) & 3u;
+        const int here = at_index<Shape>(c.field, c.tr, c.tcol);
+        const T up = pick(cu, own, ext[0], s_at, here - Shape::TC);
+        const T dn = pick(cd, own, ext[1], s_at, here + Shape::TC);
+        const T lf = pick(cl, own, ext[2], s_at, here - 1);
+        const T rt = pick(cr, own, ext[2], s_at, here + 1);
         const T lap = (((up + dn) + (lf + rt)) - (T)4 * own) * inv_dx2;
-        const int nrep = (int)w.up_rep + (int)w.dn_rep + (int)w.lf_rep + (int)w.rt_rep;
+        const int nrep = (int)(cu == NB_SELF) + (int)(cd == NB_SELF) + (int)(cl == NB_SELF) + (int)(cr == NB_SELF);
         const T dl = -(T)(4 - nrep) * inv_dx2;   // ivp.py:447-463: 2 (corner), 3 (edge), 4 (interior)
         const T u = s_at[at_index<Shape>(0, c.tr, c.tcol)];
         const T v = s_at[at_index<Shape>(1, c.tr, c.tcol)];
@@ -332,8 +375,8 @@ struct Fhn2d {
             fx = a * lap + u - u * u * u - v + k;
             jac = a * dl + (T)1 - (T)3 * (u * u);
         } else {
-            fx = (b * lap + u - v) / tau;
-            jac = (b * dl - (T)1) / tau;
+            fx = (b * lap + u - v) * inv_tau;
+            jac = (b * dl - (T)1) * inv_tau;
         }
     }
 };

@@ -16,6 +16,7 @@ static int eval_f_launch(const Geo& g, const void* y, void* fy, void* jd, const 
     TDX_SWITCH_IVP(g.kind, T, {
         using Shape = typename IVP::Shape;
         const long long grid = num_tiles<Shape>(g.rows, g.cols);
+        a.tiles_x = (unsigned)((g.cols + Shape::TC - 1) / Shape::TC);
         eval_f_kernel<IVP, T><<<(unsigned)grid, kThreads, 0, st>>>(a);
     })
     return (int)cudaGetLastError();

@@ -10,6 +10,9 @@ namespace tdx {
 #ifndef TDX_MIN_BLOCKS
 #define TDX_MIN_BLOCKS 2
 #endif
+#ifndef TDX_PREFETCH_MEAN
+#define TDX_PREFETCH_MEAN 0   // 1: hold the next tile's mean column in registers during the QR (spills at 128 regs)
+#endif
 
 template <typename T>
 __device__ __forceinline__ T tabs(T x) { return x < (T)0 ? -x : x; }
@@ -41,32 +44,52 @@ struct SmemLayout {
 };
 
 // ---------------------------------------------------------------------------------------------
-// front end shared by all step kernels: load the mean column, predict, publish the predicted state
-// to the tile, evaluate f and diag(J).      ek1.py:232,262-265,302-312 / ek0.py:161-166,142-150
+// front end shared by all step kernels, in two halves so that a persistent kernel can issue the loads of
+// the NEXT tile before it computes the current one.
+//   front_load : this thread's mean column + the out-of-tile stencil neighbours (global / L2 loads)
+//   front_eval : predict, publish the predicted state to the tile, barrier, evaluate f and diag(J)
+// ek1.py:232,262-265,302-312 / ek0.py:161-166,142-150
 // ---------------------------------------------------------------------------------------------
 template <class IVP, typename T, int N>
-__device__ __forceinline__ void front_end(const Geo& g, const Consts<T, N>& c, const T* __restrict__ mean_in,
-                                          const T* halo_lo, const T* halo_hi, const Coord& co, T* s_at, T& raw0,
-                                          T (&mp)[N], T& fx, T& jac) {
-    using Shape = typename IVP::Shape;
+struct FrontRegs {
     T raw[N];
+    T ext[IVP::NEXT > 0 ? IVP::NEXT : 1];
+    Plan<T, IVP::NEXT> plan;
+};
+
+template <class IVP, typename T, int N>
+__device__ __forceinline__ void front_load(const Geo& g, const Consts<T, N>& c, const T* __restrict__ mean_in,
+                                           const T* halo_lo, const T* halo_hi, const Coord& co,
+                                           FrontRegs<IVP, T, N>& fr) {
+    const T* src = mean_in + co.flat;
 #pragma unroll
-    for (int k = 0; k < N; ++k) raw[k] = co.valid ? __ldg(mean_in + (long long)k * g.d + co.flat) : (T)0;
+    for (int k = 0; k < N; ++k) {
+        fr.raw[k] = co.valid ? __ldg(src) : (T)0;
+        src += g.d;
+    }
+    fr.plan = IVP::plan(g, co);
     MeanAt<T, N> at{mean_in, g.d, &c};
-    const Ext<T> ext = IVP::prefetch(g, co, at, halo_lo, halo_hi);
-    predict_column<T, N>(raw, c, mp);
-    raw0 = raw[0];
+    fetch_ext<T, IVP::NEXT>(fr.plan, at, halo_lo, halo_hi, fr.ext);
+}
+
+template <class IVP, typename T, int N>
+__device__ __forceinline__ void front_eval(const Geo& g, const Consts<T, N>& c, const Coord& co,
+                                           const FrontRegs<IVP, T, N>& fr, T* s_at, T (&mp)[N], T& fx, T& jac) {
+    using Shape = typename IVP::Shape;
+    predict_column<T, N>(fr.raw, c, mp);
     const T own = c.p[0] * mp[0];
     s_at[at_index<Shape>(co.field, co.tr, co.tcol)] = own;
     __syncthreads();
     fx = (T)0;
     jac = (T)0;
-    if (co.valid) IVP::eval(g, co, s_at, ext, own, fx, jac);
+    if (co.valid) IVP::eval(g, co, s_at, own, fr.ext, fr.plan, fx, jac);
     if (c.flags & 1u) jac = (T)0;   // TDX_STEP_ZERO_JACOBIAN: DiagonalEK0, ek0.py:196-280
 }
 
 // ---------------------------------------------------------------------------------------------
-// DiagonalEK1 fused attempt
+// DiagonalEK1 fused attempt: persistent CTAs, two shared-memory slots per warp for the factor blocks.
+// While a warp computes tile i out of slot i&1, the TMA engine fills the other slot with tile i+1 and
+// drains tile i-1's results; the only CTA-wide barrier per tile is the one that publishes the stencil tile.
 // ---------------------------------------------------------------------------------------------
 template <typename T, int N>
 struct DekArgs {
@@ -83,6 +106,16 @@ struct DekArgs {
     double* partials;
     unsigned int* ticket;
     double* out_sum;
+    unsigned int num_tiles, tiles_x;
+};
+
+template <typename T, int N>
+struct DekSmem {
+    using L = SmemLayout<T, N>;
+    static constexpr int SLOTS = 2;
+    __host__ __device__ static constexpr size_t total(int at_elems) {
+        return L::BAR_BYTES + L::RED_BYTES + SLOTS * L::at_bytes(at_elems) + SLOTS * L::sc_bytes();
+    }
 };
 
 template <class IVP, typename T, int N>
@@ -91,130 +124,178 @@ __global__ void __launch_bounds__(kThreads, TDX_MIN_BLOCKS) dek1_kernel(const __
     using L = SmemLayout<T, N>;
     constexpr int NN = L::NN, STRIDE = L::STRIDE;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);                       // [2][kWarps]
     double* s_red = reinterpret_cast<double*>(smem_raw + L::BAR_BYTES);
-    T* s_at = reinterpret_cast<T*>(smem_raw + L::BAR_BYTES + L::RED_BYTES);
-    T* s_sc = reinterpret_cast<T*>(smem_raw + L::BAR_BYTES + L::RED_BYTES + L::at_bytes(Shape::AT_ELEMS));
+    T* s_at0 = reinterpret_cast<T*>(smem_raw + L::BAR_BYTES + L::RED_BYTES);      // [2][AT_ELEMS]
+    T* s_sc0 = reinterpret_cast<T*>(smem_raw + L::BAR_BYTES + L::RED_BYTES + 2 * L::at_bytes(Shape::AT_ELEMS));
+    constexpr size_t AT_STRIDE = L::at_bytes(Shape::AT_ELEMS) / sizeof(T);
+    constexpr size_t SC_STRIDE = L::sc_bytes() / sizeof(T);
 
     const Geo& g = a.g;
     const Consts<T, N>& c = a.c;
-    const Coord co = tile_coord<Shape>(g);
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    T* my_sc = s_sc + w * 32 * STRIDE;
-    uint64_t* bar = bars + w;
 
-    // (1) start streaming this warp's 32 factor blocks into shared memory
-    const long long sc_off = co.seg_base * NN;
-    const uint32_t seg_bytes = (uint32_t)(co.seg_len * NN * sizeof(T));
-    const bool full = (STRIDE == NN) && (co.seg_len == 32);
-    const bool bulk_in = full && ((reinterpret_cast<uintptr_t>(a.sc_in + sc_off) & 15) == 0);
-    const bool bulk_out = full && ((reinterpret_cast<uintptr_t>(a.sc_out + sc_off) & 15) == 0);
-    if (bulk_in) {
-        if (lane == 0) {
-            mbar_init(bar, 1);
-            fence_mbar_init();
-            fence_proxy_async();
-            mbar_expect_tx(bar, seg_bytes);
-            bulk_g2s(my_sc, a.sc_in + sc_off, seg_bytes, bar);
-        }
-    } else {
-        const int total = co.seg_len * NN;
-        for (int e = lane; e < total; e += 32) {
-            const int blk = e / NN;
-            my_sc[blk * STRIDE + (e - blk * NN)] = __ldg(a.sc_in + sc_off + e);
-        }
+    if (lane == 0) {
+        mbar_init(bars + w, 1);
+        mbar_init(bars + kWarps + w, 1);
+        fence_mbar_init();
+        fence_proxy_async();
     }
-
-    // (2) mean column, prediction, vector field
-    T raw0, mp[N], fx, jac;
-    front_end<IVP, T, N>(g, c, a.mean_in, a.halo_lo, a.halo_hi, co, s_at, raw0, mp, fx, jac);
-
-    if (bulk_in) mbar_wait(bar, 0);
     __syncwarp();
 
-    double ratio_sq = 0.0;
-    if (co.valid) {
-        const T z = c.p[1] * mp[1] - fx;
+    // issue the streaming load of one tile's 32 factor blocks of this warp into a slot; returns whether the
+    // bulk (TMA) path was used (warp-uniform), in which case the data lands on the slot's mbarrier
+    auto stage_in = [&](const Coord& co, int slot) -> bool {
+        T* dst = s_sc0 + slot * SC_STRIDE + w * 32 * STRIDE;
+        const long long off = co.seg_base * NN;
+        const bool bulk = (STRIDE == NN) && (co.seg_len == 32) && ((reinterpret_cast<uintptr_t>(a.sc_in + off) & 15) == 0);
+        if (bulk) {
+            if (lane == 0) {
+                uint64_t* bar = bars + slot * kWarps + w;
+                mbar_expect_tx(bar, (uint32_t)(32 * NN * sizeof(T)));
+                bulk_g2s(dst, a.sc_in + off, (uint32_t)(32 * NN * sizeof(T)), bar);
+            }
+        } else {
+            const int total = co.seg_len * NN;
+            for (int e = lane; e < total; e += 32) {
+                const int blk = e / NN;
+                dst[blk * STRIDE + (e - blk * NN)] = __ldg(a.sc_in + off + e);
+            }
+        }
+        return bulk;
+    };
 
-        // estimate_error / local diffusion  ek1.py:314-331.  Ql rows 0 and 1 have 1 and 2 nonzeros.
-        const T h0 = c.p[1] * QL(c, 1, 0) - jac * (c.p[0] * QL(c, 0, 0));
-        const T h1 = c.p[1] * QL(c, 1, 1);
-        const T s = h0 * h0 + h1 * h1;
-        const T sqs = tsqrt<T>(s);
-        const T sigma = tabs<T>(z / sqs);
-        const T err = sigma * sqs;
+    unsigned tile = blockIdx.x;
+    unsigned phase_bits = 0u;          // parity of each slot's mbarrier
+    double ratio_sq_acc = 0.0;
+    Coord co{};
+    FrontRegs<IVP, T, N> fr;
+    bool cur_bulk = false;
+    if (tile < a.num_tiles) {
+        co = tile_coord<Shape>(g, tile, a.tiles_x);
+        cur_bulk = stage_in(co, 0);
+        if (TDX_PREFETCH_MEAN) front_load<IVP, T, N>(g, c, a.mean_in, a.halo_lo, a.halo_hi, co, fr);
+    }
 
-        // B = A (p_inv * sc)   ek1.py:233,269
-        T B[N][N];
-        const T* blk = my_sc + lane * STRIDE;
+    for (unsigned it = 0; tile < a.num_tiles; ++it) {
+        const int slot = it & 1;
+        T* my_sc = s_sc0 + slot * SC_STRIDE + w * 32 * STRIDE;
+        T* s_at = s_at0 + slot * AT_STRIDE;
+        if (!TDX_PREFETCH_MEAN) front_load<IVP, T, N>(g, c, a.mean_in, a.halo_lo, a.halo_hi, co, fr);
+
+        // (1) predict + vector field of the current tile (its loads were issued one iteration ago)
+        T mp[N], fx, jac;
+        front_eval<IVP, T, N>(g, c, co, fr, s_at, mp, fx, jac);
+        const T raw0 = fr.raw[0];
+        const Coord cur = co;
+
+        // (2) start the loads of the next tile: factor blocks into the other slot, mean column into registers
+        const unsigned next = tile + gridDim.x;
+        bool next_bulk = false;
+        if (next < a.num_tiles) {
+            if (lane == 0) bulk_wait_read0();      // the other slot's previous results have left shared memory
+            __syncwarp();
+            co = tile_coord<Shape>(g, next, a.tiles_x);
+            next_bulk = stage_in(co, slot ^ 1);
+            if (TDX_PREFETCH_MEAN) front_load<IVP, T, N>(g, c, a.mean_in, a.halo_lo, a.halo_hi, co, fr);
+        }
+
+        // (3) wait for the current tile's blocks
+        if (cur_bulk) {
+            mbar_wait(bars + slot * kWarps + w, (phase_bits >> slot) & 1u);
+            phase_bits ^= (1u << slot);
+        }
+        __syncwarp();
+
+        const long long sc_off = cur.seg_base * NN;
+        const bool bulk_out = (STRIDE == NN) && (cur.seg_len == 32) &&
+                              ((reinterpret_cast<uintptr_t>(a.sc_out + sc_off) & 15) == 0);
+        if (cur.valid) {
+            const T z = c.p[1] * mp[1] - fx;
+
+            // estimate_error / local diffusion  ek1.py:314-331.  Ql rows 0 and 1 have 1 and 2 nonzeros.
+            const T h0 = c.p[1] * QL(c, 1, 0) - jac * (c.p[0] * QL(c, 0, 0));
+            const T h1 = c.p[1] * QL(c, 1, 1);
+            const T s = h0 * h0 + h1 * h1;
+            const T sqs = tsqrt<T>(s);
+            const T sigma = tabs<T>(z / sqs);
+            const T err = sigma * sqs;
+
+            // B = A (p_inv * sc)   ek1.py:233,269
+            T B[N][N];
+            T* blk = my_sc + lane * STRIDE;
 #pragma unroll
-        for (int j = 0; j < N; ++j) {
-            T col[N];
+            for (int j = 0; j < N; ++j) {
+                T col[N];
 #pragma unroll
-            for (int k = 0; k < N; ++k) col[k] = c.pinv[k] * blk[k * N + j];
+                for (int k = 0; k < N; ++k) col[k] = c.pinv[k] * blk[k * N + j];
 #pragma unroll
-            for (int i = 0; i < N; ++i) {
-                T acc = col[i];
+                for (int i = 0; i < N; ++i) {
+                    T acc = col[i];
 #pragma unroll
-                for (int k = i + 1; k < N; ++k) acc = fma((T)A_entry<N>(i, k), col[k], acc);
-                B[i][j] = acc;
+                    for (int k = i + 1; k < N; ++k) acc = fma((T)A_entry<N>(i, k), col[k], acc);
+                    B[i][j] = acc;
+                }
+            }
+
+            // predict_cov_sqrtm: QR of [(A sc)^T ; (sigma Ql)^T]   ek1.py:267-270, sqrt.py:8-30
+            stacked_qr<T, N>(B, sigma, c);
+
+            // observe_cov_sqrtm  ek1.py:333-349 (L = lower(B); rows 0,1 have 1 and 2 nonzeros)
+            const T g0 = c.p[1] * B[1][0] - jac * (c.p[0] * B[0][0]);
+            const T g1 = c.p[1] * B[1][1];
+            const T s2 = (g0 * g0 + g1 * g1) + (T)1e-16;
+            const T inv_s2 = (T)1 / s2;
+
+            // correct_cov_sqrtm / correct_mean  ek1.py:351-369, un-precondition ek1.py:246-247
+            T new_m0 = (T)0;
+            T* mo_ptr = a.mean_out + cur.flat;
+#pragma unroll
+            for (int r = 0; r < N; ++r) {
+                const T l0 = B[r][0];
+                const T l1 = (r >= 1) ? B[r][1] : (T)0;
+                const T kg = (l0 * g0 + l1 * g1) * inv_s2;
+                const T pr = c.p[r];
+                blk[r * N + 0] = pr * (l0 - kg * g0);
+                blk[r * N + 1] = pr * (l1 - kg * g1);
+#pragma unroll
+                for (int cc = 2; cc < N; ++cc) blk[r * N + cc] = (r >= cc) ? pr * B[r][cc] : (T)0;
+                const T mo = pr * (mp[r] - kg * z);
+                *mo_ptr = mo;
+                mo_ptr += g.d;
+                if (r == 0) new_m0 = mo;
+            }
+            const T ref = nanmax<T>(tabs<T>(raw0), tabs<T>(new_m0));   // ek1.py:249-251
+            if (a.err_out) a.err_out[cur.flat] = err;
+            if (a.ref_out) a.ref_out[cur.flat] = ref;
+            if (c.want_norm) {
+                const double ratio = ((double)c.dt * (double)err) / ((double)c.abstol + (double)c.reltol * (double)ref);
+                ratio_sq_acc += ratio * ratio;                         // step.py:101-104
             }
         }
 
-        // predict_cov_sqrtm: QR of [(A sc)^T ; (sigma Ql)^T]   ek1.py:267-270, sqrt.py:8-30
-        stacked_qr<T, N>(B, sigma, c);
-
-        // observe_cov_sqrtm  ek1.py:333-349 (L = lower(B); rows 0,1 have 1 and 2 nonzeros)
-        const T g0 = c.p[1] * B[1][0] - jac * (c.p[0] * B[0][0]);
-        const T g1 = c.p[1] * B[1][1];
-        const T s2 = (g0 * g0 + g1 * g1) + (T)1e-16;
-        const T inv_s2 = (T)1 / s2;
-
-        // correct_cov_sqrtm / correct_mean  ek1.py:351-369, un-precondition ek1.py:246-247
-        T* outblk = my_sc + lane * STRIDE;
-        T new_m0 = (T)0;
-#pragma unroll
-        for (int r = 0; r < N; ++r) {
-            const T l0 = B[r][0];
-            const T l1 = (r >= 1) ? B[r][1] : (T)0;
-            const T kg = (l0 * g0 + l1 * g1) * inv_s2;
-            const T pr = c.p[r];
-            outblk[r * N + 0] = pr * (l0 - kg * g0);
-            outblk[r * N + 1] = pr * (l1 - kg * g1);
-#pragma unroll
-            for (int cc = 2; cc < N; ++cc) outblk[r * N + cc] = (r >= cc) ? pr * B[r][cc] : (T)0;
-            const T mo = pr * (mp[r] - kg * z);
-            a.mean_out[(long long)r * g.d + co.flat] = mo;
-            if (r == 0) new_m0 = mo;
+        // (4) stream the updated blocks back
+        if (bulk_out) {
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+                bulk_s2g(a.sc_out + sc_off, my_sc, (uint32_t)(32 * NN * sizeof(T)));
+                bulk_commit();
+            }
+        } else {
+            __syncwarp();
+            const int total = cur.seg_len * NN;
+            for (int e = lane; e < total; e += 32) {
+                const int b = e / NN;
+                a.sc_out[sc_off + e] = my_sc[b * STRIDE + (e - b * NN)];
+            }
         }
-        const T ref = nanmax<T>(tabs<T>(raw0), tabs<T>(new_m0));   // ek1.py:249-251
-        if (a.err_out) a.err_out[co.flat] = err;
-        if (a.ref_out) a.ref_out[co.flat] = ref;
-        if (c.want_norm) {
-            const double ratio = ((double)c.dt * (double)err) / ((double)c.abstol + (double)c.reltol * (double)ref);
-            ratio_sq = ratio * ratio;                              // step.py:101-104
-        }
+        tile = next;
+        cur_bulk = next_bulk;
     }
 
-    // (3) stream the updated blocks back
-    if (bulk_out) {
-        fence_proxy_async();
-        __syncwarp();
-        if (lane == 0) {
-            bulk_s2g(a.sc_out + sc_off, my_sc, seg_bytes);
-            bulk_commit();
-        }
-    } else {
-        __syncwarp();
-        const int total = co.seg_len * NN;
-        for (int e = lane; e < total; e += 32) {
-            const int blk = e / NN;
-            a.sc_out[sc_off + e] = my_sc[blk * STRIDE + (e - blk * NN)];
-        }
-    }
-
-    if (c.want_norm) grid_sum(ratio_sq, s_red, a.partials, a.ticket, a.out_sum);
-    if (bulk_out && lane == 0) bulk_wait_read0();
+    if (c.want_norm) grid_sum(ratio_sq_acc, s_red, a.partials, a.ticket, a.out_sum);
+    if (lane == 0) bulk_wait_read0();
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -239,58 +320,77 @@ struct Ek0Args {
     double* partials;
     unsigned int* ticket;
     double* out_sum;
+    unsigned int num_tiles, tiles_x;
+    int reverse;             // walk the tiles backwards (sweep B re-reads what sweep A touched last: L2 reuse)
 };
 
-// sweep A: z = p1 mp[1] - f(p0 mp[0]);  sum z^2        ek0.py:166-172
-template <class IVP, typename T, int N>
-__global__ void __launch_bounds__(kThreads) ek0_sweep_a_kernel(const __grid_constant__ Ek0Args<T, N> a) {
+// Both sweeps: persistent CTAs, the loads of tile i+1 are in flight while tile i is computed.
+//   sweep A (kUpdate = false): z = p1 mp[1] - f(p0 mp[0]);  sum z^2                          ek0.py:166-172
+//   sweep B (kUpdate = true) : m_new = P (mp - K z); ref = |m_new[0]|; sum (dt err / tol)^2  ek0.py:132-140,181-184
+template <class IVP, typename T, int N, bool kUpdate>
+__global__ void __launch_bounds__(kThreads, 3) ek0_sweep_kernel(const __grid_constant__ Ek0Args<T, N> a) {
     using Shape = typename IVP::Shape;
     using L = SmemLayout<T, N>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double* s_red = reinterpret_cast<double*>(smem_raw + L::BAR_BYTES);
-    T* s_at = reinterpret_cast<T*>(smem_raw + L::BAR_BYTES + L::RED_BYTES);
-    const Coord co = tile_coord<Shape>(a.g);
-    T raw0, mp[N], fx, jac;
-    front_end<IVP, T, N>(a.g, a.c, a.mean_in, a.halo_lo, a.halo_hi, co, s_at, raw0, mp, fx, jac);
-    double zz = 0.0;
-    if (co.valid) {
-        const T z = a.c.p[1] * mp[1] - fx;
-        zz = (double)z * (double)z;
-    }
-    grid_sum(zz, s_red, a.partials, a.ticket, a.out_sum);
-}
+    T* s_at0 = reinterpret_cast<T*>(smem_raw + L::BAR_BYTES + L::RED_BYTES);
+    constexpr size_t AT_STRIDE = L::at_bytes(Shape::AT_ELEMS) / sizeof(T);
+    const Geo& g = a.g;
+    const Consts<T, N>& c = a.c;
 
-// sweep B: m_new = P (mp - K z); ref = |m_new[0]|; sum 1/(abstol + reltol ref)^2     ek0.py:132-140,181-184
-template <class IVP, typename T, int N>
-__global__ void __launch_bounds__(kThreads) ek0_sweep_b_kernel(const __grid_constant__ Ek0Args<T, N> a) {
-    using Shape = typename IVP::Shape;
-    using L = SmemLayout<T, N>;
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    double* s_red = reinterpret_cast<double*>(smem_raw + L::BAR_BYTES);
-    T* s_at = reinterpret_cast<T*>(smem_raw + L::BAR_BYTES + L::RED_BYTES);
-    const Coord co = tile_coord<Shape>(a.g);
-    T raw0, mp[N], fx, jac;
-    front_end<IVP, T, N>(a.g, a.c, a.mean_in, a.halo_lo, a.halo_hi, co, s_at, raw0, mp, fx, jac);
-    double acc = 0.0;
-    if (co.valid) {
-        const T z = a.c.p[1] * mp[1] - fx;
-        T m0 = (T)0;
+    T K[N];
+    if (kUpdate) {
 #pragma unroll
-        for (int r = 0; r < N; ++r) {
-            const T mo = a.c.p[r] * (mp[r] - a.mid->K[r] * z);
-            a.mean_out[(long long)r * a.g.d + co.flat] = mo;
-            if (r == 0) m0 = mo;
+        for (int r = 0; r < N; ++r) K[r] = a.mid->K[r];
+    }
+    auto tile_of = [&](unsigned i) { return a.reverse ? (a.num_tiles - 1u - i) : i; };
+
+    unsigned i = blockIdx.x;
+    double acc = 0.0;
+    Coord co{};
+    FrontRegs<IVP, T, N> fr;
+    if (i < a.num_tiles) {
+        co = tile_coord<Shape>(g, tile_of(i), a.tiles_x);
+        front_load<IVP, T, N>(g, c, a.mean_in, a.halo_lo, a.halo_hi, co, fr);
+    }
+    for (unsigned it = 0; i < a.num_tiles; ++it) {
+        T mp[N], fx, jac;
+        front_eval<IVP, T, N>(g, c, co, fr, s_at0 + (it & 1) * AT_STRIDE, mp, fx, jac);
+        const Coord cur = co;
+        i += gridDim.x;
+        if (i < a.num_tiles) {
+            co = tile_coord<Shape>(g, tile_of(i), a.tiles_x);
+            front_load<IVP, T, N>(g, c, a.mean_in, a.halo_lo, a.halo_hi, co, fr);
         }
-        const T ref = tabs<T>(m0);
-        if (a.ref_out) a.ref_out[co.flat] = ref;
-        if (a.c.want_norm) {
-            const double tol = (double)a.c.abstol + (double)a.c.reltol * (double)ref;
-            acc = 1.0 / (tol * tol);
+        if (cur.valid) {
+            const T z = c.p[1] * mp[1] - fx;
+            if (!kUpdate) {
+                acc += (double)z * (double)z;
+            } else {
+                T m0 = (T)0;
+                T* mo_ptr = a.mean_out + cur.flat;
+#pragma unroll
+                for (int r = 0; r < N; ++r) {
+                    const T mo = c.p[r] * (mp[r] - K[r] * z);
+                    *mo_ptr = mo;
+                    mo_ptr += g.d;
+                    if (r == 0) m0 = mo;
+                }
+                const T ref = tabs<T>(m0);
+                if (a.ref_out) a.ref_out[cur.flat] = ref;
+                if (c.want_norm) {
+                    const double tol = (double)c.abstol + (double)c.reltol * (double)ref;
+                    acc += 1.0 / (tol * tol);
+                }
+            }
         }
     }
-    // sum_i (dt err / tol_i)^2 = (dt err)^2 sum_i 1 / tol_i^2     step.py:101-104 with a scalar error estimate
-    if (a.c.want_norm)
-        grid_sum(acc, s_red, a.partials, a.ticket, a.out_sum, (double)a.c.dt * (double)a.c.dt, &a.mid->err);
+    if (!kUpdate) {
+        grid_sum(acc, s_red, a.partials, a.ticket, a.out_sum);
+    } else if (c.want_norm) {
+        // sum_i (dt err / tol_i)^2 = (dt err)^2 sum_i 1 / tol_i^2     step.py:101-104 with a scalar error estimate
+        grid_sum(acc, s_red, a.partials, a.ticket, a.out_sum, (double)c.dt * (double)c.dt, &a.mid->err);
+    }
 }
 
 // mid: calibration, ONE stacked QR, gain, factor update; a single thread in fp64.   ek0.py:123-140,175,182
@@ -381,21 +481,24 @@ struct EvalArgs {
     T* jd;
     const T* halo_lo;
     const T* halo_hi;
+    unsigned int tiles_x;
 };
 
 template <class IVP, typename T>
 __global__ void __launch_bounds__(kThreads) eval_f_kernel(const __grid_constant__ EvalArgs<T> a) {
     using Shape = typename IVP::Shape;
     __shared__ T s_at[Shape::AT_ELEMS];
-    const Coord co = tile_coord<Shape>(a.g);
+    const Coord co = tile_coord<Shape>(a.g, blockIdx.x, a.tiles_x);
     PlainAt<T> at{a.y};
     const T own = co.valid ? __ldg(a.y + co.flat) : (T)0;
-    const Ext<T> ext = IVP::prefetch(a.g, co, at, a.halo_lo, a.halo_hi);
+    const Plan<T, IVP::NEXT> pl = IVP::plan(a.g, co);
+    T ext[IVP::NEXT > 0 ? IVP::NEXT : 1];
+    fetch_ext<T, IVP::NEXT>(pl, at, a.halo_lo, a.halo_hi, ext);
     s_at[at_index<Shape>(co.field, co.tr, co.tcol)] = own;
     __syncthreads();
     if (co.valid) {
         T fx, jac;
-        IVP::eval(a.g, co, s_at, ext, own, fx, jac);
+        IVP::eval(a.g, co, s_at, own, ext, pl, fx, jac);
         a.fy[co.flat] = fx;
         if (a.jd) a.jd[co.flat] = jac;
     }

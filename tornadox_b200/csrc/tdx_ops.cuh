@@ -64,6 +64,21 @@ inline Consts<T, N> make_consts(const StepHost& h) {
         if (e__ != cudaSuccess) return (int)e__;  \
     } while (0)
 
+// grid of a persistent kernel: as many CTAs as fit on the device at once, at most one per tile
+template <class Kern>
+inline cudaError_t persistent_grid(Kern kern, size_t smem, long long tiles, unsigned& grid) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int dev = 0, sms = 0, per_sm = 0;
+    if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
+    if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
+    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, smem)) != cudaSuccess) return e;
+    if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+    const long long resident = (long long)sms * per_sm;
+    grid = (unsigned)(tiles < resident ? tiles : resident);
+    return cudaSuccess;
+}
+
 // dispatch a templated launch body over the vector field
 #define TDX_SWITCH_IVP(kind, T, ...)                                             \
     switch (kind) {                                                              \
@@ -97,11 +112,13 @@ struct Launch {
         a.out_sum = out_sum;
         TDX_SWITCH_IVP(g.kind, T, {
             using Shape = typename IVP::Shape;
-            const size_t smem = L::total(Shape::AT_ELEMS, true);
+            const size_t smem = DekSmem<T, N>::total(Shape::AT_ELEMS);
             auto kern = dek1_kernel<IVP, T, N>;
-            TDX_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            const long long grid = num_tiles<Shape>(g.rows, g.cols);
-            kern<<<(unsigned)grid, kThreads, smem, st>>>(a);
+            unsigned grid = 0;
+            TDX_CUDA_TRY(persistent_grid(kern, smem, num_tiles<Shape>(g.rows, g.cols), grid));
+            a.num_tiles = (unsigned)num_tiles<Shape>(g.rows, g.cols);
+            a.tiles_x = (unsigned)((g.cols + Shape::TC - 1) / Shape::TC);
+            kern<<<grid, kThreads, smem, st>>>(a);
         })
         return (int)cudaGetLastError();
     }
@@ -123,28 +140,32 @@ struct Launch {
         return a;
     }
 
+    template <bool kUpdate>
+    static int ek0_sweep(const Geo& g, Ek0Args<T, N>& a, cudaStream_t st) {
+        TDX_SWITCH_IVP(g.kind, T, {
+            using Shape = typename IVP::Shape;
+            const size_t smem = L::BAR_BYTES + L::RED_BYTES + 2 * L::at_bytes(Shape::AT_ELEMS);
+            auto kern = ek0_sweep_kernel<IVP, T, N, kUpdate>;
+            unsigned grid = 0;
+            TDX_CUDA_TRY(persistent_grid(kern, smem, num_tiles<Shape>(g.rows, g.cols), grid));
+            a.num_tiles = (unsigned)num_tiles<Shape>(g.rows, g.cols);
+            a.tiles_x = (unsigned)((g.cols + Shape::TC - 1) / Shape::TC);
+            a.reverse = kUpdate ? 1 : 0;
+            kern<<<grid, kThreads, smem, st>>>(a);
+        })
+        return (int)cudaGetLastError();
+    }
+
     static int ek0_a(const Geo& g, const StepHost& h, const void* mean_in, const void* halo_lo, const void* halo_hi,
                      const Workspace& ws, double* out_sum, cudaStream_t st) {
         Ek0Args<T, N> a = ek0_args(g, h, mean_in, nullptr, nullptr, halo_lo, halo_hi, ws, out_sum);
-        TDX_SWITCH_IVP(g.kind, T, {
-            using Shape = typename IVP::Shape;
-            const size_t smem = L::total(Shape::AT_ELEMS, false);
-            const long long grid = num_tiles<Shape>(g.rows, g.cols);
-            ek0_sweep_a_kernel<IVP, T, N><<<(unsigned)grid, kThreads, smem, st>>>(a);
-        })
-        return (int)cudaGetLastError();
+        return ek0_sweep<false>(g, a, st);
     }
 
     static int ek0_b(const Geo& g, const StepHost& h, const void* mean_in, void* mean_out, void* ref_out,
                      const void* halo_lo, const void* halo_hi, const Workspace& ws, double* out_sum, cudaStream_t st) {
         Ek0Args<T, N> a = ek0_args(g, h, mean_in, mean_out, ref_out, halo_lo, halo_hi, ws, out_sum);
-        TDX_SWITCH_IVP(g.kind, T, {
-            using Shape = typename IVP::Shape;
-            const size_t smem = L::total(Shape::AT_ELEMS, false);
-            const long long grid = num_tiles<Shape>(g.rows, g.cols);
-            ek0_sweep_b_kernel<IVP, T, N><<<(unsigned)grid, kThreads, smem, st>>>(a);
-        })
-        return (int)cudaGetLastError();
+        return ek0_sweep<true>(g, a, st);
     }
 
     static int ek0_mid(const StepHost& h, const void* Cl_in, const double* z_sq_sum, double d_global, void* Cl_out,
