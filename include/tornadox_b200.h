@@ -97,6 +97,12 @@ int tdx_halo_sizes(const tdx_ctx* ctx, int64_t* lo, int64_t* hi);
 
 /* Prior constants A (n,n) and Ql (n,n) the kernels use (iwp.py:19-37), written to HOST buffers. */
 int tdx_prior(int nu, double* A_out, double* Ql_out);
+/* Replace the context's Ql (row-major (n,n), lower triangular, HOST buffer) by the caller's own factor, e.g. the
+ * LAPACK dpotrf result the reference computes in iwp.py:37.  The built-in factor is computed in extended
+ * precision; dpotrf in fp64 differs from it by cond(Q) * eps (1e-11 relative at nu = 5), which matters when
+ * bit-level agreement with a particular host's reference run is wanted.  Call after tdx_set_problem. */
+int tdx_set_diffusion_sqrt(tdx_ctx* ctx, const double* Ql);
+
 /* Nordsieck preconditioner vectors (iwp.py:65-73), HOST buffers of n doubles each. */
 int tdx_nordsieck(int nu, double dt, double* p_out, double* p_inv_out);
 

@@ -63,3 +63,47 @@ def rel_err(a, b):
 def assert_close(a, b, rtol, what):
     e = rel_err(a, b)
     assert e <= rtol, f"{what}: relative error {e:.3e} > {rtol:.1e}"
+
+
+# ---- golden vectors generated from the reference's own sources (oracle/make_golden.py) ----------------
+import functools
+import pathlib
+
+GOLDEN_PATH = pathlib.Path(__file__).resolve().parent / "golden" / "reference_vectors.npz"
+
+
+@functools.lru_cache(maxsize=1)
+def golden():
+    with np.load(GOLDEN_PATH) as data:
+        return {k: data[k] for k in data.files}
+
+
+def oracle_problem(name):
+    """The oracle problem + series vector field matching the golden problem ``name`` (oracle/make_golden.py)."""
+    g = golden()
+    y0 = g[f"ivp/{name}/y0"]
+    if name == "vanderpol":
+        return oproblems.vanderpol(t0=0.0, tmax=1.0, stiffness_constant=1.0), odriver.series_vanderpol(1.0)
+    if name == "lorenz96":
+        return oproblems.lorenz96(t0=0.0, tmax=0.5, num_variables=10, forcing=8.0), odriver.series_lorenz96(8.0)
+    if name == "brusselator":
+        return oproblems.brusselator(N=7, t0=0.0, tmax=0.05), odriver.series_brusselator(7)
+    if name == "fhn_2d":
+        return oproblems.fhn_2d(t0=0.0, tmax=0.05, y0=y0, dx=0.2), odriver.series_fhn_2d(5, 5, 0.2)
+    raise KeyError(name)
+
+
+def product_problem(name):
+    """The tornadox_b200 ivp matching the golden problem ``name``."""
+    from tornadox_b200 import ivp as pivp
+
+    y0 = golden()[f"ivp/{name}/y0"]
+    if name == "vanderpol":
+        return pivp.vanderpol(t0=0.0, tmax=1.0, stiffness_constant=1.0)
+    if name == "lorenz96":
+        return pivp.lorenz96(t0=0.0, tmax=0.5, num_variables=10, forcing=8.0)
+    if name == "brusselator":
+        return pivp.brusselator(N=7, t0=0.0, tmax=0.05)
+    if name == "fhn_2d":
+        return pivp.fhn_2d(t0=0.0, tmax=0.05, y0=y0, dx=0.2)
+    raise KeyError(name)

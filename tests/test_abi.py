@@ -1,0 +1,99 @@
+"""CPU: the C-ABI shared library loads, exports every symbol include/tornadox_b200.h declares, and its
+host-only entry points agree with the reference-derived golden vectors.  No compute calls (no GPU here)."""
+
+import ctypes
+import pathlib
+import re
+
+import numpy as np
+import pytest
+
+from helpers import assert_close, golden
+
+ROOT = pathlib.Path(__file__).resolve().parent.parent
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from tornadox_b200 import _lib, build
+
+    build.build()
+    return _lib.load()
+
+
+def declared_symbols():
+    text = (ROOT / "include" / "tornadox_b200.h").read_text()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(tdx_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_every_declared_symbol_is_exported(lib):
+    from tornadox_b200 import _lib
+
+    names = declared_symbols()
+    assert len(names) >= 15
+    for name in names:
+        assert hasattr(lib, name), f"{name} declared in the header but not exported"
+    assert set(names) == set(_lib.EXPORTED_SYMBOLS), "ctypes binding and header disagree"
+
+
+def test_abi_version(lib):
+    assert lib.tdx_abi_version() == 1
+
+
+def test_struct_layouts_match_header():
+    from tornadox_b200 import _lib
+
+    assert ctypes.sizeof(_lib.ProblemDesc) == 4 + 4 + 4 * 8 + 4 + 4 + 8 * 8   # incl. 4 B padding before params
+    assert ctypes.sizeof(_lib.StepArgs) == 4 * 8 + 4 + 4
+
+
+@pytest.mark.parametrize("nu", [1, 2, 3, 4, 5])
+def test_prior_and_preconditioner_match_reference(lib, nu):
+    from tornadox_b200 import _lib
+
+    g = golden()
+    A, Ql = _lib.prior(nu)
+    np.testing.assert_array_equal(A, g[f"prior/nu{nu}/A"])
+    # built-in factor (extended precision) vs the reference's fp64 LAPACK dpotrf: cond(Q) * eps apart
+    assert_close(Ql, g[f"prior/nu{nu}/Ql"], 1e-12 if nu < 5 else 1e-10, "Ql")
+    # the factor the Python host hands to the library is the reference's, bit for bit
+    np.testing.assert_array_equal(_lib.lapack_diffusion_sqrt(nu), g[f"prior/nu{nu}/Ql"])
+    for dt in (0.1, 1e-3, 2.5):
+        p, pinv = _lib.nordsieck(nu, dt)
+        assert_close(p, g[f"prior/nu{nu}/p/{dt}"], 1e-14, "p")
+        assert_close(pinv, g[f"prior/nu{nu}/pinv/{dt}"], 1e-14, "p_inv")
+
+
+def test_invalid_arguments_are_reported(lib):
+    from tornadox_b200 import _lib
+
+    A = np.zeros((2, 2))
+    pd = ctypes.POINTER(ctypes.c_double)
+    assert lib.tdx_prior(0, A.ctypes.data_as(pd), A.ctypes.data_as(pd)) == 1
+    assert b"nu" in lib.tdx_last_error()
+    with pytest.raises(ValueError):
+        _lib.prior(17)
+
+
+def test_no_cpu_fallback(lib):
+    """Without a CUDA device the context cannot be created and the Python engine refuses to run."""
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    handle = ctypes.c_void_p()
+    rc = lib.tdx_create(ctypes.byref(handle), 0, 0)
+    assert rc == 3 and b"no CPU fallback" in lib.tdx_last_error()
+    from tornadox_b200 import _lib, ivp
+    from tornadox_b200.engine import StepEngine
+
+    with pytest.raises(_lib.TornadoxB200Error):
+        StepEngine(ivp.vanderpol().spec, 4)
+
+
+def test_product_does_not_import_the_oracle():
+    """The oracle is test infrastructure: nothing under tornadox_b200/ may reference it."""
+    for path in (ROOT / "tornadox_b200").rglob("*.py"):
+        text = path.read_text()
+        assert "oracle" not in re.sub(r"#.*", "", text), f"{path} mentions the oracle"

@@ -1,0 +1,153 @@
+"""GPU: the CUDA path (public solver API -> C ABI -> kernels) against outputs of the UNMODIFIED reference
+sources (tests/golden/reference_vectors.npz, see oracle/make_golden.py)."""
+
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import FP32_RTOL, FP64_RTOL, assert_close, golden, product_problem
+
+pytestmark = pytest.mark.gpu
+
+NAMES = ["vanderpol", "lorenz96", "brusselator", "fhn_2d"]
+
+
+def _np(x):
+    return x.detach().cpu().numpy() if isinstance(x, torch.Tensor) else np.asarray(x)
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_vector_fields(cuda_device, name):
+    g = golden()
+    p = product_problem(name)
+    for tag in ("y0", "y1"):
+        y = torch.as_tensor(g[f"ivp/{name}/{tag}"], device=cuda_device)
+        assert_close(_np(p.f(0.0, y)), g[f"ivp/{name}/f/{tag}"], 1e-13, "f")
+        assert_close(_np(p.df_diagonal(0.0, y)), g[f"ivp/{name}/df_diagonal/{tag}"], 1e-13, "df_diagonal")
+
+
+@pytest.mark.parametrize("name", NAMES)
+@pytest.mark.parametrize("nu", [2, 3, 4])
+def test_taylor_mode_init(cuda_device, name, nu):
+    from tornadox_b200 import init
+
+    p = product_problem(name)
+    m0 = init.TaylorMode.taylor_mode(p.f, p.y0, p.t0, nu)
+    assert m0.is_cuda
+    assert_close(_np(m0), golden()[f"init/{name}/nu{nu}/taylor"], 1e-13, "taylor-mode derivatives")
+
+
+@pytest.mark.parametrize("name", NAMES)
+@pytest.mark.parametrize("nu", [2, 3, 4])
+@pytest.mark.parametrize("solver", ["dek1", "ek0", "dek0"])
+def test_attempt_step_sequences(cuda_device, name, nu, solver):
+    from tornadox_b200 import ek0, ek1, step
+
+    g = golden()
+    p = product_problem(name)
+    cls = {"dek1": ek1.DiagonalEK1, "ek0": ek0.KroneckerEK0, "dek0": ek0.DiagonalEK0}[solver]
+    sol = cls(num_derivatives=nu, steprule=step.AdaptiveSteps())
+    state = sol.initialize(*p)
+    d = p.y0.shape[0]
+    for i, dt in enumerate(g[f"steps/{name}/dts"]):
+        state, info = sol.attempt_step(state, float(dt), *p)
+        key = f"steps/{name}/nu{nu}/{solver}/{i}"
+        assert_close(state.t, g[key + "/t"], 1e-15, "t")
+        assert_close(_np(state.y.mean), g[key + "/mean"], FP64_RTOL, "mean")
+        fac = state.y.cov_sqrtm_2 if solver == "ek0" else state.y.cov_sqrtm
+        assert_close(_np(fac), g[key + "/cov_sqrtm"], FP64_RTOL, "cov_sqrtm")
+        assert_close(_np(state.error_estimate), g[key + "/error_estimate"], FP64_RTOL, "error_estimate")
+        assert_close(_np(state.reference_state), g[key + "/reference_state"], FP64_RTOL, "reference_state")
+        norm = math.sqrt(float(state.scaled_error_norm_sq_sum) / d)
+        assert_close(norm, g[key + "/scaled_error_norm"], FP64_RTOL, "scaled error norm")
+        assert info["num_f_evaluations"] == 1
+        assert info.get("num_df_diagonal_evaluations", 0) == (1 if solver == "dek1" else 0)
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_attempt_step_from_dense_state(cuda_device, name):
+    from tornadox_b200 import ek0, ek1, odefilter, rv
+
+    g = golden()
+    p = product_problem(name)
+    nu = 4
+    t = lambda k: torch.as_tensor(g[f"dense/{name}/{k}"], device=cuda_device)
+    dt = float(g[f"dense/{name}/dt"])
+    sol = ek1.DiagonalEK1(num_derivatives=nu)
+    sol.initialize(*p)
+    st = odefilter.ODEFilterState(0.3, rv.BatchedMultivariateNormal(t("mean"), t("blocks")), None, None)
+    new, _ = sol.attempt_step(st, dt, *p)
+    assert_close(_np(new.y.mean), g[f"dense/{name}/dek1/mean"], FP64_RTOL, "dek1 mean")
+    assert_close(_np(new.y.cov_sqrtm), g[f"dense/{name}/dek1/cov_sqrtm"], FP64_RTOL, "dek1 cov_sqrtm")
+    assert_close(_np(new.error_estimate), g[f"dense/{name}/dek1/error_estimate"], FP64_RTOL, "dek1 error")
+    assert_close(_np(new.reference_state), g[f"dense/{name}/dek1/reference_state"], FP64_RTOL, "dek1 reference")
+    sol0 = ek0.KroneckerEK0(num_derivatives=nu)
+    sol0.initialize(*p)
+    d = p.y0.shape[0]
+    st0 = odefilter.ODEFilterState(0.3, rv.LeftIsotropicMatrixNormal(t("mean"), d, t("single")), None, None)
+    new0, _ = sol0.attempt_step(st0, dt, *p)
+    assert_close(_np(new0.y.mean), g[f"dense/{name}/ek0/mean"], FP64_RTOL, "ek0 mean")
+    assert_close(_np(new0.y.cov_sqrtm_2), g[f"dense/{name}/ek0/cov_sqrtm"], FP64_RTOL, "ek0 cov_sqrtm_2")
+    assert_close(_np(new0.error_estimate), g[f"dense/{name}/ek0/error_estimate"], FP64_RTOL, "ek0 error")
+    assert_close(_np(new0.reference_state), g[f"dense/{name}/ek0/reference_state"], FP64_RTOL, "ek0 reference")
+
+
+@pytest.mark.parametrize("name", NAMES)
+@pytest.mark.parametrize("solver", ["dek1", "ek0"])
+def test_adaptive_solves_same_accepted_steps(cuda_device, name, solver):
+    """Identical accepted-step sequences and counters as the reference's own solve (north_star)."""
+    from tornadox_b200 import ek0, ek1, step
+
+    g = golden()
+    p = product_problem(name)
+    cls = ek1.DiagonalEK1 if solver == "dek1" else ek0.KroneckerEK0
+    sol = cls(num_derivatives=4, steprule=step.AdaptiveSteps(abstol=1e-4, reltol=1e-2))
+    ts, last, info = [], None, None
+    for state, info in sol.solution_generator(p):
+        ts.append(state.t)
+        last = state
+    ref_ts = g[f"solve/{name}/{solver}/ts"]
+    assert len(ts) == len(ref_ts), "different number of accepted steps"
+    np.testing.assert_allclose(ts, ref_ts, rtol=1e-9, atol=0)
+    counters = [info[k] for k in ("num_f_evaluations", "num_df_evaluations", "num_df_diagonal_evaluations",
+                                  "num_steps", "num_attempted_steps")]
+    np.testing.assert_array_equal(counters, g[f"solve/{name}/{solver}/info"])
+    assert_close(_np(last.y.mean), g[f"solve/{name}/{solver}/final_mean"], 1e-7, "final mean")
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_constant_steps_counters(cuda_device, name):
+    """ConstantSteps: one attempt per step, five steps (tests/test_ek1.py:65-78 of the reference)."""
+    from tornadox_b200 import ek1, step
+
+    g = golden()
+    p = product_problem(name)
+    dt = float(g[f"dense/{name}/dt"])
+    p5 = p._replace(tmax=p.t0 + 5.0 * dt - 1e-12 * dt)
+    sol = ek1.DiagonalEK1(num_derivatives=3, steprule=step.ConstantSteps(dt))
+    state, info = sol.simulate_final_state(p5)
+    assert info["num_steps"] == int(g[f"solve/{name}/dek1_const/num_steps"]) == info["num_attempted_steps"]
+    assert_close(state.t, g[f"solve/{name}/dek1_const/t"], 1e-14, "t")
+    assert_close(_np(state.y.mean), g[f"solve/{name}/dek1_const/final_mean"], 1e-9, "final mean")
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_fp32_attempt_within_1e5(cuda_device, name):
+    """fp32 kernels against the x64 reference outputs: 1e-5 where the problem's conditioning allows it."""
+    from tornadox_b200 import ek1, odefilter, rv
+
+    g = golden()
+    p = product_problem(name)
+    t32 = lambda k: torch.as_tensor(g[f"dense/{name}/{k}"], device=cuda_device, dtype=torch.float32)
+    dt = float(g[f"dense/{name}/dt"])
+    sol = ek1.DiagonalEK1(num_derivatives=4, dtype=torch.float32)
+    sol.initialize(*p)
+    st = odefilter.ODEFilterState(0.3, rv.BatchedMultivariateNormal(t32("mean"), t32("blocks")), None, None)
+    new, _ = sol.attempt_step(st, dt, *p)
+    assert new.y.mean.dtype == torch.float32
+    assert_close(_np(new.y.mean), g[f"dense/{name}/dek1/mean"], FP32_RTOL, "fp32 mean")
+    S = _np(new.y.cov_sqrtm).astype(np.float64)
+    R = g[f"dense/{name}/dek1/cov_sqrtm"]
+    assert_close(S @ S.transpose(0, 2, 1), R @ R.transpose(0, 2, 1), 5 * FP32_RTOL, "fp32 covariance")

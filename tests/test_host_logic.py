@@ -1,0 +1,185 @@
+"""CPU: host-side logic of the product (step rules, time stopper, problem factories, Taylor-mode series
+algebra, state containers) and the reference's known-answer tests ported onto the oracle."""
+
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import assert_close, golden
+from oracle.ref_np import driver as odriver
+from oracle.ref_np import filters as ofilters
+from oracle.ref_np import prior as oprior
+from oracle.ref_np import problems as oproblems
+
+
+# ---- reference known-answer tests, on the oracle -------------------------------------------------------
+def test_ibm2_closed_form_at_dt_01():
+    """tests/test_iwp.py:19-47 of the reference: closed-form IBM(2) transition and process noise at dt = 0.1."""
+    dt, nu = 0.1, 2
+    A, Ql = oprior.dense_transition_no_precon(nu, 1, dt)
+    ah_22_ibm = np.array([[1.0, 0.1, 0.005], [0.0, 1.0, 0.1], [0.0, 0.0, 1.0]])
+    np.testing.assert_allclose(A, ah_22_ibm, rtol=1e-12, atol=1e-15)
+    Q = Ql @ Ql.T
+    expected_Q = np.array([[dt**5 / 20, dt**4 / 8, dt**3 / 6], [dt**4 / 8, dt**3 / 3, dt**2 / 2],
+                           [dt**3 / 6, dt**2 / 2, dt]])
+    np.testing.assert_allclose(Q, expected_Q, rtol=1e-10)
+
+
+def test_preconditioner_identities():
+    """tests/test_iwp.py:50-93: P A_pre P^-1 equals the plain transition and P P^-1 = I."""
+    for nu in (1, 2, 4):
+        for dt in (0.1, 0.7):
+            P, PI = oprior.nordsieck_diag(nu, dt)
+            np.testing.assert_allclose(P @ PI, np.eye(nu + 1), rtol=1e-13, atol=1e-13)
+            A = P @ oprior.transition_1d(nu) @ PI
+            expected = np.array([[dt ** (j - i) / math.factorial(j - i) if j >= i else 0.0 for j in range(nu + 1)]
+                                 for i in range(nu + 1)])
+            np.testing.assert_allclose(A, expected, rtol=1e-12, atol=1e-14)
+
+
+def test_propagate_cholesky_factor_identity():
+    """tests/test_sqrt.py:39-48: L L^T = S1 S1^T + S2 S2^T and L is lower triangular (also batched)."""
+    rng = np.random.default_rng(0)
+    S1, S2 = rng.standard_normal((4, 4)), rng.standard_normal((4, 4))
+    L = oprior.propagate_cholesky(S1, S2)
+    np.testing.assert_allclose(L @ L.T, S1 @ S1.T + S2 @ S2.T, rtol=1e-12)
+    np.testing.assert_allclose(L, np.tril(L))
+    B1, B2 = rng.standard_normal((3, 4, 4)), rng.standard_normal((3, 4, 4))
+    Lb = oprior.propagate_cholesky_batched(B1, B2)
+    for i in range(3):
+        np.testing.assert_allclose(Lb[i], oprior.propagate_cholesky(B1[i], B2[i]), rtol=1e-13, atol=1e-13)
+
+
+def test_kronecker_ek0_equals_dense_reference_ek0():
+    """tests/test_ek0.py:246-263: one step dt = 0.12345 on vanderpol(mu=1), nu = 2: Kronecker == dense."""
+    nu, dt = 2, 0.12345
+    prob = oproblems.vanderpol(t0=0.0, tmax=10.0, stiffness_constant=1.0)
+    m0, c0 = odriver.taylor_init(odriver.series_vanderpol(1.0), prob.y0, 0.0, nu)
+    kron, _ = ofilters.kronecker_ek0_attempt(ofilters.kronecker_ek0_initial_state(m0, c0, 0.0), dt, prob.f, nu)
+    dense, _ = ofilters.reference_ek0_attempt(ofilters.dense_initial_state(m0, c0, 0.0), dt, prob.f, nu)
+    np.testing.assert_allclose(kron.mean, dense.mean, rtol=1e-10, atol=1e-12)
+    d = 2
+    kron_cov = np.kron(np.eye(d), kron.cov_sqrtm @ kron.cov_sqrtm.T)
+    np.testing.assert_allclose(kron_cov, dense.cov_sqrtm @ dense.cov_sqrtm.T, rtol=1e-8, atol=1e-12)
+    np.testing.assert_allclose(kron.error_estimate, dense.error_estimate, rtol=1e-10)
+    np.testing.assert_allclose(kron.reference_state, dense.reference_state, rtol=1e-10)
+
+
+def test_diagonal_ek1_reference_state_equals_dense_reference_ek1():
+    """tests/test_ek1.py:239-247: with a diagonalised Jacobian, reference_state (and the first-step mean) agree."""
+    nu = 3
+    prob = oproblems.vanderpol(t0=0.0, tmax=10.0, stiffness_constant=1.0)
+    m0, c0 = odriver.taylor_init(odriver.series_vanderpol(1.0), prob.y0, 0.0, nu)
+    for dt in (0.12121, 12.345):
+        diag, _ = ofilters.diagonal_ek1_attempt(ofilters.batched_initial_state(m0, c0, 0.0), dt, prob.f,
+                                                prob.df_diagonal, nu)
+        df_diag_only = lambda t, y: np.diag(prob.df_diagonal(t, y))
+        dense, _ = ofilters.reference_ek1_attempt(ofilters.dense_initial_state(m0, c0, 0.0), dt, prob.f, df_diag_only, nu)
+        np.testing.assert_allclose(diag.reference_state, dense.reference_state, rtol=1e-9)
+        np.testing.assert_allclose(diag.mean, dense.mean, rtol=1e-8, atol=1e-10)
+
+
+def test_taylor_mode_threebody_literals():
+    """tests/test_init.py:45-148 of the reference (first derivatives of the restricted three-body problem)."""
+    y0 = np.array([0.994, 0, 0, -2.00158510637908252240537862224])
+    m = odriver.taylor_mode(odriver.series_threebody(), y0, 0.0, 4)
+    expected_col0 = [0.994, 0.0, -315.5430234888826712, 0.0, 6.390281114012432978e07]
+    expected_col1 = [0.0, -2.001585106379082379, 0.0, 99972.09449511380974, 0.0]
+    np.testing.assert_allclose(m[:, 0], expected_col0, rtol=1e-12, atol=1e-9)
+    np.testing.assert_allclose(m[:, 1], expected_col1, rtol=1e-12, atol=1e-9)
+
+
+def test_df_diagonal_equals_dense_jacobian_diagonal():
+    """tests/test_ivp.py:60-64, extended to an fhn grid with edge AND interior nodes (5 x 5)."""
+    rng = np.random.default_rng(3)
+    probs = [oproblems.vanderpol(), oproblems.brusselator(N=6), oproblems.lorenz96(num_variables=9),
+             oproblems.fhn_2d(dx=0.2, y0=rng.uniform(size=50))]
+    for prob in probs:
+        y = prob.y0 + 0.1 * rng.standard_normal(prob.y0.shape)
+        np.testing.assert_allclose(prob.df_diagonal(0.0, y), np.diag(prob.df(0.0, y)), rtol=1e-11, atol=1e-11)
+        eps = 1e-6
+        J = np.stack([(prob.f(0.0, y + eps * e) - prob.f(0.0, y - eps * e)) / (2 * eps) for e in np.eye(y.size)], axis=1)
+        np.testing.assert_allclose(prob.df(0.0, y), J, rtol=1e-5, atol=1e-4)
+
+
+# ---- product host logic ---------------------------------------------------------------------------------
+def test_step_rules_match_reference_values():
+    from tornadox_b200 import step
+
+    g = golden()
+    rule = step.AdaptiveSteps(abstol=1e-3, reltol=1e-1)
+    scaled = rule.scale_error_estimate(torch.as_tensor(g["step/err"]), torch.as_tensor(g["step/ref"]))
+    assert_close(scaled, g["step/scaled"], 1e-14, "scale_error_estimate")
+    sug = [rule.suggest(0.1, e, local_convergence_rate=5) for e in (1e-8, 0.3, 1.0, 7.0, 1e9)]
+    assert_close(sug, g["step/suggest"], 1e-15, "suggest")
+    assert rule.is_accepted(0.99) and not rule.is_accepted(1.0) and not rule.is_accepted(1.01)   # step.py:90-91
+    with pytest.raises(ValueError):
+        rule.suggest(0.1, 0.5)
+    with pytest.raises(ValueError):
+        rule.scale_error_estimate(torch.zeros(3), torch.zeros(4))
+    const = step.ConstantSteps(0.25)
+    assert const.suggest(1.0, 3.0) == 0.25 and const.is_accepted(123.0) is True
+    assert const.scale_error_estimate(torch.zeros(2), torch.zeros(2)) is None
+    assert const.first_dt(None, 0, 1, None, None, None) == 0.25
+    assert step.norm_from_sq_sum(8.0, 2) == 2.0
+
+
+def test_time_stopper():
+    from tornadox_b200.odefilter import _TimeStopper
+
+    ts = _TimeStopper([0.5, 1.0])
+    assert ts.adjust_dt_to_time_stops(0.0, 0.3) == 0.3
+    assert ts.adjust_dt_to_time_stops(0.3, 0.3) == pytest.approx(0.2)
+    assert ts.adjust_dt_to_time_stops(0.5, 0.7) == pytest.approx(0.5)
+    assert ts.adjust_dt_to_time_stops(1.0, 0.7) == 0.7
+
+
+def test_problem_factories_and_specs():
+    from tornadox_b200 import _lib, ivp
+
+    p = ivp.fhn_2d(dx=0.25, y0=np.zeros(32))
+    assert p.spec.kind == _lib.TDX_IVP_FHN2D and (p.spec.grid_rows, p.spec.grid_cols) == (4, 4)
+    assert p.dimension == 32 and p.t_span == (0.0, 20.0) and p.df is None
+    with pytest.raises(ValueError, match="quadratic spatial grids"):
+        ivp.fhn_2d(bbox=[[0.0, 0.0], [1.0, 2.0]], dx=0.1)
+    b = ivp.brusselator(N=5)
+    np.testing.assert_allclose(b.y0, oproblems.brusselator(N=5).y0)
+    lz = ivp.lorenz96(num_variables=7)
+    np.testing.assert_allclose(lz.y0, oproblems.lorenz96(num_variables=7).y0)
+    v = ivp.vanderpol()
+    assert v.spec.params == (10.0,) and v.tmax == 30
+    assert len(tuple(v)) == 6   # *ivp unpacking as in odefilter.py:109
+
+
+@pytest.mark.parametrize("name,size", [("vanderpol", 1), ("lorenz96", 9), ("brusselator", 6), ("fhn_2d", 5)])
+def test_taylor_mode_series_algebra_on_cpu_tensors(name, size):
+    """The product's Taylor-mode initialisation is plain tensor algebra: check it on CPU tensors vs the oracle."""
+    from helpers import make_pair
+    from tornadox_b200 import init
+
+    o, p, series_f = make_pair(name, size)
+    for nu in (1, 3, 4):
+        m0 = init.TaylorMode.taylor_mode(p.f, torch.as_tensor(o.y0), 0.0, nu)
+        ref = odriver.taylor_mode(series_f, o.y0, 0.0, nu)
+        assert_close(m0.numpy(), ref, 1e-13, "taylor mode")
+
+
+def test_untagged_vector_field_is_rejected():
+    from tornadox_b200 import init
+
+    with pytest.raises(ValueError, match="no CPU fallback"):
+        init.TaylorMode()(lambda t, y: y, None, np.ones(3), 0.0, 2)
+
+
+def test_rv_containers():
+    from tornadox_b200 import rv
+
+    S = torch.tril(torch.rand(3, 2, 2, dtype=torch.float64))
+    b = rv.BatchedMultivariateNormal(torch.zeros(2, 3), S)
+    assert torch.allclose(b.cov, S @ S.transpose(1, 2))
+    li = rv.LeftIsotropicMatrixNormal(torch.zeros(2, 3), 3, S[0])
+    assert li.dense_cov().shape == (6, 6)
+    assert torch.allclose(li.dense_cov(), torch.kron(torch.eye(3, dtype=torch.float64), S[0] @ S[0].T))
+    assert li.cov.shape == (3, 2, 2)

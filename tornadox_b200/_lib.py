@@ -19,7 +19,7 @@ TDX_IVP_VANDERPOL, TDX_IVP_LORENZ96, TDX_IVP_BRUSSELATOR, TDX_IVP_FHN2D = 0, 1, 
 
 EXPORTED_SYMBOLS = (
     "tdx_last_error", "tdx_abi_version", "tdx_create", "tdx_destroy", "tdx_set_problem", "tdx_local_dim",
-    "tdx_halo_sizes", "tdx_prior", "tdx_nordsieck", "tdx_eval_f", "tdx_pack_halo", "tdx_dek1_attempt_step",
+    "tdx_halo_sizes", "tdx_set_diffusion_sqrt", "tdx_prior", "tdx_nordsieck", "tdx_eval_f", "tdx_pack_halo", "tdx_dek1_attempt_step",
     "tdx_ek0_sweep_a", "tdx_ek0_mid", "tdx_ek0_sweep_b", "tdx_ek0_attempt_step", "tdx_launch_count",
 )
 
@@ -78,6 +78,7 @@ def load():
     lib.tdx_local_dim.argtypes = [vp]
     lib.tdx_halo_sizes.argtypes = [vp, ctypes.POINTER(i64), ctypes.POINTER(i64)]
     lib.tdx_prior.argtypes = [cint, pd, pd]
+    lib.tdx_set_diffusion_sqrt.argtypes = [vp, pd]
     lib.tdx_nordsieck.argtypes = [cint, dbl, pd, pd]
     lib.tdx_eval_f.argtypes = [vp, dbl, vp, vp, vp, vp, vp, vp]
     lib.tdx_pack_halo.argtypes = [vp, dbl, vp, vp, vp, vp]
@@ -116,6 +117,14 @@ def prior(nu):
     pd = ctypes.POINTER(ctypes.c_double)
     check(load().tdx_prior(nu, A.ctypes.data_as(pd), Ql.ctypes.data_as(pd)))
     return A, Ql
+
+
+def lapack_diffusion_sqrt(nu):
+    """Ql exactly as the reference computes it: LAPACK dpotrf of flip(Hilbert(n)) (iwp.py:36-37)."""
+    n = nu + 1
+    idx = np.arange(n)
+    Q = 1.0 / (2 * nu + 1 - idx[:, None] - idx[None, :])
+    return np.ascontiguousarray(np.linalg.cholesky(Q))
 
 
 def nordsieck(nu, dt):

@@ -294,6 +294,19 @@ int tdx_set_problem(tdx_ctx* ctx, const tdx_problem_desc* d) {
     return TDX_OK;
 }
 
+int tdx_set_diffusion_sqrt(tdx_ctx* ctx, const double* Ql) {
+    if (!ctx || !ctx->has_problem) return fail(TDX_ERR_INVALID, "tdx_set_diffusion_sqrt: no problem set");
+    if (!Ql) return fail(TDX_ERR_INVALID, "tdx_set_diffusion_sqrt: null factor");
+    for (int i = 0; i < ctx->n; ++i)
+        for (int j = 0; j < ctx->n; ++j) {
+            const double v = Ql[i * ctx->n + j];
+            if (!std::isfinite(v) || (j > i && v != 0.0))
+                return fail(TDX_ERR_INVALID, "tdx_set_diffusion_sqrt: factor must be finite and lower triangular");
+            if (j <= i) ctx->ql_packed[i * (i + 1) / 2 + j] = v;
+        }
+    return TDX_OK;
+}
+
 int64_t tdx_local_dim(const tdx_ctx* ctx) { return (ctx && ctx->has_problem) ? (int64_t)ctx->geo.d : -1; }
 
 int tdx_halo_sizes(const tdx_ctx* ctx, int64_t* lo, int64_t* hi) {

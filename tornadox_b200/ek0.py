@@ -28,7 +28,8 @@ class KroneckerEK0(odefilter.ODEFilter):
         """ek0.py:94-121: single (n, n) factor, scalar NaN error estimate."""
         y0 = as_device_tensor(y0, dtype=self.dtype)
         self.engine = BatchedEK1._make_engine(self, f, y0.device)
-        A, Ql = _lib.prior(self.num_derivatives)
+        A, _ = _lib.prior(self.num_derivatives)
+        Ql = self.engine.Ql
         self.A = torch.as_tensor(A, dtype=self.dtype, device=y0.device)
         self.Ql = torch.as_tensor(Ql, dtype=self.dtype, device=y0.device)
         extended_dy0, cov_sqrtm = self.init(f=f, df=df, y0=y0, t0=t0, num_derivatives=self.num_derivatives)

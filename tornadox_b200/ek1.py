@@ -44,7 +44,8 @@ class BatchedEK1(odefilter.ODEFilter):
         """ek1.py:190-205.  ``y0`` is the GLOBAL initial value; a sharded solver keeps its own slice."""
         y0 = as_device_tensor(y0, dtype=self.dtype)
         self.engine = self._make_engine(f, y0.device)
-        A, Ql = _lib.prior(self.num_derivatives)
+        A, _ = _lib.prior(self.num_derivatives)
+        Ql = self.engine.Ql
         self.phi_1d = torch.as_tensor(A, dtype=self.dtype, device=y0.device)
         self.sq_1d = torch.as_tensor(Ql, dtype=self.dtype, device=y0.device)
         extended_dy0, cov_sqrtm = self.init(f=f, df=df, y0=y0, t0=t0, num_derivatives=self.num_derivatives)

@@ -130,6 +130,11 @@ class StepEngine:
         for i, v in enumerate(spec.params):
             desc.params[i] = float(v)
         _lib.check(self.lib.tdx_set_problem(self.handle, ctypes.byref(desc)))
+        # use the LAPACK factor the reference itself computes (iwp.py:37) rather than the library's
+        # extended-precision one: they differ by cond(Q) * eps, 1e-11 relative at nu = 5
+        self.Ql = _lib.lapack_diffusion_sqrt(self.nu)
+        _lib.check(self.lib.tdx_set_diffusion_sqrt(
+            self.handle, self.Ql.ctypes.data_as(ctypes.POINTER(ctypes.c_double))))
         self.d_local = int(self.lib.tdx_local_dim(self.handle))
         lo, hi = ctypes.c_int64(), ctypes.c_int64()
         _lib.check(self.lib.tdx_halo_sizes(self.handle, ctypes.byref(lo), ctypes.byref(hi)))

@@ -64,12 +64,13 @@ class DeviceVectorField:
 
 
 def as_device_tensor(y, dtype=None, device=None):
-    """y0 / state vectors live on the GPU; numpy input is copied there once."""
+    """State vectors live on the GPU: NumPy input is copied there once; tensors stay where they are."""
     if isinstance(y, torch.Tensor):
-        if y.is_cuda:
-            return y if dtype is None or y.dtype == dtype else y.to(dtype)
-        dtype = dtype or (y.dtype if y.dtype in (torch.float32, torch.float64) else torch.float64)
-        return y.to(device=device or "cuda", dtype=dtype)
+        if device is not None:
+            y = y.to(device)
+        if dtype is None and y.dtype not in (torch.float32, torch.float64):
+            dtype = torch.float64
+        return y if dtype is None or y.dtype == dtype else y.to(dtype)
     arr = np.asarray(y, dtype=np.float64)
     return torch.as_tensor(arr, dtype=dtype or torch.float64, device=device or "cuda")
 
