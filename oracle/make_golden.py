@@ -36,6 +36,25 @@ def problems(tornadox):
     return out
 
 
+def _ulp_perturbed(tornadox, jnp, state, sname, rng):
+    """The same filter state with every entry of mean and factor multiplied by (1 + u * 2^-52), u ~ U(-1, 1)."""
+    eps = 2.0 ** -52
+    wiggle = lambda x: jnp.array(np.asarray(x) * (1.0 + eps * rng.uniform(-1, 1, size=np.shape(x))))
+    y = state.y
+    if sname == "ek0":
+        y2 = tornadox.rv.LeftIsotropicMatrixNormal(wiggle(y.mean), y.d, wiggle(y.cov_sqrtm_2))
+    else:
+        y2 = tornadox.rv.BatchedMultivariateNormal(wiggle(y.mean), wiggle(y.cov_sqrtm))
+    return tornadox.odefilter.ODEFilterState(state.t, y2, state.error_estimate, state.reference_state)
+
+
+def _outputs(a, b, sname):
+    fac = (lambda s: s.y.cov_sqrtm_2) if sname == "ek0" else (lambda s: s.y.cov_sqrtm)
+    return [("mean", a.y.mean, b.y.mean), ("cov_sqrtm", fac(a), fac(b)),
+            ("error_estimate", a.error_estimate, b.error_estimate),
+            ("reference_state", a.reference_state, b.reference_state)]
+
+
 def main():
     tornadox = import_reference()
     import jax.numpy as jnp
@@ -68,7 +87,7 @@ def main():
             m0 = np.asarray(tornadox.init.TaylorMode.taylor_mode(ivp.f, ivp.y0, ivp.t0, nu))
             g[f"init/{name}/nu{nu}/taylor"] = m0
             dts = {"vanderpol": [0.0123, 0.05, 0.02], "lorenz96": [0.01, 0.02, 0.005],
-                   "brusselator": [1e-4, 2e-4, 1e-4], "fhn_2d": [1e-3, 2e-3, 5e-4]}[name]
+                   "brusselator": [0.02, 0.05, 0.01], "fhn_2d": [0.01, 0.03, 0.01]}[name]
             g[f"steps/{name}/dts"] = np.asarray(dts)
             solvers = {
                 "dek1": tornadox.ek1.DiagonalEK1,
@@ -79,8 +98,12 @@ def main():
                 sol = cls(num_derivatives=nu, steprule=tornadox.step.AdaptiveSteps())
                 state = sol.initialize(*ivp)
                 for i, dt in enumerate(dts):
-                    state, info = sol.attempt_step(state, dt, *ivp)
                     key = f"steps/{name}/nu{nu}/{sname}/{i}"
+                    # conditioning probe: the same attempt from inputs perturbed by ~1 ulp (see tests/helpers.py)
+                    twin, _ = sol.attempt_step(_ulp_perturbed(tornadox, jnp, state, sname, rng), dt, *ivp)
+                    state, info = sol.attempt_step(state, dt, *ivp)
+                    for field, a, b in _outputs(state, twin, sname):
+                        g[key + "/noise/" + field] = np.asarray(np.max(np.abs(np.asarray(a) - np.asarray(b))))
                     g[key + "/t"] = np.asarray(state.t)
                     g[key + "/mean"] = np.asarray(state.y.mean)
                     g[key + "/cov_sqrtm"] = np.asarray(state.y.cov_sqrtm if sname != "ek0" else state.y.cov_sqrtm_2)

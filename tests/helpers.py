@@ -60,9 +60,26 @@ def rel_err(a, b):
     return diff / scale if scale > 0 else diff
 
 
-def assert_close(a, b, rtol, what):
-    e = rel_err(a, b)
-    assert e <= rtol, f"{what}: relative error {e:.3e} > {rtol:.1e}"
+NOISE_FACTOR = 50.0
+
+
+def assert_close(a, b, rtol, what, noise=0.0):
+    """|a - b| <= rtol * max|b| + NOISE_FACTOR * noise.
+
+    ``noise`` is the change the REFERENCE's own output shows when its inputs are perturbed by ~1 ulp
+    (recorded next to each golden step by oracle/make_golden.py).  It is non-negligible only where the
+    algorithm itself is ill-conditioned: right after an exact Taylor-mode initialisation the residual
+    z = p1 mp[1] - f(p0 mp[0]) cancels 8+ digits, and error_estimate = |z| and the factors (proportional to
+    |z|) carry that rounding noise in ANY fp64 implementation, including JAX/XLA vs NumPy.
+    """
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    assert a.shape == b.shape, (a.shape, b.shape)
+    scale = np.max(np.abs(b)) if b.size else 0.0
+    diff = np.max(np.abs(a - b)) if b.size else 0.0
+    bound = rtol * scale + NOISE_FACTOR * float(noise)
+    if scale == 0 and noise == 0:
+        bound = rtol
+    assert diff <= bound, f"{what}: |diff| {diff:.3e} > {bound:.3e} (rtol {rtol:.1e} * {scale:.3e} + {NOISE_FACTOR} * noise {float(noise):.3e})"
 
 
 # ---- golden vectors generated from the reference's own sources (oracle/make_golden.py) ----------------
