@@ -64,17 +64,25 @@ inline Consts<T, N> make_consts(const StepHost& h) {
         if (e__ != cudaSuccess) return (int)e__;  \
     } while (0)
 
-// grid of a persistent kernel: as many CTAs as fit on the device at once, at most one per tile
+// grid of a persistent kernel: as many CTAs as fit on the device at once, at most one per tile.
+// The occupancy query and the shared-memory opt-in are done once per (kernel instantiation, device).
 template <class Kern>
 inline cudaError_t persistent_grid(Kern kern, size_t smem, long long tiles, unsigned& grid) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    constexpr int kMaxDevices = 64;
+    static int resident_cache[kMaxDevices] = {};     // one static per template instantiation (= per kernel)
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
-    int dev = 0, sms = 0, per_sm = 0;
-    if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
-    if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
-    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, smem)) != cudaSuccess) return e;
-    if (per_sm < 1) return cudaErrorLaunchOutOfResources;
-    const long long resident = (long long)sms * per_sm;
+    int resident = (dev >= 0 && dev < kMaxDevices) ? resident_cache[dev] : 0;
+    if (resident == 0) {
+        if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+        int sms = 0, per_sm = 0;
+        if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
+        if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, smem)) != cudaSuccess) return e;
+        if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+        resident = sms * per_sm;
+        if (dev >= 0 && dev < kMaxDevices) resident_cache[dev] = resident;
+    }
     grid = (unsigned)(tiles < resident ? tiles : resident);
     return cudaSuccess;
 }
