@@ -358,7 +358,7 @@ def e2e_host_buffers(torch, sol, state, dt, problem, world, dev, d, k):
         new, _ = sol.attempt_step(st, dt, *problem)
         h_mean_out.copy_(new.y.mean, non_blocking=True)
         h_fac_out.copy_(new.y.cov_sqrtm if is_dek1 else new.y.cov_sqrtm_2, non_blocking=True)
-        h_norm.copy_(new.scaled_error_norm_sq_sum.reshape(1), non_blocking=True)
+        h_norm.copy_(new.scaled_error_norm_sq_sum.sum().reshape(1), non_blocking=True)
 
     one()
     torch.cuda.synchronize()

@@ -81,6 +81,13 @@ typedef struct {
 
 /* DiagonalEK0 (ek0.py:196-280): run the DiagonalEK1 kernel with the Jacobian diagonal forced to zero */
 #define TDX_STEP_ZERO_JACOBIAN 1u
+/* Multi-GPU overlap: process only the tiles that do NOT read the halo buffers (INTERIOR; halo pointers may be
+ * NULL) or only those that do (RIM).  The two launches together cover the shard exactly once; each writes its own
+ * partial norm sum (add them).  Neither flag (or both) = all tiles in one launch. */
+#define TDX_STEP_TILES_INTERIOR 2u
+#define TDX_STEP_TILES_RIM 4u
+/* tdx_ek0_mid: z_sq_sum points at TWO doubles (interior + rim launches of sweep A) that are added */
+#define TDX_STEP_TWO_PARTS 8u
 
 const char* tdx_last_error(void);
 int tdx_abi_version(void);

@@ -54,7 +54,7 @@ def main():
                 y = rv.LeftIsotropicMatrixNormal(mean_l, mean_l.shape[1], torch.as_tensor(single, device=dev))
                 ost, _ = ofilters.kronecker_ek0_attempt(ofilters.FilterState(0.3, mean, single, None, None), dt, o.f, nu)
             st, _ = sol.attempt_step(odefilter.ODEFilterState(0.3, y, None, None), dt, *p)
-            norm = math.sqrt(float(st.scaled_error_norm_sq_sum) / d)
+            norm = step.norm_from_sq_sum(st.scaled_error_norm_sq_sum, d)
             ref_norm = odriver.AdaptiveSteps().scale_error_estimate(dt * ost.error_estimate, ost.reference_state)
             e_mean = np.max(np.abs(st.y.mean.cpu().numpy() - ost.mean[:, idx])) / np.max(np.abs(ost.mean))
             if name == "dek1":

@@ -72,7 +72,7 @@ def test_attempt_step_sequences(cuda_device, name, nu, solver):
                      noise("error_estimate"))
         assert_close(_np(state.reference_state), g[key + "/reference_state"], FP64_RTOL, "reference_state",
                      noise("reference_state"))
-        norm = math.sqrt(float(state.scaled_error_norm_sq_sum) / d)
+        norm = step.norm_from_sq_sum(state.scaled_error_norm_sq_sum, d)
         rel_noise = float(noise("error_estimate")) / max(float(np.max(np.abs(g[key + "/error_estimate"]))), 1e-300)
         assert_close(norm, g[key + "/scaled_error_norm"], FP64_RTOL, "scaled error norm",
                      rel_noise * float(g[key + "/scaled_error_norm"]))

@@ -72,7 +72,7 @@ def test_dek1_attempt_matches_oracle(cuda_device, kind, size, nu, cov):
     assert_close(S @ S.transpose(0, 2, 1), ref_state.cov_sqrtm @ ref_state.cov_sqrtm.transpose(0, 2, 1), FP64_RTOL, "cov")
     assert_close(err.cpu().numpy(), ref_state.error_estimate, FP64_RTOL, "error_estimate")
     assert_close(ref.cpu().numpy(), ref_state.reference_state, FP64_RTOL, "reference_state")
-    norm = math.sqrt(float(sq) / d)
+    norm = math.sqrt(float(sq.sum()) / d)
     assert abs(norm - ref_norm) <= FP64_RTOL * abs(ref_norm), (norm, ref_norm)
 
 

@@ -15,6 +15,9 @@ LIB_PATH = _PKG / "lib" / "libtornadox_b200.so"
 
 TDX_F64, TDX_F32 = 0, 1
 TDX_STEP_ZERO_JACOBIAN = 1
+TDX_STEP_TILES_INTERIOR = 2
+TDX_STEP_TILES_RIM = 4
+TDX_STEP_TWO_PARTS = 8
 TDX_IVP_VANDERPOL, TDX_IVP_LORENZ96, TDX_IVP_BRUSSELATOR, TDX_IVP_FHN2D = 0, 1, 2, 3
 
 EXPORTED_SYMBOLS = (

@@ -122,7 +122,7 @@ struct tdx_ctx {
     // workspace
     double* partials = nullptr;
     long long partials_cap = 0;
-    unsigned int* ticket = nullptr;
+    unsigned int* ticket = nullptr;   // [2]: the rim launch of an interior/rim pair uses the second workspace
     void* mid = nullptr;
     long long halo_lo = 0, halo_hi = 0;
     int64_t launches = 0;
@@ -163,8 +163,8 @@ int tdx_create(tdx_ctx** out, int device, int dtype) {
     int prev = 0;
     cudaGetDevice(&prev);
     cudaSetDevice(device);
-    e = cudaMalloc(&ctx->ticket, sizeof(unsigned int));
-    if (e == cudaSuccess) e = cudaMemset(ctx->ticket, 0, sizeof(unsigned int));
+    e = cudaMalloc(&ctx->ticket, 2 * sizeof(unsigned int));
+    if (e == cudaSuccess) e = cudaMemset(ctx->ticket, 0, 2 * sizeof(unsigned int));
     if (e == cudaSuccess) e = cudaMalloc(&ctx->mid, 256);
     if (e == cudaSuccess) e = cudaMemset(ctx->mid, 0, 256);
     cudaSetDevice(prev);
@@ -274,7 +274,7 @@ int tdx_set_problem(tdx_ctx* ctx, const tdx_problem_desc* d) {
     if (grid > ctx->partials_cap) {
         cudaFree(ctx->partials);
         ctx->partials = nullptr;
-        e = cudaMalloc(&ctx->partials, sizeof(double) * (size_t)grid);
+        e = cudaMalloc(&ctx->partials, 2 * sizeof(double) * (size_t)grid);
         ctx->partials_cap = (e == cudaSuccess) ? grid : 0;
     }
     cudaSetDevice(prev);
@@ -328,7 +328,8 @@ static int check_ready(const tdx_ctx* ctx, const char* where) {
     return TDX_OK;
 }
 
-static int check_halos(const tdx_ctx* ctx, const void* lo, const void* hi, const char* where) {
+static int check_halos(const tdx_ctx* ctx, const void* lo, const void* hi, const char* where, unsigned flags = 0u) {
+    if ((flags & 6u) == TDX_STEP_TILES_INTERIOR) return TDX_OK;   // interior tiles never read the halo buffers
     if (ctx->halo_lo > 0 && !lo) return fail(TDX_ERR_INVALID, std::string(where) + ": this shard needs halo_lo");
     if (ctx->halo_hi > 0 && !hi) return fail(TDX_ERR_INVALID, std::string(where) + ": this shard needs halo_hi");
     return TDX_OK;
@@ -346,7 +347,12 @@ static StepHost make_step(const tdx_ctx* ctx, const tdx_step_args* a) {
     return h;
 }
 
-static Workspace make_ws(const tdx_ctx* ctx) { return Workspace{ctx->partials, ctx->ticket, ctx->mid}; }
+static Workspace make_ws(const tdx_ctx* ctx, unsigned flags = 0u) {
+    const bool sharded = ctx->halo_lo > 0 || ctx->halo_hi > 0;
+    const bool second = (flags & 6u) == TDX_STEP_TILES_RIM;
+    return Workspace{ctx->partials + (second ? ctx->partials_cap : 0), ctx->ticket + (second ? 1 : 0), ctx->mid,
+                     sharded ? 4 : 0, ctx->halo_lo > 0, ctx->halo_hi > 0};
+}
 
 static int check_dt(const tdx_step_args* a, const char* where) {
     if (!a) return fail(TDX_ERR_INVALID, std::string(where) + ": null step arguments");
@@ -416,13 +422,13 @@ int tdx_dek1_attempt_step(tdx_ctx* ctx, const tdx_step_args* args, const void* m
     if (!mean_in || !sc_in || !mean_out || !sc_out) return fail(TDX_ERR_INVALID, "tdx_dek1_attempt_step: null state buffer");
     if (mean_in == mean_out || sc_in == sc_out)
         return fail(TDX_ERR_INVALID, "tdx_dek1_attempt_step: in and out buffers must be distinct (a rejected attempt keeps the input state)");
-    if ((rc = check_halos(ctx, halo_lo, halo_hi, "tdx_dek1_attempt_step"))) return rc;
+    if ((rc = check_halos(ctx, halo_lo, halo_hi, "tdx_dek1_attempt_step", args->flags))) return rc;
     StepHost h = make_step(ctx, args);
     if (h.want_norm && !sq_norm_sum) return fail(TDX_ERR_INVALID, "tdx_dek1_attempt_step: sq_norm_sum is required with tolerances");
     DeviceGuard guard(ctx->device);
     ctx->launches += 1;
     return cuda_fail(ctx->ops->dek1(ctx->geo, h, mean_in, sc_in, mean_out, sc_out, err_out, ref_out, halo_lo, halo_hi,
-                                    make_ws(ctx), sq_norm_sum, (cudaStream_t)stream),
+                                    make_ws(ctx, args->flags), sq_norm_sum, (cudaStream_t)stream),
                      "tdx_dek1_attempt_step");
 }
 
@@ -432,11 +438,11 @@ int tdx_ek0_sweep_a(tdx_ctx* ctx, const tdx_step_args* args, const void* mean_in
     if (rc) return rc;
     if ((rc = check_dt(args, "tdx_ek0_sweep_a"))) return rc;
     if (!mean_in || !z_sq_sum) return fail(TDX_ERR_INVALID, "tdx_ek0_sweep_a: null buffer");
-    if ((rc = check_halos(ctx, halo_lo, halo_hi, "tdx_ek0_sweep_a"))) return rc;
+    if ((rc = check_halos(ctx, halo_lo, halo_hi, "tdx_ek0_sweep_a", args->flags))) return rc;
     StepHost h = make_step(ctx, args);
     DeviceGuard guard(ctx->device);
     ctx->launches += 1;
-    return cuda_fail(ctx->ops->ek0_a(ctx->geo, h, mean_in, halo_lo, halo_hi, make_ws(ctx), z_sq_sum, (cudaStream_t)stream),
+    return cuda_fail(ctx->ops->ek0_a(ctx->geo, h, mean_in, halo_lo, halo_hi, make_ws(ctx, args->flags), z_sq_sum, (cudaStream_t)stream),
                      "tdx_ek0_sweep_a");
 }
 

@@ -43,6 +43,12 @@ struct SmemLayout {
     }
 };
 
+// A launch processes the tiles [b0, b0 + n0) followed by [b1, b1 + n1) (interior / rim split for multi-GPU overlap).
+struct TileRanges {
+    unsigned int b0, n0, b1, n1;
+    __device__ __forceinline__ unsigned tile(unsigned v) const { return v < n0 ? b0 + v : b1 + (v - n0); }
+};
+
 // ---------------------------------------------------------------------------------------------
 // front end shared by all step kernels, in two halves so that a persistent kernel can issue the loads of
 // the NEXT tile before it computes the current one.
@@ -106,7 +112,8 @@ struct DekArgs {
     double* partials;
     unsigned int* ticket;
     double* out_sum;
-    unsigned int num_tiles, tiles_x;
+    unsigned int num_tiles, tiles_x;   // num_tiles = number of tiles THIS launch processes (both ranges)
+    TileRanges ranges;
 };
 
 template <typename T, int N>
@@ -172,7 +179,7 @@ __global__ void __launch_bounds__(kThreads, TDX_MIN_BLOCKS) dek1_kernel(const __
     FrontRegs<IVP, T, N> fr;
     bool cur_bulk = false;
     if (tile < a.num_tiles) {
-        co = tile_coord<Shape>(g, tile, a.tiles_x);
+        co = tile_coord<Shape>(g, a.ranges.tile(tile), a.tiles_x);
         cur_bulk = stage_in(co, 0);
         if (TDX_PREFETCH_MEAN) front_load<IVP, T, N>(g, c, a.mean_in, a.halo_lo, a.halo_hi, co, fr);
     }
@@ -195,7 +202,7 @@ __global__ void __launch_bounds__(kThreads, TDX_MIN_BLOCKS) dek1_kernel(const __
         if (next < a.num_tiles) {
             if (lane == 0) bulk_wait_read0();      // the other slot's previous results have left shared memory
             __syncwarp();
-            co = tile_coord<Shape>(g, next, a.tiles_x);
+            co = tile_coord<Shape>(g, a.ranges.tile(next), a.tiles_x);
             next_bulk = stage_in(co, slot ^ 1);
             if (TDX_PREFETCH_MEAN) front_load<IVP, T, N>(g, c, a.mean_in, a.halo_lo, a.halo_hi, co, fr);
         }
@@ -321,6 +328,7 @@ struct Ek0Args {
     unsigned int* ticket;
     double* out_sum;
     unsigned int num_tiles, tiles_x;
+    TileRanges ranges;
     int reverse;             // walk the tiles backwards (sweep B re-reads what sweep A touched last: L2 reuse)
 };
 
@@ -343,7 +351,7 @@ __global__ void __launch_bounds__(kThreads, 3) ek0_sweep_kernel(const __grid_con
 #pragma unroll
         for (int r = 0; r < N; ++r) K[r] = a.mid->K[r];
     }
-    auto tile_of = [&](unsigned i) { return a.reverse ? (a.num_tiles - 1u - i) : i; };
+    auto tile_of = [&](unsigned i) { return a.ranges.tile(a.reverse ? (a.num_tiles - 1u - i) : i); };
 
     unsigned i = blockIdx.x;
     double acc = 0.0;
@@ -412,7 +420,8 @@ __global__ void ek0_mid_kernel(const __grid_constant__ Ek0MidArgs<T, N> a) {
     const double p1 = c.p[1];
     const double Q11 = QL(c, 1, 0) * QL(c, 1, 0) + QL(c, 1, 1) * QL(c, 1, 1);
     const double HQH = p1 * p1 * Q11;
-    const double sigma_sq = (*a.z_sq_sum) / HQH / a.d_global;
+    const double z_sq = a.z_sq_sum[0] + ((c.flags & 8u) ? a.z_sq_sum[1] : 0.0);   // TDX_STEP_TWO_PARTS
+    const double sigma_sq = z_sq / HQH / a.d_global;
     const double err = sqrt(sigma_sq * HQH);
     const double sigma = sqrt(sigma_sq);
     double B[N][N];

@@ -17,7 +17,26 @@ struct Workspace {
     double* partials;        // >= grid doubles
     unsigned int* ticket;
     void* mid;               // Ek0Mid<T, N>
+    int reserve_ctas;        // CTAs left free on the device (room for a concurrent NCCL kernel)
+    bool has_lo, has_hi;     // the shard has a lower / upper neighbour (halo buffers exist)
 };
+
+// Which tiles does a launch process?  all / interior (no halo reads) / rim (TDX_STEP_TILES_*).
+// Rim = the first / last tile row (2-d grids) or the first / last tile (chains) on sides that have a neighbour.
+inline TileRanges tile_ranges(unsigned flags, unsigned tiles_x, unsigned tiles_y, bool has_lo, bool has_hi,
+                              bool row_sharded) {
+    const unsigned total = tiles_x * tiles_y;
+    const unsigned want = flags & 6u;
+    if (want == 0u || want == 6u) return TileRanges{0u, total, 0u, 0u};
+    const unsigned edge = row_sharded ? tiles_x : 1u;
+    unsigned lo = has_lo ? edge : 0u, hi = has_hi ? edge : 0u;
+    if (lo + hi > total) {   // a single tile (row) touches both halos
+        lo = total;
+        hi = 0u;
+    }
+    if (want == 4u) return TileRanges{0u, lo, total - hi, hi};       // rim
+    return TileRanges{lo, total - lo - hi, 0u, 0u};                   // interior
+}
 
 struct Ops {
     int (*dek1)(const Geo&, const StepHost&, const void* mean_in, const void* sc_in, void* mean_out, void* sc_out,
@@ -67,7 +86,7 @@ inline Consts<T, N> make_consts(const StepHost& h) {
 // grid of a persistent kernel: as many CTAs as fit on the device at once, at most one per tile.
 // The occupancy query and the shared-memory opt-in are done once per (kernel instantiation, device).
 template <class Kern>
-inline cudaError_t persistent_grid(Kern kern, size_t smem, long long tiles, unsigned& grid) {
+inline cudaError_t persistent_grid(Kern kern, size_t smem, long long tiles, int reserve, unsigned& grid) {
     constexpr int kMaxDevices = 64;
     static int resident_cache[kMaxDevices] = {};     // one static per template instantiation (= per kernel)
     int dev = 0;
@@ -83,6 +102,7 @@ inline cudaError_t persistent_grid(Kern kern, size_t smem, long long tiles, unsi
         resident = sms * per_sm;
         if (dev >= 0 && dev < kMaxDevices) resident_cache[dev] = resident;
     }
+    if (reserve > 0 && resident - reserve >= 1) resident -= reserve;
     grid = (unsigned)(tiles < resident ? tiles : resident);
     return cudaSuccess;
 }
@@ -122,10 +142,16 @@ struct Launch {
             using Shape = typename IVP::Shape;
             const size_t smem = DekSmem<T, N>::total(Shape::AT_ELEMS);
             auto kern = dek1_kernel<IVP, T, N>;
-            unsigned grid = 0;
-            TDX_CUDA_TRY(persistent_grid(kern, smem, num_tiles<Shape>(g.rows, g.cols), grid));
-            a.num_tiles = (unsigned)num_tiles<Shape>(g.rows, g.cols);
             a.tiles_x = (unsigned)((g.cols + Shape::TC - 1) / Shape::TC);
+            const unsigned tiles_y = (unsigned)((g.rows + Shape::TR - 1) / Shape::TR);
+            a.ranges = tile_ranges(h.flags, a.tiles_x, tiles_y, ws.has_lo, ws.has_hi, g.kind == IVP_FHN2D);
+            a.num_tiles = a.ranges.n0 + a.ranges.n1;
+            if (a.num_tiles == 0u) {
+                if (h.want_norm) TDX_CUDA_TRY(cudaMemsetAsync(out_sum, 0, sizeof(double), st));
+                return 0;
+            }
+            unsigned grid = 0;
+            TDX_CUDA_TRY(persistent_grid(kern, smem, a.num_tiles, ws.reserve_ctas, grid));
             kern<<<grid, kThreads, smem, st>>>(a);
         })
         return (int)cudaGetLastError();
@@ -149,16 +175,22 @@ struct Launch {
     }
 
     template <bool kUpdate>
-    static int ek0_sweep(const Geo& g, Ek0Args<T, N>& a, cudaStream_t st) {
+    static int ek0_sweep(const Geo& g, Ek0Args<T, N>& a, unsigned flags, const Workspace& ws, cudaStream_t st) {
         TDX_SWITCH_IVP(g.kind, T, {
             using Shape = typename IVP::Shape;
             const size_t smem = L::BAR_BYTES + L::RED_BYTES + 2 * L::at_bytes(Shape::AT_ELEMS);
             auto kern = ek0_sweep_kernel<IVP, T, N, kUpdate>;
-            unsigned grid = 0;
-            TDX_CUDA_TRY(persistent_grid(kern, smem, num_tiles<Shape>(g.rows, g.cols), grid));
-            a.num_tiles = (unsigned)num_tiles<Shape>(g.rows, g.cols);
             a.tiles_x = (unsigned)((g.cols + Shape::TC - 1) / Shape::TC);
+            const unsigned tiles_y = (unsigned)((g.rows + Shape::TR - 1) / Shape::TR);
+            a.ranges = tile_ranges(flags, a.tiles_x, tiles_y, ws.has_lo, ws.has_hi, g.kind == IVP_FHN2D);
+            a.num_tiles = a.ranges.n0 + a.ranges.n1;
             a.reverse = kUpdate ? 1 : 0;
+            if (a.num_tiles == 0u) {
+                if (a.out_sum && (!kUpdate || a.c.want_norm)) TDX_CUDA_TRY(cudaMemsetAsync(a.out_sum, 0, sizeof(double), st));
+                return 0;
+            }
+            unsigned grid = 0;
+            TDX_CUDA_TRY(persistent_grid(kern, smem, a.num_tiles, ws.reserve_ctas, grid));
             kern<<<grid, kThreads, smem, st>>>(a);
         })
         return (int)cudaGetLastError();
@@ -167,13 +199,13 @@ struct Launch {
     static int ek0_a(const Geo& g, const StepHost& h, const void* mean_in, const void* halo_lo, const void* halo_hi,
                      const Workspace& ws, double* out_sum, cudaStream_t st) {
         Ek0Args<T, N> a = ek0_args(g, h, mean_in, nullptr, nullptr, halo_lo, halo_hi, ws, out_sum);
-        return ek0_sweep<false>(g, a, st);
+        return ek0_sweep<false>(g, a, h.flags, ws, st);
     }
 
     static int ek0_b(const Geo& g, const StepHost& h, const void* mean_in, void* mean_out, void* ref_out,
                      const void* halo_lo, const void* halo_hi, const Workspace& ws, double* out_sum, cudaStream_t st) {
         Ek0Args<T, N> a = ek0_args(g, h, mean_in, mean_out, ref_out, halo_lo, halo_hi, ws, out_sum);
-        return ek0_sweep<true>(g, a, st);
+        return ek0_sweep<true>(g, a, 0u, ws, st);
     }
 
     static int ek0_mid(const StepHost& h, const void* Cl_in, const double* z_sq_sum, double d_global, void* Cl_out,

@@ -140,7 +140,12 @@ class StepEngine:
         _lib.check(self.lib.tdx_halo_sizes(self.handle, ctypes.byref(lo), ctypes.byref(hi)))
         self.halo_lo_n, self.halo_hi_n = lo.value, hi.value
 
-        self._scalars = torch.zeros(4, dtype=torch.float64, device=self.device)   # [sq_norm, z_sq, inv_tol_sq, spare]
+        # device scalars, a ring of 16 rows so that the sums of recent attempts stay readable:
+        # [0:2] norm sums (interior, rim launches), [2] EK0 z^2 sum
+        self._scalar_ring = torch.zeros((16, 4), dtype=torch.float64, device=self.device)
+        self._ring_pos = 0
+        self.overlap = world > 1          # hide the halo exchange behind the interior tiles
+        self._comm_stream = torch.cuda.Stream(device=self.device) if world > 1 else None
         self.exchanger = None
         if world > 1:
             cyclic = spec.kind == _lib.TDX_IVP_LORENZ96
@@ -182,6 +187,10 @@ class StepEngine:
         if not x.is_contiguous():
             raise ValueError(f"{name} must be C-contiguous")
 
+    def _next_scalars(self):
+        self._ring_pos = (self._ring_pos + 1) % self._scalar_ring.shape[0]
+        return self._scalar_ring[self._ring_pos]
+
     def launch_count(self):
         return int(self.lib.tdx_launch_count(self.handle))
 
@@ -191,12 +200,34 @@ class StepEngine:
         return scalar
 
     def _halos_for_mean(self, dt, mean):
-        """Predicted-state halos for a step from ``mean`` (multi-GPU only)."""
+        """Predicted-state halos for a step from ``mean`` (multi-GPU only), exchanged on the current stream."""
         if self.world == 1:
             return None, None
         _lib.check(self.lib.tdx_pack_halo(self.handle, float(dt), _ptr(mean), _ptr(self._edge_first),
                                           _ptr(self._edge_last), self._stream()))
         return self.exchanger.exchange(self._edge_first, self._edge_last)
+
+    def _halos_overlapped(self, dt, mean):
+        """Pack on the compute stream, exchange on the communication stream; returns (halo_lo, halo_hi, event)."""
+        main = torch.cuda.current_stream(self.device)
+        _lib.check(self.lib.tdx_pack_halo(self.handle, float(dt), _ptr(mean), _ptr(self._edge_first),
+                                          _ptr(self._edge_last), self._stream()))
+        self._comm_stream.wait_stream(main)
+        with torch.cuda.stream(self._comm_stream):
+            halo_lo, halo_hi = self.exchanger.exchange(self._edge_first, self._edge_last)
+            ready = torch.cuda.Event()
+            ready.record(self._comm_stream)
+        return halo_lo, halo_hi, ready
+
+    def _all_reduce_on_comm_stream(self, scalars):
+        """Sum over ranks without stalling the compute stream; returns the event to wait on before reading."""
+        main = torch.cuda.current_stream(self.device)
+        self._comm_stream.wait_stream(main)
+        with torch.cuda.stream(self._comm_stream):
+            self.exchanger.dist.all_reduce(scalars, group=self.group)
+            done = torch.cuda.Event()
+            done.record(self._comm_stream)
+        return done
 
     # ---- vector field ---------------------------------------------------------------------------
     def eval_f(self, t, y, want_jac=False):
@@ -229,13 +260,29 @@ class StepEngine:
         sc_out = torch.empty_like(sc) if sc_out is None else sc_out
         err = torch.empty(d, dtype=self.dtype, device=self.device) if want_err_ref else None
         ref = torch.empty(d, dtype=self.dtype, device=self.device) if want_err_ref else None
+        base_flags = 0 if jacobian else _lib.TDX_STEP_ZERO_JACOBIAN
+        want_norm = abstol != 0.0 or reltol != 0.0
+        call = self.lib.tdx_dek1_attempt_step
+        bufs = (_ptr(mean), _ptr(sc), _ptr(mean_out), _ptr(sc_out), _ptr(err), _ptr(ref))
+        scal = self._next_scalars()
+        if self.world > 1 and self.overlap:
+            # interior tiles run while the halos travel; the rim tiles follow once they have arrived
+            halo_lo, halo_hi, ready = self._halos_overlapped(dt, mean)
+            a_int = self._args(t, dt, abstol, reltol, base_flags | _lib.TDX_STEP_TILES_INTERIOR)
+            _lib.check(call(self.handle, ctypes.byref(a_int), *bufs, None, None, _ptr(scal[0:1]), self._stream()))
+            torch.cuda.current_stream(self.device).wait_event(ready)
+            a_rim = self._args(t, dt, abstol, reltol, base_flags | _lib.TDX_STEP_TILES_RIM)
+            _lib.check(call(self.handle, ctypes.byref(a_rim), *bufs, _ptr(halo_lo), _ptr(halo_hi),
+                            _ptr(scal[1:2]), self._stream()))
+            sq = scal[0:2]
+            if want_norm:
+                sq.ready_event = self._all_reduce_on_comm_stream(sq)
+            return mean_out, sc_out, err, ref, sq
         halo_lo, halo_hi = self._halos_for_mean(dt, mean)
-        args = self._args(t, dt, abstol, reltol, 0 if jacobian else _lib.TDX_STEP_ZERO_JACOBIAN)
-        sq = self._scalars[0:1]
-        _lib.check(self.lib.tdx_dek1_attempt_step(
-            self.handle, ctypes.byref(args), _ptr(mean), _ptr(sc), _ptr(mean_out), _ptr(sc_out), _ptr(err), _ptr(ref),
-            _ptr(halo_lo), _ptr(halo_hi), _ptr(sq), self._stream()))
-        if abstol != 0.0 or reltol != 0.0:
+        args = self._args(t, dt, abstol, reltol, base_flags)
+        sq = scal[0:1]
+        _lib.check(call(self.handle, ctypes.byref(args), *bufs, _ptr(halo_lo), _ptr(halo_hi), _ptr(sq), self._stream()))
+        if want_norm:
             self.all_reduce_(sq)
         return mean_out, sc_out, err, ref, sq
 
@@ -249,19 +296,37 @@ class StepEngine:
         Cl_out = torch.empty_like(Cl)
         err = torch.empty((), dtype=self.dtype, device=self.device)
         ref = torch.empty(d, dtype=self.dtype, device=self.device) if want_ref else None
-        halo_lo, halo_hi = self._halos_for_mean(dt, mean)
-        args = self._args(t, dt, abstol, reltol)
-        zsq, itol = self._scalars[1:2], self._scalars[2:3]
+        scal = self._next_scalars()
+        zsq, itol = scal[2:4], scal[0:1]
         st = self._stream()
-        _lib.check(self.lib.tdx_ek0_sweep_a(self.handle, ctypes.byref(args), _ptr(mean), _ptr(halo_lo), _ptr(halo_hi),
-                                            _ptr(zsq), st))
-        self.all_reduce_(zsq)
-        _lib.check(self.lib.tdx_ek0_mid(self.handle, ctypes.byref(args), _ptr(Cl), _ptr(zsq), self.d_global,
+        want_norm = abstol != 0.0 or reltol != 0.0
+        args = self._args(t, dt, abstol, reltol)
+        if self.world > 1 and self.overlap:
+            halo_lo, halo_hi, ready = self._halos_overlapped(dt, mean)
+            a_int = self._args(t, dt, abstol, reltol, _lib.TDX_STEP_TILES_INTERIOR)
+            _lib.check(self.lib.tdx_ek0_sweep_a(self.handle, ctypes.byref(a_int), _ptr(mean), None, None,
+                                                _ptr(zsq[0:1]), st))
+            torch.cuda.current_stream(self.device).wait_event(ready)
+            a_rim = self._args(t, dt, abstol, reltol, _lib.TDX_STEP_TILES_RIM)
+            _lib.check(self.lib.tdx_ek0_sweep_a(self.handle, ctypes.byref(a_rim), _ptr(mean), _ptr(halo_lo),
+                                                _ptr(halo_hi), _ptr(zsq[1:2]), st))
+            self.all_reduce_(zsq)                       # the calibration needs the global sum before anything else
+            a_mid = self._args(t, dt, abstol, reltol, _lib.TDX_STEP_TWO_PARTS)
+        else:
+            halo_lo, halo_hi = self._halos_for_mean(dt, mean)
+            _lib.check(self.lib.tdx_ek0_sweep_a(self.handle, ctypes.byref(args), _ptr(mean), _ptr(halo_lo),
+                                                _ptr(halo_hi), _ptr(zsq[0:1]), st))
+            self.all_reduce_(zsq[0:1])
+            a_mid = args
+        _lib.check(self.lib.tdx_ek0_mid(self.handle, ctypes.byref(a_mid), _ptr(Cl), _ptr(zsq), self.d_global,
                                         _ptr(Cl_out), _ptr(err), st))
         _lib.check(self.lib.tdx_ek0_sweep_b(self.handle, ctypes.byref(args), _ptr(mean), _ptr(mean_out), _ptr(ref),
                                             _ptr(halo_lo), _ptr(halo_hi), _ptr(itol), st))
-        if abstol != 0.0 or reltol != 0.0:
-            self.all_reduce_(itol)
+        if want_norm and self.world > 1:
+            if self.overlap:
+                itol.ready_event = self._all_reduce_on_comm_stream(itol)
+            else:
+                self.all_reduce_(itol)
         return mean_out, Cl_out, err, ref, itol
 
 

@@ -101,8 +101,16 @@ class AdaptiveSteps(StepRule):
 
 
 def norm_from_sq_sum(sq_sum, dim):
-    """sqrt(sum ratio_i^2 / d): finish the norm whose sum the kernel epilogue produced."""
-    return math.sqrt(float(sq_sum) / dim)
+    """sqrt(sum ratio_i^2 / d): finish the norm whose sum(s) the kernel epilogue(s) produced.
+
+    ``sq_sum`` is a device tensor with one entry per launch that contributed (interior / rim tiles of a sharded
+    step); if it carries a ``ready_event`` (all-reduce on the communication stream) that is awaited first.
+    """
+    event = getattr(sq_sum, "ready_event", None)
+    if event is not None:
+        event.synchronize()
+    total = float(sq_sum.sum()) if hasattr(sq_sum, "sum") else float(sq_sum)
+    return math.sqrt(total / dim)
 
 
 def propose_first_dt(f, t0, y0):
