@@ -85,10 +85,10 @@ inline Consts<T, N> make_consts(const StepHost& h) {
 
 // grid of a persistent kernel: as many CTAs as fit on the device at once, at most one per tile.
 // The occupancy query and the shared-memory opt-in are done once per (kernel instantiation, device).
-template <class Kern>
-inline cudaError_t persistent_grid(Kern kern, size_t smem, long long tiles, int reserve, unsigned& grid) {
+template <auto kern>
+inline cudaError_t persistent_grid(size_t smem, long long tiles, int reserve, unsigned& grid) {
     constexpr int kMaxDevices = 64;
-    static int resident_cache[kMaxDevices] = {};     // one static per template instantiation (= per kernel)
+    static int resident_cache[kMaxDevices] = {};     // one static per kernel FUNCTION (non-type template parameter)
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
@@ -141,7 +141,7 @@ struct Launch {
         TDX_SWITCH_IVP(g.kind, T, {
             using Shape = typename IVP::Shape;
             const size_t smem = DekSmem<T, N>::total(Shape::AT_ELEMS);
-            auto kern = dek1_kernel<IVP, T, N>;
+            constexpr auto kern = dek1_kernel<IVP, T, N>;
             a.tiles_x = (unsigned)((g.cols + Shape::TC - 1) / Shape::TC);
             const unsigned tiles_y = (unsigned)((g.rows + Shape::TR - 1) / Shape::TR);
             a.ranges = tile_ranges(h.flags, a.tiles_x, tiles_y, ws.has_lo, ws.has_hi, g.kind == IVP_FHN2D);
@@ -151,7 +151,7 @@ struct Launch {
                 return 0;
             }
             unsigned grid = 0;
-            TDX_CUDA_TRY(persistent_grid(kern, smem, a.num_tiles, ws.reserve_ctas, grid));
+            TDX_CUDA_TRY(persistent_grid<kern>(smem, a.num_tiles, ws.reserve_ctas, grid));
             kern<<<grid, kThreads, smem, st>>>(a);
         })
         return (int)cudaGetLastError();
@@ -179,7 +179,7 @@ struct Launch {
         TDX_SWITCH_IVP(g.kind, T, {
             using Shape = typename IVP::Shape;
             const size_t smem = L::BAR_BYTES + L::RED_BYTES + 2 * L::at_bytes(Shape::AT_ELEMS);
-            auto kern = ek0_sweep_kernel<IVP, T, N, kUpdate>;
+            constexpr auto kern = ek0_sweep_kernel<IVP, T, N, kUpdate>;
             a.tiles_x = (unsigned)((g.cols + Shape::TC - 1) / Shape::TC);
             const unsigned tiles_y = (unsigned)((g.rows + Shape::TR - 1) / Shape::TR);
             a.ranges = tile_ranges(flags, a.tiles_x, tiles_y, ws.has_lo, ws.has_hi, g.kind == IVP_FHN2D);
@@ -190,7 +190,7 @@ struct Launch {
                 return 0;
             }
             unsigned grid = 0;
-            TDX_CUDA_TRY(persistent_grid(kern, smem, a.num_tiles, ws.reserve_ctas, grid));
+            TDX_CUDA_TRY(persistent_grid<kern>(smem, a.num_tiles, ws.reserve_ctas, grid));
             kern<<<grid, kThreads, smem, st>>>(a);
         })
         return (int)cudaGetLastError();

@@ -144,7 +144,9 @@ class StepEngine:
         # [0:2] norm sums (interior, rim launches), [2] EK0 z^2 sum
         self._scalar_ring = torch.zeros((16, 4), dtype=torch.float64, device=self.device)
         self._ring_pos = 0
-        self.overlap = world > 1          # hide the halo exchange behind the interior tiles
+        # interior/rim split with the exchange on a second stream: NCCL's own kernels cannot be scheduled while the
+        # persistent step kernel holds every SM, so this only pays off with the SM-free peer-memory exchange
+        self.overlap = False
         self._comm_stream = torch.cuda.Stream(device=self.device) if world > 1 else None
         self.exchanger = None
         if world > 1:
