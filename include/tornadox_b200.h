@@ -154,6 +154,27 @@ int tdx_ek0_attempt_step(tdx_ctx* ctx, const tdx_step_args* args, const void* me
                          const void* Cl_in, void* mean_out, void* Cl_out, void* err_out,
                          void* ref_out, double* z_sq_sum, double* sq_norm_sum, void* stream);
 
+/* ---- peer-memory exchange over NVLink (multi-GPU, one process per GPU on one node) -------------------------
+ * No reference counterpart (the reference is single-device).  Instead of NCCL calls between the kernels, every
+ * context owns a small device block (halo buffers, reduction slots, sequence-numbered flags) that its neighbours
+ * map through CUDA IPC; the pack kernel stores the halos directly into the neighbours' blocks, the step kernels
+ * spin (with a timeout) on the flag before they read them, and a one-CTA kernel all-reduces the scalars in rank
+ * order (deterministic).  Nothing here needs a free SM while a persistent step kernel is running.
+ *   tdx_comm_init     allocate the block; ``handle_out`` receives TDX_COMM_HANDLE_BYTES to all-gather
+ *   tdx_comm_connect  map rank ``peer``'s block from its handle (call for every peer, then barrier)
+ *   tdx_comm_pack_halo   predicted edge state -> neighbours' halo buffers (+ flags); replaces tdx_pack_halo + send/recv
+ *   step calls with TDX_STEP_COMM_HALO read those buffers (halo pointers are ignored)
+ *   tdx_comm_allreduce   vals[0..count) summed over ranks in place (count <= 4), device scalars
+ *   tdx_comm_error    non-zero after a flag wait timed out (a peer died or diverged) */
+#define TDX_COMM_HANDLE_BYTES 64
+#define TDX_STEP_COMM_HALO 16u
+int tdx_comm_init(tdx_ctx* ctx, int rank, int world, int lower_rank /* -1: none */, int upper_rank /* -1: none */,
+                  void* handle_out);
+int tdx_comm_connect(tdx_ctx* ctx, int peer, const void* handle);
+int tdx_comm_pack_halo(tdx_ctx* ctx, double dt, const void* mean_in, void* stream);
+int tdx_comm_allreduce(tdx_ctx* ctx, double* vals, int count, void* stream);
+int tdx_comm_error(tdx_ctx* ctx, int* error_out, void* stream);
+
 /* kernels launched by this context since creation (bench.py's gpu_launches counter) */
 int64_t tdx_launch_count(const tdx_ctx* ctx);
 

@@ -18,12 +18,15 @@ TDX_STEP_ZERO_JACOBIAN = 1
 TDX_STEP_TILES_INTERIOR = 2
 TDX_STEP_TILES_RIM = 4
 TDX_STEP_TWO_PARTS = 8
+TDX_STEP_COMM_HALO = 16
+TDX_COMM_HANDLE_BYTES = 64
 TDX_IVP_VANDERPOL, TDX_IVP_LORENZ96, TDX_IVP_BRUSSELATOR, TDX_IVP_FHN2D = 0, 1, 2, 3
 
 EXPORTED_SYMBOLS = (
     "tdx_last_error", "tdx_abi_version", "tdx_create", "tdx_destroy", "tdx_set_problem", "tdx_local_dim",
     "tdx_halo_sizes", "tdx_set_diffusion_sqrt", "tdx_prior", "tdx_nordsieck", "tdx_eval_f", "tdx_pack_halo", "tdx_dek1_attempt_step",
     "tdx_ek0_sweep_a", "tdx_ek0_mid", "tdx_ek0_sweep_b", "tdx_ek0_attempt_step", "tdx_launch_count",
+    "tdx_comm_init", "tdx_comm_connect", "tdx_comm_pack_halo", "tdx_comm_allreduce", "tdx_comm_error",
 )
 
 
@@ -90,6 +93,11 @@ def load():
     lib.tdx_ek0_mid.argtypes = [vp, ctypes.POINTER(StepArgs), vp, vp, i64, vp, vp, vp]
     lib.tdx_ek0_sweep_b.argtypes = [vp, ctypes.POINTER(StepArgs), vp, vp, vp, vp, vp, vp, vp]
     lib.tdx_ek0_attempt_step.argtypes = [vp, ctypes.POINTER(StepArgs)] + [vp] * 9
+    lib.tdx_comm_init.argtypes = [vp, cint, cint, cint, cint, vp]
+    lib.tdx_comm_connect.argtypes = [vp, cint, vp]
+    lib.tdx_comm_pack_halo.argtypes = [vp, dbl, vp, vp]
+    lib.tdx_comm_allreduce.argtypes = [vp, vp, cint, vp]
+    lib.tdx_comm_error.argtypes = [vp, ctypes.POINTER(cint), vp]
     lib.tdx_launch_count.restype = i64
     lib.tdx_launch_count.argtypes = [vp]
     for name in EXPORTED_SYMBOLS:

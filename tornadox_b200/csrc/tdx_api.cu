@@ -54,6 +54,34 @@ long long grid_for(const Geo& g) {
     return 0;
 }
 
+// Deterministic all-reduce (sum in rank order) of up to 4 doubles through the peers' reduction slots.
+struct AllReduceArgs {
+    CommHeader* local;
+    CommHeader* peer[kMaxWorld];
+    double* vals;
+    int count, rank, world;
+    unsigned long long seq;
+};
+
+__global__ void comm_allreduce_kernel(const __grid_constant__ AllReduceArgs a) {
+    const int r = threadIdx.x;
+    const int parity = (int)(a.seq & 1ull);
+    if (r < a.world) {
+        CommHeader* dst = a.peer[r];
+        for (int j = 0; j < a.count; ++j) dst->red_val[parity][a.rank][j] = a.vals[j];
+        __threadfence_system();
+        st_release_sys(&dst->red_flag[parity][a.rank], a.seq);
+    }
+    __syncthreads();
+    if (r < a.world) spin_until(&a.local->red_flag[parity][r], a.seq, &a.local->error);
+    __syncthreads();
+    if (r < a.count) {
+        double acc = 0.0;
+        for (int k = 0; k < a.world; ++k) acc += *((volatile double*)&a.local->red_val[parity][k][r]);
+        a.vals[r] = acc;
+    }
+}
+
 // ---- prior constants on the host (iwp.py:19-37, 65-73) -------------------------------------------
 
 // Ql = chol(Q), Q[i][j] = 1 / (2 nu + 1 - i - j).  Computed in long double and rounded, so the result is
@@ -126,7 +154,23 @@ struct tdx_ctx {
     void* mid = nullptr;
     long long halo_lo = 0, halo_hi = 0;
     int64_t launches = 0;
+    // peer-memory exchange
+    unsigned char* comm_local = nullptr;
+    unsigned char* comm_peer[kMaxWorld] = {};
+    bool comm_opened[kMaxWorld] = {};
+    int rank = 0, world = 1, lower = -1, upper = -1;
+    unsigned long long halo_seq = 0, red_seq = 0;
+    long long halo_cap = 0;          // elements per parity and side
 };
+
+static size_t comm_bytes(const tdx_ctx* ctx) {
+    return sizeof(CommHeader) + 4 * (size_t)ctx->halo_cap * (ctx->dtype == TDX_F64 ? 8 : 4) + 64;
+}
+// halo storage behind the header: lo[parity] at (0, 1), hi[parity] at (2, 3)
+static unsigned char* comm_halo(const tdx_ctx* ctx, unsigned char* base, int hi, int parity) {
+    const size_t es = ctx->dtype == TDX_F64 ? 8 : 4;
+    return base + sizeof(CommHeader) + (size_t)(2 * hi + parity) * (size_t)ctx->halo_cap * es;
+}
 
 static size_t esize(int dtype) { return dtype == TDX_F64 ? 8 : 4; }
 
@@ -184,6 +228,9 @@ int tdx_destroy(tdx_ctx* ctx) {
     cudaFree(ctx->partials);
     cudaFree(ctx->ticket);
     cudaFree(ctx->mid);
+    for (int r = 0; r < kMaxWorld; ++r)
+        if (ctx->comm_opened[r]) cudaIpcCloseMemHandle(ctx->comm_peer[r]);
+    cudaFree(ctx->comm_local);
     cudaSetDevice(prev);
     delete ctx;
     return TDX_OK;
@@ -348,10 +395,26 @@ static StepHost make_step(const tdx_ctx* ctx, const tdx_step_args* a) {
 }
 
 static Workspace make_ws(const tdx_ctx* ctx, unsigned flags = 0u) {
-    const bool sharded = ctx->halo_lo > 0 || ctx->halo_hi > 0;
     const bool second = (flags & 6u) == TDX_STEP_TILES_RIM;
-    return Workspace{ctx->partials + (second ? ctx->partials_cap : 0), ctx->ticket + (second ? 1 : 0), ctx->mid,
-                     sharded ? 4 : 0, ctx->halo_lo > 0, ctx->halo_hi > 0};
+    Workspace ws{ctx->partials + (second ? ctx->partials_cap : 0), ctx->ticket + (second ? 1 : 0), ctx->mid, 0,
+                 ctx->halo_lo > 0, ctx->halo_hi > 0, CommWait{nullptr, nullptr, 0ull, nullptr}};
+    if ((flags & TDX_STEP_COMM_HALO) && ctx->comm_local && (flags & 6u) != TDX_STEP_TILES_INTERIOR) {
+        CommHeader* hdr = reinterpret_cast<CommHeader*>(ctx->comm_local);
+        const int parity = (int)(ctx->halo_seq & 1ull);
+        ws.wait.flag_lo = ctx->halo_lo > 0 ? &hdr->halo_flag_lo[parity] : nullptr;
+        ws.wait.flag_hi = ctx->halo_hi > 0 ? &hdr->halo_flag_hi[parity] : nullptr;
+        ws.wait.seq = ctx->halo_seq;
+        ws.wait.error = &hdr->error;
+    }
+    return ws;
+}
+
+// halo pointers of a step call: the caller's, or (TDX_STEP_COMM_HALO) the context's peer-written buffers
+static void resolve_halos(const tdx_ctx* ctx, unsigned flags, const void*& lo, const void*& hi) {
+    if (!(flags & TDX_STEP_COMM_HALO) || !ctx->comm_local) return;
+    const int parity = (int)(ctx->halo_seq & 1ull);
+    lo = ctx->halo_lo > 0 ? comm_halo(ctx, ctx->comm_local, 0, parity) : nullptr;
+    hi = ctx->halo_hi > 0 ? comm_halo(ctx, ctx->comm_local, 1, parity) : nullptr;
 }
 
 static int check_dt(const tdx_step_args* a, const char* where) {
@@ -419,6 +482,7 @@ int tdx_dek1_attempt_step(tdx_ctx* ctx, const tdx_step_args* args, const void* m
     int rc = check_ready(ctx, "tdx_dek1_attempt_step");
     if (rc) return rc;
     if ((rc = check_dt(args, "tdx_dek1_attempt_step"))) return rc;
+    resolve_halos(ctx, args->flags, halo_lo, halo_hi);
     if (!mean_in || !sc_in || !mean_out || !sc_out) return fail(TDX_ERR_INVALID, "tdx_dek1_attempt_step: null state buffer");
     if (mean_in == mean_out || sc_in == sc_out)
         return fail(TDX_ERR_INVALID, "tdx_dek1_attempt_step: in and out buffers must be distinct (a rejected attempt keeps the input state)");
@@ -437,6 +501,7 @@ int tdx_ek0_sweep_a(tdx_ctx* ctx, const tdx_step_args* args, const void* mean_in
     int rc = check_ready(ctx, "tdx_ek0_sweep_a");
     if (rc) return rc;
     if ((rc = check_dt(args, "tdx_ek0_sweep_a"))) return rc;
+    resolve_halos(ctx, args->flags, halo_lo, halo_hi);
     if (!mean_in || !z_sq_sum) return fail(TDX_ERR_INVALID, "tdx_ek0_sweep_a: null buffer");
     if ((rc = check_halos(ctx, halo_lo, halo_hi, "tdx_ek0_sweep_a", args->flags))) return rc;
     StepHost h = make_step(ctx, args);
@@ -465,6 +530,7 @@ int tdx_ek0_sweep_b(tdx_ctx* ctx, const tdx_step_args* args, const void* mean_in
     int rc = check_ready(ctx, "tdx_ek0_sweep_b");
     if (rc) return rc;
     if ((rc = check_dt(args, "tdx_ek0_sweep_b"))) return rc;
+    resolve_halos(ctx, args->flags, halo_lo, halo_hi);
     if (!mean_in || !mean_out) return fail(TDX_ERR_INVALID, "tdx_ek0_sweep_b: null buffer");
     if (mean_in == mean_out) return fail(TDX_ERR_INVALID, "tdx_ek0_sweep_b: in and out buffers must be distinct");
     if ((rc = check_halos(ctx, halo_lo, halo_hi, "tdx_ek0_sweep_b"))) return rc;
@@ -472,9 +538,124 @@ int tdx_ek0_sweep_b(tdx_ctx* ctx, const tdx_step_args* args, const void* mean_in
     if (h.want_norm && !sq_norm_sum) return fail(TDX_ERR_INVALID, "tdx_ek0_sweep_b: sq_norm_sum is required with tolerances");
     DeviceGuard guard(ctx->device);
     ctx->launches += 1;
-    return cuda_fail(ctx->ops->ek0_b(ctx->geo, h, mean_in, mean_out, ref_out, halo_lo, halo_hi, make_ws(ctx), sq_norm_sum,
+    return cuda_fail(ctx->ops->ek0_b(ctx->geo, h, mean_in, mean_out, ref_out, halo_lo, halo_hi, make_ws(ctx, args->flags & ~6u), sq_norm_sum,
                                      (cudaStream_t)stream),
                      "tdx_ek0_sweep_b");
+}
+
+// ---- peer-memory exchange ---------------------------------------------------------------------------------
+
+static void edge_counts(const Geo& g, int& n_first, int& n_last) {
+    n_first = n_last = 0;
+    switch (g.kind) {
+        case IVP_FHN2D: n_first = n_last = g.cols; break;
+        case IVP_BRUSS: n_first = n_last = 1; break;
+        case IVP_LORENZ96: n_first = 1; n_last = 2; break;
+        default: break;
+    }
+}
+
+int tdx_comm_init(tdx_ctx* ctx, int rank, int world, int lower_rank, int upper_rank, void* handle_out) {
+    int rc = check_ready(ctx, "tdx_comm_init");
+    if (rc) return rc;
+    if (world < 2 || world > kMaxWorld || rank < 0 || rank >= world || !handle_out)
+        return fail(TDX_ERR_INVALID, "tdx_comm_init: need 2 <= world <= 16, 0 <= rank < world and a handle buffer");
+    if (lower_rank >= world || upper_rank >= world) return fail(TDX_ERR_INVALID, "tdx_comm_init: neighbour rank out of range");
+    if (ctx->comm_local) return fail(TDX_ERR_INVALID, "tdx_comm_init: already initialised");
+    DeviceGuard guard(ctx->device);
+    ctx->rank = rank; ctx->world = world; ctx->lower = lower_rank; ctx->upper = upper_rank;
+    // same capacity on every rank so that the block layout is identical everywhere
+    ctx->halo_cap = (ctx->geo.kind == IVP_FHN2D) ? 2LL * ctx->geo.cols : 4;
+    cudaError_t e = cudaMalloc(&ctx->comm_local, comm_bytes(ctx));
+    if (e == cudaSuccess) e = cudaMemset(ctx->comm_local, 0, comm_bytes(ctx));
+    cudaIpcMemHandle_t h;
+    if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, ctx->comm_local);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) return cuda_fail((int)e, "tdx_comm_init");
+    static_assert(sizeof(cudaIpcMemHandle_t) == TDX_COMM_HANDLE_BYTES, "IPC handle size");
+    std::memcpy(handle_out, &h, sizeof(h));
+    ctx->comm_peer[rank] = ctx->comm_local;
+    ctx->halo_seq = 0; ctx->red_seq = 0;
+    return TDX_OK;
+}
+
+int tdx_comm_connect(tdx_ctx* ctx, int peer, const void* handle) {
+    if (!ctx || !ctx->comm_local) return fail(TDX_ERR_INVALID, "tdx_comm_connect: call tdx_comm_init first");
+    if (peer < 0 || peer >= ctx->world || !handle) return fail(TDX_ERR_INVALID, "tdx_comm_connect: bad peer or handle");
+    if (peer == ctx->rank) return TDX_OK;
+    if (ctx->comm_opened[peer]) return TDX_OK;
+    DeviceGuard guard(ctx->device);
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle, sizeof(h));
+    void* ptr = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) return cuda_fail((int)e, "tdx_comm_connect (cudaIpcOpenMemHandle)");
+    ctx->comm_peer[peer] = (unsigned char*)ptr;
+    ctx->comm_opened[peer] = true;
+    return TDX_OK;
+}
+
+int tdx_comm_pack_halo(tdx_ctx* ctx, double dt, const void* mean_in, void* stream) {
+    int rc = check_ready(ctx, "tdx_comm_pack_halo");
+    if (rc) return rc;
+    if (!ctx->comm_local) return fail(TDX_ERR_INVALID, "tdx_comm_pack_halo: call tdx_comm_init first");
+    tdx_step_args a{0.0, dt, 0.0, 0.0, 0u, 0u};
+    if ((rc = check_dt(&a, "tdx_comm_pack_halo"))) return rc;
+    if (!mean_in) return fail(TDX_ERR_INVALID, "tdx_comm_pack_halo: null buffer");
+    if ((ctx->lower >= 0 && !ctx->comm_peer[ctx->lower]) || (ctx->upper >= 0 && !ctx->comm_peer[ctx->upper]))
+        return fail(TDX_ERR_INVALID, "tdx_comm_pack_halo: neighbours are not connected");
+    int n_first = 0, n_last = 0;
+    edge_counts(ctx->geo, n_first, n_last);
+    ctx->halo_seq += 1;
+    const int parity = (int)(ctx->halo_seq & 1ull);
+    void* dst_lower = nullptr; void* dst_upper = nullptr;
+    unsigned long long* flag_lower = nullptr; unsigned long long* flag_upper = nullptr;
+    if (ctx->lower >= 0) {   // our first rows are the lower neighbour's UPPER halo
+        unsigned char* base = ctx->comm_peer[ctx->lower];
+        dst_lower = comm_halo(ctx, base, 1, parity);
+        flag_lower = &reinterpret_cast<CommHeader*>(base)->halo_flag_hi[parity];
+    }
+    if (ctx->upper >= 0) {
+        unsigned char* base = ctx->comm_peer[ctx->upper];
+        dst_upper = comm_halo(ctx, base, 0, parity);
+        flag_upper = &reinterpret_cast<CommHeader*>(base)->halo_flag_lo[parity];
+    }
+    StepHost h = make_step(ctx, &a);
+    DeviceGuard guard(ctx->device);
+    ctx->launches += 1;
+    return cuda_fail(ctx->ops->pack_peer(ctx->geo, h, mean_in, dst_lower, dst_upper, flag_lower, flag_upper, ctx->halo_seq,
+                                         n_first, n_last, (cudaStream_t)stream),
+                     "tdx_comm_pack_halo");
+}
+
+int tdx_comm_allreduce(tdx_ctx* ctx, double* vals, int count, void* stream) {
+    if (!ctx || !ctx->comm_local) return fail(TDX_ERR_INVALID, "tdx_comm_allreduce: call tdx_comm_init first");
+    if (!vals || count < 1 || count > 4) return fail(TDX_ERR_INVALID, "tdx_comm_allreduce: 1 <= count <= 4");
+    AllReduceArgs a{};
+    a.local = reinterpret_cast<CommHeader*>(ctx->comm_local);
+    for (int r = 0; r < ctx->world; ++r) {
+        if (!ctx->comm_peer[r]) return fail(TDX_ERR_INVALID, "tdx_comm_allreduce: not all peers are connected");
+        a.peer[r] = reinterpret_cast<CommHeader*>(ctx->comm_peer[r]);
+    }
+    a.vals = vals; a.count = count; a.rank = ctx->rank; a.world = ctx->world;
+    ctx->red_seq += 1;
+    a.seq = ctx->red_seq;
+    DeviceGuard guard(ctx->device);
+    ctx->launches += 1;
+    comm_allreduce_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(a);
+    return cuda_fail((int)cudaGetLastError(), "tdx_comm_allreduce");
+}
+
+int tdx_comm_error(tdx_ctx* ctx, int* error_out, void* stream) {
+    if (!ctx || !ctx->comm_local || !error_out) return fail(TDX_ERR_INVALID, "tdx_comm_error: no comm block");
+    DeviceGuard guard(ctx->device);
+    unsigned long long v = 0;
+    cudaError_t e = cudaMemcpyAsync(&v, &reinterpret_cast<CommHeader*>(ctx->comm_local)->error, sizeof(v),
+                                    cudaMemcpyDeviceToHost, (cudaStream_t)stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize((cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail((int)e, "tdx_comm_error");
+    *error_out = (int)v;
+    return TDX_OK;
 }
 
 int tdx_ek0_attempt_step(tdx_ctx* ctx, const tdx_step_args* args, const void* mean_in, const void* Cl_in,

@@ -178,8 +178,8 @@ __device__ __forceinline__ void fetch_ext(const Plan<T, NEXT>& pl, const At& at,
         T v = (T)0;
         const int src = pl.src[s];
         if (src == SRC_MEAN) v = at(pl.idx[s]);
-        else if (src == SRC_LO) v = __ldg(halo_lo + pl.idx[s]);
-        else if (src == SRC_HI) v = __ldg(halo_hi + pl.idx[s]);
+        else if (src == SRC_LO) v = __ldcg(halo_lo + pl.idx[s]);   // L2 only: written by a peer GPU
+        else if (src == SRC_HI) v = __ldcg(halo_hi + pl.idx[s]);
         else if (src == SRC_CONST) v = pl.cval[s];
         ext[s] = v;
     }
@@ -525,6 +525,64 @@ __device__ __forceinline__ void grid_sum(double v, double* s_red, double* partia
             *ticket = 0u;
         }
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Peer-memory exchange (NVLink): per-rank device block, mapped by the neighbours through CUDA IPC.
+// ---------------------------------------------------------------------------------------------
+constexpr int kMaxWorld = 16;
+
+struct CommHeader {
+    unsigned long long halo_flag_lo[2];              // sequence number of the halo the LOWER neighbour delivered (per parity)
+    unsigned long long halo_flag_hi[2];
+    unsigned long long red_flag[2][kMaxWorld];       // per parity, per source rank
+    double red_val[2][kMaxWorld][4];
+    unsigned long long error;                        // a flag wait timed out
+    unsigned long long pad[5];
+};
+static_assert(sizeof(CommHeader) % 16 == 0, "halo storage behind the header must stay 16-byte aligned");
+
+struct CommWait {                                    // what a step kernel has to wait for before it reads halos
+    const unsigned long long* flag_lo;
+    const unsigned long long* flag_hi;
+    unsigned long long seq;
+    unsigned long long* error;
+};
+
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// spin until *flag >= seq; gives up after ~4 s (sets *error) so that a dead peer cannot hang the GPU
+__device__ __forceinline__ void spin_until(const unsigned long long* flag, unsigned long long seq,
+                                           unsigned long long* error) {
+    if (flag == nullptr) return;
+    const unsigned long long t0 = global_timer_ns();
+    while (ld_acquire_sys(flag) < seq) {
+        if (global_timer_ns() - t0 > 4000000000ull) {
+            if (error) *error = 1ull;
+            break;
+        }
+        __nanosleep(100);
+    }
+}
+// one thread per CTA waits, the barrier releases the rest
+__device__ __forceinline__ void cta_wait_halos(const CommWait& w) {
+    if (w.flag_lo == nullptr && w.flag_hi == nullptr) return;
+    if (threadIdx.x == 0) {
+        spin_until(w.flag_lo, w.seq, w.error);
+        spin_until(w.flag_hi, w.seq, w.error);
+    }
+    __syncthreads();
 }
 
 }  // namespace tdx

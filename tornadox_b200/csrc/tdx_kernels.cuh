@@ -114,6 +114,7 @@ struct DekArgs {
     double* out_sum;
     unsigned int num_tiles, tiles_x;   // num_tiles = number of tiles THIS launch processes (both ranges)
     TileRanges ranges;
+    CommWait wait;                     // peer-memory halos: flags to wait for (null: nothing to wait for)
 };
 
 template <typename T, int N>
@@ -172,6 +173,7 @@ __global__ void __launch_bounds__(kThreads, TDX_MIN_BLOCKS) dek1_kernel(const __
         return bulk;
     };
 
+    cta_wait_halos(a.wait);
     unsigned tile = blockIdx.x;
     unsigned phase_bits = 0u;          // parity of each slot's mbarrier
     double ratio_sq_acc = 0.0;
@@ -329,6 +331,7 @@ struct Ek0Args {
     double* out_sum;
     unsigned int num_tiles, tiles_x;
     TileRanges ranges;
+    CommWait wait;
     int reverse;             // walk the tiles backwards (sweep B re-reads what sweep A touched last: L2 reuse)
 };
 
@@ -346,6 +349,7 @@ __global__ void __launch_bounds__(kThreads, 3) ek0_sweep_kernel(const __grid_con
     const Geo& g = a.g;
     const Consts<T, N>& c = a.c;
 
+    cta_wait_halos(a.wait);
     T K[N];
     if (kUpdate) {
 #pragma unroll
@@ -477,6 +481,39 @@ __global__ void pack_halo_kernel(const __grid_constant__ PackArgs<T, N> a) {
             a.edge_last[field * a.n_last + jj] = at((long long)field * a.g.npts + (a.g.npts - a.n_last + jj));
         }
     }
+}
+
+// Peer variant: CTA 0 delivers the shard's first rows/points into the LOWER neighbour's hi-halo buffer, CTA 1 the
+// last ones into the UPPER neighbour's lo-halo buffer, then raises that neighbour's flag to ``seq``.
+template <typename T, int N>
+struct PackPeerArgs {
+    Geo g;
+    Consts<T, N> c;
+    const T* mean_in;
+    T* dst_lower;                    // lower neighbour's halo_hi[parity] (mapped), or null
+    T* dst_upper;                    // upper neighbour's halo_lo[parity] (mapped), or null
+    unsigned long long* flag_lower;  // lower neighbour's halo_flag_hi[parity]
+    unsigned long long* flag_upper;  // upper neighbour's halo_flag_lo[parity]
+    unsigned long long seq;
+    int n_first, n_last;
+};
+
+template <typename T, int N>
+__global__ void __launch_bounds__(1024) pack_halo_peer_kernel(const __grid_constant__ PackPeerArgs<T, N> a) {
+    MeanAt<T, N> at{a.mean_in, a.g.d, &a.c};
+    const bool lower = blockIdx.x == 0;
+    T* dst = lower ? a.dst_lower : a.dst_upper;
+    if (dst == nullptr) return;
+    const int per_field = lower ? a.n_first : a.n_last;
+    const long long start = lower ? 0 : (a.g.npts - a.n_last);
+    const int total = a.g.nf * per_field;
+    for (int i = threadIdx.x; i < total; i += blockDim.x) {
+        const int field = i / per_field, j = i - field * per_field;
+        dst[i] = at((long long)field * a.g.npts + start + j);
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) st_release_sys(lower ? a.flag_lower : a.flag_upper, a.seq);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -19,6 +19,7 @@ struct Workspace {
     void* mid;               // Ek0Mid<T, N>
     int reserve_ctas;        // CTAs left free on the device (room for a concurrent NCCL kernel)
     bool has_lo, has_hi;     // the shard has a lower / upper neighbour (halo buffers exist)
+    CommWait wait;           // peer-memory halos: flags the kernel must see before it reads them (null otherwise)
 };
 
 // Which tiles does a launch process?  all / interior (no halo reads) / rim (TDX_STEP_TILES_*).
@@ -50,6 +51,9 @@ struct Ops {
                  const void* halo_hi, const Workspace&, double* out_sum, cudaStream_t);
     int (*pack)(const Geo&, const StepHost&, const void* mean_in, void* edge_first, void* edge_last, int n_first,
                 int n_last, cudaStream_t);
+    int (*pack_peer)(const Geo&, const StepHost&, const void* mean_in, void* dst_lower, void* dst_upper,
+                     unsigned long long* flag_lower, unsigned long long* flag_upper, unsigned long long seq,
+                     int n_first, int n_last, cudaStream_t);
 };
 
 struct EvalOps {
@@ -146,6 +150,7 @@ struct Launch {
             const unsigned tiles_y = (unsigned)((g.rows + Shape::TR - 1) / Shape::TR);
             a.ranges = tile_ranges(h.flags, a.tiles_x, tiles_y, ws.has_lo, ws.has_hi, g.kind == IVP_FHN2D);
             a.num_tiles = a.ranges.n0 + a.ranges.n1;
+            a.wait = ws.wait;
             if (a.num_tiles == 0u) {
                 if (h.want_norm) TDX_CUDA_TRY(cudaMemsetAsync(out_sum, 0, sizeof(double), st));
                 return 0;
@@ -184,6 +189,7 @@ struct Launch {
             const unsigned tiles_y = (unsigned)((g.rows + Shape::TR - 1) / Shape::TR);
             a.ranges = tile_ranges(flags, a.tiles_x, tiles_y, ws.has_lo, ws.has_hi, g.kind == IVP_FHN2D);
             a.num_tiles = a.ranges.n0 + a.ranges.n1;
+            a.wait = ws.wait;
             a.reverse = kUpdate ? 1 : 0;
             if (a.num_tiles == 0u) {
                 if (a.out_sum && (!kUpdate || a.c.want_norm)) TDX_CUDA_TRY(cudaMemsetAsync(a.out_sum, 0, sizeof(double), st));
@@ -239,6 +245,24 @@ struct Launch {
         return (int)cudaGetLastError();
     }
 
+    static int pack_peer(const Geo& g, const StepHost& h, const void* mean_in, void* dst_lower, void* dst_upper,
+                         unsigned long long* flag_lower, unsigned long long* flag_upper, unsigned long long seq,
+                         int n_first, int n_last, cudaStream_t st) {
+        PackPeerArgs<T, N> a;
+        a.g = g;
+        a.c = make_consts<T, N>(h);
+        a.mean_in = (const T*)mean_in;
+        a.dst_lower = (T*)dst_lower;
+        a.dst_upper = (T*)dst_upper;
+        a.flag_lower = flag_lower;
+        a.flag_upper = flag_upper;
+        a.seq = seq;
+        a.n_first = n_first;
+        a.n_last = n_last;
+        pack_halo_peer_kernel<T, N><<<2, 1024, 0, st>>>(a);
+        return (int)cudaGetLastError();
+    }
+
     static Ops ops() {
         Ops o{};
         o.dek1 = &dek1;
@@ -246,6 +270,7 @@ struct Launch {
         o.ek0_mid = &ek0_mid;
         o.ek0_b = &ek0_b;
         o.pack = &pack;
+        o.pack_peer = &pack_peer;
         return o;
     }
 };

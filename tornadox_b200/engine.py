@@ -105,7 +105,7 @@ def _ptr(t):
 class StepEngine:
     """One GPU's share of the filter step for a given (vector field, nu, dtype)."""
 
-    def __init__(self, spec, nu, dtype=torch.float64, device=None, group=None, rank=0, world=1):
+    def __init__(self, spec, nu, dtype=torch.float64, device=None, group=None, rank=0, world=1, peer_memory=True):
         if not torch.cuda.is_available():
             raise _lib.TornadoxB200Error(
                 "tornadox_b200 needs a CUDA device (sm_100a); there is no CPU fallback for the filter step"
@@ -144,9 +144,11 @@ class StepEngine:
         # [0:2] norm sums (interior, rim launches), [2] EK0 z^2 sum
         self._scalar_ring = torch.zeros((16, 4), dtype=torch.float64, device=self.device)
         self._ring_pos = 0
-        # interior/rim split with the exchange on a second stream: NCCL's own kernels cannot be scheduled while the
-        # persistent step kernel holds every SM, so this only pays off with the SM-free peer-memory exchange
+        # interior/rim split with the NCCL exchange on a second stream: NCCL's own kernels cannot be scheduled while
+        # the persistent step kernel holds every SM, so this does not pay off; kept for experiments only
         self.overlap = False
+        # default multi-GPU path: halos and scalar sums travel through NVLink peer memory written by our own kernels
+        self.peer = False
         self._comm_stream = torch.cuda.Stream(device=self.device) if world > 1 else None
         self.exchanger = None
         if world > 1:
@@ -155,6 +157,38 @@ class StepEngine:
             self._edge_first = torch.empty(self._edge_sizes()[0], dtype=dtype, device=self.device)
             self._edge_last = torch.empty(self._edge_sizes()[1], dtype=dtype, device=self.device)
             self.exchanger = HaloExchanger(group, rank, world, cyclic, self.halo_lo_n, self.halo_hi_n, dtype, self.device)
+            if peer_memory:
+                self._connect_peers(cyclic)
+
+    def _connect_peers(self, cyclic):
+        """Map every rank's exchange block through CUDA IPC (tdx_comm_init / tdx_comm_connect)."""
+        import torch.distributed as dist
+
+        rank, world = self.rank, self.world
+        lower = (rank - 1) % world if (cyclic or rank > 0) else -1
+        upper = (rank + 1) % world if (cyclic or rank < world - 1) else -1
+        handle = (ctypes.c_ubyte * _lib.TDX_COMM_HANDLE_BYTES)()
+        _lib.check(self.lib.tdx_comm_init(self.handle, rank, world, lower, upper, ctypes.cast(handle, ctypes.c_void_p)),
+                   _lib.TornadoxB200Error)
+        handles = [None] * world
+        dist.all_gather_object(handles, bytes(handle), group=self.group)
+        for peer, raw in enumerate(handles):
+            if peer == rank:
+                continue
+            buf = (ctypes.c_ubyte * _lib.TDX_COMM_HANDLE_BYTES).from_buffer_copy(raw)
+            _lib.check(self.lib.tdx_comm_connect(self.handle, peer, ctypes.cast(buf, ctypes.c_void_p)),
+                       _lib.TornadoxB200Error)
+        dist.barrier(group=self.group)
+        self.peer = True
+
+    def check_peers(self):
+        """Raise if a flag wait timed out (a neighbouring rank died or diverged)."""
+        if not self.peer:
+            return
+        err = ctypes.c_int(0)
+        _lib.check(self.lib.tdx_comm_error(self.handle, ctypes.byref(err), self._stream()))
+        if err.value:
+            raise _lib.TornadoxB200Error("peer-memory exchange timed out: a neighbouring rank did not deliver its halo")
 
     def __del__(self):
         try:
@@ -267,6 +301,19 @@ class StepEngine:
         call = self.lib.tdx_dek1_attempt_step
         bufs = (_ptr(mean), _ptr(sc), _ptr(mean_out), _ptr(sc_out), _ptr(err), _ptr(ref))
         scal = self._next_scalars()
+        if self.world > 1 and self.peer:
+            # pack kernel stores the halos straight into the neighbours' buffers; interior tiles run meanwhile,
+            # the rim launch spins on the arrival flags; the scalar sum is a one-CTA peer-memory all-reduce
+            st = self._stream()
+            _lib.check(self.lib.tdx_comm_pack_halo(self.handle, float(dt), _ptr(mean), st))
+            a_int = self._args(t, dt, abstol, reltol, base_flags | _lib.TDX_STEP_TILES_INTERIOR)
+            _lib.check(call(self.handle, ctypes.byref(a_int), *bufs, None, None, _ptr(scal[0:1]), st))
+            a_rim = self._args(t, dt, abstol, reltol, base_flags | _lib.TDX_STEP_TILES_RIM | _lib.TDX_STEP_COMM_HALO)
+            _lib.check(call(self.handle, ctypes.byref(a_rim), *bufs, None, None, _ptr(scal[1:2]), st))
+            sq = scal[0:2]
+            if want_norm:
+                _lib.check(self.lib.tdx_comm_allreduce(self.handle, _ptr(sq), 2, st))
+            return mean_out, sc_out, err, ref, sq
         if self.world > 1 and self.overlap:
             # interior tiles run while the halos travel; the rim tiles follow once they have arrived
             halo_lo, halo_hi, ready = self._halos_overlapped(dt, mean)
@@ -303,6 +350,23 @@ class StepEngine:
         st = self._stream()
         want_norm = abstol != 0.0 or reltol != 0.0
         args = self._args(t, dt, abstol, reltol)
+        if self.world > 1 and self.peer:
+            comm = _lib.TDX_STEP_COMM_HALO
+            _lib.check(self.lib.tdx_comm_pack_halo(self.handle, float(dt), _ptr(mean), st))
+            a_int = self._args(t, dt, abstol, reltol, _lib.TDX_STEP_TILES_INTERIOR)
+            _lib.check(self.lib.tdx_ek0_sweep_a(self.handle, ctypes.byref(a_int), _ptr(mean), None, None, _ptr(zsq[0:1]), st))
+            a_rim = self._args(t, dt, abstol, reltol, _lib.TDX_STEP_TILES_RIM | comm)
+            _lib.check(self.lib.tdx_ek0_sweep_a(self.handle, ctypes.byref(a_rim), _ptr(mean), None, None, _ptr(zsq[1:2]), st))
+            _lib.check(self.lib.tdx_comm_allreduce(self.handle, _ptr(zsq), 2, st))
+            a_mid = self._args(t, dt, abstol, reltol, _lib.TDX_STEP_TWO_PARTS)
+            _lib.check(self.lib.tdx_ek0_mid(self.handle, ctypes.byref(a_mid), _ptr(Cl), _ptr(zsq), self.d_global,
+                                            _ptr(Cl_out), _ptr(err), st))
+            a_b = self._args(t, dt, abstol, reltol, comm)
+            _lib.check(self.lib.tdx_ek0_sweep_b(self.handle, ctypes.byref(a_b), _ptr(mean), _ptr(mean_out), _ptr(ref),
+                                                None, None, _ptr(itol), st))
+            if want_norm:
+                _lib.check(self.lib.tdx_comm_allreduce(self.handle, _ptr(itol), 1, st))
+            return mean_out, Cl_out, err, ref, itol
         if self.world > 1 and self.overlap:
             halo_lo, halo_hi, ready = self._halos_overlapped(dt, mean)
             a_int = self._args(t, dt, abstol, reltol, _lib.TDX_STEP_TILES_INTERIOR)
