@@ -163,11 +163,15 @@ int tdx_ek0_attempt_step(tdx_ctx* ctx, const tdx_step_args* args, const void* me
  *   tdx_comm_init     allocate the block; ``handle_out`` receives TDX_COMM_HANDLE_BYTES to all-gather
  *   tdx_comm_connect  map rank ``peer``'s block from its handle (call for every peer, then barrier)
  *   tdx_comm_pack_halo   predicted edge state -> neighbours' halo buffers (+ flags); replaces tdx_pack_halo + send/recv
- *   step calls with TDX_STEP_COMM_HALO read those buffers (halo pointers are ignored)
+ *   step calls with TDX_STEP_COMM_HALO read those buffers (halo pointers are ignored); in a single launch the tiles
+ *                     that need them are processed last and only then is the arrival flag awaited
+ *   step calls with TDX_STEP_COMM_REDUCE return the GLOBAL sum (the last CTA exchanges the partial sums)
  *   tdx_comm_allreduce   vals[0..count) summed over ranks in place (count <= 4), device scalars
  *   tdx_comm_error    non-zero after a flag wait timed out (a peer died or diverged) */
 #define TDX_COMM_HANDLE_BYTES 64
 #define TDX_STEP_COMM_HALO 16u
+/* all-reduce the call's scalar result over the ranks inside the kernel epilogue (needs tdx_comm_connect to all ranks) */
+#define TDX_STEP_COMM_REDUCE 32u
 int tdx_comm_init(tdx_ctx* ctx, int rank, int world, int lower_rank /* -1: none */, int upper_rank /* -1: none */,
                   void* handle_out);
 int tdx_comm_connect(tdx_ctx* ctx, int peer, const void* handle);

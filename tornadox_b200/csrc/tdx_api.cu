@@ -397,7 +397,14 @@ static StepHost make_step(const tdx_ctx* ctx, const tdx_step_args* a) {
 static Workspace make_ws(const tdx_ctx* ctx, unsigned flags = 0u) {
     const bool second = (flags & 6u) == TDX_STEP_TILES_RIM;
     Workspace ws{ctx->partials + (second ? ctx->partials_cap : 0), ctx->ticket + (second ? 1 : 0), ctx->mid, 0,
-                 ctx->halo_lo > 0, ctx->halo_hi > 0, CommWait{nullptr, nullptr, 0ull, nullptr}};
+                 ctx->halo_lo > 0, ctx->halo_hi > 0, CommWait{nullptr, nullptr, 0ull, nullptr}, CommReduce{}};
+    if ((flags & TDX_STEP_COMM_REDUCE) && ctx->comm_local) {
+        ws.reduce.local = reinterpret_cast<CommHeader*>(ctx->comm_local);
+        for (int r = 0; r < ctx->world; ++r) ws.reduce.peer[r] = reinterpret_cast<CommHeader*>(ctx->comm_peer[r]);
+        ws.reduce.rank = ctx->rank;
+        ws.reduce.world = ctx->world;
+        ws.reduce.seq = ctx->red_seq;      // the caller has already advanced it for this launch
+    }
     if ((flags & TDX_STEP_COMM_HALO) && ctx->comm_local && (flags & 6u) != TDX_STEP_TILES_INTERIOR) {
         CommHeader* hdr = reinterpret_cast<CommHeader*>(ctx->comm_local);
         const int parity = (int)(ctx->halo_seq & 1ull);
@@ -415,6 +422,18 @@ static void resolve_halos(const tdx_ctx* ctx, unsigned flags, const void*& lo, c
     const int parity = (int)(ctx->halo_seq & 1ull);
     lo = ctx->halo_lo > 0 ? comm_halo(ctx, ctx->comm_local, 0, parity) : nullptr;
     hi = ctx->halo_hi > 0 ? comm_halo(ctx, ctx->comm_local, 1, parity) : nullptr;
+}
+
+// A launch that all-reduces its scalar in the epilogue consumes one reduction sequence number.
+static int comm_reduce_begin(tdx_ctx* ctx, unsigned flags, bool produces_sum, const char* where) {
+    if (!(flags & TDX_STEP_COMM_REDUCE) || !produces_sum) return TDX_OK;
+    if (!ctx->comm_local) return fail(TDX_ERR_INVALID, std::string(where) + ": TDX_STEP_COMM_REDUCE needs tdx_comm_init");
+    if ((flags & 6u) == TDX_STEP_TILES_INTERIOR || (flags & 6u) == TDX_STEP_TILES_RIM)
+        return fail(TDX_ERR_INVALID, std::string(where) + ": TDX_STEP_COMM_REDUCE cannot be combined with a partial tile range");
+    for (int r = 0; r < ctx->world; ++r)
+        if (!ctx->comm_peer[r]) return fail(TDX_ERR_INVALID, std::string(where) + ": not all peers are connected");
+    ctx->red_seq += 1;
+    return TDX_OK;
 }
 
 static int check_dt(const tdx_step_args* a, const char* where) {
@@ -489,6 +508,7 @@ int tdx_dek1_attempt_step(tdx_ctx* ctx, const tdx_step_args* args, const void* m
     if ((rc = check_halos(ctx, halo_lo, halo_hi, "tdx_dek1_attempt_step", args->flags))) return rc;
     StepHost h = make_step(ctx, args);
     if (h.want_norm && !sq_norm_sum) return fail(TDX_ERR_INVALID, "tdx_dek1_attempt_step: sq_norm_sum is required with tolerances");
+    if ((rc = comm_reduce_begin(ctx, args->flags, h.want_norm != 0, "tdx_dek1_attempt_step"))) return rc;
     DeviceGuard guard(ctx->device);
     ctx->launches += 1;
     return cuda_fail(ctx->ops->dek1(ctx->geo, h, mean_in, sc_in, mean_out, sc_out, err_out, ref_out, halo_lo, halo_hi,
@@ -505,6 +525,7 @@ int tdx_ek0_sweep_a(tdx_ctx* ctx, const tdx_step_args* args, const void* mean_in
     if (!mean_in || !z_sq_sum) return fail(TDX_ERR_INVALID, "tdx_ek0_sweep_a: null buffer");
     if ((rc = check_halos(ctx, halo_lo, halo_hi, "tdx_ek0_sweep_a", args->flags))) return rc;
     StepHost h = make_step(ctx, args);
+    if ((rc = comm_reduce_begin(ctx, args->flags, true, "tdx_ek0_sweep_a"))) return rc;
     DeviceGuard guard(ctx->device);
     ctx->launches += 1;
     return cuda_fail(ctx->ops->ek0_a(ctx->geo, h, mean_in, halo_lo, halo_hi, make_ws(ctx, args->flags), z_sq_sum, (cudaStream_t)stream),
@@ -536,6 +557,7 @@ int tdx_ek0_sweep_b(tdx_ctx* ctx, const tdx_step_args* args, const void* mean_in
     if ((rc = check_halos(ctx, halo_lo, halo_hi, "tdx_ek0_sweep_b"))) return rc;
     StepHost h = make_step(ctx, args);
     if (h.want_norm && !sq_norm_sum) return fail(TDX_ERR_INVALID, "tdx_ek0_sweep_b: sq_norm_sum is required with tolerances");
+    if ((rc = comm_reduce_begin(ctx, args->flags, h.want_norm != 0, "tdx_ek0_sweep_b"))) return rc;
     DeviceGuard guard(ctx->device);
     ctx->launches += 1;
     return cuda_fail(ctx->ops->ek0_b(ctx->geo, h, mean_in, mean_out, ref_out, halo_lo, halo_hi, make_ws(ctx, args->flags & ~6u), sq_norm_sum,

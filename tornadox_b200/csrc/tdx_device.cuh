@@ -478,58 +478,7 @@ __device__ __forceinline__ void bulk_s2g(void* gmem_dst, const void* smem_src, u
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 
-// ---------------------------------------------------------------------------------------------
-// Deterministic grid-wide sum of one double per thread: warp shuffle -> smem -> per-CTA partial ->
-// last-arriving CTA adds the partials in a fixed order.
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ double warp_sum(double v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-}
-
-// The final value is sum * mult * (*mult_sqrt_ptr)^2 (the last two default to 1).
-__device__ __forceinline__ void grid_sum(double v, double* s_red, double* partials, unsigned int* ticket,
-                                         double* out, double mult = 1.0, const double* mult_sqrt_ptr = nullptr) {
-    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    v = warp_sum(v);
-    if (lane == 0) s_red[w] = v;
-    __syncthreads();
-    __shared__ bool s_last;
-    if (threadIdx.x == 0) {
-        double b = 0.0;
-#pragma unroll
-        for (int i = 0; i < kWarps; ++i) b += s_red[i];
-        partials[blockIdx.x] = b;
-        __threadfence();
-        const unsigned int t = atomicAdd(ticket, 1u);
-        s_last = (t == gridDim.x - 1);
-    }
-    __syncthreads();
-    if (s_last) {
-        __threadfence();
-        double acc = 0.0;
-        for (unsigned int i = threadIdx.x; i < gridDim.x; i += kThreads) acc += __ldcg(partials + i);
-        acc = warp_sum(acc);
-        if (lane == 0) s_red[w] = acc;
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            double b = 0.0;
-#pragma unroll
-            for (int i = 0; i < kWarps; ++i) b += s_red[i];
-            if (mult_sqrt_ptr) {
-                const double r = *mult_sqrt_ptr;
-                b *= r * r;
-            }
-            *out = b * mult;
-            *ticket = 0u;
-        }
-    }
-}
-
-// ---------------------------------------------------------------------------------------------
 // Peer-memory exchange (NVLink): per-rank device block, mapped by the neighbours through CUDA IPC.
-// ---------------------------------------------------------------------------------------------
 constexpr int kMaxWorld = 16;
 
 struct CommHeader {
@@ -547,6 +496,13 @@ struct CommWait {                                    // what a step kernel has t
     const unsigned long long* flag_hi;
     unsigned long long seq;
     unsigned long long* error;
+};
+
+struct CommReduce {                                  // fused all-reduce of the kernel's scalar result (world == 0: off)
+    CommHeader* local;
+    CommHeader* peer[kMaxWorld];
+    int rank, world;
+    unsigned long long seq;
 };
 
 __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
@@ -583,6 +539,86 @@ __device__ __forceinline__ void cta_wait_halos(const CommWait& w) {
         spin_until(w.flag_hi, w.seq, w.error);
     }
     __syncthreads();
+}
+
+// Sum ``v`` (held by thread 0 of ONE CTA) over all ranks in rank order through the peers' reduction slots.
+// Called by every thread of that CTA; returns the global sum in thread 0.
+__device__ __forceinline__ double cta_allreduce(double v, const CommReduce& cr, double* s_red) {
+    const int r = threadIdx.x;
+    const int parity = (int)(cr.seq & 1ull);
+    if (r == 0) s_red[0] = v;
+    __syncthreads();
+    if (r < cr.world) {
+        CommHeader* dst = cr.peer[r];
+        dst->red_val[parity][cr.rank][0] = s_red[0];
+        __threadfence_system();
+        st_release_sys(&dst->red_flag[parity][cr.rank], cr.seq);
+    }
+    __syncthreads();
+    if (r < cr.world) spin_until(&cr.local->red_flag[parity][r], cr.seq, &cr.local->error);
+    __syncthreads();
+    double acc = 0.0;
+    if (r == 0)
+        for (int k = 0; k < cr.world; ++k) acc += *((volatile double*)&cr.local->red_val[parity][k][0]);
+    return acc;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Deterministic grid-wide sum of one double per thread: warp shuffle -> smem -> per-CTA partial ->
+// last-arriving CTA adds the partials in a fixed order.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// The final value is sum * mult * (*mult_sqrt_ptr)^2 (the last two default to 1).
+// With ``cr`` (world > 0) the last CTA then all-reduces the value over the ranks through peer memory.
+__device__ __forceinline__ void grid_sum(double v, double* s_red, double* partials, unsigned int* ticket,
+                                         double* out, double mult = 1.0, const double* mult_sqrt_ptr = nullptr,
+                                         const CommReduce* cr = nullptr) {
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    v = warp_sum(v);
+    if (lane == 0) s_red[w] = v;
+    __syncthreads();
+    __shared__ bool s_last;
+    if (threadIdx.x == 0) {
+        double b = 0.0;
+#pragma unroll
+        for (int i = 0; i < kWarps; ++i) b += s_red[i];
+        partials[blockIdx.x] = b;
+        __threadfence();
+        const unsigned int t = atomicAdd(ticket, 1u);
+        s_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (s_last) {
+        __threadfence();
+        double acc = 0.0;
+        for (unsigned int i = threadIdx.x; i < gridDim.x; i += kThreads) acc += __ldcg(partials + i);
+        acc = warp_sum(acc);
+        if (lane == 0) s_red[w] = acc;
+        __syncthreads();
+        double b = 0.0;
+        if (threadIdx.x == 0) {
+#pragma unroll
+            for (int i = 0; i < kWarps; ++i) b += s_red[i];
+            if (mult_sqrt_ptr) {
+                const double r = *mult_sqrt_ptr;
+                b *= r * r;
+            }
+            b *= mult;
+        }
+        if (cr != nullptr && cr->world > 0) {
+            __syncthreads();
+            b = cta_allreduce(b, *cr, s_red);
+        }
+        if (threadIdx.x == 0) {
+            *out = b;
+            *ticket = 0u;
+        }
+    }
 }
 
 }  // namespace tdx

@@ -44,9 +44,13 @@ struct SmemLayout {
 };
 
 // A launch processes the tiles [b0, b0 + n0) followed by [b1, b1 + n1) (interior / rim split for multi-GPU overlap).
+// Tiles from virtual index ``wait_from`` on read the halo buffers: a CTA waits for the arrival flags when it gets there.
 struct TileRanges {
-    unsigned int b0, n0, b1, n1;
-    __device__ __forceinline__ unsigned tile(unsigned v) const { return v < n0 ? b0 + v : b1 + (v - n0); }
+    unsigned int b0, n0, b1, n1, b2, n2;
+    unsigned int wait_from;
+    __device__ __forceinline__ unsigned tile(unsigned v) const {
+        return v < n0 ? b0 + v : (v < n0 + n1 ? b1 + (v - n0) : b2 + (v - n0 - n1));
+    }
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -115,6 +119,7 @@ struct DekArgs {
     unsigned int num_tiles, tiles_x;   // num_tiles = number of tiles THIS launch processes (both ranges)
     TileRanges ranges;
     CommWait wait;                     // peer-memory halos: flags to wait for (null: nothing to wait for)
+    CommReduce reduce;                 // fused all-reduce of the norm sum (world == 0: off)
 };
 
 template <typename T, int N>
@@ -173,7 +178,7 @@ __global__ void __launch_bounds__(kThreads, TDX_MIN_BLOCKS) dek1_kernel(const __
         return bulk;
     };
 
-    cta_wait_halos(a.wait);
+    bool halos_ready = false;          // CTA-uniform: the arrival flags have been seen
     unsigned tile = blockIdx.x;
     unsigned phase_bits = 0u;          // parity of each slot's mbarrier
     double ratio_sq_acc = 0.0;
@@ -190,6 +195,10 @@ __global__ void __launch_bounds__(kThreads, TDX_MIN_BLOCKS) dek1_kernel(const __
         const int slot = it & 1;
         T* my_sc = s_sc0 + slot * SC_STRIDE + w * 32 * STRIDE;
         T* s_at = s_at0 + slot * AT_STRIDE;
+        if (!halos_ready && tile >= a.ranges.wait_from) {
+            cta_wait_halos(a.wait);
+            halos_ready = true;
+        }
         if (!TDX_PREFETCH_MEAN) front_load<IVP, T, N>(g, c, a.mean_in, a.halo_lo, a.halo_hi, co, fr);
 
         // (1) predict + vector field of the current tile (its loads were issued one iteration ago)
@@ -303,7 +312,7 @@ __global__ void __launch_bounds__(kThreads, TDX_MIN_BLOCKS) dek1_kernel(const __
         cur_bulk = next_bulk;
     }
 
-    if (c.want_norm) grid_sum(ratio_sq_acc, s_red, a.partials, a.ticket, a.out_sum);
+    if (c.want_norm) grid_sum(ratio_sq_acc, s_red, a.partials, a.ticket, a.out_sum, 1.0, nullptr, &a.reduce);
     if (lane == 0) bulk_wait_read0();
 }
 
@@ -332,6 +341,7 @@ struct Ek0Args {
     unsigned int num_tiles, tiles_x;
     TileRanges ranges;
     CommWait wait;
+    CommReduce reduce;
     int reverse;             // walk the tiles backwards (sweep B re-reads what sweep A touched last: L2 reuse)
 };
 
@@ -349,7 +359,6 @@ __global__ void __launch_bounds__(kThreads, 3) ek0_sweep_kernel(const __grid_con
     const Geo& g = a.g;
     const Consts<T, N>& c = a.c;
 
-    cta_wait_halos(a.wait);
     T K[N];
     if (kUpdate) {
 #pragma unroll
@@ -357,11 +366,22 @@ __global__ void __launch_bounds__(kThreads, 3) ek0_sweep_kernel(const __grid_con
     }
     auto tile_of = [&](unsigned i) { return a.ranges.tile(a.reverse ? (a.num_tiles - 1u - i) : i); };
 
+    // virtual index of the i-th tile this launch walks (reversed for sweep B) and whether it reads halos
+    auto vidx = [&](unsigned i) { return a.reverse ? (a.num_tiles - 1u - i) : i; };
+    bool halos_ready = false;
+    auto wait_if_needed = [&](unsigned i) {
+        if (!halos_ready && vidx(i) >= a.ranges.wait_from) {
+            cta_wait_halos(a.wait);
+            halos_ready = true;
+        }
+    };
+
     unsigned i = blockIdx.x;
     double acc = 0.0;
     Coord co{};
     FrontRegs<IVP, T, N> fr;
     if (i < a.num_tiles) {
+        wait_if_needed(i);
         co = tile_coord<Shape>(g, tile_of(i), a.tiles_x);
         front_load<IVP, T, N>(g, c, a.mean_in, a.halo_lo, a.halo_hi, co, fr);
     }
@@ -371,6 +391,7 @@ __global__ void __launch_bounds__(kThreads, 3) ek0_sweep_kernel(const __grid_con
         const Coord cur = co;
         i += gridDim.x;
         if (i < a.num_tiles) {
+            wait_if_needed(i);
             co = tile_coord<Shape>(g, tile_of(i), a.tiles_x);
             front_load<IVP, T, N>(g, c, a.mean_in, a.halo_lo, a.halo_hi, co, fr);
         }
@@ -398,10 +419,10 @@ __global__ void __launch_bounds__(kThreads, 3) ek0_sweep_kernel(const __grid_con
         }
     }
     if (!kUpdate) {
-        grid_sum(acc, s_red, a.partials, a.ticket, a.out_sum);
+        grid_sum(acc, s_red, a.partials, a.ticket, a.out_sum, 1.0, nullptr, &a.reduce);
     } else if (c.want_norm) {
         // sum_i (dt err / tol_i)^2 = (dt err)^2 sum_i 1 / tol_i^2     step.py:101-104 with a scalar error estimate
-        grid_sum(acc, s_red, a.partials, a.ticket, a.out_sum, (double)c.dt * (double)c.dt, &a.mid->err);
+        grid_sum(acc, s_red, a.partials, a.ticket, a.out_sum, (double)c.dt * (double)c.dt, &a.mid->err, &a.reduce);
     }
 }
 

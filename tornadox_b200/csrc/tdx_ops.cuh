@@ -20,23 +20,26 @@ struct Workspace {
     int reserve_ctas;        // CTAs left free on the device (room for a concurrent NCCL kernel)
     bool has_lo, has_hi;     // the shard has a lower / upper neighbour (halo buffers exist)
     CommWait wait;           // peer-memory halos: flags the kernel must see before it reads them (null otherwise)
+    CommReduce reduce;       // fused all-reduce of the scalar result (world == 0: off)
 };
 
 // Which tiles does a launch process?  all / interior (no halo reads) / rim (TDX_STEP_TILES_*).
 // Rim = the first / last tile row (2-d grids) or the first / last tile (chains) on sides that have a neighbour.
 inline TileRanges tile_ranges(unsigned flags, unsigned tiles_x, unsigned tiles_y, bool has_lo, bool has_hi,
-                              bool row_sharded) {
+                              bool row_sharded, bool waits) {
     const unsigned total = tiles_x * tiles_y;
     const unsigned want = flags & 6u;
-    if (want == 0u || want == 6u) return TileRanges{0u, total, 0u, 0u};
     const unsigned edge = row_sharded ? tiles_x : 1u;
     unsigned lo = has_lo ? edge : 0u, hi = has_hi ? edge : 0u;
     if (lo + hi > total) {   // a single tile (row) touches both halos
         lo = total;
         hi = 0u;
     }
-    if (want == 4u) return TileRanges{0u, lo, total - hi, hi};       // rim
-    return TileRanges{lo, total - lo - hi, 0u, 0u};                   // interior
+    if (want == 4u) return TileRanges{0u, lo, total - hi, hi, 0u, 0u, 0u};                 // rim only
+    if (want == 2u) return TileRanges{lo, total - lo - hi, 0u, 0u, 0u, 0u, 0xffffffffu};   // interior only
+    if (!waits) return TileRanges{0u, total, 0u, 0u, 0u, 0u, 0u};                          // everything, natural order
+    // everything in one launch, the halo-reading tiles last; the CTA awaits the arrival flags when it reaches them
+    return TileRanges{lo, total - lo - hi, 0u, lo, total - hi, hi, total - lo - hi};
 }
 
 struct Ops {
@@ -148,9 +151,11 @@ struct Launch {
             constexpr auto kern = dek1_kernel<IVP, T, N>;
             a.tiles_x = (unsigned)((g.cols + Shape::TC - 1) / Shape::TC);
             const unsigned tiles_y = (unsigned)((g.rows + Shape::TR - 1) / Shape::TR);
-            a.ranges = tile_ranges(h.flags, a.tiles_x, tiles_y, ws.has_lo, ws.has_hi, g.kind == IVP_FHN2D);
-            a.num_tiles = a.ranges.n0 + a.ranges.n1;
+            a.ranges = tile_ranges(h.flags, a.tiles_x, tiles_y, ws.has_lo, ws.has_hi, g.kind == IVP_FHN2D,
+                                   ws.wait.flag_lo != nullptr || ws.wait.flag_hi != nullptr);
+            a.num_tiles = a.ranges.n0 + a.ranges.n1 + a.ranges.n2;
             a.wait = ws.wait;
+            a.reduce = ws.reduce;
             if (a.num_tiles == 0u) {
                 if (h.want_norm) TDX_CUDA_TRY(cudaMemsetAsync(out_sum, 0, sizeof(double), st));
                 return 0;
@@ -187,9 +192,11 @@ struct Launch {
             constexpr auto kern = ek0_sweep_kernel<IVP, T, N, kUpdate>;
             a.tiles_x = (unsigned)((g.cols + Shape::TC - 1) / Shape::TC);
             const unsigned tiles_y = (unsigned)((g.rows + Shape::TR - 1) / Shape::TR);
-            a.ranges = tile_ranges(flags, a.tiles_x, tiles_y, ws.has_lo, ws.has_hi, g.kind == IVP_FHN2D);
-            a.num_tiles = a.ranges.n0 + a.ranges.n1;
+            a.ranges = tile_ranges(flags, a.tiles_x, tiles_y, ws.has_lo, ws.has_hi, g.kind == IVP_FHN2D,
+                                   ws.wait.flag_lo != nullptr || ws.wait.flag_hi != nullptr);
+            a.num_tiles = a.ranges.n0 + a.ranges.n1 + a.ranges.n2;
             a.wait = ws.wait;
+            a.reduce = ws.reduce;
             a.reverse = kUpdate ? 1 : 0;
             if (a.num_tiles == 0u) {
                 if (a.out_sum && (!kUpdate || a.c.want_norm)) TDX_CUDA_TRY(cudaMemsetAsync(a.out_sum, 0, sizeof(double), st));

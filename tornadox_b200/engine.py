@@ -302,17 +302,14 @@ class StepEngine:
         bufs = (_ptr(mean), _ptr(sc), _ptr(mean_out), _ptr(sc_out), _ptr(err), _ptr(ref))
         scal = self._next_scalars()
         if self.world > 1 and self.peer:
-            # pack kernel stores the halos straight into the neighbours' buffers; interior tiles run meanwhile,
-            # the rim launch spins on the arrival flags; the scalar sum is a one-CTA peer-memory all-reduce
+            # two launches per attempt, no NCCL: the pack kernel stores the halos straight into the neighbours'
+            # buffers; the step kernel does the interior tiles first, awaits the arrival flags only when it reaches
+            # the rim tiles, and its last CTA all-reduces the norm sum through peer memory
             st = self._stream()
             _lib.check(self.lib.tdx_comm_pack_halo(self.handle, float(dt), _ptr(mean), st))
-            a_int = self._args(t, dt, abstol, reltol, base_flags | _lib.TDX_STEP_TILES_INTERIOR)
-            _lib.check(call(self.handle, ctypes.byref(a_int), *bufs, None, None, _ptr(scal[0:1]), st))
-            a_rim = self._args(t, dt, abstol, reltol, base_flags | _lib.TDX_STEP_TILES_RIM | _lib.TDX_STEP_COMM_HALO)
-            _lib.check(call(self.handle, ctypes.byref(a_rim), *bufs, None, None, _ptr(scal[1:2]), st))
-            sq = scal[0:2]
-            if want_norm:
-                _lib.check(self.lib.tdx_comm_allreduce(self.handle, _ptr(sq), 2, st))
+            a_all = self._args(t, dt, abstol, reltol, base_flags | _lib.TDX_STEP_COMM_HALO | _lib.TDX_STEP_COMM_REDUCE)
+            sq = scal[0:1]
+            _lib.check(call(self.handle, ctypes.byref(a_all), *bufs, None, None, _ptr(sq), st))
             return mean_out, sc_out, err, ref, sq
         if self.world > 1 and self.overlap:
             # interior tiles run while the halos travel; the rim tiles follow once they have arrived
@@ -351,21 +348,13 @@ class StepEngine:
         want_norm = abstol != 0.0 or reltol != 0.0
         args = self._args(t, dt, abstol, reltol)
         if self.world > 1 and self.peer:
-            comm = _lib.TDX_STEP_COMM_HALO
+            comm = self._args(t, dt, abstol, reltol, _lib.TDX_STEP_COMM_HALO | _lib.TDX_STEP_COMM_REDUCE)
             _lib.check(self.lib.tdx_comm_pack_halo(self.handle, float(dt), _ptr(mean), st))
-            a_int = self._args(t, dt, abstol, reltol, _lib.TDX_STEP_TILES_INTERIOR)
-            _lib.check(self.lib.tdx_ek0_sweep_a(self.handle, ctypes.byref(a_int), _ptr(mean), None, None, _ptr(zsq[0:1]), st))
-            a_rim = self._args(t, dt, abstol, reltol, _lib.TDX_STEP_TILES_RIM | comm)
-            _lib.check(self.lib.tdx_ek0_sweep_a(self.handle, ctypes.byref(a_rim), _ptr(mean), None, None, _ptr(zsq[1:2]), st))
-            _lib.check(self.lib.tdx_comm_allreduce(self.handle, _ptr(zsq), 2, st))
-            a_mid = self._args(t, dt, abstol, reltol, _lib.TDX_STEP_TWO_PARTS)
-            _lib.check(self.lib.tdx_ek0_mid(self.handle, ctypes.byref(a_mid), _ptr(Cl), _ptr(zsq), self.d_global,
+            _lib.check(self.lib.tdx_ek0_sweep_a(self.handle, ctypes.byref(comm), _ptr(mean), None, None, _ptr(zsq[0:1]), st))
+            _lib.check(self.lib.tdx_ek0_mid(self.handle, ctypes.byref(args), _ptr(Cl), _ptr(zsq), self.d_global,
                                             _ptr(Cl_out), _ptr(err), st))
-            a_b = self._args(t, dt, abstol, reltol, comm)
-            _lib.check(self.lib.tdx_ek0_sweep_b(self.handle, ctypes.byref(a_b), _ptr(mean), _ptr(mean_out), _ptr(ref),
+            _lib.check(self.lib.tdx_ek0_sweep_b(self.handle, ctypes.byref(comm), _ptr(mean), _ptr(mean_out), _ptr(ref),
                                                 None, None, _ptr(itol), st))
-            if want_norm:
-                _lib.check(self.lib.tdx_comm_allreduce(self.handle, _ptr(itol), 1, st))
             return mean_out, Cl_out, err, ref, itol
         if self.world > 1 and self.overlap:
             halo_lo, halo_hi, ready = self._halos_overlapped(dt, mean)
