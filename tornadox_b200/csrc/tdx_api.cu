@@ -645,7 +645,8 @@ int tdx_comm_pack_halo(tdx_ctx* ctx, double dt, const void* mean_in, void* strea
     StepHost h = make_step(ctx, &a);
     DeviceGuard guard(ctx->device);
     ctx->launches += 1;
-    return cuda_fail(ctx->ops->pack_peer(ctx->geo, h, mean_in, dst_lower, dst_upper, flag_lower, flag_upper, ctx->halo_seq,
+    return cuda_fail(ctx->ops->pack_peer(ctx->geo, h, mean_in, dst_lower, dst_upper, flag_lower, flag_upper,
+                                         reinterpret_cast<CommHeader*>(ctx->comm_local)->pack_count, ctx->halo_seq,
                                          n_first, n_last, (cudaStream_t)stream),
                      "tdx_comm_pack_halo");
 }

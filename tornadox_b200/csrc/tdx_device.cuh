@@ -487,7 +487,8 @@ struct CommHeader {
     unsigned long long red_flag[2][kMaxWorld];       // per parity, per source rank
     double red_val[2][kMaxWorld][4];
     unsigned long long error;                        // a flag wait timed out
-    unsigned long long pad[5];
+    unsigned int pack_count[2];                      // CTAs of the local pack kernel that have finished (per direction)
+    unsigned long long pad[4];
 };
 static_assert(sizeof(CommHeader) % 16 == 0, "halo storage behind the header must stay 16-byte aligned");
 

@@ -504,8 +504,11 @@ __global__ void pack_halo_kernel(const __grid_constant__ PackArgs<T, N> a) {
     }
 }
 
-// Peer variant: CTA 0 delivers the shard's first rows/points into the LOWER neighbour's hi-halo buffer, CTA 1 the
-// last ones into the UPPER neighbour's lo-halo buffer, then raises that neighbour's flag to ``seq``.
+// Peer variant: the first kPackCtas CTAs deliver the shard's first rows/points into the LOWER neighbour's hi-halo
+// buffer, the others the last ones into the UPPER neighbour's lo-halo buffer; the last CTA of each direction to
+// finish raises that neighbour's arrival flag to ``seq``.
+constexpr int kPackCtas = 16;
+
 template <typename T, int N>
 struct PackPeerArgs {
     Geo g;
@@ -515,26 +518,36 @@ struct PackPeerArgs {
     T* dst_upper;                    // upper neighbour's halo_lo[parity] (mapped), or null
     unsigned long long* flag_lower;  // lower neighbour's halo_flag_hi[parity]
     unsigned long long* flag_upper;  // upper neighbour's halo_flag_lo[parity]
+    unsigned int* done_count;        // local CommHeader::pack_count
     unsigned long long seq;
     int n_first, n_last;
 };
 
 template <typename T, int N>
-__global__ void __launch_bounds__(1024) pack_halo_peer_kernel(const __grid_constant__ PackPeerArgs<T, N> a) {
+__global__ void __launch_bounds__(256) pack_halo_peer_kernel(const __grid_constant__ PackPeerArgs<T, N> a) {
     MeanAt<T, N> at{a.mean_in, a.g.d, &a.c};
-    const bool lower = blockIdx.x == 0;
+    const bool lower = blockIdx.x < kPackCtas;
+    const int part = lower ? blockIdx.x : blockIdx.x - kPackCtas;
     T* dst = lower ? a.dst_lower : a.dst_upper;
     if (dst == nullptr) return;
     const int per_field = lower ? a.n_first : a.n_last;
     const long long start = lower ? 0 : (a.g.npts - a.n_last);
     const int total = a.g.nf * per_field;
-    for (int i = threadIdx.x; i < total; i += blockDim.x) {
+    for (int i = part * blockDim.x + threadIdx.x; i < total; i += kPackCtas * blockDim.x) {
         const int field = i / per_field, j = i - field * per_field;
         dst[i] = at((long long)field * a.g.npts + start + j);
     }
     __threadfence_system();
     __syncthreads();
-    if (threadIdx.x == 0) st_release_sys(lower ? a.flag_lower : a.flag_upper, a.seq);
+    if (threadIdx.x == 0) {
+        unsigned int* cnt = a.done_count + (lower ? 0 : 1);
+        const unsigned int prev = atomicAdd(cnt, 1u);
+        if (prev == kPackCtas - 1) {
+            *cnt = 0u;
+            __threadfence_system();
+            st_release_sys(lower ? a.flag_lower : a.flag_upper, a.seq);
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------

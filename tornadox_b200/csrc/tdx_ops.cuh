@@ -55,8 +55,8 @@ struct Ops {
     int (*pack)(const Geo&, const StepHost&, const void* mean_in, void* edge_first, void* edge_last, int n_first,
                 int n_last, cudaStream_t);
     int (*pack_peer)(const Geo&, const StepHost&, const void* mean_in, void* dst_lower, void* dst_upper,
-                     unsigned long long* flag_lower, unsigned long long* flag_upper, unsigned long long seq,
-                     int n_first, int n_last, cudaStream_t);
+                     unsigned long long* flag_lower, unsigned long long* flag_upper, unsigned int* done_count,
+                     unsigned long long seq, int n_first, int n_last, cudaStream_t);
 };
 
 struct EvalOps {
@@ -253,8 +253,8 @@ struct Launch {
     }
 
     static int pack_peer(const Geo& g, const StepHost& h, const void* mean_in, void* dst_lower, void* dst_upper,
-                         unsigned long long* flag_lower, unsigned long long* flag_upper, unsigned long long seq,
-                         int n_first, int n_last, cudaStream_t st) {
+                         unsigned long long* flag_lower, unsigned long long* flag_upper, unsigned int* done_count,
+                         unsigned long long seq, int n_first, int n_last, cudaStream_t st) {
         PackPeerArgs<T, N> a;
         a.g = g;
         a.c = make_consts<T, N>(h);
@@ -263,10 +263,11 @@ struct Launch {
         a.dst_upper = (T*)dst_upper;
         a.flag_lower = flag_lower;
         a.flag_upper = flag_upper;
+        a.done_count = done_count;
         a.seq = seq;
         a.n_first = n_first;
         a.n_last = n_last;
-        pack_halo_peer_kernel<T, N><<<2, 1024, 0, st>>>(a);
+        pack_halo_peer_kernel<T, N><<<2 * kPackCtas, 256, 0, st>>>(a);
         return (int)cudaGetLastError();
     }
 
