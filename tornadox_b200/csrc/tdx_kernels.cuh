@@ -507,7 +507,7 @@ __global__ void pack_halo_kernel(const __grid_constant__ PackArgs<T, N> a) {
 // Peer variant: the first kPackCtas CTAs deliver the shard's first rows/points into the LOWER neighbour's hi-halo
 // buffer, the others the last ones into the UPPER neighbour's lo-halo buffer; the last CTA of each direction to
 // finish raises that neighbour's arrival flag to ``seq``.
-constexpr int kPackCtas = 16;
+constexpr int kPackCtas = 4;
 
 template <typename T, int N>
 struct PackPeerArgs {
@@ -524,7 +524,7 @@ struct PackPeerArgs {
 };
 
 template <typename T, int N>
-__global__ void __launch_bounds__(256) pack_halo_peer_kernel(const __grid_constant__ PackPeerArgs<T, N> a) {
+__global__ void __launch_bounds__(1024) pack_halo_peer_kernel(const __grid_constant__ PackPeerArgs<T, N> a) {
     MeanAt<T, N> at{a.mean_in, a.g.d, &a.c};
     const bool lower = blockIdx.x < kPackCtas;
     const int part = lower ? blockIdx.x : blockIdx.x - kPackCtas;
@@ -537,9 +537,10 @@ __global__ void __launch_bounds__(256) pack_halo_peer_kernel(const __grid_consta
         const int field = i / per_field, j = i - field * per_field;
         dst[i] = at((long long)field * a.g.npts + start + j);
     }
-    __threadfence_system();
     __syncthreads();
     if (threadIdx.x == 0) {
+        // one system-scope fence per CTA: it is cumulative over the stores the barrier above ordered before it
+        __threadfence_system();
         unsigned int* cnt = a.done_count + (lower ? 0 : 1);
         const unsigned int prev = atomicAdd(cnt, 1u);
         if (prev == kPackCtas - 1) {

@@ -267,7 +267,7 @@ struct Launch {
         a.seq = seq;
         a.n_first = n_first;
         a.n_last = n_last;
-        pack_halo_peer_kernel<T, N><<<2 * kPackCtas, 256, 0, st>>>(a);
+        pack_halo_peer_kernel<T, N><<<2 * kPackCtas, 1024, 0, st>>>(a);
         return (int)cudaGetLastError();
     }
 
