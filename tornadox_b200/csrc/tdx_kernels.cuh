@@ -545,7 +545,7 @@ __global__ void __launch_bounds__(1024) pack_halo_peer_kernel(const __grid_const
         const unsigned int prev = atomicAdd(cnt, 1u);
         if (prev == kPackCtas - 1) {
             *cnt = 0u;
-            __threadfence_system();
+            __threadfence();   // the other CTAs' fences happened before their atomicAdd; order our read of the count
             st_release_sys(lower ? a.flag_lower : a.flag_upper, a.seq);
         }
     }
