@@ -170,6 +170,9 @@ int tdx_ek0_attempt_step(tdx_ctx* ctx, const tdx_step_args* args, const void* me
  *   tdx_comm_error    non-zero after a flag wait timed out (a peer died or diverged) */
 #define TDX_COMM_HANDLE_BYTES 64
 #define TDX_STEP_COMM_HALO 16u
+/* the launch itself first delivers this shard's edge state to the neighbours (a fused tdx_comm_pack_halo: a few of
+ * its CTAs do it before they start on their tiles), then behaves like TDX_STEP_COMM_HALO */
+#define TDX_STEP_COMM_PACK 64u
 /* all-reduce the call's scalar result over the ranks inside the kernel epilogue (needs tdx_comm_connect to all ranks) */
 #define TDX_STEP_COMM_REDUCE 32u
 int tdx_comm_init(tdx_ctx* ctx, int rank, int world, int lower_rank /* -1: none */, int upper_rank /* -1: none */,

@@ -20,6 +20,7 @@ TDX_STEP_TILES_RIM = 4
 TDX_STEP_TWO_PARTS = 8
 TDX_STEP_COMM_HALO = 16
 TDX_STEP_COMM_REDUCE = 32
+TDX_STEP_COMM_PACK = 64
 TDX_COMM_HANDLE_BYTES = 64
 TDX_IVP_VANDERPOL, TDX_IVP_LORENZ96, TDX_IVP_BRUSSELATOR, TDX_IVP_FHN2D = 0, 1, 2, 3
 

@@ -394,10 +394,43 @@ static StepHost make_step(const tdx_ctx* ctx, const tdx_step_args* a) {
     return h;
 }
 
+static void edge_counts(const Geo& g, int& n_first, int& n_last) {
+    n_first = n_last = 0;
+    switch (g.kind) {
+        case IVP_FHN2D: n_first = n_last = g.cols; break;
+        case IVP_BRUSS: n_first = n_last = 1; break;
+        case IVP_LORENZ96: n_first = 1; n_last = 2; break;
+        default: break;
+    }
+}
+
+// where this shard's edge state goes for the CURRENT halo sequence number (ctx->halo_seq already advanced)
+static PackPeer<double> pack_descriptor(const tdx_ctx* ctx) {
+    PackPeer<double> pk{};
+    edge_counts(ctx->geo, pk.n_first, pk.n_last);
+    const int parity = (int)(ctx->halo_seq & 1ull);
+    if (ctx->lower >= 0) {   // our first rows are the lower neighbour's UPPER halo
+        unsigned char* base = ctx->comm_peer[ctx->lower];
+        pk.dst_lower = reinterpret_cast<double*>(comm_halo(ctx, base, 1, parity));
+        pk.flag_lower = &reinterpret_cast<CommHeader*>(base)->halo_flag_hi[parity];
+    }
+    if (ctx->upper >= 0) {
+        unsigned char* base = ctx->comm_peer[ctx->upper];
+        pk.dst_upper = reinterpret_cast<double*>(comm_halo(ctx, base, 0, parity));
+        pk.flag_upper = &reinterpret_cast<CommHeader*>(base)->halo_flag_lo[parity];
+    }
+    pk.done_count = reinterpret_cast<CommHeader*>(ctx->comm_local)->pack_count;
+    pk.seq = ctx->halo_seq;
+    pk.enabled = 1;
+    return pk;
+}
+
 static Workspace make_ws(const tdx_ctx* ctx, unsigned flags = 0u) {
     const bool second = (flags & 6u) == TDX_STEP_TILES_RIM;
     Workspace ws{ctx->partials + (second ? ctx->partials_cap : 0), ctx->ticket + (second ? 1 : 0), ctx->mid, 0,
-                 ctx->halo_lo > 0, ctx->halo_hi > 0, CommWait{nullptr, nullptr, 0ull, nullptr}, CommReduce{}};
+                 ctx->halo_lo > 0, ctx->halo_hi > 0, CommWait{nullptr, nullptr, 0ull, nullptr}, CommReduce{},
+                 PackPeer<double>{}};
+    if ((flags & TDX_STEP_COMM_PACK) && ctx->comm_local) ws.pack = pack_descriptor(ctx);
     if ((flags & TDX_STEP_COMM_REDUCE) && ctx->comm_local) {
         ws.reduce.local = reinterpret_cast<CommHeader*>(ctx->comm_local);
         for (int r = 0; r < ctx->world; ++r) ws.reduce.peer[r] = reinterpret_cast<CommHeader*>(ctx->comm_peer[r]);
@@ -405,7 +438,7 @@ static Workspace make_ws(const tdx_ctx* ctx, unsigned flags = 0u) {
         ws.reduce.world = ctx->world;
         ws.reduce.seq = ctx->red_seq;      // the caller has already advanced it for this launch
     }
-    if ((flags & TDX_STEP_COMM_HALO) && ctx->comm_local && (flags & 6u) != TDX_STEP_TILES_INTERIOR) {
+    if ((flags & (TDX_STEP_COMM_HALO | TDX_STEP_COMM_PACK)) && ctx->comm_local && (flags & 6u) != TDX_STEP_TILES_INTERIOR) {
         CommHeader* hdr = reinterpret_cast<CommHeader*>(ctx->comm_local);
         const int parity = (int)(ctx->halo_seq & 1ull);
         ws.wait.flag_lo = ctx->halo_lo > 0 ? &hdr->halo_flag_lo[parity] : nullptr;
@@ -418,10 +451,22 @@ static Workspace make_ws(const tdx_ctx* ctx, unsigned flags = 0u) {
 
 // halo pointers of a step call: the caller's, or (TDX_STEP_COMM_HALO) the context's peer-written buffers
 static void resolve_halos(const tdx_ctx* ctx, unsigned flags, const void*& lo, const void*& hi) {
-    if (!(flags & TDX_STEP_COMM_HALO) || !ctx->comm_local) return;
+    if (!(flags & (TDX_STEP_COMM_HALO | TDX_STEP_COMM_PACK)) || !ctx->comm_local) return;
     const int parity = (int)(ctx->halo_seq & 1ull);
     lo = ctx->halo_lo > 0 ? comm_halo(ctx, ctx->comm_local, 0, parity) : nullptr;
     hi = ctx->halo_hi > 0 ? comm_halo(ctx, ctx->comm_local, 1, parity) : nullptr;
+}
+
+// A launch that delivers the halos itself (TDX_STEP_COMM_PACK) starts a new halo sequence number.
+static int comm_pack_begin(tdx_ctx* ctx, unsigned flags, const char* where) {
+    if (!(flags & TDX_STEP_COMM_PACK)) return TDX_OK;
+    if (!ctx->comm_local) return fail(TDX_ERR_INVALID, std::string(where) + ": TDX_STEP_COMM_PACK needs tdx_comm_init");
+    if ((flags & 6u) == TDX_STEP_TILES_INTERIOR || (flags & 6u) == TDX_STEP_TILES_RIM)
+        return fail(TDX_ERR_INVALID, std::string(where) + ": TDX_STEP_COMM_PACK cannot be combined with a partial tile range");
+    if ((ctx->lower >= 0 && !ctx->comm_peer[ctx->lower]) || (ctx->upper >= 0 && !ctx->comm_peer[ctx->upper]))
+        return fail(TDX_ERR_INVALID, std::string(where) + ": neighbours are not connected");
+    ctx->halo_seq += 1;
+    return TDX_OK;
 }
 
 // A launch that all-reduces its scalar in the epilogue consumes one reduction sequence number.
@@ -501,6 +546,7 @@ int tdx_dek1_attempt_step(tdx_ctx* ctx, const tdx_step_args* args, const void* m
     int rc = check_ready(ctx, "tdx_dek1_attempt_step");
     if (rc) return rc;
     if ((rc = check_dt(args, "tdx_dek1_attempt_step"))) return rc;
+    if ((rc = comm_pack_begin(ctx, args->flags, "tdx_dek1_attempt_step"))) return rc;
     resolve_halos(ctx, args->flags, halo_lo, halo_hi);
     if (!mean_in || !sc_in || !mean_out || !sc_out) return fail(TDX_ERR_INVALID, "tdx_dek1_attempt_step: null state buffer");
     if (mean_in == mean_out || sc_in == sc_out)
@@ -521,6 +567,7 @@ int tdx_ek0_sweep_a(tdx_ctx* ctx, const tdx_step_args* args, const void* mean_in
     int rc = check_ready(ctx, "tdx_ek0_sweep_a");
     if (rc) return rc;
     if ((rc = check_dt(args, "tdx_ek0_sweep_a"))) return rc;
+    if ((rc = comm_pack_begin(ctx, args->flags, "tdx_ek0_sweep_a"))) return rc;
     resolve_halos(ctx, args->flags, halo_lo, halo_hi);
     if (!mean_in || !z_sq_sum) return fail(TDX_ERR_INVALID, "tdx_ek0_sweep_a: null buffer");
     if ((rc = check_halos(ctx, halo_lo, halo_hi, "tdx_ek0_sweep_a", args->flags))) return rc;
@@ -566,16 +613,6 @@ int tdx_ek0_sweep_b(tdx_ctx* ctx, const tdx_step_args* args, const void* mean_in
 }
 
 // ---- peer-memory exchange ---------------------------------------------------------------------------------
-
-static void edge_counts(const Geo& g, int& n_first, int& n_last) {
-    n_first = n_last = 0;
-    switch (g.kind) {
-        case IVP_FHN2D: n_first = n_last = g.cols; break;
-        case IVP_BRUSS: n_first = n_last = 1; break;
-        case IVP_LORENZ96: n_first = 1; n_last = 2; break;
-        default: break;
-    }
-}
 
 int tdx_comm_init(tdx_ctx* ctx, int rank, int world, int lower_rank, int upper_rank, void* handle_out) {
     int rc = check_ready(ctx, "tdx_comm_init");
@@ -626,29 +663,12 @@ int tdx_comm_pack_halo(tdx_ctx* ctx, double dt, const void* mean_in, void* strea
     if (!mean_in) return fail(TDX_ERR_INVALID, "tdx_comm_pack_halo: null buffer");
     if ((ctx->lower >= 0 && !ctx->comm_peer[ctx->lower]) || (ctx->upper >= 0 && !ctx->comm_peer[ctx->upper]))
         return fail(TDX_ERR_INVALID, "tdx_comm_pack_halo: neighbours are not connected");
-    int n_first = 0, n_last = 0;
-    edge_counts(ctx->geo, n_first, n_last);
     ctx->halo_seq += 1;
-    const int parity = (int)(ctx->halo_seq & 1ull);
-    void* dst_lower = nullptr; void* dst_upper = nullptr;
-    unsigned long long* flag_lower = nullptr; unsigned long long* flag_upper = nullptr;
-    if (ctx->lower >= 0) {   // our first rows are the lower neighbour's UPPER halo
-        unsigned char* base = ctx->comm_peer[ctx->lower];
-        dst_lower = comm_halo(ctx, base, 1, parity);
-        flag_lower = &reinterpret_cast<CommHeader*>(base)->halo_flag_hi[parity];
-    }
-    if (ctx->upper >= 0) {
-        unsigned char* base = ctx->comm_peer[ctx->upper];
-        dst_upper = comm_halo(ctx, base, 0, parity);
-        flag_upper = &reinterpret_cast<CommHeader*>(base)->halo_flag_lo[parity];
-    }
+    PackPeer<double> pk = pack_descriptor(ctx);
     StepHost h = make_step(ctx, &a);
     DeviceGuard guard(ctx->device);
     ctx->launches += 1;
-    return cuda_fail(ctx->ops->pack_peer(ctx->geo, h, mean_in, dst_lower, dst_upper, flag_lower, flag_upper,
-                                         reinterpret_cast<CommHeader*>(ctx->comm_local)->pack_count, ctx->halo_seq,
-                                         n_first, n_last, (cudaStream_t)stream),
-                     "tdx_comm_pack_halo");
+    return cuda_fail(ctx->ops->pack_peer(ctx->geo, h, mean_in, pk, (cudaStream_t)stream), "tdx_comm_pack_halo");
 }
 
 int tdx_comm_allreduce(tdx_ctx* ctx, double* vals, int count, void* stream) {

@@ -97,6 +97,68 @@ __device__ __forceinline__ void front_eval(const Geo& g, const Consts<T, N>& c, 
 }
 
 // ---------------------------------------------------------------------------------------------
+// Peer-memory halo delivery: 2 * kPackCtas CTAs (kPackCtas per direction) store the predicted state of the shard's
+// first rows/points into the LOWER neighbour's hi-halo buffer and of the last ones into the UPPER neighbour's
+// lo-halo buffer; the last CTA of each direction to finish raises that neighbour's arrival flag to ``seq``.
+// Runs either as its own launch (pack_halo_peer_kernel) or fused at the start of a step kernel.
+// ---------------------------------------------------------------------------------------------
+constexpr int kPackCtas = 4;
+
+template <typename T>
+struct PackPeer {
+    T* dst_lower;                    // lower neighbour's halo_hi[parity] (mapped), or null
+    T* dst_upper;                    // upper neighbour's halo_lo[parity] (mapped), or null
+    unsigned long long* flag_lower;  // lower neighbour's halo_flag_hi[parity]
+    unsigned long long* flag_upper;  // upper neighbour's halo_flag_lo[parity]
+    unsigned int* done_count;        // local CommHeader::pack_count
+    unsigned long long seq;
+    int n_first, n_last;
+    int enabled;
+};
+
+template <typename T, int N>
+__device__ __forceinline__ void pack_halo_part(const Geo& g, const Consts<T, N>& c, const T* mean_in,
+                                               const PackPeer<T>& pk, int part_index) {
+    MeanAt<T, N> at{mean_in, g.d, &c};
+    const bool lower = part_index < kPackCtas;
+    const int part = lower ? part_index : part_index - kPackCtas;
+    T* dst = lower ? pk.dst_lower : pk.dst_upper;
+    if (dst == nullptr) return;      // CTA-uniform
+    const int per_field = lower ? pk.n_first : pk.n_last;
+    const long long start = lower ? 0 : (g.npts - pk.n_last);
+    const int total = g.nf * per_field;
+    for (int i = part * blockDim.x + threadIdx.x; i < total; i += kPackCtas * blockDim.x) {
+        const int field = i / per_field, j = i - field * per_field;
+        dst[i] = at((long long)field * g.npts + start + j);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        // one system-scope fence per CTA: it is cumulative over the stores the barrier above ordered before it
+        __threadfence_system();
+        unsigned int* cnt = pk.done_count + (lower ? 0 : 1);
+        const unsigned int prev = atomicAdd(cnt, 1u);
+        if (prev == kPackCtas - 1) {
+            *cnt = 0u;
+            __threadfence();   // the other CTAs' fences happened before their atomicAdd; order our read of the count
+            st_release_sys(lower ? pk.flag_lower : pk.flag_upper, pk.seq);
+        }
+    }
+}
+
+template <typename T, int N>
+struct PackPeerArgs {
+    Geo g;
+    Consts<T, N> c;
+    const T* mean_in;
+    PackPeer<T> pk;
+};
+
+template <typename T, int N>
+__global__ void __launch_bounds__(1024) pack_halo_peer_kernel(const __grid_constant__ PackPeerArgs<T, N> a) {
+    pack_halo_part<T, N>(a.g, a.c, a.mean_in, a.pk, (int)blockIdx.x);
+}
+
+// ---------------------------------------------------------------------------------------------
 // DiagonalEK1 fused attempt: persistent CTAs, two shared-memory slots per warp for the factor blocks.
 // While a warp computes tile i out of slot i&1, the TMA engine fills the other slot with tile i+1 and
 // drains tile i-1's results; the only CTA-wide barrier per tile is the one that publishes the stencil tile.
@@ -120,6 +182,7 @@ struct DekArgs {
     TileRanges ranges;
     CommWait wait;                     // peer-memory halos: flags to wait for (null: nothing to wait for)
     CommReduce reduce;                 // fused all-reduce of the norm sum (world == 0: off)
+    PackPeer<T> pack;                  // fused halo delivery (enabled == 0: off)
 };
 
 template <typename T, int N>
@@ -178,8 +241,11 @@ __global__ void __launch_bounds__(kThreads, TDX_MIN_BLOCKS) dek1_kernel(const __
         return bulk;
     };
 
+    // CTA b walks the virtual tiles (G-1-b), (G-1-b)+G, ...: the lowest block indices (scheduled first, always resident)
+    // have the shortest lists when tiles % G != 0, and they deliver this shard's halos before they start on them
+    if (a.pack.enabled && blockIdx.x < 2 * kPackCtas) pack_halo_part<T, N>(g, c, a.mean_in, a.pack, (int)blockIdx.x);
     bool halos_ready = false;          // CTA-uniform: the arrival flags have been seen
-    unsigned tile = blockIdx.x;
+    unsigned tile = gridDim.x - 1u - blockIdx.x;
     unsigned phase_bits = 0u;          // parity of each slot's mbarrier
     double ratio_sq_acc = 0.0;
     Coord co{};
@@ -342,6 +408,7 @@ struct Ek0Args {
     TileRanges ranges;
     CommWait wait;
     CommReduce reduce;
+    PackPeer<T> pack;
     int reverse;             // walk the tiles backwards (sweep B re-reads what sweep A touched last: L2 reuse)
 };
 
@@ -376,7 +443,8 @@ __global__ void __launch_bounds__(kThreads, 3) ek0_sweep_kernel(const __grid_con
         }
     };
 
-    unsigned i = blockIdx.x;
+    if (a.pack.enabled && blockIdx.x < 2 * kPackCtas) pack_halo_part<T, N>(g, c, a.mean_in, a.pack, (int)blockIdx.x);
+    unsigned i = gridDim.x - 1u - blockIdx.x;
     double acc = 0.0;
     Coord co{};
     FrontRegs<IVP, T, N> fr;
@@ -500,53 +568,6 @@ __global__ void pack_halo_kernel(const __grid_constant__ PackArgs<T, N> a) {
         } else {
             const int jj = j - a.n_first;
             a.edge_last[field * a.n_last + jj] = at((long long)field * a.g.npts + (a.g.npts - a.n_last + jj));
-        }
-    }
-}
-
-// Peer variant: the first kPackCtas CTAs deliver the shard's first rows/points into the LOWER neighbour's hi-halo
-// buffer, the others the last ones into the UPPER neighbour's lo-halo buffer; the last CTA of each direction to
-// finish raises that neighbour's arrival flag to ``seq``.
-constexpr int kPackCtas = 4;
-
-template <typename T, int N>
-struct PackPeerArgs {
-    Geo g;
-    Consts<T, N> c;
-    const T* mean_in;
-    T* dst_lower;                    // lower neighbour's halo_hi[parity] (mapped), or null
-    T* dst_upper;                    // upper neighbour's halo_lo[parity] (mapped), or null
-    unsigned long long* flag_lower;  // lower neighbour's halo_flag_hi[parity]
-    unsigned long long* flag_upper;  // upper neighbour's halo_flag_lo[parity]
-    unsigned int* done_count;        // local CommHeader::pack_count
-    unsigned long long seq;
-    int n_first, n_last;
-};
-
-template <typename T, int N>
-__global__ void __launch_bounds__(1024) pack_halo_peer_kernel(const __grid_constant__ PackPeerArgs<T, N> a) {
-    MeanAt<T, N> at{a.mean_in, a.g.d, &a.c};
-    const bool lower = blockIdx.x < kPackCtas;
-    const int part = lower ? blockIdx.x : blockIdx.x - kPackCtas;
-    T* dst = lower ? a.dst_lower : a.dst_upper;
-    if (dst == nullptr) return;
-    const int per_field = lower ? a.n_first : a.n_last;
-    const long long start = lower ? 0 : (a.g.npts - a.n_last);
-    const int total = a.g.nf * per_field;
-    for (int i = part * blockDim.x + threadIdx.x; i < total; i += kPackCtas * blockDim.x) {
-        const int field = i / per_field, j = i - field * per_field;
-        dst[i] = at((long long)field * a.g.npts + start + j);
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        // one system-scope fence per CTA: it is cumulative over the stores the barrier above ordered before it
-        __threadfence_system();
-        unsigned int* cnt = a.done_count + (lower ? 0 : 1);
-        const unsigned int prev = atomicAdd(cnt, 1u);
-        if (prev == kPackCtas - 1) {
-            *cnt = 0u;
-            __threadfence();   // the other CTAs' fences happened before their atomicAdd; order our read of the count
-            st_release_sys(lower ? a.flag_lower : a.flag_upper, a.seq);
         }
     }
 }

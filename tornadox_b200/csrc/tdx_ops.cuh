@@ -21,6 +21,7 @@ struct Workspace {
     bool has_lo, has_hi;     // the shard has a lower / upper neighbour (halo buffers exist)
     CommWait wait;           // peer-memory halos: flags the kernel must see before it reads them (null otherwise)
     CommReduce reduce;       // fused all-reduce of the scalar result (world == 0: off)
+    PackPeer<double> pack;   // fused halo delivery (pointers are dtype-agnostic; enabled == 0: off)
 };
 
 // Which tiles does a launch process?  all / interior (no halo reads) / rim (TDX_STEP_TILES_*).
@@ -54,9 +55,7 @@ struct Ops {
                  const void* halo_hi, const Workspace&, double* out_sum, cudaStream_t);
     int (*pack)(const Geo&, const StepHost&, const void* mean_in, void* edge_first, void* edge_last, int n_first,
                 int n_last, cudaStream_t);
-    int (*pack_peer)(const Geo&, const StepHost&, const void* mean_in, void* dst_lower, void* dst_upper,
-                     unsigned long long* flag_lower, unsigned long long* flag_upper, unsigned int* done_count,
-                     unsigned long long seq, int n_first, int n_last, cudaStream_t);
+    int (*pack_peer)(const Geo&, const StepHost&, const void* mean_in, const PackPeer<double>& pk, cudaStream_t);
 };
 
 struct EvalOps {
@@ -162,6 +161,12 @@ struct Launch {
             }
             unsigned grid = 0;
             TDX_CUDA_TRY(persistent_grid<kern>(smem, a.num_tiles, ws.reserve_ctas, grid));
+            a.pack = typed_pack(ws.pack);
+            if (a.pack.enabled && grid < 2u * kPackCtas) {   // tiny shard: deliver the halos with their own launch
+                const int rc = pack_peer(g, h, mean_in, ws.pack, st);
+                if (rc) return rc;
+                a.pack.enabled = 0;
+            }
             kern<<<grid, kThreads, smem, st>>>(a);
         })
         return (int)cudaGetLastError();
@@ -204,6 +209,17 @@ struct Launch {
             }
             unsigned grid = 0;
             TDX_CUDA_TRY(persistent_grid<kern>(smem, a.num_tiles, ws.reserve_ctas, grid));
+            a.pack = typed_pack(ws.pack);
+            if (kUpdate) a.pack.enabled = 0;
+            if (a.pack.enabled && grid < 2u * kPackCtas) {
+                PackPeerArgs<T, N> pa;
+                pa.g = g;
+                pa.c = a.c;
+                pa.mean_in = a.mean_in;
+                pa.pk = a.pack;
+                pack_halo_peer_kernel<T, N><<<2 * kPackCtas, 1024, 0, st>>>(pa);
+                a.pack.enabled = 0;
+            }
             kern<<<grid, kThreads, smem, st>>>(a);
         })
         return (int)cudaGetLastError();
@@ -252,21 +268,27 @@ struct Launch {
         return (int)cudaGetLastError();
     }
 
-    static int pack_peer(const Geo& g, const StepHost& h, const void* mean_in, void* dst_lower, void* dst_upper,
-                         unsigned long long* flag_lower, unsigned long long* flag_upper, unsigned int* done_count,
-                         unsigned long long seq, int n_first, int n_last, cudaStream_t st) {
+    static PackPeer<T> typed_pack(const PackPeer<double>& pk) {
+        PackPeer<T> out;
+        out.dst_lower = (T*)pk.dst_lower;
+        out.dst_upper = (T*)pk.dst_upper;
+        out.flag_lower = pk.flag_lower;
+        out.flag_upper = pk.flag_upper;
+        out.done_count = pk.done_count;
+        out.seq = pk.seq;
+        out.n_first = pk.n_first;
+        out.n_last = pk.n_last;
+        out.enabled = pk.enabled;
+        return out;
+    }
+
+    static int pack_peer(const Geo& g, const StepHost& h, const void* mean_in, const PackPeer<double>& pk,
+                         cudaStream_t st) {
         PackPeerArgs<T, N> a;
         a.g = g;
         a.c = make_consts<T, N>(h);
         a.mean_in = (const T*)mean_in;
-        a.dst_lower = (T*)dst_lower;
-        a.dst_upper = (T*)dst_upper;
-        a.flag_lower = flag_lower;
-        a.flag_upper = flag_upper;
-        a.done_count = done_count;
-        a.seq = seq;
-        a.n_first = n_first;
-        a.n_last = n_last;
+        a.pk = typed_pack(pk);
         pack_halo_peer_kernel<T, N><<<2 * kPackCtas, 1024, 0, st>>>(a);
         return (int)cudaGetLastError();
     }

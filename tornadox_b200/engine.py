@@ -302,12 +302,11 @@ class StepEngine:
         bufs = (_ptr(mean), _ptr(sc), _ptr(mean_out), _ptr(sc_out), _ptr(err), _ptr(ref))
         scal = self._next_scalars()
         if self.world > 1 and self.peer:
-            # two launches per attempt, no NCCL: the pack kernel stores the halos straight into the neighbours'
-            # buffers; the step kernel does the interior tiles first, awaits the arrival flags only when it reaches
-            # the rim tiles, and its last CTA all-reduces the norm sum through peer memory
+            # ONE launch per attempt, no NCCL: a few CTAs first store this shard's edge state straight into the
+            # neighbours' halo buffers (NVLink), all CTAs do the interior tiles first and await the arrival flags only
+            # when they reach the rim tiles, and the last CTA all-reduces the norm sum through peer memory
             st = self._stream()
-            _lib.check(self.lib.tdx_comm_pack_halo(self.handle, float(dt), _ptr(mean), st))
-            a_all = self._args(t, dt, abstol, reltol, base_flags | _lib.TDX_STEP_COMM_HALO | _lib.TDX_STEP_COMM_REDUCE)
+            a_all = self._args(t, dt, abstol, reltol, base_flags | _lib.TDX_STEP_COMM_PACK | _lib.TDX_STEP_COMM_REDUCE)
             sq = scal[0:1]
             _lib.check(call(self.handle, ctypes.byref(a_all), *bufs, None, None, _ptr(sq), st))
             return mean_out, sc_out, err, ref, sq
@@ -349,8 +348,8 @@ class StepEngine:
         args = self._args(t, dt, abstol, reltol)
         if self.world > 1 and self.peer:
             comm = self._args(t, dt, abstol, reltol, _lib.TDX_STEP_COMM_HALO | _lib.TDX_STEP_COMM_REDUCE)
-            _lib.check(self.lib.tdx_comm_pack_halo(self.handle, float(dt), _ptr(mean), st))
-            _lib.check(self.lib.tdx_ek0_sweep_a(self.handle, ctypes.byref(comm), _ptr(mean), None, None, _ptr(zsq[0:1]), st))
+            first = self._args(t, dt, abstol, reltol, _lib.TDX_STEP_COMM_PACK | _lib.TDX_STEP_COMM_REDUCE)
+            _lib.check(self.lib.tdx_ek0_sweep_a(self.handle, ctypes.byref(first), _ptr(mean), None, None, _ptr(zsq[0:1]), st))
             _lib.check(self.lib.tdx_ek0_mid(self.handle, ctypes.byref(args), _ptr(Cl), _ptr(zsq), self.d_global,
                                             _ptr(Cl_out), _ptr(err), st))
             _lib.check(self.lib.tdx_ek0_sweep_b(self.handle, ctypes.byref(comm), _ptr(mean), _ptr(mean_out), _ptr(ref),
