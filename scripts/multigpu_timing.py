@@ -49,5 +49,15 @@ t0.record()
 for _ in range(30): plain()
 t1.record(); torch.cuda.synchronize()
 print(f"rank {rank}: interior-only kernel {t0.elapsed_time(t1)/30*1e3:.1f} us", flush=True)
+# fused: one launch delivers the halos, does all tiles and all-reduces the norm
+args3 = _lib.StepArgs(0.0, 1e-6, 1e-4, 1e-2, _lib.TDX_STEP_COMM_PACK | _lib.TDX_STEP_COMM_REDUCE, 0)
+def fused():
+    _lib.check(eng.lib.tdx_dek1_attempt_step(eng.handle, ctypes.byref(args3), _ptr(mean), _ptr(sc), _ptr(mo), _ptr(so), _ptr(err), _ptr(ref), None, None, _ptr(sq), st))
+for _ in range(3): fused()
+torch.cuda.synchronize(); dist.barrier()
+t0.record()
+for _ in range(30): fused()
+t1.record(); torch.cuda.synchronize()
+print(f"rank {rank}: fused pack+step+allreduce launch {t0.elapsed_time(t1)/30*1e3:.1f} us", flush=True)
 eng.check_peers()
 dist.barrier(); dist.destroy_process_group()

@@ -194,7 +194,9 @@ struct DekSmem {
     }
 };
 
-template <class IVP, typename T, int N>
+// kComm = false: single-GPU instantiation without any of the peer-memory code paths (halo delivery, flag waits,
+// fused all-reduce); the register allocation of this kernel sits at the 128-register cap and is sensitive to them.
+template <class IVP, typename T, int N, bool kComm>
 __global__ void __launch_bounds__(kThreads, TDX_MIN_BLOCKS) dek1_kernel(const __grid_constant__ DekArgs<T, N> a) {
     using Shape = typename IVP::Shape;
     using L = SmemLayout<T, N>;
@@ -243,45 +245,41 @@ __global__ void __launch_bounds__(kThreads, TDX_MIN_BLOCKS) dek1_kernel(const __
 
     // CTA b walks the virtual tiles (G-1-b), (G-1-b)+G, ...: the lowest block indices (scheduled first, always resident)
     // have the shortest lists when tiles % G != 0, and they deliver this shard's halos before they start on them
-    if (a.pack.enabled && blockIdx.x < 2 * kPackCtas) pack_halo_part<T, N>(g, c, a.mean_in, a.pack, (int)blockIdx.x);
+    if (kComm && a.pack.enabled && blockIdx.x < 2 * kPackCtas)
+        pack_halo_part<T, N>(g, c, a.mean_in, a.pack, (int)blockIdx.x);
     bool halos_ready = false;          // CTA-uniform: the arrival flags have been seen
-    unsigned tile = gridDim.x - 1u - blockIdx.x;
+    unsigned tile = kComm ? (gridDim.x - 1u - blockIdx.x) : blockIdx.x;
     unsigned phase_bits = 0u;          // parity of each slot's mbarrier
     double ratio_sq_acc = 0.0;
-    Coord co{};
-    FrontRegs<IVP, T, N> fr;
     bool cur_bulk = false;
-    if (tile < a.num_tiles) {
-        co = tile_coord<Shape>(g, a.ranges.tile(tile), a.tiles_x);
-        cur_bulk = stage_in(co, 0);
-        if (TDX_PREFETCH_MEAN) front_load<IVP, T, N>(g, c, a.mean_in, a.halo_lo, a.halo_hi, co, fr);
-    }
+    if (tile < a.num_tiles) cur_bulk = stage_in(tile_coord<Shape>(g, a.ranges.tile(tile), a.tiles_x), 0);
 
     for (unsigned it = 0; tile < a.num_tiles; ++it) {
         const int slot = it & 1;
         T* my_sc = s_sc0 + slot * SC_STRIDE + w * 32 * STRIDE;
         T* s_at = s_at0 + slot * AT_STRIDE;
-        if (!halos_ready && tile >= a.ranges.wait_from) {
+        if (kComm && !halos_ready && tile >= a.ranges.wait_from) {
             cta_wait_halos(a.wait);
             halos_ready = true;
         }
-        if (!TDX_PREFETCH_MEAN) front_load<IVP, T, N>(g, c, a.mean_in, a.halo_lo, a.halo_hi, co, fr);
 
-        // (1) predict + vector field of the current tile (its loads were issued one iteration ago)
-        T mp[N], fx, jac;
-        front_eval<IVP, T, N>(g, c, co, fr, s_at, mp, fx, jac);
-        const T raw0 = fr.raw[0];
-        const Coord cur = co;
+        // (1) mean column, prediction and vector field of the current tile
+        const Coord cur = tile_coord<Shape>(g, a.ranges.tile(tile), a.tiles_x);
+        T mp[N], fx, jac, raw0;
+        {
+            FrontRegs<IVP, T, N> fr;
+            front_load<IVP, T, N>(g, c, a.mean_in, a.halo_lo, a.halo_hi, cur, fr);
+            front_eval<IVP, T, N>(g, c, cur, fr, s_at, mp, fx, jac);
+            raw0 = fr.raw[0];
+        }
 
-        // (2) start the loads of the next tile: factor blocks into the other slot, mean column into registers
+        // (2) start streaming the next tile's factor blocks into the other slot
         const unsigned next = tile + gridDim.x;
         bool next_bulk = false;
         if (next < a.num_tiles) {
             if (lane == 0) bulk_wait_read0();      // the other slot's previous results have left shared memory
             __syncwarp();
-            co = tile_coord<Shape>(g, a.ranges.tile(next), a.tiles_x);
-            next_bulk = stage_in(co, slot ^ 1);
-            if (TDX_PREFETCH_MEAN) front_load<IVP, T, N>(g, c, a.mean_in, a.halo_lo, a.halo_hi, co, fr);
+            next_bulk = stage_in(tile_coord<Shape>(g, a.ranges.tile(next), a.tiles_x), slot ^ 1);
         }
 
         // (3) wait for the current tile's blocks
@@ -378,7 +376,7 @@ __global__ void __launch_bounds__(kThreads, TDX_MIN_BLOCKS) dek1_kernel(const __
         cur_bulk = next_bulk;
     }
 
-    if (c.want_norm) grid_sum(ratio_sq_acc, s_red, a.partials, a.ticket, a.out_sum, 1.0, nullptr, &a.reduce);
+    if (c.want_norm) grid_sum(ratio_sq_acc, s_red, a.partials, a.ticket, a.out_sum, 1.0, nullptr, kComm ? &a.reduce : nullptr);
     if (lane == 0) bulk_wait_read0();
 }
 

@@ -1,6 +1,8 @@
 // Host-side launch table: one Ops entry per (dtype, n), defined in the per-instantiation translation units.
 #pragma once
 
+#include <cstdlib>
+
 #include "tdx_kernels.cuh"
 
 namespace tdx {
@@ -123,6 +125,11 @@ inline cudaError_t persistent_grid(size_t smem, long long tiles, int reserve, un
         default: return -1;                                                      \
     }
 
+inline bool force_comm_kernel() {
+    static const bool on = std::getenv("TDX_FORCE_COMM_KERNEL") != nullptr;   // experiments only
+    return on;
+}
+
 template <typename T, int N>
 struct Launch {
     using L = SmemLayout<T, N>;
@@ -144,10 +151,10 @@ struct Launch {
         a.partials = ws.partials;
         a.ticket = ws.ticket;
         a.out_sum = out_sum;
+        const bool comm = ws.pack.enabled || ws.wait.flag_lo || ws.wait.flag_hi || ws.reduce.world > 0 || force_comm_kernel();
         TDX_SWITCH_IVP(g.kind, T, {
             using Shape = typename IVP::Shape;
             const size_t smem = DekSmem<T, N>::total(Shape::AT_ELEMS);
-            constexpr auto kern = dek1_kernel<IVP, T, N>;
             a.tiles_x = (unsigned)((g.cols + Shape::TC - 1) / Shape::TC);
             const unsigned tiles_y = (unsigned)((g.rows + Shape::TR - 1) / Shape::TR);
             a.ranges = tile_ranges(h.flags, a.tiles_x, tiles_y, ws.has_lo, ws.has_hi, g.kind == IVP_FHN2D,
@@ -159,15 +166,22 @@ struct Launch {
                 if (h.want_norm) TDX_CUDA_TRY(cudaMemsetAsync(out_sum, 0, sizeof(double), st));
                 return 0;
             }
-            unsigned grid = 0;
-            TDX_CUDA_TRY(persistent_grid<kern>(smem, a.num_tiles, ws.reserve_ctas, grid));
             a.pack = typed_pack(ws.pack);
-            if (a.pack.enabled && grid < 2u * kPackCtas) {   // tiny shard: deliver the halos with their own launch
-                const int rc = pack_peer(g, h, mean_in, ws.pack, st);
-                if (rc) return rc;
-                a.pack.enabled = 0;
+            unsigned grid = 0;
+            if (comm) {
+                constexpr auto kern = dek1_kernel<IVP, T, N, true>;
+                TDX_CUDA_TRY(persistent_grid<kern>(smem, a.num_tiles, ws.reserve_ctas, grid));
+                if (a.pack.enabled && grid < 2u * kPackCtas) {   // tiny shard: deliver the halos with their own launch
+                    const int rc = pack_peer(g, h, mean_in, ws.pack, st);
+                    if (rc) return rc;
+                    a.pack.enabled = 0;
+                }
+                kern<<<grid, kThreads, smem, st>>>(a);
+            } else {
+                constexpr auto kern = dek1_kernel<IVP, T, N, false>;
+                TDX_CUDA_TRY(persistent_grid<kern>(smem, a.num_tiles, ws.reserve_ctas, grid));
+                kern<<<grid, kThreads, smem, st>>>(a);
             }
-            kern<<<grid, kThreads, smem, st>>>(a);
         })
         return (int)cudaGetLastError();
     }
