@@ -145,63 +145,58 @@ __device__ __forceinline__ Coord tile_coord(const Geo& g, unsigned tile, unsigne
     return c;
 }
 
-template <class Shape>
-__device__ __forceinline__ int at_index(int field, int tr, int tcol) {
-    return (field * Shape::TR + tr) * Shape::TC + tcol;
-}
-
 // ---------------------------------------------------------------------------------------------
-// Vector fields.  The stencil reads the predicted state of neighbouring points.  Neighbours inside the
-// CTA's tile come from shared memory; the few that are not are described by a Plan (at most NEXT
-// "external" values per thread) and fetched BEFORE the tile barrier: recomputed from the mean in
-// global/L2 (SRC_MEAN), read from the exchanged shard halos (SRC_LO / SRC_HI), or a boundary constant.
-//   plan(g, c)                    -> Plan   (where does every stencil neighbour of this thread come from)
-//   eval(g, c, s_at, own, ext, plan, fx, jac)   f_i and (df/dy)_ii, AFTER the barrier
+// Vector fields.  The stencil reads the predicted state of neighbouring points.  Every CTA fills an EXTENDED tile
+// in shared memory: its own TR x TC points plus a ring of HV rows above/below and HL / HR columns left/right.
+// Ring points are computed by the first NF * NRING threads (one point each) from the mean through L2 (recomputed
+// with MeanAt: bitwise what the owner computes), from the exchanged shard halos, or from the boundary rule of the
+// problem (edge replication = coordinate clamping, constant pads, cyclic wrap).  After ONE barrier the stencil
+// is branch-free shared-memory reads.
+//   ring_value(g, row0, col0, field, er, ec, at, halo_lo, halo_hi)   value of extended-tile point (er, ec)
+//   eval(g, c, s_ext, own, fx, jac)                                  f_i and (df/dy)_ii
 // ---------------------------------------------------------------------------------------------
-enum : int { SRC_NONE = 0, SRC_MEAN = 1, SRC_LO = 2, SRC_HI = 3, SRC_CONST = 4 };
-enum : unsigned { NB_TILE = 0u, NB_SELF = 1u, NB_EXT = 2u };   // 2-bit codes, NB_EXT + slot
-
-template <typename T, int NEXT_>
-struct Plan {
-    static constexpr int NEXT = NEXT_;
-    long long idx[NEXT_ > 0 ? NEXT_ : 1];
-    int src[NEXT_ > 0 ? NEXT_ : 1];
-    T cval[NEXT_ > 0 ? NEXT_ : 1];
-    unsigned code;   // per-field-kind encoding, 2 bits per stencil neighbour
-};
-
-template <typename T, int NEXT, class At>
-__device__ __forceinline__ void fetch_ext(const Plan<T, NEXT>& pl, const At& at, const T* __restrict__ halo_lo,
-                                          const T* __restrict__ halo_hi, T (&ext)[NEXT > 0 ? NEXT : 1]) {
-#pragma unroll
-    for (int s = 0; s < NEXT; ++s) {
-        T v = (T)0;
-        const int src = pl.src[s];
-        if (src == SRC_MEAN) v = at(pl.idx[s]);
-        else if (src == SRC_LO) v = __ldcg(halo_lo + pl.idx[s]);   // L2 only: written by a peer GPU
-        else if (src == SRC_HI) v = __ldcg(halo_hi + pl.idx[s]);
-        else if (src == SRC_CONST) v = pl.cval[s];
-        ext[s] = v;
+template <class IVP>
+struct ExtTile {
+    using Shape = typename IVP::Shape;
+    static constexpr int HL = IVP::HL, HR = IVP::HR, HV = IVP::HV;
+    static constexpr int ER = Shape::TR + 2 * HV, EC = Shape::TC + HL + HR;
+    static constexpr int ELEMS = Shape::NF * ER * EC;
+    static constexpr int NRING = ER * EC - Shape::TR * Shape::TC;       // ring points per field
+    static_assert(Shape::NF * NRING <= kThreads, "one ring point per thread");
+    __device__ static __forceinline__ int index(int field, int er, int ec) { return (field * ER + er) * EC + ec; }
+    // this thread's own slot
+    __device__ static __forceinline__ int own(const Coord& c) { return index(c.field, c.tr + HV, c.tcol + HL); }
+    // h-th ring point of a field -> (er, ec)
+    __device__ static __forceinline__ void ring(int h, int& er, int& ec) {
+        if (HV > 0) {
+            if (h < HV * EC) { er = h / EC; ec = h - er * EC; return; }
+            h -= HV * EC;
+            if (h < HV * EC) { er = h / EC; ec = h - er * EC; er += Shape::TR + HV; return; }
+            h -= HV * EC;
+        }
+        // side columns of the TR middle rows: HL left ones then HR right ones per row
+        const int per_row = HL + HR;
+        const int r = h / per_row, k = h - r * per_row;
+        er = HV + r;
+        ec = (k < HL) ? k : (Shape::TC + k);
     }
-}
+};
 
 // --- vanderpol: ivp.py:28-49.  One point, two fields (y1, y2). ---------------------------------
 template <typename T>
 struct VanderPol {
     using Shape = TileShape<2, 1, 4>;
-    static constexpr int NEXT = 0;
+    static constexpr int HL = 0, HR = 0, HV = 0;
     static __host__ void halo_sizes(const Geo&, long long& lo, long long& hi) { lo = hi = 0; }
-    __device__ static __forceinline__ Plan<T, NEXT> plan(const Geo&, const Coord&) {
-        Plan<T, NEXT> pl;
-        pl.src[0] = SRC_NONE;
-        pl.code = 0u;
-        return pl;
+    template <class At>
+    __device__ static __forceinline__ T ring_value(const Geo&, int, int, int, int, int, const At&, const T*, const T*) {
+        return (T)0;
     }
-    __device__ static __forceinline__ void eval(const Geo& g, const Coord& c, const T* s_at, T own, const T (&)[1],
-                                                const Plan<T, NEXT>&, T& fx, T& jac) {
+    __device__ static __forceinline__ void eval(const Geo& g, const Coord& c, const T* s_ext, T own, T& fx, T& jac) {
+        using E = ExtTile<VanderPol<T>>;
         const T mu = (T)g.prm[0];
-        const T y1 = s_at[at_index<Shape>(0, 0, c.tcol)];
-        const T y2 = s_at[at_index<Shape>(1, 0, c.tcol)];
+        const T y1 = s_ext[E::index(0, 0, c.tcol)];
+        const T y2 = s_ext[E::index(1, 0, c.tcol)];
         const T damp = mu * ((T)1 - y1 * y1);
         if (c.field == 0) {
             fx = y2;
@@ -218,49 +213,29 @@ struct VanderPol {
 template <typename T>
 struct Lorenz96 {
     using Shape = TileShape<1, 1, 8>;
-    static constexpr int NEXT = 3;   // slots: i-2, i-1, i+1
+    static constexpr int HL = 2, HR = 1, HV = 0;
     // lower halo = points (i0-2, i0-1), upper halo = point i0+cols (all cyclic)
     static __host__ void halo_sizes(const Geo& g, long long& lo, long long& hi) {
         const bool sharded = g.cols != g.gcols;
         lo = sharded ? 2 : 0;
         hi = sharded ? 1 : 0;
     }
-    __device__ static __forceinline__ void outside(const Geo& g, const Coord& c, int off, Plan<T, NEXT>& pl, int s) {
-        // cyclic neighbour col + off that is not inside the tile
-        long long gi = g.gcol0 + c.col + off;
+    template <class At>
+    __device__ static __forceinline__ T ring_value(const Geo& g, int, int col0, int, int, int ec, const At& at,
+                                                   const T* halo_lo, const T* halo_hi) {
+        const long long col = (long long)col0 + ec - HL;          // shard-local, may be outside [0, cols)
+        long long gi = (g.gcol0 + col) % g.gcols;                 // cyclic
         if (gi < 0) gi += g.gcols;
-        if (gi >= g.gcols) gi -= g.gcols;
-        if (gi < 0) gi += g.gcols;          // chains shorter than the stencil reach
         const long long li = gi - g.gcol0;
-        if (li >= 0 && li < g.cols) {
-            pl.src[s] = SRC_MEAN;
-            pl.idx[s] = li;
-        } else if (off < 0) {
-            pl.src[s] = SRC_LO;
-            pl.idx[s] = 2 + ((long long)c.col + off);   // halo_lo = [i0-2, i0-1]
-        } else {
-            pl.src[s] = SRC_HI;
-            pl.idx[s] = 0;
-        }
+        if (li >= 0 && li < g.cols) return at(li);
+        if (col < 0 && col >= -2 && halo_lo) return __ldcg(halo_lo + (2 + col));
+        if (col == g.cols && halo_hi) return __ldcg(halo_hi);
+        return (T)0;                                               // only feeds threads beyond the shard
     }
-    __device__ static __forceinline__ Plan<T, NEXT> plan(const Geo& g, const Coord& c) {
-        Plan<T, NEXT> pl;
-        pl.code = 0u;
-#pragma unroll
-        for (int s = 0; s < NEXT; ++s) pl.src[s] = SRC_NONE;
-        if (!c.valid) return pl;
-        if (c.tcol - 2 < 0) { outside(g, c, -2, pl, 0); pl.code |= 1u; }
-        if (c.tcol - 1 < 0) { outside(g, c, -1, pl, 1); pl.code |= 2u; }
-        if (c.tcol + 1 >= Shape::TC || c.col + 1 >= g.cols) { outside(g, c, +1, pl, 2); pl.code |= 4u; }
-        return pl;
-    }
-    __device__ static __forceinline__ void eval(const Geo& g, const Coord& c, const T* s_at, T own, const T (&ext)[NEXT],
-                                                const Plan<T, NEXT>& pl, T& fx, T& jac) {
+    __device__ static __forceinline__ void eval(const Geo& g, const Coord& c, const T* s_ext, T own, T& fx, T& jac) {
         const T F = (T)g.prm[0];
-        const T ym2 = (pl.code & 1u) ? ext[0] : s_at[c.tcol - 2];
-        const T ym1 = (pl.code & 2u) ? ext[1] : s_at[c.tcol - 1];
-        const T yp1 = (pl.code & 4u) ? ext[2] : s_at[c.tcol + 1];
-        fx = (yp1 - ym2) * ym1 - own + F;
+        const T* p = s_ext + c.tcol;                               // p[HL] is the own point
+        fx = (p[3] - p[0]) * p[1] - own + F;
         jac = (T)-1;
     }
 };
@@ -269,39 +244,29 @@ struct Lorenz96 {
 template <typename T>
 struct Brusselator {
     using Shape = TileShape<2, 1, 4>;
-    static constexpr int NEXT = 2;   // slots: left, right
+    static constexpr int HL = 1, HR = 1, HV = 0;
     static __host__ void halo_sizes(const Geo& g, long long& lo, long long& hi) {
         lo = (g.gcol0 > 0) ? 2 : 0;                  // (u, v) of point i0-1
         hi = (g.gcol0 + g.cols < g.gcols) ? 2 : 0;   // (u, v) of point i0+cols
     }
-    __device__ static __forceinline__ Plan<T, NEXT> plan(const Geo& g, const Coord& c) {
-        Plan<T, NEXT> pl;
-        pl.code = 0u;
-        pl.src[0] = pl.src[1] = SRC_NONE;
-        if (!c.valid) return pl;
-        const T pad = (c.field == 0) ? (T)1 : (T)3;
-        const long long gi = g.gcol0 + c.col;
-        if (gi == 0) { pl.src[0] = SRC_CONST; pl.cval[0] = pad; pl.code |= 1u; }
-        else if (c.tcol == 0) {
-            pl.code |= 1u;
-            if (c.col > 0) { pl.src[0] = SRC_MEAN; pl.idx[0] = c.flat - 1; }
-            else { pl.src[0] = SRC_LO; pl.idx[0] = c.field; }
-        }
-        if (gi == g.gcols - 1) { pl.src[1] = SRC_CONST; pl.cval[1] = pad; pl.code |= 2u; }
-        else if (c.tcol + 1 >= Shape::TC || c.col + 1 >= g.cols) {
-            pl.code |= 2u;
-            if (c.col + 1 < g.cols) { pl.src[1] = SRC_MEAN; pl.idx[1] = c.flat + 1; }
-            else { pl.src[1] = SRC_HI; pl.idx[1] = c.field; }
-        }
-        return pl;
+    template <class At>
+    __device__ static __forceinline__ T ring_value(const Geo& g, int, int col0, int field, int, int ec, const At& at,
+                                                   const T* halo_lo, const T* halo_hi) {
+        const long long col = (long long)col0 + ec - HL;
+        const long long gi = g.gcol0 + col;
+        if (gi < 0 || gi >= g.gcols) return (field == 0) ? (T)1 : (T)3;      // ivp.py:233-236
+        if (col >= 0 && col < g.cols) return at((long long)field * g.npts + col);
+        if (col == -1 && halo_lo) return __ldcg(halo_lo + field);
+        if (col == g.cols && halo_hi) return __ldcg(halo_hi + field);
+        return (T)0;
     }
-    __device__ static __forceinline__ void eval(const Geo& g, const Coord& c, const T* s_at, T own, const T (&ext)[NEXT],
-                                                const Plan<T, NEXT>& pl, T& fx, T& jac) {
+    __device__ static __forceinline__ void eval(const Geo& g, const Coord& c, const T* s_ext, T own, T& fx, T& jac) {
+        using E = ExtTile<Brusselator<T>>;
         const T cc = (T)g.prm[0];
-        const T left = (pl.code & 1u) ? ext[0] : s_at[at_index<Shape>(c.field, 0, c.tcol - 1)];
-        const T right = (pl.code & 2u) ? ext[1] : s_at[at_index<Shape>(c.field, 0, c.tcol + 1)];
-        const T u = s_at[at_index<Shape>(0, 0, c.tcol)];
-        const T v = s_at[at_index<Shape>(1, 0, c.tcol)];
+        const int here = E::index(c.field, 0, c.tcol + HL);
+        const T left = s_ext[here - 1], right = s_ext[here + 1];
+        const T u = s_ext[E::index(0, 0, c.tcol + HL)];
+        const T v = s_ext[E::index(1, 0, c.tcol + HL)];
         const T conv = (left - (T)2 * own) + right;
         const T uu = u * u;
         if (c.field == 0) {
@@ -319,58 +284,35 @@ struct Brusselator {
 template <typename T>
 struct Fhn2d {
     using Shape = TileShape<2, 4, 1>;
-    static constexpr int NEXT = 3;   // slots: up, down, horizontal (left for tcol == 0, right for the last column)
+    static constexpr int HL = 1, HR = 1, HV = 1;
     static __host__ void halo_sizes(const Geo& g, long long& lo, long long& hi) {
         lo = (g.grow0 > 0) ? 2LL * g.cols : 0;                 // row above, both fields
         hi = (g.grow0 + g.rows < g.grows) ? 2LL * g.cols : 0;  // row below
     }
-    // code: bits [1:0] up, [3:2] down, [5:4] left, [7:6] right, each NB_TILE / NB_SELF / NB_EXT
-    __device__ static __forceinline__ Plan<T, NEXT> plan(const Geo& g, const Coord& c) {
-        Plan<T, NEXT> pl;
-        pl.code = 0u;
-#pragma unroll
-        for (int s = 0; s < NEXT; ++s) pl.src[s] = SRC_NONE;
-        if (!c.valid) return pl;
-        const long long gr = g.grow0 + c.row;
-        const long long halo_idx = (long long)c.field * g.cols + c.col;
-        // up
-        if (gr == 0) pl.code |= NB_SELF;
-        else if (c.tr == 0) {
-            pl.code |= NB_EXT;
-            if (c.row > 0) { pl.src[0] = SRC_MEAN; pl.idx[0] = c.flat - g.cols; }
-            else { pl.src[0] = SRC_LO; pl.idx[0] = halo_idx; }
-        }
-        // down
-        if (gr == g.grows - 1) pl.code |= NB_SELF << 2;
-        else if (c.tr + 1 >= Shape::TR || c.row + 1 >= g.rows) {
-            pl.code |= NB_EXT << 2;
-            if (c.row + 1 < g.rows) { pl.src[1] = SRC_MEAN; pl.idx[1] = c.flat + g.cols; }
-            else { pl.src[1] = SRC_HI; pl.idx[1] = halo_idx; }
-        }
-        // left / right share slot 2 (a thread is never both the first and the last column of a 32-wide tile)
-        if (c.col == 0) pl.code |= NB_SELF << 4;
-        else if (c.tcol == 0) { pl.code |= NB_EXT << 4; pl.src[2] = SRC_MEAN; pl.idx[2] = c.flat - 1; }
-        if (c.col == g.cols - 1) pl.code |= NB_SELF << 6;
-        else if (c.tcol + 1 >= Shape::TC) { pl.code |= NB_EXT << 6; pl.src[2] = SRC_MEAN; pl.idx[2] = c.flat + 1; }
-        return pl;
+    template <class At>
+    __device__ static __forceinline__ T ring_value(const Geo& g, int row0, int col0, int field, int er, int ec,
+                                                   const At& at, const T* halo_lo, const T* halo_hi) {
+        // edge replication (ivp.py:488-490) == clamp the coordinates to the global grid
+        long long col = (long long)col0 + ec - HL;
+        col = col < 0 ? 0 : (col > g.cols - 1 ? g.cols - 1 : col);
+        long long gr = g.grow0 + row0 + er - HV;
+        gr = gr < 0 ? 0 : (gr > g.grows - 1 ? g.grows - 1 : gr);
+        const long long row = gr - g.grow0;
+        if (row >= 0 && row < g.rows) return at((long long)field * g.npts + row * g.cols + col);
+        if (row < 0) return halo_lo ? __ldcg(halo_lo + (long long)field * g.cols + col) : (T)0;
+        return halo_hi ? __ldcg(halo_hi + (long long)field * g.cols + col) : (T)0;
     }
-    __device__ static __forceinline__ T pick(unsigned code, T own, T extv, const T* s_at, int idx) {
-        return code == NB_TILE ? s_at[idx] : (code == NB_SELF ? own : extv);
-    }
-    __device__ static __forceinline__ void eval(const Geo& g, const Coord& c, const T* s_at, T own, const T (&ext)[NEXT],
-                                                const Plan<T, NEXT>& pl, T& fx, T& jac) {
+    __device__ static __forceinline__ void eval(const Geo& g, const Coord& c, const T* s_ext, T own, T& fx, T& jac) {
+        using E = ExtTile<Fhn2d<T>>;
         const T inv_dx2 = (T)g.prm[0], a = (T)g.prm[1], b = (T)g.prm[2], k = (T)g.prm[3], inv_tau = (T)g.prm[5];
-        const unsigned cu = pl.code & 3u, cd = (pl.code >> 2) & 3u, cl = (pl.code >> 4) & 3u, cr = (pl.code >> 6) & 3u;
-        const int here = at_index<Shape>(c.field, c.tr, c.tcol);
-        const T up = pick(cu, own, ext[0], s_at, here - Shape::TC);
-        const T dn = pick(cd, own, ext[1], s_at, here + Shape::TC);
-        const T lf = pick(cl, own, ext[2], s_at, here - 1);
-        const T rt = pick(cr, own, ext[2], s_at, here + 1);
+        const int here = E::index(c.field, c.tr + HV, c.tcol + HL);
+        const T up = s_ext[here - E::EC], dn = s_ext[here + E::EC], lf = s_ext[here - 1], rt = s_ext[here + 1];
         const T lap = (((up + dn) + (lf + rt)) - (T)4 * own) * inv_dx2;
-        const int nrep = (int)(cu == NB_SELF) + (int)(cd == NB_SELF) + (int)(cl == NB_SELF) + (int)(cr == NB_SELF);
+        const long long gr = g.grow0 + c.row;
+        const int nrep = (int)(gr == 0) + (int)(gr == g.grows - 1) + (int)(c.col == 0) + (int)(c.col == g.cols - 1);
         const T dl = -(T)(4 - nrep) * inv_dx2;   // ivp.py:447-463: 2 (corner), 3 (edge), 4 (interior)
-        const T u = s_at[at_index<Shape>(0, c.tr, c.tcol)];
-        const T v = s_at[at_index<Shape>(1, c.tr, c.tcol)];
+        const T u = s_ext[E::index(0, c.tr + HV, c.tcol + HL)];
+        const T v = s_ext[E::index(1, c.tr + HV, c.tcol + HL)];
         if (c.field == 0) {
             fx = a * lap + u - u * u * u - v + k;
             jac = a * dl + (T)1 - (T)3 * (u * u);

@@ -62,37 +62,58 @@ struct TileRanges {
 // ---------------------------------------------------------------------------------------------
 template <class IVP, typename T, int N>
 struct FrontRegs {
-    T raw[N];
-    T ext[IVP::NEXT > 0 ? IVP::NEXT : 1];
-    Plan<T, IVP::NEXT> plan;
+    T raw[N];     // this thread's mean column
+    T ring;       // the ring point of the extended tile this thread is responsible for (if any)
+    T fill;       // threads beyond the shard (ragged tiles) publish what their slot means to the valid neighbours:
+                  // the replicated / padded / wrapped value the boundary rule prescribes
 };
+
+// tile-local origin (shard-local row/col of the tile's first point) from a thread's coordinates
+__device__ __forceinline__ int tile_row0(const Coord& c) { return c.row - c.tr; }
+__device__ __forceinline__ int tile_col0(const Coord& c) { return c.col - c.tcol; }
 
 template <class IVP, typename T, int N>
 __device__ __forceinline__ void front_load(const Geo& g, const Consts<T, N>& c, const T* __restrict__ mean_in,
                                            const T* halo_lo, const T* halo_hi, const Coord& co,
                                            FrontRegs<IVP, T, N>& fr) {
+    using E = ExtTile<IVP>;
     const T* src = mean_in + co.flat;
 #pragma unroll
     for (int k = 0; k < N; ++k) {
         fr.raw[k] = co.valid ? __ldg(src) : (T)0;
         src += g.d;
     }
-    fr.plan = IVP::plan(g, co);
+    fr.ring = (T)0;
+    fr.fill = (T)0;
     MeanAt<T, N> at{mean_in, g.d, &c};
-    fetch_ext<T, IVP::NEXT>(fr.plan, at, halo_lo, halo_hi, fr.ext);
+    if (E::NRING > 0 && (int)threadIdx.x < IVP::Shape::NF * E::NRING) {
+        const int field = threadIdx.x / (E::NRING > 0 ? E::NRING : 1);
+        int er, ec;
+        E::ring(threadIdx.x - field * E::NRING, er, ec);
+        fr.ring = IVP::ring_value(g, tile_row0(co), tile_col0(co), field, er, ec, at, halo_lo, halo_hi);
+    }
+    if (E::NRING > 0 && !co.valid)
+        fr.fill = IVP::ring_value(g, tile_row0(co), tile_col0(co), co.field, co.tr + E::HV, co.tcol + E::HL, at, halo_lo,
+                                  halo_hi);
 }
 
 template <class IVP, typename T, int N>
 __device__ __forceinline__ void front_eval(const Geo& g, const Consts<T, N>& c, const Coord& co,
-                                           const FrontRegs<IVP, T, N>& fr, T* s_at, T (&mp)[N], T& fx, T& jac) {
-    using Shape = typename IVP::Shape;
+                                           const FrontRegs<IVP, T, N>& fr, T* s_ext, T (&mp)[N], T& fx, T& jac) {
+    using E = ExtTile<IVP>;
     predict_column<T, N>(fr.raw, c, mp);
-    const T own = c.p[0] * mp[0];
-    s_at[at_index<Shape>(co.field, co.tr, co.tcol)] = own;
+    const T own = co.valid ? c.p[0] * mp[0] : fr.fill;
+    s_ext[E::own(co)] = own;
+    if (E::NRING > 0 && (int)threadIdx.x < IVP::Shape::NF * E::NRING) {
+        const int field = threadIdx.x / (E::NRING > 0 ? E::NRING : 1);
+        int er, ec;
+        E::ring(threadIdx.x - field * E::NRING, er, ec);
+        s_ext[E::index(field, er, ec)] = fr.ring;
+    }
     __syncthreads();
     fx = (T)0;
     jac = (T)0;
-    if (co.valid) IVP::eval(g, co, s_at, own, fr.ext, fr.plan, fx, jac);
+    if (co.valid) IVP::eval(g, co, s_ext, own, fx, jac);
     if (c.flags & 1u) jac = (T)0;   // TDX_STEP_ZERO_JACOBIAN: DiagonalEK0, ek0.py:196-280
 }
 
@@ -205,8 +226,8 @@ __global__ void __launch_bounds__(kThreads, TDX_MIN_BLOCKS) dek1_kernel(const __
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);                       // [2][kWarps]
     double* s_red = reinterpret_cast<double*>(smem_raw + L::BAR_BYTES);
     T* s_at0 = reinterpret_cast<T*>(smem_raw + L::BAR_BYTES + L::RED_BYTES);      // [2][AT_ELEMS]
-    T* s_sc0 = reinterpret_cast<T*>(smem_raw + L::BAR_BYTES + L::RED_BYTES + 2 * L::at_bytes(Shape::AT_ELEMS));
-    constexpr size_t AT_STRIDE = L::at_bytes(Shape::AT_ELEMS) / sizeof(T);
+    T* s_sc0 = reinterpret_cast<T*>(smem_raw + L::BAR_BYTES + L::RED_BYTES + 2 * L::at_bytes(ExtTile<IVP>::ELEMS));
+    constexpr size_t AT_STRIDE = L::at_bytes(ExtTile<IVP>::ELEMS) / sizeof(T);
     constexpr size_t SC_STRIDE = L::sc_bytes() / sizeof(T);
 
     const Geo& g = a.g;
@@ -420,7 +441,7 @@ __global__ void __launch_bounds__(kThreads, 3) ek0_sweep_kernel(const __grid_con
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double* s_red = reinterpret_cast<double*>(smem_raw + L::BAR_BYTES);
     T* s_at0 = reinterpret_cast<T*>(smem_raw + L::BAR_BYTES + L::RED_BYTES);
-    constexpr size_t AT_STRIDE = L::at_bytes(Shape::AT_ELEMS) / sizeof(T);
+    constexpr size_t AT_STRIDE = L::at_bytes(ExtTile<IVP>::ELEMS) / sizeof(T);
     const Geo& g = a.g;
     const Consts<T, N>& c = a.c;
 
@@ -587,18 +608,26 @@ struct EvalArgs {
 template <class IVP, typename T>
 __global__ void __launch_bounds__(kThreads) eval_f_kernel(const __grid_constant__ EvalArgs<T> a) {
     using Shape = typename IVP::Shape;
-    __shared__ T s_at[Shape::AT_ELEMS];
+    using E = ExtTile<IVP>;
+    __shared__ T s_ext[E::ELEMS];
     const Coord co = tile_coord<Shape>(a.g, blockIdx.x, a.tiles_x);
     PlainAt<T> at{a.y};
-    const T own = co.valid ? __ldg(a.y + co.flat) : (T)0;
-    const Plan<T, IVP::NEXT> pl = IVP::plan(a.g, co);
-    T ext[IVP::NEXT > 0 ? IVP::NEXT : 1];
-    fetch_ext<T, IVP::NEXT>(pl, at, a.halo_lo, a.halo_hi, ext);
-    s_at[at_index<Shape>(co.field, co.tr, co.tcol)] = own;
+    const T own = co.valid ? __ldg(a.y + co.flat)
+                           : (E::NRING > 0 ? IVP::ring_value(a.g, tile_row0(co), tile_col0(co), co.field, co.tr + E::HV,
+                                                             co.tcol + E::HL, at, a.halo_lo, a.halo_hi)
+                                           : (T)0);
+    s_ext[E::own(co)] = own;
+    if (E::NRING > 0 && (int)threadIdx.x < Shape::NF * E::NRING) {
+        const int field = threadIdx.x / (E::NRING > 0 ? E::NRING : 1);
+        int er, ec;
+        E::ring(threadIdx.x - field * E::NRING, er, ec);
+        s_ext[E::index(field, er, ec)] =
+            IVP::ring_value(a.g, tile_row0(co), tile_col0(co), field, er, ec, at, a.halo_lo, a.halo_hi);
+    }
     __syncthreads();
     if (co.valid) {
         T fx, jac;
-        IVP::eval(a.g, co, s_at, own, ext, pl, fx, jac);
+        IVP::eval(a.g, co, s_ext, own, fx, jac);
         a.fy[co.flat] = fx;
         if (a.jd) a.jd[co.flat] = jac;
     }

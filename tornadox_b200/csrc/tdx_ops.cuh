@@ -154,7 +154,7 @@ struct Launch {
         const bool comm = ws.pack.enabled || ws.wait.flag_lo || ws.wait.flag_hi || ws.reduce.world > 0 || force_comm_kernel();
         TDX_SWITCH_IVP(g.kind, T, {
             using Shape = typename IVP::Shape;
-            const size_t smem = DekSmem<T, N>::total(Shape::AT_ELEMS);
+            const size_t smem = DekSmem<T, N>::total(ExtTile<IVP>::ELEMS);
             a.tiles_x = (unsigned)((g.cols + Shape::TC - 1) / Shape::TC);
             const unsigned tiles_y = (unsigned)((g.rows + Shape::TR - 1) / Shape::TR);
             a.ranges = tile_ranges(h.flags, a.tiles_x, tiles_y, ws.has_lo, ws.has_hi, g.kind == IVP_FHN2D,
@@ -207,7 +207,7 @@ struct Launch {
     static int ek0_sweep(const Geo& g, Ek0Args<T, N>& a, unsigned flags, const Workspace& ws, cudaStream_t st) {
         TDX_SWITCH_IVP(g.kind, T, {
             using Shape = typename IVP::Shape;
-            const size_t smem = L::BAR_BYTES + L::RED_BYTES + 2 * L::at_bytes(Shape::AT_ELEMS);
+            const size_t smem = L::BAR_BYTES + L::RED_BYTES + 2 * L::at_bytes(ExtTile<IVP>::ELEMS);
             constexpr auto kern = ek0_sweep_kernel<IVP, T, N, kUpdate>;
             a.tiles_x = (unsigned)((g.cols + Shape::TC - 1) / Shape::TC);
             const unsigned tiles_y = (unsigned)((g.rows + Shape::TR - 1) / Shape::TR);
