@@ -160,6 +160,7 @@ struct tdx_ctx {
     bool comm_opened[kMaxWorld] = {};
     int rank = 0, world = 1, lower = -1, upper = -1;
     unsigned long long halo_seq = 0, red_seq = 0;
+    unsigned long long mid_seq = 0;  // fused EK0 launches so far (the in-kernel barrier flag counts them)
     long long halo_cap = 0;          // elements per parity and side
 };
 
@@ -312,7 +313,8 @@ int tdx_set_problem(tdx_ctx* ctx, const tdx_problem_desc* d) {
         case IVP_FHN2D: Fhn2d<double>::halo_sizes(g, lo, hi); break;
     }
 
-    const long long grid = grid_for(g);
+    long long grid = grid_for(g);
+    if (grid < 4096) grid = 4096;   // the fused EK0 kernel stores two partial sums per resident CTA
     if (grid > 2147483647LL) return fail(TDX_ERR_INVALID, "tdx_set_problem: shard too large for one launch");
     int prev = 0;
     cudaGetDevice(&prev);
@@ -701,16 +703,57 @@ int tdx_comm_error(tdx_ctx* ctx, int* error_out, void* stream) {
     return TDX_OK;
 }
 
+static bool three_phase_forced() {
+    static const bool on = std::getenv("TDX_EK0_THREE_PHASE") != nullptr;   // experiments / A-B comparison only
+    return on;
+}
+
 int tdx_ek0_attempt_step(tdx_ctx* ctx, const tdx_step_args* args, const void* mean_in, const void* Cl_in,
                          void* mean_out, void* Cl_out, void* err_out, void* ref_out, double* z_sq_sum,
                          double* sq_norm_sum, void* stream) {
     int rc = check_ready(ctx, "tdx_ek0_attempt_step");
     if (rc) return rc;
-    if (ctx->halo_lo > 0 || ctx->halo_hi > 0)
-        return fail(TDX_ERR_INVALID, "tdx_ek0_attempt_step: sharded contexts must call the three phases and all-reduce in between");
-    if ((rc = tdx_ek0_sweep_a(ctx, args, mean_in, nullptr, nullptr, z_sq_sum, stream))) return rc;
-    if ((rc = tdx_ek0_mid(ctx, args, Cl_in, z_sq_sum, (int64_t)ctx->geo.d, Cl_out, err_out, stream))) return rc;
-    return tdx_ek0_sweep_b(ctx, args, mean_in, mean_out, ref_out, nullptr, nullptr, sq_norm_sum, stream);
+    if ((rc = check_dt(args, "tdx_ek0_attempt_step"))) return rc;
+    const bool sharded = ctx->halo_lo > 0 || ctx->halo_hi > 0;
+    const unsigned comm_flags = TDX_STEP_COMM_PACK | TDX_STEP_COMM_REDUCE;
+    if (sharded && (args->flags & comm_flags) != comm_flags)
+        return fail(TDX_ERR_INVALID,
+                    "tdx_ek0_attempt_step: a sharded context needs TDX_STEP_COMM_PACK | TDX_STEP_COMM_REDUCE (peer-memory "
+                    "exchange), or the three phases with the caller's own all-reduce in between");
+    if (args->flags & 6u) return fail(TDX_ERR_INVALID, "tdx_ek0_attempt_step: partial tile ranges are not supported");
+    if (!z_sq_sum) return fail(TDX_ERR_INVALID, "tdx_ek0_attempt_step: z_sq_sum is required");
+    const int64_t d_global = (int64_t)ctx->geo.nf * ctx->geo.grows * ctx->geo.gcols;
+    if (ctx->geo.kind != IVP_FHN2D || three_phase_forced()) {
+        tdx_step_args a = *args, b = *args;
+        if (!sharded) a.flags = b.flags = args->flags & TDX_STEP_ZERO_JACOBIAN;
+        else b.flags = (args->flags & ~TDX_STEP_COMM_PACK) | TDX_STEP_COMM_HALO;
+        if ((rc = tdx_ek0_sweep_a(ctx, &a, mean_in, nullptr, nullptr, z_sq_sum, stream))) return rc;
+        if ((rc = tdx_ek0_mid(ctx, args, Cl_in, z_sq_sum, d_global, Cl_out, err_out, stream))) return rc;
+        return tdx_ek0_sweep_b(ctx, &b, mean_in, mean_out, ref_out, nullptr, nullptr, sq_norm_sum, stream);
+    }
+    // fhn_2d: the whole attempt is one cooperative launch
+    const unsigned flags = sharded ? args->flags : 0u;
+    if ((rc = comm_pack_begin(ctx, flags, "tdx_ek0_attempt_step"))) return rc;
+    const void* halo_lo = nullptr;
+    const void* halo_hi = nullptr;
+    resolve_halos(ctx, flags, halo_lo, halo_hi);
+    if (!mean_in || !mean_out || !Cl_in || !Cl_out || !err_out) return fail(TDX_ERR_INVALID, "tdx_ek0_attempt_step: null buffer");
+    if (mean_in == mean_out) return fail(TDX_ERR_INVALID, "tdx_ek0_attempt_step: in and out buffers must be distinct");
+    StepHost h = make_step(ctx, args);
+    if (h.want_norm && !sq_norm_sum) return fail(TDX_ERR_INVALID, "tdx_ek0_attempt_step: sq_norm_sum is required with tolerances");
+    if ((rc = comm_reduce_begin(ctx, flags, true, "tdx_ek0_attempt_step"))) return rc;
+    Workspace ws = make_ws(ctx, flags);
+    if ((rc = comm_reduce_begin(ctx, flags, h.want_norm != 0, "tdx_ek0_attempt_step"))) return rc;
+    CommReduce reduce_b = ws.reduce;
+    reduce_b.seq = ctx->red_seq;
+    ctx->mid_seq += 1;
+    DeviceGuard guard(ctx->device);
+    ctx->launches += 1;
+    unsigned long long* mid_flag = reinterpret_cast<unsigned long long*>(static_cast<unsigned char*>(ctx->mid) + 128);
+    return cuda_fail(ctx->ops->ek0_fused(ctx->geo, h, mean_in, Cl_in, mean_out, Cl_out, err_out, ref_out, halo_lo, halo_hi, ws,
+                                         reduce_b, mid_flag, ctx->mid_seq, (double)d_global, z_sq_sum, sq_norm_sum,
+                                         (cudaStream_t)stream),
+                     "tdx_ek0_attempt_step");
 }
 
 }  // extern "C"

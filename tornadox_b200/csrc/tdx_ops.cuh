@@ -4,6 +4,7 @@
 #include <cstdlib>
 
 #include "tdx_kernels.cuh"
+#include "tdx_ek0_fused.cuh"
 
 namespace tdx {
 
@@ -55,10 +56,17 @@ struct Ops {
                    void* err_out, const Workspace&, cudaStream_t);
     int (*ek0_b)(const Geo&, const StepHost&, const void* mean_in, void* mean_out, void* ref_out, const void* halo_lo,
                  const void* halo_hi, const Workspace&, double* out_sum, cudaStream_t);
+    // whole KroneckerEK0 attempt in one cooperative launch (fhn_2d only; returns kNoFusedKernel otherwise)
+    int (*ek0_fused)(const Geo&, const StepHost&, const void* mean_in, const void* Cl_in, void* mean_out, void* Cl_out,
+                     void* err_out, void* ref_out, const void* halo_lo, const void* halo_hi, const Workspace&,
+                     const CommReduce& reduce_b, unsigned long long* mid_flag, unsigned long long mid_seq,
+                     double d_global, double* z_sq_out, double* out_sum, cudaStream_t);
     int (*pack)(const Geo&, const StepHost&, const void* mean_in, void* edge_first, void* edge_last, int n_first,
                 int n_last, cudaStream_t);
     int (*pack_peer)(const Geo&, const StepHost&, const void* mean_in, const PackPeer<double>& pk, cudaStream_t);
 };
+
+constexpr int kNoFusedKernel = -2;
 
 struct EvalOps {
     int (*eval_f)(const Geo&, const void* y, void* fy, void* jd, const void* halo_lo, const void* halo_hi,
@@ -94,7 +102,7 @@ inline Consts<T, N> make_consts(const StepHost& h) {
 // grid of a persistent kernel: as many CTAs as fit on the device at once, at most one per tile.
 // The occupancy query and the shared-memory opt-in are done once per (kernel instantiation, device).
 template <auto kern>
-inline cudaError_t persistent_grid(size_t smem, long long tiles, int reserve, unsigned& grid) {
+inline cudaError_t persistent_grid(size_t smem, long long tiles, int reserve, unsigned& grid, int threads = kThreads) {
     constexpr int kMaxDevices = 64;
     static int resident_cache[kMaxDevices] = {};     // one static per kernel FUNCTION (non-type template parameter)
     int dev = 0;
@@ -105,7 +113,7 @@ inline cudaError_t persistent_grid(size_t smem, long long tiles, int reserve, un
         if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
         int sms = 0, per_sm = 0;
         if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
-        if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, smem)) != cudaSuccess) return e;
+        if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem)) != cudaSuccess) return e;
         if (per_sm < 1) return cudaErrorLaunchOutOfResources;
         resident = sms * per_sm;
         if (dev >= 0 && dev < kMaxDevices) resident_cache[dev] = resident;
@@ -239,6 +247,64 @@ struct Launch {
         return (int)cudaGetLastError();
     }
 
+    static int ek0_fused(const Geo& g, const StepHost& h, const void* mean_in, const void* Cl_in, void* mean_out,
+                         void* Cl_out, void* err_out, void* ref_out, const void* halo_lo, const void* halo_hi,
+                         const Workspace& ws, const CommReduce& reduce_b, unsigned long long* mid_flag,
+                         unsigned long long mid_seq, double d_global, double* z_sq_out, double* out_sum,
+                         cudaStream_t st) {
+        if (g.kind != IVP_FHN2D) return kNoFusedKernel;
+        constexpr int W = 256;
+        using Cfg = Ek0FusedCfg<T, N, W>;
+        constexpr auto kern = ek0_fused_fhn_kernel<T, N, W>;
+        Ek0FusedArgs<T, N> a;
+        a.g = g;
+        a.c = make_consts<T, N>(h);
+        a.cd = make_consts<double, N>(h);
+        a.mean_in = (const T*)mean_in;
+        a.mean_out = (T*)mean_out;
+        a.ref_out = (T*)ref_out;
+        a.halo_lo = (const T*)halo_lo;
+        a.halo_hi = (const T*)halo_hi;
+        a.Cl_in = (const T*)Cl_in;
+        a.Cl_out = (T*)Cl_out;
+        a.err_out = (T*)err_out;
+        a.mid = (Ek0Mid<T, N>*)ws.mid;
+        a.mid_flag = mid_flag;
+        a.mid_seq = mid_seq;
+        a.partials = ws.partials;
+        a.ticket = ws.ticket;
+        a.z_sq_out = z_sq_out;
+        a.out_sum = out_sum;
+        a.d_global = d_global;
+        a.wait = ws.wait;
+        a.reduce_a = ws.reduce;
+        a.reduce_b = reduce_b;
+        a.pack = typed_pack(ws.pack);
+        constexpr int PADC = Cfg::PADC;
+        a.use_bulk = (g.cols % PADC == 0) && ((reinterpret_cast<uintptr_t>(mean_in) & 15) == 0) ? 1 : 0;
+        unsigned resident = 0;
+        TDX_CUDA_TRY(persistent_grid<kern>(Cfg::total(), 1LL << 40, 0, resident, W));
+        a.col_blocks = (unsigned)((g.cols + W - 1) / W);
+        unsigned chunks = resident / a.col_blocks;
+        if (chunks < 1u) chunks = 1u;
+        if (chunks > (unsigned)g.rows) chunks = (unsigned)g.rows;
+        a.chunks = chunks;
+        a.total_strips = a.col_blocks * chunks;
+        const unsigned grid = a.total_strips < resident ? a.total_strips : resident;
+        if (a.pack.enabled && grid < 2u * kPackCtas) {   // tiny shard: deliver the halos with their own launch
+            PackPeerArgs<T, N> pa;
+            pa.g = g;
+            pa.c = a.c;
+            pa.mean_in = a.mean_in;
+            pa.pk = a.pack;
+            pack_halo_peer_kernel<T, N><<<2 * kPackCtas, 1024, 0, st>>>(pa);
+            a.pack.enabled = 0;
+        }
+        void* params[] = {(void*)&a};
+        TDX_CUDA_TRY(cudaLaunchCooperativeKernel((const void*)kern, dim3(grid), dim3(W), params, Cfg::total(), st));
+        return (int)cudaGetLastError();
+    }
+
     static int ek0_a(const Geo& g, const StepHost& h, const void* mean_in, const void* halo_lo, const void* halo_hi,
                      const Workspace& ws, double* out_sum, cudaStream_t st) {
         Ek0Args<T, N> a = ek0_args(g, h, mean_in, nullptr, nullptr, halo_lo, halo_hi, ws, out_sum);
@@ -313,6 +379,7 @@ struct Launch {
         o.ek0_a = &ek0_a;
         o.ek0_mid = &ek0_mid;
         o.ek0_b = &ek0_b;
+        o.ek0_fused = &ek0_fused;
         o.pack = &pack;
         o.pack_peer = &pack_peer;
         return o;

@@ -346,14 +346,13 @@ class StepEngine:
         st = self._stream()
         want_norm = abstol != 0.0 or reltol != 0.0
         args = self._args(t, dt, abstol, reltol)
-        if self.world > 1 and self.peer:
-            comm = self._args(t, dt, abstol, reltol, _lib.TDX_STEP_COMM_HALO | _lib.TDX_STEP_COMM_REDUCE)
-            first = self._args(t, dt, abstol, reltol, _lib.TDX_STEP_COMM_PACK | _lib.TDX_STEP_COMM_REDUCE)
-            _lib.check(self.lib.tdx_ek0_sweep_a(self.handle, ctypes.byref(first), _ptr(mean), None, None, _ptr(zsq[0:1]), st))
-            _lib.check(self.lib.tdx_ek0_mid(self.handle, ctypes.byref(args), _ptr(Cl), _ptr(zsq), self.d_global,
-                                            _ptr(Cl_out), _ptr(err), st))
-            _lib.check(self.lib.tdx_ek0_sweep_b(self.handle, ctypes.byref(comm), _ptr(mean), _ptr(mean_out), _ptr(ref),
-                                                None, None, _ptr(itol), st))
+        if self.world == 1 or self.peer:
+            # ONE call per attempt (fhn_2d: one cooperative launch that holds both sweeps, the calibration and, on
+            # several GPUs, the halo delivery and both scalar all-reduces over NVLink peer memory)
+            flags = (_lib.TDX_STEP_COMM_PACK | _lib.TDX_STEP_COMM_REDUCE) if self.world > 1 else 0
+            one = self._args(t, dt, abstol, reltol, flags)
+            _lib.check(self.lib.tdx_ek0_attempt_step(self.handle, ctypes.byref(one), _ptr(mean), _ptr(Cl), _ptr(mean_out),
+                                                     _ptr(Cl_out), _ptr(err), _ptr(ref), _ptr(zsq[0:1]), _ptr(itol), st))
             return mean_out, Cl_out, err, ref, itol
         if self.world > 1 and self.overlap:
             halo_lo, halo_hi, ready = self._halos_overlapped(dt, mean)
