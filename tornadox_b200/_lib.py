@@ -11,7 +11,7 @@ import pathlib
 import numpy as np
 
 _PKG = pathlib.Path(__file__).resolve().parent
-LIB_PATH = _PKG / "lib" / "libtornadox_b200.so"
+LIB_PATH = pathlib.Path(os.environ.get("TDX_LIB", _PKG / "lib" / "libtornadox_b200.so"))   # TDX_LIB: tuning variants
 
 TDX_F64, TDX_F32 = 0, 1
 TDX_STEP_ZERO_JACOBIAN = 1

@@ -46,8 +46,8 @@ def _stamp():
 
 
 def _compile_one(args):
-    nvcc, src, obj, verbose = args
-    cmd = [nvcc, *NVCC_FLAGS, "-c", str(src), "-o", str(obj)]
+    nvcc, src, obj, verbose, defines = args
+    cmd = [nvcc, *NVCC_FLAGS, *defines, "-c", str(src), "-o", str(obj)]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError(f"nvcc failed for {src.name}:\n{res.stdout}\n{res.stderr}")
@@ -57,26 +57,33 @@ def _compile_one(args):
     return obj
 
 
-def build(force=False, verbose=False):
-    """Compile every .cu under csrc/ (in parallel) and link the shared library.  Returns its path."""
+def build(force=False, verbose=False, defines=(), variant=""):
+    """Compile every .cu under csrc/ (in parallel) and link the shared library.  Returns its path.
+
+    ``variant`` / ``defines`` build an experimental copy ``libtornadox_b200_<variant>.so`` with extra -D flags
+    (tuning experiments; select it at run time with the environment variable TDX_LIB)."""
     OUT_DIR.mkdir(exist_ok=True)
-    OBJ_DIR.mkdir(exist_ok=True)
-    stamp_file = OUT_DIR / "build.stamp"
-    stamp = _stamp()
-    if not force and LIB.exists() and stamp_file.exists() and stamp_file.read_text() == stamp:
-        return LIB
+    lib = LIB if not variant else OUT_DIR / f"libtornadox_b200_{variant}.so"
+    obj_dir = OBJ_DIR if not variant else OUT_DIR / f"obj_{variant}"
+    obj_dir.mkdir(exist_ok=True)
+    stamp_file = OUT_DIR / ("build.stamp" if not variant else f"build_{variant}.stamp")
+    stamp = _stamp() + " ".join(defines)
+    if not force and lib.exists() and stamp_file.exists() and stamp_file.read_text() == stamp:
+        return lib
     nvcc = _nvcc()
-    jobs = [(nvcc, src, OBJ_DIR / (src.stem + ".o"), verbose) for src in _sources()]
+    jobs = [(nvcc, src, obj_dir / (src.stem + ".o"), verbose, list(defines)) for src in _sources()]
     with concurrent.futures.ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 4)) as pool:
         objs = list(pool.map(_compile_one, jobs))
-    link = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(LIB), *map(str, objs), "-lcudart"]
+    link = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(lib), *map(str, objs), "-lcudart"]
     res = subprocess.run(link, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError(f"link failed:\n{res.stdout}\n{res.stderr}")
     stamp_file.write_text(stamp)
-    return LIB
+    return lib
 
 
 if __name__ == "__main__":
-    path = build(force="--force" in sys.argv, verbose="--verbose" in sys.argv)
+    extra = [a for a in sys.argv[1:] if a.startswith("-D")]
+    var = next((a.split("=", 1)[1] for a in sys.argv[1:] if a.startswith("--variant=")), "")
+    path = build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, defines=extra, variant=var)
     print(path)

@@ -474,32 +474,46 @@ __device__ __forceinline__ void spin_until(const unsigned long long* flag, unsig
         __nanosleep(100);
     }
 }
+// Who takes part in a CTA-level helper: the whole CTA (barrier 0), or the first COUNT threads through a named barrier
+// (warp-specialised kernels whose producer warp must not be waited for).
+struct FullSync {
+    __device__ __forceinline__ void operator()() const { __syncthreads(); }
+    __device__ __forceinline__ int threads() const { return (int)blockDim.x; }
+};
+template <int ID, int COUNT>
+struct NamedSync {
+    __device__ __forceinline__ void operator()() const { asm volatile("bar.sync %0, %1;" ::"n"(ID), "n"(COUNT) : "memory"); }
+    __device__ __forceinline__ int threads() const { return COUNT; }
+};
+
 // one thread per CTA waits, the barrier releases the rest
-__device__ __forceinline__ void cta_wait_halos(const CommWait& w) {
+template <class Sync = FullSync>
+__device__ __forceinline__ void cta_wait_halos(const CommWait& w, Sync sync = Sync()) {
     if (w.flag_lo == nullptr && w.flag_hi == nullptr) return;
     if (threadIdx.x == 0) {
         spin_until(w.flag_lo, w.seq, w.error);
         spin_until(w.flag_hi, w.seq, w.error);
     }
-    __syncthreads();
+    sync();
 }
 
 // Sum ``v`` (held by thread 0 of ONE CTA) over all ranks in rank order through the peers' reduction slots.
 // Called by every thread of that CTA; returns the global sum in thread 0.
-__device__ __forceinline__ double cta_allreduce(double v, const CommReduce& cr, double* s_red) {
+template <class Sync = FullSync>
+__device__ __forceinline__ double cta_allreduce(double v, const CommReduce& cr, double* s_red, Sync sync = Sync()) {
     const int r = threadIdx.x;
     const int parity = (int)(cr.seq & 1ull);
     if (r == 0) s_red[0] = v;
-    __syncthreads();
+    sync();
     if (r < cr.world) {
         CommHeader* dst = cr.peer[r];
         dst->red_val[parity][cr.rank][0] = s_red[0];
         __threadfence_system();
         st_release_sys(&dst->red_flag[parity][cr.rank], cr.seq);
     }
-    __syncthreads();
+    sync();
     if (r < cr.world) spin_until(&cr.local->red_flag[parity][r], cr.seq, &cr.local->error);
-    __syncthreads();
+    sync();
     double acc = 0.0;
     if (r == 0)
         for (int k = 0; k < cr.world; ++k) acc += *((volatile double*)&cr.local->red_val[parity][k][0]);

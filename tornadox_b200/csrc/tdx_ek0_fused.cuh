@@ -25,7 +25,7 @@ namespace tdx {
 
 template <typename T, int N, int W_>
 struct Ek0FusedCfg {
-    static constexpr int W = W_;                          // columns per strip == threads per CTA
+    static constexpr int W = W_;                          // columns per strip == consumer threads per CTA (+ one producer warp)
     static constexpr int PADC = 16 / (int)sizeof(T);      // columns of left/right overlap (16-byte granularity of TMA)
     static constexpr int WP = W + 2 * PADC;
     static constexpr int STAGES = 4;
@@ -116,13 +116,14 @@ __device__ __noinline__ void ek0_mid_compute(const Consts<double, N>& c, const T
     mid->err = err;
 }
 
-// per-CTA partial -> global memory; returns (CTA-uniform) whether this CTA arrived last
-__device__ __forceinline__ bool publish_partial(double v, double* s_red, double* partials, unsigned int* ticket) {
-    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = (blockDim.x + 31) >> 5;
+// per-CTA partial -> global memory; returns (uniform over the participants) whether this CTA arrived last
+template <class Sync>
+__device__ __forceinline__ bool publish_partial(double v, double* s_red, double* partials, unsigned int* ticket, Sync sync) {
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = (sync.threads() + 31) >> 5;
     v = warp_sum(v);
-    __syncthreads();                 // s_red may still be read by a previous use
+    sync();                          // s_red may still be read by a previous use
     if (lane == 0) s_red[w] = v;
-    __syncthreads();
+    sync();
     if (threadIdx.x == 0) {
         double b = 0.0;
         for (int i = 0; i < nw; ++i) b += s_red[i];
@@ -131,32 +132,30 @@ __device__ __forceinline__ bool publish_partial(double v, double* s_red, double*
         const unsigned int t = atomicAdd(ticket, 1u);
         s_red[31] = (t == gridDim.x - 1) ? 1.0 : 0.0;
     }
-    __syncthreads();
+    sync();
     return s_red[31] != 0.0;
 }
 
-// all threads of the last CTA: the partials in a fixed order; the result is valid in thread 0
-__device__ __forceinline__ double sum_partials(double* s_red, const double* partials) {
-    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = (blockDim.x + 31) >> 5;
+// the participants of the last CTA: the partials in a fixed order; the result is valid in thread 0
+template <class Sync>
+__device__ __forceinline__ double sum_partials(double* s_red, const double* partials, Sync sync) {
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = (sync.threads() + 31) >> 5;
     __threadfence();
     double acc = 0.0;
-    for (unsigned int i = threadIdx.x; i < gridDim.x; i += blockDim.x) acc += __ldcg(partials + i);
+    for (unsigned int i = threadIdx.x; i < gridDim.x; i += sync.threads()) acc += __ldcg(partials + i);
     acc = warp_sum(acc);
-    __syncthreads();
+    sync();
     if (lane == 0) s_red[w] = acc;
-    __syncthreads();
+    sync();
     double b = 0.0;
     if (threadIdx.x == 0)
         for (int i = 0; i < nw; ++i) b += s_red[i];
     return b;
 }
 
-// Enumeration of the (strip, row) items a CTA walks: phase 0 its strips in order, phase 1 the same strips backwards
-// with the row direction flipped.  The TMA producer runs the same enumeration STAGES items ahead of the consumer.
-struct ItemIter {
-    int phase, k, i, L, ns;
-    StripGeom s;
-};
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 
 template <int W>
 __device__ __forceinline__ StripGeom strip_geom(const Geo& g, unsigned strip, unsigned col_blocks, unsigned chunks,
@@ -172,47 +171,15 @@ __device__ __forceinline__ StripGeom strip_geom(const Geo& g, unsigned strip, un
     return s;
 }
 
-template <int W, typename Args>
-__device__ __forceinline__ void iter_load(ItemIter& it, const Args& a) {
-    if (it.phase >= 2) return;
-    it.s = strip_geom<W>(a.g, blockIdx.x + (unsigned)it.k * gridDim.x, a.col_blocks, a.chunks, a.halo_lo != nullptr,
-                         a.halo_hi != nullptr);
-    if (it.phase == 1) it.s.dir = -it.s.dir;
-    it.L = it.s.r1 - it.s.r0 + 2;
-}
-template <int W, typename Args>
-__device__ __forceinline__ void iter_init(ItemIter& it, const Args& a) {
-    it.ns = (int)((a.total_strips - blockIdx.x + gridDim.x - 1) / gridDim.x);
-    it.phase = it.ns > 0 ? 0 : 2;
-    it.k = 0;
-    it.i = 0;
-    iter_load<W>(it, a);
-}
-template <int W, typename Args>
-__device__ __forceinline__ void iter_next(ItemIter& it, const Args& a) {
-    if (it.phase >= 2) return;
-    if (++it.i < it.L) return;
-    it.i = 0;
-    if (it.phase == 0) {
-        if (++it.k == it.ns) {
-            it.phase = 1;
-            it.k = it.ns - 1;
-        }
-    } else if (--it.k < 0) {
-        it.phase = 2;
-    }
-    iter_load<W>(it, a);
-}
-__device__ __forceinline__ int iter_row(const ItemIter& it) {
-    return it.s.dir > 0 ? it.s.r0 - 1 + it.i : it.s.r1 - it.i;
-}
-
+// Threads [0, W): consumers, thread t owns column c0 + t of both fields.  Threads [W, W + 32): the producer warp.
 template <typename T, int N, int W>
-__global__ void __launch_bounds__(W, 2) ek0_fused_fhn_kernel(const __grid_constant__ Ek0FusedArgs<T, N> a) {
+__global__ void __launch_bounds__(W + 32, 2) ek0_fused_fhn_kernel(const __grid_constant__ Ek0FusedArgs<T, N> a) {
     using Cfg = Ek0FusedCfg<T, N, W>;
+    using CSync = NamedSync<1, W>;                         // the consumers' barrier (the producer warp never joins)
     constexpr int PADC = Cfg::PADC, WP = Cfg::WP, S = Cfg::STAGES, AT_ROW = Cfg::AT_ROW;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);                                   // [S]
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);                                   // [S] data has landed
+    uint64_t* empty = full + S;                                                               // [S] consumers are done
     double* s_red = reinterpret_cast<double*>(smem_raw + Cfg::BAR_BYTES);                     // [32]
     T* s_at = reinterpret_cast<T*>(smem_raw + Cfg::BAR_BYTES + Cfg::RED_BYTES);               // [2][2][AT_ROW]
     T* s_stage = reinterpret_cast<T*>(smem_raw + Cfg::BAR_BYTES + Cfg::RED_BYTES + Cfg::at_bytes());
@@ -220,63 +187,76 @@ __global__ void __launch_bounds__(W, 2) ek0_fused_fhn_kernel(const __grid_consta
     const Geo& g = a.g;
     const Consts<T, N>& c = a.c;
     const int tc = threadIdx.x;
-    const T inv_dx2 = (T)g.prm[0], pa = (T)g.prm[1], pb = (T)g.prm[2], pk = (T)g.prm[3], inv_tau = (T)g.prm[5];
+    const bool has_lo = a.halo_lo != nullptr, has_hi = a.halo_hi != nullptr;
+    const int ns = (int)((a.total_strips - blockIdx.x + gridDim.x - 1) / gridDim.x);   // strips of this CTA
 
     if (tc == 0) {
 #pragma unroll
-        for (int s = 0; s < S; ++s) mbar_init(full + s, 1);
+        for (int s = 0; s < S; ++s) {
+            mbar_init(full + s, 1);
+            mbar_init(empty + s, 1);
+        }
         fence_mbar_init();
         fence_proxy_async();
     }
     __syncthreads();
 
-    // deliver this shard's edge rows to the neighbours before anything else (multi-GPU)
-    if (a.pack.enabled && blockIdx.x < 2 * kPackCtas) pack_halo_part<T, N>(g, c, a.mean_in, a.pack, (int)blockIdx.x);
-
-    // ---- producer: fill stage (pq % S) with the raw mean rows of the producer's current item ---------------------
-    ItemIter pit;
-    iter_init<W>(pit, a);
-    unsigned pq = 0;
-    auto produce = [&]() {
-        if (pit.phase < 2) {
-            const int rr = iter_row(pit);
-            if (rr >= 0 && rr < g.rows) {
-                T* dst = s_stage + (size_t)(pq % S) * Cfg::STAGE_ELEMS;
-                const int gs = max(pit.s.c0 - PADC, 0), ge = min(pit.s.c0 + W + PADC, g.cols);
-                const int off = gs - (pit.s.c0 - PADC);
-                const T* src = a.mean_in + (long long)rr * g.cols + gs;
-                if (a.use_bulk) {
-                    if (tc == 0) {
-                        uint64_t* bar = full + (pq % S);
-                        const uint32_t bytes = (uint32_t)((ge - gs) * (int)sizeof(T));
-                        mbar_expect_tx(bar, 2u * N * bytes);
-#pragma unroll
-                        for (int f = 0; f < 2; ++f)
-#pragma unroll
-                            for (int k = 0; k < N; ++k)
-                                bulk_g2s(dst + (f * N + k) * WP + off, src + (long long)k * g.d + (long long)f * g.npts, bytes, bar);
-                    }
-                } else {
-                    for (int seg = 0; seg < 2 * N; ++seg) {
-                        const int f = seg / N, k = seg - f * N;
-                        const T* sp = src + (long long)k * g.d + (long long)f * g.npts;
-                        for (int j = tc; j < ge - gs; j += W) dst[seg * WP + off + j] = __ldg(sp + j);
+    if (tc >= W) {
+        // ---- producer warp: walks the same (strip, row) enumeration as the consumers, up to S rows ahead ------------
+        // Every item owns ring slot q % S (items beyond the shard simply load nothing).  The 2 n row segments of a
+        // row are issued by 2 n lanes in one instruction.
+        const int lane = tc - W;
+        const int seg_f = lane / N, seg_k = lane - seg_f * N;           // (field, derivative) of this lane's segment
+        const long long seg_src = (long long)seg_k * g.d + (long long)seg_f * g.npts;
+        const int seg_dst = (seg_f * N + seg_k) * WP;
+        unsigned q = 0;
+#pragma unroll 1
+        for (int phase = 0; phase < 2; ++phase) {
+#pragma unroll 1
+            for (int kk = 0; kk < ns; ++kk) {
+                const int k = phase ? ns - 1 - kk : kk;
+                StripGeom s = strip_geom<W>(g, blockIdx.x + (unsigned)k * gridDim.x, a.col_blocks, a.chunks, has_lo, has_hi);
+                if (phase) s.dir = -s.dir;
+                const int L = s.r1 - s.r0 + 2;
+                const int gs = max(s.c0 - PADC, 0), ge = min(s.c0 + W + PADC, g.cols);
+                const int off = gs - (s.c0 - PADC);
+                const uint32_t bytes = (uint32_t)((ge - gs) * (int)sizeof(T));
+                int rr = s.dir > 0 ? s.r0 - 1 : s.r1;
+#pragma unroll 1
+                for (int i = 0; i < L; ++i, rr += s.dir, ++q) {
+                    const unsigned stage = q % S, round = q / S;
+                    if (round > 0) mbar_wait(empty + stage, (round - 1u) & 1u);     // the slot's previous row is consumed
+                    if (rr < 0 || rr >= g.rows) continue;
+                    T* dst = s_stage + (size_t)stage * Cfg::STAGE_ELEMS;
+                    const T* src = a.mean_in + (long long)rr * g.cols + gs;
+                    if (a.use_bulk) {
+                        if (lane == 0) mbar_expect_tx(full + stage, 2u * N * bytes);
+                        __syncwarp();
+                        if (lane < 2 * N) bulk_g2s(dst + seg_dst + off, src + seg_src, bytes, full + stage);
+                    } else {
+                        // unaligned / odd-sized grids: plain loads by the 32 lanes, then a normal arrival
+                        for (int seg = 0; seg < 2 * N; ++seg) {
+                            const int f = seg / N, kd = seg - f * N;
+                            const T* sp = src + (long long)kd * g.d + (long long)f * g.npts;
+                            for (int j = lane; j < ge - gs; j += 32) dst[seg * WP + off + j] = __ldg(sp + j);
+                        }
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(full + stage);
                     }
                 }
             }
         }
-        iter_next<W>(pit, a);
-        ++pq;
-    };
-#pragma unroll 1
-    for (int s = 0; s < S; ++s) produce();
-    __syncthreads();   // the non-bulk fallback fills the stages with plain stores
+        return;
+    }
 
-    // ---- consumer -------------------------------------------------------------------------------------------------
-    ItemIter cit;
-    iter_init<W>(cit, a);
+    // ---- consumers ----------------------------------------------------------------------------------------------------
+    CSync csync;
+    // deliver this shard's edge rows to the neighbours before anything else (multi-GPU)
+    if (a.pack.enabled && blockIdx.x < 2 * kPackCtas) pack_halo_part<T, N>(g, c, a.mean_in, a.pack, (int)blockIdx.x, csync);
+
     unsigned cq = 0, phase_bits = 0u;
     bool halos_ready = false;
+    const T inv_dx2 = (T)g.prm[0], pa = (T)g.prm[1], pb = (T)g.prm[2], pk = (T)g.prm[3], inv_tau = (T)g.prm[5];
 
     auto m_at_from = [&](const T* fld, int idx) -> T {     // predicted, un-preconditioned state of a stage column
         T acc = c.pinv[0] * fld[idx];
@@ -285,129 +265,133 @@ __global__ void __launch_bounds__(W, 2) ek0_fused_fhn_kernel(const __grid_consta
         return c.p[0] * acc;
     };
 
-    // one phase over this CTA's strips.  kUpdate = false: phase A, true: phase B.
+    // one phase over this CTA's strips.  kUpdate = false: phase A (forward), true: phase B (backward).
     auto run_phase = [&](auto update_tag, const T (&K)[N]) -> double {
         constexpr bool kUpdate = decltype(update_tag)::value;
         constexpr int NK = kUpdate ? N : 2;                 // rows of the predicted mean kept for the row being finalised
         double acc = 0.0;
-        T at_m1[2] = {}, at_m2[2] = {}, hs_m1[2] = {}, mp_m1[2][NK] = {};
-        bool first_replicated = false;
-        while (cit.phase == (kUpdate ? 1 : 0)) {
-            const StripGeom s = cit.s;
-            const int i = cit.i;
-            const int rr = iter_row(cit);
+#pragma unroll 1
+        for (int kk = 0; kk < ns; ++kk) {
+            const int k = kUpdate ? ns - 1 - kk : kk;
+            StripGeom s = strip_geom<W>(g, blockIdx.x + (unsigned)k * gridDim.x, a.col_blocks, a.chunks, has_lo, has_hi);
+            if (kUpdate) s.dir = -s.dir;
+            const int L = s.r1 - s.r0 + 2;
             const int col = s.c0 + tc;
             const bool valid = tc < s.wlen;
-            const int stage = (int)(cq % S), slot = (int)(cq & 1u);
-            T* at_row = s_at + slot * 2 * AT_ROW;
-            T at_cur[2], mp_cur[2][NK];
-            if (i == 0) first_replicated = false;
-            if (rr >= 0 && rr < g.rows) {
-                if (a.use_bulk) {
+            const bool left_inner = (tc == 0) && s.c0 > 0;                            // recompute the column left of the strip
+            const bool right_inner = (tc == s.wlen - 1) && (s.c0 + s.wlen < g.cols);  // ... right of the strip
+            const bool left_edge = (tc == 0) && s.c0 == 0;                            // grid edge: replicate own value
+            const bool right_edge = (tc == s.wlen - 1) && (s.c0 + s.wlen >= g.cols);
+            int rr = s.dir > 0 ? s.r0 - 1 : s.r1;
+            T at_m1[2] = {}, at_m2[2] = {}, hs_m1[2] = {}, mp_m1[2][NK] = {};
+            bool first_replicated = false;
+            T* out_ptr = a.mean_out + ((long long)(rr - s.dir) * g.cols + col);      // row being finalised, field 0
+#pragma unroll 1
+            for (int i = 0; i < L; ++i, rr += s.dir, ++cq, out_ptr += (long long)s.dir * g.cols) {
+                const unsigned stage = cq % S;
+                T* at_row = s_at + (cq & 1u) * 2 * AT_ROW;
+                T at_cur[2], mp_cur[2][NK];
+                if (rr >= 0 && rr < g.rows) {
                     mbar_wait(full + stage, (phase_bits >> stage) & 1u);
                     phase_bits ^= (1u << stage);
-                }
-                const T* st = s_stage + (size_t)stage * Cfg::STAGE_ELEMS;
+                    const T* st = s_stage + (size_t)stage * Cfg::STAGE_ELEMS;
 #pragma unroll
-                for (int f = 0; f < 2; ++f) {
-                    T raw[N], mp[N];
+                    for (int f = 0; f < 2; ++f) {
+                        T raw[N], mp[N];
 #pragma unroll
-                    for (int k = 0; k < N; ++k) raw[k] = st[(f * N + k) * WP + PADC + tc];
-                    predict_column<T, N>(raw, c, mp);
-                    at_cur[f] = c.p[0] * mp[0];
+                        for (int kd = 0; kd < N; ++kd) raw[kd] = st[(f * N + kd) * WP + PADC + tc];
+                        predict_column<T, N>(raw, c, mp);
+                        at_cur[f] = c.p[0] * mp[0];
 #pragma unroll
-                    for (int r = 0; r < NK; ++r) mp_cur[f][r] = mp[r];
-                }
-                // columns just outside the strip (inside the grid): recomputed from the stage's overlap columns
-                if (tc == 0 && s.c0 > 0) {
-#pragma unroll
-                    for (int f = 0; f < 2; ++f) at_row[f * AT_ROW] = m_at_from(st + f * N * WP, PADC - 1);
-                }
-                if (tc == s.wlen - 1 && s.c0 + s.wlen < g.cols) {
-#pragma unroll
-                    for (int f = 0; f < 2; ++f) at_row[f * AT_ROW + s.wlen + 1] = m_at_from(st + f * N * WP, PADC + s.wlen);
-                }
-            } else {
-                const T* h = rr < 0 ? a.halo_lo : a.halo_hi;
-                if (h != nullptr) {
-                    if (!halos_ready) {
-                        cta_wait_halos(a.wait);
-                        halos_ready = true;
+                        for (int r = 0; r < NK; ++r) mp_cur[f][r] = mp[r];
                     }
+                    // columns just outside the strip (inside the grid): recomputed from the stage's overlap columns
+                    if (left_inner) {
 #pragma unroll
-                    for (int f = 0; f < 2; ++f) at_cur[f] = valid ? __ldcg(h + (long long)f * g.cols + col) : (T)0;
+                        for (int f = 0; f < 2; ++f) at_row[f * AT_ROW] = m_at_from(st + f * N * WP, PADC - 1);
+                    }
+                    if (right_inner) {
+#pragma unroll
+                        for (int f = 0; f < 2; ++f) at_row[f * AT_ROW + s.wlen + 1] = m_at_from(st + f * N * WP, PADC + s.wlen);
+                    }
                 } else {
-                    // edge replication (ivp.py:488-490): the row beyond the grid equals the grid's edge row
-#pragma unroll
-                    for (int f = 0; f < 2; ++f) at_cur[f] = at_m1[f];
-                    if (i == 0) first_replicated = true;
-                }
-#pragma unroll
-                for (int f = 0; f < 2; ++f)
-#pragma unroll
-                    for (int r = 0; r < NK; ++r) mp_cur[f][r] = (T)0;
-            }
-            if (i == 1 && first_replicated) {
-                at_m1[0] = at_cur[0];
-                at_m1[1] = at_cur[1];
-            }
-            if (valid) {
-#pragma unroll
-                for (int f = 0; f < 2; ++f) {
-                    at_row[f * AT_ROW + tc + 1] = at_cur[f];
-                    if (tc == 0 && s.c0 == 0) at_row[f * AT_ROW] = at_cur[f];                               // left grid edge
-                    if (tc == s.wlen - 1 && s.c0 + s.wlen >= g.cols) at_row[f * AT_ROW + s.wlen + 1] = at_cur[f];   // right
-                }
-            }
-            __syncthreads();          // publishes the row; every thread has consumed the stage -> it can be refilled
-            produce();
-            T hs_cur[2];
-#pragma unroll
-            for (int f = 0; f < 2; ++f) hs_cur[f] = at_row[f * AT_ROW + tc] + at_row[f * AT_ROW + tc + 2];
-
-            if (i >= 2 && valid) {    // the previous row now has both vertical neighbours
-                const int prev = rr - s.dir;
-                const T u = at_m1[0], v = at_m1[1];
-#pragma unroll
-                for (int f = 0; f < 2; ++f) {
-                    const T own = at_m1[f];
-                    const T lap = (((at_m2[f] + at_cur[f]) + hs_m1[f]) - (T)4 * own) * inv_dx2;
-                    T fx;
-                    if (f == 0) fx = pa * lap + u - u * u * u - v + pk;       // ivp.py:441
-                    else fx = (pb * lap + u - v) * inv_tau;                   // ivp.py:442
-                    const T z = c.p[1] * mp_m1[f][1] - fx;
-                    if constexpr (!kUpdate) {
-                        acc += (double)z * (double)z;
-                    } else {
-                        const long long flat = (long long)f * g.npts + (long long)prev * g.cols + col;
-                        T* mo_ptr = a.mean_out + flat;
-                        T m0 = (T)0;
-#pragma unroll
-                        for (int r = 0; r < N; ++r) {
-                            const T mo = c.p[r] * (mp_m1[f][r] - K[r] * z);
-                            *mo_ptr = mo;
-                            mo_ptr += g.d;
-                            if (r == 0) m0 = mo;
+                    const T* h = rr < 0 ? a.halo_lo : a.halo_hi;
+                    if (h != nullptr) {
+                        if (!halos_ready) {
+                            cta_wait_halos(a.wait, csync);
+                            halos_ready = true;
                         }
-                        const T ref = tabs<T>(m0);
-                        if (a.ref_out) a.ref_out[flat] = ref;
-                        if (c.want_norm) {
-                            const double tol = (double)c.abstol + (double)c.reltol * (double)ref;
-                            acc += 1.0 / (tol * tol);
+#pragma unroll
+                        for (int f = 0; f < 2; ++f) at_cur[f] = valid ? __ldcg(h + (long long)f * g.cols + col) : (T)0;
+                    } else {
+                        // edge replication (ivp.py:488-490): the row beyond the grid equals the grid's edge row
+#pragma unroll
+                        for (int f = 0; f < 2; ++f) at_cur[f] = at_m1[f];
+                        if (i == 0) first_replicated = true;
+                    }
+#pragma unroll
+                    for (int f = 0; f < 2; ++f)
+#pragma unroll
+                        for (int r = 0; r < NK; ++r) mp_cur[f][r] = (T)0;
+                }
+                if (i == 1 && first_replicated) {
+                    at_m1[0] = at_cur[0];
+                    at_m1[1] = at_cur[1];
+                }
+                if (valid) {
+#pragma unroll
+                    for (int f = 0; f < 2; ++f) {
+                        at_row[f * AT_ROW + tc + 1] = at_cur[f];
+                        if (left_edge) at_row[f * AT_ROW] = at_cur[f];
+                        if (right_edge) at_row[f * AT_ROW + s.wlen + 1] = at_cur[f];
+                    }
+                }
+                csync();              // publishes the row; every consumer has read the stage -> hand it back
+                if (tc == 0) mbar_arrive(empty + stage);
+                T hs_cur[2];
+#pragma unroll
+                for (int f = 0; f < 2; ++f) hs_cur[f] = at_row[f * AT_ROW + tc] + at_row[f * AT_ROW + tc + 2];
+
+                if (i >= 2 && valid) {    // the previous row now has both vertical neighbours
+                    const T u = at_m1[0], v = at_m1[1];
+#pragma unroll
+                    for (int f = 0; f < 2; ++f) {
+                        const T own = at_m1[f];
+                        const T lap = (((at_m2[f] + at_cur[f]) + hs_m1[f]) - (T)4 * own) * inv_dx2;
+                        T fx;
+                        if (f == 0) fx = pa * lap + u - u * u * u - v + pk;       // ivp.py:441
+                        else fx = (pb * lap + u - v) * inv_tau;                   // ivp.py:442
+                        const T z = c.p[1] * mp_m1[f][1] - fx;
+                        if constexpr (!kUpdate) {
+                            acc += (double)z * (double)z;
+                        } else {
+                            T* mo_ptr = out_ptr + (long long)f * g.npts;
+                            T m0 = (T)0;
+#pragma unroll
+                            for (int r = 0; r < N; ++r) {
+                                const T mo = c.p[r] * (mp_m1[f][r] - K[r] * z);
+                                *mo_ptr = mo;
+                                mo_ptr += g.d;
+                                if (r == 0) m0 = mo;
+                            }
+                            const T ref = tabs<T>(m0);
+                            if (a.ref_out) a.ref_out[(out_ptr - a.mean_out) + (long long)f * g.npts] = ref;
+                            if (c.want_norm) {
+                                const double tol = (double)c.abstol + (double)c.reltol * (double)ref;
+                                acc += 1.0 / (tol * tol);
+                            }
                         }
                     }
                 }
-            }
 #pragma unroll
-            for (int f = 0; f < 2; ++f) {
-                at_m2[f] = at_m1[f];
-                at_m1[f] = at_cur[f];
-                hs_m1[f] = hs_cur[f];
+                for (int f = 0; f < 2; ++f) {
+                    at_m2[f] = at_m1[f];
+                    at_m1[f] = at_cur[f];
+                    hs_m1[f] = hs_cur[f];
 #pragma unroll
-                for (int r = 0; r < NK; ++r) mp_m1[f][r] = mp_cur[f][r];
+                    for (int r = 0; r < NK; ++r) mp_m1[f][r] = mp_cur[f][r];
+                }
             }
-            iter_next<W>(cit, a);
-            ++cq;
         }
         return acc;
     };
@@ -418,13 +402,13 @@ __global__ void __launch_bounds__(W, 2) ek0_fused_fhn_kernel(const __grid_consta
 
     // ---- phase A ----------------------------------------------------------------------------------------------------
     const double acc_a = run_phase(std::false_type{}, K);
-    if (publish_partial(acc_a, s_red, a.partials, a.ticket)) {
-        double z_sq = sum_partials(s_red, a.partials);
+    if (publish_partial(acc_a, s_red, a.partials, a.ticket, csync)) {
+        double z_sq = sum_partials(s_red, a.partials, csync);
         if (a.reduce_a.world > 0) {
-            __syncthreads();
-            z_sq = cta_allreduce(z_sq, a.reduce_a, s_red);
+            csync();
+            z_sq = cta_allreduce(z_sq, a.reduce_a, s_red, csync);
         }
-        if (threadIdx.x == 0) {
+        if (tc == 0) {
             ek0_mid_compute<T, N>(a.cd, a.Cl_in, z_sq, a.d_global, a.Cl_out, a.err_out, a.mid);
             if (a.z_sq_out) *a.z_sq_out = z_sq;
             *a.ticket = 0u;
@@ -432,32 +416,32 @@ __global__ void __launch_bounds__(W, 2) ek0_fused_fhn_kernel(const __grid_consta
             st_release_gpu(a.mid_flag, a.mid_seq);
         }
     }
-    if (threadIdx.x == 0) {
+    if (tc == 0) {
         const unsigned long long t0 = global_timer_ns();
         while (ld_acquire_gpu(a.mid_flag) < a.mid_seq) {
             if (global_timer_ns() - t0 > 4000000000ull) break;   // a dead peer must not hang the GPU
             __nanosleep(64);
         }
     }
-    __syncthreads();
+    csync();
 #pragma unroll
     for (int r = 0; r < N; ++r) K[r] = __ldcg(&a.mid->K[r]);
 
     // ---- phase B ----------------------------------------------------------------------------------------------------
     const double acc_b = run_phase(std::true_type{}, K);
     if (c.want_norm) {
-        if (publish_partial(acc_b, s_red, a.partials + gridDim.x, a.ticket + 1)) {
-            double b = sum_partials(s_red, a.partials + gridDim.x);
-            if (threadIdx.x == 0) {
+        if (publish_partial(acc_b, s_red, a.partials + gridDim.x, a.ticket + 1, csync)) {
+            double b = sum_partials(s_red, a.partials + gridDim.x, csync);
+            if (tc == 0) {
                 const double e = __ldcg(&a.mid->err);
                 b *= e * e;
                 b *= (double)c.dt * (double)c.dt;      // sum_i (dt err / tol_i)^2   step.py:101-104, scalar error estimate
             }
             if (a.reduce_b.world > 0) {
-                __syncthreads();
-                b = cta_allreduce(b, a.reduce_b, s_red);
+                csync();
+                b = cta_allreduce(b, a.reduce_b, s_red, csync);
             }
-            if (threadIdx.x == 0) {
+            if (tc == 0) {
                 *a.out_sum = b;
                 a.ticket[1] = 0u;
             }

@@ -137,9 +137,9 @@ struct PackPeer {
     int enabled;
 };
 
-template <typename T, int N>
+template <typename T, int N, class Sync = FullSync>
 __device__ __forceinline__ void pack_halo_part(const Geo& g, const Consts<T, N>& c, const T* mean_in,
-                                               const PackPeer<T>& pk, int part_index) {
+                                               const PackPeer<T>& pk, int part_index, Sync sync = Sync()) {
     MeanAt<T, N> at{mean_in, g.d, &c};
     const bool lower = part_index < kPackCtas;
     const int part = lower ? part_index : part_index - kPackCtas;
@@ -148,11 +148,12 @@ __device__ __forceinline__ void pack_halo_part(const Geo& g, const Consts<T, N>&
     const int per_field = lower ? pk.n_first : pk.n_last;
     const long long start = lower ? 0 : (g.npts - pk.n_last);
     const int total = g.nf * per_field;
-    for (int i = part * blockDim.x + threadIdx.x; i < total; i += kPackCtas * blockDim.x) {
+    const int nthr = sync.threads();
+    for (int i = part * nthr + threadIdx.x; i < total; i += kPackCtas * nthr) {
         const int field = i / per_field, j = i - field * per_field;
         dst[i] = at((long long)field * g.npts + start + j);
     }
-    __syncthreads();
+    sync();
     if (threadIdx.x == 0) {
         // one system-scope fence per CTA: it is cumulative over the stores the barrier above ordered before it
         __threadfence_system();

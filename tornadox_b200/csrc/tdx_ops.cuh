@@ -6,6 +6,10 @@
 #include "tdx_kernels.cuh"
 #include "tdx_ek0_fused.cuh"
 
+#ifndef TDX_EK0_W
+#define TDX_EK0_W 256      // columns per strip (= threads per CTA) of the fused KroneckerEK0 kernel
+#endif
+
 namespace tdx {
 
 struct StepHost {
@@ -253,7 +257,7 @@ struct Launch {
                          unsigned long long mid_seq, double d_global, double* z_sq_out, double* out_sum,
                          cudaStream_t st) {
         if (g.kind != IVP_FHN2D) return kNoFusedKernel;
-        constexpr int W = 256;
+        constexpr int W = TDX_EK0_W;
         using Cfg = Ek0FusedCfg<T, N, W>;
         constexpr auto kern = ek0_fused_fhn_kernel<T, N, W>;
         Ek0FusedArgs<T, N> a;
@@ -283,7 +287,7 @@ struct Launch {
         constexpr int PADC = Cfg::PADC;
         a.use_bulk = (g.cols % PADC == 0) && ((reinterpret_cast<uintptr_t>(mean_in) & 15) == 0) ? 1 : 0;
         unsigned resident = 0;
-        TDX_CUDA_TRY(persistent_grid<kern>(Cfg::total(), 1LL << 40, 0, resident, W));
+        TDX_CUDA_TRY(persistent_grid<kern>(Cfg::total(), 1LL << 40, 0, resident, W + 32));
         a.col_blocks = (unsigned)((g.cols + W - 1) / W);
         unsigned chunks = resident / a.col_blocks;
         if (chunks < 1u) chunks = 1u;
@@ -301,7 +305,7 @@ struct Launch {
             a.pack.enabled = 0;
         }
         void* params[] = {(void*)&a};
-        TDX_CUDA_TRY(cudaLaunchCooperativeKernel((const void*)kern, dim3(grid), dim3(W), params, Cfg::total(), st));
+        TDX_CUDA_TRY(cudaLaunchCooperativeKernel((const void*)kern, dim3(grid), dim3(W + 32), params, Cfg::total(), st));
         return (int)cudaGetLastError();
     }
 
