@@ -184,6 +184,8 @@ int tdx_comm_error(tdx_ctx* ctx, int* error_out, void* stream);
 
 /* kernels launched by this context since creation (bench.py's gpu_launches counter) */
 int64_t tdx_launch_count(const tdx_ctx* ctx);
+/* development aid: copy ``count`` doubles of the context's reduction workspace to the host (synchronous) */
+int tdx_debug_read_workspace(tdx_ctx* ctx, double* host_out, int64_t offset, int64_t count);
 
 #ifdef __cplusplus
 }

@@ -28,7 +28,7 @@ EXPORTED_SYMBOLS = (
     "tdx_last_error", "tdx_abi_version", "tdx_create", "tdx_destroy", "tdx_set_problem", "tdx_local_dim",
     "tdx_halo_sizes", "tdx_set_diffusion_sqrt", "tdx_prior", "tdx_nordsieck", "tdx_eval_f", "tdx_pack_halo", "tdx_dek1_attempt_step",
     "tdx_ek0_sweep_a", "tdx_ek0_mid", "tdx_ek0_sweep_b", "tdx_ek0_attempt_step", "tdx_launch_count",
-    "tdx_comm_init", "tdx_comm_connect", "tdx_comm_pack_halo", "tdx_comm_allreduce", "tdx_comm_error",
+    "tdx_debug_read_workspace", "tdx_comm_init", "tdx_comm_connect", "tdx_comm_pack_halo", "tdx_comm_allreduce", "tdx_comm_error",
 )
 
 
@@ -100,6 +100,7 @@ def load():
     lib.tdx_comm_pack_halo.argtypes = [vp, dbl, vp, vp]
     lib.tdx_comm_allreduce.argtypes = [vp, vp, cint, vp]
     lib.tdx_comm_error.argtypes = [vp, ctypes.POINTER(cint), vp]
+    lib.tdx_debug_read_workspace.argtypes = [vp, pd, i64, i64]
     lib.tdx_launch_count.restype = i64
     lib.tdx_launch_count.argtypes = [vp]
     for name in EXPORTED_SYMBOLS:

@@ -367,6 +367,13 @@ int tdx_halo_sizes(const tdx_ctx* ctx, int64_t* lo, int64_t* hi) {
 
 int64_t tdx_launch_count(const tdx_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
+int tdx_debug_read_workspace(tdx_ctx* ctx, double* host_out, int64_t offset, int64_t count) {
+    if (!ctx || !ctx->partials || !host_out || offset < 0 || count < 0 || offset + count > 2 * ctx->partials_cap)
+        return fail(TDX_ERR_INVALID, "tdx_debug_read_workspace: bad range");
+    cudaError_t e = cudaMemcpy(host_out, ctx->partials + offset, (size_t)count * sizeof(double), cudaMemcpyDeviceToHost);
+    return e == cudaSuccess ? TDX_OK : cuda_fail((int)e, "tdx_debug_read_workspace");
+}
+
 }  // extern "C"
 
 // ---- helpers ---------------------------------------------------------------------------------------

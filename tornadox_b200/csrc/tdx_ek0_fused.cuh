@@ -21,6 +21,13 @@
 
 #include "tdx_kernels.cuh"
 
+#ifndef TDX_EK0_STAGES
+#define TDX_EK0_STAGES 4     // depth of the TMA ring (rows in flight per CTA)
+#endif
+#ifndef TDX_EK0_MAXREG
+#define TDX_EK0_MAXREG 96    // 2 CTAs x 9 warps: 5 warps share one of the four 16 K-register sub-partitions -> <= 102
+#endif
+
 namespace tdx {
 
 template <typename T, int N, int W_>
@@ -28,7 +35,7 @@ struct Ek0FusedCfg {
     static constexpr int W = W_;                          // columns per strip == consumer threads per CTA (+ one producer warp)
     static constexpr int PADC = 16 / (int)sizeof(T);      // columns of left/right overlap (16-byte granularity of TMA)
     static constexpr int WP = W + 2 * PADC;
-    static constexpr int STAGES = 4;
+    static constexpr int STAGES = TDX_EK0_STAGES;
     static constexpr int STAGE_ELEMS = 2 * N * WP;        // [field][derivative][WP]
     static constexpr int AT_ROW = W + 2;                  // [left edge][W own][right edge]
     static constexpr int AT_ELEMS = 2 * 2 * AT_ROW;       // [slot][field][AT_ROW]
@@ -62,6 +69,7 @@ struct Ek0FusedArgs {
     double d_global;
     unsigned int col_blocks, chunks, total_strips;
     int use_bulk;
+    float keep_frac;                 // share of a strip's rows kept in L2 across the phase turn-arounds (>= 1: no hints)
     CommWait wait;
     CommReduce reduce_a, reduce_b;
     PackPeer<T> pack;
@@ -91,11 +99,15 @@ __device__ __noinline__ void ek0_mid_compute(const Consts<double, N>& c, const T
     const double err = sqrt(sigma_sq * HQH);
     const double sigma = sqrt(sigma_sq);
     double B[N][N];
+#pragma unroll
     for (int j = 0; j < N; ++j) {
         double col[N];
+#pragma unroll
         for (int k = 0; k < N; ++k) col[k] = c.pinv[k] * (double)Cl_in[k * N + j];
+#pragma unroll
         for (int i = 0; i < N; ++i) {
             double acc = col[i];
+#pragma unroll
             for (int k = i + 1; k < N; ++k) acc = fma(A_entry<N>(i, k), col[k], acc);
             B[i][j] = acc;
         }
@@ -103,6 +115,7 @@ __device__ __noinline__ void ek0_mid_compute(const Consts<double, N>& c, const T
     stacked_qr<double, N>(B, sigma, c);
     const double g0 = p1 * B[1][0], g1 = p1 * B[1][1];   // H Clp = p1 * Clp[1, :]
     const double S = p1 * p1 * (B[1][0] * B[1][0] + B[1][1] * B[1][1]);
+#pragma unroll
     for (int r = 0; r < N; ++r) {
         const double l0 = B[r][0], l1 = (r >= 1) ? B[r][1] : 0.0;
         const double kg = (l0 * g0 + l1 * g1) / S;
@@ -110,15 +123,16 @@ __device__ __noinline__ void ek0_mid_compute(const Consts<double, N>& c, const T
         const double pr = c.p[r];
         Cl_out[r * N + 0] = (T)(pr * (l0 - kg * g0));
         Cl_out[r * N + 1] = (T)(pr * (l1 - kg * g1));
+#pragma unroll
         for (int cc = 2; cc < N; ++cc) Cl_out[r * N + cc] = (r >= cc) ? (T)(pr * B[r][cc]) : (T)0;
     }
     *err_out = (T)err;
     mid->err = err;
 }
 
-// per-CTA partial -> global memory; returns (uniform over the participants) whether this CTA arrived last
+// per-CTA partial -> global memory; returns (uniform over the participants) this CTA's arrival number 0 .. gridDim.x - 1
 template <class Sync>
-__device__ __forceinline__ bool publish_partial(double v, double* s_red, double* partials, unsigned int* ticket, Sync sync) {
+__device__ __forceinline__ unsigned publish_partial(double v, double* s_red, double* partials, unsigned int* ticket, Sync sync) {
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = (sync.threads() + 31) >> 5;
     v = warp_sum(v);
     sync();                          // s_red may still be read by a previous use
@@ -130,10 +144,10 @@ __device__ __forceinline__ bool publish_partial(double v, double* s_red, double*
         partials[blockIdx.x] = b;
         __threadfence();
         const unsigned int t = atomicAdd(ticket, 1u);
-        s_red[31] = (t == gridDim.x - 1) ? 1.0 : 0.0;
+        s_red[31] = (double)t;
     }
     sync();
-    return s_red[31] != 0.0;
+    return (unsigned)s_red[31];
 }
 
 // the participants of the last CTA: the partials in a fixed order; the result is valid in thread 0
@@ -166,14 +180,17 @@ __device__ __forceinline__ StripGeom strip_geom(const Geo& g, unsigned strip, un
     s.wlen = min(W, g.cols - s.c0);
     s.r0 = (int)(((long long)chunk * g.rows) / chunks);
     s.r1 = (int)(((long long)(chunk + 1) * g.rows) / chunks);
-    // a strip under the shard's lower edge walks upwards in phase A so that the neighbour's halo row is needed LAST
-    s.dir = (chunk == 0 && has_lo && !(chunk + 1 == chunks && has_hi)) ? -1 : 1;
+    // Vertically adjacent strips walk in opposite directions: they read the row they share (one's halo row is the
+    // other's edge row) at about the same time, so the second read is an L2 hit.  A strip under the shard's lower /
+    // upper edge walks towards that edge in phase A so that the neighbour GPU's halo row is needed LAST.
+    s.dir = (((chunk & 1u) != 0u) != has_lo) ? -1 : 1;
+    if (chunk + 1 == chunks && has_hi && !(chunk == 0 && has_lo)) s.dir = 1;
     return s;
 }
 
 // Threads [0, W): consumers, thread t owns column c0 + t of both fields.  Threads [W, W + 32): the producer warp.
 template <typename T, int N, int W>
-__global__ void __launch_bounds__(W + 32, 2) ek0_fused_fhn_kernel(const __grid_constant__ Ek0FusedArgs<T, N> a) {
+__global__ void __maxnreg__(TDX_EK0_MAXREG) ek0_fused_fhn_kernel(const __grid_constant__ Ek0FusedArgs<T, N> a) {
     using Cfg = Ek0FusedCfg<T, N, W>;
     using CSync = NamedSync<1, W>;                         // the consumers' barrier (the producer warp never joins)
     constexpr int PADC = Cfg::PADC, WP = Cfg::WP, S = Cfg::STAGES, AT_ROW = Cfg::AT_ROW;
@@ -188,6 +205,7 @@ __global__ void __launch_bounds__(W + 32, 2) ek0_fused_fhn_kernel(const __grid_c
     const Consts<T, N>& c = a.c;
     const int tc = threadIdx.x;
     const bool has_lo = a.halo_lo != nullptr, has_hi = a.halo_hi != nullptr;
+    const bool hints = a.keep_frac < 1.0f;
     const int ns = (int)((a.total_strips - blockIdx.x + gridDim.x - 1) / gridDim.x);   // strips of this CTA
 
     if (tc == 0) {
@@ -210,6 +228,7 @@ __global__ void __launch_bounds__(W + 32, 2) ek0_fused_fhn_kernel(const __grid_c
         const long long seg_src = (long long)seg_k * g.d + (long long)seg_f * g.npts;
         const int seg_dst = (seg_f * N + seg_k) * WP;
         unsigned q = 0;
+        const uint64_t pol_keep = l2_policy_evict_last(), pol_stream = l2_policy_evict_first();
 #pragma unroll 1
         for (int phase = 0; phase < 2; ++phase) {
 #pragma unroll 1
@@ -221,6 +240,8 @@ __global__ void __launch_bounds__(W + 32, 2) ek0_fused_fhn_kernel(const __grid_c
                 const int gs = max(s.c0 - PADC, 0), ge = min(s.c0 + W + PADC, g.cols);
                 const int off = gs - (s.c0 - PADC);
                 const uint32_t bytes = (uint32_t)((ge - gs) * (int)sizeof(T));
+                // L2 residency: the rows phase A reads last are the rows phase B reads first -> keep those, stream the rest
+                const int keep_from = (phase == 0 && hints) ? L - 1 - (int)ceilf(a.keep_frac * (float)(s.r1 - s.r0)) : L;
                 int rr = s.dir > 0 ? s.r0 - 1 : s.r1;
 #pragma unroll 1
                 for (int i = 0; i < L; ++i, rr += s.dir, ++q) {
@@ -232,7 +253,10 @@ __global__ void __launch_bounds__(W + 32, 2) ek0_fused_fhn_kernel(const __grid_c
                     if (a.use_bulk) {
                         if (lane == 0) mbar_expect_tx(full + stage, 2u * N * bytes);
                         __syncwarp();
-                        if (lane < 2 * N) bulk_g2s(dst + seg_dst + off, src + seg_src, bytes, full + stage);
+                        if (lane < 2 * N) {
+                            if (hints) bulk_g2s_hint(dst + seg_dst + off, src + seg_src, bytes, full + stage, i >= keep_from ? pol_keep : pol_stream);
+                            else bulk_g2s(dst + seg_dst + off, src + seg_src, bytes, full + stage);
+                        }
                     } else {
                         // unaligned / odd-sized grids: plain loads by the 32 lanes, then a normal arrival
                         for (int seg = 0; seg < 2 * N; ++seg) {
@@ -254,8 +278,38 @@ __global__ void __launch_bounds__(W + 32, 2) ek0_fused_fhn_kernel(const __grid_c
     // deliver this shard's edge rows to the neighbours before anything else (multi-GPU)
     if (a.pack.enabled && blockIdx.x < 2 * kPackCtas) pack_halo_part<T, N>(g, c, a.mean_in, a.pack, (int)blockIdx.x, csync);
 
+    // Column 1 of the predicted covariance without the diffusion term, M1 = (B B^T)[:, 1] with B = A (p_inv * Cl).
+    // The gain K = Clp Clp^T H^T / S (ek0.py:136) only needs column 1 of Clp Clp^T = B B^T + sigma^2 Ql Ql^T, so once
+    // sigma^2 is known (after phase A) every CTA derives K in a handful of flops; the stacked QR that produces the new
+    // factor itself (ek0.py:175,138) is off the critical path (done by the first CTA to finish phase B).
+    double* s_m1 = s_red + 16;
+    if (tc == 0) {
+        const Consts<double, N>& cd = a.cd;
+        double B[N][N];
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+            double colv[N];
+#pragma unroll
+            for (int kd = 0; kd < N; ++kd) colv[kd] = cd.pinv[kd] * (double)__ldg(a.Cl_in + kd * N + j);
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                double accb = colv[i];
+#pragma unroll
+                for (int kd = i + 1; kd < N; ++kd) accb = fma(A_entry<N>(i, kd), colv[kd], accb);
+                B[i][j] = accb;
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < N; ++r) {
+            double m = 0.0;
+#pragma unroll
+            for (int j = 0; j < N; ++j) m = fma(B[r][j], B[1][j], m);
+            s_m1[r] = m;
+        }
+    }
     unsigned cq = 0, phase_bits = 0u;
     bool halos_ready = false;
+    const uint64_t pol_keep = l2_policy_evict_last(), pol_stream = l2_policy_evict_first();
     const T inv_dx2 = (T)g.prm[0], pa = (T)g.prm[1], pb = (T)g.prm[2], pk = (T)g.prm[3], inv_tau = (T)g.prm[5];
 
     auto m_at_from = [&](const T* fld, int idx) -> T {     // predicted, un-preconditioned state of a stage column
@@ -286,6 +340,8 @@ __global__ void __launch_bounds__(W + 32, 2) ek0_fused_fhn_kernel(const __grid_c
             T at_m1[2] = {}, at_m2[2] = {}, hs_m1[2] = {}, mp_m1[2][NK] = {};
             bool first_replicated = false;
             T* out_ptr = a.mean_out + ((long long)(rr - s.dir) * g.cols + col);      // row being finalised, field 0
+            // the rows phase B writes last are the rows the NEXT attempt's phase A reads first -> keep those in L2
+            const int keep_from = (kUpdate && hints) ? L - (int)ceilf(a.keep_frac * (float)(s.r1 - s.r0)) : L;
 #pragma unroll 1
             for (int i = 0; i < L; ++i, rr += s.dir, ++cq, out_ptr += (long long)s.dir * g.cols) {
                 const unsigned stage = cq % S;
@@ -370,12 +426,17 @@ __global__ void __launch_bounds__(W + 32, 2) ek0_fused_fhn_kernel(const __grid_c
 #pragma unroll
                             for (int r = 0; r < N; ++r) {
                                 const T mo = c.p[r] * (mp_m1[f][r] - K[r] * z);
-                                *mo_ptr = mo;
+                                if (hints) st_global_hint(mo_ptr, mo, i >= keep_from ? pol_keep : pol_stream);
+                                else *mo_ptr = mo;
                                 mo_ptr += g.d;
                                 if (r == 0) m0 = mo;
                             }
                             const T ref = tabs<T>(m0);
-                            if (a.ref_out) a.ref_out[(out_ptr - a.mean_out) + (long long)f * g.npts] = ref;
+                            if (a.ref_out) {
+                                T* rp = a.ref_out + ((out_ptr - a.mean_out) + (long long)f * g.npts);
+                                if (hints) st_global_hint(rp, ref, pol_stream);
+                                else *rp = ref;
+                            }
                             if (c.want_norm) {
                                 const double tol = (double)c.abstol + (double)c.reltol * (double)ref;
                                 acc += 1.0 / (tol * tol);
@@ -400,16 +461,28 @@ __global__ void __launch_bounds__(W + 32, 2) ek0_fused_fhn_kernel(const __grid_c
 #pragma unroll
     for (int r = 0; r < N; ++r) K[r] = (T)0;
 
+#ifdef TDX_EK0_TIMING
+    double* stamps = a.partials + 1024 + 4 * blockIdx.x;    // [t_start, t_end_A, t_gain_seen, t_end_B] in ns
+    if (tc == 0) {
+        stamps[0] = (double)global_timer_ns();
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        a.partials[1024 + 4096 + blockIdx.x] = (double)smid;
+    }
+#endif
     // ---- phase A ----------------------------------------------------------------------------------------------------
     const double acc_a = run_phase(std::false_type{}, K);
-    if (publish_partial(acc_a, s_red, a.partials, a.ticket, csync)) {
+#ifdef TDX_EK0_TIMING
+    if (tc == 0) stamps[1] = (double)global_timer_ns();
+#endif
+    if (publish_partial(acc_a, s_red, a.partials, a.ticket, csync) == gridDim.x - 1) {
         double z_sq = sum_partials(s_red, a.partials, csync);
         if (a.reduce_a.world > 0) {
             csync();
             z_sq = cta_allreduce(z_sq, a.reduce_a, s_red, csync);
         }
         if (tc == 0) {
-            ek0_mid_compute<T, N>(a.cd, a.Cl_in, z_sq, a.d_global, a.Cl_out, a.err_out, a.mid);
+            a.mid->z_sq = z_sq;
             if (a.z_sq_out) *a.z_sq_out = z_sq;
             *a.ticket = 0u;
             __threadfence();
@@ -424,28 +497,52 @@ __global__ void __launch_bounds__(W + 32, 2) ek0_fused_fhn_kernel(const __grid_c
         }
     }
     csync();
+#ifdef TDX_EK0_TIMING
+    if (tc == 0) stamps[2] = (double)global_timer_ns();
+#endif
+    // calibration (ek0.py:123-130) and gain (ek0.py:132-136), redundantly in every thread
+    const double z_sq_all = __ldcg(&a.mid->z_sq);
+    double err_cal;
+    {
+        const Consts<double, N>& cd = a.cd;
+        const double p1 = cd.p[1];
+        const double Q11 = QL(cd, 1, 0) * QL(cd, 1, 0) + QL(cd, 1, 1) * QL(cd, 1, 1);
+        const double HQH = p1 * p1 * Q11;
+        const double sigma_sq = z_sq_all / HQH / a.d_global;
+        err_cal = sqrt(sigma_sq * HQH);
+        const double den = p1 * fma(sigma_sq, Q11, s_m1[1]);
 #pragma unroll
-    for (int r = 0; r < N; ++r) K[r] = __ldcg(&a.mid->K[r]);
+        for (int r = 0; r < N; ++r) {
+            // (Ql Ql^T)[r][1]: rows 0 and 1 of Ql have 1 and 2 nonzeros
+            const double q = (r == 0) ? QL(cd, 0, 0) * QL(cd, 1, 0) : QL(cd, r, 0) * QL(cd, 1, 0) + QL(cd, r, 1) * QL(cd, 1, 1);
+            K[r] = (T)(fma(sigma_sq, q, s_m1[r]) / den);
+        }
+    }
 
     // ---- phase B ----------------------------------------------------------------------------------------------------
     const double acc_b = run_phase(std::true_type{}, K);
-    if (c.want_norm) {
-        if (publish_partial(acc_b, s_red, a.partials + gridDim.x, a.ticket + 1, csync)) {
+#ifdef TDX_EK0_TIMING
+    if (tc == 0) stamps[3] = (double)global_timer_ns();
+#endif
+    const unsigned arrival = publish_partial(acc_b, s_red, a.partials + gridDim.x, a.ticket + 1, csync);
+    if (arrival == 0u && tc == 0) {
+        // the first CTA to finish has the most slack: it runs the stacked QR for the new factor  ek0.py:175,138
+        ek0_mid_compute<T, N>(a.cd, a.Cl_in, z_sq_all, a.d_global, a.Cl_out, a.err_out, a.mid);
+    }
+    if (arrival == gridDim.x - 1) {
+        if (c.want_norm) {
             double b = sum_partials(s_red, a.partials + gridDim.x, csync);
             if (tc == 0) {
-                const double e = __ldcg(&a.mid->err);
-                b *= e * e;
+                b *= err_cal * err_cal;
                 b *= (double)c.dt * (double)c.dt;      // sum_i (dt err / tol_i)^2   step.py:101-104, scalar error estimate
             }
             if (a.reduce_b.world > 0) {
                 csync();
                 b = cta_allreduce(b, a.reduce_b, s_red, csync);
             }
-            if (tc == 0) {
-                *a.out_sum = b;
-                a.ticket[1] = 0u;
-            }
+            if (tc == 0) *a.out_sum = b;
         }
+        if (tc == 0) a.ticket[1] = 0u;
     }
 }
 

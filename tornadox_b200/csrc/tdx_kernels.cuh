@@ -409,6 +409,7 @@ template <typename T, int N>
 struct Ek0Mid {          // written by ek0_mid_kernel, read by sweep B
     T K[kMaxN];          // gain  ek0.py:136
     double err;          // calibrated scalar error estimate  ek0.py:129
+    double z_sq;         // fused kernel: the global sum of z^2 (every CTA derives the gain from it)
 };
 
 template <typename T, int N>

@@ -295,6 +295,12 @@ struct Launch {
         a.chunks = chunks;
         a.total_strips = a.col_blocks * chunks;
         const unsigned grid = a.total_strips < resident ? a.total_strips : resident;
+        // L2 residency hints: keep as many rows of every strip as fit the budget; everything fits -> no hints at all
+        {
+            static const double budget_mb = std::getenv("TDX_EK0_L2_KEEP_MB") ? std::atof(std::getenv("TDX_EK0_L2_KEEP_MB")) : 80.0;
+            const double mean_mb = (double)g.d * N * sizeof(T) / 1.0e6;
+            a.keep_frac = (budget_mb <= 0.0) ? 2.0f : (float)(budget_mb / mean_mb);
+        }
         if (a.pack.enabled && grid < 2u * kPackCtas) {   // tiny shard: deliver the halos with their own launch
             PackPeerArgs<T, N> pa;
             pa.g = g;
