@@ -133,6 +133,15 @@ int tdx_dek1_attempt_step(tdx_ctx* ctx, const tdx_step_args* args, const void* m
                           void* ref_out, const void* halo_lo, const void* halo_hi,
                           double* sq_norm_sum, void* stream);
 
+/* The same attempt for a state that lives in HOST memory (all array pointers are host pointers with the reference's
+ * layouts; pinned memory is needed for full PCIe speed, pageable memory works).  The state is streamed through the
+ * device in ``nchunks`` pieces (0 = default) with the copies in both directions overlapping the kernels; the call
+ * returns when the outputs are complete in host memory.  ``sq_norm_sum`` is a HOST double.  err_out / ref_out may be
+ * NULL.  The context must own the whole problem (no sharding). */
+int tdx_dek1_attempt_step_host(tdx_ctx* ctx, const tdx_step_args* args, const void* mean_in,
+                               const void* sc_in, void* mean_out, void* sc_out, void* err_out,
+                               void* ref_out, double* sq_norm_sum, int nchunks);
+
 /* KroneckerEK0.attempt_step (ek0.py:152-193) in three phases, so that a multi-GPU caller can
  * all-reduce the device scalar between them:
  *  sweep_a : predict + measure, writes sum_i z_i^2 over the local shard to ``z_sq_sum`` (double);

@@ -28,7 +28,7 @@ EXPORTED_SYMBOLS = (
     "tdx_last_error", "tdx_abi_version", "tdx_create", "tdx_destroy", "tdx_set_problem", "tdx_local_dim",
     "tdx_halo_sizes", "tdx_set_diffusion_sqrt", "tdx_prior", "tdx_nordsieck", "tdx_eval_f", "tdx_pack_halo", "tdx_dek1_attempt_step",
     "tdx_ek0_sweep_a", "tdx_ek0_mid", "tdx_ek0_sweep_b", "tdx_ek0_attempt_step", "tdx_launch_count",
-    "tdx_debug_read_workspace", "tdx_comm_init", "tdx_comm_connect", "tdx_comm_pack_halo", "tdx_comm_allreduce", "tdx_comm_error",
+    "tdx_debug_read_workspace", "tdx_dek1_attempt_step_host", "tdx_comm_init", "tdx_comm_connect", "tdx_comm_pack_halo", "tdx_comm_allreduce", "tdx_comm_error",
 )
 
 
@@ -91,6 +91,7 @@ def load():
     lib.tdx_eval_f.argtypes = [vp, dbl, vp, vp, vp, vp, vp, vp]
     lib.tdx_pack_halo.argtypes = [vp, dbl, vp, vp, vp, vp]
     lib.tdx_dek1_attempt_step.argtypes = [vp, ctypes.POINTER(StepArgs)] + [vp] * 10
+    lib.tdx_dek1_attempt_step_host.argtypes = [vp, ctypes.POINTER(StepArgs)] + [vp] * 6 + [pd, cint]
     lib.tdx_ek0_sweep_a.argtypes = [vp, ctypes.POINTER(StepArgs), vp, vp, vp, vp, vp]
     lib.tdx_ek0_mid.argtypes = [vp, ctypes.POINTER(StepArgs), vp, vp, i64, vp, vp, vp]
     lib.tdx_ek0_sweep_b.argtypes = [vp, ctypes.POINTER(StepArgs), vp, vp, vp, vp, vp, vp, vp]

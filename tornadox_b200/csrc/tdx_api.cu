@@ -2,7 +2,9 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <algorithm>
 #include <string>
+#include <vector>
 
 #include "../../include/tornadox_b200.h"
 #include "tdx_ops.cuh"
@@ -137,7 +139,10 @@ static int cuda_fail(int cuda_code, const char* where) {
     return TDX_ERR_CUDA;
 }
 
+struct HostPipe;
+
 struct tdx_ctx {
+    HostPipe* pipe = nullptr;        // chunked host-buffer pipeline (tdx_dek1_attempt_step_host), built on first use
     int device = 0;
     int dtype = TDX_F64;
     bool has_problem = false;
@@ -221,8 +226,11 @@ int tdx_create(tdx_ctx** out, int device, int dtype) {
     return TDX_OK;
 }
 
+static void destroy_pipe(tdx_ctx* ctx);
+
 int tdx_destroy(tdx_ctx* ctx) {
     if (!ctx) return TDX_OK;
+    destroy_pipe(ctx);
     int prev = 0;
     cudaGetDevice(&prev);
     cudaSetDevice(ctx->device);
@@ -764,3 +772,222 @@ int tdx_ek0_attempt_step(tdx_ctx* ctx, const tdx_step_args* args, const void* me
 }
 
 }  // extern "C"
+
+
+// =====================================================================================================================
+// Host-buffer entry point: DiagonalEK1.attempt_step on a state that lives in HOST memory (what a caller without
+// device arrays hands over, e.g. the reference's NumPy/JAX-CPU arrays).  The state is cut into chunks of grid rows
+// (fhn_2d) / chain points; three streams run  H2D(chunk c+1) | step kernel(chunk c) | D2H(chunk c-1)  concurrently, so
+// the call costs about max(H2D, D2H) of the state over PCIe instead of H2D + kernel + D2H.  Every chunk is an
+// ordinary sharded context: the stencil's halo values come from tdx_pack_halo on the neighbouring chunks' means.
+// =====================================================================================================================
+struct HostPipe {
+    int nchunks = 0;
+    std::vector<tdx_ctx*> ctx;            // one sharded context per chunk
+    std::vector<long long> p0, p1;        // owned points [p0, p1) of every chunk (per field)
+    std::vector<cudaEvent_t> ev_mean, ev_fac, ev_kernel, ev_d2h;
+    cudaStream_t s_h2d = nullptr, s_comp = nullptr, s_d2h = nullptr;
+    unsigned char *mean_in = nullptr, *mean_out = nullptr, *err = nullptr, *ref = nullptr;   // all chunks, compact per chunk
+    unsigned char *fac_in[3] = {}, *fac_out[3] = {};                                          // rings over the chunks
+    unsigned char *edge_first = nullptr, *edge_last = nullptr;                                // [nchunks][edge_cap]
+    double* sq = nullptr;                 // [nchunks] partial norm sums (device)
+    double* sq_host = nullptr;            // pinned
+    long long edge_cap = 0;
+    static constexpr int kSlots = 3;
+};
+
+static void destroy_pipe(tdx_ctx* ctx) {
+    HostPipe* hp = ctx->pipe;
+    if (!hp) return;
+    int prev = 0;
+    cudaGetDevice(&prev);
+    cudaSetDevice(ctx->device);
+    for (tdx_ctx* c : hp->ctx) tdx_destroy(c);
+    for (auto& v : {&hp->ev_mean, &hp->ev_fac, &hp->ev_kernel, &hp->ev_d2h})
+        for (cudaEvent_t e : *v) cudaEventDestroy(e);
+    if (hp->s_h2d) cudaStreamDestroy(hp->s_h2d);
+    if (hp->s_comp) cudaStreamDestroy(hp->s_comp);
+    if (hp->s_d2h) cudaStreamDestroy(hp->s_d2h);
+    cudaFree(hp->mean_in); cudaFree(hp->mean_out); cudaFree(hp->err); cudaFree(hp->ref);
+    for (int i = 0; i < HostPipe::kSlots; ++i) { cudaFree(hp->fac_in[i]); cudaFree(hp->fac_out[i]); }
+    cudaFree(hp->edge_first); cudaFree(hp->edge_last); cudaFree(hp->sq);
+    if (hp->sq_host) cudaFreeHost(hp->sq_host);
+    cudaSetDevice(prev);
+    delete hp;
+    ctx->pipe = nullptr;
+}
+
+static int build_pipe(tdx_ctx* ctx, int nchunks_hint) {
+    const Geo& g = ctx->geo;
+    const bool rows_axis = g.kind == IVP_FHN2D;
+    const long long extent = rows_axis ? g.rows : g.cols;
+    long long min_chunk = rows_axis ? 8 : 4096;
+    int n = nchunks_hint > 0 ? nchunks_hint : 16;
+    if (g.kind == IVP_VDP) n = 1;
+    while (n > 1 && extent / n < min_chunk) --n;
+    HostPipe* hp = new HostPipe();
+    hp->nchunks = n;
+    const size_t w = esize(ctx->dtype);
+    const long long nn = (long long)ctx->n * ctx->n;
+    long long max_pts = 0;
+    cudaError_t e = cudaSuccess;
+    for (int c = 0; c < n && e == cudaSuccess; ++c) {
+        const long long b = extent * c / n, en = extent * (c + 1) / n;
+        tdx_ctx* cc = nullptr;
+        int rc = tdx_create(&cc, ctx->device, ctx->dtype);
+        if (rc) { delete hp; return rc; }
+        tdx_problem_desc d = ctx->desc;
+        d.shard_begin = b;
+        d.shard_end = en;
+        if ((rc = tdx_set_problem(cc, &d))) { tdx_destroy(cc); delete hp; return rc; }
+        hp->ctx.push_back(cc);
+        const long long per_unit = rows_axis ? g.cols : 1;
+        hp->p0.push_back(b * per_unit);
+        hp->p1.push_back(en * per_unit);
+        max_pts = std::max(max_pts, (en - b) * per_unit);
+    }
+    int nf = 0, nl = 0;
+    edge_counts(g, nf, nl);
+    hp->edge_cap = (long long)g.nf * std::max(nf, nl) + 8;
+    auto alloc = [&](unsigned char** p, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(p, bytes ? bytes : 16); };
+    alloc(&hp->mean_in, (size_t)ctx->n * g.d * w);
+    alloc(&hp->mean_out, (size_t)ctx->n * g.d * w);
+    alloc(&hp->err, (size_t)g.d * w);
+    alloc(&hp->ref, (size_t)g.d * w);
+    for (int i = 0; i < HostPipe::kSlots; ++i) {
+        alloc(&hp->fac_in[i], (size_t)g.nf * max_pts * nn * w);
+        alloc(&hp->fac_out[i], (size_t)g.nf * max_pts * nn * w);
+    }
+    alloc(&hp->edge_first, (size_t)n * hp->edge_cap * w);
+    alloc(&hp->edge_last, (size_t)n * hp->edge_cap * w);
+    alloc((unsigned char**)&hp->sq, (size_t)n * sizeof(double));
+    if (e == cudaSuccess) e = cudaMallocHost(&hp->sq_host, (size_t)n * sizeof(double));
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&hp->s_h2d, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&hp->s_comp, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&hp->s_d2h, cudaStreamNonBlocking);
+    for (auto* v : {&hp->ev_mean, &hp->ev_fac, &hp->ev_kernel, &hp->ev_d2h})
+        for (int c = 0; c < n && e == cudaSuccess; ++c) {
+            cudaEvent_t ev;
+            e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+            if (e == cudaSuccess) v->push_back(ev);
+        }
+    ctx->pipe = hp;
+    if (e != cudaSuccess) {
+        destroy_pipe(ctx);
+        return cuda_fail((int)e, "tdx_dek1_attempt_step_host (pipeline setup)");
+    }
+    return TDX_OK;
+}
+
+extern "C" int tdx_dek1_attempt_step_host(tdx_ctx* ctx, const tdx_step_args* args, const void* h_mean_in,
+                                          const void* h_sc_in, void* h_mean_out, void* h_sc_out, void* h_err_out,
+                                          void* h_ref_out, double* h_sq_norm_sum, int nchunks) {
+    int rc = check_ready(ctx, "tdx_dek1_attempt_step_host");
+    if (rc) return rc;
+    if ((rc = check_dt(args, "tdx_dek1_attempt_step_host"))) return rc;
+    if (ctx->halo_lo > 0 || ctx->halo_hi > 0)
+        return fail(TDX_ERR_INVALID, "tdx_dek1_attempt_step_host: the context must own the whole problem (no sharding)");
+    if (!h_mean_in || !h_sc_in || !h_mean_out || !h_sc_out) return fail(TDX_ERR_INVALID, "tdx_dek1_attempt_step_host: null state buffer");
+    if (args->flags & ~TDX_STEP_ZERO_JACOBIAN) return fail(TDX_ERR_INVALID, "tdx_dek1_attempt_step_host: only TDX_STEP_ZERO_JACOBIAN is accepted");
+    const bool want_norm = args->abstol != 0.0 || args->reltol != 0.0;
+    if (want_norm && !h_sq_norm_sum) return fail(TDX_ERR_INVALID, "tdx_dek1_attempt_step_host: sq_norm_sum is required with tolerances");
+    DeviceGuard guard(ctx->device);
+    if (ctx->pipe && nchunks > 0 && ctx->pipe->nchunks != nchunks) destroy_pipe(ctx);
+    if (!ctx->pipe && (rc = build_pipe(ctx, nchunks))) return rc;
+    HostPipe& hp = *ctx->pipe;
+    const Geo& g = ctx->geo;
+    const int n = ctx->n, nc = hp.nchunks;
+    const size_t w = esize(ctx->dtype);
+    const long long nn = (long long)n * n, npts = g.npts;
+    const bool cyclic = g.kind == IVP_LORENZ96 && nc > 1;
+    for (tdx_ctx* c : hp.ctx) std::memcpy(c->ql_packed, ctx->ql_packed, sizeof(ctx->ql_packed));   // tdx_set_diffusion_sqrt of the parent
+
+    const unsigned char* hm_in = (const unsigned char*)h_mean_in;
+    const unsigned char* hs_in = (const unsigned char*)h_sc_in;
+    unsigned char* hm_out = (unsigned char*)h_mean_out;
+    unsigned char* hs_out = (unsigned char*)h_sc_out;
+    auto dmean = [&](unsigned char* base, int c) { return base + (size_t)n * g.nf * hp.p0[c] * w; };   // compact (n, d_c) block
+    auto dvec = [&](unsigned char* base, int c) { return base + (size_t)g.nf * hp.p0[c] * w; };
+    auto nb = [&](int c) -> int { return cyclic ? (c + nc) % nc : ((c < 0 || c >= nc) ? -1 : c); };
+    std::vector<char> mean_up(nc, 0), packed(nc, 0);
+    cudaError_t e = cudaSuccess;
+#define TDX_PIPE_TRY(expr) do { if (e == cudaSuccess) e = (expr); } while (0)
+
+    auto upload_mean = [&](int c) {
+        if (c < 0 || mean_up[c]) return;
+        const long long np = hp.p1[c] - hp.p0[c];
+        for (int f = 0; f < g.nf; ++f)   // rows = derivatives: (n) x (np) block of the (n, d) host array
+            TDX_PIPE_TRY(cudaMemcpy2DAsync(dmean(hp.mean_in, c) + (size_t)f * np * w, (size_t)g.nf * np * w,
+                                           hm_in + ((size_t)f * npts + hp.p0[c]) * w, (size_t)g.d * w, (size_t)np * w, n,
+                                           cudaMemcpyHostToDevice, hp.s_h2d));
+        TDX_PIPE_TRY(cudaEventRecord(hp.ev_mean[c], hp.s_h2d));
+        mean_up[c] = 1;
+    };
+    auto pack = [&](int c) {
+        if (c < 0 || packed[c] || nc == 1) return;
+        TDX_PIPE_TRY(cudaStreamWaitEvent(hp.s_comp, hp.ev_mean[c], 0));
+        if (e == cudaSuccess && tdx_pack_halo(hp.ctx[c], args->dt, dmean(hp.mean_in, c), hp.edge_first + (size_t)c * hp.edge_cap * w,
+                                              hp.edge_last + (size_t)c * hp.edge_cap * w, hp.s_comp))
+            e = cudaErrorUnknown;
+        packed[c] = 1;
+    };
+
+    for (int c = 0; c < nc && e == cudaSuccess; ++c) {
+        const long long np = hp.p1[c] - hp.p0[c];
+        const int slot = c % HostPipe::kSlots;
+        const int lo = nb(c - 1), hi = nb(c + 1);
+        // ---- host -> device: the means this chunk's stencil touches, then its factor blocks
+        upload_mean(lo);
+        upload_mean(c);
+        upload_mean(hi);
+        if (c >= HostPipe::kSlots) TDX_PIPE_TRY(cudaStreamWaitEvent(hp.s_h2d, hp.ev_kernel[c - HostPipe::kSlots], 0));
+        for (int f = 0; f < g.nf; ++f)
+            TDX_PIPE_TRY(cudaMemcpyAsync(hp.fac_in[slot] + (size_t)f * np * nn * w, hs_in + ((size_t)f * npts + hp.p0[c]) * nn * w,
+                                         (size_t)np * nn * w, cudaMemcpyHostToDevice, hp.s_h2d));
+        TDX_PIPE_TRY(cudaEventRecord(hp.ev_fac[c], hp.s_h2d));
+        // ---- compute
+        pack(lo);
+        pack(c);
+        pack(hi);
+        TDX_PIPE_TRY(cudaStreamWaitEvent(hp.s_comp, hp.ev_fac[c], 0));
+        if (c >= HostPipe::kSlots) TDX_PIPE_TRY(cudaStreamWaitEvent(hp.s_comp, hp.ev_d2h[c - HostPipe::kSlots], 0));
+        const void* halo_lo = (lo >= 0 && hp.ctx[c]->halo_lo > 0) ? hp.edge_last + (size_t)lo * hp.edge_cap * w : nullptr;
+        const void* halo_hi = (hi >= 0 && hp.ctx[c]->halo_hi > 0) ? hp.edge_first + (size_t)hi * hp.edge_cap * w : nullptr;
+        if (e == cudaSuccess) {
+            rc = tdx_dek1_attempt_step(hp.ctx[c], args, dmean(hp.mean_in, c), hp.fac_in[slot], dmean(hp.mean_out, c), hp.fac_out[slot],
+                                       h_err_out ? dvec(hp.err, c) : nullptr, h_ref_out ? dvec(hp.ref, c) : nullptr, halo_lo, halo_hi,
+                                       hp.sq + c, hp.s_comp);
+            if (rc) return rc;
+        }
+        TDX_PIPE_TRY(cudaEventRecord(hp.ev_kernel[c], hp.s_comp));
+        // ---- device -> host
+        TDX_PIPE_TRY(cudaStreamWaitEvent(hp.s_d2h, hp.ev_kernel[c], 0));
+        for (int f = 0; f < g.nf; ++f) {
+            TDX_PIPE_TRY(cudaMemcpy2DAsync(hm_out + ((size_t)f * npts + hp.p0[c]) * w, (size_t)g.d * w,
+                                           dmean(hp.mean_out, c) + (size_t)f * np * w, (size_t)g.nf * np * w, (size_t)np * w, n,
+                                           cudaMemcpyDeviceToHost, hp.s_d2h));
+            TDX_PIPE_TRY(cudaMemcpyAsync(hs_out + ((size_t)f * npts + hp.p0[c]) * nn * w, hp.fac_out[slot] + (size_t)f * np * nn * w,
+                                         (size_t)np * nn * w, cudaMemcpyDeviceToHost, hp.s_d2h));
+            if (h_err_out)
+                TDX_PIPE_TRY(cudaMemcpyAsync((unsigned char*)h_err_out + ((size_t)f * npts + hp.p0[c]) * w, dvec(hp.err, c) + (size_t)f * np * w,
+                                             (size_t)np * w, cudaMemcpyDeviceToHost, hp.s_d2h));
+            if (h_ref_out)
+                TDX_PIPE_TRY(cudaMemcpyAsync((unsigned char*)h_ref_out + ((size_t)f * npts + hp.p0[c]) * w, dvec(hp.ref, c) + (size_t)f * np * w,
+                                             (size_t)np * w, cudaMemcpyDeviceToHost, hp.s_d2h));
+        }
+        TDX_PIPE_TRY(cudaEventRecord(hp.ev_d2h[c], hp.s_d2h));
+        ctx->launches += 1;
+    }
+    if (want_norm) TDX_PIPE_TRY(cudaMemcpyAsync(hp.sq_host, hp.sq, (size_t)nc * sizeof(double), cudaMemcpyDeviceToHost, hp.s_d2h));
+    TDX_PIPE_TRY(cudaStreamSynchronize(hp.s_d2h));
+    TDX_PIPE_TRY(cudaStreamSynchronize(hp.s_comp));
+    TDX_PIPE_TRY(cudaStreamSynchronize(hp.s_h2d));
+#undef TDX_PIPE_TRY
+    if (e != cudaSuccess) return cuda_fail((int)e, "tdx_dek1_attempt_step_host");
+    if (want_norm) {
+        double acc = 0.0;
+        for (int c = 0; c < nc; ++c) acc += hp.sq_host[c];   // chunk order: deterministic
+        *h_sq_norm_sum = acc;
+    }
+    return TDX_OK;
+}

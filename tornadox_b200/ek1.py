@@ -78,6 +78,8 @@ class BatchedEK1(odefilter.ODEFilter):
         if self.engine is None:
             raise RuntimeError("call initialize() first")
         abstol, reltol = self.steprule.kernel_tolerances
+        if state.y.mean.device.type == "cpu":
+            return self._attempt_step_host(state, dt, abstol, reltol)
         mean, sc, err, ref, sq = self.engine.dek1_attempt(
             state.t, dt, state.y.mean, state.y.cov_sqrtm, abstol=abstol, reltol=reltol,
             want_err_ref=self.materialize_error_vectors, jacobian=self._uses_jacobian)
@@ -87,6 +89,35 @@ class BatchedEK1(odefilter.ODEFilter):
             error_estimate=err,
             reference_state=ref,
         )
+        if abstol != 0.0 or reltol != 0.0:
+            new_state.scaled_error_norm_sq_sum = sq
+            new_state.scaled_error_norm_dim = self.engine.d_global
+        info = dict(num_f_evaluations=1)
+        if self._uses_jacobian:
+            info["num_df_diagonal_evaluations"] = 1
+        return new_state, info
+
+    def _attempt_step_host(self, state, dt, abstol, reltol):
+        """``attempt_step`` for a state held in host memory (CPU tensors): chunked H2D | kernel | D2H pipeline inside the
+        library.  The outputs live in two alternating sets of pinned buffers owned by the solver (allocating pinned memory
+        per call would cost more than the step), so a returned state stays valid for ONE further host attempt."""
+        n, d = state.y.mean.shape
+        sets = getattr(self, "_host_out", None)
+        if sets is None or sets[0][0].shape != (n, d):
+            def pinned(shape):
+                return torch.empty(shape, dtype=self.dtype, pin_memory=True)
+            sets = [(pinned((n, d)), pinned((d, n, n))) for _ in range(2)]
+            self._host_out, self._host_turn = sets, 0
+        mean_out, sc_out = sets[self._host_turn]
+        if mean_out.data_ptr() == state.y.mean.data_ptr():
+            self._host_turn ^= 1
+            mean_out, sc_out = sets[self._host_turn]
+        self._host_turn ^= 1
+        mean, sc, err, ref, sq = self.engine.dek1_attempt_host(
+            state.t, dt, state.y.mean, state.y.cov_sqrtm, abstol=abstol, reltol=reltol, mean_out=mean_out, sc_out=sc_out,
+            want_err_ref=self.materialize_error_vectors, jacobian=self._uses_jacobian)
+        new_state = odefilter.ODEFilterState(
+            t=state.t + dt, y=rv.BatchedMultivariateNormal(mean, sc), error_estimate=err, reference_state=ref)
         if abstol != 0.0 or reltol != 0.0:
             new_state.scaled_error_norm_sq_sum = sq
             new_state.scaled_error_norm_dim = self.engine.d_global

@@ -331,6 +331,33 @@ class StepEngine:
             self.all_reduce_(sq)
         return mean_out, sc_out, err, ref, sq
 
+    def dek1_attempt_host(self, t, dt, mean, sc, abstol=0.0, reltol=0.0, mean_out=None, sc_out=None, want_err_ref=True,
+                          jacobian=True, nchunks=0):
+        """One DiagonalEK1 attempt on a state in HOST memory (CPU tensors, pinned for full PCIe speed): the library streams
+        the state through the GPU in chunks, copies in both directions overlapping the kernels (``tdx_dek1_attempt_step_host``).
+        Returns (mean_out, sc_out, err, ref, sq_norm_sum[float]) as CPU tensors; synchronous."""
+        if self.world != 1:
+            raise ValueError("the host-buffer path needs an unsharded solver (one GPU owns the whole problem)")
+        n, d = self.n, self.d_local
+        for x, shape, name in ((mean, (n, d), "mean"), (sc, (d, n, n), "cov_sqrtm")):
+            if not isinstance(x, torch.Tensor) or x.device.type != "cpu" or x.dtype != self.dtype:
+                raise ValueError(f"{name} must be a {self.dtype} CPU tensor")
+            if tuple(x.shape) != tuple(shape) or not x.is_contiguous():
+                raise ValueError(f"{name} must be C-contiguous with shape {tuple(shape)}")
+
+        def host_empty(shape):
+            return torch.empty(shape, dtype=self.dtype, pin_memory=True)
+
+        mean_out = host_empty((n, d)) if mean_out is None else mean_out
+        sc_out = host_empty((d, n, n)) if sc_out is None else sc_out
+        err = host_empty((d,)) if want_err_ref else None
+        ref = host_empty((d,)) if want_err_ref else None
+        sq = ctypes.c_double(0.0)
+        args = self._args(t, dt, abstol, reltol, 0 if jacobian else _lib.TDX_STEP_ZERO_JACOBIAN)
+        _lib.check(self.lib.tdx_dek1_attempt_step_host(self.handle, ctypes.byref(args), _ptr(mean), _ptr(sc), _ptr(mean_out),
+                                                       _ptr(sc_out), _ptr(err), _ptr(ref), ctypes.byref(sq), int(nchunks)))
+        return mean_out, sc_out, err, ref, sq.value
+
     # ---- KroneckerEK0 -----------------------------------------------------------------------------
     def ek0_attempt(self, t, dt, mean, Cl, abstol=0.0, reltol=0.0, mean_out=None, want_ref=True):
         """One KroneckerEK0 attempt.  Returns (mean_out, Cl_out, err[device scalar], ref, sq_norm_sum)."""
