@@ -226,8 +226,10 @@ def run_mine(args):
         start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         launches0 = sol.engine.launch_count()
         start.record()
+        h0 = time.perf_counter()
         for _ in range(k):
             state, _ = sol.attempt_step(state, dt, *problem)
+        host_ms = (time.perf_counter() - h0) * 1e3 / k          # host time to enqueue one attempt (Python + C ABI)
         stop.record()
         barrier()
         ms = start.elapsed_time(stop)
@@ -235,7 +237,7 @@ def run_mine(args):
             t = torch.tensor([ms], device=dev, dtype=torch.float64)
             torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
             ms = float(t.item())
-        return ms, state, sol.engine.launch_count() - launches0
+        return ms, state, sol.engine.launch_count() - launches0, host_ms
 
     def kernel_time(sol, state, dt, k):
         """Average duration of the dominant kernel: CUDA events on the launch stream around k back-to-back launches into
@@ -275,12 +277,13 @@ def run_mine(args):
         dt = 0.5 * sol.steprule.first_dt(*problem)
         if name == args.solver and rank == 0:
             sampler.start()
-        ms, state, launches = timed_steps(sol, state, dt, args.steps, args.warmup)
+        ms, state, launches, host_ms = timed_steps(sol, state, dt, args.steps, args.warmup)
         clocks = sampler.stop() if (name == args.solver and rank == 0) else None
         kms = kernel_time(sol, state, dt, min(args.steps, 10))
         alg = ALG_BYTES[name](n, w) * (d / world)        # per launch, per GPU
         results[name] = {
             "value": d * args.steps / (ms * 1e-3), "ms_per_step": ms / args.steps, "launches": launches, "clocks": clocks,
+            "host_enqueue_ms_per_step": host_ms,
             "roofline": {"bound": "hbm", "achieved": alg / (kms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                          "frac": alg / (kms * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
                          "kernel_ms": kms, "algorithmic_bytes_per_launch": alg},
@@ -323,7 +326,8 @@ def run_mine(args):
             "gpu_launches": main["launches"],
             "roofline": main["roofline"],
             "cpu_baseline": cpu,
-            "also": {other: {k: results[other][k] for k in ("value", "ms_per_step", "roofline", "launches")}},
+            "host_enqueue_ms_per_step": main["host_enqueue_ms_per_step"],
+            "also": {other: {k: results[other][k] for k in ("value", "ms_per_step", "roofline", "launches", "host_enqueue_ms_per_step")}},
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -163,6 +163,41 @@ int tdx_ek0_attempt_step(tdx_ctx* ctx, const tdx_step_args* args, const void* me
                          const void* Cl_in, void* mean_out, void* Cl_out, void* err_out,
                          void* ref_out, double* z_sq_sum, double* sq_norm_sum, void* stream);
 
+/* ---- native accept / reject loop --------------------------------------------------------------------------------
+ * ODEFilter.perform_full_step (odefilter.py:171-223) with the step rules of step.py:28-108: attempt steps from the input
+ * state until one is accepted, entirely inside the library.  The kernel epilogue writes the reduced error norm to
+ * mapped pinned host memory, the host loop polls it (a few microseconds instead of a stream synchronisation + a Python
+ * round trip per attempt), decides accept / reject, proposes the next dt exactly as AdaptiveSteps.suggest does
+ * (step.py:80-91) and relaunches.  Rejected attempts overwrite the same output buffers; the input state is untouched.
+ * Sharded contexts need the peer-memory exchange (flags TDX_STEP_COMM_PACK | TDX_STEP_COMM_REDUCE): every rank then sees
+ * the same global norm and takes the same decisions.  Blocks until a step is accepted (ConstantSteps: returns after the
+ * launch, nothing to wait for). */
+typedef struct {
+    int32_t adaptive;      /* 1: AdaptiveSteps (step.py:55-108); 0: ConstantSteps (step.py:28-52)          */
+    int32_t reserved;
+    double abstol, reltol; /* AdaptiveSteps                                                               */
+    double min_change, max_change; /* AdaptiveSteps.max_changes                                           */
+    double safety_scale;
+    double constant_dt;    /* ConstantSteps.dt                                                            */
+} tdx_steprule;
+
+typedef struct {
+    double t_new;          /* time of the accepted state                                                  */
+    double dt_accepted;    /* the step that was accepted                                                  */
+    double dt_next;        /* next step: suggestion clipped to tmax - t_new (odefilter.py:214-219)         */
+    double error_norm;     /* scaled error norm of the accepted attempt (NaN for ConstantSteps)           */
+    int64_t attempts;      /* num_attempted_steps of this call                                            */
+} tdx_full_step_result;
+
+#define TDX_ERR_NUMERIC 4  /* the error estimate became NaN (the reference would loop forever, odefilter.py:179-219) */
+
+int tdx_dek1_full_step(tdx_ctx* ctx, const tdx_steprule* rule, double t, double dt, double tmax, uint32_t flags,
+                       const void* mean_in, const void* sc_in, void* mean_out, void* sc_out, void* err_out,
+                       void* ref_out, tdx_full_step_result* result, void* stream);
+int tdx_ek0_full_step(tdx_ctx* ctx, const tdx_steprule* rule, double t, double dt, double tmax, uint32_t flags,
+                      const void* mean_in, const void* Cl_in, void* mean_out, void* Cl_out, void* err_out,
+                      void* ref_out, tdx_full_step_result* result, void* stream);
+
 /* ---- peer-memory exchange over NVLink (multi-GPU, one process per GPU on one node) -------------------------
  * No reference counterpart (the reference is single-device).  Instead of NCCL calls between the kernels, every
  * context owns a small device block (halo buffers, reduction slots, sequence-numbered flags) that its neighbours

@@ -82,3 +82,30 @@ def test_solver_attempt_step_accepts_a_host_state(cuda_device):
     # chained host attempts alternate between the solver's two pinned output sets
     again, _ = sol.attempt_step(host_new, dt, *p)
     assert again.y.mean.data_ptr() != host_new.y.mean.data_ptr()
+
+
+@pytest.mark.parametrize("solver_name", ["ek0", "ek1", "dek0"])
+@pytest.mark.parametrize("kind,size,tmax", [("vanderpol", 1, 1.0), ("fhn_2d", 32, 2e-3), ("lorenz96", 300, 1.0), ("brusselator", 200, 3e-3)])
+def test_native_full_step_loop_equals_the_python_loop(cuda_device, solver_name, kind, size, tmax):
+    """tdx_*_full_step (accept / reject in C, norm polled from pinned memory) against odefilter.perform_full_step in Python:
+    same accepted times, same dt proposals, same counters, same final state."""
+    from tornadox_b200 import ek0, ek1, step
+
+    class PyLoopSteps(step.AdaptiveSteps):      # not the reference's exact class -> the solvers take the generic host loop
+        pass
+
+    _, p, _ = make_pair(kind, size, tmax=tmax) if kind == "vanderpol" else make_pair(kind, size)
+    p = p._replace(tmax=tmax)
+    cls = {"ek0": ek0.KroneckerEK0, "ek1": ek1.DiagonalEK1, "dek0": ek0.DiagonalEK0}[solver_name]
+    runs = []
+    for rule in (step.AdaptiveSteps(), PyLoopSteps()):
+        sol = cls(num_derivatives=3, steprule=rule)
+        ts, final, info = [], None, None
+        for st, info in sol.solution_generator(p):
+            ts.append(st.t)
+            final = st
+        runs.append((ts, final, dict(info)))
+    (ts_c, fin_c, info_c), (ts_py, fin_py, info_py) = runs
+    assert info_c == info_py and len(ts_c) > 3
+    np.testing.assert_allclose(ts_c, ts_py, rtol=1e-13, atol=0)
+    assert torch.equal(fin_c.y.mean, fin_py.y.mean)

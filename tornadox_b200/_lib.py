@@ -28,7 +28,7 @@ EXPORTED_SYMBOLS = (
     "tdx_last_error", "tdx_abi_version", "tdx_create", "tdx_destroy", "tdx_set_problem", "tdx_local_dim",
     "tdx_halo_sizes", "tdx_set_diffusion_sqrt", "tdx_prior", "tdx_nordsieck", "tdx_eval_f", "tdx_pack_halo", "tdx_dek1_attempt_step",
     "tdx_ek0_sweep_a", "tdx_ek0_mid", "tdx_ek0_sweep_b", "tdx_ek0_attempt_step", "tdx_launch_count",
-    "tdx_debug_read_workspace", "tdx_dek1_attempt_step_host", "tdx_comm_init", "tdx_comm_connect", "tdx_comm_pack_halo", "tdx_comm_allreduce", "tdx_comm_error",
+    "tdx_debug_read_workspace", "tdx_dek1_attempt_step_host", "tdx_dek1_full_step", "tdx_ek0_full_step", "tdx_comm_init", "tdx_comm_connect", "tdx_comm_pack_halo", "tdx_comm_allreduce", "tdx_comm_error",
 )
 
 
@@ -53,6 +53,29 @@ class StepArgs(ctypes.Structure):
         ("reltol", ctypes.c_double),
         ("flags", ctypes.c_uint32),
         ("reserved", ctypes.c_uint32),
+    ]
+
+
+class StepRule(ctypes.Structure):
+    _fields_ = [
+        ("adaptive", ctypes.c_int32),
+        ("reserved", ctypes.c_int32),
+        ("abstol", ctypes.c_double),
+        ("reltol", ctypes.c_double),
+        ("min_change", ctypes.c_double),
+        ("max_change", ctypes.c_double),
+        ("safety_scale", ctypes.c_double),
+        ("constant_dt", ctypes.c_double),
+    ]
+
+
+class FullStepResult(ctypes.Structure):
+    _fields_ = [
+        ("t_new", ctypes.c_double),
+        ("dt_accepted", ctypes.c_double),
+        ("dt_next", ctypes.c_double),
+        ("error_norm", ctypes.c_double),
+        ("attempts", ctypes.c_int64),
     ]
 
 
@@ -92,6 +115,9 @@ def load():
     lib.tdx_pack_halo.argtypes = [vp, dbl, vp, vp, vp, vp]
     lib.tdx_dek1_attempt_step.argtypes = [vp, ctypes.POINTER(StepArgs)] + [vp] * 10
     lib.tdx_dek1_attempt_step_host.argtypes = [vp, ctypes.POINTER(StepArgs)] + [vp] * 6 + [pd, cint]
+    full = [vp, ctypes.POINTER(StepRule), dbl, dbl, dbl, ctypes.c_uint32] + [vp] * 6 + [ctypes.POINTER(FullStepResult), vp]
+    lib.tdx_dek1_full_step.argtypes = full
+    lib.tdx_ek0_full_step.argtypes = full
     lib.tdx_ek0_sweep_a.argtypes = [vp, ctypes.POINTER(StepArgs), vp, vp, vp, vp, vp]
     lib.tdx_ek0_mid.argtypes = [vp, ctypes.POINTER(StepArgs), vp, vp, i64, vp, vp, vp]
     lib.tdx_ek0_sweep_b.argtypes = [vp, ctypes.POINTER(StepArgs), vp, vp, vp, vp, vp, vp, vp]
@@ -121,6 +147,8 @@ def check(rc, exc=None):
         raise (exc or ValueError)(msg)
     if rc == 2:
         raise NotImplementedError(msg)
+    if rc == 4:
+        raise FloatingPointError(msg)
     raise TornadoxB200Error(msg)
 
 

@@ -142,6 +142,9 @@ static int cuda_fail(int cuda_code, const char* where) {
 struct HostPipe;
 
 struct tdx_ctx {
+    double* host_norm = nullptr;     // mapped pinned: [0] reduced norm sum written by the kernel epilogue (full-step loop)
+    double* host_norm_dev = nullptr; // its device alias
+    double* zsq_scratch = nullptr;   // device scalar for the EK0 z^2 sum inside the full-step loop
     HostPipe* pipe = nullptr;        // chunked host-buffer pipeline (tdx_dek1_attempt_step_host), built on first use
     int device = 0;
     int dtype = TDX_F64;
@@ -234,6 +237,8 @@ int tdx_destroy(tdx_ctx* ctx) {
     int prev = 0;
     cudaGetDevice(&prev);
     cudaSetDevice(ctx->device);
+    if (ctx->host_norm) cudaFreeHost(ctx->host_norm);
+    cudaFree(ctx->zsq_scratch);
     cudaFree(ctx->partials);
     cudaFree(ctx->ticket);
     cudaFree(ctx->mid);
@@ -990,4 +995,127 @@ extern "C" int tdx_dek1_attempt_step_host(tdx_ctx* ctx, const tdx_step_args* arg
         *h_sq_norm_sum = acc;
     }
     return TDX_OK;
+}
+
+
+// =====================================================================================================================
+// Native accept / reject loop (odefilter.py:171-223, step.py:28-108)
+// =====================================================================================================================
+static int ensure_host_norm(tdx_ctx* ctx) {
+    if (ctx->host_norm) return TDX_OK;
+    cudaError_t e = cudaHostAlloc((void**)&ctx->host_norm, 64, cudaHostAllocMapped);
+    if (e == cudaSuccess) e = cudaHostGetDevicePointer((void**)&ctx->host_norm_dev, ctx->host_norm, 0);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&ctx->zsq_scratch, 64);
+    return e == cudaSuccess ? TDX_OK : cuda_fail((int)e, "full-step loop (pinned scalar)");
+}
+
+// wait until the kernel epilogue has replaced the sentinel; polls the stream now and then so that a failed launch
+// cannot spin forever
+static int wait_norm(tdx_ctx* ctx, cudaStream_t st, double* value) {
+    volatile double* p = ctx->host_norm;
+    unsigned long long spins = 0;
+    for (;;) {
+        const double v = *p;
+        if (!(v == -1.0)) {
+            *value = v;
+            return TDX_OK;
+        }
+        if ((++spins & 0xfffffull) == 0ull) {
+            cudaError_t q = cudaStreamQuery(st);
+            if (q == cudaSuccess) {           // the stream drained: the value must be there now
+                *value = *p;
+                if (*value == -1.0) return fail(TDX_ERR_CUDA, "full-step loop: the step kernel finished without writing its norm");
+                return TDX_OK;
+            }
+            if (q != cudaErrorNotReady) return cuda_fail((int)q, "full-step loop");
+        }
+    }
+}
+
+template <class Attempt>
+static int full_step_loop(tdx_ctx* ctx, const tdx_steprule* rule, double t, double dt, double tmax, int rate,
+                          tdx_full_step_result* result, cudaStream_t st, const char* where, Attempt attempt) {
+    if (!rule || !result) return fail(TDX_ERR_INVALID, std::string(where) + ": null step rule or result");
+    if (!(dt > 0.0) || !std::isfinite(dt)) return fail(TDX_ERR_INVALID, std::string(where) + ": Invalid step size: dt must be positive and finite");
+    int rc = ensure_host_norm(ctx);
+    if (rc) return rc;
+    const double d_global = (double)ctx->geo.nf * (double)ctx->geo.grows * (double)ctx->geo.gcols;
+    int64_t attempts = 0;
+    for (;;) {
+        ++attempts;
+        tdx_step_args a{t, dt, rule->adaptive ? rule->abstol : 0.0, rule->adaptive ? rule->reltol : 0.0, 0u, 0u};
+        *ctx->host_norm = -1.0;                      // sentinel: the sum of squares is >= 0 or NaN
+        if ((rc = attempt(a))) return rc;
+        if (!rule->adaptive) {                       // ConstantSteps: always accepted (step.py:41-42), nothing to read
+            result->t_new = t + dt;
+            result->dt_accepted = dt;
+            result->dt_next = std::min(rule->constant_dt, tmax - (t + dt));
+            result->error_norm = std::nan("");
+            result->attempts = attempts;
+            return TDX_OK;
+        }
+        double sum = 0.0;
+        if ((rc = wait_norm(ctx, st, &sum))) return rc;
+        const double norm = std::sqrt(sum / d_global);                       // step.py:101-104
+        if (std::isnan(norm)) return fail(TDX_ERR_NUMERIC, std::string(where) + ": error estimate is NaN");
+        const bool accepted = norm < 1.0;                                     // step.py:90-91
+        double factor = rule->safety_scale * std::pow(norm != 0.0 ? 1.0 / norm : INFINITY, 1.0 / (double)rate);   // step.py:80-88
+        factor = std::max(rule->min_change, std::min(factor, rule->max_change));
+        const double suggested = factor * dt;
+        const double remaining = tmax - (accepted ? t + dt : t);              // odefilter.py:214-219
+        const double dt_next = std::min(suggested, remaining);
+        if (accepted) {
+            result->t_new = t + dt;
+            result->dt_accepted = dt;
+            result->dt_next = dt_next;
+            result->error_norm = norm;
+            result->attempts = attempts;
+            return TDX_OK;
+        }
+        if (!(dt_next > 0.0)) return fail(TDX_ERR_INVALID, std::string(where) + ": Invalid step size after a rejected attempt");
+        dt = dt_next;
+    }
+}
+
+static int check_full_step_flags(const tdx_ctx* ctx, uint32_t flags, const char* where) {
+    const bool sharded = ctx->halo_lo > 0 || ctx->halo_hi > 0;
+    const unsigned comm = TDX_STEP_COMM_PACK | TDX_STEP_COMM_REDUCE;
+    if (sharded && (flags & comm) != comm)
+        return fail(TDX_ERR_INVALID, std::string(where) + ": a sharded context needs TDX_STEP_COMM_PACK | TDX_STEP_COMM_REDUCE so "
+                                                          "that every rank sees the global norm");
+    if (flags & ~(comm | TDX_STEP_ZERO_JACOBIAN)) return fail(TDX_ERR_INVALID, std::string(where) + ": unsupported flags");
+    return TDX_OK;
+}
+
+extern "C" int tdx_dek1_full_step(tdx_ctx* ctx, const tdx_steprule* rule, double t, double dt, double tmax, uint32_t flags,
+                                  const void* mean_in, const void* sc_in, void* mean_out, void* sc_out, void* err_out,
+                                  void* ref_out, tdx_full_step_result* result, void* stream) {
+    int rc = check_ready(ctx, "tdx_dek1_full_step");
+    if (rc) return rc;
+    if ((rc = check_full_step_flags(ctx, flags, "tdx_dek1_full_step"))) return rc;
+    DeviceGuard guard(ctx->device);
+    const bool sharded = ctx->halo_lo > 0 || ctx->halo_hi > 0;
+    return full_step_loop(ctx, rule, t, dt, tmax, ctx->n, result, (cudaStream_t)stream, "tdx_dek1_full_step",
+                          [&](tdx_step_args& a) {
+                              a.flags = sharded ? flags : (flags & TDX_STEP_ZERO_JACOBIAN);
+                              return tdx_dek1_attempt_step(ctx, &a, mean_in, sc_in, mean_out, sc_out, err_out, ref_out, nullptr,
+                                                           nullptr, ctx->host_norm_dev, stream);
+                          });
+}
+
+extern "C" int tdx_ek0_full_step(tdx_ctx* ctx, const tdx_steprule* rule, double t, double dt, double tmax, uint32_t flags,
+                                 const void* mean_in, const void* Cl_in, void* mean_out, void* Cl_out, void* err_out,
+                                 void* ref_out, tdx_full_step_result* result, void* stream) {
+    int rc = check_ready(ctx, "tdx_ek0_full_step");
+    if (rc) return rc;
+    if ((rc = check_full_step_flags(ctx, flags, "tdx_ek0_full_step"))) return rc;
+    DeviceGuard guard(ctx->device);
+    if ((rc = ensure_host_norm(ctx))) return rc;
+    const bool sharded = ctx->halo_lo > 0 || ctx->halo_hi > 0;
+    return full_step_loop(ctx, rule, t, dt, tmax, ctx->n, result, (cudaStream_t)stream, "tdx_ek0_full_step",
+                          [&](tdx_step_args& a) {
+                              a.flags = sharded ? flags : 0u;
+                              return tdx_ek0_attempt_step(ctx, &a, mean_in, Cl_in, mean_out, Cl_out, err_out, ref_out,
+                                                          ctx->zsq_scratch, ctx->host_norm_dev, stream);
+                          });
 }

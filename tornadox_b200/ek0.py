@@ -59,6 +59,24 @@ class KroneckerEK0(odefilter.ODEFilter):
         return new_state, dict(num_f_evaluations=1)
 
 
+    def perform_full_step(self, state, initial_dt, f, t0, tmax, y0, df, df_diagonal):
+        """odefilter.py:171-223 inside the library (``tdx_ek0_full_step``) when the step rule is one of the reference's."""
+        rule = self.engine.native_steprule(self.steprule) if self.engine is not None else None
+        if rule is None or state.y.mean.device.type != "cuda" or not self.engine.can_run_full_steps():
+            return super().perform_full_step(state, initial_dt, f, t0, tmax, y0, df, df_diagonal)
+        mean, Cl, err, ref, res = self.engine.ek0_full_step(
+            rule, state.t, initial_dt, tmax, state.y.mean, state.y.cov_sqrtm_2, want_ref=self.materialize_reference_state)
+        proposed = odefilter.ODEFilterState(t=res.t_new, error_estimate=err, reference_state=ref,
+                                            y=rv.LeftIsotropicMatrixNormal(mean, state.y.d, Cl))
+        assert res.dt_next >= 0, f"Invalid step size: dt={res.dt_next}"   # odefilter.py:221
+        n_att = int(res.attempts)
+        step_info = dict(num_f_evaluations=n_att, num_df_evaluations=0, num_df_diagonal_evaluations=0,
+                         num_attempted_steps=n_att)
+        return proposed, res.dt_next, step_info
+
+    perform_full_step_compiled = perform_full_step
+
+
 class DiagonalEK0(BatchedEK1):
     """ek0.py:196-280: block-diagonal EK0 = DiagonalEK1 with a zero Jacobian diagonal."""
 

@@ -97,6 +97,26 @@ class BatchedEK1(odefilter.ODEFilter):
             info["num_df_diagonal_evaluations"] = 1
         return new_state, info
 
+    def perform_full_step(self, state, initial_dt, f, t0, tmax, y0, df, df_diagonal):
+        """odefilter.py:171-223.  With one of the reference's own step rules and a device-resident state the whole
+        accept / reject loop runs inside the library (``tdx_dek1_full_step``: no Python round trip and no stream
+        synchronisation per attempt); anything else takes the generic host loop."""
+        rule = self.engine.native_steprule(self.steprule) if self.engine is not None else None
+        if rule is None or state.y.mean.device.type != "cuda" or not self.engine.can_run_full_steps():
+            return super().perform_full_step(state, initial_dt, f, t0, tmax, y0, df, df_diagonal)
+        mean, sc, err, ref, res = self.engine.dek1_full_step(
+            rule, state.t, initial_dt, tmax, state.y.mean, state.y.cov_sqrtm,
+            want_err_ref=self.materialize_error_vectors, jacobian=self._uses_jacobian)
+        proposed = odefilter.ODEFilterState(t=res.t_new, y=rv.BatchedMultivariateNormal(mean, sc), error_estimate=err,
+                                            reference_state=ref)
+        assert res.dt_next >= 0, f"Invalid step size: dt={res.dt_next}"   # odefilter.py:221
+        n_att = int(res.attempts)
+        step_info = dict(num_f_evaluations=n_att, num_df_evaluations=0,
+                         num_df_diagonal_evaluations=n_att if self._uses_jacobian else 0, num_attempted_steps=n_att)
+        return proposed, res.dt_next, step_info
+
+    perform_full_step_compiled = perform_full_step
+
     def _attempt_step_host(self, state, dt, abstol, reltol):
         """``attempt_step`` for a state held in host memory (CPU tensors): chunked H2D | kernel | D2H pipeline inside the
         library.  The outputs live in two alternating sets of pinned buffers owned by the solver (allocating pinned memory

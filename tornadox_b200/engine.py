@@ -114,6 +114,7 @@ class StepEngine:
         self.spec, self.nu, self.n = spec, int(nu), int(nu) + 1
         self.dtype = dtype
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        self._dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
         self.group, self.rank, self.world = group, rank, world
         self.begin, self.end = shard_range(spec, rank, world)
         self.d_global = spec.n_fields * spec.grid_rows * spec.grid_cols
@@ -210,7 +211,8 @@ class StepEngine:
         return 0, 0
 
     def _stream(self):
-        return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        # torch.cuda.current_stream() builds a Stream object (7 us); the raw handle is all the C ABI needs
+        return ctypes.c_void_p(torch._C._cuda_getCurrentRawStream(self._dev_index))
 
     def _args(self, t, dt, abstol, reltol, flags=0):
         return _lib.StepArgs(float(t), float(dt), float(abstol), float(reltol), int(flags), 0)
@@ -357,6 +359,54 @@ class StepEngine:
         _lib.check(self.lib.tdx_dek1_attempt_step_host(self.handle, ctypes.byref(args), _ptr(mean), _ptr(sc), _ptr(mean_out),
                                                        _ptr(sc_out), _ptr(err), _ptr(ref), ctypes.byref(sq), int(nchunks)))
         return mean_out, sc_out, err, ref, sq.value
+
+    # ---- native accept / reject loop (odefilter.py:171-223 inside the library) --------------------------------------
+    def native_steprule(self, steprule):
+        """The C mirror of a step rule, or None if it is not exactly one of the reference's two rules."""
+        from . import step as _step
+
+        if type(steprule) is _step.AdaptiveSteps:
+            lower, upper = steprule.max_changes
+            return _lib.StepRule(1, 0, float(steprule.abstol), float(steprule.reltol), float(lower), float(upper),
+                                 float(steprule.safety_scale), 0.0)
+        if type(steprule) is _step.ConstantSteps:
+            return _lib.StepRule(0, 0, 0.0, 0.0, 0.0, 0.0, 0.0, float(steprule.dt))
+        return None
+
+    def can_run_full_steps(self):
+        return self.world == 1 or self.peer
+
+    def _full_step_flags(self, base=0):
+        return base | ((_lib.TDX_STEP_COMM_PACK | _lib.TDX_STEP_COMM_REDUCE) if self.world > 1 else 0)
+
+    def dek1_full_step(self, rule, t, dt, tmax, mean, sc, want_err_ref=True, jacobian=True):
+        """Attempt DiagonalEK1 steps from (mean, sc) until one is accepted; returns (mean_out, sc_out, err, ref, result)."""
+        n, d = self.n, self.d_local
+        self._check(mean, (n, d), "mean")
+        self._check(sc, (d, n, n), "cov_sqrtm")
+        mean_out, sc_out = torch.empty_like(mean), torch.empty_like(sc)
+        err = torch.empty(d, dtype=self.dtype, device=self.device) if want_err_ref else None
+        ref = torch.empty(d, dtype=self.dtype, device=self.device) if want_err_ref else None
+        res = _lib.FullStepResult()
+        flags = self._full_step_flags(0 if jacobian else _lib.TDX_STEP_ZERO_JACOBIAN)
+        _lib.check(self.lib.tdx_dek1_full_step(self.handle, ctypes.byref(rule), float(t), float(dt), float(tmax), flags,
+                                               _ptr(mean), _ptr(sc), _ptr(mean_out), _ptr(sc_out), _ptr(err), _ptr(ref),
+                                               ctypes.byref(res), self._stream()))
+        return mean_out, sc_out, err, ref, res
+
+    def ek0_full_step(self, rule, t, dt, tmax, mean, Cl, want_ref=True):
+        """Attempt KroneckerEK0 steps from (mean, Cl) until one is accepted; returns (mean_out, Cl_out, err, ref, result)."""
+        n, d = self.n, self.d_local
+        self._check(mean, (n, d), "mean")
+        self._check(Cl, (n, n), "cov_sqrtm_2")
+        mean_out, Cl_out = torch.empty_like(mean), torch.empty_like(Cl)
+        err = torch.empty((), dtype=self.dtype, device=self.device)
+        ref = torch.empty(d, dtype=self.dtype, device=self.device) if want_ref else None
+        res = _lib.FullStepResult()
+        _lib.check(self.lib.tdx_ek0_full_step(self.handle, ctypes.byref(rule), float(t), float(dt), float(tmax),
+                                              self._full_step_flags(), _ptr(mean), _ptr(Cl), _ptr(mean_out), _ptr(Cl_out),
+                                              _ptr(err), _ptr(ref), ctypes.byref(res), self._stream()))
+        return mean_out, Cl_out, err, ref, res
 
     # ---- KroneckerEK0 -----------------------------------------------------------------------------
     def ek0_attempt(self, t, dt, mean, Cl, abstol=0.0, reltol=0.0, mean_out=None, want_ref=True):
