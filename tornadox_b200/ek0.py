@@ -21,8 +21,9 @@ class KroneckerEK0(odefilter.ODEFilter):
         self.Ql = None
         self.engine = None
 
-    #: when False, reference_state = |mean[0]| is not written by the kernel (it is implied by the mean)
-    materialize_reference_state = True
+    #: when False (default), reference_state = |mean[0]| is not written by the kernel every attempt: it is implied by the
+    #: new mean and is computed on first access of ``state.reference_state`` (``odefilter.DeferredAbsRow``)
+    materialize_reference_state = False
 
     def initialize(self, f, t0, tmax, y0, df, df_diagonal):
         """ek0.py:94-121: single (n, n) factor, scalar NaN error estimate."""
@@ -50,7 +51,7 @@ class KroneckerEK0(odefilter.ODEFilter):
         new_state = odefilter.ODEFilterState(
             t=state.t + dt,
             error_estimate=err,
-            reference_state=ref,
+            reference_state=ref if ref is not None else odefilter.DeferredAbsRow(mean),
             y=rv.LeftIsotropicMatrixNormal(mean, state.y.d, Cl),
         )
         if abstol != 0.0 or reltol != 0.0:
@@ -66,7 +67,8 @@ class KroneckerEK0(odefilter.ODEFilter):
             return super().perform_full_step(state, initial_dt, f, t0, tmax, y0, df, df_diagonal)
         mean, Cl, err, ref, res = self.engine.ek0_full_step(
             rule, state.t, initial_dt, tmax, state.y.mean, state.y.cov_sqrtm_2, want_ref=self.materialize_reference_state)
-        proposed = odefilter.ODEFilterState(t=res.t_new, error_estimate=err, reference_state=ref,
+        proposed = odefilter.ODEFilterState(t=res.t_new, error_estimate=err,
+                                            reference_state=ref if ref is not None else odefilter.DeferredAbsRow(mean),
                                             y=rv.LeftIsotropicMatrixNormal(mean, state.y.d, Cl))
         assert res.dt_next >= 0, f"Invalid step size: dt={res.dt_next}"   # odefilter.py:221
         n_att = int(res.attempts)

@@ -19,15 +19,36 @@ import torch
 from . import init, step
 
 
+class DeferredAbsRow:
+    """``|mean[0]|`` computed when somebody asks for it.  KroneckerEK0's reference_state (ek0.py:184) is implied by the
+    new mean; the fused kernel already consumed it for the error norm, so writing it to HBM every attempt (8 B per
+    dimension) only pays off if the caller reads it."""
+
+    def __init__(self, mean):
+        self._mean, self._value = mean, None
+
+    def get(self):
+        if self._value is None:
+            self._value = self._mean[0].abs()
+            self._mean = None
+        return self._value
+
+
 class ODEFilterState(namedtuple("_ODEFilterState", "t y error_estimate reference_state")):
     """(t, y, error_estimate, reference_state) as in odefilter.py:17-20.
 
     Instances produced by the fused solvers additionally carry ``scaled_error_norm_sq_sum``: the device
     scalar the kernel epilogue reduced (None otherwise); see ``ODEFilter._scaled_error_norm``.
+    ``reference_state`` may be stored as a ``DeferredAbsRow``; attribute access resolves it.
     """
 
     scaled_error_norm_sq_sum = None
     scaled_error_norm_dim = None
+
+    @property
+    def reference_state(self):
+        raw = tuple.__getitem__(self, 3)
+        return raw.get() if isinstance(raw, DeferredAbsRow) else raw
 
 
 @dataclasses.dataclass(frozen=False)
