@@ -50,6 +50,8 @@ extern "C" {
 #define TDX_IVP_LORENZ96 1    /* params: [forcing]                   ivp.py:268-294 */
 #define TDX_IVP_BRUSSELATOR 2 /* params: [] (c derived from N)       ivp.py:219-265 */
 #define TDX_IVP_FHN2D 3       /* params: [dx, a, b, k, tau]          ivp.py:409-505 */
+#define TDX_IVP_BURGERS1D 4   /* params: [dx, diffusion_param]       ivp.py:76-107  (one GPU only) */
+#define TDX_IVP_WAVE1D 5      /* params: [dx, diffusion_param]       ivp.py:110-140 (one GPU only) */
 
 typedef struct tdx_ctx tdx_ctx;
 

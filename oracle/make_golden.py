@@ -33,6 +33,8 @@ def problems(tornadox):
     import jax.numpy as jnp
 
     out["fhn_2d"] = (tornadox.ivp.fhn_2d(t0=0.0, tmax=0.05, y0=jnp.array(y0), dx=0.2), dict(dx=0.2, nx=5))
+    out["burgers_1d"] = (tornadox.ivp.burgers_1d(t0=0.0, tmax=0.05, dx=0.1), dict(dx=0.1))
+    out["wave_1d"] = (tornadox.ivp.wave_1d(t0=0.0, tmax=0.05, dx=0.1), dict(dx=0.1))
     return out
 
 
@@ -87,7 +89,8 @@ def main():
             m0 = np.asarray(tornadox.init.TaylorMode.taylor_mode(ivp.f, ivp.y0, ivp.t0, nu))
             g[f"init/{name}/nu{nu}/taylor"] = m0
             dts = {"vanderpol": [0.0123, 0.05, 0.02], "lorenz96": [0.01, 0.02, 0.005],
-                   "brusselator": [0.02, 0.05, 0.01], "fhn_2d": [0.01, 0.03, 0.01]}[name]
+                   "brusselator": [0.02, 0.05, 0.01], "fhn_2d": [0.01, 0.03, 0.01],
+                   "burgers_1d": [0.01, 0.02, 0.005], "wave_1d": [0.01, 0.03, 0.01]}[name]
             g[f"steps/{name}/dts"] = np.asarray(dts)
             solvers = {
                 "dek1": tornadox.ek1.DiagonalEK1,
@@ -119,7 +122,8 @@ def main():
         mean[0] = y0
         blocks = 1e-2 * rng.standard_normal((d, n, n))
         single = 1e-2 * rng.standard_normal((n, n))
-        dt = {"vanderpol": 0.0123, "lorenz96": 0.01, "brusselator": 1e-4, "fhn_2d": 1e-3}[name]
+        dt = {"vanderpol": 0.0123, "lorenz96": 0.01, "brusselator": 1e-4, "fhn_2d": 1e-3, "burgers_1d": 1e-3,
+              "wave_1d": 1e-3}[name]
         g[f"dense/{name}/mean"], g[f"dense/{name}/blocks"], g[f"dense/{name}/single"] = mean, blocks, single
         g[f"dense/{name}/dt"] = np.asarray(dt)
         sol = tornadox.ek1.DiagonalEK1(num_derivatives=nu)

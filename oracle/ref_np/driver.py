@@ -262,6 +262,33 @@ def series_brusselator(N):
     return f
 
 
+def series_burgers_1d(dx, diffusion_param=0.02):
+    """ivp.py:86-96 on Series arguments."""
+
+    def f(_, x):
+        n = x.c.shape[1]
+        mid, left, right = x[1:n - 1], x[0:n - 2], x[2:n]
+        interior = -(mid * (mid - left)) / dx + diffusion_param * (right - 2.0 * mid + left) / (dx**2)
+        x0, x1, xm = x[0:1], x[1:2], x[n - 2:n - 1]
+        boundary = -(x0 * (x0 - xm)) / dx + diffusion_param * (x1 - 2.0 * x0 + xm) / (dx**2)
+        return series_concat([boundary, interior, boundary])
+
+    return f
+
+
+def series_wave_1d(dx, diffusion_param=0.01):
+    """ivp.py:124-130 on Series arguments."""
+
+    def f(_, y):
+        n = y.c.shape[1] // 2
+        x, v = y[0:n], y[n:2 * n]
+        interior = diffusion_param * (x[2:n] - 2.0 * x[1:n - 1] + x[0:n - 2]) / (dx**2)
+        zero = x[0:1] * 0.0
+        return series_concat([zero, v[1:n - 1], zero, x[0:1], interior, x[n - 1:n]])
+
+    return f
+
+
 def series_fhn_2d(nx, ny, dx, a=2.8e-4, b=5e-3, k=-0.005, tau=0.1):
     from .problems import laplace_2d
 

@@ -1,7 +1,7 @@
 """ORACLE (test infrastructure): NumPy restatement of the in-scope vector fields of ``tornadox/ivp.py``.
 
-vanderpol (ivp.py:28-49), brusselator (ivp.py:219-265), lorenz96 (ivp.py:268-294, 335-341),
-fhn_2d (ivp.py:409-481) with its 5-point Neumann Laplacian (ivp.py:484-505).
+vanderpol (ivp.py:28-49), burgers_1d (ivp.py:76-107), wave_1d (ivp.py:110-140), brusselator (ivp.py:219-265),
+lorenz96 (ivp.py:268-294, 335-341), fhn_2d (ivp.py:409-481) with its 5-point Neumann Laplacian (ivp.py:484-505).
 Each factory returns ``Problem(f, t0, tmax, y0, df, df_diagonal)`` -- the field order of the
 reference's ``InitialValueProblem`` namedtuple (ivp.py:10-25).  ``df`` (dense Jacobian, the
 reference gets it from ``jax.jacfwd``) is built analytically and is only meant for small d.
@@ -30,6 +30,75 @@ def vanderpol(t0=0.0, tmax=30, y0=None, stiffness_constant=1e1):
         return np.array([0.0, mu * (1.0 - Y[0] ** 2)])
 
     return Problem(f, t0, tmax, y0, df, df_diagonal)
+
+
+def mesh_1d(bbox, dx):
+    """ivp.py:81, 115: ``arange(bbox[0], bbox[1] + dx, step=dx)`` (NumPy's arange is what jnp.arange evaluates)."""
+    if bbox is None:
+        bbox = [0.0, 1.0]
+    return np.arange(bbox[0], bbox[1] + dx, step=dx), bbox
+
+
+def burgers_1d(t0=0.0, tmax=10.0, y0=None, bbox=None, dx=0.02, diffusion_param=0.02):
+    """ivp.py:76-107.  Upwind convection + diffusion in the interior; BOTH end points get the same "cyclic" value built
+    from x[0], x[1] and x[-2].  The reference's Jacobian diagonal is ``diag(jacfwd(f))`` (:106): written out here."""
+    mesh, bbox = mesh_1d(bbox, dx)
+    if y0 is None:
+        y0 = np.exp(-500.0 * (mesh - (0.6 * (bbox[1] - bbox[0]))) ** 2)
+
+    def f(_, x):
+        nonlinear_convection = x[1:-1] * (x[1:-1] - x[:-2]) / dx
+        diffusion = diffusion_param * (x[2:] - 2.0 * x[1:-1] + x[:-2]) / (dx**2)
+        interior = (-nonlinear_convection + diffusion).reshape(-1)
+        boundary = np.array(-x[0] * (x[0] - x[-2]) / dx + diffusion_param * (x[1] - 2.0 * x[0] + x[-2]) / (dx**2)).reshape(-1)
+        return np.concatenate((boundary, interior, boundary))
+
+    def df_diagonal(_, x):
+        d = np.empty_like(x)
+        d[1:-1] = -(2.0 * x[1:-1] - x[:-2]) / dx - 2.0 * diffusion_param / (dx**2)
+        d[0] = -(2.0 * x[0] - x[-2]) / dx - 2.0 * diffusion_param / (dx**2)
+        d[-1] = 0.0                      # f[-1] is the boundary value, which does not depend on x[-1]
+        return d
+
+    def df(t, x):
+        return _dense_jacobian(f, t, x)
+
+    return Problem(f, t0, tmax, np.asarray(y0, dtype=float), df, df_diagonal)
+
+
+def wave_1d(t0=0.0, tmax=20.0, y0=None, bbox=None, dx=0.02, diffusion_param=0.01):
+    """ivp.py:110-140.  y = [x(N); x'(N)]; the end points are frozen in a peculiar way: d/dt x = 0 and d/dt x' = x there.
+    Every diagonal entry of the Jacobian is zero."""
+    mesh, bbox = mesh_1d(bbox, dx)
+    if y0 is None:
+        x0 = np.exp(-70.0 * (mesh - (0.6 * (bbox[1] - bbox[0]))) ** 2)
+        y0 = np.concatenate((x0, np.zeros_like(x0)))
+
+    def f(_, x):
+        _x, _dx = np.split(x, 2)
+        interior = diffusion_param * (_x[2:] - 2.0 * _x[1:-1] + _x[:-2]) / (dx**2)
+        _ddx = np.concatenate((_x[:1], interior, _x[-1:]))
+        new_dx = np.concatenate((np.zeros(1), _dx[1:-1], np.zeros(1)))
+        return np.concatenate((new_dx, _ddx))
+
+    def df_diagonal(_, x):
+        return np.zeros_like(x)
+
+    def df(t, x):
+        return _dense_jacobian(f, t, x)
+
+    return Problem(f, t0, tmax, np.asarray(y0, dtype=float), df, df_diagonal)
+
+
+def _dense_jacobian(f, t, x, h=1e-30):
+    """Complex-step Jacobian (exact to rounding for the polynomial fields above; small d only)."""
+    n = x.shape[0]
+    J = np.zeros((n, n))
+    for j in range(n):
+        xc = x.astype(complex)
+        xc[j] += 1j * h
+        J[:, j] = np.imag(f(t, xc)) / h
+    return J
 
 
 def brusselator(N=20, t0=0.0, tmax=10.0, y0=None):

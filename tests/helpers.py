@@ -26,6 +26,16 @@ def make_pair(kind, size, **kw):
         o = oproblems.brusselator(N=size)
         p = pivp.brusselator(N=size)
         return o, p, odriver.series_brusselator(size)
+    if kind == "burgers_1d":                      # size = number of mesh points
+        dx = 1.0 / (size - 1)
+        o = oproblems.burgers_1d(dx=dx)
+        assert o.y0.shape[0] == size, (o.y0.shape, size)
+        return o, pivp.burgers_1d(dx=dx), odriver.series_burgers_1d(dx)
+    if kind == "wave_1d":
+        dx = 1.0 / (size - 1)
+        o = oproblems.wave_1d(dx=dx)
+        assert o.y0.shape[0] == 2 * size, (o.y0.shape, size)
+        return o, pivp.wave_1d(dx=dx), odriver.series_wave_1d(dx)
     if kind == "fhn_2d":
         dx = 1.0 / size
         y0 = np.random.default_rng(2).uniform(size=(2 * size * size,))
@@ -107,6 +117,10 @@ def oracle_problem(name):
         return oproblems.brusselator(N=7, t0=0.0, tmax=0.05), odriver.series_brusselator(7)
     if name == "fhn_2d":
         return oproblems.fhn_2d(t0=0.0, tmax=0.05, y0=y0, dx=0.2), odriver.series_fhn_2d(5, 5, 0.2)
+    if name == "burgers_1d":
+        return oproblems.burgers_1d(t0=0.0, tmax=0.05, dx=0.1), odriver.series_burgers_1d(0.1)
+    if name == "wave_1d":
+        return oproblems.wave_1d(t0=0.0, tmax=0.05, dx=0.1), odriver.series_wave_1d(0.1)
     raise KeyError(name)
 
 
@@ -123,4 +137,8 @@ def product_problem(name):
         return pivp.brusselator(N=7, t0=0.0, tmax=0.05)
     if name == "fhn_2d":
         return pivp.fhn_2d(t0=0.0, tmax=0.05, y0=y0, dx=0.2)
+    if name == "burgers_1d":
+        return pivp.burgers_1d(t0=0.0, tmax=0.05, dx=0.1)
+    if name == "wave_1d":
+        return pivp.wave_1d(t0=0.0, tmax=0.05, dx=0.1)
     raise KeyError(name)

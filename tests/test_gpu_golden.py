@@ -11,7 +11,7 @@ from helpers import FP32_RTOL, FP64_RTOL, assert_close, golden, product_problem
 
 pytestmark = pytest.mark.gpu
 
-NAMES = ["vanderpol", "lorenz96", "brusselator", "fhn_2d"]
+NAMES = ["vanderpol", "lorenz96", "brusselator", "fhn_2d", "burgers_1d", "wave_1d"]
 
 
 def _np(x):

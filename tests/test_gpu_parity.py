@@ -20,6 +20,14 @@ CASES = [
     ("brusselator", 20),
     ("brusselator", 517),
     ("brusselator", 4096),
+    ("burgers_1d", 3),
+    ("burgers_1d", 11),
+    ("burgers_1d", 257),
+    ("burgers_1d", 1001),
+    ("wave_1d", 3),
+    ("wave_1d", 11),
+    ("wave_1d", 129),
+    ("wave_1d", 1001),
     ("fhn_2d", 2),
     ("fhn_2d", 7),
     ("fhn_2d", 50),

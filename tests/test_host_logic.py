@@ -95,7 +95,7 @@ def test_df_diagonal_equals_dense_jacobian_diagonal():
     """tests/test_ivp.py:60-64, extended to an fhn grid with edge AND interior nodes (5 x 5)."""
     rng = np.random.default_rng(3)
     probs = [oproblems.vanderpol(), oproblems.brusselator(N=6), oproblems.lorenz96(num_variables=9),
-             oproblems.fhn_2d(dx=0.2, y0=rng.uniform(size=50))]
+             oproblems.fhn_2d(dx=0.2, y0=rng.uniform(size=50)), oproblems.burgers_1d(dx=0.1), oproblems.wave_1d(dx=0.125)]
     for prob in probs:
         y = prob.y0 + 0.1 * rng.standard_normal(prob.y0.shape)
         np.testing.assert_allclose(prob.df_diagonal(0.0, y), np.diag(prob.df(0.0, y)), rtol=1e-11, atol=1e-11)
@@ -153,7 +153,8 @@ def test_problem_factories_and_specs():
     assert len(tuple(v)) == 6   # *ivp unpacking as in odefilter.py:109
 
 
-@pytest.mark.parametrize("name,size", [("vanderpol", 1), ("lorenz96", 9), ("brusselator", 6), ("fhn_2d", 5)])
+@pytest.mark.parametrize("name,size", [("vanderpol", 1), ("lorenz96", 9), ("brusselator", 6), ("fhn_2d", 5),
+                                       ("burgers_1d", 11), ("wave_1d", 9)])
 def test_taylor_mode_series_algebra_on_cpu_tensors(name, size):
     """The product's Taylor-mode initialisation is plain tensor algebra: check it on CPU tensors vs the oracle."""
     from helpers import make_pair

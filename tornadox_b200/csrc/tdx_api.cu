@@ -52,6 +52,8 @@ long long grid_for(const Geo& g) {
         case IVP_LORENZ96: return num_tiles<Lorenz96<double>::Shape>(g.rows, g.cols);
         case IVP_BRUSS: return num_tiles<Brusselator<double>::Shape>(g.rows, g.cols);
         case IVP_FHN2D: return num_tiles<Fhn2d<double>::Shape>(g.rows, g.cols);
+        case IVP_BURGERS1D: return num_tiles<Burgers1d<double>::Shape>(g.rows, g.cols);
+        case IVP_WAVE1D: return num_tiles<Wave1d<double>::Shape>(g.rows, g.cols);
     }
     return 0;
 }
@@ -293,6 +295,19 @@ int tdx_set_problem(tdx_ctx* ctx, const tdx_problem_desc* d) {
                 g.prm[0] = alpha * (np1 * np1);
             }
             break;
+        case TDX_IVP_BURGERS1D:
+        case TDX_IVP_WAVE1D:
+            if (d->grid_rows != 1) return fail(TDX_ERR_INVALID, "tdx_set_problem: burgers_1d / wave_1d are one-dimensional (grid_rows = 1)");
+            if (d->grid_cols < 3) return fail(TDX_ERR_INVALID, "tdx_set_problem: burgers_1d / wave_1d need at least 3 mesh points");
+            if (d->shard_begin != 0 || d->shard_end != d->grid_cols)
+                return fail(TDX_ERR_UNSUPPORTED, "tdx_set_problem: burgers_1d / wave_1d run on one GPU only (their end-point "
+                                                 "rules couple the two ends of the mesh)");
+            if (d->n_params < 2) return fail(TDX_ERR_INVALID, "tdx_set_problem: burgers_1d / wave_1d need params = [dx, diffusion_param]");
+            g.nf = d->kind == TDX_IVP_WAVE1D ? 2 : 1;
+            g.rows = 1; g.cols = (int)d->grid_cols; g.grow0 = 0; g.gcol0 = 0;
+            g.prm[0] = 1.0 / d->params[0];                                  // 1 / dx
+            g.prm[1] = d->params[1] / (d->params[0] * d->params[0]);        // diffusion_param / dx^2  (ivp.py:88, 126)
+            break;
         case TDX_IVP_FHN2D:
             if (d->grid_rows != d->grid_cols)
                 return fail(TDX_ERR_INVALID,
@@ -312,8 +327,8 @@ int tdx_set_problem(tdx_ctx* ctx, const tdx_problem_desc* d) {
             break;
         default:
             return fail(TDX_ERR_UNSUPPORTED,
-                        "tdx_set_problem: unknown vector field kind; only vanderpol, lorenz96, brusselator and fhn_2d "
-                        "are evaluated in-kernel (there is no CPU fallback)");
+                        "tdx_set_problem: unknown vector field kind; only vanderpol, lorenz96, brusselator, fhn_2d, "
+                        "burgers_1d and wave_1d are evaluated in-kernel (there is no CPU fallback)");
     }
     g.npts = (long long)g.rows * g.cols;
     g.d = (long long)g.nf * g.npts;
@@ -324,6 +339,7 @@ int tdx_set_problem(tdx_ctx* ctx, const tdx_problem_desc* d) {
         case IVP_LORENZ96: Lorenz96<double>::halo_sizes(g, lo, hi); break;
         case IVP_BRUSS: Brusselator<double>::halo_sizes(g, lo, hi); break;
         case IVP_FHN2D: Fhn2d<double>::halo_sizes(g, lo, hi); break;
+        default: break;   // burgers_1d, wave_1d: never sharded
     }
 
     long long grid = grid_for(g);

@@ -16,7 +16,7 @@ constexpr int kMaxN = 7;       // n = nu + 1 <= 7
 constexpr int kWarps = 8;      // warps per CTA; every warp owns one 32-wide segment of one field
 constexpr int kThreads = kWarps * 32;
 
-enum : int { IVP_VDP = 0, IVP_LORENZ96 = 1, IVP_BRUSS = 2, IVP_FHN2D = 3 };
+enum : int { IVP_VDP = 0, IVP_LORENZ96 = 1, IVP_BRUSS = 2, IVP_FHN2D = 3, IVP_BURGERS1D = 4, IVP_WAVE1D = 5 };
 
 // Local shard geometry.  Flat local state index = field * npts + row * cols + col.
 struct Geo {
@@ -276,6 +276,66 @@ struct Brusselator {
             fx = (T)3 * u - uu * v + cc * conv;
             jac = -uu - (T)2 * cc;
         }
+    }
+};
+
+// --- burgers_1d: ivp.py:76-107.  Interior: -x_i (x_i - x_{i-1}) / dx + nu (x_{i+1} - 2 x_i + x_{i-1}) / dx^2.  BOTH end
+//     points get the same "cyclic" value built from x_0, x_1 and x_{N-2}: the ring maps the column left of the mesh to
+//     x_{N-2} and the two columns right of it to x_0, x_1, so point 0 is the interior formula and point N-1 re-evaluates
+//     point 0's.  diag J (the reference takes diag(jacfwd f), :106): -(2 x_i - x_{i-1}) / dx - 2 nu / dx^2, 0 at N-1.
+//     One GPU only (prm[0] = 1/dx, prm[1] = nu/dx^2). -------------------------------------------------------------------
+template <typename T>
+struct Burgers1d {
+    using Shape = TileShape<1, 1, 8>;
+    static constexpr int HL = 1, HR = 2, HV = 0;
+    static __host__ void halo_sizes(const Geo&, long long& lo, long long& hi) { lo = hi = 0; }
+    template <class At>
+    __device__ static __forceinline__ T ring_value(const Geo& g, int, int col0, int, int, int ec, const At& at, const T*,
+                                                   const T*) {
+        const long long col = (long long)col0 + ec - HL;
+        if (col >= 0 && col < g.cols) return at(col);
+        if (col == -1) return at(g.cols - 2);
+        if (col == g.cols) return at(0);
+        if (col == g.cols + 1) return at(1);
+        return (T)0;
+    }
+    __device__ static __forceinline__ void eval(const Geo& g, const Coord& c, const T* s_ext, T own, T& fx, T& jac) {
+        const T inv_dx = (T)g.prm[0], nu_dx2 = (T)g.prm[1];
+        const T* p = s_ext + c.tcol;                               // p[HL] is the own point
+        const bool last = c.col == g.cols - 1;
+        const T xl = p[0];                                         // x_{i-1}; x_{N-2} for i = 0 and for i = N-1
+        const T xc = last ? p[2] : own;                            // the last point evaluates x_0's formula
+        const T xr = last ? p[3] : p[2];
+        fx = -xc * (xc - xl) * inv_dx + nu_dx2 * (xr - (T)2 * xc + xl);
+        jac = last ? (T)0 : -((T)2 * xc - xl) * inv_dx - (T)2 * nu_dx2;
+    }
+};
+
+// --- wave_1d: ivp.py:110-140.  y = [x(N); v(N)]: x' = v and v' = nu (x_{i+1} - 2 x_i + x_{i-1}) / dx^2 in the interior;
+//     at the two end points x' = 0 and v' = x.  The Jacobian diagonal vanishes everywhere.  One GPU only
+//     (prm[1] = nu/dx^2). ----------------------------------------------------------------------------------------------
+template <typename T>
+struct Wave1d {
+    using Shape = TileShape<2, 1, 4>;
+    static constexpr int HL = 1, HR = 1, HV = 0;
+    static __host__ void halo_sizes(const Geo&, long long& lo, long long& hi) { lo = hi = 0; }
+    template <class At>
+    __device__ static __forceinline__ T ring_value(const Geo& g, int, int col0, int field, int, int ec, const At& at,
+                                                   const T*, const T*) {
+        const long long col = (long long)col0 + ec - HL;
+        if (col >= 0 && col < g.cols) return at((long long)field * g.npts + col);
+        return (T)0;                                               // never used: the end points have their own rule
+    }
+    __device__ static __forceinline__ void eval(const Geo& g, const Coord& c, const T* s_ext, T own, T& fx, T& jac) {
+        using E = ExtTile<Wave1d<T>>;
+        const T nu_dx2 = (T)g.prm[1];
+        const bool edge = c.col == 0 || c.col == g.cols - 1;
+        const int xi = E::index(0, 0, c.tcol + HL);
+        const T x = s_ext[xi], v = s_ext[E::index(1, 0, c.tcol + HL)];
+        if (c.field == 0) fx = edge ? (T)0 : v;
+        else fx = edge ? x : nu_dx2 * (s_ext[xi + 1] - (T)2 * x + s_ext[xi - 1]);
+        jac = (T)0;
+        (void)own;
     }
 };
 

@@ -134,6 +134,8 @@ inline cudaError_t persistent_grid(size_t smem, long long tiles, int reserve, un
         case IVP_LORENZ96: { using IVP = Lorenz96<T>; __VA_ARGS__ } break;       \
         case IVP_BRUSS: { using IVP = Brusselator<T>; __VA_ARGS__ } break;       \
         case IVP_FHN2D: { using IVP = Fhn2d<T>; __VA_ARGS__ } break;             \
+        case IVP_BURGERS1D: { using IVP = Burgers1d<T>; __VA_ARGS__ } break;     \
+        case IVP_WAVE1D: { using IVP = Wave1d<T>; __VA_ARGS__ } break;           \
         default: return -1;                                                      \
     }
 

@@ -25,6 +25,8 @@ def shard_range(spec, rank, world):
         return 0, extent
     if spec.kind == _lib.TDX_IVP_VANDERPOL:
         raise ValueError("vanderpol (d = 2) cannot be sharded across GPUs")
+    if spec.kind in (_lib.TDX_IVP_BURGERS1D, _lib.TDX_IVP_WAVE1D):
+        raise NotImplementedError(f"{spec.name} runs on one GPU only (its end-point rules couple the two ends of the mesh)")
     if extent < 2 * world:
         raise ValueError(f"cannot shard an axis of {extent} across {world} ranks")
     base, rem = divmod(extent, world)

@@ -147,6 +147,31 @@ def _series_rhs(spec):
             u, v = y.fields(2)
             return [a * laplace(u) + u - u.cube() - v + k_, (b * laplace(v) + u - v) / tau]
 
+    elif kind == _lib.TDX_IVP_BURGERS1D:
+        dx, nu_ = spec.params
+
+        def rhs(y):
+            def shifted(s, lo, hi):
+                return _PowerSeries(s.c[:, lo:hi])
+
+            n = y.c.shape[1]
+            mid, left, right = shifted(y, 1, n - 1), shifted(y, 0, n - 2), shifted(y, 2, n)
+            interior = -(mid * (mid - left)) / dx + nu_ * (right - 2.0 * mid + left) / (dx * dx)
+            x0, x1, xm = shifted(y, 0, 1), shifted(y, 1, 2), shifted(y, n - 2, n - 1)
+            boundary = -(x0 * (x0 - xm)) / dx + nu_ * (x1 - 2.0 * x0 + xm) / (dx * dx)
+            return [boundary, interior, boundary]
+
+    elif kind == _lib.TDX_IVP_WAVE1D:
+        dx, nu_ = spec.params
+
+        def rhs(y):
+            x, v = y.fields(2)
+            n = x.c.shape[1]
+            cut = lambda s, lo, hi: _PowerSeries(s.c[:, lo:hi])
+            interior = nu_ * (cut(x, 2, n) - 2.0 * cut(x, 1, n - 1) + cut(x, 0, n - 2)) / (dx * dx)
+            zero = _PowerSeries(torch.zeros_like(x.c[:, :1]))
+            return [zero, cut(v, 1, n - 1), zero, cut(x, 0, 1), interior, cut(x, n - 1, n)]
+
     else:
         raise NotImplementedError(f"no Taylor-mode rule for {spec.name}")
     return rhs

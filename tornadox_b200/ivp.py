@@ -1,7 +1,7 @@
 """Initial value problems whose right-hand sides are evaluated INSIDE the fused CUDA step kernels.
 
-Mirrors the factory functions of the reference (tornadox/ivp.py): ``vanderpol`` (:28-49),
-``brusselator`` (:219-265), ``lorenz96`` (:268-294), ``fhn_2d`` (:409-481).  Each returns an
+Mirrors the factory functions of the reference (tornadox/ivp.py): ``vanderpol`` (:28-49), ``burgers_1d`` (:76-107),
+``wave_1d`` (:110-140), ``brusselator`` (:219-265), ``lorenz96`` (:268-294), ``fhn_2d`` (:409-481).  Each returns an
 ``InitialValueProblem(f, t0, tmax, y0, df, df_diagonal)`` (:10-25); ``f`` and ``df_diagonal`` are callables
 on device tensors (they launch ``tdx_eval_f``) that additionally carry the ``KernelSpec`` the solvers
 dispatch on.  ``df`` (dense Jacobian) is ``None``: the O(d^2) dense solvers are out of scope.
@@ -90,6 +90,38 @@ def vanderpol(t0=0.0, tmax=30, y0=None, stiffness_constant=1e1):
     """Van der Pol oscillator, y' = [y2, mu (1 - y1^2) y2 - y1]  (ivp.py:28-49)."""
     y0 = np.array([2.0, 0.0]) if y0 is None else y0
     spec = KernelSpec(_lib.TDX_IVP_VANDERPOL, (float(stiffness_constant),), 1, 1, 2, "vanderpol")
+    return _problem(spec, t0, tmax, y0)
+
+
+def _mesh_1d(bbox, dx):
+    """``arange(bbox[0], bbox[1] + dx, step=dx)`` as in ivp.py:81, 115."""
+    if bbox is None:
+        bbox = [0.0, 1.0]
+    return np.arange(bbox[0], bbox[1] + dx, step=dx), bbox
+
+
+def burgers_1d(t0=0.0, tmax=10.0, y0=None, bbox=None, dx=0.02, diffusion_param=0.02):
+    """Viscous Burgers equation on a 1-d mesh, upwind convection, "cyclic" end points  (ivp.py:76-107)."""
+    mesh, bbox = _mesh_1d(bbox, dx)
+    if y0 is None:
+        y0 = np.exp(-500.0 * (mesh - (0.6 * (bbox[1] - bbox[0]))) ** 2)
+    n = int(np.shape(y0)[0])
+    if n < 3:
+        raise ValueError("burgers_1d needs at least 3 mesh points")
+    spec = KernelSpec(_lib.TDX_IVP_BURGERS1D, (float(dx), float(diffusion_param)), 1, n, 1, "burgers_1d")
+    return _problem(spec, t0, tmax, y0)
+
+
+def wave_1d(t0=0.0, tmax=20.0, y0=None, bbox=None, dx=0.02, diffusion_param=0.01):
+    """Wave equation as a first-order system y = [x; x'] on a 1-d mesh  (ivp.py:110-140)."""
+    mesh, bbox = _mesh_1d(bbox, dx)
+    if y0 is None:
+        x0 = np.exp(-70.0 * (mesh - (0.6 * (bbox[1] - bbox[0]))) ** 2)
+        y0 = np.concatenate((x0, np.zeros_like(x0)))
+    n = int(np.shape(y0)[0]) // 2
+    if n < 3 or 2 * n != int(np.shape(y0)[0]):
+        raise ValueError("wave_1d needs y0 = [x; x'] on at least 3 mesh points")
+    spec = KernelSpec(_lib.TDX_IVP_WAVE1D, (float(dx), float(diffusion_param)), 1, n, 2, "wave_1d")
     return _problem(spec, t0, tmax, y0)
 
 
