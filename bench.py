@@ -290,6 +290,7 @@ def run_mine(args):
         }
         if name == args.solver and not args.no_e2e:
             results[name]["e2e_resident"] = e2e_resident_solve(torch, sol, state, dt, problem, world, dev, d, args.steps)
+            results[name]["e2e_device_loop"] = e2e_device_loop(torch, sol, state, dt, problem, d, args.steps)
             torch.cuda.empty_cache()
             results[name]["e2e"] = e2e_host_buffers(torch, sol, state, dt, problem, world, dev, d, max(2, min(args.steps, 5)))
         del sol, state
@@ -323,6 +324,7 @@ def run_mine(args):
             "clocks": main["clocks"],
             "e2e": main.get("e2e"),
             "e2e_resident": main.get("e2e_resident"),
+            "e2e_device_loop": main.get("e2e_device_loop"),
             "gpu_launches": main["launches"],
             "roofline": main["roofline"],
             "cpu_baseline": cpu,
@@ -426,6 +428,38 @@ def e2e_resident_solve(torch, sol, state, dt, problem, world, dev, d, k):
     return {"value": d * attempts / sec, "unit": "state-dims*steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 8,
             "attempts": attempts, "accepted": k, "ms_per_attempt": sec / attempts * 1e3,
             "what": "public perform_full_step loop (adaptive accept/reject on the host), wall clock incl. the per-attempt sync"}
+
+
+def e2e_device_loop(torch, sol, state, dt, problem, d, k):
+    """k attempts of the adaptive solve under the device-resident step controller: dt, accept / reject and the buffer flip
+    are decided by the kernels; the host enqueues the batch and reads the controller block once at the end."""
+    from tornadox_b200 import ek1
+
+    eng = sol.engine
+    rule = eng.native_steprule(sol.steprule)
+    is_dek1 = isinstance(sol, ek1.DiagonalEK1)
+    pair_a = (state.y.mean, state.y.cov_sqrtm if is_dek1 else state.y.cov_sqrtm_2)
+    pair_b = (torch.empty_like(pair_a[0]), torch.empty_like(pair_a[1]))
+    err = torch.empty((), dtype=pair_a[0].dtype, device=pair_a[0].device)
+
+    def batch():
+        eng.ctl_begin(rule, state.t, dt, 1e300)          # no end time: every launch of the batch is a real attempt
+        if is_dek1:
+            eng.dek1_enqueue_attempts(k, pair_a, pair_b, None, None)
+        else:
+            eng.ek0_enqueue_attempts(k, pair_a, pair_b, err, None)
+        return eng.ctl_read()
+
+    batch()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    ctl = batch()
+    sec = time.perf_counter() - t0
+    attempts = max(1, int(ctl.attempts))
+    return {"value": d * attempts / sec, "unit": "state-dims*steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+            "attempts": attempts, "accepted": int(ctl.accepted), "ms_per_attempt": sec / attempts * 1e3,
+            "what": "adaptive attempts under the device-resident step controller (tdx_*_enqueue_attempts): wall clock per "
+                    "attempt incl. enqueueing the batch and one controller read; error vectors not materialised"}
 
 
 def main():

@@ -200,6 +200,31 @@ int tdx_ek0_full_step(tdx_ctx* ctx, const tdx_steprule* rule, double t, double d
                       const void* mean_in, const void* Cl_in, void* mean_out, void* Cl_out, void* err_out,
                       void* ref_out, tdx_full_step_result* result, void* stream);
 
+/* ---- device-resident step controller ----------------------------------------------------------------------------
+ * The same loop with NO host involvement between attempts: the step to attempt, its Nordsieck vectors, the time and
+ * the index of the current buffer pair live in a controller block in device memory.  Every launch of a batch reads them,
+ * its last CTA decides accept / reject from the (globally reduced) norm, proposes the next dt, flips the buffers on
+ * accept and stops the solve at tmax; launches enqueued after that return immediately.  The host enqueues k attempts
+ * blindly and looks at the controller once per batch.  State buffers: pair A holds the initial state, pair B is scratch;
+ * after tdx_ctl_read the current state is pair ``cur`` (0 = A, 1 = B).
+ *   tdx_ctl_begin             reset the controller: rule, t0, first dt, tmax (buffers: cur = A)
+ *   tdx_dek1_enqueue_attempts k DiagonalEK1 attempts (all vector fields)
+ *   tdx_ek0_enqueue_attempts  k KroneckerEK0 attempts (fhn_2d: the fused kernel; other fields: TDX_ERR_UNSUPPORTED)
+ *   tdx_ctl_read              synchronise ``stream`` and copy the controller's scalars (and, optionally, the ring of the
+ *                             last TDX_CTL_HISTORY accepted (t, dt) pairs, indexed by accepted-count % TDX_CTL_HISTORY) */
+#define TDX_CTL_HISTORY 256
+typedef struct {
+    double t, dt, last_norm;
+    int64_t attempts, accepted;
+    int32_t cur, done, failed, reserved;
+} tdx_ctl_state;
+int tdx_ctl_begin(tdx_ctx* ctx, const tdx_steprule* rule, double t0, double dt0, double tmax, void* stream);
+int tdx_dek1_enqueue_attempts(tdx_ctx* ctx, int k, uint32_t flags, void* mean_a, void* sc_a, void* mean_b, void* sc_b,
+                              void* err_out, void* ref_out, void* stream);
+int tdx_ek0_enqueue_attempts(tdx_ctx* ctx, int k, uint32_t flags, void* mean_a, void* Cl_a, void* mean_b, void* Cl_b,
+                             void* err_out, void* ref_out, void* stream);
+int tdx_ctl_read(tdx_ctx* ctx, tdx_ctl_state* out, double* hist_t, double* hist_dt, void* stream);
+
 /* ---- peer-memory exchange over NVLink (multi-GPU, one process per GPU on one node) -------------------------
  * No reference counterpart (the reference is single-device).  Instead of NCCL calls between the kernels, every
  * context owns a small device block (halo buffers, reduction slots, sequence-numbered flags) that its neighbours

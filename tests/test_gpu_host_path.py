@@ -109,3 +109,42 @@ def test_native_full_step_loop_equals_the_python_loop(cuda_device, solver_name, 
     assert info_c == info_py and len(ts_c) > 3
     np.testing.assert_allclose(ts_c, ts_py, rtol=1e-13, atol=0)
     assert torch.equal(fin_c.y.mean, fin_py.y.mean)
+
+
+@pytest.mark.parametrize("solver_name", ["ek0", "ek1", "dek0"])
+@pytest.mark.parametrize("kind,size,tmax", [("vanderpol", 1, 1.0), ("fhn_2d", 32, 2e-3), ("fhn_2d", 50, 1e-3), ("lorenz96", 300, 1.0),
+                                            ("brusselator", 200, 3e-3), ("burgers_1d", 101, 0.02)])
+@pytest.mark.parametrize("rule", ["adaptive", "constant"])
+def test_device_resident_controller_equals_the_host_loop(cuda_device, solver_name, kind, size, tmax, rule):
+    """simulate_final_state under the device-resident step controller (dt, accept / reject and the buffer flip decided by the
+    kernels' last CTA, the host only enqueues batches) against the host-driven loop: same number of steps and attempts,
+    same accepted times, same final state."""
+    from tornadox_b200 import ek0, ek1, step
+
+    _, p, _ = make_pair(kind, size, tmax=tmax) if kind == "vanderpol" else make_pair(kind, size)
+    p = p._replace(tmax=tmax)
+    cls = {"ek0": ek0.KroneckerEK0, "ek1": ek1.DiagonalEK1, "dek0": ek0.DiagonalEK0}[solver_name]
+
+    def make_rule(solver):
+        if rule == "adaptive":
+            return step.AdaptiveSteps()
+        return step.ConstantSteps(0.07 * tmax)
+
+    host = cls(num_derivatives=3, steprule=make_rule(None))
+    host.device_loop = False
+    fin_h, info_h = host.simulate_final_state(p)
+    dev = cls(num_derivatives=3, steprule=make_rule(None))
+    dev.device_loop_batch = 7                       # several batches, and a tail of launches after the solve is over
+    fin_d, info_d = dev.simulate_final_state(p)
+    uses_ctl = not (solver_name == "ek0" and kind != "fhn_2d")
+    assert dict(info_d) == dict(info_h), (info_d, info_h)
+    assert abs(fin_d.t - fin_h.t) <= 1e-12 * abs(fin_h.t)
+    # device pow() in the dt proposal is within an ulp or two of the host's: the trajectories agree to rounding, not bit for bit
+    assert_close(fin_d.y.mean.cpu().numpy(), fin_h.y.mean.cpu().numpy(), 1e-9, "final mean")
+    if uses_ctl:
+        st, ht, hd = dev.engine.ctl_read(history=True)
+        assert st.done == 1 and st.failed == 0 and st.accepted == info_h["num_steps"]
+        n_acc = int(st.accepted)
+        ts = ht[:n_acc] if n_acc <= len(ht) else None
+        if ts is not None:
+            assert abs(ts[-1] - fin_h.t) <= 1e-12 * abs(fin_h.t) and np.all(np.diff(ts) > 0)

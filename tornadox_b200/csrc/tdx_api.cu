@@ -110,8 +110,9 @@ static void prior_host(int nu, double* A, double* Ql) {
         }
 }
 
+// p[k] = |dt|^(nu-k+1/2) / (nu-k)!   (iwp.py:65-73) with libm's pow, as NumPy / the oracle evaluate it.  (The device-resident
+// step controller builds its vectors with nordsieck_vectors(): sqrt and products, a few ulp from these.)
 static void nordsieck_host(int nu, double dt, double* p, double* pinv) {
-    // p[k] = |dt|^(nu-k+1/2) / (nu-k)!   (iwp.py:65-73)
     const double adt = std::fabs(dt);
     for (int k = 0; k <= nu; ++k) {
         const int q = nu - k;
@@ -144,6 +145,9 @@ static int cuda_fail(int cuda_code, const char* where) {
 struct HostPipe;
 
 struct tdx_ctx {
+    StepCtl* ctl = nullptr;          // device-resident step controller block
+    StepCtl* ctl_host = nullptr;     // pinned staging copy
+    tdx_steprule ctl_rule{};
     double* host_norm = nullptr;     // mapped pinned: [0] reduced norm sum written by the kernel epilogue (full-step loop)
     double* host_norm_dev = nullptr; // its device alias
     double* zsq_scratch = nullptr;   // device scalar for the EK0 z^2 sum inside the full-step loop
@@ -239,6 +243,8 @@ int tdx_destroy(tdx_ctx* ctx) {
     int prev = 0;
     cudaGetDevice(&prev);
     cudaSetDevice(ctx->device);
+    if (ctx->ctl_host) cudaFreeHost(ctx->ctl_host);
+    cudaFree(ctx->ctl);
     if (ctx->host_norm) cudaFreeHost(ctx->host_norm);
     cudaFree(ctx->zsq_scratch);
     cudaFree(ctx->partials);
@@ -1134,4 +1140,134 @@ extern "C" int tdx_ek0_full_step(tdx_ctx* ctx, const tdx_steprule* rule, double 
                               return tdx_ek0_attempt_step(ctx, &a, mean_in, Cl_in, mean_out, Cl_out, err_out, ref_out,
                                                           ctx->zsq_scratch, ctx->host_norm_dev, stream);
                           });
+}
+
+
+// =====================================================================================================================
+// Device-resident step controller
+// =====================================================================================================================
+static_assert(TDX_CTL_HISTORY == kCtlHistory, "history ring size");
+
+extern "C" int tdx_ctl_begin(tdx_ctx* ctx, const tdx_steprule* rule, double t0, double dt0, double tmax, void* stream) {
+    int rc = check_ready(ctx, "tdx_ctl_begin");
+    if (rc) return rc;
+    if (!rule) return fail(TDX_ERR_INVALID, "tdx_ctl_begin: null step rule");
+    if (!(dt0 > 0.0) || !std::isfinite(dt0)) return fail(TDX_ERR_INVALID, "tdx_ctl_begin: Invalid step size: dt must be positive and finite");
+    DeviceGuard guard(ctx->device);
+    cudaError_t e = cudaSuccess;
+    if (!ctx->ctl) {
+        e = cudaMalloc((void**)&ctx->ctl, sizeof(StepCtl));
+        if (e == cudaSuccess) e = cudaMallocHost((void**)&ctx->ctl_host, sizeof(StepCtl));
+    }
+    if (e == cudaSuccess && (rc = ensure_host_norm(ctx))) return rc;
+    if (e != cudaSuccess) return cuda_fail((int)e, "tdx_ctl_begin");
+    StepCtl& c = *ctx->ctl_host;
+    std::memset(&c, 0, sizeof(c));
+    c.nu = ctx->n - 1;
+    nordsieck_host(c.nu, dt0, c.p, c.pinv);
+    c.t = t0; c.dt = dt0; c.tmax = tmax;
+    c.adaptive = rule->adaptive ? 1 : 0;
+    c.abstol = rule->abstol; c.reltol = rule->reltol; c.safety_scale = rule->safety_scale;
+    c.min_change = rule->min_change; c.max_change = rule->max_change; c.constant_dt = rule->constant_dt;
+    c.done = (t0 < tmax) ? 0 : 1;
+    ctx->ctl_rule = *rule;
+    e = cudaMemcpyAsync(ctx->ctl, ctx->ctl_host, sizeof(StepCtl), cudaMemcpyHostToDevice, (cudaStream_t)stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize((cudaStream_t)stream);     // the staging copy is reused by tdx_ctl_read
+    return e == cudaSuccess ? TDX_OK : cuda_fail((int)e, "tdx_ctl_begin");
+}
+
+static StepHost ctl_step_host(const tdx_ctx* ctx, uint32_t flags) {
+    StepHost h{};                                   // p, p_inv and dt come from the controller block
+    std::memcpy(h.ql, ctx->ql_packed, sizeof(h.ql));
+    const tdx_steprule& r = ctx->ctl_rule;
+    h.abstol = r.adaptive ? r.abstol : 0.0;
+    h.reltol = r.adaptive ? r.reltol : 0.0;
+    h.want_norm = (h.abstol != 0.0 || h.reltol != 0.0) ? 1 : 0;
+    h.flags = flags;
+    return h;
+}
+
+extern "C" int tdx_dek1_enqueue_attempts(tdx_ctx* ctx, int k, uint32_t flags, void* mean_a, void* sc_a, void* mean_b, void* sc_b,
+                                         void* err_out, void* ref_out, void* stream) {
+    int rc = check_ready(ctx, "tdx_dek1_enqueue_attempts");
+    if (rc) return rc;
+    if (!ctx->ctl) return fail(TDX_ERR_INVALID, "tdx_dek1_enqueue_attempts: call tdx_ctl_begin first");
+    if ((rc = check_full_step_flags(ctx, flags, "tdx_dek1_enqueue_attempts"))) return rc;
+    if (!mean_a || !sc_a || !mean_b || !sc_b || mean_a == mean_b || sc_a == sc_b)
+        return fail(TDX_ERR_INVALID, "tdx_dek1_enqueue_attempts: two distinct state buffer pairs are required");
+    if (k < 1) return fail(TDX_ERR_INVALID, "tdx_dek1_enqueue_attempts: k must be positive");
+    DeviceGuard guard(ctx->device);
+    const bool sharded = ctx->halo_lo > 0 || ctx->halo_hi > 0;
+    const uint32_t f = sharded ? flags : (flags & TDX_STEP_ZERO_JACOBIAN);
+    const double d_global = (double)ctx->geo.nf * (double)ctx->geo.grows * (double)ctx->geo.gcols;
+    void* mean_ab[2] = {mean_a, mean_b};
+    void* sc_ab[2] = {sc_a, sc_b};
+    for (int i = 0; i < k; ++i) {
+        if ((rc = comm_pack_begin(ctx, f, "tdx_dek1_enqueue_attempts"))) return rc;
+        const void* halo_lo = nullptr;
+        const void* halo_hi = nullptr;
+        resolve_halos(ctx, f, halo_lo, halo_hi);
+        StepHost h = ctl_step_host(ctx, f);
+        if ((rc = comm_reduce_begin(ctx, f, h.want_norm != 0, "tdx_dek1_enqueue_attempts"))) return rc;
+        ctx->launches += 1;
+        const int code = ctx->ops->dek1_ctl(ctx->geo, h, mean_ab, sc_ab, err_out, ref_out, halo_lo, halo_hi, make_ws(ctx, f), ctx->ctl,
+                                            d_global, ctx->host_norm_dev, (cudaStream_t)stream);
+        if (code == -3) return fail(TDX_ERR_UNSUPPORTED, "tdx_dek1_enqueue_attempts: shard too small for the fused halo delivery");
+        if ((rc = cuda_fail(code, "tdx_dek1_enqueue_attempts"))) return rc;
+    }
+    return TDX_OK;
+}
+
+extern "C" int tdx_ek0_enqueue_attempts(tdx_ctx* ctx, int k, uint32_t flags, void* mean_a, void* Cl_a, void* mean_b, void* Cl_b,
+                                        void* err_out, void* ref_out, void* stream) {
+    int rc = check_ready(ctx, "tdx_ek0_enqueue_attempts");
+    if (rc) return rc;
+    if (!ctx->ctl) return fail(TDX_ERR_INVALID, "tdx_ek0_enqueue_attempts: call tdx_ctl_begin first");
+    if (ctx->geo.kind != IVP_FHN2D)
+        return fail(TDX_ERR_UNSUPPORTED, "tdx_ek0_enqueue_attempts: only fhn_2d has the one-launch KroneckerEK0 kernel; use tdx_ek0_full_step");
+    if ((rc = check_full_step_flags(ctx, flags, "tdx_ek0_enqueue_attempts"))) return rc;
+    if (!mean_a || !Cl_a || !mean_b || !Cl_b || !err_out || mean_a == mean_b || Cl_a == Cl_b)
+        return fail(TDX_ERR_INVALID, "tdx_ek0_enqueue_attempts: two distinct state buffer pairs and err_out are required");
+    if (k < 1) return fail(TDX_ERR_INVALID, "tdx_ek0_enqueue_attempts: k must be positive");
+    DeviceGuard guard(ctx->device);
+    const bool sharded = ctx->halo_lo > 0 || ctx->halo_hi > 0;
+    const uint32_t f = sharded ? flags : 0u;
+    const double d_global = (double)ctx->geo.nf * (double)ctx->geo.grows * (double)ctx->geo.gcols;
+    void* mean_ab[2] = {mean_a, mean_b};
+    void* Cl_ab[2] = {Cl_a, Cl_b};
+    unsigned long long* mid_flag = reinterpret_cast<unsigned long long*>(static_cast<unsigned char*>(ctx->mid) + 128);
+    for (int i = 0; i < k; ++i) {
+        if ((rc = comm_pack_begin(ctx, f, "tdx_ek0_enqueue_attempts"))) return rc;
+        const void* halo_lo = nullptr;
+        const void* halo_hi = nullptr;
+        resolve_halos(ctx, f, halo_lo, halo_hi);
+        StepHost h = ctl_step_host(ctx, f);
+        if ((rc = comm_reduce_begin(ctx, f, true, "tdx_ek0_enqueue_attempts"))) return rc;
+        Workspace ws = make_ws(ctx, f);
+        if ((rc = comm_reduce_begin(ctx, f, h.want_norm != 0, "tdx_ek0_enqueue_attempts"))) return rc;
+        CommReduce reduce_b = ws.reduce;
+        reduce_b.seq = ctx->red_seq;
+        ctx->mid_seq += 1;
+        ctx->launches += 1;
+        const int code = ctx->ops->ek0_ctl(ctx->geo, h, mean_ab, Cl_ab, err_out, ref_out, halo_lo, halo_hi, ws, reduce_b, mid_flag,
+                                           ctx->mid_seq, ctx->ctl, d_global, ctx->zsq_scratch, ctx->host_norm_dev, (cudaStream_t)stream);
+        if (code == -3) return fail(TDX_ERR_UNSUPPORTED, "tdx_ek0_enqueue_attempts: shard too small for the fused halo delivery");
+        if ((rc = cuda_fail(code, "tdx_ek0_enqueue_attempts"))) return rc;
+    }
+    return TDX_OK;
+}
+
+extern "C" int tdx_ctl_read(tdx_ctx* ctx, tdx_ctl_state* out, double* hist_t, double* hist_dt, void* stream) {
+    if (!ctx || !ctx->ctl || !out) return fail(TDX_ERR_INVALID, "tdx_ctl_read: call tdx_ctl_begin first");
+    DeviceGuard guard(ctx->device);
+    cudaError_t e = cudaMemcpyAsync(ctx->ctl_host, ctx->ctl, sizeof(StepCtl), cudaMemcpyDeviceToHost, (cudaStream_t)stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize((cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail((int)e, "tdx_ctl_read");
+    const StepCtl& c = *ctx->ctl_host;
+    out->t = c.t; out->dt = c.dt; out->last_norm = c.last_norm;
+    out->attempts = c.attempts; out->accepted = c.accepted;
+    out->cur = c.cur; out->done = c.done; out->failed = c.failed; out->reserved = 0;
+    if (hist_t) std::memcpy(hist_t, c.hist_t, sizeof(c.hist_t));
+    if (hist_dt) std::memcpy(hist_dt, c.hist_dt, sizeof(c.hist_dt));
+    return TDX_OK;
 }

@@ -44,6 +44,76 @@ __device__ __forceinline__ T QL(const Consts<T, N>& c, int i, int j) {
     return c.ql[i * (i + 1) / 2 + j];
 }
 
+// Nordsieck preconditioner vectors  p[k] = |dt|^(nu-k+1/2) / (nu-k)!,  p_inv[k] = 1 / p[k]   (iwp.py:65-73).
+// Built from sqrt, multiplications and divisions only (used by the device-resident step controller; the host path
+// evaluates the same vectors with libm's pow like NumPy does -- the two agree to a few ulp).
+__host__ __device__ inline void nordsieck_vectors(int nu, double dt, double* p, double* pinv) {
+    const double adt = dt < 0.0 ? -dt : dt;
+    double pw = sqrt(adt), fact = 1.0;
+    for (int q = 0; q <= nu; ++q) {       // q = nu - k
+        if (q > 1) fact *= (double)q;
+        const int k = nu - q;
+        if (p) p[k] = pw / fact;
+        if (pinv) pinv[k] = fact / pw;
+        pw *= adt;
+    }
+}
+
+// Device-resident step controller (odefilter.py:171-223 + step.py:28-108 in device memory): the step kernels read the
+// step to attempt and which of the two state buffers is current from this block, and the last CTA of every attempt
+// decides accept / reject, proposes the next dt and flips the buffers.  The host enqueues attempts without reading anything
+// back and looks at the block once per batch.
+constexpr int kCtlHistory = 256;
+struct StepCtl {
+    double p[kMaxN], pinv[kMaxN];        // Nordsieck vectors of the step to attempt next
+    double t, dt, tmax;
+    double abstol, reltol, safety_scale, min_change, max_change, constant_dt;
+    int adaptive, nu;
+    int cur;                              // index of the buffer pair that holds the current state
+    int done;                             // t reached tmax (or the norm became NaN): further launches do nothing
+    int failed;                           // the error estimate became NaN
+    int pad_;
+    long long attempts, accepted;
+    double last_norm;
+    double hist_t[kCtlHistory];           // times of the accepted states, ring indexed by accepted % kCtlHistory
+    double hist_dt[kCtlHistory];          // the accepted steps
+};
+
+// after one attempt: ``sum`` = sum_i (dt err_i / tol_i)^2 over ALL ranks (ignored for ConstantSteps)
+__device__ inline void ctl_update(StepCtl* ctl, double sum, double d_global) {
+    const double t = ctl->t, dt = ctl->dt;
+    ctl->attempts += 1;
+    bool accepted = true;
+    double dt_next;
+    if (ctl->adaptive) {
+        const double norm = sqrt(sum / d_global);                                   // step.py:101-104
+        ctl->last_norm = norm;
+        if (norm != norm) {                                                          // odefilter.py:179-219 would spin forever
+            ctl->failed = 1;
+            ctl->done = 1;
+            return;
+        }
+        accepted = norm < 1.0;                                                       // step.py:90-91
+        double factor = ctl->safety_scale * pow(norm != 0.0 ? 1.0 / norm : INFINITY, 1.0 / (double)(ctl->nu + 1));   // step.py:80-88
+        factor = fmax(ctl->min_change, fmin(factor, ctl->max_change));
+        dt_next = fmin(factor * dt, ctl->tmax - (accepted ? t + dt : t));           // odefilter.py:214-219
+    } else {
+        dt_next = fmin(ctl->constant_dt, ctl->tmax - (t + dt));
+    }
+    if (accepted) {
+        const long long slot = ctl->accepted % kCtlHistory;
+        ctl->hist_t[slot] = t + dt;
+        ctl->hist_dt[slot] = dt;
+        ctl->accepted += 1;
+        ctl->t = t + dt;
+        ctl->cur ^= 1;
+        if (!(ctl->t < ctl->tmax)) ctl->done = 1;                                    // odefilter.py:111 ``while state.t < tmax``
+    }
+    if (!(dt_next > 0.0)) ctl->done = 1;
+    ctl->dt = dt_next;
+    nordsieck_vectors(ctl->nu, dt_next, ctl->p, ctl->pinv);
+}
+
 // A[i][j] = C(nu - i, nu - j) for j >= i: flip(lower Pascal), iwp.py:31-35 (unit upper triangular).
 __host__ __device__ constexpr double binom(int n, int k) {
     double r = 1.0;
@@ -617,9 +687,11 @@ __device__ __forceinline__ double warp_sum(double v) {
 
 // The final value is sum * mult * (*mult_sqrt_ptr)^2 (the last two default to 1).
 // With ``cr`` (world > 0) the last CTA then all-reduces the value over the ranks through peer memory.
-__device__ __forceinline__ void grid_sum(double v, double* s_red, double* partials, unsigned int* ticket,
+// Returns true in exactly one thread of the grid (thread 0 of the last CTA), after ``*out`` has been written; that thread
+// receives the final value in ``*final_value`` (the device-resident step controller runs there).
+__device__ __forceinline__ bool grid_sum(double v, double* s_red, double* partials, unsigned int* ticket,
                                          double* out, double mult = 1.0, const double* mult_sqrt_ptr = nullptr,
-                                         const CommReduce* cr = nullptr) {
+                                         const CommReduce* cr = nullptr, double* final_value = nullptr) {
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     v = warp_sum(v);
     if (lane == 0) s_red[w] = v;
@@ -657,10 +729,13 @@ __device__ __forceinline__ void grid_sum(double v, double* s_red, double* partia
             b = cta_allreduce(b, *cr, s_red);
         }
         if (threadIdx.x == 0) {
-            *out = b;
+            if (out) *out = b;
             *ticket = 0u;
+            if (final_value) *final_value = b;
+            return true;
         }
     }
+    return false;
 }
 
 }  // namespace tdx

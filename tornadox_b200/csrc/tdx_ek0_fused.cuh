@@ -73,6 +73,10 @@ struct Ek0FusedArgs {
     CommWait wait;
     CommReduce reduce_a, reduce_b;
     PackPeer<T> pack;
+    // device-resident step controller (kCtl instantiation)
+    StepCtl* ctl;
+    T* mean_ab[2];
+    T* Cl_ab[2];
 };
 
 struct StripGeom {
@@ -189,7 +193,7 @@ __device__ __forceinline__ StripGeom strip_geom(const Geo& g, unsigned strip, un
 }
 
 // Threads [0, W): consumers, thread t owns column c0 + t of both fields.  Threads [W, W + 32): the producer warp.
-template <typename T, int N, int W>
+template <typename T, int N, int W, bool kCtl = false>
 __global__ void __maxnreg__(TDX_EK0_MAXREG) ek0_fused_fhn_kernel(const __grid_constant__ Ek0FusedArgs<T, N> a) {
     using Cfg = Ek0FusedCfg<T, N, W>;
     using CSync = NamedSync<1, W>;                         // the consumers' barrier (the producer warp never joins)
@@ -202,8 +206,45 @@ __global__ void __maxnreg__(TDX_EK0_MAXREG) ek0_fused_fhn_kernel(const __grid_co
     T* s_stage = reinterpret_cast<T*>(smem_raw + Cfg::BAR_BYTES + Cfg::RED_BYTES + Cfg::at_bytes());
 
     const Geo& g = a.g;
-    const Consts<T, N>& c = a.c;
     const int tc = threadIdx.x;
+    const Consts<T, N>* cp = &a.c;
+    const Consts<double, N>* cdp = &a.cd;
+    const T* mean_in = a.mean_in;
+    T* mean_out = a.mean_out;
+    const T* Cl_in = a.Cl_in;
+    T* Cl_out = a.Cl_out;
+    if constexpr (kCtl) {
+        __shared__ Consts<T, N> s_c;
+        __shared__ Consts<double, N> s_cd;
+        __shared__ int s_cur;
+        if (tc == 0) {
+            const StepCtl* ctl = a.ctl;
+            Consts<T, N> cc = a.c;
+            Consts<double, N> ccd = a.cd;
+#pragma unroll
+            for (int k = 0; k < N; ++k) {
+                ccd.p[k] = ctl->p[k];
+                ccd.pinv[k] = ctl->pinv[k];
+                cc.p[k] = (T)ctl->p[k];
+                cc.pinv[k] = (T)ctl->pinv[k];
+            }
+            ccd.dt = ctl->dt;
+            cc.dt = (T)ctl->dt;
+            s_c = cc;
+            s_cd = ccd;
+            s_cur = ctl->done ? -1 : ctl->cur;
+        }
+        __syncthreads();
+        if (s_cur < 0) return;
+        cp = &s_c;
+        cdp = &s_cd;
+        mean_in = a.mean_ab[s_cur];
+        mean_out = a.mean_ab[s_cur ^ 1];
+        Cl_in = a.Cl_ab[s_cur];
+        Cl_out = a.Cl_ab[s_cur ^ 1];
+    }
+    const Consts<T, N>& c = *cp;
+    const Consts<double, N>& cdr = *cdp;
     const bool has_lo = a.halo_lo != nullptr, has_hi = a.halo_hi != nullptr;
     const bool hints = a.keep_frac < 1.0f;
     const int ns = (int)((a.total_strips - blockIdx.x + gridDim.x - 1) / gridDim.x);   // strips of this CTA
@@ -249,7 +290,7 @@ __global__ void __maxnreg__(TDX_EK0_MAXREG) ek0_fused_fhn_kernel(const __grid_co
                     if (round > 0) mbar_wait(empty + stage, (round - 1u) & 1u);     // the slot's previous row is consumed
                     if (rr < 0 || rr >= g.rows) continue;
                     T* dst = s_stage + (size_t)stage * Cfg::STAGE_ELEMS;
-                    const T* src = a.mean_in + (long long)rr * g.cols + gs;
+                    const T* src = mean_in + (long long)rr * g.cols + gs;
                     if (a.use_bulk) {
                         if (lane == 0) mbar_expect_tx(full + stage, 2u * N * bytes);
                         __syncwarp();
@@ -276,7 +317,7 @@ __global__ void __maxnreg__(TDX_EK0_MAXREG) ek0_fused_fhn_kernel(const __grid_co
     // ---- consumers ----------------------------------------------------------------------------------------------------
     CSync csync;
     // deliver this shard's edge rows to the neighbours before anything else (multi-GPU)
-    if (a.pack.enabled && blockIdx.x < 2 * kPackCtas) pack_halo_part<T, N>(g, c, a.mean_in, a.pack, (int)blockIdx.x, csync);
+    if (a.pack.enabled && blockIdx.x < 2 * kPackCtas) pack_halo_part<T, N>(g, c, mean_in, a.pack, (int)blockIdx.x, csync);
 
     // Column 1 of the predicted covariance without the diffusion term, M1 = (B B^T)[:, 1] with B = A (p_inv * Cl).
     // The gain K = Clp Clp^T H^T / S (ek0.py:136) only needs column 1 of Clp Clp^T = B B^T + sigma^2 Ql Ql^T, so once
@@ -284,13 +325,13 @@ __global__ void __maxnreg__(TDX_EK0_MAXREG) ek0_fused_fhn_kernel(const __grid_co
     // factor itself (ek0.py:175,138) is off the critical path (done by the first CTA to finish phase B).
     double* s_m1 = s_red + 16;
     if (tc == 0) {
-        const Consts<double, N>& cd = a.cd;
+        const Consts<double, N>& cd = cdr;
         double B[N][N];
 #pragma unroll
         for (int j = 0; j < N; ++j) {
             double colv[N];
 #pragma unroll
-            for (int kd = 0; kd < N; ++kd) colv[kd] = cd.pinv[kd] * (double)__ldg(a.Cl_in + kd * N + j);
+            for (int kd = 0; kd < N; ++kd) colv[kd] = cd.pinv[kd] * (double)__ldg(Cl_in + kd * N + j);
 #pragma unroll
             for (int i = 0; i < N; ++i) {
                 double accb = colv[i];
@@ -339,7 +380,7 @@ __global__ void __maxnreg__(TDX_EK0_MAXREG) ek0_fused_fhn_kernel(const __grid_co
             int rr = s.dir > 0 ? s.r0 - 1 : s.r1;
             T at_m1[2] = {}, at_m2[2] = {}, hs_m1[2] = {}, mp_m1[2][NK] = {};
             bool first_replicated = false;
-            T* out_ptr = a.mean_out + ((long long)(rr - s.dir) * g.cols + col);      // row being finalised, field 0
+            T* out_ptr = mean_out + ((long long)(rr - s.dir) * g.cols + col);      // row being finalised, field 0
             // the rows phase B writes last are the rows the NEXT attempt's phase A reads first -> keep those in L2
             const int keep_from = (kUpdate && hints) ? L - (int)ceilf(a.keep_frac * (float)(s.r1 - s.r0)) : L;
 #pragma unroll 1
@@ -433,7 +474,7 @@ __global__ void __maxnreg__(TDX_EK0_MAXREG) ek0_fused_fhn_kernel(const __grid_co
                             }
                             const T ref = tabs<T>(m0);
                             if (a.ref_out) {
-                                T* rp = a.ref_out + ((out_ptr - a.mean_out) + (long long)f * g.npts);
+                                T* rp = a.ref_out + ((out_ptr - mean_out) + (long long)f * g.npts);
                                 if (hints) st_global_hint(rp, ref, pol_stream);
                                 else *rp = ref;
                             }
@@ -504,7 +545,7 @@ __global__ void __maxnreg__(TDX_EK0_MAXREG) ek0_fused_fhn_kernel(const __grid_co
     const double z_sq_all = __ldcg(&a.mid->z_sq);
     double err_cal;
     {
-        const Consts<double, N>& cd = a.cd;
+        const Consts<double, N>& cd = cdr;
         const double p1 = cd.p[1];
         const double Q11 = QL(cd, 1, 0) * QL(cd, 1, 0) + QL(cd, 1, 1) * QL(cd, 1, 1);
         const double HQH = p1 * p1 * Q11;
@@ -527,7 +568,7 @@ __global__ void __maxnreg__(TDX_EK0_MAXREG) ek0_fused_fhn_kernel(const __grid_co
     const unsigned arrival = publish_partial(acc_b, s_red, a.partials + gridDim.x, a.ticket + 1, csync);
     if (arrival == 0u && tc == 0) {
         // the first CTA to finish has the most slack: it runs the stacked QR for the new factor  ek0.py:175,138
-        ek0_mid_compute<T, N>(a.cd, a.Cl_in, z_sq_all, a.d_global, a.Cl_out, a.err_out, a.mid);
+        ek0_mid_compute<T, N>(cdr, Cl_in, z_sq_all, a.d_global, Cl_out, a.err_out, a.mid);
     }
     if (arrival == gridDim.x - 1) {
         if (c.want_norm) {
@@ -541,6 +582,9 @@ __global__ void __maxnreg__(TDX_EK0_MAXREG) ek0_fused_fhn_kernel(const __grid_co
                 b = cta_allreduce(b, a.reduce_b, s_red, csync);
             }
             if (tc == 0) *a.out_sum = b;
+            if (kCtl && tc == 0) ctl_update(a.ctl, b, a.d_global);
+        } else if (kCtl && tc == 0) {
+            ctl_update(a.ctl, 0.0, a.d_global);
         }
         if (tc == 0) a.ticket[1] = 0u;
     }

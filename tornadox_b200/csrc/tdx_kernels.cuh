@@ -205,6 +205,11 @@ struct DekArgs {
     CommWait wait;                     // peer-memory halos: flags to wait for (null: nothing to wait for)
     CommReduce reduce;                 // fused all-reduce of the norm sum (world == 0: off)
     PackPeer<T> pack;                  // fused halo delivery (enabled == 0: off)
+    // device-resident step controller (kCtl instantiation): dt, Nordsieck vectors and the current buffer come from ``ctl``
+    StepCtl* ctl;
+    T* mean_ab[2];
+    T* sc_ab[2];
+    double d_global;
 };
 
 template <typename T, int N>
@@ -218,7 +223,9 @@ struct DekSmem {
 
 // kComm = false: single-GPU instantiation without any of the peer-memory code paths (halo delivery, flag waits,
 // fused all-reduce); the register allocation of this kernel sits at the 128-register cap and is sensitive to them.
-template <class IVP, typename T, int N, bool kComm>
+// kCtl = true: the step to attempt and the in / out buffers are read from the device-resident controller block, and the
+// last CTA updates it (accept / reject, next dt) -- no host involvement between attempts.
+template <class IVP, typename T, int N, bool kComm, bool kCtl = false>
 __global__ void __launch_bounds__(kThreads, TDX_MIN_BLOCKS) dek1_kernel(const __grid_constant__ DekArgs<T, N> a) {
     using Shape = typename IVP::Shape;
     using L = SmemLayout<T, N>;
@@ -232,8 +239,36 @@ __global__ void __launch_bounds__(kThreads, TDX_MIN_BLOCKS) dek1_kernel(const __
     constexpr size_t SC_STRIDE = L::sc_bytes() / sizeof(T);
 
     const Geo& g = a.g;
-    const Consts<T, N>& c = a.c;
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const Consts<T, N>* cp = &a.c;
+    const T* mean_in = a.mean_in;
+    const T* sc_in = a.sc_in;
+    T* mean_out = a.mean_out;
+    T* sc_out = a.sc_out;
+    if constexpr (kCtl) {
+        __shared__ Consts<T, N> s_c;
+        __shared__ int s_cur;
+        if (threadIdx.x == 0) {
+            const StepCtl* ctl = a.ctl;
+            Consts<T, N> cc = a.c;            // Ql, tolerances and flags come with the launch, the step with the controller
+#pragma unroll
+            for (int k = 0; k < N; ++k) {
+                cc.p[k] = (T)ctl->p[k];
+                cc.pinv[k] = (T)ctl->pinv[k];
+            }
+            cc.dt = (T)ctl->dt;
+            s_c = cc;
+            s_cur = ctl->done ? -1 : ctl->cur;
+        }
+        __syncthreads();
+        if (s_cur < 0) return;                // the solve is over: the remaining launches of the batch do nothing
+        cp = &s_c;
+        mean_in = a.mean_ab[s_cur];
+        sc_in = a.sc_ab[s_cur];
+        mean_out = a.mean_ab[s_cur ^ 1];
+        sc_out = a.sc_ab[s_cur ^ 1];
+    }
+    const Consts<T, N>& c = *cp;
 
     if (lane == 0) {
         mbar_init(bars + w, 1);
@@ -248,18 +283,18 @@ __global__ void __launch_bounds__(kThreads, TDX_MIN_BLOCKS) dek1_kernel(const __
     auto stage_in = [&](const Coord& co, int slot) -> bool {
         T* dst = s_sc0 + slot * SC_STRIDE + w * 32 * STRIDE;
         const long long off = co.seg_base * NN;
-        const bool bulk = (STRIDE == NN) && (co.seg_len == 32) && ((reinterpret_cast<uintptr_t>(a.sc_in + off) & 15) == 0);
+        const bool bulk = (STRIDE == NN) && (co.seg_len == 32) && ((reinterpret_cast<uintptr_t>(sc_in + off) & 15) == 0);
         if (bulk) {
             if (lane == 0) {
                 uint64_t* bar = bars + slot * kWarps + w;
                 mbar_expect_tx(bar, (uint32_t)(32 * NN * sizeof(T)));
-                bulk_g2s(dst, a.sc_in + off, (uint32_t)(32 * NN * sizeof(T)), bar);
+                bulk_g2s(dst, sc_in + off, (uint32_t)(32 * NN * sizeof(T)), bar);
             }
         } else {
             const int total = co.seg_len * NN;
             for (int e = lane; e < total; e += 32) {
                 const int blk = e / NN;
-                dst[blk * STRIDE + (e - blk * NN)] = __ldg(a.sc_in + off + e);
+                dst[blk * STRIDE + (e - blk * NN)] = __ldg(sc_in + off + e);
             }
         }
         return bulk;
@@ -268,7 +303,7 @@ __global__ void __launch_bounds__(kThreads, TDX_MIN_BLOCKS) dek1_kernel(const __
     // CTA b walks the virtual tiles (G-1-b), (G-1-b)+G, ...: the lowest block indices (scheduled first, always resident)
     // have the shortest lists when tiles % G != 0, and they deliver this shard's halos before they start on them
     if (kComm && a.pack.enabled && blockIdx.x < 2 * kPackCtas)
-        pack_halo_part<T, N>(g, c, a.mean_in, a.pack, (int)blockIdx.x);
+        pack_halo_part<T, N>(g, c, mean_in, a.pack, (int)blockIdx.x);
     bool halos_ready = false;          // CTA-uniform: the arrival flags have been seen
     unsigned tile = kComm ? (gridDim.x - 1u - blockIdx.x) : blockIdx.x;
     unsigned phase_bits = 0u;          // parity of each slot's mbarrier
@@ -290,7 +325,7 @@ __global__ void __launch_bounds__(kThreads, TDX_MIN_BLOCKS) dek1_kernel(const __
         T mp[N], fx, jac, raw0;
         {
             FrontRegs<IVP, T, N> fr;
-            front_load<IVP, T, N>(g, c, a.mean_in, a.halo_lo, a.halo_hi, cur, fr);
+            front_load<IVP, T, N>(g, c, mean_in, a.halo_lo, a.halo_hi, cur, fr);
             front_eval<IVP, T, N>(g, c, cur, fr, s_at, mp, fx, jac);
             raw0 = fr.raw[0];
         }
@@ -313,7 +348,7 @@ __global__ void __launch_bounds__(kThreads, TDX_MIN_BLOCKS) dek1_kernel(const __
 
         const long long sc_off = cur.seg_base * NN;
         const bool bulk_out = (STRIDE == NN) && (cur.seg_len == 32) &&
-                              ((reinterpret_cast<uintptr_t>(a.sc_out + sc_off) & 15) == 0);
+                              ((reinterpret_cast<uintptr_t>(sc_out + sc_off) & 15) == 0);
         if (cur.valid) {
             const T z = c.p[1] * mp[1] - fx;
 
@@ -353,7 +388,7 @@ __global__ void __launch_bounds__(kThreads, TDX_MIN_BLOCKS) dek1_kernel(const __
 
             // correct_cov_sqrtm / correct_mean  ek1.py:351-369, un-precondition ek1.py:246-247
             T new_m0 = (T)0;
-            T* mo_ptr = a.mean_out + cur.flat;
+            T* mo_ptr = mean_out + cur.flat;
 #pragma unroll
             for (int r = 0; r < N; ++r) {
                 const T l0 = B[r][0];
@@ -383,7 +418,7 @@ __global__ void __launch_bounds__(kThreads, TDX_MIN_BLOCKS) dek1_kernel(const __
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) {
-                bulk_s2g(a.sc_out + sc_off, my_sc, (uint32_t)(32 * NN * sizeof(T)));
+                bulk_s2g(sc_out + sc_off, my_sc, (uint32_t)(32 * NN * sizeof(T)));
                 bulk_commit();
             }
         } else {
@@ -391,14 +426,21 @@ __global__ void __launch_bounds__(kThreads, TDX_MIN_BLOCKS) dek1_kernel(const __
             const int total = cur.seg_len * NN;
             for (int e = lane; e < total; e += 32) {
                 const int b = e / NN;
-                a.sc_out[sc_off + e] = my_sc[b * STRIDE + (e - b * NN)];
+                sc_out[sc_off + e] = my_sc[b * STRIDE + (e - b * NN)];
             }
         }
         tile = next;
         cur_bulk = next_bulk;
     }
 
-    if (c.want_norm) grid_sum(ratio_sq_acc, s_red, a.partials, a.ticket, a.out_sum, 1.0, nullptr, kComm ? &a.reduce : nullptr);
+    if constexpr (kCtl) {
+        double total = 0.0;
+        const bool fin = grid_sum(ratio_sq_acc, s_red, a.partials, a.ticket, c.want_norm ? a.out_sum : nullptr, 1.0, nullptr,
+                                  (kComm && c.want_norm) ? &a.reduce : nullptr, &total);
+        if (fin) ctl_update(a.ctl, total, a.d_global);
+    } else {
+        if (c.want_norm) grid_sum(ratio_sq_acc, s_red, a.partials, a.ticket, a.out_sum, 1.0, nullptr, kComm ? &a.reduce : nullptr);
+    }
     if (lane == 0) bulk_wait_read0();
 }
 

@@ -60,6 +60,14 @@ struct Ops {
                    void* err_out, const Workspace&, cudaStream_t);
     int (*ek0_b)(const Geo&, const StepHost&, const void* mean_in, void* mean_out, void* ref_out, const void* halo_lo,
                  const void* halo_hi, const Workspace&, double* out_sum, cudaStream_t);
+    // the same attempts driven by the device-resident step controller: in/out = pair[ctl->cur] / pair[ctl->cur ^ 1]
+    int (*dek1_ctl)(const Geo&, const StepHost&, void* const mean_ab[2], void* const sc_ab[2], void* err_out, void* ref_out,
+                    const void* halo_lo, const void* halo_hi, const Workspace&, StepCtl* ctl, double d_global,
+                    double* out_sum, cudaStream_t);
+    int (*ek0_ctl)(const Geo&, const StepHost&, void* const mean_ab[2], void* const Cl_ab[2], void* err_out, void* ref_out,
+                   const void* halo_lo, const void* halo_hi, const Workspace&, const CommReduce& reduce_b,
+                   unsigned long long* mid_flag, unsigned long long mid_seq, StepCtl* ctl, double d_global, double* z_sq_out,
+                   double* out_sum, cudaStream_t);
     // whole KroneckerEK0 attempt in one cooperative launch (fhn_2d only; returns kNoFusedKernel otherwise)
     int (*ek0_fused)(const Geo&, const StepHost&, const void* mean_in, const void* Cl_in, void* mean_out, void* Cl_out,
                      void* err_out, void* ref_out, const void* halo_lo, const void* halo_hi, const Workspace&,
@@ -148,10 +156,31 @@ template <typename T, int N>
 struct Launch {
     using L = SmemLayout<T, N>;
 
+    static int dek1_ctl(const Geo& g, const StepHost& h, void* const mean_ab[2], void* const sc_ab[2], void* err_out,
+                        void* ref_out, const void* halo_lo, const void* halo_hi, const Workspace& ws, StepCtl* ctl,
+                        double d_global, double* out_sum, cudaStream_t st) {
+        return dek1_impl(g, h, nullptr, nullptr, nullptr, nullptr, err_out, ref_out, halo_lo, halo_hi, ws, out_sum, st, ctl,
+                         mean_ab, sc_ab, d_global);
+    }
+
     static int dek1(const Geo& g, const StepHost& h, const void* mean_in, const void* sc_in, void* mean_out,
                     void* sc_out, void* err_out, void* ref_out, const void* halo_lo, const void* halo_hi,
                     const Workspace& ws, double* out_sum, cudaStream_t st) {
+        return dek1_impl(g, h, mean_in, sc_in, mean_out, sc_out, err_out, ref_out, halo_lo, halo_hi, ws, out_sum, st, nullptr,
+                         nullptr, nullptr, 0.0);
+    }
+
+    static int dek1_impl(const Geo& g, const StepHost& h, const void* mean_in, const void* sc_in, void* mean_out,
+                         void* sc_out, void* err_out, void* ref_out, const void* halo_lo, const void* halo_hi,
+                         const Workspace& ws, double* out_sum, cudaStream_t st, StepCtl* ctl, void* const mean_ab[2],
+                         void* const sc_ab[2], double d_global) {
         DekArgs<T, N> a;
+        a.ctl = ctl;
+        a.d_global = d_global;
+        for (int i = 0; i < 2; ++i) {
+            a.mean_ab[i] = ctl ? (T*)mean_ab[i] : nullptr;
+            a.sc_ab[i] = ctl ? (T*)sc_ab[i] : nullptr;
+        }
         a.g = g;
         a.c = make_consts<T, N>(h);
         a.mean_in = (const T*)mean_in;
@@ -182,7 +211,13 @@ struct Launch {
             }
             a.pack = typed_pack(ws.pack);
             unsigned grid = 0;
-            if (comm) {
+            if (ctl) {
+                constexpr auto kern = dek1_kernel<IVP, T, N, true, true>;
+                TDX_CUDA_TRY(persistent_grid<kern>(smem, a.num_tiles, ws.reserve_ctas, grid));
+                if (a.pack.enabled && grid < 2u * kPackCtas)
+                    return -3;   // tiny sharded problems: the separate pack launch cannot follow the controller's buffers
+                kern<<<grid, kThreads, smem, st>>>(a);
+            } else if (comm) {
                 constexpr auto kern = dek1_kernel<IVP, T, N, true>;
                 TDX_CUDA_TRY(persistent_grid<kern>(smem, a.num_tiles, ws.reserve_ctas, grid));
                 if (a.pack.enabled && grid < 2u * kPackCtas) {   // tiny shard: deliver the halos with their own launch
@@ -253,16 +288,39 @@ struct Launch {
         return (int)cudaGetLastError();
     }
 
+    static int ek0_ctl(const Geo& g, const StepHost& h, void* const mean_ab[2], void* const Cl_ab[2], void* err_out,
+                       void* ref_out, const void* halo_lo, const void* halo_hi, const Workspace& ws,
+                       const CommReduce& reduce_b, unsigned long long* mid_flag, unsigned long long mid_seq, StepCtl* ctl,
+                       double d_global, double* z_sq_out, double* out_sum, cudaStream_t st) {
+        return ek0_fused_impl<true>(g, h, mean_ab[0], nullptr, nullptr, nullptr, err_out, ref_out, halo_lo, halo_hi, ws, reduce_b,
+                                    mid_flag, mid_seq, d_global, z_sq_out, out_sum, st, ctl, mean_ab, Cl_ab);
+    }
+
     static int ek0_fused(const Geo& g, const StepHost& h, const void* mean_in, const void* Cl_in, void* mean_out,
                          void* Cl_out, void* err_out, void* ref_out, const void* halo_lo, const void* halo_hi,
                          const Workspace& ws, const CommReduce& reduce_b, unsigned long long* mid_flag,
                          unsigned long long mid_seq, double d_global, double* z_sq_out, double* out_sum,
                          cudaStream_t st) {
+        return ek0_fused_impl<false>(g, h, mean_in, Cl_in, mean_out, Cl_out, err_out, ref_out, halo_lo, halo_hi, ws, reduce_b,
+                                     mid_flag, mid_seq, d_global, z_sq_out, out_sum, st, nullptr, nullptr, nullptr);
+    }
+
+    template <bool kCtl>
+    static int ek0_fused_impl(const Geo& g, const StepHost& h, const void* mean_in, const void* Cl_in, void* mean_out,
+                              void* Cl_out, void* err_out, void* ref_out, const void* halo_lo, const void* halo_hi,
+                              const Workspace& ws, const CommReduce& reduce_b, unsigned long long* mid_flag,
+                              unsigned long long mid_seq, double d_global, double* z_sq_out, double* out_sum,
+                              cudaStream_t st, StepCtl* ctl, void* const mean_ab[2], void* const Cl_ab[2]) {
         if (g.kind != IVP_FHN2D) return kNoFusedKernel;
         constexpr int W = TDX_EK0_W;
         using Cfg = Ek0FusedCfg<T, N, W>;
-        constexpr auto kern = ek0_fused_fhn_kernel<T, N, W>;
+        constexpr auto kern = ek0_fused_fhn_kernel<T, N, W, kCtl>;
         Ek0FusedArgs<T, N> a;
+        a.ctl = ctl;
+        for (int i = 0; i < 2; ++i) {
+            a.mean_ab[i] = ctl ? (T*)mean_ab[i] : nullptr;
+            a.Cl_ab[i] = ctl ? (T*)Cl_ab[i] : nullptr;
+        }
         a.g = g;
         a.c = make_consts<T, N>(h);
         a.cd = make_consts<double, N>(h);
@@ -304,6 +362,7 @@ struct Launch {
             a.keep_frac = (budget_mb <= 0.0) ? 2.0f : (float)(budget_mb / mean_mb);
         }
         if (a.pack.enabled && grid < 2u * kPackCtas) {   // tiny shard: deliver the halos with their own launch
+            if (kCtl) return -3;                          // ... which cannot follow the controller's buffers
             PackPeerArgs<T, N> pa;
             pa.g = g;
             pa.c = a.c;
@@ -392,6 +451,8 @@ struct Launch {
         o.ek0_mid = &ek0_mid;
         o.ek0_b = &ek0_b;
         o.ek0_fused = &ek0_fused;
+        o.dek1_ctl = &dek1_ctl;
+        o.ek0_ctl = &ek0_ctl;
         o.pack = &pack;
         o.pack_peer = &pack_peer;
         return o;

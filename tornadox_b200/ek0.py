@@ -78,6 +78,46 @@ class KroneckerEK0(odefilter.ODEFilter):
 
     perform_full_step_compiled = perform_full_step
 
+    def _device_loop_final_state(self, ivp):
+        """The whole solve under the device-resident step controller (``tdx_ek0_enqueue_attempts``; fhn_2d only)."""
+        state = self.initialize(*ivp)
+        eng = self.engine
+        rule = eng.native_steprule(self.steprule)
+        if (rule is None or state.y.mean.device.type != "cuda" or not eng.can_run_full_steps()
+                or eng.spec.kind != _lib.TDX_IVP_FHN2D):
+            return None
+        if not state.t < ivp.tmax:
+            return state, dict(num_f_evaluations=0, num_df_evaluations=0, num_df_diagonal_evaluations=0, num_steps=0,
+                               num_attempted_steps=0)
+        return self.run_device_loop(state, self.steprule.first_dt(*ivp), ivp.tmax)
+
+    def run_device_loop(self, state, dt0, tmax):
+        """Advance ``state`` to ``tmax`` under the device-resident step controller, starting with step ``dt0``; the input
+        state's buffers become one of the two buffer pairs.  Returns (final state, info)."""
+        eng = self.engine
+        rule = eng.native_steprule(self.steprule)
+        info = dict(num_f_evaluations=0, num_df_evaluations=0, num_df_diagonal_evaluations=0, num_steps=0,
+                    num_attempted_steps=0)
+        pair_a = (state.y.mean, state.y.cov_sqrtm_2)
+        pair_b = (torch.empty_like(pair_a[0]), torch.empty_like(pair_a[1]))
+        err = torch.empty((), dtype=self.dtype, device=pair_a[0].device)
+        ref = torch.empty(pair_a[0].shape[1], dtype=self.dtype, device=err.device) if self.materialize_reference_state else None
+        eng.ctl_begin(rule, state.t, dt0, tmax)
+        while True:
+            eng.ek0_enqueue_attempts(self.device_loop_batch, pair_a, pair_b, err, ref)
+            ctl = eng.ctl_read()
+            if ctl.failed:
+                raise FloatingPointError(f"error estimate is NaN at t={ctl.t}, dt={ctl.dt}")
+            if ctl.done:
+                break
+        mean, Cl = pair_b if ctl.cur else pair_a
+        final = odefilter.ODEFilterState(t=ctl.t, error_estimate=err,
+                                         reference_state=ref if ref is not None else odefilter.DeferredAbsRow(mean),
+                                         y=rv.LeftIsotropicMatrixNormal(mean, state.y.d, Cl))
+        n_att = int(ctl.attempts)
+        info.update(num_f_evaluations=n_att, num_steps=int(ctl.accepted), num_attempted_steps=n_att)
+        return final, info
+
 
 class DiagonalEK0(BatchedEK1):
     """ek0.py:196-280: block-diagonal EK0 = DiagonalEK1 with a zero Jacobian diagonal."""

@@ -117,6 +117,46 @@ class BatchedEK1(odefilter.ODEFilter):
 
     perform_full_step_compiled = perform_full_step
 
+    def _device_loop_final_state(self, ivp):
+        """The whole solve under the device-resident step controller (``tdx_dek1_enqueue_attempts``)."""
+        state = self.initialize(*ivp)
+        eng = self.engine
+        rule = eng.native_steprule(self.steprule)
+        if rule is None or state.y.mean.device.type != "cuda" or not eng.can_run_full_steps():
+            return None
+        if not state.t < ivp.tmax:
+            return state, dict(num_f_evaluations=0, num_df_evaluations=0, num_df_diagonal_evaluations=0, num_steps=0,
+                               num_attempted_steps=0)
+        return self.run_device_loop(state, self.steprule.first_dt(*ivp), ivp.tmax)
+
+    def run_device_loop(self, state, dt0, tmax):
+        """Advance ``state`` to ``tmax`` under the device-resident step controller, starting with step ``dt0``; the input
+        state's buffers become one of the two buffer pairs.  Returns (final state, info)."""
+        eng = self.engine
+        rule = eng.native_steprule(self.steprule)
+        info = dict(num_f_evaluations=0, num_df_evaluations=0, num_df_diagonal_evaluations=0, num_steps=0,
+                    num_attempted_steps=0)
+        pair_a = (state.y.mean, state.y.cov_sqrtm)
+        pair_b = (torch.empty_like(pair_a[0]), torch.empty_like(pair_a[1]))
+        d = pair_a[0].shape[1]
+        err = torch.empty(d, dtype=self.dtype, device=pair_a[0].device) if self.materialize_error_vectors else None
+        ref = torch.empty_like(err) if err is not None else None
+        eng.ctl_begin(rule, state.t, dt0, tmax)
+        while True:
+            eng.dek1_enqueue_attempts(self.device_loop_batch, pair_a, pair_b, err, ref, jacobian=self._uses_jacobian)
+            ctl = eng.ctl_read()
+            if ctl.failed:
+                raise FloatingPointError(f"error estimate is NaN at t={ctl.t}, dt={ctl.dt}")
+            if ctl.done:
+                break
+        mean, sc = pair_b if ctl.cur else pair_a
+        final = odefilter.ODEFilterState(t=ctl.t, y=rv.BatchedMultivariateNormal(mean, sc), error_estimate=err,
+                                         reference_state=ref)
+        n_att = int(ctl.attempts)
+        info.update(num_f_evaluations=n_att, num_df_diagonal_evaluations=n_att if self._uses_jacobian else 0,
+                    num_steps=int(ctl.accepted), num_attempted_steps=n_att)
+        return final, info
+
     def _attempt_step_host(self, state, dt, abstol, reltol):
         """``attempt_step`` for a state held in host memory (CPU tensors): chunked H2D | kernel | D2H pipeline inside the
         library.  The outputs live in two alternating sets of pinned buffers owned by the solver (allocating pinned memory

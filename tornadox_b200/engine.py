@@ -410,6 +410,30 @@ class StepEngine:
                                               _ptr(err), _ptr(ref), ctypes.byref(res), self._stream()))
         return mean_out, Cl_out, err, ref, res
 
+    # ---- device-resident step controller (no host involvement between attempts) -------------------------------------
+    def ctl_begin(self, rule, t0, dt0, tmax):
+        _lib.check(self.lib.tdx_ctl_begin(self.handle, ctypes.byref(rule), float(t0), float(dt0), float(tmax), self._stream()))
+
+    def ctl_read(self, history=False):
+        st = _lib.CtlState()
+        if history:
+            ht = np.zeros(_lib.TDX_CTL_HISTORY)
+            hd = np.zeros(_lib.TDX_CTL_HISTORY)
+            pd = ctypes.POINTER(ctypes.c_double)
+            _lib.check(self.lib.tdx_ctl_read(self.handle, ctypes.byref(st), ht.ctypes.data_as(pd), hd.ctypes.data_as(pd), self._stream()))
+            return st, ht, hd
+        _lib.check(self.lib.tdx_ctl_read(self.handle, ctypes.byref(st), None, None, self._stream()))
+        return st
+
+    def dek1_enqueue_attempts(self, k, pair_a, pair_b, err=None, ref=None, jacobian=True):
+        flags = self._full_step_flags(0 if jacobian else _lib.TDX_STEP_ZERO_JACOBIAN)
+        _lib.check(self.lib.tdx_dek1_enqueue_attempts(self.handle, int(k), flags, _ptr(pair_a[0]), _ptr(pair_a[1]), _ptr(pair_b[0]),
+                                                      _ptr(pair_b[1]), _ptr(err), _ptr(ref), self._stream()))
+
+    def ek0_enqueue_attempts(self, k, pair_a, pair_b, err, ref=None):
+        _lib.check(self.lib.tdx_ek0_enqueue_attempts(self.handle, int(k), self._full_step_flags(), _ptr(pair_a[0]), _ptr(pair_a[1]),
+                                                     _ptr(pair_b[0]), _ptr(pair_b[1]), _ptr(err), _ptr(ref), self._stream()))
+
     # ---- KroneckerEK0 -----------------------------------------------------------------------------
     def ek0_attempt(self, t, dt, mean, Cl, abstol=0.0, reltol=0.0, mean_out=None, want_ref=True):
         """One KroneckerEK0 attempt.  Returns (mean_out, Cl_out, err[device scalar], ref, sq_norm_sum)."""

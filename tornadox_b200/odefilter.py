@@ -100,8 +100,26 @@ class ODEFilter(ABC):
             info=info,
         )
 
+    #: attempts enqueued per look at the device-resident controller (``simulate_final_state`` fast path)
+    device_loop_batch = 64
+    #: set False to force the host-driven loop everywhere
+    device_loop = True
+
+    def _device_loop_final_state(self, ivp):
+        """Solvers with a device-resident step controller override this; None = not available for this configuration."""
+        return None
+
     def simulate_final_state(self, *args, **kwargs):
-        """Drain the generator, return the last (state, info) (odefilter.py:73-78)."""
+        """Drain the generator, return the last (state, info) (odefilter.py:73-78).
+
+        Nobody looks at the intermediate states here, so when the solver has a device-resident step controller the
+        whole solve runs without the host in the loop (batches of attempts, one look at the controller per batch)."""
+        ivp = args[0] if args else kwargs.get("ivp")
+        plain = len(args) <= 1 and not kwargs.get("stop_at") and not kwargs.get("progressbar")
+        if self.device_loop and plain and ivp is not None:
+            out = self._device_loop_final_state(ivp)
+            if out is not None:
+                return out
         state, info = None, None
         for state, info in self.solution_generator(*args, **kwargs):
             pass
