@@ -71,6 +71,32 @@ def main():
             fy = eng.eval_f(0.0, yv)
             e_f = np.max(np.abs(fy.cpu().numpy() - o.f(0.0, o.y0)[idx])) / np.max(np.abs(o.f(0.0, o.y0)))
             assert e_f < 1e-13, (kind, e_f)
+    # whole adaptive solves, sharded: the native accept / reject loop and the device-resident step controller must both
+    # reproduce the unsharded oracle's accepted-step count and final state on every rank
+    for kind, size, tmax in (("fhn_2d", 32, 2e-3), ("brusselator", 400, 3e-3), ("lorenz96", 600, 0.5)):
+        o, p, series_f = make_pair(kind, size)
+        o, p = o._replace(tmax=tmax), p._replace(tmax=tmax)
+        nu = 3
+        m0, c0 = odriver.taylor_init(series_f, o.y0, o.t0, nu)
+        for name in ("dek1", "ek0"):
+            if name == "dek1":
+                states, info, _ = odriver.solve_diagonal_ek1(o, nu, odriver.AdaptiveSteps(), m0, c0)
+                cls = ek1.DiagonalEK1
+            else:
+                states, info, _ = odriver.solve_kronecker_ek0(o, nu, odriver.AdaptiveSteps(), m0, c0)
+                cls = ek0.KroneckerEK0
+            for device_loop in (False, True):
+                sol = cls(num_derivatives=nu, steprule=step.AdaptiveSteps(), process_group=group)
+                sol.device_loop = device_loop
+                sol.device_loop_batch = 5
+                final, finfo = sol.simulate_final_state(p)
+                eng = sol.engine
+                idx = np.concatenate([np.arange(o.y0.shape[0])[s] for s in local_slices(eng.spec, eng.begin, eng.end)])
+                assert dict(finfo) == info, (kind, name, device_loop, finfo, info)
+                assert abs(final.t - states[-1].t) <= 1e-12 * abs(states[-1].t), (kind, name, device_loop)
+                e_fin = np.max(np.abs(final.y.mean.cpu().numpy() - states[-1].mean[:, idx])) / np.max(np.abs(states[-1].mean))
+                assert e_fin < 1e-8, (kind, name, device_loop, e_fin)
+                worst = max(worst, e_fin * 1e-2)
     t = torch.tensor([worst], device=dev, dtype=torch.float64)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     if rank == 0:

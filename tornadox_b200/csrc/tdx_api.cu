@@ -1212,7 +1212,6 @@ extern "C" int tdx_dek1_enqueue_attempts(tdx_ctx* ctx, int k, uint32_t flags, vo
         ctx->launches += 1;
         const int code = ctx->ops->dek1_ctl(ctx->geo, h, mean_ab, sc_ab, err_out, ref_out, halo_lo, halo_hi, make_ws(ctx, f), ctx->ctl,
                                             d_global, ctx->host_norm_dev, (cudaStream_t)stream);
-        if (code == -3) return fail(TDX_ERR_UNSUPPORTED, "tdx_dek1_enqueue_attempts: shard too small for the fused halo delivery");
         if ((rc = cuda_fail(code, "tdx_dek1_enqueue_attempts"))) return rc;
     }
     return TDX_OK;
@@ -1251,7 +1250,6 @@ extern "C" int tdx_ek0_enqueue_attempts(tdx_ctx* ctx, int k, uint32_t flags, voi
         ctx->launches += 1;
         const int code = ctx->ops->ek0_ctl(ctx->geo, h, mean_ab, Cl_ab, err_out, ref_out, halo_lo, halo_hi, ws, reduce_b, mid_flag,
                                            ctx->mid_seq, ctx->ctl, d_global, ctx->zsq_scratch, ctx->host_norm_dev, (cudaStream_t)stream);
-        if (code == -3) return fail(TDX_ERR_UNSUPPORTED, "tdx_ek0_enqueue_attempts: shard too small for the fused halo delivery");
         if ((rc = cuda_fail(code, "tdx_ek0_enqueue_attempts"))) return rc;
     }
     return TDX_OK;

@@ -317,7 +317,9 @@ __global__ void __maxnreg__(TDX_EK0_MAXREG) ek0_fused_fhn_kernel(const __grid_co
     // ---- consumers ----------------------------------------------------------------------------------------------------
     CSync csync;
     // deliver this shard's edge rows to the neighbours before anything else (multi-GPU)
-    if (a.pack.enabled && blockIdx.x < 2 * kPackCtas) pack_halo_part<T, N>(g, c, mean_in, a.pack, (int)blockIdx.x, csync);
+    if (a.pack.enabled)
+        for (int part = (int)blockIdx.x; part < 2 * kPackCtas; part += (int)gridDim.x)   // a small grid takes several parts per CTA
+            pack_halo_part<T, N>(g, c, mean_in, a.pack, part, csync);
 
     // Column 1 of the predicted covariance without the diffusion term, M1 = (B B^T)[:, 1] with B = A (p_inv * Cl).
     // The gain K = Clp Clp^T H^T / S (ek0.py:136) only needs column 1 of Clp Clp^T = B B^T + sigma^2 Ql Ql^T, so once

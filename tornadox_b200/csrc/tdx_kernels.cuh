@@ -302,8 +302,9 @@ __global__ void __launch_bounds__(kThreads, TDX_MIN_BLOCKS) dek1_kernel(const __
 
     // CTA b walks the virtual tiles (G-1-b), (G-1-b)+G, ...: the lowest block indices (scheduled first, always resident)
     // have the shortest lists when tiles % G != 0, and they deliver this shard's halos before they start on them
-    if (kComm && a.pack.enabled && blockIdx.x < 2 * kPackCtas)
-        pack_halo_part<T, N>(g, c, mean_in, a.pack, (int)blockIdx.x);
+    if (kComm && a.pack.enabled)
+        for (int part = (int)blockIdx.x; part < 2 * kPackCtas; part += (int)gridDim.x)   // a small grid takes several parts per CTA
+            pack_halo_part<T, N>(g, c, mean_in, a.pack, part);
     bool halos_ready = false;          // CTA-uniform: the arrival flags have been seen
     unsigned tile = kComm ? (gridDim.x - 1u - blockIdx.x) : blockIdx.x;
     unsigned phase_bits = 0u;          // parity of each slot's mbarrier
@@ -506,7 +507,9 @@ __global__ void __launch_bounds__(kThreads, 3) ek0_sweep_kernel(const __grid_con
         }
     };
 
-    if (a.pack.enabled && blockIdx.x < 2 * kPackCtas) pack_halo_part<T, N>(g, c, a.mean_in, a.pack, (int)blockIdx.x);
+    if (a.pack.enabled)
+        for (int part = (int)blockIdx.x; part < 2 * kPackCtas; part += (int)gridDim.x)
+            pack_halo_part<T, N>(g, c, a.mean_in, a.pack, part);
     unsigned i = gridDim.x - 1u - blockIdx.x;
     double acc = 0.0;
     Coord co{};

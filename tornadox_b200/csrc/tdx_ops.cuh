@@ -214,17 +214,10 @@ struct Launch {
             if (ctl) {
                 constexpr auto kern = dek1_kernel<IVP, T, N, true, true>;
                 TDX_CUDA_TRY(persistent_grid<kern>(smem, a.num_tiles, ws.reserve_ctas, grid));
-                if (a.pack.enabled && grid < 2u * kPackCtas)
-                    return -3;   // tiny sharded problems: the separate pack launch cannot follow the controller's buffers
                 kern<<<grid, kThreads, smem, st>>>(a);
             } else if (comm) {
                 constexpr auto kern = dek1_kernel<IVP, T, N, true>;
                 TDX_CUDA_TRY(persistent_grid<kern>(smem, a.num_tiles, ws.reserve_ctas, grid));
-                if (a.pack.enabled && grid < 2u * kPackCtas) {   // tiny shard: deliver the halos with their own launch
-                    const int rc = pack_peer(g, h, mean_in, ws.pack, st);
-                    if (rc) return rc;
-                    a.pack.enabled = 0;
-                }
                 kern<<<grid, kThreads, smem, st>>>(a);
             } else {
                 constexpr auto kern = dek1_kernel<IVP, T, N, false>;
@@ -274,15 +267,6 @@ struct Launch {
             TDX_CUDA_TRY(persistent_grid<kern>(smem, a.num_tiles, ws.reserve_ctas, grid));
             a.pack = typed_pack(ws.pack);
             if (kUpdate) a.pack.enabled = 0;
-            if (a.pack.enabled && grid < 2u * kPackCtas) {
-                PackPeerArgs<T, N> pa;
-                pa.g = g;
-                pa.c = a.c;
-                pa.mean_in = a.mean_in;
-                pa.pk = a.pack;
-                pack_halo_peer_kernel<T, N><<<2 * kPackCtas, 1024, 0, st>>>(pa);
-                a.pack.enabled = 0;
-            }
             kern<<<grid, kThreads, smem, st>>>(a);
         })
         return (int)cudaGetLastError();
@@ -360,16 +344,6 @@ struct Launch {
             static const double budget_mb = std::getenv("TDX_EK0_L2_KEEP_MB") ? std::atof(std::getenv("TDX_EK0_L2_KEEP_MB")) : 80.0;
             const double mean_mb = (double)g.d * N * sizeof(T) / 1.0e6;
             a.keep_frac = (budget_mb <= 0.0) ? 2.0f : (float)(budget_mb / mean_mb);
-        }
-        if (a.pack.enabled && grid < 2u * kPackCtas) {   // tiny shard: deliver the halos with their own launch
-            if (kCtl) return -3;                          // ... which cannot follow the controller's buffers
-            PackPeerArgs<T, N> pa;
-            pa.g = g;
-            pa.c = a.c;
-            pa.mean_in = a.mean_in;
-            pa.pk = a.pack;
-            pack_halo_peer_kernel<T, N><<<2 * kPackCtas, 1024, 0, st>>>(pa);
-            a.pack.enabled = 0;
         }
         void* params[] = {(void*)&a};
         TDX_CUDA_TRY(cudaLaunchCooperativeKernel((const void*)kern, dim3(grid), dim3(W + 32), params, Cfg::total(), st));
