@@ -224,6 +224,88 @@ def taylor_init(series_f, y0, t0, num_derivatives):
     return taylor_mode(series_f, y0, t0, num_derivatives), np.zeros((n, n))
 
 
+# ---------------------------------------------------------------------------------------------
+# Runge-Kutta initialisation                                         tornadox/init.py:109-315
+# ---------------------------------------------------------------------------------------------
+def stack_init(f, y0, t0, num_derivatives):
+    """``Stack(use_df=False)`` -- init.py:382-391: [y0, f(y0), 0, ...] with a diag(0, 0, 1e3, ...) factor."""
+    n = num_derivatives + 1
+    y0 = np.asarray(y0, dtype=float)
+    m = np.stack([y0, f(t0, y0)] + [np.zeros_like(y0)] * (n - 2))
+    return m, np.diag(np.array([0.0, 0.0] + [1e3] * (n - 2)))
+
+
+def rk_data(f, t0, dt, num_steps, y0, method="RK45"):
+    """init.py:128-144: SciPy's solve_ivp with tolerances so loose that it takes its own fixed steps, read at t_eval."""
+    import scipy.integrate
+
+    t_eval = np.arange(t0, t0 + num_steps * dt, dt)
+    sol = scipy.integrate.solve_ivp(fun=f, t_span=(min(t_eval), max(t_eval)), y0=y0, atol=1e12, rtol=1e12, t_eval=t_eval,
+                                    method=method)
+    return sol.t, sol.y.T
+
+
+def _rk_forward_step(y, sc, m, sq, p, pinv, phi):
+    """init.py:280-313."""
+    import scipy.linalg
+
+    m = pinv[:, None] * m
+    sc = pinv[:, None] * sc
+    m_pred = phi @ m
+    x = phi @ sc
+    sc_pred = prior.propagate_cholesky(x, sq)
+    cross = (x @ sc.T).T
+    sgain = scipy.linalg.cho_solve((sc_pred, True), cross.T).T
+    sc_pred_np = p[:, None] * sc_pred
+    h = sc_pred_np[0, :]
+    s = h @ h.T
+    kgain = (sc_pred @ h.T) / s
+    z = (p[:, None] * m_pred)[0]
+    m_loc = m_pred - kgain[:, None] * (z - y)[None, :]
+    sc_loc = sc_pred - kgain[:, None] * h[None, :]
+    return p[:, None] * m_loc, p[:, None] * sc_loc, m_pred, sc_pred, sgain, x
+
+
+def _smoother_step_sqrt(m, sc, m_fut, sc_fut, sgain, sq, mp, x):
+    """kalman.py:47-64."""
+    new_mean = m - sgain @ (mp - m_fut)
+    n = m.shape[0]
+    zeros = np.zeros((n, n))
+    M = np.block([[x.T, sc.T], [sq.T, zeros.T], [zeros.T, sc_fut.T @ sgain.T]])
+    R = np.linalg.qr(M, mode="r")
+    return new_mean, R[n:2 * n, n:].T
+
+
+def rk_init_improve(m, sc, t0, ts, ys):
+    """init.py:146-277: fit the stacked initial state to the RK points with a Kalman filter + RTS smoother (both in
+    square-root form, Nordsieck-preconditioned) over the n x n Kronecker factor."""
+    nu = m.shape[0] - 1
+    phi, sq = prior.transition_1d(nu), prior.diffusion_sqrt_1d(nu)
+    init = dict(m=m, sc=sc, m_pred=None, sgain=None, x=None, p=None, pinv=None)
+    states, carry, t_loc = [], init, t0
+    for t, y in zip(ts[1:], ys[1:]):
+        p, pinv = prior.nordsieck_raw(nu, t - t_loc)
+        mm, ss, m_pred, sc_pred, sgain, x = _rk_forward_step(y, carry["sc"], carry["m"], sq, p, pinv, phi)
+        carry = dict(m=mm, sc=ss, m_pred=m_pred, sgain=sgain, x=x, p=p, pinv=pinv)
+        states.append(carry)
+        t_loc = t
+    prev, m_fut, sc_fut = states[-1], states[-1]["m"], states[-1]["sc"]
+    for fs in list(reversed(states[:-1])) + [init]:
+        p, pinv = prev["p"], prev["pinv"]
+        mm, ss = _smoother_step_sqrt(pinv[:, None] * fs["m"], pinv[:, None] * fs["sc"], pinv[:, None] * m_fut,
+                                     pinv[:, None] * sc_fut, prev["sgain"], sq, prev["m_pred"], prev["x"])
+        m_fut, sc_fut = p[:, None] * mm, p[:, None] * ss
+        prev = fs
+    return m_fut, sc_fut
+
+
+def runge_kutta_init(f, y0, t0, num_derivatives, dt=0.01, method="RK45"):
+    """``RungeKutta(dt, method, use_df=False).__call__`` -- init.py:119-126."""
+    ts, ys = rk_data(f, t0, dt, num_derivatives + 1, np.asarray(y0, dtype=float), method)
+    m, sc = stack_init(f, y0, t0, num_derivatives)
+    return rk_init_improve(m, sc, t0, ts, ys)
+
+
 # Series versions of the in-scope vector fields (same arithmetic as oracle.ref_np.problems).
 
 

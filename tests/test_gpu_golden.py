@@ -41,6 +41,51 @@ def test_taylor_mode_init(cuda_device, name, nu):
 
 @pytest.mark.parametrize("name", NAMES)
 @pytest.mark.parametrize("nu", [2, 3, 4])
+def test_runge_kutta_init(cuda_device, name, nu):
+    """init.RungeKutta(use_df=False) (init.py:109-315) against the reference's own output; and a solve started from it."""
+    from tornadox_b200 import ek0, init, step
+
+    import torch
+
+    from helpers import oracle_problem
+    from oracle.ref_np import driver as odriver
+
+    p = product_problem(name)
+    o, _ = oracle_problem(name)
+    dt = 0.01 if name not in ("fhn_2d", "brusselator") else 1e-3
+    rk = init.RungeKutta(dt=dt, method="RK45", use_df=False)
+    g = golden()
+    # (1) the filter + smoother on the SAME Runge-Kutta points the reference saw: tight
+    ts, ys = odriver.rk_data(o.f, o.t0, dt, nu + 1, o.y0)
+    m_stack, sc_stack = init.Stack(use_df=False)(f=p.f, df=None, y0=p.y0, t0=p.t0, num_derivatives=nu)
+    m, sc = init.RungeKutta.rk_init_improve(m_stack, sc_stack, p.t0, ts, torch.as_tensor(ys, device=m_stack.device))
+    assert m.is_cuda and sc.is_cuda
+    # fitting nu derivatives to points dt apart amplifies rounding by ~dt^-nu: the golden file carries the change of the
+    # reference's own output under a 1-ulp perturbation of the RK points, row by row (helpers.assert_close)
+    ref_m, noise_m = g[f"init/{name}/nu{nu}/rk_mean"], g[f"init/{name}/nu{nu}/rk_noise_mean"]
+    for r in range(nu + 1):
+        assert_close(_np(m)[r], ref_m[r], 1e-12, f"RK-initialised mean row {r} (same RK data)", noise=noise_m[r])
+    assert_close(_np(sc), g[f"init/{name}/nu{nu}/rk_cov_sqrtm"], 1e-10, "RK-initialised factor (same RK data)",
+                 noise=g[f"init/{name}/nu{nu}/rk_noise_cov_sqrtm"])
+    # (2) end to end, with SciPy's RK45 driven by the in-kernel vector field.  solve_ivp picks its first step through
+    # thresholds on |f| differences (select_initial_step), so rounding-level differences in f can change its step sequence
+    # and the dense-output values by the method's truncation error, which the fit then amplifies by ~dt^-nu: only the rows
+    # the fit pins exactly (y0 and f(y0), zero prior variance) and the low-order case are comparable end to end
+    m2, sc2 = rk(f=p.f, df=None, y0=p.y0, t0=p.t0, num_derivatives=nu)
+    assert bool(m2.isfinite().all()) and bool(sc2.isfinite().all())
+    assert_close(_np(m2)[:2], ref_m[:2], 1e-12, "RK-initialised mean rows 0, 1")
+    assert_close(_np(sc2), g[f"init/{name}/nu{nu}/rk_cov_sqrtm"], 1e-8, "RK-initialised factor")
+    if nu == 2 and dt == 0.01:
+        assert_close(_np(m2), ref_m, 1e-5, "RK-initialised mean")
+    if nu == 3:
+        sol = ek0.KroneckerEK0(num_derivatives=nu, steprule=step.AdaptiveSteps(), initialization=rk)
+        state = sol.initialize(*p)
+        new, _ = sol.attempt_step(state, 1e-3, *p)
+        assert bool(new.y.mean.isfinite().all())
+
+
+@pytest.mark.parametrize("name", NAMES)
+@pytest.mark.parametrize("nu", [2, 3, 4])
 @pytest.mark.parametrize("solver", ["dek1", "ek0", "dek0"])
 def test_attempt_step_sequences(cuda_device, name, nu, solver):
     from tornadox_b200 import ek0, ek1, odefilter, rv, step

@@ -5,11 +5,14 @@
   through a truncated power-series algebra on device tensors.
 * ``Stack``       (init.py:359-391): [y0, f(y0), 0, ...] with a diag(0, 0, 1e3, ...) factor
   (``use_df=False`` only -- the dense ``df @ f`` variant is O(d^2) and out of scope).
+* ``RungeKutta``  (init.py:109-315, ``use_df=False``): SciPy RK45 points fitted by a square-root Kalman filter + RTS smoother
+  over the (n, n) Kronecker factor; the d-wide mean rows stay on the device, the n x n algebra runs in NumPy.
 """
 
 import abc
 import math
 
+import numpy as np
 import torch
 
 from . import _lib
@@ -222,3 +225,98 @@ class Stack(InitializationRoutine):
 
     def __repr__(self):
         return f"{self.__class__.__name__}(use_df=False)"
+
+
+class RungeKutta(InitializationRoutine):
+    """Fit the stacked initial state to a few Runge-Kutta steps (init.py:109-315; ``use_df=False`` only).
+
+    The filter / smoother of the reference acts on the Kronecker structure: an (n, n) factor shared by all coordinates and
+    an (n, d) mean.  Here the factor algebra (QR, Cholesky solves) runs in NumPy on the host exactly as in the reference,
+    and every d-wide operation is a torch expression on the device.  The RK points come from
+    ``scipy.integrate.solve_ivp`` (init.py:128-144) with the vector field evaluated by the CUDA library.
+    """
+
+    def __init__(self, dt=0.01, method="RK45", use_df=False):
+        self.dt = dt
+        self.method = method
+        self.stack_initvals = Stack(use_df=use_df)
+
+    def __repr__(self):
+        return f"{self.__class__.__name__}(dt={self.dt}, method={self.method})"
+
+    def __call__(self, f, df, y0, t0, num_derivatives):
+        y0 = as_device_tensor(y0).reshape(-1)
+        ts, ys = self.rk_data(f=f, t0=t0, dt=self.dt, num_steps=num_derivatives + 1, y0=y0, method=self.method)
+        m, sc = self.stack_initvals(f=f, df=df, y0=y0, t0=t0, num_derivatives=num_derivatives)
+        return RungeKutta.rk_init_improve(m=m, sc=sc, t0=t0, ts=ts, ys=ys)
+
+    @staticmethod
+    def rk_data(f, t0, dt, num_steps, y0, method):
+        """init.py:128-144: fixed steps forced through t_eval, tolerances of 1e12."""
+        import scipy.integrate
+
+        y0 = as_device_tensor(y0).reshape(-1)
+        t_eval = np.arange(t0, t0 + num_steps * dt, dt)
+
+        def fun(t, y):
+            return f(t, torch.as_tensor(y, dtype=y0.dtype, device=y0.device)).cpu().numpy()
+
+        sol = scipy.integrate.solve_ivp(fun=fun, t_span=(min(t_eval), max(t_eval)), y0=y0.cpu().numpy(), atol=1e12, rtol=1e12,
+                                        t_eval=t_eval, method=method)
+        return sol.t, torch.as_tensor(sol.y.T.copy(), dtype=y0.dtype, device=y0.device)
+
+    @staticmethod
+    def _factor_step(sc, phi, sq, p, pinv):
+        """The (n, n) part of init.py:280-313 in NumPy: returns (sc_new, sc_pred-free quantities the mean update needs)."""
+        import scipy.linalg
+
+        sc = pinv[:, None] * sc
+        x = phi @ sc
+        stacked = np.vstack((x.T, sq.T))
+        sc_pred = np.linalg.qr(stacked, mode="r").T                 # sqrt.propagate_cholesky_factor
+        cross = (x @ sc.T).T
+        sgain = scipy.linalg.cho_solve((sc_pred, True), cross.T).T
+        h = (p[:, None] * sc_pred)[0, :]
+        kgain = (sc_pred @ h.T) / (h @ h.T)
+        sc_loc = sc_pred - kgain[:, None] * h[None, :]
+        return p[:, None] * sc_loc, sgain, x, kgain
+
+    @staticmethod
+    def rk_init_improve(m, sc, t0, ts, ys):
+        """init.py:146-277."""
+        nu = m.shape[0] - 1
+        dev, dtype = m.device, m.dtype
+        A, _ = _lib.prior(nu)
+        phi, sq = np.asarray(A), _lib.lapack_diffusion_sqrt(nu)
+        on_dev = lambda a: torch.as_tensor(np.ascontiguousarray(a), dtype=dtype, device=dev)
+        sc = np.asarray(sc.detach().cpu().numpy() if isinstance(sc, torch.Tensor) else sc, dtype=float)
+
+        init = dict(m=m, sc=sc, m_pred=None, sgain=None, x=None, p=None, pinv=None)
+        states, carry, t_loc = [], init, t0
+        for t, y in zip(ts[1:], ys[1:]):
+            p, pinv = _lib.nordsieck(nu, float(t - t_loc))
+            sc_new, sgain, x, kgain = RungeKutta._factor_step(carry["sc"], phi, sq, p, pinv)
+            m_pred = on_dev(phi) @ (on_dev(pinv)[:, None] * carry["m"])                       # (n, d) on the device
+            z = on_dev(p)[0] * m_pred[0]
+            m_new = on_dev(p)[:, None] * (m_pred - on_dev(kgain)[:, None] * (z - y)[None, :])
+            carry = dict(m=m_new, sc=sc_new, m_pred=m_pred, sgain=sgain, x=x, p=p, pinv=pinv)
+            states.append(carry)
+            t_loc = t
+        if not states:
+            return m, on_dev(sc)
+
+        prev, m_fut, sc_fut = states[-1], states[-1]["m"], states[-1]["sc"]
+        n = nu + 1
+        zeros = np.zeros((n, n))
+        for fs in list(reversed(states[:-1])) + [init]:
+            p, pinv = prev["p"], prev["pinv"]
+            sgain = prev["sgain"]
+            # kalman.smoother_step_sqrt (kalman.py:47-64) in the preconditioned coordinates of the LATER step
+            m_s = on_dev(pinv)[:, None] * fs["m"]
+            new_mean = m_s - on_dev(sgain) @ (prev["m_pred"] - on_dev(pinv)[:, None] * m_fut)
+            M = np.block([[prev["x"].T, (pinv[:, None] * fs["sc"]).T], [sq.T, zeros.T],
+                          [zeros.T, (pinv[:, None] * sc_fut).T @ sgain.T]])
+            new_sc = np.linalg.qr(M, mode="r")[n:2 * n, n:].T
+            m_fut, sc_fut = on_dev(p)[:, None] * new_mean, p[:, None] * new_sc
+            prev = fs
+        return m_fut, on_dev(sc_fut)
