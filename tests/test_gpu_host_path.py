@@ -148,3 +148,20 @@ def test_device_resident_controller_equals_the_host_loop(cuda_device, solver_nam
         ts = ht[:n_acc] if n_acc <= len(ht) else None
         if ts is not None:
             assert abs(ts[-1] - fin_h.t) <= 1e-12 * abs(fin_h.t) and np.all(np.diff(ts) > 0)
+
+
+def test_solve_offload_streams_states_to_the_host(cuda_device):
+    """solve(offload=True): accepted states are copied to pinned host memory as they are produced; same values as on the device."""
+    from tornadox_b200 import ek0, ek1, step
+
+    _, p, _ = make_pair("fhn_2d", 32)
+    p = p._replace(tmax=1e-3)
+    for cls in (ek1.DiagonalEK1, ek0.KroneckerEK0):
+        dev = cls(num_derivatives=3, steprule=step.AdaptiveSteps()).solve(p)
+        host = cls(num_derivatives=3, steprule=step.AdaptiveSteps()).solve(p, offload=True)
+        assert host.mean.device.type == "cpu" and host.cov_sqrtm.device.type == "cpu"
+        assert torch.equal(host.t, dev.t) and torch.equal(host.mean, dev.mean.cpu()) and torch.equal(host.cov_sqrtm, dev.cov_sqrtm.cpu())
+        assert host.info == dev.info
+    # KroneckerEK0 on a problem too large for the dense kron(I_d, C): the (n, n) factors are stored instead
+    sol = ek0.KroneckerEK0(num_derivatives=3, steprule=step.AdaptiveSteps()).solve(p)
+    assert sol.cov_sqrtm.shape[1:] == (4, 4)

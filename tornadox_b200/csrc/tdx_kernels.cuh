@@ -344,6 +344,10 @@ __global__ void __launch_bounds__(kThreads, TDX_MIN_BLOCKS) dek1_kernel(const __
         if (cur_bulk) {
             mbar_wait(bars + slot * kWarps + w, (phase_bits >> slot) & 1u);
             phase_bits ^= (1u << slot);
+        } else if (next < a.num_tiles && !next_bulk) {
+            cp_async_wait_group<1>();  // everything but the next tile's group, which was committed just above
+        } else {
+            cp_async_wait_group<0>();
         }
         __syncwarp();
 

@@ -81,18 +81,41 @@ class ODEFilter(ABC):
         )
 
     # ---- user-facing drivers ----------------------------------------------------------------------
-    def solve(self, *args, **kwargs):
-        """Collect every accepted state (odefilter.py:51-71)."""
+    #: ``solve`` materialises KroneckerEK0's dense kron(I_d, C) factor per state (as the reference does) only while it
+    #: stays below this many entries; beyond that the (n, n) factor itself is stored per state
+    dense_output_limit = 1 << 22
+
+    def solve(self, *args, offload=False, **kwargs):
+        """Collect every accepted state (odefilter.py:51-71).
+
+        ``offload=True`` streams the accepted states to pinned host memory as they are produced (asynchronous device-to-host
+        copies behind the step kernels), so that a long solve of a large problem does not have to fit on the GPU; the
+        returned tensors then live on the CPU.  For KroneckerEK0 the reference stacks the dense ``kron(I_d, C)`` factor of
+        every state (O(d^2 n^2) each); here that happens only for small problems (``dense_output_limit``), otherwise
+        ``cov_sqrtm`` holds the (n, n) factors."""
         from . import ek0
+
+        def keep(x):
+            if not offload or not isinstance(x, torch.Tensor) or x.device.type == "cpu":
+                return x
+            host = torch.empty(x.shape, dtype=x.dtype, pin_memory=True)
+            host.copy_(x, non_blocking=True)
+            return host
 
         times, means, cov_sqrtms, info = [], [], [], dict()
         for state, info in self.solution_generator(*args, **kwargs):
             times.append(float(state.t))
-            means.append(state.y.mean)
+            means.append(keep(state.y.mean))
             if isinstance(self, ek0.KroneckerEK0):
-                cov_sqrtms.append(state.y.dense_cov_sqrtm())   # O(d^2 n^2): small problems only, as upstream
+                n, d = state.y.mean.shape
+                if (n * d) ** 2 <= self.dense_output_limit:
+                    cov_sqrtms.append(keep(state.y.dense_cov_sqrtm()))   # as upstream: small problems only
+                else:
+                    cov_sqrtms.append(keep(state.y.cov_sqrtm_2))
             else:
-                cov_sqrtms.append(state.y.cov_sqrtm)
+                cov_sqrtms.append(keep(state.y.cov_sqrtm))
+        if offload and torch.cuda.is_available():
+            torch.cuda.synchronize()
         return ODESolution(
             t=torch.tensor(times, dtype=torch.float64),
             mean=torch.stack(means),
