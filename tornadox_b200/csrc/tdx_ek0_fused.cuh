@@ -534,8 +534,12 @@ __global__ void __maxnreg__(TDX_EK0_MAXREG) ek0_fused_fhn_kernel(const __grid_co
     }
     if (tc == 0) {
         const unsigned long long t0 = global_timer_ns();
+        s_red[30] = 0.0;
         while (ld_acquire_gpu(a.mid_flag) < a.mid_seq) {
-            if (global_timer_ns() - t0 > 4000000000ull) break;   // a dead peer must not hang the GPU
+            if (global_timer_ns() - t0 > 4000000000ull) {        // a dead peer must not hang the GPU ...
+                s_red[30] = 1.0;                                 // ... and must not go unnoticed: poison the attempt
+                break;
+            }
             __nanosleep(64);
         }
     }
@@ -544,7 +548,7 @@ __global__ void __maxnreg__(TDX_EK0_MAXREG) ek0_fused_fhn_kernel(const __grid_co
     if (tc == 0) stamps[2] = (double)global_timer_ns();
 #endif
     // calibration (ek0.py:123-130) and gain (ek0.py:132-136), redundantly in every thread
-    const double z_sq_all = __ldcg(&a.mid->z_sq);
+    const double z_sq_all = (s_red[30] != 0.0) ? nan("") : __ldcg(&a.mid->z_sq);   // timed out: NaN state, NaN norm, the host raises
     double err_cal;
     {
         const Consts<double, N>& cd = cdr;
