@@ -318,7 +318,9 @@ def run_mine(args):
                 "workload": f"ivp.fhn_2d {side}x{side} grid (d={d}), "
                             f"{'ek1.DiagonalEK1' if args.solver == 'dek1' else 'ek0.KroneckerEK0'}(num_derivatives=4) "
                             "attempt_step, y0 ~ U[0,1) seed 2, TaylorMode init, AdaptiveSteps tolerances fused",
-                "solver": args.solver, "sharding": f"grid rows over {world} GPU(s), NCCL halo + scalar all-reduce",
+                "solver": args.solver,
+                "sharding": f"grid rows over {world} GPU(s); halo rows and scalar all-reduce through NVLink peer memory "
+                            "inside the step kernel (torch.distributed/NCCL only for rendezvous)",
                 "l2": "state (mean+factors) is 2.0 GB per attempt for DiagonalEK1 / 0.34 GB for KroneckerEK0, larger than the 126 MB L2; no flush needed",
             },
             "clocks": main["clocks"],
