@@ -215,9 +215,12 @@ struct DekArgs {
 template <typename T, int N>
 struct DekSmem {
     using L = SmemLayout<T, N>;
-    static constexpr int SLOTS = 2;
+    static constexpr int SLOTS = 2;           // stencil tiles: always double-buffered (small)
+    // factor blocks: double-buffered while two CTAs per SM still fit (n <= 5 in fp64); beyond that ONE slot per warp keeps
+    // two CTAs resident (their phases interleave) instead of one CTA with a prefetch slot (2.6x slower at n = 6)
+    static constexpr int SC_SLOTS = (2 * (L::BAR_BYTES + L::RED_BYTES + 2 * 4096 + 2 * L::sc_bytes()) <= 225 * 1024) ? 2 : 1;
     __host__ __device__ static constexpr size_t total(int at_elems) {
-        return L::BAR_BYTES + L::RED_BYTES + SLOTS * L::at_bytes(at_elems) + SLOTS * L::sc_bytes();
+        return L::BAR_BYTES + L::RED_BYTES + SLOTS * L::at_bytes(at_elems) + SC_SLOTS * L::sc_bytes();
     }
 };
 
@@ -312,10 +315,11 @@ __global__ void __launch_bounds__(kThreads, TDX_MIN_BLOCKS) dek1_kernel(const __
     bool cur_bulk = false;
     if (tile < a.num_tiles) cur_bulk = stage_in(tile_coord<Shape>(g, a.ranges.tile(tile), a.tiles_x), 0);
 
+    constexpr int SC_SLOTS = DekSmem<T, N>::SC_SLOTS;
     for (unsigned it = 0; tile < a.num_tiles; ++it) {
-        const int slot = it & 1;
+        const int slot = (SC_SLOTS == 2) ? (int)(it & 1u) : 0;
         T* my_sc = s_sc0 + slot * SC_STRIDE + w * 32 * STRIDE;
-        T* s_at = s_at0 + slot * AT_STRIDE;
+        T* s_at = s_at0 + (it & 1u) * AT_STRIDE;
         if (kComm && !halos_ready && tile >= a.ranges.wait_from) {
             cta_wait_halos(a.wait);
             halos_ready = true;
@@ -334,7 +338,7 @@ __global__ void __launch_bounds__(kThreads, TDX_MIN_BLOCKS) dek1_kernel(const __
         // (2) start streaming the next tile's factor blocks into the other slot
         const unsigned next = tile + gridDim.x;
         bool next_bulk = false;
-        if (next < a.num_tiles) {
+        if (SC_SLOTS == 2 && next < a.num_tiles) {
             if (lane == 0) bulk_wait_read0();      // the other slot's previous results have left shared memory
             __syncwarp();
             next_bulk = stage_in(tile_coord<Shape>(g, a.ranges.tile(next), a.tiles_x), slot ^ 1);
@@ -344,7 +348,7 @@ __global__ void __launch_bounds__(kThreads, TDX_MIN_BLOCKS) dek1_kernel(const __
         if (cur_bulk) {
             mbar_wait(bars + slot * kWarps + w, (phase_bits >> slot) & 1u);
             phase_bits ^= (1u << slot);
-        } else if (next < a.num_tiles && !next_bulk) {
+        } else if (SC_SLOTS == 2 && next < a.num_tiles && !next_bulk) {
             cp_async_wait_group<1>();  // everything but the next tile's group, which was committed just above
         } else {
             cp_async_wait_group<0>();
@@ -433,6 +437,12 @@ __global__ void __launch_bounds__(kThreads, TDX_MIN_BLOCKS) dek1_kernel(const __
                 const int b = e / NN;
                 sc_out[sc_off + e] = my_sc[b * STRIDE + (e - b * NN)];
             }
+        }
+        if (SC_SLOTS == 1 && next < a.num_tiles) {
+            // single slot: refill it as soon as this tile's results have left (the other resident CTA covers the gap)
+            if (lane == 0) bulk_wait_read0();
+            __syncwarp();
+            next_bulk = stage_in(tile_coord<Shape>(g, a.ranges.tile(next), a.tiles_x), 0);
         }
         tile = next;
         cur_bulk = next_bulk;
