@@ -46,6 +46,25 @@ def test_struct_layouts_match_header():
 
     assert ctypes.sizeof(_lib.ProblemDesc) == 4 + 4 + 4 * 8 + 4 + 4 + 8 * 8   # incl. 4 B padding before params
     assert ctypes.sizeof(_lib.StepArgs) == 4 * 8 + 4 + 4
+    assert ctypes.sizeof(_lib.StepRule) == 4 + 4 + 6 * 8              # tdx_steprule
+    assert ctypes.sizeof(_lib.FullStepResult) == 4 * 8 + 8            # tdx_full_step_result
+    assert ctypes.sizeof(_lib.CtlState) == 3 * 8 + 2 * 8 + 4 * 4      # tdx_ctl_state
+    # the C side agrees: a C translation unit that includes the header prints the same sizes
+    import pathlib, shutil, subprocess, tempfile
+
+    cc = shutil.which("gcc") or shutil.which("cc")
+    if cc:
+        root = pathlib.Path(__file__).resolve().parent.parent
+        with tempfile.TemporaryDirectory() as tmp:
+            src = pathlib.Path(tmp) / "sizes.c"
+            src.write_text('#include <stdio.h>\n#include "tornadox_b200.h"\nint main(void){printf("%zu %zu %zu %zu %zu\\n", '
+                           'sizeof(tdx_problem_desc), sizeof(tdx_step_args), sizeof(tdx_steprule), sizeof(tdx_full_step_result), '
+                           'sizeof(tdx_ctl_state));return 0;}\n')
+            exe = pathlib.Path(tmp) / "sizes"
+            subprocess.run([cc, "-I", str(root / "include"), str(src), "-o", str(exe)], check=True)
+            out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()
+        assert [int(x) for x in out] == [ctypes.sizeof(t) for t in (_lib.ProblemDesc, _lib.StepArgs, _lib.StepRule,
+                                                                     _lib.FullStepResult, _lib.CtlState)]
 
 
 @pytest.mark.parametrize("nu", [1, 2, 3, 4, 5])
