@@ -448,6 +448,14 @@ __global__ void __launch_bounds__(kThreads, TDX_MIN_BLOCKS) dek1_kernel(const __
         cur_bulk = next_bulk;
     }
 
+#ifdef TDX_DEK1_TIMING
+    if (threadIdx.x == 0) {      // development aid: when did this CTA run out of tiles? (scripts/dek1_timeline.py)
+        a.partials[1024 + 2 * blockIdx.x] = (double)global_timer_ns();
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        a.partials[1024 + 2 * blockIdx.x + 1] = (double)smid;
+    }
+#endif
     if constexpr (kCtl) {
         double total = 0.0;
         const bool fin = grid_sum(ratio_sq_acc, s_red, a.partials, a.ticket, c.want_norm ? a.out_sum : nullptr, 1.0, nullptr,
