@@ -136,7 +136,7 @@ def test_device_resident_controller_equals_the_host_loop(cuda_device, solver_nam
     dev = cls(num_derivatives=3, steprule=make_rule(None))
     dev.device_loop_batch = 7                       # several batches, and a tail of launches after the solve is over
     fin_d, info_d = dev.simulate_final_state(p)
-    uses_ctl = not (solver_name == "ek0" and kind != "fhn_2d")
+    uses_ctl = True
     assert dict(info_d) == dict(info_h), (info_d, info_h)
     assert abs(fin_d.t - fin_h.t) <= 1e-12 * abs(fin_h.t)
     # device pow() in the dt proposal is within an ulp or two of the host's: the trajectories agree to rounding, not bit for bit

@@ -765,7 +765,7 @@ int tdx_ek0_attempt_step(tdx_ctx* ctx, const tdx_step_args* args, const void* me
     if (args->flags & 6u) return fail(TDX_ERR_INVALID, "tdx_ek0_attempt_step: partial tile ranges are not supported");
     if (!z_sq_sum) return fail(TDX_ERR_INVALID, "tdx_ek0_attempt_step: z_sq_sum is required");
     const int64_t d_global = (int64_t)ctx->geo.nf * ctx->geo.grows * ctx->geo.gcols;
-    if (ctx->geo.kind != IVP_FHN2D || three_phase_forced()) {
+    if (three_phase_forced()) {
         tdx_step_args a = *args, b = *args;
         if (!sharded) a.flags = b.flags = args->flags & TDX_STEP_ZERO_JACOBIAN;
         else b.flags = (args->flags & ~TDX_STEP_COMM_PACK) | TDX_STEP_COMM_HALO;
@@ -773,7 +773,7 @@ int tdx_ek0_attempt_step(tdx_ctx* ctx, const tdx_step_args* args, const void* me
         if ((rc = tdx_ek0_mid(ctx, args, Cl_in, z_sq_sum, d_global, Cl_out, err_out, stream))) return rc;
         return tdx_ek0_sweep_b(ctx, &b, mean_in, mean_out, ref_out, nullptr, nullptr, sq_norm_sum, stream);
     }
-    // fhn_2d: the whole attempt is one cooperative launch
+    // the whole attempt is one cooperative launch (fhn_2d: row-streaming strips; 1-d fields: tile ranges)
     const unsigned flags = sharded ? args->flags : 0u;
     if ((rc = comm_pack_begin(ctx, flags, "tdx_ek0_attempt_step"))) return rc;
     const void* halo_lo = nullptr;
@@ -1222,8 +1222,6 @@ extern "C" int tdx_ek0_enqueue_attempts(tdx_ctx* ctx, int k, uint32_t flags, voi
     int rc = check_ready(ctx, "tdx_ek0_enqueue_attempts");
     if (rc) return rc;
     if (!ctx->ctl) return fail(TDX_ERR_INVALID, "tdx_ek0_enqueue_attempts: call tdx_ctl_begin first");
-    if (ctx->geo.kind != IVP_FHN2D)
-        return fail(TDX_ERR_UNSUPPORTED, "tdx_ek0_enqueue_attempts: only fhn_2d has the one-launch KroneckerEK0 kernel; use tdx_ek0_full_step");
     if ((rc = check_full_step_flags(ctx, flags, "tdx_ek0_enqueue_attempts"))) return rc;
     if (!mean_a || !Cl_a || !mean_b || !Cl_b || !err_out || mean_a == mean_b || Cl_a == Cl_b)
         return fail(TDX_ERR_INVALID, "tdx_ek0_enqueue_attempts: two distinct state buffer pairs and err_out are required");

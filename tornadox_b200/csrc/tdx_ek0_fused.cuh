@@ -596,4 +596,290 @@ __global__ void __maxnreg__(TDX_EK0_MAXREG) ek0_fused_fhn_kernel(const __grid_co
     }
 }
 
+// =====================================================================================================================
+// The same one-launch attempt for the 1-d vector fields (vanderpol, lorenz96, brusselator, burgers_1d, wave_1d).
+//
+// Work unit = the 256-coordinate tile of the sweep kernels (tile_coord / ExtTile / IVP::ring_value / IVP::eval are reused as
+// they are): thread = one state coordinate.  A CTA owns a CONTIGUOUS range of tiles, walks it forwards in phase A and
+// backwards in phase B (L2 reuse), and gets every tile's raw mean columns through the same TMA ring + producer warp as the
+// fhn kernel; the few stencil neighbours outside a tile (2-3 per field) are recomputed from the mean through L2.
+// =====================================================================================================================
+template <typename T, int N>
+struct Ek0ChainCfg {
+    static constexpr int STAGES = 4;
+    static constexpr int STAGE_ELEMS = N * kThreads;                 // [derivative][thread]
+    static constexpr size_t BAR_BYTES = 128, RED_BYTES = 256;
+    __host__ __device__ static constexpr size_t at_bytes(int at_elems) { return ((size_t)at_elems * sizeof(T) + 127) / 128 * 128; }
+    __host__ __device__ static constexpr size_t total(int at_elems) {
+        return BAR_BYTES + RED_BYTES + 2 * at_bytes(at_elems) + STAGES * (size_t)STAGE_ELEMS * sizeof(T);
+    }
+};
+
+// sigma-independent part of column 1 of the predicted covariance: M1 = (B B^T)[:, 1], B = A (p_inv * Cl)   (see the fhn kernel)
+template <typename T, int N>
+__device__ __forceinline__ void ek0_m1_column(const Consts<double, N>& cd, const T* Cl_in, double* m1) {
+    double B[N][N];
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+        double colv[N];
+#pragma unroll
+        for (int kd = 0; kd < N; ++kd) colv[kd] = cd.pinv[kd] * (double)__ldg(Cl_in + kd * N + j);
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            double accb = colv[i];
+#pragma unroll
+            for (int kd = i + 1; kd < N; ++kd) accb = fma(A_entry<N>(i, kd), colv[kd], accb);
+            B[i][j] = accb;
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < N; ++r) {
+        double m = 0.0;
+#pragma unroll
+        for (int j = 0; j < N; ++j) m = fma(B[r][j], B[1][j], m);
+        m1[r] = m;
+    }
+}
+
+// calibration (ek0.py:123-130) and gain (ek0.py:132-136) from the global sum of z^2; returns the calibrated error estimate
+template <typename T, int N>
+__device__ __forceinline__ double ek0_gain(const Consts<double, N>& cd, const double* m1, double z_sq, double d_global, T (&K)[N]) {
+    const double p1 = cd.p[1];
+    const double Q11 = QL(cd, 1, 0) * QL(cd, 1, 0) + QL(cd, 1, 1) * QL(cd, 1, 1);
+    const double HQH = p1 * p1 * Q11;
+    const double sigma_sq = z_sq / HQH / d_global;
+    const double den = p1 * fma(sigma_sq, Q11, m1[1]);
+#pragma unroll
+    for (int r = 0; r < N; ++r) {
+        const double q = (r == 0) ? QL(cd, 0, 0) * QL(cd, 1, 0) : QL(cd, r, 0) * QL(cd, 1, 0) + QL(cd, r, 1) * QL(cd, 1, 1);
+        K[r] = (T)(fma(sigma_sq, q, m1[r]) / den);
+    }
+    return sqrt(sigma_sq * HQH);
+}
+
+template <class IVP, typename T, int N, bool kCtl = false>
+__global__ void __maxnreg__(72) ek0_fused_chain_kernel(const __grid_constant__ Ek0FusedArgs<T, N> a) {
+    using Shape = typename IVP::Shape;
+    using E = ExtTile<IVP>;
+    using Cfg = Ek0ChainCfg<T, N>;
+    using CSync = NamedSync<1, kThreads>;
+    constexpr int S = Cfg::STAGES, NF = Shape::NF, TCOLS = Shape::TC;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);
+    uint64_t* empty = full + S;
+    double* s_red = reinterpret_cast<double*>(smem_raw + Cfg::BAR_BYTES);
+    T* s_at0 = reinterpret_cast<T*>(smem_raw + Cfg::BAR_BYTES + Cfg::RED_BYTES);
+    constexpr size_t AT_STRIDE = Cfg::at_bytes(E::ELEMS) / sizeof(T);
+    T* s_stage = reinterpret_cast<T*>(smem_raw + Cfg::BAR_BYTES + Cfg::RED_BYTES + 2 * Cfg::at_bytes(E::ELEMS));
+
+    const Geo& g = a.g;
+    const int tid = threadIdx.x;
+    const Consts<T, N>* cp = &a.c;
+    const Consts<double, N>* cdp = &a.cd;
+    const T* mean_in = a.mean_in;
+    T* mean_out = a.mean_out;
+    const T* Cl_in = a.Cl_in;
+    T* Cl_out = a.Cl_out;
+    if constexpr (kCtl) {
+        __shared__ Consts<T, N> s_c;
+        __shared__ Consts<double, N> s_cd;
+        __shared__ int s_cur;
+        if (tid == 0) {
+            const StepCtl* ctl = a.ctl;
+            Consts<T, N> cc = a.c;
+            Consts<double, N> ccd = a.cd;
+#pragma unroll
+            for (int k = 0; k < N; ++k) {
+                ccd.p[k] = ctl->p[k];
+                ccd.pinv[k] = ctl->pinv[k];
+                cc.p[k] = (T)ctl->p[k];
+                cc.pinv[k] = (T)ctl->pinv[k];
+            }
+            ccd.dt = ctl->dt;
+            cc.dt = (T)ctl->dt;
+            s_c = cc;
+            s_cd = ccd;
+            s_cur = ctl->done ? -1 : ctl->cur;
+        }
+        __syncthreads();
+        if (s_cur < 0) return;
+        cp = &s_c;
+        cdp = &s_cd;
+        mean_in = a.mean_ab[s_cur];
+        mean_out = a.mean_ab[s_cur ^ 1];
+        Cl_in = a.Cl_ab[s_cur];
+        Cl_out = a.Cl_ab[s_cur ^ 1];
+    }
+    const Consts<T, N>& c = *cp;
+    const Consts<double, N>& cdr = *cdp;
+
+    // this CTA's contiguous range of tiles
+    const unsigned num_tiles = a.total_strips, tiles_x = a.col_blocks;
+    const unsigned t0 = (unsigned)(((unsigned long long)blockIdx.x * num_tiles) / gridDim.x);
+    const unsigned t1 = (unsigned)(((unsigned long long)(blockIdx.x + 1) * num_tiles) / gridDim.x);
+
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+            mbar_init(full + s, 1);
+            mbar_init(empty + s, 1);
+        }
+        fence_mbar_init();
+        fence_proxy_async();
+    }
+    __syncthreads();
+
+    if (tid >= kThreads) {
+        // ---- producer warp: one tile per ring slot; per tile NF * n contiguous row segments -------------------------
+        const int lane = tid - kThreads;
+        const int seg_f = lane / N, seg_k = lane - seg_f * N;
+        unsigned q = 0;
+#pragma unroll 1
+        for (int phase = 0; phase < 2; ++phase) {
+#pragma unroll 1
+            for (unsigned j = 0; j < t1 - t0; ++j, ++q) {
+                const unsigned tile = phase ? (t1 - 1u - j) : (t0 + j);
+                const unsigned stage = q % S, round = q / S;
+                if (round > 0) mbar_wait(empty + stage, (round - 1u) & 1u);
+                // the tile's columns of field f: [col0, col0 + len) of a chain (one tile row)
+                const long long col0 = (long long)(tile % tiles_x) * TCOLS;
+                long long len = (long long)g.cols - col0;
+                len = len > TCOLS ? TCOLS : len;
+                T* dst = s_stage + (size_t)stage * Cfg::STAGE_ELEMS;
+                const uint32_t bytes = (uint32_t)(len * (long long)sizeof(T));
+                const bool bulk = a.use_bulk && (bytes % 16u == 0u) && (((col0 * (long long)sizeof(T)) & 15) == 0);
+                if (bulk) {
+                    if (lane == 0) mbar_expect_tx(full + stage, (uint32_t)(NF * N) * bytes);
+                    __syncwarp();
+                    if (lane < NF * N)
+                        bulk_g2s(dst + seg_k * kThreads + seg_f * TCOLS, mean_in + (long long)seg_k * g.d + (long long)seg_f * g.npts + col0,
+                                 bytes, full + stage);
+                } else {
+                    for (int seg = 0; seg < NF * N; ++seg) {
+                        const int f = seg / N, kd = seg - f * N;
+                        const T* sp = mean_in + (long long)kd * g.d + (long long)f * g.npts + col0;
+                        for (int jj = lane; jj < (int)len; jj += 32) dst[kd * kThreads + f * TCOLS + jj] = __ldg(sp + jj);
+                    }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(full + stage);
+                }
+            }
+        }
+        return;
+    }
+
+    // ---- consumers ----------------------------------------------------------------------------------------------------
+    CSync csync;
+    if (a.pack.enabled)
+        for (int part = (int)blockIdx.x; part < 2 * kPackCtas; part += (int)gridDim.x)
+            pack_halo_part<T, N>(g, c, mean_in, a.pack, part, csync);
+    double* s_m1 = s_red + 16;
+    if (tid == 0) ek0_m1_column<T, N>(cdr, Cl_in, s_m1);
+    // the shard's end tiles read the neighbours' halo values: they are tiny and on their way since the peers' kernels started
+    if ((a.halo_lo != nullptr || a.halo_hi != nullptr) && (t0 == 0u || t1 == num_tiles)) cta_wait_halos(a.wait, csync);
+
+    unsigned cq = 0, phase_bits = 0u;
+    T K[N];
+#pragma unroll
+    for (int r = 0; r < N; ++r) K[r] = (T)0;
+
+    auto run_phase = [&](auto update_tag) -> double {
+        constexpr bool kUpdate = decltype(update_tag)::value;
+        double acc = 0.0;
+#pragma unroll 1
+        for (unsigned j = 0; j < t1 - t0; ++j, ++cq) {
+            const unsigned tile = kUpdate ? (t1 - 1u - j) : (t0 + j);
+            const unsigned stage = cq % S;
+            const Coord co = tile_coord<Shape>(g, tile, tiles_x);
+            FrontRegs<IVP, T, N> fr;
+            front_load<IVP, T, N, false>(g, c, mean_in, a.halo_lo, a.halo_hi, co, fr);     // ring / fill values only
+            mbar_wait(full + stage, (phase_bits >> stage) & 1u);
+            phase_bits ^= (1u << stage);
+            const T* st = s_stage + (size_t)stage * Cfg::STAGE_ELEMS + tid;
+#pragma unroll
+            for (int kd = 0; kd < N; ++kd) fr.raw[kd] = co.valid ? st[kd * kThreads] : (T)0;
+            T mp[N], fx, jac;
+            front_eval<IVP, T, N>(g, c, co, fr, s_at0 + (cq & 1u) * AT_STRIDE, mp, fx, jac, csync);
+            if (tid == 0) mbar_arrive(empty + stage);       // every consumer has its column in registers (barrier above)
+            if (co.valid) {
+                const T z = c.p[1] * mp[1] - fx;
+                if constexpr (!kUpdate) {
+                    acc += (double)z * (double)z;
+                } else {
+                    T m0 = (T)0;
+                    T* mo_ptr = mean_out + co.flat;
+#pragma unroll
+                    for (int r = 0; r < N; ++r) {
+                        const T mo = c.p[r] * (mp[r] - K[r] * z);
+                        *mo_ptr = mo;
+                        mo_ptr += g.d;
+                        if (r == 0) m0 = mo;
+                    }
+                    const T ref = tabs<T>(m0);
+                    if (a.ref_out) a.ref_out[co.flat] = ref;
+                    if (c.want_norm) {
+                        const double tol = (double)c.abstol + (double)c.reltol * (double)ref;
+                        acc += 1.0 / (tol * tol);
+                    }
+                }
+            }
+        }
+        return acc;
+    };
+
+    // ---- phase A, barrier, gain ---------------------------------------------------------------------------------------
+    const double acc_a = run_phase(std::false_type{});
+    if (publish_partial(acc_a, s_red, a.partials, a.ticket, csync) == gridDim.x - 1) {
+        double z_sq = sum_partials(s_red, a.partials, csync);
+        if (a.reduce_a.world > 0) {
+            csync();
+            z_sq = cta_allreduce(z_sq, a.reduce_a, s_red, csync);
+        }
+        if (tid == 0) {
+            a.mid->z_sq = z_sq;
+            if (a.z_sq_out) *a.z_sq_out = z_sq;
+            *a.ticket = 0u;
+            __threadfence();
+            st_release_gpu(a.mid_flag, a.mid_seq);
+        }
+    }
+    if (tid == 0) {
+        const unsigned long long ts = global_timer_ns();
+        s_red[30] = 0.0;
+        while (ld_acquire_gpu(a.mid_flag) < a.mid_seq) {
+            if (global_timer_ns() - ts > 4000000000ull) {
+                s_red[30] = 1.0;
+                break;
+            }
+            __nanosleep(64);
+        }
+    }
+    csync();
+    const double z_sq_all = (s_red[30] != 0.0) ? nan("") : __ldcg(&a.mid->z_sq);
+    const double err_cal = ek0_gain<T, N>(cdr, s_m1, z_sq_all, a.d_global, K);
+
+    // ---- phase B ----------------------------------------------------------------------------------------------------
+    const double acc_b = run_phase(std::true_type{});
+    const unsigned arrival = publish_partial(acc_b, s_red, a.partials + gridDim.x, a.ticket + 1, csync);
+    if (arrival == 0u && tid == 0) ek0_mid_compute<T, N>(cdr, Cl_in, z_sq_all, a.d_global, Cl_out, a.err_out, a.mid);
+    if (arrival == gridDim.x - 1) {
+        if (c.want_norm) {
+            double b = sum_partials(s_red, a.partials + gridDim.x, csync);
+            if (tid == 0) {
+                b *= err_cal * err_cal;
+                b *= (double)c.dt * (double)c.dt;
+            }
+            if (a.reduce_b.world > 0) {
+                csync();
+                b = cta_allreduce(b, a.reduce_b, s_red, csync);
+            }
+            if (tid == 0) *a.out_sum = b;
+            if (kCtl && tid == 0) ctl_update(a.ctl, b, a.d_global);
+        } else if (kCtl && tid == 0) {
+            ctl_update(a.ctl, 0.0, a.d_global);
+        }
+        if (tid == 0) a.ticket[1] = 0u;
+    }
+}
+
 }  // namespace tdx

@@ -72,16 +72,19 @@ struct FrontRegs {
 __device__ __forceinline__ int tile_row0(const Coord& c) { return c.row - c.tr; }
 __device__ __forceinline__ int tile_col0(const Coord& c) { return c.col - c.tcol; }
 
-template <class IVP, typename T, int N>
+// kOwn = false: only the ring / fill values (the caller gets the thread's own column from somewhere else, e.g. a TMA stage)
+template <class IVP, typename T, int N, bool kOwn = true>
 __device__ __forceinline__ void front_load(const Geo& g, const Consts<T, N>& c, const T* __restrict__ mean_in,
                                            const T* halo_lo, const T* halo_hi, const Coord& co,
                                            FrontRegs<IVP, T, N>& fr) {
     using E = ExtTile<IVP>;
-    const T* src = mean_in + co.flat;
+    if (kOwn) {
+        const T* src = mean_in + co.flat;
 #pragma unroll
-    for (int k = 0; k < N; ++k) {
-        fr.raw[k] = co.valid ? __ldg(src) : (T)0;
-        src += g.d;
+        for (int k = 0; k < N; ++k) {
+            fr.raw[k] = co.valid ? __ldg(src) : (T)0;
+            src += g.d;
+        }
     }
     fr.ring = (T)0;
     fr.fill = (T)0;
@@ -97,9 +100,10 @@ __device__ __forceinline__ void front_load(const Geo& g, const Consts<T, N>& c, 
                                   halo_hi);
 }
 
-template <class IVP, typename T, int N>
+template <class IVP, typename T, int N, class Sync = FullSync>
 __device__ __forceinline__ void front_eval(const Geo& g, const Consts<T, N>& c, const Coord& co,
-                                           const FrontRegs<IVP, T, N>& fr, T* s_ext, T (&mp)[N], T& fx, T& jac) {
+                                           const FrontRegs<IVP, T, N>& fr, T* s_ext, T (&mp)[N], T& fx, T& jac,
+                                           Sync sync = Sync()) {
     using E = ExtTile<IVP>;
     predict_column<T, N>(fr.raw, c, mp);
     const T own = co.valid ? c.p[0] * mp[0] : fr.fill;
@@ -110,7 +114,7 @@ __device__ __forceinline__ void front_eval(const Geo& g, const Consts<T, N>& c, 
         E::ring(threadIdx.x - field * E::NRING, er, ec);
         s_ext[E::index(field, er, ec)] = fr.ring;
     }
-    __syncthreads();
+    sync();
     fx = (T)0;
     jac = (T)0;
     if (co.valid) IVP::eval(g, co, s_ext, own, fx, jac);

@@ -289,13 +289,27 @@ struct Launch {
                                      mid_flag, mid_seq, d_global, z_sq_out, out_sum, st, nullptr, nullptr, nullptr);
     }
 
+    template <class IVP, bool kCtl>
+    static int launch_chain(const Geo& g, Ek0FusedArgs<T, N>& a, cudaStream_t st) {
+        using Shape = typename IVP::Shape;
+        using CCfg = Ek0ChainCfg<T, N>;
+        constexpr auto kern = ek0_fused_chain_kernel<IVP, T, N, kCtl>;
+        const size_t smem = CCfg::total(ExtTile<IVP>::ELEMS);
+        a.col_blocks = (unsigned)((g.cols + Shape::TC - 1) / Shape::TC);                       // tiles per tile row
+        a.total_strips = a.col_blocks * (unsigned)((g.rows + Shape::TR - 1) / Shape::TR);     // tiles
+        unsigned grid = 0;
+        TDX_CUDA_TRY(persistent_grid<kern>(smem, (long long)a.total_strips, 0, grid, kThreads + 32));
+        void* params[] = {(void*)&a};
+        TDX_CUDA_TRY(cudaLaunchCooperativeKernel((const void*)kern, dim3(grid), dim3(kThreads + 32), params, smem, st));
+        return (int)cudaGetLastError();
+    }
+
     template <bool kCtl>
     static int ek0_fused_impl(const Geo& g, const StepHost& h, const void* mean_in, const void* Cl_in, void* mean_out,
                               void* Cl_out, void* err_out, void* ref_out, const void* halo_lo, const void* halo_hi,
                               const Workspace& ws, const CommReduce& reduce_b, unsigned long long* mid_flag,
                               unsigned long long mid_seq, double d_global, double* z_sq_out, double* out_sum,
                               cudaStream_t st, StepCtl* ctl, void* const mean_ab[2], void* const Cl_ab[2]) {
-        if (g.kind != IVP_FHN2D) return kNoFusedKernel;
         constexpr int W = TDX_EK0_W;
         using Cfg = Ek0FusedCfg<T, N, W>;
         constexpr auto kern = ek0_fused_fhn_kernel<T, N, W, kCtl>;
@@ -304,6 +318,45 @@ struct Launch {
         for (int i = 0; i < 2; ++i) {
             a.mean_ab[i] = ctl ? (T*)mean_ab[i] : nullptr;
             a.Cl_ab[i] = ctl ? (T*)Cl_ab[i] : nullptr;
+        }
+        if (g.kind != IVP_FHN2D) {
+            // 1-d vector fields: the tile-based one-launch kernel
+            a.g = g;
+            a.c = make_consts<T, N>(h);
+            a.cd = make_consts<double, N>(h);
+            a.mean_in = (const T*)mean_in;
+            a.mean_out = (T*)mean_out;
+            a.ref_out = (T*)ref_out;
+            a.halo_lo = (const T*)halo_lo;
+            a.halo_hi = (const T*)halo_hi;
+            a.Cl_in = (const T*)Cl_in;
+            a.Cl_out = (T*)Cl_out;
+            a.err_out = (T*)err_out;
+            a.mid = (Ek0Mid<T, N>*)ws.mid;
+            a.mid_flag = mid_flag;
+            a.mid_seq = mid_seq;
+            a.partials = ws.partials;
+            a.ticket = ws.ticket;
+            a.z_sq_out = z_sq_out;
+            a.out_sum = out_sum;
+            a.d_global = d_global;
+            a.wait = ws.wait;
+            a.reduce_a = ws.reduce;
+            a.reduce_b = reduce_b;
+            a.pack = typed_pack(ws.pack);
+            a.chunks = 0;
+            a.keep_frac = 2.0f;
+            a.use_bulk = (g.cols % (16 / (int)sizeof(T)) == 0) && ((reinterpret_cast<uintptr_t>(ctl ? mean_ab[0] : mean_in) & 15) == 0) &&
+                                 (!ctl || (reinterpret_cast<uintptr_t>(mean_ab[1]) & 15) == 0)
+                             ? 1 : 0;
+            switch (g.kind) {
+                case IVP_VDP: return launch_chain<VanderPol<T>, kCtl>(g, a, st);
+                case IVP_LORENZ96: return launch_chain<Lorenz96<T>, kCtl>(g, a, st);
+                case IVP_BRUSS: return launch_chain<Brusselator<T>, kCtl>(g, a, st);
+                case IVP_BURGERS1D: return launch_chain<Burgers1d<T>, kCtl>(g, a, st);
+                case IVP_WAVE1D: return launch_chain<Wave1d<T>, kCtl>(g, a, st);
+                default: return kNoFusedKernel;
+            }
         }
         a.g = g;
         a.c = make_consts<T, N>(h);

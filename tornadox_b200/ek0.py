@@ -79,12 +79,11 @@ class KroneckerEK0(odefilter.ODEFilter):
     perform_full_step_compiled = perform_full_step
 
     def _device_loop_final_state(self, ivp):
-        """The whole solve under the device-resident step controller (``tdx_ek0_enqueue_attempts``; fhn_2d only)."""
+        """The whole solve under the device-resident step controller (``tdx_ek0_enqueue_attempts``)."""
         state = self.initialize(*ivp)
         eng = self.engine
         rule = eng.native_steprule(self.steprule)
-        if (rule is None or state.y.mean.device.type != "cuda" or not eng.can_run_full_steps()
-                or eng.spec.kind != _lib.TDX_IVP_FHN2D):
+        if rule is None or state.y.mean.device.type != "cuda" or not eng.can_run_full_steps():
             return None
         if not state.t < ivp.tmax:
             return state, dict(num_f_evaluations=0, num_df_evaluations=0, num_df_diagonal_evaluations=0, num_steps=0,
