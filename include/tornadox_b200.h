@@ -112,6 +112,15 @@ int tdx_prior(int nu, double* A_out, double* Ql_out);
  * bit-level agreement with a particular host's reference run is wanted.  Call after tdx_set_problem. */
 int tdx_set_diffusion_sqrt(tdx_ctx* ctx, const double* Ql);
 
+/* sqrt.propagate_cholesky_factor / sqrt.sqrtm_to_cholesky and their vmapped versions (sqrt.py:8-30) as a standalone
+ * batched op on DEVICE buffers: out[b] (n, n) = lower factor L with L L^T = S1[b] S1[b]^T + S2[b] S2[b]^T, i.e. the
+ * transposed R-factor of qr([S1^T ; S2^T]) with LAPACK's sign convention (what jnp.linalg.qr returns on CPU).
+ * S2 == NULL: sqrtm_to_cholesky of the square right square root St = S1^T.  ``*_broadcast`` != 0: the same (n, n)
+ * matrix for every batch element.  ``rows_given`` != 0: S1 / S2 hold the rows of the stacked matrix St itself.
+ * No context needed; 1 <= n - 1 <= 5 (the instantiated orders). */
+int tdx_propagate_cholesky_factor(int dtype, int n, int64_t batch, const void* S1, const void* S2, void* out,
+                                  int s1_broadcast, int s2_broadcast, int rows_given, void* stream);
+
 /* Nordsieck preconditioner vectors (iwp.py:65-73), HOST buffers of n doubles each. */
 int tdx_nordsieck(int nu, double dt, double* p_out, double* p_inv_out);
 

@@ -7,6 +7,6 @@ mirrors ``from tornadox import ek0, ek1, init, ivp, step`` (tornadox/__init__.py
 thin ctypes layer over the C ABI in include/tornadox_b200.h; there is no CPU fallback.
 """
 
-from . import ek0, ek1, engine, init, ivp, odefilter, rv, step  # noqa: F401
+from . import ek0, ek1, engine, init, ivp, iwp, odefilter, rv, sqrt, step  # noqa: F401
 
 __version__ = "0.1.0"

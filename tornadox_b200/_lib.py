@@ -28,7 +28,7 @@ EXPORTED_SYMBOLS = (
     "tdx_last_error", "tdx_abi_version", "tdx_create", "tdx_destroy", "tdx_set_problem", "tdx_local_dim",
     "tdx_halo_sizes", "tdx_set_diffusion_sqrt", "tdx_prior", "tdx_nordsieck", "tdx_eval_f", "tdx_pack_halo", "tdx_dek1_attempt_step",
     "tdx_ek0_sweep_a", "tdx_ek0_mid", "tdx_ek0_sweep_b", "tdx_ek0_attempt_step", "tdx_launch_count",
-    "tdx_debug_read_workspace", "tdx_dek1_attempt_step_host", "tdx_dek1_full_step", "tdx_ek0_full_step",
+    "tdx_debug_read_workspace", "tdx_dek1_attempt_step_host", "tdx_dek1_full_step", "tdx_ek0_full_step", "tdx_propagate_cholesky_factor",
     "tdx_ctl_begin", "tdx_dek1_enqueue_attempts", "tdx_ek0_enqueue_attempts", "tdx_ctl_read", "tdx_comm_init", "tdx_comm_connect", "tdx_comm_pack_halo", "tdx_comm_allreduce", "tdx_comm_error",
 )
 
@@ -136,6 +136,7 @@ def load():
     full = [vp, ctypes.POINTER(StepRule), dbl, dbl, dbl, ctypes.c_uint32] + [vp] * 6 + [ctypes.POINTER(FullStepResult), vp]
     lib.tdx_dek1_full_step.argtypes = full
     lib.tdx_ek0_full_step.argtypes = full
+    lib.tdx_propagate_cholesky_factor.argtypes = [cint, cint, i64, vp, vp, vp, cint, cint, cint, vp]
     lib.tdx_ctl_begin.argtypes = [vp, ctypes.POINTER(StepRule), dbl, dbl, dbl, vp]
     lib.tdx_dek1_enqueue_attempts.argtypes = [vp, cint, ctypes.c_uint32] + [vp] * 7
     lib.tdx_ek0_enqueue_attempts.argtypes = [vp, cint, ctypes.c_uint32] + [vp] * 7

@@ -200,6 +200,17 @@ int tdx_prior(int nu, double* A_out, double* Ql_out) {
     return TDX_OK;
 }
 
+int tdx_propagate_cholesky_factor(int dtype, int n, int64_t batch, const void* S1, const void* S2, void* out,
+                                  int s1_broadcast, int s2_broadcast, int rows_given, void* stream) {
+    const Ops* ops = find_ops(dtype, n);
+    if (!ops) return fail(TDX_ERR_UNSUPPORTED, "tdx_propagate_cholesky_factor: no kernel instantiated for this (n, dtype)");
+    if (!S1 || !out || batch < 0) return fail(TDX_ERR_INVALID, "tdx_propagate_cholesky_factor: null buffer or negative batch");
+    const int code = ops->qr_lower(S1, S2, out, (long long)batch, s1_broadcast, s2_broadcast, rows_given, (cudaStream_t)stream);
+    if (code == 0) return TDX_OK;
+    g_last_error = std::string("tdx_propagate_cholesky_factor: ") + cudaGetErrorString((cudaError_t)code);
+    return TDX_ERR_CUDA;
+}
+
 int tdx_nordsieck(int nu, double dt, double* p_out, double* p_inv_out) {
     if (nu < 0 || nu + 1 > kMaxN) return fail(TDX_ERR_INVALID, "tdx_nordsieck: nu out of range");
     nordsieck_host(nu, dt, p_out, p_inv_out);

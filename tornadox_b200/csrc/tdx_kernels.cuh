@@ -665,6 +665,69 @@ __global__ void pack_halo_kernel(const __grid_constant__ PackArgs<T, N> a) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// sqrt.propagate_cholesky_factor / sqrtm_to_cholesky as a standalone batched op (sqrt.py:8-30): the lower factor
+// L = R^T of the QR decomposition of a 'right' square root St (M x N per batch element, M = N or 2 N), LAPACK
+// dgeqr2 / dlarfg convention like stacked_qr.  One thread per matrix, everything in registers; the inputs are read
+// as S1[b] (N x N) and, for M = 2 N, S2[b] (N x N) with St = [S1^T ; S2^T]  (``transposed`` = 0: the rows of St are given).
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+struct QrArgs {
+    const T* s1;        // (batch, N, N)
+    const T* s2;        // (batch, N, N) or null (M = N)
+    T* out;             // (batch, N, N) lower triangular
+    long long batch;
+    int s1_broadcast, s2_broadcast;   // the same matrix for every batch element
+    int rows_given;     // 1: s1 / s2 hold St itself (rows of the stacked matrix) instead of S1, S2
+};
+
+template <typename T, int N, int M>
+__global__ void __launch_bounds__(128) batched_qr_lower_kernel(const __grid_constant__ QrArgs<T> a) {
+    const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= a.batch) return;
+    // C[c][r] = St[r][c]: column c of the stacked matrix
+    T C[N][M];
+    const T* p1 = a.s1 + (a.s1_broadcast ? 0 : b * N * N);
+    const T* p2 = (M > N) ? a.s2 + (a.s2_broadcast ? 0 : b * N * N) : nullptr;
+#pragma unroll
+    for (int c = 0; c < N; ++c)
+#pragma unroll
+        for (int r = 0; r < M; ++r) {
+            const T* src = (r < N) ? p1 : p2;
+            const int rr = (r < N) ? r : r - N;
+            C[c][r] = a.rows_given ? src[rr * N + c] : src[c * N + rr];     // St = S^T: St[r][c] = S[c][r]
+        }
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+        const T alpha = C[k][k];
+        T ns = (T)0;
+#pragma unroll
+        for (int r = k + 1; r < M; ++r) ns = fma(C[k][r], C[k][r], ns);
+        if (ns != (T)0) {
+            const T nrm = tsqrt<T>(fma(alpha, alpha, ns));
+            const T beta = (alpha >= (T)0 && !(alpha == (T)0 && signbit(alpha))) ? -nrm : nrm;
+            const T u0 = alpha - beta;
+            const T gamma = (T)1 / (beta * (beta - alpha));
+#pragma unroll
+            for (int cc = k + 1; cc < N; ++cc) {
+                T w = u0 * C[cc][k];
+#pragma unroll
+                for (int r = k + 1; r < M; ++r) w = fma(C[k][r], C[cc][r], w);
+                w *= gamma;
+                C[cc][k] = fma(-w, u0, C[cc][k]);
+#pragma unroll
+                for (int r = k + 1; r < M; ++r) C[cc][r] = fma(-w, C[k][r], C[cc][r]);
+            }
+            C[k][k] = beta;
+        }
+    }
+    T* o = a.out + b * N * N;
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+#pragma unroll
+        for (int j = 0; j < N; ++j) o[i * N + j] = (j <= i) ? C[i][j] : (T)0;   // L[i][j] = R[j][i] = C[i][j]
+}
+
+// ---------------------------------------------------------------------------------------------
 // f(y) and diag J(y) on a plain state vector
 // ---------------------------------------------------------------------------------------------
 template <typename T>

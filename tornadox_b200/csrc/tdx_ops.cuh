@@ -73,6 +73,8 @@ struct Ops {
                      void* err_out, void* ref_out, const void* halo_lo, const void* halo_hi, const Workspace&,
                      const CommReduce& reduce_b, unsigned long long* mid_flag, unsigned long long mid_seq,
                      double d_global, double* z_sq_out, double* out_sum, cudaStream_t);
+    int (*qr_lower)(const void* s1, const void* s2, void* out, long long batch, int s1_broadcast, int s2_broadcast,
+                    int rows_given, cudaStream_t);
     int (*pack)(const Geo&, const StepHost&, const void* mean_in, void* edge_first, void* edge_last, int n_first,
                 int n_last, cudaStream_t);
     int (*pack_peer)(const Geo&, const StepHost&, const void* mean_in, const PackPeer<double>& pk, cudaStream_t);
@@ -431,6 +433,16 @@ struct Launch {
         return (int)cudaGetLastError();
     }
 
+    static int qr_lower(const void* s1, const void* s2, void* out, long long batch, int s1_broadcast, int s2_broadcast,
+                        int rows_given, cudaStream_t st) {
+        QrArgs<T> a{(const T*)s1, (const T*)s2, (T*)out, batch, s1_broadcast, s2_broadcast, rows_given};
+        if (batch <= 0) return 0;
+        const unsigned blocks = (unsigned)((batch + 127) / 128);
+        if (s2) batched_qr_lower_kernel<T, N, 2 * N><<<blocks, 128, 0, st>>>(a);
+        else batched_qr_lower_kernel<T, N, N><<<blocks, 128, 0, st>>>(a);
+        return (int)cudaGetLastError();
+    }
+
     static int pack(const Geo& g, const StepHost& h, const void* mean_in, void* edge_first, void* edge_last,
                     int n_first, int n_last, cudaStream_t st) {
         PackArgs<T, N> a;
@@ -480,6 +492,7 @@ struct Launch {
         o.ek0_mid = &ek0_mid;
         o.ek0_b = &ek0_b;
         o.ek0_fused = &ek0_fused;
+        o.qr_lower = &qr_lower;
         o.dek1_ctl = &dek1_ctl;
         o.ek0_ctl = &ek0_ctl;
         o.pack = &pack;
