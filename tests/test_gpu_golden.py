@@ -210,3 +210,17 @@ def test_fp32_attempt_within_1e5(cuda_device, name):
     S = _np(new.y.cov_sqrtm).astype(np.float64)
     R = g[f"dense/{name}/dek1/cov_sqrtm"]
     assert_close(S @ S.transpose(0, 2, 1), R @ R.transpose(0, 2, 1), 5 * FP32_RTOL, "fp32 covariance")
+    # KroneckerEK0 in fp32 (the one-launch kernels' float instantiations; the calibration / QR stay in fp64 inside)
+    from tornadox_b200 import ek0
+
+    sol0 = ek0.KroneckerEK0(num_derivatives=4, dtype=torch.float32)
+    sol0.initialize(*p)
+    d = p.y0.shape[0]
+    st0 = odefilter.ODEFilterState(0.3, rv.LeftIsotropicMatrixNormal(t32("mean"), d, t32("single")), None, None)
+    new0, _ = sol0.attempt_step(st0, dt, *p)
+    assert new0.y.mean.dtype == torch.float32
+    assert_close(_np(new0.y.mean), g[f"dense/{name}/ek0/mean"], FP32_RTOL, "fp32 ek0 mean")
+    C = _np(new0.y.cov_sqrtm_2).astype(np.float64)
+    Rc = g[f"dense/{name}/ek0/cov_sqrtm"]
+    assert_close(C @ C.T, Rc @ Rc.T, 5 * FP32_RTOL, "fp32 ek0 covariance")
+    assert_close(float(new0.error_estimate), g[f"dense/{name}/ek0/error_estimate"], 5 * FP32_RTOL, "fp32 ek0 error estimate")
