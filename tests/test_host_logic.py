@@ -184,3 +184,35 @@ def test_rv_containers():
     assert li.dense_cov().shape == (6, 6)
     assert torch.allclose(li.dense_cov(), torch.kron(torch.eye(3, dtype=torch.float64), S[0] @ S[0].T))
     assert li.cov.shape == (3, 2, 2)
+
+
+def test_deferred_reference_state_resolves_on_access():
+    """KroneckerEK0 stores reference_state = |mean[0]| lazily (odefilter.DeferredAbsRow); attribute access materialises it."""
+    from tornadox_b200 import odefilter
+
+    mean = torch.tensor([[1.0, -2.0, 3.0], [0.5, 0.5, 0.5]], dtype=torch.float64)
+    st = odefilter.ODEFilterState(t=0.1, y=None, error_estimate=0.0, reference_state=odefilter.DeferredAbsRow(mean))
+    assert torch.equal(st.reference_state, torch.tensor([1.0, 2.0, 3.0], dtype=torch.float64))
+    assert st.reference_state is st.reference_state            # computed once
+    row = mean[0]
+    plain = odefilter.ODEFilterState(t=0.1, y=None, error_estimate=0.0, reference_state=row)
+    assert plain.reference_state is row
+    assert plain._replace(t=0.2).t == 0.2 and len(tuple(plain)) == 4
+
+
+def test_native_steprule_mirror_and_shard_ranges():
+    """engine.native_steprule only maps the reference's own rule classes; burgers_1d / wave_1d refuse to shard."""
+    from tornadox_b200 import engine, ivp, step
+
+    class Mine(step.AdaptiveSteps):
+        pass
+
+    fake = engine.StepEngine.__new__(engine.StepEngine)
+    r = engine.StepEngine.native_steprule(fake, step.AdaptiveSteps(abstol=1e-3, reltol=1e-2, max_changes=(0.1, 5.0), safety_scale=0.9))
+    assert (r.adaptive, r.abstol, r.reltol, r.min_change, r.max_change, r.safety_scale) == (1, 1e-3, 1e-2, 0.1, 5.0, 0.9)
+    c = engine.StepEngine.native_steprule(fake, step.ConstantSteps(0.25))
+    assert (c.adaptive, c.constant_dt) == (0, 0.25)
+    assert engine.StepEngine.native_steprule(fake, Mine()) is None
+    with pytest.raises(NotImplementedError):
+        engine.shard_range(ivp.burgers_1d(dx=0.1).spec, 0, 2)
+    assert engine.shard_range(ivp.lorenz96(num_variables=10).spec, 1, 2) == (5, 10)
