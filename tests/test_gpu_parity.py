@@ -135,3 +135,31 @@ def test_config1_vanderpol_adaptive_solve_same_step_sequence(cuda_device, solver
     np.testing.assert_allclose(ts, ref_ts, rtol=1e-9, atol=0)
     assert dict(final_info) == info
     assert_close(final.y.mean.cpu().numpy(), states[-1].mean, 1e-8, "final mean")
+
+
+@pytest.mark.parametrize("size", [257, 300, 513])
+def test_awkward_fhn_grids(cuda_device, size):
+    """Grids that exercise the strip kernel's ragged last column block (300 = 256 + 44), a one-column block (257, 513) and, for
+    odd sizes, the non-bulk staging path; DiagonalEK1 on the same grid for the smallest two."""
+    o, p, _ = make_pair("fhn_2d", size)
+    nu = 4
+    n, d = nu + 1, o.y0.shape[0]
+    rng = np.random.default_rng(size)
+    mean, sc = random_state(rng, n, d, "dense")
+    mean[0] = o.y0 + 0.05 * rng.standard_normal(d)
+    Cl = 1e-2 * rng.standard_normal((n, n))
+    dt, abstol, reltol = 1e-4, 1e-4, 1e-2
+    eng = _engine(p, nu)
+    ref0, _ = ofilters.kronecker_ek0_attempt(ofilters.FilterState(0.3, mean, Cl, None, None), dt, o.f, nu)
+    m, C, err, ref, itol = eng.ek0_attempt(0.3, dt, _t(mean), _t(Cl), abstol=abstol, reltol=reltol)
+    assert_close(m.cpu().numpy(), ref0.mean, FP64_RTOL, "ek0 mean")
+    assert_close(C.cpu().numpy(), ref0.cov_sqrtm, FP64_RTOL, "ek0 cov_sqrtm_2")
+    assert_close(ref.cpu().numpy(), ref0.reference_state, FP64_RTOL, "ek0 reference_state")
+    ref_norm = odriver.AdaptiveSteps(abstol, reltol).scale_error_estimate(dt * ref0.error_estimate, ref0.reference_state)
+    assert abs(math.sqrt(float(itol) / d) - ref_norm) <= FP64_RTOL * abs(ref_norm)
+    if size <= 300:
+        ref1, _ = ofilters.diagonal_ek1_attempt(ofilters.FilterState(0.3, mean, sc, None, None), dt, o.f, o.df_diagonal, nu)
+        m1, s1, err1, ref_1, _ = eng.dek1_attempt(0.3, dt, _t(mean), _t(sc), abstol=abstol, reltol=reltol)
+        assert_close(m1.cpu().numpy(), ref1.mean, FP64_RTOL, "dek1 mean")
+        assert_close(s1.cpu().numpy(), ref1.cov_sqrtm, FP64_RTOL, "dek1 cov_sqrtm")
+        assert_close(err1.cpu().numpy(), ref1.error_estimate, FP64_RTOL, "dek1 error_estimate")
