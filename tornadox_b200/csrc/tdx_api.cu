@@ -873,11 +873,16 @@ static int build_pipe(tdx_ctx* ctx, int nchunks_hint) {
         const long long b = extent * c / n, en = extent * (c + 1) / n;
         tdx_ctx* cc = nullptr;
         int rc = tdx_create(&cc, ctx->device, ctx->dtype);
-        if (rc) { delete hp; return rc; }
         tdx_problem_desc d = ctx->desc;
         d.shard_begin = b;
         d.shard_end = en;
-        if ((rc = tdx_set_problem(cc, &d))) { tdx_destroy(cc); delete hp; return rc; }
+        if (!rc) rc = tdx_set_problem(cc, &d);
+        if (rc) {
+            tdx_destroy(cc);
+            for (tdx_ctx* made : hp->ctx) tdx_destroy(made);
+            delete hp;
+            return rc;
+        }
         hp->ctx.push_back(cc);
         const long long per_unit = rows_axis ? g.cols : 1;
         hp->p0.push_back(b * per_unit);
@@ -995,7 +1000,12 @@ extern "C" int tdx_dek1_attempt_step_host(tdx_ctx* ctx, const tdx_step_args* arg
             rc = tdx_dek1_attempt_step(hp.ctx[c], args, dmean(hp.mean_in, c), hp.fac_in[slot], dmean(hp.mean_out, c), hp.fac_out[slot],
                                        h_err_out ? dvec(hp.err, c) : nullptr, h_ref_out ? dvec(hp.ref, c) : nullptr, halo_lo, halo_hi,
                                        hp.sq + c, hp.s_comp);
-            if (rc) return rc;
+            if (rc) {      // drain what is in flight before the caller gets its buffers back
+                cudaStreamSynchronize(hp.s_h2d);
+                cudaStreamSynchronize(hp.s_comp);
+                cudaStreamSynchronize(hp.s_d2h);
+                return rc;
+            }
         }
         TDX_PIPE_TRY(cudaEventRecord(hp.ev_kernel[c], hp.s_comp));
         // ---- device -> host

@@ -163,9 +163,9 @@ class BatchedEK1(odefilter.ODEFilter):
         per call would cost more than the step), so a returned state stays valid for ONE further host attempt."""
         n, d = state.y.mean.shape
         sets = getattr(self, "_host_out", None)
-        if sets is None or sets[0][0].shape != (n, d):
+        if sets is None or sets[0][0].shape != (n, d) or sets[0][0].dtype != state.y.mean.dtype:
             def pinned(shape):
-                return torch.empty(shape, dtype=self.dtype, pin_memory=True)
+                return torch.empty(shape, dtype=state.y.mean.dtype, pin_memory=True)
             sets = [(pinned((n, d)), pinned((d, n, n))) for _ in range(2)]
             self._host_out, self._host_turn = sets, 0
         mean_out, sc_out = sets[self._host_turn]
