@@ -350,9 +350,10 @@ def e2e_host_buffers(torch, sol, state, dt, problem, world, dev, d, k):
     """Same metric through the public attempt_step with the state in HOST (pinned) memory: every step moves the whole
     input state host->device and the whole output state (+ the error norm) device->host.
 
-    DiagonalEK1, one GPU: the library's host-buffer entry point (tdx_dek1_attempt_step_host) streams the state through
-    the device in chunks with the copies in both directions overlapping the kernels.  KroneckerEK0 and sharded runs:
-    plain copy-in / step / copy-out around the device-resident call."""
+    DiagonalEK1: the library's host-buffer entry point (tdx_dek1_attempt_step_host[_sharded]) streams the (shard of the)
+    state through the device in chunks with the copies in both directions overlapping the kernels; a sharded run first
+    exchanges the halos of the shards' edge rows.  KroneckerEK0: plain copy-in / step / copy-out around the device-resident
+    call."""
     from tornadox_b200 import ek1, odefilter, rv
 
     is_dek1 = isinstance(sol, ek1.DiagonalEK1)
@@ -361,11 +362,13 @@ def e2e_host_buffers(torch, sol, state, dt, problem, world, dev, d, k):
     h_mean_in = torch.empty(y.mean.shape, dtype=y.mean.dtype, pin_memory=True).copy_(y.mean)
     h_fac_in = torch.empty(fac.shape, dtype=fac.dtype, pin_memory=True).copy_(fac)
     h2d = h_mean_in.numel() * h_mean_in.element_size() + h_fac_in.numel() * h_fac_in.element_size()
-    pipelined = is_dek1 and world == 1
+    pipelined = is_dek1
 
     if pipelined:
         host_state = odefilter.ODEFilterState(state.t, rv.BatchedMultivariateNormal(h_mean_in, h_fac_in), None, None)
         vec_bytes = 2 * y.mean.shape[1] * y.mean.element_size() if sol.materialize_error_vectors else 0
+        if world > 1:   # + the shard's edge rows for the halo exchange that precedes the pipeline
+            h2d += 4 * problem.spec.grid_cols * y.mean.shape[0] * y.mean.element_size()
 
         def one():
             new, _ = sol.attempt_step(host_state, dt, *problem)      # synchronous: outputs are complete in host memory

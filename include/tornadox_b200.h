@@ -153,6 +153,14 @@ int tdx_dek1_attempt_step_host(tdx_ctx* ctx, const tdx_step_args* args, const vo
                                const void* sc_in, void* mean_out, void* sc_out, void* err_out,
                                void* ref_out, double* sq_norm_sum, int nchunks);
 
+/* The same for ONE SHARD of a multi-GPU run: the host arrays hold the shard's state ((n, d_local), (d_local, n, n)), and
+ * halo_lo / halo_hi are DEVICE buffers with the predicted edge state received from the neighbouring ranks (tdx_pack_halo of
+ * the shard's edge rows + the caller's exchange); sq_norm_sum receives the shard's partial sum (all-reduce it). */
+int tdx_dek1_attempt_step_host_sharded(tdx_ctx* ctx, const tdx_step_args* args, const void* mean_in,
+                                       const void* sc_in, void* mean_out, void* sc_out, void* err_out,
+                                       void* ref_out, const void* halo_lo, const void* halo_hi,
+                                       double* sq_norm_sum, int nchunks);
+
 /* KroneckerEK0.attempt_step (ek0.py:152-193) in three phases, so that a multi-GPU caller can
  * all-reduce the device scalar between them:
  *  sweep_a : predict + measure, writes sum_i z_i^2 over the local shard to ``z_sq_sum`` (double);

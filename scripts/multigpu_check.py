@@ -66,6 +66,13 @@ def main():
             e_norm = abs(norm - ref_norm) / abs(ref_norm)
             worst = max(worst, e_mean, e_cov, e_err, e_norm)
             assert max(e_mean, e_cov, e_err, e_norm) < 1e-10, (kind, size, name, dt, e_mean, e_cov, e_err, e_norm)
+            if name == "dek1":
+                # the shard's state in HOST memory: halo exchange of the edge rows + chunked pipeline must reproduce the same bits
+                pin = lambda x: torch.empty(x.shape, dtype=x.dtype, pin_memory=True).copy_(x)
+                hm, hs, herr, href, hsq = eng.dek1_attempt_host(0.3, dt, pin(y.mean), pin(y.cov_sqrtm), 1e-4, 1e-2, nchunks=3)
+                assert torch.equal(hm, st.y.mean.cpu()) and torch.equal(hs, st.y.cov_sqrtm.cpu()), (kind, size, "host path")
+                assert torch.equal(herr, st.error_estimate.cpu()), (kind, size, "host path err")
+                assert abs(math.sqrt(hsq / d) - norm) <= 1e-12 * norm, (kind, size, "host path norm")
             # f evaluation with halos
             yv = torch.as_tensor(o.y0[idx], device=dev)
             fy = eng.eval_f(0.0, yv)

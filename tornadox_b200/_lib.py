@@ -28,7 +28,7 @@ EXPORTED_SYMBOLS = (
     "tdx_last_error", "tdx_abi_version", "tdx_create", "tdx_destroy", "tdx_set_problem", "tdx_local_dim",
     "tdx_halo_sizes", "tdx_set_diffusion_sqrt", "tdx_prior", "tdx_nordsieck", "tdx_eval_f", "tdx_pack_halo", "tdx_dek1_attempt_step",
     "tdx_ek0_sweep_a", "tdx_ek0_mid", "tdx_ek0_sweep_b", "tdx_ek0_attempt_step", "tdx_launch_count",
-    "tdx_debug_read_workspace", "tdx_dek1_attempt_step_host", "tdx_dek1_full_step", "tdx_ek0_full_step", "tdx_propagate_cholesky_factor",
+    "tdx_debug_read_workspace", "tdx_dek1_attempt_step_host", "tdx_dek1_attempt_step_host_sharded", "tdx_dek1_full_step", "tdx_ek0_full_step", "tdx_propagate_cholesky_factor",
     "tdx_ctl_begin", "tdx_dek1_enqueue_attempts", "tdx_ek0_enqueue_attempts", "tdx_ctl_read", "tdx_comm_init", "tdx_comm_connect", "tdx_comm_pack_halo", "tdx_comm_allreduce", "tdx_comm_error",
 )
 
@@ -141,6 +141,7 @@ def load():
     lib.tdx_dek1_enqueue_attempts.argtypes = [vp, cint, ctypes.c_uint32] + [vp] * 7
     lib.tdx_ek0_enqueue_attempts.argtypes = [vp, cint, ctypes.c_uint32] + [vp] * 7
     lib.tdx_ctl_read.argtypes = [vp, ctypes.POINTER(CtlState), pd, pd, vp]
+    lib.tdx_dek1_attempt_step_host_sharded.argtypes = [vp, ctypes.POINTER(StepArgs)] + [vp] * 8 + [pd, cint]
     lib.tdx_ek0_sweep_a.argtypes = [vp, ctypes.POINTER(StepArgs), vp, vp, vp, vp, vp]
     lib.tdx_ek0_mid.argtypes = [vp, ctypes.POINTER(StepArgs), vp, vp, i64, vp, vp, vp]
     lib.tdx_ek0_sweep_b.argtypes = [vp, ctypes.POINTER(StepArgs), vp, vp, vp, vp, vp, vp, vp]

@@ -874,8 +874,8 @@ static int build_pipe(tdx_ctx* ctx, int nchunks_hint) {
         tdx_ctx* cc = nullptr;
         int rc = tdx_create(&cc, ctx->device, ctx->dtype);
         tdx_problem_desc d = ctx->desc;
-        d.shard_begin = b;
-        d.shard_end = en;
+        d.shard_begin = ctx->desc.shard_begin + b;     // sub-shards of the parent's own shard
+        d.shard_end = ctx->desc.shard_begin + en;
         if (!rc) rc = tdx_set_problem(cc, &d);
         if (rc) {
             tdx_destroy(cc);
@@ -922,14 +922,38 @@ static int build_pipe(tdx_ctx* ctx, int nchunks_hint) {
     return TDX_OK;
 }
 
+static int host_pipeline(tdx_ctx* ctx, const tdx_step_args* args, const void* h_mean_in, const void* h_sc_in, void* h_mean_out,
+                         void* h_sc_out, void* h_err_out, void* h_ref_out, double* h_sq_norm_sum, int nchunks,
+                         const void* ext_halo_lo, const void* ext_halo_hi);
+
 extern "C" int tdx_dek1_attempt_step_host(tdx_ctx* ctx, const tdx_step_args* args, const void* h_mean_in,
                                           const void* h_sc_in, void* h_mean_out, void* h_sc_out, void* h_err_out,
                                           void* h_ref_out, double* h_sq_norm_sum, int nchunks) {
     int rc = check_ready(ctx, "tdx_dek1_attempt_step_host");
     if (rc) return rc;
-    if ((rc = check_dt(args, "tdx_dek1_attempt_step_host"))) return rc;
     if (ctx->halo_lo > 0 || ctx->halo_hi > 0)
-        return fail(TDX_ERR_INVALID, "tdx_dek1_attempt_step_host: the context must own the whole problem (no sharding)");
+        return fail(TDX_ERR_INVALID, "tdx_dek1_attempt_step_host: the context must own the whole problem; a shard needs "
+                                     "tdx_dek1_attempt_step_host_sharded (halo buffers from its neighbours)");
+    return host_pipeline(ctx, args, h_mean_in, h_sc_in, h_mean_out, h_sc_out, h_err_out, h_ref_out, h_sq_norm_sum, nchunks, nullptr,
+                         nullptr);
+}
+
+extern "C" int tdx_dek1_attempt_step_host_sharded(tdx_ctx* ctx, const tdx_step_args* args, const void* h_mean_in,
+                                                  const void* h_sc_in, void* h_mean_out, void* h_sc_out, void* h_err_out,
+                                                  void* h_ref_out, const void* d_halo_lo, const void* d_halo_hi,
+                                                  double* h_sq_norm_sum, int nchunks) {
+    int rc = check_ready(ctx, "tdx_dek1_attempt_step_host_sharded");
+    if (rc) return rc;
+    if ((rc = check_halos(ctx, d_halo_lo, d_halo_hi, "tdx_dek1_attempt_step_host_sharded"))) return rc;
+    return host_pipeline(ctx, args, h_mean_in, h_sc_in, h_mean_out, h_sc_out, h_err_out, h_ref_out, h_sq_norm_sum, nchunks, d_halo_lo,
+                         d_halo_hi);
+}
+
+static int host_pipeline(tdx_ctx* ctx, const tdx_step_args* args, const void* h_mean_in, const void* h_sc_in, void* h_mean_out,
+                         void* h_sc_out, void* h_err_out, void* h_ref_out, double* h_sq_norm_sum, int nchunks,
+                         const void* ext_halo_lo, const void* ext_halo_hi) {
+    int rc = check_dt(args, "tdx_dek1_attempt_step_host");
+    if (rc) return rc;
     if (!h_mean_in || !h_sc_in || !h_mean_out || !h_sc_out) return fail(TDX_ERR_INVALID, "tdx_dek1_attempt_step_host: null state buffer");
     if (args->flags & ~TDX_STEP_ZERO_JACOBIAN) return fail(TDX_ERR_INVALID, "tdx_dek1_attempt_step_host: only TDX_STEP_ZERO_JACOBIAN is accepted");
     const bool want_norm = args->abstol != 0.0 || args->reltol != 0.0;
@@ -942,7 +966,8 @@ extern "C" int tdx_dek1_attempt_step_host(tdx_ctx* ctx, const tdx_step_args* arg
     const int n = ctx->n, nc = hp.nchunks;
     const size_t w = esize(ctx->dtype);
     const long long nn = (long long)n * n, npts = g.npts;
-    const bool cyclic = g.kind == IVP_LORENZ96 && nc > 1;
+    const bool parent_sharded = ctx->halo_lo > 0 || ctx->halo_hi > 0;
+    const bool cyclic = g.kind == IVP_LORENZ96 && nc > 1 && !parent_sharded;    // a shard's ends talk to other ranks, not to each other
     for (tdx_ctx* c : hp.ctx) std::memcpy(c->ql_packed, ctx->ql_packed, sizeof(ctx->ql_packed));   // tdx_set_diffusion_sqrt of the parent
 
     const unsigned char* hm_in = (const unsigned char*)h_mean_in;
@@ -994,8 +1019,10 @@ extern "C" int tdx_dek1_attempt_step_host(tdx_ctx* ctx, const tdx_step_args* arg
         pack(hi);
         TDX_PIPE_TRY(cudaStreamWaitEvent(hp.s_comp, hp.ev_fac[c], 0));
         if (c >= HostPipe::kSlots) TDX_PIPE_TRY(cudaStreamWaitEvent(hp.s_comp, hp.ev_d2h[c - HostPipe::kSlots], 0));
-        const void* halo_lo = (lo >= 0 && hp.ctx[c]->halo_lo > 0) ? hp.edge_last + (size_t)lo * hp.edge_cap * w : nullptr;
-        const void* halo_hi = (hi >= 0 && hp.ctx[c]->halo_hi > 0) ? hp.edge_first + (size_t)hi * hp.edge_cap * w : nullptr;
+        // stencil neighbours beyond the chunk: the adjacent chunk's packed edge, or (first / last chunk of a shard) the halo the
+        // caller received from the neighbouring rank
+        const void* halo_lo = hp.ctx[c]->halo_lo > 0 ? (lo >= 0 ? hp.edge_last + (size_t)lo * hp.edge_cap * w : ext_halo_lo) : nullptr;
+        const void* halo_hi = hp.ctx[c]->halo_hi > 0 ? (hi >= 0 ? hp.edge_first + (size_t)hi * hp.edge_cap * w : ext_halo_hi) : nullptr;
         if (e == cudaSuccess) {
             rc = tdx_dek1_attempt_step(hp.ctx[c], args, dmean(hp.mean_in, c), hp.fac_in[slot], dmean(hp.mean_out, c), hp.fac_out[slot],
                                        h_err_out ? dvec(hp.err, c) : nullptr, h_ref_out ? dvec(hp.ref, c) : nullptr, halo_lo, halo_hi,

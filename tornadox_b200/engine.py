@@ -340,8 +340,6 @@ class StepEngine:
         """One DiagonalEK1 attempt on a state in HOST memory (CPU tensors, pinned for full PCIe speed): the library streams
         the state through the GPU in chunks, copies in both directions overlapping the kernels (``tdx_dek1_attempt_step_host``).
         Returns (mean_out, sc_out, err, ref, sq_norm_sum[float]) as CPU tensors; synchronous."""
-        if self.world != 1:
-            raise ValueError("the host-buffer path needs an unsharded solver (one GPU owns the whole problem)")
         n, d = self.n, self.d_local
         for x, shape, name in ((mean, (n, d), "mean"), (sc, (d, n, n), "cov_sqrtm")):
             if not isinstance(x, torch.Tensor) or x.device.type != "cpu" or x.dtype != self.dtype:
@@ -358,9 +356,33 @@ class StepEngine:
         ref = host_empty((d,)) if want_err_ref else None
         sq = ctypes.c_double(0.0)
         args = self._args(t, dt, abstol, reltol, 0 if jacobian else _lib.TDX_STEP_ZERO_JACOBIAN)
+        if self.world > 1:
+            # one shard of a multi-GPU run: the stencil halos of the shard's edges have to come from the neighbouring ranks
+            # first -- upload just the edge rows / points, pack, exchange -- then the shard streams through its own pipeline
+            halo_lo, halo_hi = self._exchange_halos_of_host_mean(dt, mean)
+            torch.cuda.current_stream(self.device).synchronize()      # the library's pipeline runs on its own streams
+            _lib.check(self.lib.tdx_dek1_attempt_step_host_sharded(
+                self.handle, ctypes.byref(args), _ptr(mean), _ptr(sc), _ptr(mean_out), _ptr(sc_out), _ptr(err), _ptr(ref),
+                _ptr(halo_lo), _ptr(halo_hi), ctypes.byref(sq), int(nchunks)))
+            total = torch.tensor([sq.value], dtype=torch.float64, device=self.device)
+            self.all_reduce_(total)
+            return mean_out, sc_out, err, ref, float(total.item())
         _lib.check(self.lib.tdx_dek1_attempt_step_host(self.handle, ctypes.byref(args), _ptr(mean), _ptr(sc), _ptr(mean_out),
                                                        _ptr(sc_out), _ptr(err), _ptr(ref), ctypes.byref(sq), int(nchunks)))
         return mean_out, sc_out, err, ref, sq.value
+
+    def _exchange_halos_of_host_mean(self, dt, host_mean):
+        """Predicted edge state of a HOST-resident shard mean, exchanged with the neighbouring ranks: only the shard's first
+        and last grid row (fhn_2d) / two points (chains) of every derivative row travel to the device for this."""
+        n, d = self.n, self.d_local
+        if getattr(self, "_edge_mean_dev", None) is None:
+            self._edge_mean_dev = torch.zeros((n, d), dtype=self.dtype, device=self.device)
+        npts = d // self.spec.n_fields
+        width = self.spec.grid_cols if self.spec.kind == _lib.TDX_IVP_FHN2D else min(2, npts)
+        for f in range(self.spec.n_fields):
+            for a in (f * npts, f * npts + npts - width):
+                self._edge_mean_dev[:, a:a + width].copy_(host_mean[:, a:a + width], non_blocking=True)
+        return self._halos_for_mean(dt, self._edge_mean_dev)
 
     # ---- native accept / reject loop (odefilter.py:171-223 inside the library) --------------------------------------
     def native_steprule(self, steprule):
