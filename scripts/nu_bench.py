@@ -6,7 +6,7 @@ from tornadox_b200 import ivp
 from tornadox_b200.engine import StepEngine
 g = torch.Generator(device="cuda").manual_seed(0)
 size = 2048; d = 2 * size * size
-for nu in (1, 2, 3, 4, 5):
+for nu in ([int(a) for a in sys.argv[1:]] or (1, 2, 3, 4, 5)):
     n = nu + 1
     eng = StepEngine(ivp.fhn_2d(dx=1/size, y0=np.zeros(2)).spec, nu, device="cuda:0")
     mean = torch.rand((n, d), generator=g, device="cuda", dtype=torch.float64)

@@ -580,6 +580,10 @@ __device__ __forceinline__ void cp_async_elem(double* smem_dst, const double* gm
 __device__ __forceinline__ void cp_async_elem(float* smem_dst, const float* gmem_src) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
 }
+// 16 bytes, L2 only (both addresses 16-byte aligned)
+__device__ __forceinline__ void cp_async_unit(void* smem_dst, const void* gmem_src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int kPending>
 __device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(kPending) : "memory"); }

@@ -31,8 +31,17 @@ __device__ __forceinline__ T nanmax(T a, T b) { return (a > b || a != a) ? a : b
 template <typename T, int N>
 struct SmemLayout {
     static constexpr int NN = N * N;
-    // odd stride (in elements) => conflict-free one-block-per-lane access; even n^2 gets one pad element
-    static constexpr int STRIDE = (NN % 2 == 1) ? NN : NN + 1;
+    // One (n, n) block per lane.  Odd n: the block stride is n^2 elements (odd => conflict-free element accesses).
+    // Even n: a block is a whole number of 16-byte units; it is accessed with 128-bit loads / stores only and its stride is
+    // padded to an ODD number of units (=> conflict-free within every quarter-warp phase of a 128-bit access).
+#ifdef TDX_PAD_ELEMENTWISE
+    static constexpr bool VEC = false;
+#else
+    static constexpr bool VEC = (N % 2 == 0);
+#endif
+    static constexpr int PER_UNIT = 16 / (int)sizeof(T);            // elements per 16-byte unit
+    static constexpr int UNITS = NN / PER_UNIT;                     // units per block (VEC only)
+    static constexpr int STRIDE = VEC ? ((UNITS | 1) * PER_UNIT) : ((NN % 2 == 1) ? NN : NN + 1);
     static constexpr int SC_ELEMS = kWarps * 32 * STRIDE;
     static constexpr size_t BAR_BYTES = 128;                       // kWarps mbarriers, padded
     static constexpr size_t RED_BYTES = 128;                       // kWarps doubles, padded
@@ -42,6 +51,47 @@ struct SmemLayout {
         return BAR_BYTES + RED_BYTES + at_bytes(at_elems) + (with_sc ? sc_bytes() : 0);
     }
 };
+
+// 128-bit shared-memory access to a lane's block (even n, see SmemLayout): the whole block to / from registers
+template <typename T, int NN>
+__device__ __forceinline__ void block_load_vec(const T* blk, T (&v)[NN]) {
+    constexpr int PER = 16 / (int)sizeof(T);
+    const uint4* src = reinterpret_cast<const uint4*>(blk);
+#pragma unroll
+    for (int u = 0; u < NN / PER; ++u) {
+        const uint4 q = src[u];
+        if constexpr (sizeof(T) == 8) {
+            v[2 * u] = (T)__hiloint2double((int)q.y, (int)q.x);
+            v[2 * u + 1] = (T)__hiloint2double((int)q.w, (int)q.z);
+        } else {
+            v[4 * u] = (T)__uint_as_float(q.x);
+            v[4 * u + 1] = (T)__uint_as_float(q.y);
+            v[4 * u + 2] = (T)__uint_as_float(q.z);
+            v[4 * u + 3] = (T)__uint_as_float(q.w);
+        }
+    }
+}
+template <typename T, int NN>
+__device__ __forceinline__ void block_store_vec(T* blk, const T (&v)[NN]) {
+    constexpr int PER = 16 / (int)sizeof(T);
+    uint4* dst = reinterpret_cast<uint4*>(blk);
+#pragma unroll
+    for (int u = 0; u < NN / PER; ++u) {
+        uint4 q;
+        if constexpr (sizeof(T) == 8) {
+            q.x = (unsigned)__double2loint((double)v[2 * u]);
+            q.y = (unsigned)__double2hiint((double)v[2 * u]);
+            q.z = (unsigned)__double2loint((double)v[2 * u + 1]);
+            q.w = (unsigned)__double2hiint((double)v[2 * u + 1]);
+        } else {
+            q.x = __float_as_uint((float)v[4 * u]);
+            q.y = __float_as_uint((float)v[4 * u + 1]);
+            q.z = __float_as_uint((float)v[4 * u + 2]);
+            q.w = __float_as_uint((float)v[4 * u + 3]);
+        }
+        dst[u] = q;
+    }
+}
 
 // A launch processes the tiles [b0, b0 + n0) followed by [b1, b1 + n1) (interior / rim split for multi-GPU overlap).
 // Tiles from virtual index ``wait_from`` on read the halo buffers: a CTA waits for the arrival flags when it gets there.
@@ -298,11 +348,22 @@ __global__ void __launch_bounds__(kThreads, TDX_MIN_BLOCKS) dek1_kernel(const __
                 bulk_g2s(dst, sc_in + off, (uint32_t)(32 * NN * sizeof(T)), bar);
             }
         } else {
-            const int total = co.seg_len * NN;
-            for (int e = lane; e < total; e += 32) {
-                const int blk = e / NN;
-                dst[blk * STRIDE + (e - blk * NN)] = __ldg(sc_in + off + e);
+            // padded layout: element-wise asynchronous copies (LDGSTS), one group per tile; they land while the current
+            // tile is being factorised
+            if (L::VEC && (reinterpret_cast<uintptr_t>(sc_in) & 15) == 0) {      // 16-byte units, L1 bypassed
+                const int total = co.seg_len * L::UNITS;
+                for (int u = lane; u < total; u += 32) {
+                    const int blk = u / L::UNITS;
+                    cp_async_unit(dst + blk * STRIDE + (u - blk * L::UNITS) * L::PER_UNIT, sc_in + off + (long long)u * L::PER_UNIT);
+                }
+            } else {
+                const int total = co.seg_len * NN;
+                for (int e = lane; e < total; e += 32) {
+                    const int blk = e / NN;
+                    cp_async_elem(dst + blk * STRIDE + (e - blk * NN), sc_in + off + e);
+                }
             }
+            cp_async_commit();
         }
         return bulk;
     };
@@ -376,11 +437,13 @@ __global__ void __launch_bounds__(kThreads, TDX_MIN_BLOCKS) dek1_kernel(const __
             // B = A (p_inv * sc)   ek1.py:233,269
             T B[N][N];
             T* blk = my_sc + lane * STRIDE;
+            T blkv[L::VEC ? NN : 1];           // even n: the block travels through registers, 128 bits per access
+            if constexpr (L::VEC) block_load_vec<T, NN>(blk, blkv);
 #pragma unroll
             for (int j = 0; j < N; ++j) {
                 T col[N];
 #pragma unroll
-                for (int k = 0; k < N; ++k) col[k] = c.pinv[k] * blk[k * N + j];
+                for (int k = 0; k < N; ++k) col[k] = c.pinv[k] * (L::VEC ? blkv[L::VEC ? k * N + j : 0] : blk[k * N + j]);
 #pragma unroll
                 for (int i = 0; i < N; ++i) {
                     T acc = col[i];
@@ -408,15 +471,17 @@ __global__ void __launch_bounds__(kThreads, TDX_MIN_BLOCKS) dek1_kernel(const __
                 const T l1 = (r >= 1) ? B[r][1] : (T)0;
                 const T kg = (l0 * g0 + l1 * g1) * inv_s2;
                 const T pr = c.p[r];
-                blk[r * N + 0] = pr * (l0 - kg * g0);
-                blk[r * N + 1] = pr * (l1 - kg * g1);
+                T* row = L::VEC ? (blkv + (L::VEC ? r * N : 0)) : (blk + r * N);
+                row[0] = pr * (l0 - kg * g0);
+                row[1] = pr * (l1 - kg * g1);
 #pragma unroll
-                for (int cc = 2; cc < N; ++cc) blk[r * N + cc] = (r >= cc) ? pr * B[r][cc] : (T)0;
+                for (int cc = 2; cc < N; ++cc) row[cc] = (r >= cc) ? pr * B[r][cc] : (T)0;
                 const T mo = pr * (mp[r] - kg * z);
                 *mo_ptr = mo;
                 mo_ptr += g.d;
                 if (r == 0) new_m0 = mo;
             }
+            if constexpr (L::VEC) block_store_vec<T, NN>(blk, blkv);
             const T ref = nanmax<T>(tabs<T>(raw0), tabs<T>(new_m0));   // ek1.py:249-251
             if (a.err_out) a.err_out[cur.flat] = err;
             if (a.ref_out) a.ref_out[cur.flat] = ref;
@@ -436,10 +501,19 @@ __global__ void __launch_bounds__(kThreads, TDX_MIN_BLOCKS) dek1_kernel(const __
             }
         } else {
             __syncwarp();
-            const int total = cur.seg_len * NN;
-            for (int e = lane; e < total; e += 32) {
-                const int b = e / NN;
-                sc_out[sc_off + e] = my_sc[b * STRIDE + (e - b * NN)];
+            if (L::VEC && (reinterpret_cast<uintptr_t>(sc_out) & 15) == 0) {
+                const int total = cur.seg_len * L::UNITS;
+                uint4* out_units = reinterpret_cast<uint4*>(sc_out + sc_off);
+                for (int u = lane; u < total; u += 32) {
+                    const int b = u / L::UNITS;
+                    out_units[u] = *reinterpret_cast<const uint4*>(my_sc + b * STRIDE + (u - b * L::UNITS) * L::PER_UNIT);
+                }
+            } else {
+                const int total = cur.seg_len * NN;
+                for (int e = lane; e < total; e += 32) {
+                    const int b = e / NN;
+                    sc_out[sc_off + e] = my_sc[b * STRIDE + (e - b * NN)];
+                }
             }
         }
         if (SC_SLOTS == 1 && next < a.num_tiles) {
