@@ -163,3 +163,34 @@ def test_awkward_fhn_grids(cuda_device, size):
         assert_close(m1.cpu().numpy(), ref1.mean, FP64_RTOL, "dek1 mean")
         assert_close(s1.cpu().numpy(), ref1.cov_sqrtm, FP64_RTOL, "dek1 cov_sqrtm")
         assert_close(err1.cpu().numpy(), ref1.error_estimate, FP64_RTOL, "dek1 error_estimate")
+
+
+@pytest.mark.parametrize("kind,size", [("fhn_2d", 64), ("lorenz96", 4099)])
+@pytest.mark.parametrize("nu", [1, 2, 3, 4, 5])
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+def test_dek1_factor_buffers_without_16_byte_alignment(cuda_device, kind, size, nu, dtype):
+    """Caller-owned buffers need element alignment only: factor arrays that start one element past a 16-byte boundary take
+    the element-wise staging routes (no TMA bulk copies, no 16-byte units) and must give the same bits as aligned ones."""
+    o, p, _ = make_pair(kind, size)
+    n, d = nu + 1, o.y0.shape[0]
+    rng = np.random.default_rng(7 * nu + size)
+    mean, sc = random_state(rng, n, d, "dense")
+    mean[0] = o.y0 + 0.05 * rng.standard_normal(d)
+    dt = 0.0123 if kind != "fhn_2d" else 1e-3
+    eng = _engine(p, nu, dtype)
+    m_in, sc_in = _t(mean, dtype), _t(sc, dtype)
+    m0, s0, e0, r0, q0 = eng.dek1_attempt(0.3, dt, m_in, sc_in, abstol=1e-4, reltol=1e-2)
+
+    def shifted(x):
+        buf = torch.empty(x.numel() + 1, dtype=x.dtype, device=x.device)
+        view = buf[1:].view(x.shape)
+        view.copy_(x)
+        assert view.data_ptr() % 16 != 0
+        return view
+
+    sc_shift, out_shift = shifted(sc_in), shifted(torch.zeros_like(sc_in))
+    m1, s1, e1, r1, q1 = eng.dek1_attempt(0.3, dt, m_in, sc_shift, abstol=1e-4, reltol=1e-2, sc_out=out_shift)
+    assert s1.data_ptr() == out_shift.data_ptr()
+    for a, b, name in ((m0, m1, "mean"), (s0, s1, "cov_sqrtm"), (e0, e1, "error_estimate"), (r0, r1, "reference_state")):
+        assert torch.equal(a, b), name
+    assert float(q0.sum()) == float(q1.sum())
