@@ -46,12 +46,14 @@ extern "C" {
 #define TDX_F32 1
 
 /* vector fields evaluated in-kernel (tornadox/ivp.py) */
-#define TDX_IVP_VANDERPOL 0   /* params: [mu]                        ivp.py:28-49   */
+#define TDX_IVP_VANDERPOL 0   /* params: [mu] or [mu, 1] (vanderpol_julia, ivp.py:52-73)   ivp.py:28-49 */
 #define TDX_IVP_LORENZ96 1    /* params: [forcing]                   ivp.py:268-294 */
 #define TDX_IVP_BRUSSELATOR 2 /* params: [] (c derived from N)       ivp.py:219-265 */
 #define TDX_IVP_FHN2D 3       /* params: [dx, a, b, k, tau]          ivp.py:409-505 */
 #define TDX_IVP_BURGERS1D 4   /* params: [dx, diffusion_param]       ivp.py:76-107  (one GPU only) */
 #define TDX_IVP_WAVE1D 5      /* params: [dx, diffusion_param]       ivp.py:110-140 (one GPU only) */
+#define TDX_IVP_THREEBODY 6   /* params: []   grid_cols = 4          ivp.py:188-216 (one GPU only) */
+#define TDX_IVP_PLEIADES 7    /* params: []   grid_cols = 28         ivp.py:344-406 (one GPU only) */
 
 typedef struct tdx_ctx tdx_ctx;
 

@@ -212,6 +212,12 @@ def taylor_function(name, fn, args, kwargs):
             zero_kw["constant_values"] = 0.0
             return TaylorArray(np.stack([fn(x.c[k], *args[1:], **(kwargs if k == 0 else zero_kw)) for k in range(order)]))
         return TaylorArray(np.stack([fn(x.c[k], *args[1:], **kwargs) for k in range(order)]))
+    if name == "nan_to_num":
+        # jnp.nan_to_num is select(isnan(x), 0, x) (+ the same for the infinities); jet's select rule applies the PRIMAL's
+        # predicate to every Taylor coefficient, and the constant branch has a zero series
+        x = args[0]
+        bad = ~np.isfinite(x.c[0])
+        return TaylorArray(np.stack([fn(x.c[0], *args[1:], **kwargs)] + [np.where(bad, 0.0, x.c[k]) for k in range(1, order)]))
     raise NotImplementedError(f"jnp.{name} has no Taylor-mode rule in the shim")
 
 

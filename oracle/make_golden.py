@@ -2,6 +2,7 @@
 (/root/reference/tornadox) on the NumPy-backed jax shim (oracle/jaxshim).
 
     python oracle/make_golden.py          # only works in the build container, where /root/reference exists
+    python oracle/make_golden.py --small  # reference_vectors_small.npz: vanderpol_julia, threebody, pleiades, lorenz96_loop
 
 The fixtures pin (i) the NumPy restatement in oracle/ref_np and (ii) the CUDA kernels against outputs of the
 reference's own code: prior constants, vector fields and Jacobian diagonals, Taylor-mode initial states,
@@ -20,6 +21,7 @@ sys.path.insert(0, str(ROOT))
 from oracle.run_reference import import_reference  # noqa: E402
 
 OUT = ROOT / "tests" / "golden" / "reference_vectors.npz"
+OUT_SMALL = ROOT / "tests" / "golden" / "reference_vectors_small.npz"      # python oracle/make_golden.py --small
 
 
 def problems(tornadox):
@@ -35,6 +37,16 @@ def problems(tornadox):
     out["fhn_2d"] = (tornadox.ivp.fhn_2d(t0=0.0, tmax=0.05, y0=jnp.array(y0), dx=0.2), dict(dx=0.2, nx=5))
     out["burgers_1d"] = (tornadox.ivp.burgers_1d(t0=0.0, tmax=0.05, dx=0.1), dict(dx=0.1))
     out["wave_1d"] = (tornadox.ivp.wave_1d(t0=0.0, tmax=0.05, dx=0.1), dict(dx=0.1))
+    return out
+
+
+def small_problems(tornadox):
+    """The reference's remaining (small, dense) problems; kept in a file of their own (``--small``)."""
+    out = {}
+    out["vanderpol_julia"] = (tornadox.ivp.vanderpol_julia(t0=0.0, tmax=0.5, stiffness_constant=2.0), dict(mu=2.0))
+    out["threebody"] = (tornadox.ivp.threebody(tmax=0.02), dict())
+    out["pleiades"] = (tornadox.ivp.pleiades(t0=0.0, tmax=0.2), dict())
+    out["lorenz96_loop"] = (tornadox.ivp.lorenz96_loop(t0=0.0, tmax=0.3, num_variables=6, forcing=8.0), dict(N=6, forcing=8.0))
     return out
 
 
@@ -57,15 +69,15 @@ def _outputs(a, b, sname):
             ("reference_state", a.reference_state, b.reference_state)]
 
 
-def main():
+def main(small=False):
     tornadox = import_reference()
     import jax.numpy as jnp
 
     g = {}
-    rng = np.random.default_rng(11)
+    rng = np.random.default_rng(12 if small else 11)
 
     # ---- prior constants (iwp.py:19-37, 65-73) ---------------------------------------------------
-    for nu in (1, 2, 3, 4, 5):
+    for nu in (() if small else (1, 2, 3, 4, 5)):
         iwp = tornadox.iwp.IntegratedWienerTransition(wiener_process_dimension=1, num_derivatives=nu)
         A, Ql = iwp.preconditioned_discretize_1d
         g[f"prior/nu{nu}/A"], g[f"prior/nu{nu}/Ql"] = np.asarray(A), np.asarray(Ql)
@@ -73,7 +85,7 @@ def main():
             p, pinv = iwp.nordsieck_preconditioner_1d_raw(dt)
             g[f"prior/nu{nu}/p/{dt}"], g[f"prior/nu{nu}/pinv/{dt}"] = np.asarray(p), np.asarray(pinv)
 
-    probs = problems(tornadox)
+    probs = small_problems(tornadox) if small else problems(tornadox)
     for name, (ivp, facts) in probs.items():
         y0 = np.asarray(ivp.y0, dtype=float)
         g[f"ivp/{name}/y0"] = y0
@@ -102,7 +114,9 @@ def main():
             g[f"init/{name}/nu{nu}/rk_noise_cov_sqrtm"] = np.asarray(np.max(np.abs(np.asarray(sc_w) - np.asarray(sc_rk))))
             dts = {"vanderpol": [0.0123, 0.05, 0.02], "lorenz96": [0.01, 0.02, 0.005],
                    "brusselator": [0.02, 0.05, 0.01], "fhn_2d": [0.01, 0.03, 0.01],
-                   "burgers_1d": [0.01, 0.02, 0.005], "wave_1d": [0.01, 0.03, 0.01]}[name]
+                   "burgers_1d": [0.01, 0.02, 0.005], "wave_1d": [0.01, 0.03, 0.01],
+                   "vanderpol_julia": [0.0123, 0.05, 0.02], "threebody": [1e-3, 2e-3, 5e-4],
+                   "pleiades": [0.01, 0.02, 0.005], "lorenz96_loop": [0.01, 0.02, 0.005]}[name]
             g[f"steps/{name}/dts"] = np.asarray(dts)
             solvers = {
                 "dek1": tornadox.ek1.DiagonalEK1,
@@ -139,7 +153,7 @@ def main():
         blocks = 1e-2 * rng.standard_normal((d, n, n))
         single = 1e-2 * rng.standard_normal((n, n))
         dt = {"vanderpol": 0.0123, "lorenz96": 0.01, "brusselator": 1e-4, "fhn_2d": 1e-3, "burgers_1d": 1e-3,
-              "wave_1d": 1e-3}[name]
+              "wave_1d": 1e-3, "vanderpol_julia": 0.0123, "threebody": 1e-3, "pleiades": 0.01, "lorenz96_loop": 0.01}[name]
         g[f"dense/{name}/mean"], g[f"dense/{name}/blocks"], g[f"dense/{name}/single"] = mean, blocks, single
         g[f"dense/{name}/dt"] = np.asarray(dt)
         sol = tornadox.ek1.DiagonalEK1(num_derivatives=nu)
@@ -177,6 +191,17 @@ def main():
             g[key + "/info"] = np.asarray([info[k] for k in ("num_f_evaluations", "num_df_evaluations",
                                                               "num_df_diagonal_evaluations", "num_steps",
                                                               "num_attempted_steps")])
+            if small:
+                # conditioning probe: how far do the reference's own accepted times move when y0 changes by ~1 ulp?  (the
+                # controller feeds every rounding difference of the error norm into all later steps; threebody starts next
+                # to a singularity)  inf = the perturbed solve took a different number of steps
+                worst = 0.0
+                for _ in range(4):
+                    yw = jnp.array(y0 * (1.0 + 2.0 ** -52 * rng.uniform(-1, 1, size=y0.shape)))
+                    tw = [float(st.t) for st, _ in sol.solution_generator(ivp._replace(y0=yw))]
+                    same = len(tw) == len(ts)
+                    worst = max(worst, float(np.max(np.abs(np.asarray(tw)[1:] / np.asarray(ts)[1:] - 1.0))) if same else np.inf)
+                g[key + "/ts_noise"] = np.asarray(worst)
         # ConstantSteps counters (tests/test_ek0.py:70-82, tests/test_ek1.py:65-78)
         sol = tornadox.ek1.DiagonalEK1(num_derivatives=3, steprule=tornadox.step.ConstantSteps(dt))
         ivp5 = ivp._replace(tmax=ivp.t0 + 5.0 * dt - 1e-12 * dt) if hasattr(ivp, "_replace") else ivp
@@ -186,16 +211,18 @@ def main():
         g[f"solve/{name}/dek1_const/num_steps"] = np.asarray(info["num_steps"])
 
     # step rule scalars (step.py:76-104)
-    rule = tornadox.step.AdaptiveSteps(abstol=1e-3, reltol=1e-1)
-    err, ref = rng.uniform(size=7), rng.uniform(size=7) + 0.5
-    g["step/err"], g["step/ref"] = err, ref
-    g["step/scaled"] = np.asarray(rule.scale_error_estimate(jnp.array(err), jnp.array(ref)))
-    g["step/suggest"] = np.asarray([rule.suggest(0.1, e, local_convergence_rate=5) for e in (1e-8, 0.3, 1.0, 7.0, 1e9)])
+    if not small:
+        rule = tornadox.step.AdaptiveSteps(abstol=1e-3, reltol=1e-1)
+        err, ref = rng.uniform(size=7), rng.uniform(size=7) + 0.5
+        g["step/err"], g["step/ref"] = err, ref
+        g["step/scaled"] = np.asarray(rule.scale_error_estimate(jnp.array(err), jnp.array(ref)))
+        g["step/suggest"] = np.asarray([rule.suggest(0.1, e, local_convergence_rate=5) for e in (1e-8, 0.3, 1.0, 7.0, 1e9)])
 
-    OUT.parent.mkdir(parents=True, exist_ok=True)
-    np.savez_compressed(OUT, **g)
-    print(f"wrote {OUT} with {len(g)} arrays, {OUT.stat().st_size / 1024:.0f} KiB")
+    out = OUT_SMALL if small else OUT
+    out.parent.mkdir(parents=True, exist_ok=True)
+    np.savez_compressed(out, **g)
+    print(f"wrote {out} with {len(g)} arrays, {out.stat().st_size / 1024:.0f} KiB")
 
 
 if __name__ == "__main__":
-    main()
+    main(small="--small" in sys.argv)

@@ -316,6 +316,13 @@ def series_vanderpol(mu):
     return f
 
 
+def series_vanderpol_julia(mu):
+    def f(_, Y):
+        return series_stack([Y[1], mu * ((1.0 - Y[0] ** 2) * Y[1] - Y[0])], Y.order)
+
+    return f
+
+
 def series_lorenz96(forcing):
     def f(_, y):
         A = y.linear(lambda c: np.roll(c, -1))
@@ -398,6 +405,28 @@ def series_threebody():
         y1p = Y[0] + 2 * Y[3] - mp * (Y[0] + mu) / D1 - mu * (Y[0] - mp) / D2
         y2p = Y[1] - 2 * Y[2] - mp * Y[1] / D1 - mu * Y[1] / D2
         return series_stack([Y[2], Y[3], y1p, y2p], Y.order)
+
+    return f
+
+
+def series_pleiades():
+    """tornadox/ivp.py:344-406 on Series arguments; the self-interaction terms (0/0 -> 0 in the reference) are skipped."""
+
+    def f(_, u):
+        comps = [u[14 + k] for k in range(14)]
+        acc = {}
+        for i in range(7):
+            ddx, ddy = 0.0, 0.0
+            for j in range(7):
+                if i == j:
+                    continue
+                dxs, dys = u[j] - u[i], u[7 + j] - u[7 + i]
+                r3 = (dxs ** 2 + dys ** 2) ** (3 / 2)
+                ddx = ddx + (j + 1) * dxs / r3
+                ddy = ddy + (j + 1) * dys / r3
+            acc[i] = (ddx, ddy)
+        comps += [acc[i][0] for i in range(7)] + [acc[i][1] for i in range(7)]
+        return series_stack(comps, u.order)
 
     return f
 

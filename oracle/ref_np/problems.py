@@ -1,7 +1,8 @@
 """ORACLE (test infrastructure): NumPy restatement of the in-scope vector fields of ``tornadox/ivp.py``.
 
-vanderpol (ivp.py:28-49), burgers_1d (ivp.py:76-107), wave_1d (ivp.py:110-140), brusselator (ivp.py:219-265),
-lorenz96 (ivp.py:268-294, 335-341), fhn_2d (ivp.py:409-481) with its 5-point Neumann Laplacian (ivp.py:484-505).
+vanderpol (ivp.py:28-49), vanderpol_julia (ivp.py:52-73), burgers_1d (ivp.py:76-107), wave_1d (ivp.py:110-140),
+threebody (ivp.py:188-216), brusselator (ivp.py:219-265), lorenz96 (ivp.py:268-294, 335-341), lorenz96_loop (ivp.py:298-332),
+pleiades (ivp.py:344-406), fhn_2d (ivp.py:409-481) with its 5-point Neumann Laplacian (ivp.py:484-505).
 Each factory returns ``Problem(f, t0, tmax, y0, df, df_diagonal)`` -- the field order of the
 reference's ``InitialValueProblem`` namedtuple (ivp.py:10-25).  ``df`` (dense Jacobian, the
 reference gets it from ``jax.jacfwd``) is built analytically and is only meant for small d.
@@ -30,6 +31,91 @@ def vanderpol(t0=0.0, tmax=30, y0=None, stiffness_constant=1e1):
         return np.array([0.0, mu * (1.0 - Y[0] ** 2)])
 
     return Problem(f, t0, tmax, y0, df, df_diagonal)
+
+
+def vanderpol_julia(t0=0.0, tmax=6.3, y0=None, stiffness_constant=1e1):
+    """ivp.py:52-73: mu scales the whole second component."""
+    mu = stiffness_constant
+    y0 = np.array([2.0, 0.0]) if y0 is None else np.asarray(y0, dtype=float)
+
+    def f(_, Y):
+        return np.array([Y[1], mu * ((1.0 - Y[0] ** 2) * Y[1] - Y[0])])
+
+    def df(_, Y):
+        return np.array([[0.0, 1.0], [mu * (-2.0 * Y[0] * Y[1] - 1.0), mu * (1.0 - Y[0] ** 2)]])
+
+    def df_diagonal(_, Y):
+        return np.array([0.0, mu * (1.0 - Y[0] ** 2)])
+
+    return Problem(f, t0, tmax, y0, df, df_diagonal)
+
+
+def threebody(tmax=17.0652165601579625588917206249):
+    """ivp.py:188-216 (restricted three-body problem, Y = [y1, y2, y1', y2']); the reference DEFINES its Jacobian diagonal
+    as zero (:204-205)."""
+    mu = 0.012277471
+    mp = 1 - mu
+
+    def f(_, Y):
+        D1 = ((Y[0] + mu) ** 2 + Y[1] ** 2) ** (3 / 2)
+        D2 = ((Y[0] - mp) ** 2 + Y[1] ** 2) ** (3 / 2)
+        y1p = Y[0] + 2 * Y[3] - mp * (Y[0] + mu) / D1 - mu * (Y[0] - mp) / D2
+        y2p = Y[1] - 2 * Y[2] - mp * Y[1] / D1 - mu * Y[1] / D2
+        return np.array([Y[2], Y[3], y1p, y2p])
+
+    def df(t, Y):
+        return _dense_jacobian(f, t, np.asarray(Y, dtype=float))
+
+    def df_diagonal(*args, **kwargs):
+        return np.array([0.0, 0.0, 0.0, 0.0])
+
+    y0 = np.array([0.994, 0, 0, -2.00158510637908252240537862224])
+    return Problem(f, 0.0, tmax, y0, df, df_diagonal)
+
+
+PLEIADES_Y0 = np.array([3.0, 3.0, -1.0, -3.0, 2.0, -2.0, 2.0, 3.0, -3.0, 2.0, 0, 0, -4.0, 4.0, 0, 0, 0, 0, 0, 1.75, -1.5, 0, 0, 0,
+                        -1.25, 1, 0, 0])
+
+
+def pleiades(t0=0.0, tmax=3.0):
+    """ivp.py:344-406 (PLEI of Hairer I): u = [x(7); y(7); x'(7); y'(7)], body j has mass j.  The 0/0 of a body with itself
+    is mapped to 0 (``nan_to_num``, :384-385).  The Jacobian diagonal (``diagonal(jacfwd(f))``, :393-397) vanishes: positions'
+    derivatives are velocities, accelerations depend on positions only."""
+
+    def f(t, u):
+        x, y, dx, dy = u[0:7], u[7:14], u[14:21], u[21:28]
+        xi, xj = x[:, None], x[None, :]
+        yi, yj = y[:, None], y[None, :]
+        rij = ((xi - xj) ** 2 + (yi - yj) ** 2) ** (3 / 2)
+        mj = np.arange(1, 8)[None, :]
+        with np.errstate(invalid="ignore", divide="ignore"):
+            ddx = np.sum(np.nan_to_num(mj * (xj - xi) / rij), axis=1)
+            ddy = np.sum(np.nan_to_num(mj * (yj - yi) / rij), axis=1)
+        return np.concatenate((dx, dy, ddx, ddy))
+
+    def df(t, u):
+        # complex step with the self-interaction masked out (nan_to_num is not analytic)
+        u = np.asarray(u, dtype=float)
+        J = np.zeros((28, 28))
+        off = ~np.eye(7, dtype=bool)
+        for k in range(28):
+            uc = u.astype(complex)
+            uc[k] += 1e-30j
+            x, y = uc[0:7], uc[7:14]
+            ddx, ddy = np.zeros(7, complex), np.zeros(7, complex)
+            for i in range(7):
+                for j in range(7):
+                    if off[i, j]:
+                        r3 = ((x[i] - x[j]) ** 2 + (y[i] - y[j]) ** 2) ** 1.5
+                        ddx[i] += (j + 1) * (x[j] - x[i]) / r3
+                        ddy[i] += (j + 1) * (y[j] - y[i]) / r3
+            J[:, k] = np.imag(np.concatenate((uc[14:21], uc[21:28], ddx, ddy))) / 1e-30
+        return J
+
+    def df_diagonal(t, u):
+        return np.zeros(28)
+
+    return Problem(f, t0, tmax, PLEIADES_Y0.copy(), df, df_diagonal)
 
 
 def mesh_1d(bbox, dx):
@@ -164,6 +250,11 @@ def lorenz96(t0=0.0, tmax=30.0, y0=None, num_variables=10, forcing=8.0):
         return -1.0 * np.ones(y.shape[0])
 
     return Problem(f, t0, tmax, np.asarray(y0, dtype=float), df, df_diagonal)
+
+
+def lorenz96_loop(t0=0.0, tmax=30.0, y0=None, num_variables=10, forcing=8.0):
+    """ivp.py:298-332: the same vector field written as a loop over the coordinates (identical arithmetic per entry)."""
+    return lorenz96(t0=t0, tmax=tmax, y0=y0, num_variables=num_variables, forcing=forcing)
 
 
 def laplace_2d(grid, dx):

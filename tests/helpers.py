@@ -18,6 +18,14 @@ def make_pair(kind, size, **kw):
         o = oproblems.vanderpol(t0=0.0, tmax=kw.get("tmax", 1.0), stiffness_constant=mu)
         p = pivp.vanderpol(t0=0.0, tmax=kw.get("tmax", 1.0), stiffness_constant=mu)
         return o, p, odriver.series_vanderpol(mu)
+    if kind == "vanderpol_julia":
+        mu = kw.get("mu", 2.0)
+        return (oproblems.vanderpol_julia(t0=0.0, tmax=0.5, stiffness_constant=mu),
+                pivp.vanderpol_julia(t0=0.0, tmax=0.5, stiffness_constant=mu), odriver.series_vanderpol_julia(mu))
+    if kind == "threebody":
+        return oproblems.threebody(tmax=0.02), pivp.threebody(tmax=0.02), odriver.series_threebody()
+    if kind == "pleiades":
+        return oproblems.pleiades(tmax=0.2), pivp.pleiades(tmax=0.2), odriver.series_pleiades()
     if kind == "lorenz96":
         o = oproblems.lorenz96(num_variables=size)
         p = pivp.lorenz96(num_variables=size)
@@ -101,8 +109,11 @@ GOLDEN_PATH = pathlib.Path(__file__).resolve().parent / "golden" / "reference_ve
 
 @functools.lru_cache(maxsize=1)
 def golden():
-    with np.load(GOLDEN_PATH) as data:
-        return {k: data[k] for k in data.files}
+    out = {}
+    for path in (GOLDEN_PATH, GOLDEN_PATH.with_name("reference_vectors_small.npz")):   # disjoint keys (different problems)
+        with np.load(path) as data:
+            out.update({k: data[k] for k in data.files})
+    return out
 
 
 def oracle_problem(name):
@@ -121,6 +132,14 @@ def oracle_problem(name):
         return oproblems.burgers_1d(t0=0.0, tmax=0.05, dx=0.1), odriver.series_burgers_1d(0.1)
     if name == "wave_1d":
         return oproblems.wave_1d(t0=0.0, tmax=0.05, dx=0.1), odriver.series_wave_1d(0.1)
+    if name == "vanderpol_julia":
+        return oproblems.vanderpol_julia(t0=0.0, tmax=0.5, stiffness_constant=2.0), odriver.series_vanderpol_julia(2.0)
+    if name == "threebody":
+        return oproblems.threebody(tmax=0.02), odriver.series_threebody()
+    if name == "pleiades":
+        return oproblems.pleiades(t0=0.0, tmax=0.2), odriver.series_pleiades()
+    if name == "lorenz96_loop":
+        return oproblems.lorenz96_loop(t0=0.0, tmax=0.3, num_variables=6, forcing=8.0), odriver.series_lorenz96(8.0)
     raise KeyError(name)
 
 
@@ -141,4 +160,12 @@ def product_problem(name):
         return pivp.burgers_1d(t0=0.0, tmax=0.05, dx=0.1)
     if name == "wave_1d":
         return pivp.wave_1d(t0=0.0, tmax=0.05, dx=0.1)
+    if name == "vanderpol_julia":
+        return pivp.vanderpol_julia(t0=0.0, tmax=0.5, stiffness_constant=2.0)
+    if name == "threebody":
+        return pivp.threebody(tmax=0.02)
+    if name == "pleiades":
+        return pivp.pleiades(t0=0.0, tmax=0.2)
+    if name == "lorenz96_loop":
+        return pivp.lorenz96_loop(t0=0.0, tmax=0.3, num_variables=6, forcing=8.0)
     raise KeyError(name)

@@ -11,7 +11,8 @@ from helpers import FP32_RTOL, FP64_RTOL, assert_close, golden, product_problem
 
 pytestmark = pytest.mark.gpu
 
-NAMES = ["vanderpol", "lorenz96", "brusselator", "fhn_2d", "burgers_1d", "wave_1d"]
+NAMES = ["vanderpol", "lorenz96", "brusselator", "fhn_2d", "burgers_1d", "wave_1d",
+         "vanderpol_julia", "threebody", "pleiades", "lorenz96_loop"]
 
 
 def _np(x):
@@ -169,7 +170,10 @@ def test_adaptive_solves_same_accepted_steps(cuda_device, name, solver):
         last = state
     ref_ts = g[f"solve/{name}/{solver}/ts"]
     assert len(ts) == len(ref_ts), "different number of accepted steps"
-    np.testing.assert_allclose(ts, ref_ts, rtol=1e-9, atol=0)
+    # 1e-9 (north_star); where the reference's own accepted times move by more than that under a 1-ulp change of y0 (probe in
+    # the golden file: threebody starts next to a singularity), ten times that change
+    noise = float(g.get(f"solve/{name}/{solver}/ts_noise", 0.0))
+    np.testing.assert_allclose(ts, ref_ts, rtol=max(1e-9, 10.0 * noise), atol=0)
     counters = [info[k] for k in ("num_f_evaluations", "num_df_evaluations", "num_df_diagonal_evaluations",
                                   "num_steps", "num_attempted_steps")]
     np.testing.assert_array_equal(counters, g[f"solve/{name}/{solver}/info"])

@@ -14,6 +14,9 @@ pytestmark = pytest.mark.gpu
 
 CASES = [
     ("vanderpol", 1),
+    ("vanderpol_julia", 1),
+    ("threebody", 4),
+    ("pleiades", 28),
     ("lorenz96", 10),
     ("lorenz96", 1000),
     ("lorenz96", 4099),

@@ -154,7 +154,8 @@ def test_problem_factories_and_specs():
 
 
 @pytest.mark.parametrize("name,size", [("vanderpol", 1), ("lorenz96", 9), ("brusselator", 6), ("fhn_2d", 5),
-                                       ("burgers_1d", 11), ("wave_1d", 9)])
+                                       ("burgers_1d", 11), ("wave_1d", 9), ("vanderpol_julia", 1), ("threebody", 4),
+                                       ("pleiades", 28)])
 def test_taylor_mode_series_algebra_on_cpu_tensors(name, size):
     """The product's Taylor-mode initialisation is plain tensor algebra: check it on CPU tensors vs the oracle."""
     from helpers import make_pair

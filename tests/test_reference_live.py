@@ -55,11 +55,17 @@ def test_golden_file_is_reproducible(tornadox, tmp_path, monkeypatch):
     import oracle.make_golden as mg
 
     monkeypatch.setattr(mg, "OUT", tmp_path / "regen.npz")
+    monkeypatch.setattr(mg, "OUT_SMALL", tmp_path / "regen_small.npz")
     mg.main()
+    mg.main(small=True)
     from helpers import golden
 
-    with np.load(tmp_path / "regen.npz") as new:
-        old = golden()
-        assert set(new.files) == set(old)
-        for k in new.files:
-            np.testing.assert_array_equal(new[k], old[k], err_msg=k)
+    old = golden()
+    seen = set()
+    for path in (tmp_path / "regen.npz", tmp_path / "regen_small.npz"):
+        with np.load(path) as new:
+            assert not (seen & set(new.files)), "the two fixture files must not share keys"
+            seen |= set(new.files)
+            for k in new.files:
+                np.testing.assert_array_equal(new[k], old[k], err_msg=k)
+    assert seen == set(old)

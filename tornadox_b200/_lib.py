@@ -23,6 +23,7 @@ TDX_STEP_COMM_REDUCE = 32
 TDX_STEP_COMM_PACK = 64
 TDX_COMM_HANDLE_BYTES = 64
 TDX_IVP_VANDERPOL, TDX_IVP_LORENZ96, TDX_IVP_BRUSSELATOR, TDX_IVP_FHN2D, TDX_IVP_BURGERS1D, TDX_IVP_WAVE1D = 0, 1, 2, 3, 4, 5
+TDX_IVP_THREEBODY, TDX_IVP_PLEIADES = 6, 7
 
 EXPORTED_SYMBOLS = (
     "tdx_last_error", "tdx_abi_version", "tdx_create", "tdx_destroy", "tdx_set_problem", "tdx_local_dim",

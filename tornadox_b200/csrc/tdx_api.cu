@@ -54,6 +54,8 @@ long long grid_for(const Geo& g) {
         case IVP_FHN2D: return num_tiles<Fhn2d<double>::Shape>(g.rows, g.cols);
         case IVP_BURGERS1D: return num_tiles<Burgers1d<double>::Shape>(g.rows, g.cols);
         case IVP_WAVE1D: return num_tiles<Wave1d<double>::Shape>(g.rows, g.cols);
+        case IVP_THREEBODY: return num_tiles<ThreeBody<double>::Shape>(g.rows, g.cols);
+        case IVP_PLEIADES: return num_tiles<Pleiades<double>::Shape>(g.rows, g.cols);
     }
     return 0;
 }
@@ -290,7 +292,18 @@ int tdx_set_problem(tdx_ctx* ctx, const tdx_problem_desc* d) {
             g.nf = 2;
             g.rows = 1; g.cols = 1; g.grow0 = 0; g.gcol0 = 0;
             g.prm[0] = d->params[0];
+            g.prm[1] = (d->n_params >= 2 && d->params[1] != 0.0) ? 1.0 : 0.0;     // vanderpol_julia's scaling (ivp.py:52-73)
             break;
+        case TDX_IVP_THREEBODY:
+        case TDX_IVP_PLEIADES: {
+            const long long dim = d->kind == TDX_IVP_THREEBODY ? 4 : 28;
+            if (d->grid_rows != 1 || d->grid_cols != dim || d->shard_begin != 0 || d->shard_end != dim)
+                return fail(TDX_ERR_INVALID, "tdx_set_problem: threebody (d = 4) / pleiades (d = 28) are laid out as one field of d "
+                                             "points (grid_rows = 1, grid_cols = d) and do not shard");
+            g.nf = 1;
+            g.rows = 1; g.cols = (int)dim; g.grow0 = 0; g.gcol0 = 0;
+            break;
+        }
         case TDX_IVP_LORENZ96:
             if (d->grid_rows != 1) return fail(TDX_ERR_INVALID, "tdx_set_problem: lorenz96 is one-dimensional (grid_rows = 1)");
             if (d->shard_end > d->grid_cols) return fail(TDX_ERR_INVALID, "tdx_set_problem: shard exceeds the chain");
@@ -345,7 +358,7 @@ int tdx_set_problem(tdx_ctx* ctx, const tdx_problem_desc* d) {
         default:
             return fail(TDX_ERR_UNSUPPORTED,
                         "tdx_set_problem: unknown vector field kind; only vanderpol, lorenz96, brusselator, fhn_2d, "
-                        "burgers_1d and wave_1d are evaluated in-kernel (there is no CPU fallback)");
+                        "burgers_1d, wave_1d, threebody and pleiades are evaluated in-kernel (there is no CPU fallback)");
     }
     g.npts = (long long)g.rows * g.cols;
     g.d = (long long)g.nf * g.npts;
@@ -356,7 +369,7 @@ int tdx_set_problem(tdx_ctx* ctx, const tdx_problem_desc* d) {
         case IVP_LORENZ96: Lorenz96<double>::halo_sizes(g, lo, hi); break;
         case IVP_BRUSS: Brusselator<double>::halo_sizes(g, lo, hi); break;
         case IVP_FHN2D: Fhn2d<double>::halo_sizes(g, lo, hi); break;
-        default: break;   // burgers_1d, wave_1d: never sharded
+        default: break;   // burgers_1d, wave_1d, threebody, pleiades: never sharded
     }
 
     long long grid = grid_for(g);

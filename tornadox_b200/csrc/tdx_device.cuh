@@ -16,7 +16,7 @@ constexpr int kMaxN = 7;       // n = nu + 1 <= 7
 constexpr int kWarps = 8;      // warps per CTA; every warp owns one 32-wide segment of one field
 constexpr int kThreads = kWarps * 32;
 
-enum : int { IVP_VDP = 0, IVP_LORENZ96 = 1, IVP_BRUSS = 2, IVP_FHN2D = 3, IVP_BURGERS1D = 4, IVP_WAVE1D = 5 };
+enum : int { IVP_VDP = 0, IVP_LORENZ96 = 1, IVP_BRUSS = 2, IVP_FHN2D = 3, IVP_BURGERS1D = 4, IVP_WAVE1D = 5, IVP_THREEBODY = 6, IVP_PLEIADES = 7 };
 
 // Local shard geometry.  Flat local state index = field * npts + row * cols + col.
 struct Geo {
@@ -252,7 +252,7 @@ struct ExtTile {
     }
 };
 
-// --- vanderpol: ivp.py:28-49.  One point, two fields (y1, y2). ---------------------------------
+// --- vanderpol: ivp.py:28-49 (prm[1] != 0: vanderpol_julia, ivp.py:52-73).  One point, two fields (y1, y2). ---
 template <typename T>
 struct VanderPol {
     using Shape = TileShape<2, 1, 4>;
@@ -271,8 +271,11 @@ struct VanderPol {
         if (c.field == 0) {
             fx = y2;
             jac = (T)0;
-        } else {
+        } else if (g.prm[1] == 0.0) {
             fx = damp * y2 - y1;
+            jac = damp;
+        } else {                                   // vanderpol_julia (ivp.py:52-73): mu scales the whole right-hand side
+            fx = mu * (((T)1 - y1 * y1) * y2 - y1);
             jac = damp;
         }
         (void)own;
@@ -406,6 +409,72 @@ struct Wave1d {
         else fx = edge ? x : nu_dx2 * (s_ext[xi + 1] - (T)2 * x + s_ext[xi - 1]);
         jac = (T)0;
         (void)own;
+    }
+};
+
+template <typename T>
+__device__ __forceinline__ T tsqrt(T x);          // specialised further down
+
+// --- threebody (ivp.py:188-216) and pleiades (ivp.py:344-406): small dense systems, every coordinate reads the positions of
+//     all bodies.  The flat state is laid out as ONE field of d points (d = 4 / 28 <= one tile), so after the front end's
+//     barrier the tile in shared memory IS the predicted state vector and coordinate j sits at index j.  The Jacobian
+//     diagonal vanishes for both (the accelerations depend on positions only; threebody's is zero by definition, :204-205).
+template <typename T>
+struct ThreeBody {
+    using Shape = TileShape<1, 1, 8>;
+    static constexpr int HL = 0, HR = 0, HV = 0;
+    static __host__ void halo_sizes(const Geo&, long long& lo, long long& hi) { lo = hi = 0; }
+    template <class At>
+    __device__ static __forceinline__ T ring_value(const Geo&, int, int, int, int, int, const At&, const T*, const T*) {
+        return (T)0;
+    }
+    __device__ static __forceinline__ void eval(const Geo&, const Coord& c, const T* y, T own, T& fx, T& jac) {
+        const T mu = (T)0.012277471, mp = (T)1 - mu;
+        jac = (T)0;
+        (void)own;
+        if (c.col < 2) {                          // positions: y' = velocity
+            fx = y[c.col + 2];
+            return;
+        }
+        const T a = y[0] + mu, b = y[0] - mp;
+        const T s1 = a * a + y[1] * y[1], s2 = b * b + y[1] * y[1];
+        const T D1 = s1 * tsqrt<T>(s1), D2 = s2 * tsqrt<T>(s2);            // (...)^(3/2)
+        if (c.col == 2) fx = y[0] + (T)2 * y[3] - mp * a / D1 - mu * b / D2;
+        else fx = y[1] - (T)2 * y[2] - mp * y[1] / D1 - mu * y[1] / D2;
+    }
+};
+
+template <typename T>
+struct Pleiades {
+    using Shape = TileShape<1, 1, 8>;
+    static constexpr int HL = 0, HR = 0, HV = 0;
+    static __host__ void halo_sizes(const Geo&, long long& lo, long long& hi) { lo = hi = 0; }
+    template <class At>
+    __device__ static __forceinline__ T ring_value(const Geo&, int, int, int, int, int, const At&, const T*, const T*) {
+        return (T)0;
+    }
+    // y = [x(7); y(7); x'(7); y'(7)];  x_i'' = sum_{j != i} m_j (x_j - x_i) / r_ij^3, m_j = j + 1 (the reference's 0/0 at
+    // j = i is mapped to 0 by nan_to_num, :384-385)
+    __device__ static __forceinline__ void eval(const Geo&, const Coord& c, const T* y, T own, T& fx, T& jac) {
+        jac = (T)0;
+        (void)own;
+        if (c.col < 14) {
+            fx = y[(c.col + 14) % 28];            // % keeps the threads beyond the state inside the tile
+            return;
+        }
+        const int i = (c.col - 14) % 7;
+        const bool is_x = c.col < 21;
+        const T xi = y[i], yi = y[7 + i];
+        T acc = (T)0;
+#pragma unroll
+        for (int j = 0; j < 7; ++j) {
+            const T dx = y[j] - xi, dy = y[7 + j] - yi;
+            const T s = dx * dx + dy * dy;
+            const T r3 = s * tsqrt<T>(s);
+            const T term = (T)(j + 1) * (is_x ? dx : dy) / r3;
+            acc += (j == i) ? (T)0 : term;
+        }
+        fx = acc;
     }
 };
 

@@ -146,6 +146,8 @@ inline cudaError_t persistent_grid(size_t smem, long long tiles, int reserve, un
         case IVP_FHN2D: { using IVP = Fhn2d<T>; __VA_ARGS__ } break;             \
         case IVP_BURGERS1D: { using IVP = Burgers1d<T>; __VA_ARGS__ } break;     \
         case IVP_WAVE1D: { using IVP = Wave1d<T>; __VA_ARGS__ } break;           \
+        case IVP_THREEBODY: { using IVP = ThreeBody<T>; __VA_ARGS__ } break;     \
+        case IVP_PLEIADES: { using IVP = Pleiades<T>; __VA_ARGS__ } break;       \
         default: return -1;                                                      \
     }
 
@@ -357,6 +359,8 @@ struct Launch {
                 case IVP_BRUSS: return launch_chain<Brusselator<T>, kCtl>(g, a, st);
                 case IVP_BURGERS1D: return launch_chain<Burgers1d<T>, kCtl>(g, a, st);
                 case IVP_WAVE1D: return launch_chain<Wave1d<T>, kCtl>(g, a, st);
+                case IVP_THREEBODY: return launch_chain<ThreeBody<T>, kCtl>(g, a, st);
+                case IVP_PLEIADES: return launch_chain<Pleiades<T>, kCtl>(g, a, st);
                 default: return kNoFusedKernel;
             }
         }

@@ -27,6 +27,8 @@ def shard_range(spec, rank, world):
         raise ValueError("vanderpol (d = 2) cannot be sharded across GPUs")
     if spec.kind in (_lib.TDX_IVP_BURGERS1D, _lib.TDX_IVP_WAVE1D):
         raise NotImplementedError(f"{spec.name} runs on one GPU only (its end-point rules couple the two ends of the mesh)")
+    if spec.kind in (_lib.TDX_IVP_THREEBODY, _lib.TDX_IVP_PLEIADES):
+        raise ValueError(f"{spec.name} (d = {spec.grid_cols}) cannot be sharded across GPUs")
     if extent < 2 * world:
         raise ValueError(f"cannot shard an axis of {extent} across {world} ranks")
     base, rem = divmod(extent, world)

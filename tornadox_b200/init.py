@@ -77,8 +77,30 @@ class _PowerSeries:
 
     __rmul__ = __mul__
 
-    def __truediv__(self, scalar):
-        return _PowerSeries(self.c / scalar)
+    def __truediv__(self, other):
+        if not isinstance(other, _PowerSeries):
+            return _PowerSeries(self.c / other)
+        out = torch.zeros_like(self.c)
+        for k in range(self.order):          # q b = a  =>  q_k = (a_k - sum_{j=1..k} b_j q_{k-j}) / b_0
+            acc = self.c[k].clone()
+            for j in range(1, k + 1):
+                acc -= other.c[j] * out[k - j]
+            out[k] = acc / other.c[0]
+        return _PowerSeries(out)
+
+    def pow(self, r):
+        """Real power of a series with nonzero constant term: y = x^r solves x y' = r x' y."""
+        out = torch.zeros_like(self.c)
+        out[0] = self.c[0] ** r
+        for k in range(1, self.order):
+            acc = torch.zeros_like(self.c[0])
+            for j in range(1, k + 1):
+                acc += (r * j - (k - j)) * self.c[j] * out[k - j]
+            out[k] = acc / (k * self.c[0])
+        return _PowerSeries(out)
+
+    def entry(self, i):
+        return _PowerSeries(self.c[:, i:i + 1])
 
     def square(self):
         return self * self
@@ -97,10 +119,12 @@ def _series_rhs(spec):
     """The vector field of ``spec`` acting on a _PowerSeries (same arithmetic as the kernels)."""
     kind = spec.kind
     if kind == _lib.TDX_IVP_VANDERPOL:
-        (mu,) = spec.params
+        mu, julia = spec.params[0], len(spec.params) > 1 and spec.params[1] != 0.0
 
         def rhs(y):
             y1, y2 = y.fields(2)
+            if julia:                                   # ivp.py:52-73
+                return [y2, mu * ((1.0 - y1.square()) * y2 - y1)]
             return [y2, mu * (1.0 - y1.square()) * y2 - y1]
 
     elif kind == _lib.TDX_IVP_LORENZ96:
@@ -174,6 +198,35 @@ def _series_rhs(spec):
             interior = nu_ * (cut(x, 2, n) - 2.0 * cut(x, 1, n - 1) + cut(x, 0, n - 2)) / (dx * dx)
             zero = _PowerSeries(torch.zeros_like(x.c[:, :1]))
             return [zero, cut(v, 1, n - 1), zero, cut(x, 0, 1), interior, cut(x, n - 1, n)]
+
+    elif kind == _lib.TDX_IVP_THREEBODY:
+        mu = 0.012277471
+        mp = 1 - mu
+
+        def rhs(y):
+            y1, y2, v1, v2 = (y.entry(i) for i in range(4))
+            D1 = ((y1 + mu).square() + y2.square()).pow(1.5)
+            D2 = ((y1 - mp).square() + y2.square()).pow(1.5)
+            return [v1, v2,
+                    y1 + 2.0 * v2 - mp * (y1 + mu) / D1 - mu * (y1 - mp) / D2,
+                    y2 - 2.0 * v1 - mp * y2 / D1 - mu * y2 / D2]
+
+    elif kind == _lib.TDX_IVP_PLEIADES:
+
+        def rhs(y):
+            # pairwise differences as (7, 7) series; the diagonal (a body with itself: 0/0 -> 0 in the reference, ivp.py:384-385)
+            # is given a unit distance and masked out of the sums
+            x, yy = y.c[:, 0:7], y.c[:, 7:14]
+            eye = torch.eye(7, dtype=y.c.dtype, device=y.c.device)
+            dx = _PowerSeries(x[:, None, :] - x[:, :, None])          # [k, i, j] = x_j - x_i
+            dy = _PowerSeries(yy[:, None, :] - yy[:, :, None])
+            sq = dx.square() + dy.square()
+            sq.c[0] += eye
+            r3 = sq.pow(1.5)
+            mass = torch.arange(1, 8, dtype=y.c.dtype, device=y.c.device)[None, :] * (1.0 - eye)
+            ddx = _PowerSeries(((dx / r3).c * mass).sum(-1))
+            ddy = _PowerSeries(((dy / r3).c * mass).sum(-1))
+            return [_PowerSeries(y.c[:, 14:28]), ddx, ddy]
 
     else:
         raise NotImplementedError(f"no Taylor-mode rule for {spec.name}")

@@ -1,7 +1,9 @@
 """Initial value problems whose right-hand sides are evaluated INSIDE the fused CUDA step kernels.
 
-Mirrors the factory functions of the reference (tornadox/ivp.py): ``vanderpol`` (:28-49), ``burgers_1d`` (:76-107),
-``wave_1d`` (:110-140), ``brusselator`` (:219-265), ``lorenz96`` (:268-294), ``fhn_2d`` (:409-481).  Each returns an
+Mirrors the factory functions of the reference (tornadox/ivp.py): ``vanderpol`` (:28-49), ``vanderpol_julia`` (:52-73),
+``burgers_1d`` (:76-107), ``wave_1d`` (:110-140), ``threebody`` (:188-216), ``brusselator`` (:219-265), ``lorenz96`` (:268-294),
+``lorenz96_loop`` (:298-332), ``pleiades`` (:344-406), ``fhn_2d`` (:409-481); ``wave_2d`` (:143-185) does not run upstream
+(``jax.ops.index_update`` is gone) and is not provided.  Each returns an
 ``InitialValueProblem(f, t0, tmax, y0, df, df_diagonal)`` (:10-25); ``f`` and ``df_diagonal`` are callables
 on device tensors (they launch ``tdx_eval_f``) that additionally carry the ``KernelSpec`` the solvers
 dispatch on.  ``df`` (dense Jacobian) is ``None``: the O(d^2) dense solvers are out of scope.
@@ -93,6 +95,28 @@ def vanderpol(t0=0.0, tmax=30, y0=None, stiffness_constant=1e1):
     return _problem(spec, t0, tmax, y0)
 
 
+def vanderpol_julia(t0=0.0, tmax=6.3, y0=None, stiffness_constant=1e1):
+    """Van der Pol in the scaling of the Julia benchmarks, y' = [y2, mu ((1 - y1^2) y2 - y1)]  (ivp.py:52-73)."""
+    y0 = np.array([2.0, 0.0]) if y0 is None else y0
+    spec = KernelSpec(_lib.TDX_IVP_VANDERPOL, (float(stiffness_constant), 1.0), 1, 1, 2, "vanderpol_julia")
+    return _problem(spec, t0, tmax, y0)
+
+
+def threebody(tmax=17.0652165601579625588917206249):
+    """Restricted three-body problem, Y = [y1, y2, y1', y2']; the Jacobian diagonal is defined as zero  (ivp.py:188-216)."""
+    y0 = np.array([0.994, 0, 0, -2.00158510637908252240537862224])
+    spec = KernelSpec(_lib.TDX_IVP_THREEBODY, (), 1, 4, 1, "threebody")
+    return _problem(spec, 0.0, tmax, y0)
+
+
+def pleiades(t0=0.0, tmax=3.0):
+    """Seven-body Pleiades problem (PLEI of Hairer I), u = [x(7); y(7); x'(7); y'(7)]  (ivp.py:344-406)."""
+    y0 = np.array([3.0, 3.0, -1.0, -3.0, 2.0, -2.0, 2.0, 3.0, -3.0, 2.0, 0, 0, -4.0, 4.0, 0, 0, 0, 0, 0, 1.75, -1.5, 0, 0, 0,
+                   -1.25, 1, 0, 0])
+    spec = KernelSpec(_lib.TDX_IVP_PLEIADES, (), 1, 28, 1, "pleiades")
+    return _problem(spec, t0, tmax, y0)
+
+
 def _mesh_1d(bbox, dx):
     """``arange(bbox[0], bbox[1] + dx, step=dx)`` as in ivp.py:81, 115."""
     if bbox is None:
@@ -144,6 +168,12 @@ def lorenz96(t0=0.0, tmax=30.0, y0=None, num_variables=10, forcing=8.0):
         num_variables = int(y0.shape[0])
     spec = KernelSpec(_lib.TDX_IVP_LORENZ96, (float(forcing),), 1, int(num_variables), 1, "lorenz96")
     return _problem(spec, t0, tmax, y0)
+
+
+def lorenz96_loop(t0=0.0, tmax=30.0, y0=None, num_variables=10, forcing=8.0):
+    """The reference's loop formulation of Lorenz-96 (ivp.py:298-332, written that way for jet): same vector field, same
+    kernel."""
+    return lorenz96(t0=t0, tmax=tmax, y0=y0, num_variables=num_variables, forcing=forcing)
 
 
 def fhn_2d(t0=0.0, tmax=20.0, y0=None, bbox=None, dx=0.02, a=2.8e-4, b=5e-3, k=-0.005, tau=0.1, prng_key=None):
