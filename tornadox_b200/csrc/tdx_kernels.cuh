@@ -7,6 +7,15 @@
 
 namespace tdx {
 
+#ifndef TDX_MIN_BLOCKS_N2
+#define TDX_MIN_BLOCKS_N2 4
+#endif
+#ifndef TDX_MIN_BLOCKS_N3
+#define TDX_MIN_BLOCKS_N3 4
+#endif
+#ifndef TDX_MIN_BLOCKS_N4
+#define TDX_MIN_BLOCKS_N4 3
+#endif
 #ifndef TDX_MIN_BLOCKS
 #define TDX_MIN_BLOCKS 2
 #endif
@@ -272,7 +281,11 @@ struct DekSmem {
     static constexpr int SLOTS = 2;           // stencil tiles: always double-buffered (small)
     // factor blocks: double-buffered while two CTAs per SM still fit (n <= 5 in fp64); beyond that ONE slot per warp keeps
     // two CTAs resident (their phases interleave) instead of one CTA with a prefetch slot (2.6x slower at n = 6)
-    static constexpr int SC_SLOTS = (2 * (L::BAR_BYTES + L::RED_BYTES + 2 * 4096 + 2 * L::sc_bytes()) <= 225 * 1024) ? 2 : 1;
+    // resident CTAs per SM the kernel is compiled for (register cap 64 / 85 / 128 per thread): the small blocks of n <= 4 leave
+    // registers for a third and fourth CTA, which is what hides the front end's load latency when there are few factor bytes
+    // per coordinate to wait for (8.4 M dimensions, fp64: nu = 1 39 -> 53 %, nu = 2 63 -> 81 %, nu = 3 78 -> 85 % of the roofline)
+    static constexpr int MIN_BLOCKS = (N <= 2) ? TDX_MIN_BLOCKS_N2 : (N == 3) ? TDX_MIN_BLOCKS_N3 : (N == 4) ? TDX_MIN_BLOCKS_N4 : TDX_MIN_BLOCKS;
+    static constexpr int SC_SLOTS = (MIN_BLOCKS * (L::BAR_BYTES + L::RED_BYTES + 2 * 4096 + 2 * L::sc_bytes()) <= 225 * 1024) ? 2 : 1;
     __host__ __device__ static constexpr size_t total(int at_elems) {
         return L::BAR_BYTES + L::RED_BYTES + SLOTS * L::at_bytes(at_elems) + SC_SLOTS * L::sc_bytes();
     }
@@ -283,7 +296,7 @@ struct DekSmem {
 // kCtl = true: the step to attempt and the in / out buffers are read from the device-resident controller block, and the
 // last CTA updates it (accept / reject, next dt) -- no host involvement between attempts.
 template <class IVP, typename T, int N, bool kComm, bool kCtl = false>
-__global__ void __launch_bounds__(kThreads, TDX_MIN_BLOCKS) dek1_kernel(const __grid_constant__ DekArgs<T, N> a) {
+__global__ void __launch_bounds__(kThreads, DekSmem<T, N>::MIN_BLOCKS) dek1_kernel(const __grid_constant__ DekArgs<T, N> a) {
     using Shape = typename IVP::Shape;
     using L = SmemLayout<T, N>;
     constexpr int NN = L::NN, STRIDE = L::STRIDE;
