@@ -216,4 +216,8 @@ def test_native_steprule_mirror_and_shard_ranges():
     assert engine.StepEngine.native_steprule(fake, Mine()) is None
     with pytest.raises(NotImplementedError):
         engine.shard_range(ivp.burgers_1d(dx=0.1).spec, 0, 2)
+    for small in (ivp.threebody(), ivp.pleiades(), ivp.vanderpol_julia()):
+        assert engine.shard_range(small.spec, 0, 1) == (0, small.spec.grid_cols)
+        with pytest.raises(ValueError):
+            engine.shard_range(small.spec, 0, 2)
     assert engine.shard_range(ivp.lorenz96(num_variables=10).spec, 1, 2) == (5, 10)
