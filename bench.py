@@ -105,7 +105,7 @@ class ClockSampler:
 # CPU reference arm: the NumPy oracle (a port of the reference; JAX is not installable here) on all host cores
 # ---------------------------------------------------------------------------------------------------
 def _cpu_worker(job):
-    solver, side, attempts, seed = job
+    solver, side, attempts, warmup, seed = job
     from oracle.ref_np import filters, problems
 
     n = NU + 1
@@ -121,15 +121,17 @@ def _cpu_worker(job):
     else:
         state = filters.FilterState(0.0, mean, 1e-3 * rng.standard_normal((n, n)), None, None)
         step = lambda s: filters.kronecker_ek0_attempt(s, dt, prob.f, NU)[0]
-    state = step(state)   # warm caches / page in
+    for _ in range(max(1, warmup)):   # warm caches / page in
+        state = step(state)
     t0 = time.perf_counter()
     for _ in range(attempts):
         state = step(state)
     return time.perf_counter() - t0, d * attempts
 
 
-def cpu_reference(solver, steps, warmup, target_seconds=12.0):
-    """All host cores, one independent fhn_2d sub-grid per worker process; returns throughput + description."""
+def cpu_reference(solver, steps, warmup):
+    """All host cores, one independent fhn_2d sub-grid per worker process, ``warmup`` untimed and ``steps`` timed attempts
+    each (a DiagonalEK1 attempt on the 384x384 sub-grid takes ~0.6 s per core); returns throughput + description."""
     import multiprocessing as mp
 
     cores = min(os.cpu_count() or 1, 16)   # bounded: every worker holds ~1 GB of NumPy temporaries
@@ -138,7 +140,7 @@ def cpu_reference(solver, steps, warmup, target_seconds=12.0):
     os.environ.setdefault("OMP_NUM_THREADS", "1")
     os.environ.setdefault("OPENBLAS_NUM_THREADS", "1")
     os.environ.setdefault("MKL_NUM_THREADS", "1")
-    jobs = [(solver, side, attempts, 1000 + i) for i in range(cores)]
+    jobs = [(solver, side, attempts, warmup, 1000 + i) for i in range(cores)]
     ctx = mp.get_context("spawn")
     t0 = time.perf_counter()
     with ctx.Pool(cores) as pool:
@@ -157,13 +159,14 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps = max(1, min(args.steps, 3))
-    value, cores, sample, ms = cpu_reference(args.solver, steps, args.warmup)
+    steps = max(1, min(args.steps, 200))          # a step = one attempt on every worker's sub-grid (bounded sample, ~0.6 s)
+    warmup = max(1, min(args.warmup, 20))
+    value, cores, sample, ms = cpu_reference(args.solver, steps, warmup)
     n, w = NU + 1, 8
     line = {
         "impl": "reference",
         "metric": "filter state-dims*steps/sec (fhn_2d, nu=4, fp64)",
-        "value": value, "unit": "state-dims*steps/s", "n_gpus": args.gpus, "steps": steps, "warmup": 1,
+        "value": value, "unit": "state-dims*steps/s", "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
         "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
         "config": {"workload": f"fhn_2d {args.grid}x{args.grid} (d={2 * args.grid ** 2}), "
@@ -302,7 +305,7 @@ def run_mine(args):
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        v, cores, sample, _ = cpu_reference(args.solver, 2, 1)
+        v, cores, sample, _ = cpu_reference(args.solver, 16, 1)      # ~10 s of work on every host core
         cpu = {"value": v, "unit": "state-dims*steps/s", "cores": cores, "kind": "port", "sample": sample}
 
     if rank == 0:
