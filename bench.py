@@ -11,7 +11,6 @@ One JSON line on stdout (rank 0).  For N > 1 launch with torchrun; d is sharded 
 
 import argparse
 import json
-import math
 import os
 import subprocess
 import sys
@@ -187,7 +186,6 @@ def run_mine(args):
     import torch
 
     from tornadox_b200 import ek0, ek1, ivp, step
-    from tornadox_b200 import _lib
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))

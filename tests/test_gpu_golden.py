@@ -1,8 +1,6 @@
 """GPU: the CUDA path (public solver API -> C ABI -> kernels) against outputs of the UNMODIFIED reference
 sources (tests/golden/reference_vectors.npz, see oracle/make_golden.py)."""
 
-import math
-
 import numpy as np
 import pytest
 import torch

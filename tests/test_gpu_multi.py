@@ -1,6 +1,5 @@
 """GPU, >= 2 devices: sharded solvers over NCCL against the unsharded oracle (skipped on single-GPU boxes)."""
 
-import os
 import pathlib
 import subprocess
 import sys

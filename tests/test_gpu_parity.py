@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 import torch
 
-from helpers import FP32_RTOL, FP64_RTOL, assert_close, make_pair, random_state
+from helpers import FP64_RTOL, assert_close, make_pair, random_state
 from oracle.ref_np import driver as odriver
 from oracle.ref_np import filters as ofilters
 

@@ -118,7 +118,6 @@ def _worker(rank, world, port, kind):
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        from tornadox_b200 import _lib
         from tornadox_b200.engine import HaloExchanger, local_slices, shard_range
 
         spec, prob = _spec_and_problem(kind)

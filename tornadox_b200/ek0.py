@@ -10,7 +10,6 @@ import torch
 
 from . import _lib, odefilter, rv
 from .ek1 import BatchedEK1
-from .init import _spec_of
 from .ivp import as_device_tensor
 
 
