@@ -116,3 +116,49 @@ def test_product_does_not_import_the_oracle():
     for path in (ROOT / "tornadox_b200").rglob("*.py"):
         text = path.read_text()
         assert "oracle" not in re.sub(r"#.*", "", text), f"{path} mentions the oracle"
+
+
+def test_c_client_links_and_runs_the_host_only_entry_points(lib):
+    """A plain C program built against include/tornadox_b200.h and linked with the shared library (what a cgo / JNI / FFI
+    binding does): the host-only entry points run without a GPU, tdx_create reports the missing device."""
+    import pathlib, shutil, subprocess, tempfile
+
+    from tornadox_b200 import _lib
+
+    cc = shutil.which("gcc") or shutil.which("cc")
+    if not cc:
+        pytest.skip("no C compiler")
+    root = pathlib.Path(__file__).resolve().parent.parent
+    libdir = pathlib.Path(_lib.LIB_PATH).resolve().parent
+    program = r'''
+#include <stdio.h>
+#include "tornadox_b200.h"
+int main(void) {
+    double A[25], Ql[25], p[5], pinv[5];
+    if (tdx_abi_version() != 1) return 10;
+    if (tdx_prior(4, A, Ql) != TDX_OK) return 11;
+    if (tdx_nordsieck(4, 0.1, p, pinv) != TDX_OK) return 12;
+    if (tdx_prior(0, A, Ql) == TDX_OK || tdx_last_error()[0] == 0) return 13;
+    printf("%.17g %.17g %.17g %.17g\n", A[1], Ql[0], p[0], pinv[4]);
+    tdx_ctx* ctx = 0;
+    int rc = tdx_create(&ctx, 0, TDX_F64);
+    printf("%d\n", rc);
+    if (rc == TDX_OK) tdx_destroy(ctx);
+    return 0;
+}
+'''
+    with tempfile.TemporaryDirectory() as tmp:
+        src = pathlib.Path(tmp) / "client.c"
+        src.write_text(program)
+        exe = pathlib.Path(tmp) / "client"
+        subprocess.run([cc, "-std=c99", "-Wall", "-Werror", "-I", str(root / "include"), str(src), "-o", str(exe),
+                        "-L", str(libdir), "-ltornadox_b200", f"-Wl,-rpath,{libdir}"], check=True)
+        out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()
+    g = golden()
+    assert float(out[0]) == g["prior/nu4/A"][0, 1] == 4.0
+    assert abs(float(out[1]) - g["prior/nu4/Ql"][0, 0]) <= 1e-15
+    assert abs(float(out[2]) - g["prior/nu4/p/0.1"][0]) <= 1e-14 * abs(g["prior/nu4/p/0.1"][0])
+    assert abs(float(out[3]) - g["prior/nu4/pinv/0.1"][4]) <= 1e-14 * abs(g["prior/nu4/pinv/0.1"][4])
+    import torch
+
+    assert int(out[4]) == (0 if torch.cuda.is_available() else 3)
