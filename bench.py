@@ -1,15 +1,22 @@
 #!/usr/bin/env python
 """Benchmark of the tornadox filter step on B200 (contract: see the task statement / DESIGN.md section Measurement).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl mine|reference] [--solver dek1|ek0] [--grid 2048]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl mine|reference] [--solver dek1|ek0]
+                    [--workload fhn_2d|brusselator] [--grid 2048] [--points 1000000] [--dtype f64|f32]
 
 metric: filter state-dims * steps / second ("step" = one attempt_step) on BASELINE.json config 5:
-ivp.fhn_2d on a 2048 x 2048 grid (d = 8 388 608), nu = 4, fp64.  The headline ``value`` is
-DiagonalEK1; the KroneckerEK0 numbers of the same run are reported under ``also``.
-One JSON line on stdout (rank 0).  For N > 1 launch with torchrun; d is sharded by grid rows (strong scaling).
+ivp.fhn_2d on a 2048 x 2048 grid (d = 8 388 608), nu = 4, fp64.  The headline ``value`` is DiagonalEK1;
+the KroneckerEK0 numbers of the same run are reported under ``also``.  ``--workload brusselator`` is BASELINE
+config 4 (N = 1 000 000, d = 2 000 000, DiagonalEK1).  One JSON line on stdout (rank 0).  For N > 1 launch with
+torchrun; d is sharded by grid rows / chain points (strong scaling).
+
+``--impl reference``: the CPU arm -- the NumPy restatement of the reference (oracle/; JAX cannot be installed here) on all
+host cores, on the SAME problem: the grid is cut into one row strip per core, the strips exchange their halo rows
+(and, for KroneckerEK0, their shares of z^T z) through shared memory every attempt.
 """
 
 import argparse
+import hashlib
 import json
 import os
 import subprocess
@@ -24,6 +31,7 @@ sys.path.insert(0, ROOT)
 
 NU = 4
 ALG_BYTES = {"dek1": lambda n, w: 2 * (n + n * n) * w, "ek0": lambda n, w: 2 * n * w}   # per state dimension
+SOLVER_NAMES = {"dek1": "ek1.DiagonalEK1", "ek0": "ek0.KroneckerEK0"}
 
 
 def parse():
@@ -33,11 +41,37 @@ def parse():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="mine", choices=["mine", "reference"])
     ap.add_argument("--solver", default="dek1", choices=["dek1", "ek0"])
+    ap.add_argument("--workload", default="fhn_2d", choices=["fhn_2d", "brusselator"])
     ap.add_argument("--grid", type=int, default=2048, help="fhn_2d grid side (BASELINE config 5: 2048)")
+    ap.add_argument("--points", type=int, default=1_000_000, help="brusselator N (BASELINE config 4: 1 000 000)")
     ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
     return ap.parse_args()
+
+
+def problem_dim(args):
+    return 2 * args.grid * args.grid if args.workload == "fhn_2d" else 2 * args.points
+
+
+def shared_config(args):
+    """The workload description: IDENTICAL in both arms (the driver compares them)."""
+    d = problem_dim(args)
+    if args.workload == "fhn_2d":
+        what = f"ivp.fhn_2d {args.grid}x{args.grid} grid (d={d})"
+    else:
+        what = f"ivp.brusselator N={args.points} (d={d})"
+    return {
+        "workload": f"{what}, {SOLVER_NAMES[args.solver]}(num_derivatives={NU}) attempt_step, y0 "
+                    f"{'~ U[0,1) seed 2' if args.workload == 'fhn_2d' else 'default'}, TaylorMode init, dt = 0.5 * first_dt, "
+                    "AdaptiveSteps tolerances (1e-4, 1e-2), attempts chained state -> state",
+        "solver": args.solver, "dims": d, "dtype": args.dtype,
+    }
+
+
+def metric_name(args):
+    return f"filter state-dims*steps/sec ({args.workload}, nu={NU}, {'fp64' if args.dtype == 'f64' else 'fp32'})"
 
 
 def measured_peak():
@@ -46,6 +80,35 @@ def measured_peak():
         with open(path) as fh:
             return float(json.load(fh)["hbm_gbs"]), "MEASURED_PEAKS.json"
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def csrc_sha():
+    """Hash of the CUDA sources: ties a recorded ncu traffic figure to the tree it was captured on."""
+    h = hashlib.sha256()
+    src = os.path.join(ROOT, "tornadox_b200", "csrc")
+    for name in sorted(os.listdir(src)):
+        if name.endswith((".cu", ".cuh")):
+            h.update(name.encode())
+            with open(os.path.join(src, name), "rb") as fh:
+                h.update(fh.read())
+    return h.hexdigest()[:16]
+
+
+def recorded_traffic(args, solver):
+    """dram bytes per launch from the last ``ncu --set full`` capture (profiles/traffic.json), or None when that capture was
+    taken on different kernel sources / another workload (a stale number is not evidence about this tree)."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    if not os.path.exists(path):
+        return None, "no capture recorded"
+    with open(path) as fh:
+        rec = json.load(fh)
+    key = f"{args.workload}:{args.grid if args.workload == 'fhn_2d' else args.points}:{args.dtype}:{solver}"
+    entry = rec.get("captures", {}).get(key)
+    if entry is None:
+        return None, "no capture for this workload"
+    if entry.get("csrc_sha") != csrc_sha():
+        return None, f"capture is from other kernel sources ({entry.get('csrc_sha')}, {entry.get('profile')})"
+    return entry.get("dram_bytes_per_launch"), entry.get("profile")
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -101,80 +164,235 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------------
-# CPU reference arm: the NumPy oracle (a port of the reference; JAX is not installable here) on all host cores
+# CPU arm: the NumPy oracle (a port of the reference; JAX is not installable here) on all host cores, SAME problem
 # ---------------------------------------------------------------------------------------------------
-def _cpu_worker(job):
-    solver, side, attempts, warmup, seed = job
+def _strip_bounds(extent, nworkers):
+    return [(extent * i) // nworkers for i in range(nworkers + 1)]
+
+
+def _cpu_strip_worker(wid, nworkers, workload, solver, size, dt, attempts, warmup, shm_names, barrier, queue):
+    """One core's share of the problem: grid rows (fhn_2d) / chain points (brusselator) [b0, b1) of both fields.  Every
+    attempt the strips publish their edge rows of the predicted state (and, KroneckerEK0, their z^T z) in shared memory."""
+    from multiprocessing import shared_memory
+
     from oracle.ref_np import filters, problems
 
     n = NU + 1
-    rng = np.random.default_rng(seed)
-    d = 2 * side * side
-    prob = problems.fhn_2d(dx=1.0 / side, y0=rng.uniform(size=d))
-    mean = rng.standard_normal((n, d))
-    mean[0] = prob.y0
-    dt = 1e-7
-    if solver == "dek1":
-        state = filters.FilterState(0.0, mean, 1e-3 * rng.standard_normal((d, n, n)), None, None)
-        step = lambda s: filters.diagonal_ek1_attempt(s, dt, prob.f, prob.df_diagonal, NU)[0]
-    else:
-        state = filters.FilterState(0.0, mean, 1e-3 * rng.standard_normal((n, n)), None, None)
-        step = lambda s: filters.kronecker_ek0_attempt(s, dt, prob.f, NU)[0]
-    for _ in range(max(1, warmup)):   # warm caches / page in
-        state = step(state)
-    t0 = time.perf_counter()
-    for _ in range(attempts):
-        state = step(state)
-    return time.perf_counter() - t0, d * attempts
+    shm_mean = shared_memory.SharedMemory(name=shm_names["mean"])
+    shm_edge = shared_memory.SharedMemory(name=shm_names["edge"])
+    shm_sum = shared_memory.SharedMemory(name=shm_names["sum"])
+    try:
+        if workload == "fhn_2d":
+            side = size
+            npts, d = side * side, 2 * side * side
+            bounds = _strip_bounds(side, nworkers)
+            r0, r1 = bounds[wid], bounds[wid + 1]
+            rows, width = r1 - r0, side
+            dx, a, b, k, tau = 1.0 / side, 2.8e-4, 5e-3, -0.005, 0.1
+        else:
+            N = size
+            npts, d = N, 2 * N
+            bounds = _strip_bounds(N, nworkers)
+            r0, r1 = bounds[wid], bounds[wid + 1]
+            rows, width = 1, r1 - r0
+            c = (N + 1) ** 2 / 50.0
+        mean_all = np.ndarray((n, d), dtype=np.float64, buffer=shm_mean.buf)
+        per_field = rows * width if workload == "fhn_2d" else width
+        lo = r0 * width if workload == "fhn_2d" else r0
+        idx = np.concatenate([np.arange(f * npts + lo, f * npts + lo + per_field) for f in range(2)])
+        mean = np.ascontiguousarray(mean_all[:, idx])
+        d_loc = idx.shape[0]
+        edge_w = 2 * (width if workload == "fhn_2d" else 1)
+        edges = np.ndarray((2, nworkers, 2, edge_w), dtype=np.float64, buffer=shm_edge.buf)   # [parity][worker][first/last]
+        sums = np.ndarray((2, nworkers), dtype=np.float64, buffer=shm_sum.buf)
+        counter = {"k": 0}
+
+        if workload == "fhn_2d":
+            diag = 4.0 * np.ones((rows, width))
+            diag[:, 0] -= 1.0
+            diag[:, -1] -= 1.0
+            if r0 == 0:
+                diag[0, :] -= 1.0
+            if r1 == side:
+                diag[-1, :] -= 1.0
+            dlap = (-diag / dx**2).reshape(-1)
+
+            def f(_, y):
+                par = counter["k"] & 1
+                fields = y.reshape(2, rows, width)
+                edges[par, wid, 0] = fields[:, 0, :].reshape(-1)
+                edges[par, wid, 1] = fields[:, -1, :].reshape(-1)
+                barrier.wait()
+                out = []
+                for fl in range(2):
+                    blocks = []
+                    if wid > 0:
+                        blocks.append(edges[par, wid - 1, 1].reshape(2, width)[fl][None, :])
+                    blocks.append(fields[fl])
+                    if wid < nworkers - 1:
+                        blocks.append(edges[par, wid + 1, 0].reshape(2, width)[fl][None, :])
+                    ext = np.concatenate(blocks, axis=0)
+                    lap = problems.laplace_2d(ext, dx=dx)       # ivp.py:484-505 (edge replication at the true grid edges)
+                    out.append(lap[(1 if wid > 0 else 0): ext.shape[0] - (1 if wid < nworkers - 1 else 0)].reshape(-1))
+                u, v = y.reshape(2, -1)
+                return np.concatenate((a * out[0] + u - u**3 - v + k, (b * out[1] + u - v) / tau))    # ivp.py:440-442
+
+            def df_diagonal(_, y):
+                u = y.reshape(2, -1)[0]
+                return np.concatenate((a * dlap + 1.0 - 3.0 * u**2, (b * dlap - 1.0) / tau * np.ones_like(u)))   # ivp.py:447-463
+        else:
+            def f(_, y):
+                par = counter["k"] & 1
+                u, v = y.reshape(2, -1)
+                edges[par, wid, 0] = (u[0], v[0])
+                edges[par, wid, 1] = (u[-1], v[-1])
+                barrier.wait()
+                ul, vl = (1.0, 3.0) if wid == 0 else edges[par, wid - 1, 1]            # ivp.py:233-236 boundary pads
+                ur, vr = (1.0, 3.0) if wid == nworkers - 1 else edges[par, wid + 1, 0]
+                up = np.concatenate(([ul], u, [ur]))
+                vp = np.concatenate(([vl], v, [vr]))
+                conv_u = up[:-2] - 2.0 * u + up[2:]
+                conv_v = vp[:-2] - 2.0 * v + vp[2:]
+                return np.concatenate((1.0 + u**2 * v - 4.0 * u + c * conv_u, 3.0 * u - u**2 * v + c * conv_v))   # ivp.py:240-241
+
+            def df_diagonal(_, y):
+                u, v = y.reshape(2, -1)
+                return np.concatenate((2.0 * u * v - 4.0 - 2.0 * c, -u**2 - 2.0 * c))   # ivp.py:252-257
+
+        def sum_over_shards(local):
+            par = counter["k"] & 1
+            sums[par, wid] = local
+            barrier.wait()
+            return float(np.sum(sums[par]))            # worker order: identical on every strip
+
+        if solver == "dek1":
+            state = filters.FilterState(0.0, mean, np.zeros((d_loc, n, n)), None, None)
+            step = lambda s: filters.diagonal_ek1_attempt(s, dt, f, df_diagonal, NU)[0]
+        else:
+            state = filters.FilterState(0.0, mean, np.zeros((n, n)), None, None)
+            step = lambda s: filters.kronecker_ek0_attempt(s, dt, f, NU, sum_over_shards=sum_over_shards, d_global=d)[0]
+        for _ in range(warmup):
+            state = step(state)
+            counter["k"] += 1
+        barrier.wait()
+        t0 = time.perf_counter()
+        for _ in range(attempts):
+            state = step(state)
+            counter["k"] += 1
+        elapsed = time.perf_counter() - t0
+        ok = bool(np.all(np.isfinite(state.mean)))
+        if "out" in shm_names:                      # tests: the strips' final means, to be compared with the unsharded oracle
+            shm_out = shared_memory.SharedMemory(name=shm_names["out"])
+            np.ndarray((n, d), dtype=np.float64, buffer=shm_out.buf)[:, idx] = state.mean
+            shm_out.close()
+        queue.put((wid, elapsed, d_loc, ok))
+    finally:
+        shm_mean.close()
+        shm_edge.close()
+        shm_sum.close()
 
 
-def cpu_reference(solver, steps, warmup):
-    """All host cores, one independent fhn_2d sub-grid per worker process, ``warmup`` untimed and ``steps`` timed attempts
-    each (a DiagonalEK1 attempt on the 384x384 sub-grid takes ~0.6 s per core); returns throughput + description."""
+def initial_condition(args):
+    """(y0, oracle problem, oracle series) of the workload -- NumPy only."""
+    from oracle.ref_np import driver, problems
+
+    if args.workload == "fhn_2d":
+        side = args.grid
+        y0 = np.random.default_rng(2).uniform(size=2 * side * side)
+        return y0, problems.fhn_2d(dx=1.0 / side, y0=y0), driver.series_fhn_2d(side, side, 1.0 / side)
+    prob = problems.brusselator(N=args.points)
+    return prob.y0, prob, driver.series_brusselator(args.points)
+
+
+def cpu_reference(args, solver, steps, warmup, cores=None, final_mean_out=None):
+    """All host cores on the benchmark's own problem: one strip per worker process, ``warmup`` untimed and ``steps`` timed
+    attempts, chained.  Returns (dims*steps/s, cores, description, ms per attempt).  ``final_mean_out``: an (n, d) array that
+    receives the mean after the last attempt (tests)."""
     import multiprocessing as mp
+    from multiprocessing import shared_memory
 
-    cores = min(os.cpu_count() or 1, 16)   # bounded: every worker holds ~1 GB of NumPy temporaries
-    side = {"dek1": 384, "ek0": 1024}[solver]
-    attempts = max(1, steps)
+    from oracle.ref_np import driver
+
+    cores = cores or min(os.cpu_count() or 1, 16)   # bounded: every worker holds ~1.5 GB of NumPy temporaries
     os.environ.setdefault("OMP_NUM_THREADS", "1")
     os.environ.setdefault("OPENBLAS_NUM_THREADS", "1")
     os.environ.setdefault("MKL_NUM_THREADS", "1")
-    jobs = [(solver, side, attempts, warmup, 1000 + i) for i in range(cores)]
-    ctx = mp.get_context("spawn")
-    t0 = time.perf_counter()
-    with ctx.Pool(cores) as pool:
-        res = pool.map(_cpu_worker, jobs)
-    wall = time.perf_counter() - t0
-    slowest = max(r[0] for r in res)
-    units = sum(r[1] for r in res)
-    value = units / slowest
-    sample = (f"{cores} worker processes x fhn_2d {side}x{side} (d={2 * side * side} each) x {attempts} "
-              f"{'DiagonalEK1' if solver == 'dek1' else 'KroneckerEK0'} attempts of the NumPy oracle "
-              f"(LAPACK dgeqrf via numpy.linalg.qr); wall {wall:.1f}s incl. process start")
-    return value, cores, sample, slowest / attempts * 1e3
+    size = args.grid if args.workload == "fhn_2d" else args.points
+    n, d = NU + 1, problem_dim(args)
+    y0, prob, series = initial_condition(args)
+    dt = 0.5 * driver.propose_first_dt(prob.f, prob.t0, y0)                 # step.py:111-115, as the GPU arm
+    mean0, _ = driver.taylor_init(series, y0, prob.t0, NU)                  # init.py:22-103
+    edge_w = 2 * (args.grid if args.workload == "fhn_2d" else 1)
+    shms = {
+        "mean": shared_memory.SharedMemory(create=True, size=n * d * 8),
+        "edge": shared_memory.SharedMemory(create=True, size=2 * cores * 2 * edge_w * 8),
+        "sum": shared_memory.SharedMemory(create=True, size=2 * cores * 8),
+    }
+    if final_mean_out is not None:
+        shms["out"] = shared_memory.SharedMemory(create=True, size=n * d * 8)
+    try:
+        np.ndarray((n, d), dtype=np.float64, buffer=shms["mean"].buf)[:] = mean0
+        del mean0
+        ctx = mp.get_context("spawn")
+        barrier, queue = ctx.Barrier(cores), ctx.Queue()
+        names = {k: v.name for k, v in shms.items()}
+        t0 = time.perf_counter()
+        procs = [ctx.Process(target=_cpu_strip_worker, args=(w, cores, args.workload, solver, size, dt, steps, warmup, names, barrier, queue))
+                 for w in range(cores)]
+        for p in procs:
+            p.start()
+        results = []
+        deadline = time.time() + 1500
+        while len(results) < cores and time.time() < deadline:
+            try:
+                results.append(queue.get(timeout=5))
+            except Exception:
+                if any(p.exitcode not in (None, 0) for p in procs):
+                    break
+        for p in procs:
+            p.join(timeout=30)
+            if p.is_alive():
+                p.terminate()
+        wall = time.perf_counter() - t0
+        if final_mean_out is not None:
+            final_mean_out[:] = np.ndarray((n, d), dtype=np.float64, buffer=shms["out"].buf)
+    finally:
+        for v in shms.values():
+            v.close()
+            v.unlink()
+    if len(results) < cores:
+        raise RuntimeError("CPU reference arm: a worker process died")
+    if not all(r[3] for r in results):
+        raise RuntimeError("CPU reference arm: non-finite state")
+    slowest = max(r[1] for r in results)
+    assert sum(r[2] for r in results) == d
+    value = d * steps / slowest
+    what = f"fhn_2d {args.grid}x{args.grid}" if args.workload == "fhn_2d" else f"brusselator N={args.points}"
+    sample = (f"the whole problem ({what}, d={d}) as {cores} strips, one worker process (core) each, halo rows"
+              f"{' and z^T z' if solver == 'ek0' else ''} exchanged through shared memory every attempt; {warmup} warm-up + {steps} timed "
+              f"chained {'DiagonalEK1' if solver == 'dek1' else 'KroneckerEK0'} attempts of the NumPy oracle (LAPACK dgeqrf via "
+              f"numpy.linalg.qr); wall {wall:.1f}s incl. process start")
+    return value, cores, sample, slowest / steps * 1e3
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps = max(1, min(args.steps, 200))          # a step = one attempt on every worker's sub-grid (bounded sample, ~0.6 s)
-    warmup = max(1, min(args.warmup, 20))
-    value, cores, sample, ms = cpu_reference(args.solver, steps, warmup)
-    n, w = NU + 1, 8
+    steps = max(1, min(args.steps, 100))          # a step = one attempt of the whole problem (~1.1 s on 16 cores for DiagonalEK1)
+    warmup = max(1, min(args.warmup, 10))
+    value, cores, sample, ms = cpu_reference(args, args.solver, steps, warmup)
     line = {
         "impl": "reference",
-        "metric": "filter state-dims*steps/sec (fhn_2d, nu=4, fp64)",
+        "metric": metric_name(args),
         "value": value, "unit": "state-dims*steps/s", "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
-        "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": args.dtype,
         "data": "synthetic",
-        "config": {"workload": f"fhn_2d {args.grid}x{args.grid} (d={2 * args.grid ** 2}), "
-                               f"{'DiagonalEK1' if args.solver == 'dek1' else 'KroneckerEK0'} nu=4 attempt_step; "
-                               "CPU arm timed on a bounded sample of it", "solver": args.solver},
+        "config": shared_config(args),
         "cpu_baseline": {"value": value, "unit": "state-dims*steps/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "state-dims*steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "the reference is pure Python on JAX, which cannot be installed here (no network, no wheel); this arm is "
-                "the op-for-op NumPy restatement under oracle/ (LAPACK geqrf like JAX-CPU) on all host cores",
+                "the op-for-op NumPy restatement under oracle/ (LAPACK geqrf like JAX-CPU, fp64) on all host cores",
     }
     print(json.dumps(line), flush=True)
 
@@ -203,10 +421,12 @@ def run_mine(args):
     dtype = {"f64": torch.float64, "f32": torch.float32}[args.dtype]
     w = 8 if dtype == torch.float64 else 4
     n = NU + 1
-    side = args.grid
-    d = 2 * side * side
-    y0 = np.random.default_rng(2).uniform(size=d)
-    problem = ivp.fhn_2d(dx=1.0 / side, y0=y0)
+    d = problem_dim(args)
+    if args.workload == "fhn_2d":
+        y0 = np.random.default_rng(2).uniform(size=d)
+        problem = ivp.fhn_2d(dx=1.0 / args.grid, y0=y0)
+    else:
+        problem = ivp.brusselator(N=args.points)
 
     def make(solver_name):
         cls = ek1.DiagonalEK1 if solver_name == "dek1" else ek0.KroneckerEK0
@@ -219,8 +439,15 @@ def run_mine(args):
             torch.distributed.barrier()
         torch.cuda.synchronize()
 
+    def max_over_ranks(ms):
+        if world > 1:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+            return float(t.item())
+        return ms
+
     def timed_steps(sol, state, dt, k, warm):
-        """W untimed + K timed attempt_step calls through the public API, state resident in HBM."""
+        """W untimed + K timed attempt_step calls through the public API, state resident in HBM, one kernel launch each."""
         for _ in range(warm):
             state, _ = sol.attempt_step(state, dt, *problem)
         barrier()
@@ -233,44 +460,14 @@ def run_mine(args):
         host_ms = (time.perf_counter() - h0) * 1e3 / k          # host time to enqueue one attempt (Python + C ABI)
         stop.record()
         barrier()
-        ms = start.elapsed_time(stop)
-        if world > 1:
-            t = torch.tensor([ms], device=dev, dtype=torch.float64)
-            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
-            ms = float(t.item())
+        ms = max_over_ranks(start.elapsed_time(stop))
         return ms, state, sol.engine.launch_count() - launches0, host_ms
-
-    def kernel_time(sol, state, dt, k):
-        """Average duration of the dominant kernel: CUDA events on the launch stream around k back-to-back launches into
-        preallocated outputs (a single launch after a synchronize would also time the host's enqueue latency)."""
-        eng = sol.engine
-        is_dek1 = isinstance(sol, ek1.DiagonalEK1)
-        mo = torch.empty_like(state.y.mean)
-        so = torch.empty_like(state.y.cov_sqrtm) if is_dek1 else None
-
-        def launch():
-            if is_dek1:
-                eng.dek1_attempt(state.t, dt, state.y.mean, state.y.cov_sqrtm, 1e-4, 1e-2, mean_out=mo, sc_out=so,
-                                 want_err_ref=sol.materialize_error_vectors)
-            else:
-                eng.ek0_attempt(state.t, dt, state.y.mean, state.y.cov_sqrtm_2, 1e-4, 1e-2, mean_out=mo,
-                                want_ref=sol.materialize_reference_state)
-
-        for _ in range(2):
-            launch()
-        barrier()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        for _ in range(k):
-            launch()
-        b.record()
-        torch.cuda.synchronize()
-        return a.elapsed_time(b) / k
 
     results = {}
     sampler = ClockSampler(local_rank)
     peak, peak_src = measured_peak()
     order = [args.solver] + [s for s in ("dek1", "ek0") if s != args.solver]
+    parity = {}
     for name in order:
         sol, state = make(name)
         # the step the adaptive rule itself would start with (step.py:111-115); a fixed larger dt makes the
@@ -280,71 +477,242 @@ def run_mine(args):
             sampler.start()
         ms, state, launches, host_ms = timed_steps(sol, state, dt, args.steps, args.warmup)
         clocks = sampler.stop() if (name == args.solver and rank == 0) else None
-        kms = kernel_time(sol, state, dt, min(args.steps, 10))
-        alg = ALG_BYTES[name](n, w) * (d / world)        # per launch, per GPU
+        kms = ms / args.steps                                    # one launch per step, back to back: the kernel's average duration
+        alg = ALG_BYTES[name](n, w) * (d / world)                # per launch, per GPU
+        traffic, traffic_src = recorded_traffic(args, name) if world == 1 else (None, "single-GPU captures only")
         results[name] = {
             "value": d * args.steps / (ms * 1e-3), "ms_per_step": ms / args.steps, "launches": launches, "clocks": clocks,
             "host_enqueue_ms_per_step": host_ms,
             "roofline": {"bound": "hbm", "achieved": alg / (kms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                         "frac": alg / (kms * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
-                         "kernel_ms": kms, "algorithmic_bytes_per_launch": alg},
+                         "frac": alg / (kms * 1e-3) / 1e9 / peak, "traffic": traffic, "traffic_source": traffic_src,
+                         "peak_source": peak_src, "kernel_ms": kms, "algorithmic_bytes_per_launch": alg,
+                         "kernel": "dek1_kernel" if name == "dek1" else ("ek0_fused_fhn_kernel" if args.workload == "fhn_2d" else "ek0_fused_chain_kernel")},
         }
-        if name == args.solver and not args.no_e2e:
-            results[name]["e2e_resident"] = e2e_resident_solve(torch, sol, state, dt, problem, world, dev, d, args.steps)
-            results[name]["e2e_device_loop"] = e2e_device_loop(torch, sol, state, dt, problem, d, args.steps)
+        # the controller-driven path: K attempts inside ONE persistent cooperative launch (halos + all-reduces in-kernel)
+        results[name]["device_loop"] = device_loop_timed(torch, sol, state, dt, d, args.steps, max_over_ranks, barrier)
+        if not args.no_parity and args.dtype == "f64":
+            parity[name] = parity_check(torch, args, sol, state, dt, problem, world, rank, dev)
+        if not args.no_e2e:
+            if name == args.solver:
+                results[name]["e2e_resident"] = e2e_resident_solve(torch, sol, state, dt, problem, world, dev, d, args.steps)
             torch.cuda.empty_cache()
-            results[name]["e2e"] = e2e_host_buffers(torch, sol, state, dt, problem, world, dev, d, max(2, min(args.steps, 5)))
+            results[name]["e2e"] = e2e_host_buffers(torch, sol, state, dt, problem, world, dev, d, args.steps)
         del sol, state
         torch.cuda.empty_cache()
 
-    if world == 1 and side == 2048 and args.dtype == "f64":
-        for name in results:
-            results[name]["roofline"]["traffic"] = _recorded_traffic(name)
-
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        v, cores, sample, _ = cpu_reference(args.solver, 16, 1)      # ~10 s of work on every host core
+        v, cores, sample, _ = cpu_reference(args, args.solver, 10 if args.solver == "dek1" else 20, 1)   # ~10-20 s of work per core
         cpu = {"value": v, "unit": "state-dims*steps/s", "cores": cores, "kind": "port", "sample": sample}
 
     if rank == 0:
         main = results[args.solver]
         other = [s for s in results if s != args.solver][0]
         line = {
-            "metric": "filter state-dims*steps/sec (fhn_2d, nu=4, fp64)" if args.dtype == "f64"
-            else "filter state-dims*steps/sec (fhn_2d, nu=4, fp32)",
+            "metric": metric_name(args),
             "value": main["value"], "unit": "state-dims*steps/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": main["ms_per_step"], "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
-            "config": {
-                "workload": f"ivp.fhn_2d {side}x{side} grid (d={d}), "
-                            f"{'ek1.DiagonalEK1' if args.solver == 'dek1' else 'ek0.KroneckerEK0'}(num_derivatives=4) "
-                            "attempt_step, y0 ~ U[0,1) seed 2, TaylorMode init, AdaptiveSteps tolerances fused",
-                "solver": args.solver,
-                "sharding": f"grid rows over {world} GPU(s); halo rows and scalar all-reduce through NVLink peer memory "
-                            "inside the step kernel (torch.distributed/NCCL only for rendezvous)",
-                "l2": "state (mean+factors) is 2.0 GB per attempt for DiagonalEK1 / 0.34 GB for KroneckerEK0, larger than the 126 MB L2; no flush needed",
+            "config": shared_config(args),
+            "notes": {
+                "sharding": f"{'grid rows' if args.workload == 'fhn_2d' else 'chain points'} over {world} GPU(s); halo rows and scalar "
+                            "all-reduces through NVLink peer memory inside the step kernel (torch.distributed/NCCL only for rendezvous)",
+                "l2": "the state streamed per attempt (mean+factors: 2.0 GB for DiagonalEK1, mean: 0.34 GB for KroneckerEK0 at "
+                      "d = 8.4M fp64, divided by the number of GPUs) is larger than the 126 MB L2 on 1-2 GPUs; no flush (every attempt "
+                      "reads the buffer the previous one wrote)",
+                "value": "attempt_step through the public API, one launch per attempt, state resident in HBM",
+                "device_loop": "the same attempts under the device-resident controller: ONE persistent cooperative launch for all "
+                               "--steps attempts (tdx_*_run_attempts), accept / reject and next dt decided on the device",
             },
             "clocks": main["clocks"],
             "e2e": main.get("e2e"),
             "e2e_resident": main.get("e2e_resident"),
-            "e2e_device_loop": main.get("e2e_device_loop"),
+            "device_loop": main.get("device_loop"),
             "gpu_launches": main["launches"],
             "roofline": main["roofline"],
             "cpu_baseline": cpu,
+            "parity": parity or None,
             "host_enqueue_ms_per_step": main["host_enqueue_ms_per_step"],
-            "also": {other: {k: results[other][k] for k in ("value", "ms_per_step", "roofline", "launches", "host_enqueue_ms_per_step")}},
+            "also": {other: {k: results[other].get(k) for k in ("value", "ms_per_step", "roofline", "launches", "host_enqueue_ms_per_step",
+                                                                "device_loop", "e2e")}},
         }
         print(json.dumps(line), flush=True)
     if world > 1:
         torch.distributed.destroy_process_group()
 
 
-def _recorded_traffic(solver):
-    path = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(path):
-        with open(path) as fh:
-            return json.load(fh).get(solver)
-    return None
+def device_loop_timed(torch, sol, state, dt, d, k, max_over_ranks, barrier):
+    """k attempts inside ONE persistent launch (tdx_*_run_attempts): CUDA events around the launch, max over ranks."""
+    eng = sol.engine
+    rule = eng.native_steprule(sol.steprule)
+    ring = sol._ctl_ring(state, 2, clone_first=True)
+
+    def run():
+        eng.ctl_begin(rule, state.t, dt, 1e300)          # no end time: every attempt of the launch is a real attempt
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        sol._ctl_launch(k, ring)
+        b.record()
+        barrier()
+        return a.elapsed_time(b)
+
+    run()
+    ms = max_over_ranks(run())
+    ctl = eng.ctl_read()
+    attempts = max(1, int(ctl.attempts))
+    return {"value": d * attempts / (ms * 1e-3), "unit": "state-dims*steps/s", "ms_per_attempt": ms / attempts, "attempts": attempts,
+            "accepted": int(ctl.accepted), "launches": 1, "failed": int(ctl.failed)}
+
+
+def parity_check(torch, args, sol, state, dt, problem, world, rank, dev):
+    """Outside the timed region: ONE attempt from the benchmark's state against the oracle.  DiagonalEK1: a window at the
+    start of every rank's shard (its first row / point needs the neighbour rank's halo); KroneckerEK0: the whole attempt on
+    rank 0 (the state is gathered).  Also: the kernels' fused norm against the norm recomputed from the output vectors."""
+    from oracle.ref_np import filters, problems
+    from tornadox_b200 import ek1
+
+    eng = sol.engine
+    is_dek1 = isinstance(sol, ek1.DiagonalEK1)
+    n = NU + 1
+    new, _ = sol.attempt_step(state, dt, *problem)
+    torch.cuda.synchronize()
+    out = {}
+    spec = eng.spec
+    nf = spec.n_fields
+    d_loc = state.y.mean.shape[1]
+    npts_loc = d_loc // nf
+    fhn = args.workload == "fhn_2d"
+    width = spec.grid_cols if fhn else 1          # coordinates per row of the sharded axis
+    extent_loc = npts_loc // width
+    take = min(6 if fhn else 2048, extent_loc)
+
+    def gather_rows(t, lo, hi):
+        """rows / points [lo, hi) of the sharded axis of a local (.., d_loc) tensor, both fields"""
+        idx = torch.cat([torch.arange(f * npts_loc + lo * width, f * npts_loc + hi * width, device=dev) for f in range(nf)])
+        return t.index_select(-1, idx) if t.dim() <= 2 and t.shape[-1] == d_loc else t.index_select(0, idx)
+
+    if is_dek1:
+        # neighbour's last row of the INPUT mean (for the stencil of this shard's first row)
+        last = gather_rows(state.y.mean, extent_loc - 1, extent_loc).contiguous()
+        above = None
+        if world > 1:
+            import torch.distributed as dist
+
+            bufs = [torch.empty_like(last) for _ in range(world)]
+            dist.all_gather(bufs, last)
+            above = bufs[rank - 1] if rank > 0 else None
+        wm = gather_rows(state.y.mean, 0, take).cpu().numpy().reshape(n, nf, take * width)
+        wsc = gather_rows(state.y.cov_sqrtm, 0, take).cpu().numpy()
+        halo = 0
+        if above is not None:
+            ab = above.cpu().numpy().reshape(n, nf, width)
+            wm = np.concatenate((ab, wm), axis=2)
+            halo = 1
+            # the neighbour's factor blocks do not enter this shard's results: any block will do for the halo row
+            wsc = np.concatenate([np.concatenate((wsc[f * take * width: f * take * width + width], wsc[f * take * width:(f + 1) * take * width]))
+                                  for f in range(nf)])
+        rows = take + halo
+        wm = wm.reshape(n, nf * rows * width)
+        g0 = eng.begin - halo                       # global row / point of the window's first row
+        if fhn:
+            side, dx = args.grid, 1.0 / args.grid
+            a_, b_, k_, tau = 2.8e-4, 5e-3, -0.005, 0.1
+
+            def f(_, x):
+                u, v = np.split(x, 2)
+                du = problems.laplace_2d(u.reshape(rows, side), dx=dx).reshape(-1)
+                dv = problems.laplace_2d(v.reshape(rows, side), dx=dx).reshape(-1)
+                return np.concatenate((a_ * du + u - u**3 - v + k_, (b_ * dv + u - v) / tau))
+
+            gr = np.arange(g0, g0 + rows)[:, None] * np.ones((1, side), dtype=int)
+            gc = np.arange(side)[None, :] * np.ones((rows, 1), dtype=int)
+            nrep = (gr == 0).astype(int) + (gr == side - 1) + (gc == 0) + (gc == side - 1)
+            dlap = (-(4.0 - nrep) / dx**2).reshape(-1)
+
+            def dfd(_, x):
+                u, _v = np.split(x, 2)
+                return np.concatenate((a_ * dlap + 1.0 - 3.0 * u**2, (b_ * dlap - 1.0) / tau * np.ones_like(u)))
+        else:
+            N = args.points
+            c = (N + 1) ** 2 / 50.0
+
+            def f(_, x):
+                u, v = np.split(x, 2)
+                ul = 1.0 if g0 == 0 else u[0]
+                vl = 3.0 if g0 == 0 else v[0]
+                up = np.concatenate(([ul], u, [u[-1]]))
+                vp = np.concatenate(([vl], v, [v[-1]]))
+                return np.concatenate((1.0 + u**2 * v - 4.0 * u + c * (up[:-2] - 2.0 * u + up[2:]),
+                                       3.0 * u - u**2 * v + c * (vp[:-2] - 2.0 * v + vp[2:])))
+
+            def dfd(_, x):
+                u, v = np.split(x, 2)
+                return np.concatenate((2.0 * u * v - 4.0 - 2.0 * c, -u**2 - 2.0 * c))
+        ost, _ = filters.diagonal_ek1_attempt(filters.FilterState(float(state.t), wm, wsc, None, None), dt, f, dfd, NU)
+        # keep what the window computes exactly: drop the halo row on top and the last row (its lower neighbour is outside)
+        keep_lo, keep_hi = halo, rows - 1
+        keep = np.concatenate([np.arange(fl * rows * width + keep_lo * width, fl * rows * width + keep_hi * width) for fl in range(nf)])
+        got_m = gather_rows(new.y.mean, 0, take - 1).cpu().numpy()
+        got_s = gather_rows(new.y.cov_sqrtm, 0, take - 1).cpu().numpy()
+
+        def rel(x, y):
+            return float(np.max(np.abs(x - y)) / max(np.max(np.abs(y)), 1e-300))
+
+        errs = torch.tensor([rel(got_m, ost.mean[:, keep]), rel(got_s, ost.cov_sqrtm[keep])], device=dev, dtype=torch.float64)
+        if world > 1:
+            torch.distributed.all_reduce(errs, op=torch.distributed.ReduceOp.MAX)
+        out["window"] = f"first {take - 1} {'grid rows' if fhn else 'points'} of every rank's shard vs the NumPy oracle"
+        out["max_rel_err_mean"], out["max_rel_err_cov_sqrtm"] = float(errs[0]), float(errs[1])
+        # fused norm vs the norm of the materialised vectors (torch fp64, all ranks)
+        if new.error_estimate is not None:
+            ratio = dt * new.error_estimate.double() / (1e-4 + 1e-2 * new.reference_state.double())
+            tot = (ratio * ratio).sum().reshape(1)
+            if world > 1:
+                torch.distributed.all_reduce(tot)
+            fused = float(new.scaled_error_norm_sq_sum.sum())
+            out["norm_sq_sum_fused"], out["norm_sq_sum_recomputed"] = fused, float(tot)
+            out["norm_rel_diff"] = abs(fused - float(tot)) / max(abs(float(tot)), 1e-300)
+        out["ok"] = bool(out["max_rel_err_mean"] < 1e-10 and out["max_rel_err_cov_sqrtm"] < 1e-10 and out.get("norm_rel_diff", 0.0) < 1e-10)
+    else:
+        # the whole KroneckerEK0 attempt on rank 0
+        from tornadox_b200.engine import local_slices
+
+        def gather_full(t):
+            if world == 1:
+                return t.cpu().numpy()
+            import torch.distributed as dist
+
+            parts = [None] * world
+            dist.all_gather_object(parts, (eng.begin, eng.end, t.cpu().numpy()))
+            if rank != 0:
+                return None
+            full = np.empty((n, eng.d_global))
+            for b, e, arr in parts:
+                sl = local_slices(spec, b, e)
+                per = arr.shape[1] // nf
+                for fl, s in enumerate(sl):
+                    full[:, s] = arr[:, fl * per:(fl + 1) * per]
+            return full
+
+        m_in, m_out = gather_full(state.y.mean), gather_full(new.y.mean)
+        if rank == 0:
+            _, oprob, _ = initial_condition(args)
+            ost, _ = filters.kronecker_ek0_attempt(filters.FilterState(float(state.t), m_in, state.y.cov_sqrtm_2.cpu().numpy(), None, None),
+                                                   dt, oprob.f, NU)
+            e_mean = float(np.max(np.abs(m_out - ost.mean)) / np.max(np.abs(ost.mean)))
+            e_cl = float(np.max(np.abs(new.y.cov_sqrtm_2.cpu().numpy() - ost.cov_sqrtm)) / np.max(np.abs(ost.cov_sqrtm)))
+            e_err = abs(float(new.error_estimate) - ost.error_estimate) / abs(ost.error_estimate)
+            tol = 1e-4 + 1e-2 * ost.reference_state
+            ref_sum = float(np.sum((dt * ost.error_estimate / tol) ** 2))
+            fused = float(new.scaled_error_norm_sq_sum.sum())
+            out = {"window": "the whole attempt vs the NumPy oracle (state gathered on rank 0)", "max_rel_err_mean": e_mean,
+                   "max_rel_err_cov_sqrtm": e_cl, "rel_err_error_estimate": e_err, "norm_sq_sum_fused": fused,
+                   "norm_sq_sum_oracle": ref_sum, "norm_rel_diff": abs(fused - ref_sum) / abs(ref_sum)}
+            out["ok"] = bool(e_mean < 1e-10 and e_cl < 1e-10 and e_err < 1e-10 and out["norm_rel_diff"] < 1e-10)
+    if world > 1:
+        torch.distributed.barrier()
+    return out
 
 
 def e2e_host_buffers(torch, sol, state, dt, problem, world, dev, d, k):
@@ -353,8 +721,8 @@ def e2e_host_buffers(torch, sol, state, dt, problem, world, dev, d, k):
 
     DiagonalEK1: the library's host-buffer entry point (tdx_dek1_attempt_step_host[_sharded]) streams the (shard of the)
     state through the device in chunks with the copies in both directions overlapping the kernels; a sharded run first
-    exchanges the halos of the shards' edge rows.  KroneckerEK0: plain copy-in / step / copy-out around the device-resident
-    call."""
+    exchanges the halos of the shards' edge rows.  KroneckerEK0: copy-in / step / copy-out around the device-resident
+    call (0.34 GB each way at d = 8.4M)."""
     from tornadox_b200 import ek1, odefilter, rv
 
     is_dek1 = isinstance(sol, ek1.DiagonalEK1)
@@ -363,9 +731,8 @@ def e2e_host_buffers(torch, sol, state, dt, problem, world, dev, d, k):
     h_mean_in = torch.empty(y.mean.shape, dtype=y.mean.dtype, pin_memory=True).copy_(y.mean)
     h_fac_in = torch.empty(fac.shape, dtype=fac.dtype, pin_memory=True).copy_(fac)
     h2d = h_mean_in.numel() * h_mean_in.element_size() + h_fac_in.numel() * h_fac_in.element_size()
-    pipelined = is_dek1
 
-    if pipelined:
+    if is_dek1:
         host_state = odefilter.ODEFilterState(state.t, rv.BatchedMultivariateNormal(h_mean_in, h_fac_in), None, None)
         vec_bytes = 2 * y.mean.shape[1] * y.mean.element_size() if sol.materialize_error_vectors else 0
         if world > 1:   # + the shard's edge rows for the halo exchange that precedes the pipeline
@@ -387,16 +754,15 @@ def e2e_host_buffers(torch, sol, state, dt, problem, world, dev, d, k):
         def one():
             d_mean.copy_(h_mean_in, non_blocking=True)
             d_fac.copy_(h_fac_in, non_blocking=True)
-            if is_dek1:
-                st = odefilter.ODEFilterState(state.t, rv.BatchedMultivariateNormal(d_mean, d_fac), None, None)
-            else:
-                st = odefilter.ODEFilterState(state.t, rv.LeftIsotropicMatrixNormal(d_mean, y.d, d_fac), None, None)
+            st = odefilter.ODEFilterState(state.t, rv.LeftIsotropicMatrixNormal(d_mean, y.d, d_fac), None, None)
             new, _ = sol.attempt_step(st, dt, *problem)
             h_mean_out.copy_(new.y.mean, non_blocking=True)
-            h_fac_out.copy_(new.y.cov_sqrtm if is_dek1 else new.y.cov_sqrtm_2, non_blocking=True)
+            h_fac_out.copy_(new.y.cov_sqrtm_2, non_blocking=True)
             h_norm.copy_(new.scaled_error_norm_sq_sum.sum().reshape(1), non_blocking=True)
+            torch.cuda.current_stream().synchronize()                # the step's result is in host memory when the call returns
 
-        what = "attempt_step with the whole state in pinned host memory: H2D of mean+factors, kernel, D2H of mean+factors+norm, every step"
+        what = ("KroneckerEK0.attempt_step with the state in pinned host memory: H2D of mean + factor, the fused kernel, D2H of "
+                "mean + factor + norm, every step")
         d2h = h2d + 8
 
     one()
@@ -410,17 +776,17 @@ def e2e_host_buffers(torch, sol, state, dt, problem, world, dev, d, k):
         one()
     b.record()
     torch.cuda.synchronize()
-    ms = max(a.elapsed_time(b), (time.perf_counter() - t0) * 1e3)   # the pipelined call blocks the host: wall clock counts
+    ms = max(a.elapsed_time(b), (time.perf_counter() - t0) * 1e3)   # the calls block the host: wall clock counts
     if world > 1:
         t = torch.tensor([ms], device=dev, dtype=torch.float64)
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
         ms = float(t.item())
     return {"value": d * k / (ms * 1e-3), "unit": "state-dims*steps/s", "h2d_bytes_per_step": h2d * world,
-            "d2h_bytes_per_step": d2h * world, "ms_per_step": ms / k, "what": what}
+            "d2h_bytes_per_step": d2h * world, "ms_per_step": ms / k, "steps": k, "what": what}
 
 
 def e2e_resident_solve(torch, sol, state, dt, problem, world, dev, d, k):
-    """The solver's own loop (perform_full_step): state stays in HBM, the host reads the error norm (8 B D2H)
+    """The solver's own host loop (perform_full_step): state stays in HBM, the host reads the error norm (8 B D2H)
     and decides accept/reject + next dt every attempt."""
     torch.cuda.synchronize()
     t0 = time.perf_counter()
@@ -434,38 +800,6 @@ def e2e_resident_solve(torch, sol, state, dt, problem, world, dev, d, k):
     return {"value": d * attempts / sec, "unit": "state-dims*steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 8,
             "attempts": attempts, "accepted": k, "ms_per_attempt": sec / attempts * 1e3,
             "what": "public perform_full_step loop (adaptive accept/reject on the host), wall clock incl. the per-attempt sync"}
-
-
-def e2e_device_loop(torch, sol, state, dt, problem, d, k):
-    """k attempts of the adaptive solve under the device-resident step controller: dt, accept / reject and the buffer flip
-    are decided by the kernels; the host enqueues the batch and reads the controller block once at the end."""
-    from tornadox_b200 import ek1
-
-    eng = sol.engine
-    rule = eng.native_steprule(sol.steprule)
-    is_dek1 = isinstance(sol, ek1.DiagonalEK1)
-    pair_a = (state.y.mean, state.y.cov_sqrtm if is_dek1 else state.y.cov_sqrtm_2)
-    pair_b = (torch.empty_like(pair_a[0]), torch.empty_like(pair_a[1]))
-    err = torch.empty((), dtype=pair_a[0].dtype, device=pair_a[0].device)
-
-    def batch():
-        eng.ctl_begin(rule, state.t, dt, 1e300)          # no end time: every launch of the batch is a real attempt
-        if is_dek1:
-            eng.dek1_enqueue_attempts(k, pair_a, pair_b, None, None)
-        else:
-            eng.ek0_enqueue_attempts(k, pair_a, pair_b, err, None)
-        return eng.ctl_read()
-
-    batch()
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    ctl = batch()
-    sec = time.perf_counter() - t0
-    attempts = max(1, int(ctl.attempts))
-    return {"value": d * attempts / sec, "unit": "state-dims*steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
-            "attempts": attempts, "accepted": int(ctl.accepted), "ms_per_attempt": sec / attempts * 1e3,
-            "what": "adaptive attempts under the device-resident step controller (tdx_*_enqueue_attempts): wall clock per "
-                    "attempt incl. enqueueing the batch and one controller read; error vectors not materialised"}
 
 
 def main():

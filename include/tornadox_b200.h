@@ -22,7 +22,13 @@
  *  - layouts are the reference's: mean (n, d) C-order, DiagonalEK1 factors (d, n, n) C-order,
  *    KroneckerEK0 factor (n, n) C-order; n = nu + 1; dtype is f64 (default) or f32.
  *  - multi-GPU: one context per process/GPU owning a shard (rows of the fhn grid, or a range of the
- *    1-d chain) of BOTH fields; the caller exchanges the halo buffers and all-reduces the scalars.
+ *    1-d chain) of BOTH fields.  Halos and scalar sums travel through NVLink peer memory written and read by the step
+ *    kernels themselves (tdx_comm_*, flags TDX_STEP_COMM_PACK | TDX_STEP_COMM_REDUCE); a caller without peer access can
+ *    still exchange the halo buffers and all-reduce the scalars itself (tdx_pack_halo + the three-phase entry points).
+ *  - sums over the state dimension (error norm, sum of z^2) are formed from one partial per 256-coordinate tile (or per
+ *    grid row of a 256-column strip) in a fixed order over 16 global chunks, so their bits do not depend on how many CTAs ran
+ *    and -- when the shard boundaries fall on chunk boundaries, e.g. 2 / 4 / 8 equal shards of a 2048 x 2048 grid -- not
+ *    on the number of GPUs either: the accepted-step sequence is identical at 1 / 2 / 4 / 8 GPUs.
  */
 #ifndef TORNADOX_B200_H_
 #define TORNADOX_B200_H_
@@ -243,6 +249,46 @@ int tdx_dek1_enqueue_attempts(tdx_ctx* ctx, int k, uint32_t flags, void* mean_a,
 int tdx_ek0_enqueue_attempts(tdx_ctx* ctx, int k, uint32_t flags, void* mean_a, void* Cl_a, void* mean_b, void* Cl_b,
                              void* err_out, void* ref_out, void* stream);
 int tdx_ctl_read(tdx_ctx* ctx, tdx_ctl_state* out, double* hist_t, double* hist_dt, void* stream);
+
+/* ---- many attempts in ONE launch ----------------------------------------------------------------------------------
+ * The reference compiles the whole accept / reject loop into one ``lax.while_loop`` (odefilter.py:225-344).  Here
+ * tdx_*_run_attempts is ONE persistent cooperative kernel that runs up to ``k`` attempts: after every attempt the last CTA
+ * reduces the norm (over the ranks too), updates the controller and releases an in-kernel grid barrier; halo delivery and both
+ * all-reduces of a sharded run happen inside the same launch.  The launch ends early when the solve reaches tmax.
+ * State buffers form a RING of ``nbuf`` (mean, factor) pairs (2 <= nbuf <= TDX_CTL_MAX_RING; the same ring must be passed to
+ * every launch of a solve): attempt output goes to slot (cur + 1) % nbuf, an accepted attempt advances ``cur``, so accepted
+ * state number j (0 = the initial state, in slot 0) lives in slot j % nbuf until nbuf - 1 further steps have been accepted.
+ *   tdx_ctl_begin_ex   tdx_ctl_begin with options: ring size, time stops (odefilter.py:355-373: the solve lands exactly on
+ *                      every stop), and ``follow``: the kernel publishes its progress to mapped pinned memory and does not
+ *                      rewrite a ring slot before the host has released the state it holds
+ *   tdx_ctl_poll       (follow) accepted / attempted steps so far, without synchronising anything
+ *   tdx_ctl_history    (follow) time and step of accepted state ``state_index`` >= 1 (kept for the last TDX_CTL_HISTORY states)
+ *   tdx_ctl_consume    (follow) states [0, upto] have been copied out of the ring
+ *   tdx_ctl_abort      (follow) stop the running launch at the next attempt boundary
+ * A wait inside the kernels (peer halos, reductions, grid barriers) that exceeds TDX_WAIT_TIMEOUT_MS (environment, default
+ * 4000) poisons the attempt's norm with NaN and stops the solve with ``failed`` = 2 on every rank. */
+#define TDX_CTL_MAX_RING 8
+typedef struct {
+    int32_t nbuf;          /* ring size                                                                            */
+    int32_t follow;        /* 1: dense output, the host follows the solve                                          */
+    const double* stop_at; /* HOST array of time stops, sorted ascending, or NULL                                   */
+    int64_t n_stops;
+} tdx_ctl_options;
+typedef struct {
+    int64_t accepted, attempts;
+} tdx_ctl_progress;
+int tdx_ctl_begin_ex(tdx_ctx* ctx, const tdx_steprule* rule, double t0, double dt0, double tmax,
+                     const tdx_ctl_options* options, void* stream);
+/* err_ring / ref_ring: per-slot error_estimate (DiagonalEK1: (d) vectors or NULL; KroneckerEK0: scalars, required) and
+ * reference_state vectors (NULL, or NULL entries: not written), so that they belong to the state in the same slot */
+int tdx_dek1_run_attempts(tdx_ctx* ctx, int k, uint32_t flags, void* const* mean_ring, void* const* sc_ring, int nbuf,
+                          void* const* err_ring, void* const* ref_ring, void* stream);
+int tdx_ek0_run_attempts(tdx_ctx* ctx, int k, uint32_t flags, void* const* mean_ring, void* const* Cl_ring, int nbuf,
+                         void* const* err_ring, void* const* ref_ring, void* stream);
+int tdx_ctl_poll(tdx_ctx* ctx, tdx_ctl_progress* out);
+int tdx_ctl_history(tdx_ctx* ctx, int64_t state_index, double* t, double* dt, int64_t* attempts);
+int tdx_ctl_consume(tdx_ctx* ctx, int64_t upto);
+int tdx_ctl_abort(tdx_ctx* ctx);
 
 /* ---- peer-memory exchange over NVLink (multi-GPU, one process per GPU on one node) -------------------------
  * No reference counterpart (the reference is single-device).  Instead of NCCL calls between the kernels, every

@@ -30,8 +30,12 @@ def kronecker_ek0_initial_state(mean0, cov_sqrtm0, t0):
     return FilterState(t0, mean0, cov_sqrtm0, np.nan, np.nan * np.ones(d))
 
 
-def kronecker_ek0_attempt(state, dt, f, nu):
-    """One ``KroneckerEK0.attempt_step`` -- tornadox/ek0.py:152-193."""
+def kronecker_ek0_attempt(state, dt, f, nu, sum_over_shards=None, d_global=None):
+    """One ``KroneckerEK0.attempt_step`` -- tornadox/ek0.py:152-193.
+
+    ``sum_over_shards`` / ``d_global``: when the state is one shard of a larger problem (bench.py's CPU arm cuts the grid into
+    row strips, one per core) the calibration needs z^T z and the dimension of the WHOLE problem (ek0.py:126-128); the callable
+    turns the local sum into the global one.  Default: the state is the whole problem."""
     A, Ql = prior.transition_1d(nu), prior.diffusion_sqrt_1d(nu)
     e1 = prior.unit_row(nu, 1)
     _m, _Cl = state.mean, state.cov_sqrtm
@@ -53,7 +57,8 @@ def kronecker_ek0_attempt(state, dt, f, nu):
     # [Calibration]  ek0.py:123-130
     Q11 = Ql[1, :] @ Ql[1, :].T
     HQH = P[1, 1] ** 2 * Q11
-    sigma_squared = z.T @ z / HQH / z.shape[0]
+    z_sq = z.T @ z if sum_over_shards is None else sum_over_shards(z.T @ z)
+    sigma_squared = z_sq / HQH / (z.shape[0] if d_global is None else d_global)
     error_estimate = np.sqrt(sigma_squared * HQH)
 
     # [Predict covariance]  ek0.py:175

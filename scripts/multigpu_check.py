@@ -1,5 +1,8 @@
-"""Multi-GPU correctness check (launch with torchrun): sharded DiagonalEK1 / KroneckerEK0 attempts with NCCL halo
-exchange + scalar all-reduce must reproduce the unsharded NumPy oracle.  Prints MULTIGPU_CHECK_OK on rank 0."""
+"""Multi-GPU correctness check (launch with torchrun): sharded DiagonalEK1 / KroneckerEK0 attempts (halos and scalar
+all-reduces through NVLink peer memory inside the step kernels) must reproduce the unsharded NumPy oracle, and -- where the
+shard boundaries fall on the chunk grid of the reductions -- the SAME BITS of the error norm and the same accepted-step
+sequence as an unsharded run on one GPU (step.py:93-104 is one norm).  Prints MULTIGPU_CHECK_OK on rank 0 and
+writes a JSON summary to gpurun_out/multigpu_check_<world>gpu.json."""
 import math
 import os
 import sys
@@ -15,7 +18,7 @@ from helpers import make_pair  # noqa: E402
 from oracle.ref_np import driver as odriver  # noqa: E402
 from oracle.ref_np import filters as ofilters  # noqa: E402
 from tornadox_b200 import ek0, ek1, step  # noqa: E402
-from tornadox_b200.engine import local_slices  # noqa: E402
+from tornadox_b200.engine import local_slices, reduction_is_sharding_independent  # noqa: E402
 
 
 def main():
@@ -26,6 +29,7 @@ def main():
     dist.init_process_group("nccl", device_id=dev)
     group = dist.group.WORLD
     worst = 0.0
+    report = {"world": world, "attempts": [], "solves": []}
     from helpers import random_state
     from tornadox_b200 import odefilter, rv
 
@@ -55,6 +59,25 @@ def main():
                 ost, _ = ofilters.kronecker_ek0_attempt(ofilters.FilterState(0.3, mean, single, None, None), dt, o.f, nu)
             st, _ = sol.attempt_step(odefilter.ODEFilterState(0.3, y, None, None), dt, *p)
             norm = step.norm_from_sq_sum(st.scaled_error_norm_sq_sum, d)
+            # the same attempt unsharded on this rank's GPU: the reduced sum must have the same bits
+            one = cls(num_derivatives=nu, steprule=step.AdaptiveSteps())
+            one.initialize(*p)
+            mean_g = torch.as_tensor(mean, device=dev)
+            if name == "dek1":
+                y1 = rv.BatchedMultivariateNormal(mean_g, torch.as_tensor(blocks, device=dev))
+            else:
+                y1 = rv.LeftIsotropicMatrixNormal(mean_g, d, torch.as_tensor(single, device=dev))
+            st1, _ = one.attempt_step(odefilter.ODEFilterState(0.3, y1, None, None), dt, *p)
+            sum_sharded, sum_one = float(st.scaled_error_norm_sq_sum.sum()), float(st1.scaled_error_norm_sq_sum.sum())
+            independent = reduction_is_sharding_independent(eng.spec, world)
+            if independent:
+                assert sum_sharded == sum_one, (kind, size, name, "norm sum differs from the single-GPU bits", sum_sharded, sum_one)
+                assert torch.equal(st.y.mean, st1.y.mean[:, torch.as_tensor(idx, device=dev)]), (kind, size, name, "mean bits")
+            else:
+                assert abs(sum_sharded - sum_one) <= 1e-12 * abs(sum_one), (kind, size, name, sum_sharded, sum_one)
+            report["attempts"].append(dict(problem=f"{kind} {size}", solver=name, sharding_independent=bool(independent),
+                                           norm_sq_sum_sharded=sum_sharded.hex(), norm_sq_sum_single_gpu=sum_one.hex(),
+                                           bit_equal=bool(sum_sharded == sum_one)))
             ref_norm = odriver.AdaptiveSteps().scale_error_estimate(dt * ost.error_estimate, ost.reference_state)
             e_mean = np.max(np.abs(st.y.mean.cpu().numpy() - ost.mean[:, idx])) / np.max(np.abs(ost.mean))
             if name == "dek1":
@@ -92,12 +115,28 @@ def main():
             else:
                 states, info, _ = odriver.solve_kronecker_ek0(o, nu, odriver.AdaptiveSteps(), m0, c0)
                 cls = ek0.KroneckerEK0
+            # unsharded on this rank's GPU, under the device-resident controller: the reference sequence of accepted steps
+            one = cls(num_derivatives=nu, steprule=step.AdaptiveSteps())
+            one.device_loop_batch = 64
+            fin1, info1 = one.simulate_final_state(p)
+            st1, ht1, hd1 = one.engine.ctl_read(history=True)
             for device_loop in (False, True):
                 sol = cls(num_derivatives=nu, steprule=step.AdaptiveSteps(), process_group=group)
                 sol.device_loop = device_loop
                 sol.device_loop_batch = 5
                 final, finfo = sol.simulate_final_state(p)
                 eng = sol.engine
+                if device_loop:
+                    stN, htN, hdN = eng.ctl_read(history=True)
+                    independent = reduction_is_sharding_independent(eng.spec, world)
+                    n_acc = min(int(stN.accepted), len(htN))
+                    same = bool(stN.accepted == st1.accepted and stN.attempts == st1.attempts and np.array_equal(htN[:n_acc], ht1[:n_acc])
+                                and np.array_equal(hdN[:n_acc], hd1[:n_acc]))
+                    if independent:
+                        assert same, (kind, name, "accepted-step sequence differs from the single-GPU run", stN.accepted, st1.accepted)
+                    report["solves"].append(dict(problem=f"{kind} {size}", solver=name, sharding_independent=bool(independent),
+                                                 accepted=int(stN.accepted), attempts=int(stN.attempts),
+                                                 identical_step_sequence_to_single_gpu=same))
                 idx = np.concatenate([np.arange(o.y0.shape[0])[s] for s in local_slices(eng.spec, eng.begin, eng.end)])
                 assert dict(finfo) == info, (kind, name, device_loop, finfo, info)
                 assert abs(final.t - states[-1].t) <= 1e-12 * abs(states[-1].t), (kind, name, device_loop)
@@ -107,7 +146,17 @@ def main():
     t = torch.tensor([worst], device=dev, dtype=torch.float64)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     if rank == 0:
-        print(f"MULTIGPU_CHECK_OK world={world} worst_rel_err={float(t):.3e}")
+        import json
+
+        report["worst_rel_err_vs_oracle"] = float(t)
+        out_dir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+        os.makedirs(out_dir, exist_ok=True)
+        with open(os.path.join(out_dir, f"multigpu_check_{world}gpu.json"), "w") as fh:
+            json.dump(report, fh, indent=1)
+        n_bits = sum(1 for a in report["attempts"] if a["bit_equal"])
+        n_seq = sum(1 for a in report["solves"] if a["identical_step_sequence_to_single_gpu"])
+        print(f"MULTIGPU_CHECK_OK world={world} worst_rel_err={float(t):.3e} bit_equal_norms={n_bits}/{len(report['attempts'])} "
+              f"identical_step_sequences={n_seq}/{len(report['solves'])}")
     dist.destroy_process_group()
 
 

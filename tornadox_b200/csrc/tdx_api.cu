@@ -67,24 +67,29 @@ struct AllReduceArgs {
     double* vals;
     int count, rank, world;
     unsigned long long seq;
+    unsigned long long timeout_ns;
 };
 
 __global__ void comm_allreduce_kernel(const __grid_constant__ AllReduceArgs a) {
     const int r = threadIdx.x;
     const int parity = (int)(a.seq & 1ull);
+    __shared__ int s_bad;
+    if (r == 0) s_bad = 0;
+    __syncthreads();
     if (r < a.world) {
         CommHeader* dst = a.peer[r];
         for (int j = 0; j < a.count; ++j) dst->red_val[parity][a.rank][j] = a.vals[j];
+        dst->red_cnt[parity][a.rank] = a.count;
         __threadfence_system();
         st_release_sys(&dst->red_flag[parity][a.rank], a.seq);
     }
     __syncthreads();
-    if (r < a.world) spin_until(&a.local->red_flag[parity][r], a.seq, &a.local->error);
+    if (r < a.world && !spin_until(&a.local->red_flag[parity][r], a.seq, &a.local->error, a.timeout_ns)) s_bad = 1;
     __syncthreads();
     if (r < a.count) {
         double acc = 0.0;
         for (int k = 0; k < a.world; ++k) acc += *((volatile double*)&a.local->red_val[parity][k][r]);
-        a.vals[r] = acc;
+        a.vals[r] = s_bad ? nan("") : acc;     // a dead peer must not go unnoticed
     }
 }
 
@@ -176,9 +181,27 @@ struct tdx_ctx {
     bool comm_opened[kMaxWorld] = {};
     int rank = 0, world = 1, lower = -1, upper = -1;
     unsigned long long halo_seq = 0, red_seq = 0;
-    unsigned long long mid_seq = 0;  // fused EK0 launches so far (the in-kernel barrier flag counts them)
+    unsigned long long mid_seq = 0;  // fused EK0 attempts so far (the in-kernel barrier flag counts them)
+    unsigned long long cl_seq = 0;   // fused EK0: "new factor written" flag, one count per attempt
     long long halo_cap = 0;          // elements per parity and side
+    // unit partials of the sharding-independent reductions: [2][unit_cap]
+    double* units = nullptr;
+    long long unit_cap = 0;
+    unsigned long long timeout_ns = 0;   // in-kernel waits (peers, grid barriers); TDX_WAIT_TIMEOUT_MS, default 4000
+    // device-resident controller extras
+    double* ctl_stops = nullptr;     // device copy of the time stops
+    long long ctl_stops_cap = 0;
+    HostFeed* feed = nullptr;        // mapped pinned
+    HostFeed* feed_dev = nullptr;
+    int ctl_nbuf = 2;
 };
+
+static unsigned long long env_timeout_ns() {
+    const char* v = std::getenv("TDX_WAIT_TIMEOUT_MS");
+    double ms = v ? std::atof(v) : 4000.0;
+    if (!(ms > 0.0)) ms = 4000.0;
+    return (unsigned long long)(ms * 1.0e6);
+}
 
 static size_t comm_bytes(const tdx_ctx* ctx) {
     return sizeof(CommHeader) + 4 * (size_t)ctx->halo_cap * (ctx->dtype == TDX_F64 ? 8 : 4) + 64;
@@ -232,6 +255,7 @@ int tdx_create(tdx_ctx** out, int device, int dtype) {
     ctx->device = device;
     ctx->dtype = dtype;
     ctx->eval_ops = find_eval_ops(dtype);
+    ctx->timeout_ns = env_timeout_ns();
     int prev = 0;
     cudaGetDevice(&prev);
     cudaSetDevice(device);
@@ -261,6 +285,9 @@ int tdx_destroy(tdx_ctx* ctx) {
     if (ctx->host_norm) cudaFreeHost(ctx->host_norm);
     cudaFree(ctx->zsq_scratch);
     cudaFree(ctx->partials);
+    cudaFree(ctx->units);
+    cudaFree(ctx->ctl_stops);
+    if (ctx->feed) cudaFreeHost(ctx->feed);
     cudaFree(ctx->ticket);
     cudaFree(ctx->mid);
     for (int r = 0; r < kMaxWorld; ++r)
@@ -385,6 +412,18 @@ int tdx_set_problem(tdx_ctx* ctx, const tdx_problem_desc* d) {
         e = cudaMalloc(&ctx->partials, 2 * sizeof(double) * (size_t)grid);
         ctx->partials_cap = (e == cudaSuccess) ? grid : 0;
     }
+    {
+        // one partial per 256-coordinate tile, or per (grid row, 256-column block) of the fused fhn_2d kernel
+        long long units = grid_for(g);
+        if (g.kind == IVP_FHN2D) units = std::max(units, (long long)g.rows * ((g.cols + TDX_EK0_W - 1) / TDX_EK0_W));
+        units = (units + 63) / 64 * 64;
+        if (e == cudaSuccess && units > ctx->unit_cap) {
+            cudaFree(ctx->units);
+            ctx->units = nullptr;
+            e = cudaMalloc(&ctx->units, 2 * sizeof(double) * (size_t)units);
+            ctx->unit_cap = (e == cudaSuccess) ? units : 0;
+        }
+    }
     cudaSetDevice(prev);
     if (e != cudaSuccess) return cuda_fail((int)e, "tdx_set_problem");
 
@@ -472,32 +511,46 @@ static void edge_counts(const Geo& g, int& n_first, int& n_last) {
     }
 }
 
-// where this shard's edge state goes for the CURRENT halo sequence number (ctx->halo_seq already advanced)
+// where this shard's edge state goes (parity-0 buffers / flags; the kernels add the parity of the sequence number)
 static PackPeer<double> pack_descriptor(const tdx_ctx* ctx) {
     PackPeer<double> pk{};
     edge_counts(ctx->geo, pk.n_first, pk.n_last);
-    const int parity = (int)(ctx->halo_seq & 1ull);
     if (ctx->lower >= 0) {   // our first rows are the lower neighbour's UPPER halo
         unsigned char* base = ctx->comm_peer[ctx->lower];
-        pk.dst_lower = reinterpret_cast<double*>(comm_halo(ctx, base, 1, parity));
-        pk.flag_lower = &reinterpret_cast<CommHeader*>(base)->halo_flag_hi[parity];
+        pk.dst_lower = reinterpret_cast<double*>(comm_halo(ctx, base, 1, 0));
+        pk.flag_lower = &reinterpret_cast<CommHeader*>(base)->halo_flag_hi[0];
     }
     if (ctx->upper >= 0) {
         unsigned char* base = ctx->comm_peer[ctx->upper];
-        pk.dst_upper = reinterpret_cast<double*>(comm_halo(ctx, base, 0, parity));
-        pk.flag_upper = &reinterpret_cast<CommHeader*>(base)->halo_flag_lo[parity];
+        pk.dst_upper = reinterpret_cast<double*>(comm_halo(ctx, base, 0, 0));
+        pk.flag_upper = &reinterpret_cast<CommHeader*>(base)->halo_flag_lo[0];
     }
     pk.done_count = reinterpret_cast<CommHeader*>(ctx->comm_local)->pack_count;
     pk.seq = ctx->halo_seq;
+    pk.parity_stride = (long long)((size_t)ctx->halo_cap * esize(ctx->dtype));     // bytes (Launch::typed_pack converts)
     pk.enabled = 1;
     return pk;
 }
 
+static bool uses_comm_halos(const tdx_ctx* ctx, unsigned flags) {
+    return (flags & (TDX_STEP_COMM_HALO | TDX_STEP_COMM_PACK)) && ctx->comm_local;
+}
+
 static Workspace make_ws(const tdx_ctx* ctx, unsigned flags = 0u) {
     const bool second = (flags & 6u) == TDX_STEP_TILES_RIM;
-    Workspace ws{ctx->partials + (second ? ctx->partials_cap : 0), ctx->ticket + (second ? 1 : 0), ctx->mid, 0,
-                 ctx->halo_lo > 0, ctx->halo_hi > 0, CommWait{nullptr, nullptr, 0ull, nullptr}, CommReduce{},
-                 PackPeer<double>{}};
+    Workspace ws{};
+    ws.partials = ctx->partials + (second ? ctx->partials_cap : 0);
+    ws.ticket = ctx->ticket + (second ? 1 : 0);
+    ws.mid = ctx->mid;
+    ws.reserve_ctas = 0;
+    ws.has_lo = ctx->halo_lo > 0;
+    ws.has_hi = ctx->halo_hi > 0;
+    ws.wait = CommWait{nullptr, nullptr, 0ull, nullptr, ctx->timeout_ns};
+    ws.unit_a = ctx->units;
+    ws.unit_b = ctx->units ? ctx->units + ctx->unit_cap : nullptr;
+    ws.unit_cap = ctx->unit_cap;
+    ws.cl_flag = reinterpret_cast<unsigned long long*>(static_cast<unsigned char*>(ctx->mid) + 136);
+    ws.cl_seq = ctx->cl_seq;
     if ((flags & TDX_STEP_COMM_PACK) && ctx->comm_local) ws.pack = pack_descriptor(ctx);
     if ((flags & TDX_STEP_COMM_REDUCE) && ctx->comm_local) {
         ws.reduce.local = reinterpret_cast<CommHeader*>(ctx->comm_local);
@@ -505,48 +558,56 @@ static Workspace make_ws(const tdx_ctx* ctx, unsigned flags = 0u) {
         ws.reduce.rank = ctx->rank;
         ws.reduce.world = ctx->world;
         ws.reduce.seq = ctx->red_seq;      // the caller has already advanced it for this launch
+        ws.reduce.timeout_ns = ctx->timeout_ns;
     }
-    if ((flags & (TDX_STEP_COMM_HALO | TDX_STEP_COMM_PACK)) && ctx->comm_local && (flags & 6u) != TDX_STEP_TILES_INTERIOR) {
-        CommHeader* hdr = reinterpret_cast<CommHeader*>(ctx->comm_local);
-        const int parity = (int)(ctx->halo_seq & 1ull);
-        ws.wait.flag_lo = ctx->halo_lo > 0 ? &hdr->halo_flag_lo[parity] : nullptr;
-        ws.wait.flag_hi = ctx->halo_hi > 0 ? &hdr->halo_flag_hi[parity] : nullptr;
-        ws.wait.seq = ctx->halo_seq;
-        ws.wait.error = &hdr->error;
+    if (uses_comm_halos(ctx, flags)) {
+        ws.halo_parity_stride_bytes = (long long)((size_t)ctx->halo_cap * esize(ctx->dtype));
+        if ((flags & 6u) != TDX_STEP_TILES_INTERIOR) {
+            CommHeader* hdr = reinterpret_cast<CommHeader*>(ctx->comm_local);
+            ws.wait.flag_lo = ctx->halo_lo > 0 ? &hdr->halo_flag_lo[0] : nullptr;
+            ws.wait.flag_hi = ctx->halo_hi > 0 ? &hdr->halo_flag_hi[0] : nullptr;
+            ws.wait.error = &hdr->error;
+        }
     }
+    ws.wait.seq = ctx->halo_seq;
     return ws;
 }
 
-// halo pointers of a step call: the caller's, or (TDX_STEP_COMM_HALO) the context's peer-written buffers
+// halo pointers of a step call: the caller's, or (TDX_STEP_COMM_HALO / _PACK) the context's peer-written buffers of parity 0
 static void resolve_halos(const tdx_ctx* ctx, unsigned flags, const void*& lo, const void*& hi) {
-    if (!(flags & (TDX_STEP_COMM_HALO | TDX_STEP_COMM_PACK)) || !ctx->comm_local) return;
-    const int parity = (int)(ctx->halo_seq & 1ull);
-    lo = ctx->halo_lo > 0 ? comm_halo(ctx, ctx->comm_local, 0, parity) : nullptr;
-    hi = ctx->halo_hi > 0 ? comm_halo(ctx, ctx->comm_local, 1, parity) : nullptr;
+    if (!uses_comm_halos(ctx, flags)) return;
+    lo = ctx->halo_lo > 0 ? comm_halo(ctx, ctx->comm_local, 0, 0) : nullptr;
+    hi = ctx->halo_hi > 0 ? comm_halo(ctx, ctx->comm_local, 1, 0) : nullptr;
 }
 
-// A launch that delivers the halos itself (TDX_STEP_COMM_PACK) starts a new halo sequence number.
-static int comm_pack_begin(tdx_ctx* ctx, unsigned flags, const char* where) {
+// A launch that delivers the halos itself (TDX_STEP_COMM_PACK) starts a new halo sequence number.  Split into a check (no
+// side effects; call it with the other argument checks) and the advance (immediately before the launch), so that a rank
+// whose arguments are rejected does not get out of step with its neighbours.
+static int comm_pack_check(const tdx_ctx* ctx, unsigned flags, const char* where) {
     if (!(flags & TDX_STEP_COMM_PACK)) return TDX_OK;
     if (!ctx->comm_local) return fail(TDX_ERR_INVALID, std::string(where) + ": TDX_STEP_COMM_PACK needs tdx_comm_init");
     if ((flags & 6u) == TDX_STEP_TILES_INTERIOR || (flags & 6u) == TDX_STEP_TILES_RIM)
         return fail(TDX_ERR_INVALID, std::string(where) + ": TDX_STEP_COMM_PACK cannot be combined with a partial tile range");
     if ((ctx->lower >= 0 && !ctx->comm_peer[ctx->lower]) || (ctx->upper >= 0 && !ctx->comm_peer[ctx->upper]))
         return fail(TDX_ERR_INVALID, std::string(where) + ": neighbours are not connected");
-    ctx->halo_seq += 1;
     return TDX_OK;
 }
+static void comm_pack_advance(tdx_ctx* ctx, unsigned flags, unsigned long long count = 1ull) {
+    if (flags & TDX_STEP_COMM_PACK) ctx->halo_seq += count;
+}
 
-// A launch that all-reduces its scalar in the epilogue consumes one reduction sequence number.
-static int comm_reduce_begin(tdx_ctx* ctx, unsigned flags, bool produces_sum, const char* where) {
+// A launch that all-reduces its scalar in the epilogue consumes reduction sequence numbers (same split).
+static int comm_reduce_check(const tdx_ctx* ctx, unsigned flags, bool produces_sum, const char* where) {
     if (!(flags & TDX_STEP_COMM_REDUCE) || !produces_sum) return TDX_OK;
     if (!ctx->comm_local) return fail(TDX_ERR_INVALID, std::string(where) + ": TDX_STEP_COMM_REDUCE needs tdx_comm_init");
     if ((flags & 6u) == TDX_STEP_TILES_INTERIOR || (flags & 6u) == TDX_STEP_TILES_RIM)
         return fail(TDX_ERR_INVALID, std::string(where) + ": TDX_STEP_COMM_REDUCE cannot be combined with a partial tile range");
     for (int r = 0; r < ctx->world; ++r)
         if (!ctx->comm_peer[r]) return fail(TDX_ERR_INVALID, std::string(where) + ": not all peers are connected");
-    ctx->red_seq += 1;
     return TDX_OK;
+}
+static void comm_reduce_advance(tdx_ctx* ctx, unsigned flags, bool produces_sum, unsigned long long count = 1ull) {
+    if ((flags & TDX_STEP_COMM_REDUCE) && produces_sum) ctx->red_seq += count;
 }
 
 static int check_dt(const tdx_step_args* a, const char* where) {
@@ -614,7 +675,7 @@ int tdx_dek1_attempt_step(tdx_ctx* ctx, const tdx_step_args* args, const void* m
     int rc = check_ready(ctx, "tdx_dek1_attempt_step");
     if (rc) return rc;
     if ((rc = check_dt(args, "tdx_dek1_attempt_step"))) return rc;
-    if ((rc = comm_pack_begin(ctx, args->flags, "tdx_dek1_attempt_step"))) return rc;
+    if ((rc = comm_pack_check(ctx, args->flags, "tdx_dek1_attempt_step"))) return rc;
     resolve_halos(ctx, args->flags, halo_lo, halo_hi);
     if (!mean_in || !sc_in || !mean_out || !sc_out) return fail(TDX_ERR_INVALID, "tdx_dek1_attempt_step: null state buffer");
     if (mean_in == mean_out || sc_in == sc_out)
@@ -622,7 +683,10 @@ int tdx_dek1_attempt_step(tdx_ctx* ctx, const tdx_step_args* args, const void* m
     if ((rc = check_halos(ctx, halo_lo, halo_hi, "tdx_dek1_attempt_step", args->flags))) return rc;
     StepHost h = make_step(ctx, args);
     if (h.want_norm && !sq_norm_sum) return fail(TDX_ERR_INVALID, "tdx_dek1_attempt_step: sq_norm_sum is required with tolerances");
-    if ((rc = comm_reduce_begin(ctx, args->flags, h.want_norm != 0, "tdx_dek1_attempt_step"))) return rc;
+    if ((rc = comm_reduce_check(ctx, args->flags, h.want_norm != 0, "tdx_dek1_attempt_step"))) return rc;
+    // every argument is valid: only now do the exchange's sequence numbers move (all ranks stay in step)
+    comm_pack_advance(ctx, args->flags);
+    comm_reduce_advance(ctx, args->flags, h.want_norm != 0);
     DeviceGuard guard(ctx->device);
     ctx->launches += 1;
     return cuda_fail(ctx->ops->dek1(ctx->geo, h, mean_in, sc_in, mean_out, sc_out, err_out, ref_out, halo_lo, halo_hi,
@@ -635,12 +699,14 @@ int tdx_ek0_sweep_a(tdx_ctx* ctx, const tdx_step_args* args, const void* mean_in
     int rc = check_ready(ctx, "tdx_ek0_sweep_a");
     if (rc) return rc;
     if ((rc = check_dt(args, "tdx_ek0_sweep_a"))) return rc;
-    if ((rc = comm_pack_begin(ctx, args->flags, "tdx_ek0_sweep_a"))) return rc;
+    if ((rc = comm_pack_check(ctx, args->flags, "tdx_ek0_sweep_a"))) return rc;
     resolve_halos(ctx, args->flags, halo_lo, halo_hi);
     if (!mean_in || !z_sq_sum) return fail(TDX_ERR_INVALID, "tdx_ek0_sweep_a: null buffer");
     if ((rc = check_halos(ctx, halo_lo, halo_hi, "tdx_ek0_sweep_a", args->flags))) return rc;
     StepHost h = make_step(ctx, args);
-    if ((rc = comm_reduce_begin(ctx, args->flags, true, "tdx_ek0_sweep_a"))) return rc;
+    if ((rc = comm_reduce_check(ctx, args->flags, true, "tdx_ek0_sweep_a"))) return rc;
+    comm_pack_advance(ctx, args->flags);
+    comm_reduce_advance(ctx, args->flags, true);
     DeviceGuard guard(ctx->device);
     ctx->launches += 1;
     return cuda_fail(ctx->ops->ek0_a(ctx->geo, h, mean_in, halo_lo, halo_hi, make_ws(ctx, args->flags), z_sq_sum, (cudaStream_t)stream),
@@ -672,7 +738,8 @@ int tdx_ek0_sweep_b(tdx_ctx* ctx, const tdx_step_args* args, const void* mean_in
     if ((rc = check_halos(ctx, halo_lo, halo_hi, "tdx_ek0_sweep_b"))) return rc;
     StepHost h = make_step(ctx, args);
     if (h.want_norm && !sq_norm_sum) return fail(TDX_ERR_INVALID, "tdx_ek0_sweep_b: sq_norm_sum is required with tolerances");
-    if ((rc = comm_reduce_begin(ctx, args->flags, h.want_norm != 0, "tdx_ek0_sweep_b"))) return rc;
+    if ((rc = comm_reduce_check(ctx, args->flags, h.want_norm != 0, "tdx_ek0_sweep_b"))) return rc;
+    comm_reduce_advance(ctx, args->flags, h.want_norm != 0);
     DeviceGuard guard(ctx->device);
     ctx->launches += 1;
     return cuda_fail(ctx->ops->ek0_b(ctx->geo, h, mean_in, mean_out, ref_out, halo_lo, halo_hi, make_ws(ctx, args->flags & ~6u), sq_norm_sum,
@@ -695,6 +762,11 @@ int tdx_comm_init(tdx_ctx* ctx, int rank, int world, int lower_rank, int upper_r
     ctx->halo_cap = (ctx->geo.kind == IVP_FHN2D) ? 2LL * ctx->geo.cols : 4;
     cudaError_t e = cudaMalloc(&ctx->comm_local, comm_bytes(ctx));
     if (e == cudaSuccess) e = cudaMemset(ctx->comm_local, 0, comm_bytes(ctx));
+    if (e == cudaSuccess) {
+        CommHeader init{};
+        init.wait_timeout_ns = ctx->timeout_ns;
+        e = cudaMemcpy(ctx->comm_local, &init, sizeof(init), cudaMemcpyHostToDevice);
+    }
     cudaIpcMemHandle_t h;
     if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, ctx->comm_local);
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
@@ -751,6 +823,7 @@ int tdx_comm_allreduce(tdx_ctx* ctx, double* vals, int count, void* stream) {
     a.vals = vals; a.count = count; a.rank = ctx->rank; a.world = ctx->world;
     ctx->red_seq += 1;
     a.seq = ctx->red_seq;
+    a.timeout_ns = ctx->timeout_ns;
     DeviceGuard guard(ctx->device);
     ctx->launches += 1;
     comm_allreduce_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(a);
@@ -799,7 +872,7 @@ int tdx_ek0_attempt_step(tdx_ctx* ctx, const tdx_step_args* args, const void* me
     }
     // the whole attempt is one cooperative launch (fhn_2d: row-streaming strips; 1-d fields: tile ranges)
     const unsigned flags = sharded ? args->flags : 0u;
-    if ((rc = comm_pack_begin(ctx, flags, "tdx_ek0_attempt_step"))) return rc;
+    if ((rc = comm_pack_check(ctx, flags, "tdx_ek0_attempt_step"))) return rc;
     const void* halo_lo = nullptr;
     const void* halo_hi = nullptr;
     resolve_halos(ctx, flags, halo_lo, halo_hi);
@@ -807,12 +880,15 @@ int tdx_ek0_attempt_step(tdx_ctx* ctx, const tdx_step_args* args, const void* me
     if (mean_in == mean_out) return fail(TDX_ERR_INVALID, "tdx_ek0_attempt_step: in and out buffers must be distinct");
     StepHost h = make_step(ctx, args);
     if (h.want_norm && !sq_norm_sum) return fail(TDX_ERR_INVALID, "tdx_ek0_attempt_step: sq_norm_sum is required with tolerances");
-    if ((rc = comm_reduce_begin(ctx, flags, true, "tdx_ek0_attempt_step"))) return rc;
+    if ((rc = comm_reduce_check(ctx, flags, true, "tdx_ek0_attempt_step"))) return rc;
+    comm_pack_advance(ctx, flags);
+    comm_reduce_advance(ctx, flags, true);                   // sum of z^2 ...
     Workspace ws = make_ws(ctx, flags);
-    if ((rc = comm_reduce_begin(ctx, flags, h.want_norm != 0, "tdx_ek0_attempt_step"))) return rc;
+    comm_reduce_advance(ctx, flags, h.want_norm != 0);       // ... and the norm sum
     CommReduce reduce_b = ws.reduce;
     reduce_b.seq = ctx->red_seq;
     ctx->mid_seq += 1;
+    ctx->cl_seq += 1;                                        // the launch releases cl_seq(base) + 1
     DeviceGuard guard(ctx->device);
     ctx->launches += 1;
     unsigned long long* mid_flag = reinterpret_cast<unsigned long long*>(static_cast<unsigned char*>(ctx->mid) + 128);
@@ -1208,33 +1284,72 @@ extern "C" int tdx_ek0_full_step(tdx_ctx* ctx, const tdx_steprule* rule, double 
 // Device-resident step controller
 // =====================================================================================================================
 static_assert(TDX_CTL_HISTORY == kCtlHistory, "history ring size");
+static_assert(TDX_CTL_MAX_RING == kMaxRing, "state ring size");
 
-extern "C" int tdx_ctl_begin(tdx_ctx* ctx, const tdx_steprule* rule, double t0, double dt0, double tmax, void* stream) {
+extern "C" int tdx_ctl_begin_ex(tdx_ctx* ctx, const tdx_steprule* rule, double t0, double dt0, double tmax,
+                                const tdx_ctl_options* opt, void* stream) {
     int rc = check_ready(ctx, "tdx_ctl_begin");
     if (rc) return rc;
     if (!rule) return fail(TDX_ERR_INVALID, "tdx_ctl_begin: null step rule");
     if (!(dt0 > 0.0) || !std::isfinite(dt0)) return fail(TDX_ERR_INVALID, "tdx_ctl_begin: Invalid step size: dt must be positive and finite");
+    const int nbuf = opt ? opt->nbuf : 2;
+    if (nbuf < 2 || nbuf > kMaxRing) return fail(TDX_ERR_INVALID, "tdx_ctl_begin: the state ring holds 2 .. TDX_CTL_MAX_RING buffers");
+    const long long n_stops = (opt && opt->stop_at) ? opt->n_stops : 0;
+    if (n_stops < 0) return fail(TDX_ERR_INVALID, "tdx_ctl_begin: negative number of time stops");
+    for (long long i = 1; i < n_stops; ++i)
+        if (!(opt->stop_at[i] >= opt->stop_at[i - 1])) return fail(TDX_ERR_INVALID, "tdx_ctl_begin: time stops must be sorted");
     DeviceGuard guard(ctx->device);
     cudaError_t e = cudaSuccess;
     if (!ctx->ctl) {
         e = cudaMalloc((void**)&ctx->ctl, sizeof(StepCtl));
         if (e == cudaSuccess) e = cudaMallocHost((void**)&ctx->ctl_host, sizeof(StepCtl));
     }
+    if (e == cudaSuccess && !ctx->feed) {
+        e = cudaHostAlloc((void**)&ctx->feed, sizeof(HostFeed), cudaHostAllocMapped);
+        if (e == cudaSuccess) e = cudaHostGetDevicePointer((void**)&ctx->feed_dev, ctx->feed, 0);
+    }
+    if (e == cudaSuccess && n_stops > ctx->ctl_stops_cap) {
+        cudaFree(ctx->ctl_stops);
+        ctx->ctl_stops = nullptr;
+        e = cudaMalloc((void**)&ctx->ctl_stops, (size_t)n_stops * sizeof(double));
+        ctx->ctl_stops_cap = (e == cudaSuccess) ? n_stops : 0;
+    }
     if (e == cudaSuccess && (rc = ensure_host_norm(ctx))) return rc;
+    if (e == cudaSuccess && n_stops > 0)
+        e = cudaMemcpyAsync(ctx->ctl_stops, opt->stop_at, (size_t)n_stops * sizeof(double), cudaMemcpyHostToDevice, (cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail((int)e, "tdx_ctl_begin");
     StepCtl& c = *ctx->ctl_host;
     std::memset(&c, 0, sizeof(c));
     c.nu = ctx->n - 1;
-    nordsieck_host(c.nu, dt0, c.p, c.pinv);
-    c.t = t0; c.dt = dt0; c.tmax = tmax;
+    c.t = t0; c.tmax = tmax;
     c.adaptive = rule->adaptive ? 1 : 0;
     c.abstol = rule->abstol; c.reltol = rule->reltol; c.safety_scale = rule->safety_scale;
     c.min_change = rule->min_change; c.max_change = rule->max_change; c.constant_dt = rule->constant_dt;
     c.done = (t0 < tmax) ? 0 : 1;
+    c.nbuf = nbuf;
+    c.wait_timeout_ns = (long long)ctx->timeout_ns;
+    c.stops = n_stops > 0 ? ctx->ctl_stops : nullptr;
+    c.n_stops = (int)n_stops;
+    c.next_stop = 0;
+    if (n_stops > 0) {       // the first step is clipped like every later one (odefilter.py:134-135, 355-373)
+        if (t0 >= opt->stop_at[0]) c.next_stop = 1;
+        const double loc = c.next_stop < c.n_stops ? opt->stop_at[c.next_stop] : INFINITY;
+        if (t0 + dt0 > loc) dt0 = loc - t0;
+        if (!(dt0 > 0.0)) return fail(TDX_ERR_INVALID, "tdx_ctl_begin: the first time stop leaves no room for a step");
+    }
+    c.dt = dt0;
+    nordsieck_host(c.nu, dt0, c.p, c.pinv);
+    std::memset((void*)ctx->feed, 0, sizeof(HostFeed));
+    c.feed = (opt && opt->follow) ? ctx->feed_dev : nullptr;
     ctx->ctl_rule = *rule;
+    ctx->ctl_nbuf = nbuf;
     e = cudaMemcpyAsync(ctx->ctl, ctx->ctl_host, sizeof(StepCtl), cudaMemcpyHostToDevice, (cudaStream_t)stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize((cudaStream_t)stream);     // the staging copy is reused by tdx_ctl_read
     return e == cudaSuccess ? TDX_OK : cuda_fail((int)e, "tdx_ctl_begin");
+}
+
+extern "C" int tdx_ctl_begin(tdx_ctx* ctx, const tdx_steprule* rule, double t0, double dt0, double tmax, void* stream) {
+    return tdx_ctl_begin_ex(ctx, rule, t0, dt0, tmax, nullptr, stream);
 }
 
 static StepHost ctl_step_host(const tdx_ctx* ctx, uint32_t flags) {
@@ -1248,33 +1363,118 @@ static StepHost ctl_step_host(const tdx_ctx* ctx, uint32_t flags) {
     return h;
 }
 
+static int check_ring(const tdx_ctx* ctx, void* const* a, void* const* b, int nbuf, const char* where) {
+    if (!a || !b || nbuf != ctx->ctl_nbuf)
+        return fail(TDX_ERR_INVALID, std::string(where) + ": the state ring must have the size given to tdx_ctl_begin");
+    for (int i = 0; i < nbuf; ++i) {
+        if (!a[i] || !b[i]) return fail(TDX_ERR_INVALID, std::string(where) + ": null buffer in the state ring");
+        for (int j = 0; j < i; ++j)
+            if (a[i] == a[j] || b[i] == b[j]) return fail(TDX_ERR_INVALID, std::string(where) + ": the ring's buffers must be distinct");
+    }
+    return TDX_OK;
+}
+
+// one cooperative launch that runs up to ``k`` attempts
+static int dek1_launch_attempts(tdx_ctx* ctx, int k, uint32_t flags, void* const* mean_ring, void* const* sc_ring, int nbuf,
+                                void* const* err_ring, void* const* ref_ring, void* stream, const char* where) {
+    const bool sharded = ctx->halo_lo > 0 || ctx->halo_hi > 0;
+    const uint32_t f = sharded ? flags : (flags & TDX_STEP_ZERO_JACOBIAN);
+    const double d_global = (double)ctx->geo.nf * (double)ctx->geo.grows * (double)ctx->geo.gcols;
+    int rc = comm_pack_check(ctx, f, where);
+    if (rc) return rc;
+    if ((rc = comm_reduce_check(ctx, f, true, where))) return rc;
+    const void* halo_lo = nullptr;
+    const void* halo_hi = nullptr;
+    resolve_halos(ctx, f, halo_lo, halo_hi);
+    StepHost h = ctl_step_host(ctx, f);
+    comm_pack_advance(ctx, f);
+    comm_reduce_advance(ctx, f, true);             // under the controller every attempt ends with a reduction over the ranks
+    Workspace ws = make_ws(ctx, f);
+    comm_pack_advance(ctx, f, (unsigned long long)(k - 1));          // attempt i of the launch uses base + i
+    comm_reduce_advance(ctx, f, true, (unsigned long long)(k - 1));
+    ctx->launches += 1;
+    const int code = ctx->ops->dek1_ctl(ctx->geo, h, mean_ring, sc_ring, nbuf, k, err_ring, ref_ring, halo_lo, halo_hi, ws, ctx->ctl,
+                                        d_global, ctx->host_norm_dev, (cudaStream_t)stream);
+    return cuda_fail(code, where);
+}
+
+static int ek0_launch_attempts(tdx_ctx* ctx, int k, uint32_t flags, void* const* mean_ring, void* const* Cl_ring, int nbuf,
+                               void* const* err_ring, void* const* ref_ring, void* stream, const char* where) {
+    const bool sharded = ctx->halo_lo > 0 || ctx->halo_hi > 0;
+    const uint32_t f = sharded ? flags : 0u;
+    const double d_global = (double)ctx->geo.nf * (double)ctx->geo.grows * (double)ctx->geo.gcols;
+    int rc = comm_pack_check(ctx, f, where);
+    if (rc) return rc;
+    if ((rc = comm_reduce_check(ctx, f, true, where))) return rc;
+    const void* halo_lo = nullptr;
+    const void* halo_hi = nullptr;
+    resolve_halos(ctx, f, halo_lo, halo_hi);
+    StepHost h = ctl_step_host(ctx, f);
+    comm_pack_advance(ctx, f);
+    comm_reduce_advance(ctx, f, true);
+    Workspace ws = make_ws(ctx, f);                 // reduce_a: base sequence number, cl_seq: base
+    comm_reduce_advance(ctx, f, true);
+    CommReduce reduce_b = ws.reduce;
+    reduce_b.seq = ctx->red_seq;
+    comm_pack_advance(ctx, f, (unsigned long long)(k - 1));
+    comm_reduce_advance(ctx, f, true, 2ull * (unsigned long long)(k - 1));   // two reductions per attempt
+    ctx->mid_seq += 1;
+    const unsigned long long mid_base = ctx->mid_seq;
+    ctx->mid_seq += (unsigned long long)(k - 1);
+    ctx->cl_seq += (unsigned long long)k;
+    ctx->launches += 1;
+    unsigned long long* mid_flag = reinterpret_cast<unsigned long long*>(static_cast<unsigned char*>(ctx->mid) + 128);
+    const int code = ctx->ops->ek0_ctl(ctx->geo, h, mean_ring, Cl_ring, nbuf, k, err_ring, ref_ring, halo_lo, halo_hi, ws, reduce_b,
+                                       mid_flag, mid_base, ctx->ctl, d_global, ctx->zsq_scratch, ctx->host_norm_dev,
+                                       (cudaStream_t)stream);
+    return cuda_fail(code, where);
+}
+
+extern "C" int tdx_dek1_run_attempts(tdx_ctx* ctx, int k, uint32_t flags, void* const* mean_ring, void* const* sc_ring, int nbuf,
+                                     void* const* err_ring, void* const* ref_ring, void* stream) {
+    int rc = check_ready(ctx, "tdx_dek1_run_attempts");
+    if (rc) return rc;
+    if (!ctx->ctl) return fail(TDX_ERR_INVALID, "tdx_dek1_run_attempts: call tdx_ctl_begin first");
+    if ((rc = check_full_step_flags(ctx, flags, "tdx_dek1_run_attempts"))) return rc;
+    if ((rc = check_ring(ctx, mean_ring, sc_ring, nbuf, "tdx_dek1_run_attempts"))) return rc;
+    if (k < 1) return fail(TDX_ERR_INVALID, "tdx_dek1_run_attempts: k must be positive");
+    DeviceGuard guard(ctx->device);
+    return dek1_launch_attempts(ctx, k, flags, mean_ring, sc_ring, nbuf, err_ring, ref_ring, stream, "tdx_dek1_run_attempts");
+}
+
+extern "C" int tdx_ek0_run_attempts(tdx_ctx* ctx, int k, uint32_t flags, void* const* mean_ring, void* const* Cl_ring, int nbuf,
+                                    void* const* err_ring, void* const* ref_ring, void* stream) {
+    int rc = check_ready(ctx, "tdx_ek0_run_attempts");
+    if (rc) return rc;
+    if (!ctx->ctl) return fail(TDX_ERR_INVALID, "tdx_ek0_run_attempts: call tdx_ctl_begin first");
+    if ((rc = check_full_step_flags(ctx, flags, "tdx_ek0_run_attempts"))) return rc;
+    if ((rc = check_ring(ctx, mean_ring, Cl_ring, nbuf, "tdx_ek0_run_attempts"))) return rc;
+    if (!err_ring) return fail(TDX_ERR_INVALID, "tdx_ek0_run_attempts: err_ring is required");
+    for (int i = 0; i < nbuf; ++i)
+        if (!err_ring[i]) return fail(TDX_ERR_INVALID, "tdx_ek0_run_attempts: null entry in err_ring");
+    if (k < 1) return fail(TDX_ERR_INVALID, "tdx_ek0_run_attempts: k must be positive");
+    DeviceGuard guard(ctx->device);
+    return ek0_launch_attempts(ctx, k, flags, mean_ring, Cl_ring, nbuf, err_ring, ref_ring, stream, "tdx_ek0_run_attempts");
+}
+
+// the same attempts as k separate launches of one attempt each (the first design of the controller; kept as the A/B partner
+// of the multi-attempt launch)
 extern "C" int tdx_dek1_enqueue_attempts(tdx_ctx* ctx, int k, uint32_t flags, void* mean_a, void* sc_a, void* mean_b, void* sc_b,
                                          void* err_out, void* ref_out, void* stream) {
     int rc = check_ready(ctx, "tdx_dek1_enqueue_attempts");
     if (rc) return rc;
     if (!ctx->ctl) return fail(TDX_ERR_INVALID, "tdx_dek1_enqueue_attempts: call tdx_ctl_begin first");
     if ((rc = check_full_step_flags(ctx, flags, "tdx_dek1_enqueue_attempts"))) return rc;
-    if (!mean_a || !sc_a || !mean_b || !sc_b || mean_a == mean_b || sc_a == sc_b)
-        return fail(TDX_ERR_INVALID, "tdx_dek1_enqueue_attempts: two distinct state buffer pairs are required");
+    if (!mean_a || !sc_a || !mean_b || !sc_b || mean_a == mean_b || sc_a == sc_b || ctx->ctl_nbuf != 2)
+        return fail(TDX_ERR_INVALID, "tdx_dek1_enqueue_attempts: two distinct state buffer pairs are required (ring of 2)");
     if (k < 1) return fail(TDX_ERR_INVALID, "tdx_dek1_enqueue_attempts: k must be positive");
     DeviceGuard guard(ctx->device);
-    const bool sharded = ctx->halo_lo > 0 || ctx->halo_hi > 0;
-    const uint32_t f = sharded ? flags : (flags & TDX_STEP_ZERO_JACOBIAN);
-    const double d_global = (double)ctx->geo.nf * (double)ctx->geo.grows * (double)ctx->geo.gcols;
     void* mean_ab[2] = {mean_a, mean_b};
     void* sc_ab[2] = {sc_a, sc_b};
-    for (int i = 0; i < k; ++i) {
-        if ((rc = comm_pack_begin(ctx, f, "tdx_dek1_enqueue_attempts"))) return rc;
-        const void* halo_lo = nullptr;
-        const void* halo_hi = nullptr;
-        resolve_halos(ctx, f, halo_lo, halo_hi);
-        StepHost h = ctl_step_host(ctx, f);
-        if ((rc = comm_reduce_begin(ctx, f, h.want_norm != 0, "tdx_dek1_enqueue_attempts"))) return rc;
-        ctx->launches += 1;
-        const int code = ctx->ops->dek1_ctl(ctx->geo, h, mean_ab, sc_ab, err_out, ref_out, halo_lo, halo_hi, make_ws(ctx, f), ctx->ctl,
-                                            d_global, ctx->host_norm_dev, (cudaStream_t)stream);
-        if ((rc = cuda_fail(code, "tdx_dek1_enqueue_attempts"))) return rc;
-    }
+    void* err_ab[2] = {err_out, err_out};
+    void* ref_ab[2] = {ref_out, ref_out};
+    for (int i = 0; i < k; ++i)
+        if ((rc = dek1_launch_attempts(ctx, 1, flags, mean_ab, sc_ab, 2, err_ab, ref_ab, stream, "tdx_dek1_enqueue_attempts"))) return rc;
     return TDX_OK;
 }
 
@@ -1284,33 +1484,16 @@ extern "C" int tdx_ek0_enqueue_attempts(tdx_ctx* ctx, int k, uint32_t flags, voi
     if (rc) return rc;
     if (!ctx->ctl) return fail(TDX_ERR_INVALID, "tdx_ek0_enqueue_attempts: call tdx_ctl_begin first");
     if ((rc = check_full_step_flags(ctx, flags, "tdx_ek0_enqueue_attempts"))) return rc;
-    if (!mean_a || !Cl_a || !mean_b || !Cl_b || !err_out || mean_a == mean_b || Cl_a == Cl_b)
-        return fail(TDX_ERR_INVALID, "tdx_ek0_enqueue_attempts: two distinct state buffer pairs and err_out are required");
+    if (!mean_a || !Cl_a || !mean_b || !Cl_b || !err_out || mean_a == mean_b || Cl_a == Cl_b || ctx->ctl_nbuf != 2)
+        return fail(TDX_ERR_INVALID, "tdx_ek0_enqueue_attempts: two distinct state buffer pairs (ring of 2) and err_out are required");
     if (k < 1) return fail(TDX_ERR_INVALID, "tdx_ek0_enqueue_attempts: k must be positive");
     DeviceGuard guard(ctx->device);
-    const bool sharded = ctx->halo_lo > 0 || ctx->halo_hi > 0;
-    const uint32_t f = sharded ? flags : 0u;
-    const double d_global = (double)ctx->geo.nf * (double)ctx->geo.grows * (double)ctx->geo.gcols;
     void* mean_ab[2] = {mean_a, mean_b};
     void* Cl_ab[2] = {Cl_a, Cl_b};
-    unsigned long long* mid_flag = reinterpret_cast<unsigned long long*>(static_cast<unsigned char*>(ctx->mid) + 128);
-    for (int i = 0; i < k; ++i) {
-        if ((rc = comm_pack_begin(ctx, f, "tdx_ek0_enqueue_attempts"))) return rc;
-        const void* halo_lo = nullptr;
-        const void* halo_hi = nullptr;
-        resolve_halos(ctx, f, halo_lo, halo_hi);
-        StepHost h = ctl_step_host(ctx, f);
-        if ((rc = comm_reduce_begin(ctx, f, true, "tdx_ek0_enqueue_attempts"))) return rc;
-        Workspace ws = make_ws(ctx, f);
-        if ((rc = comm_reduce_begin(ctx, f, h.want_norm != 0, "tdx_ek0_enqueue_attempts"))) return rc;
-        CommReduce reduce_b = ws.reduce;
-        reduce_b.seq = ctx->red_seq;
-        ctx->mid_seq += 1;
-        ctx->launches += 1;
-        const int code = ctx->ops->ek0_ctl(ctx->geo, h, mean_ab, Cl_ab, err_out, ref_out, halo_lo, halo_hi, ws, reduce_b, mid_flag,
-                                           ctx->mid_seq, ctx->ctl, d_global, ctx->zsq_scratch, ctx->host_norm_dev, (cudaStream_t)stream);
-        if ((rc = cuda_fail(code, "tdx_ek0_enqueue_attempts"))) return rc;
-    }
+    void* err_ab[2] = {err_out, err_out};
+    void* ref_ab[2] = {ref_out, ref_out};
+    for (int i = 0; i < k; ++i)
+        if ((rc = ek0_launch_attempts(ctx, 1, flags, mean_ab, Cl_ab, 2, err_ab, ref_ab, stream, "tdx_ek0_enqueue_attempts"))) return rc;
     return TDX_OK;
 }
 
@@ -1318,13 +1501,54 @@ extern "C" int tdx_ctl_read(tdx_ctx* ctx, tdx_ctl_state* out, double* hist_t, do
     if (!ctx || !ctx->ctl || !out) return fail(TDX_ERR_INVALID, "tdx_ctl_read: call tdx_ctl_begin first");
     DeviceGuard guard(ctx->device);
     cudaError_t e = cudaMemcpyAsync(ctx->ctl_host, ctx->ctl, sizeof(StepCtl), cudaMemcpyDeviceToHost, (cudaStream_t)stream);
+    unsigned long long comm_err = 0ull;
+    if (e == cudaSuccess && ctx->comm_local)
+        e = cudaMemcpyAsync(&comm_err, &reinterpret_cast<CommHeader*>(ctx->comm_local)->error, sizeof(comm_err),
+                            cudaMemcpyDeviceToHost, (cudaStream_t)stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize((cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail((int)e, "tdx_ctl_read");
     const StepCtl& c = *ctx->ctl_host;
     out->t = c.t; out->dt = c.dt; out->last_norm = c.last_norm;
     out->attempts = c.attempts; out->accepted = c.accepted;
     out->cur = c.cur; out->done = c.done; out->failed = c.failed; out->reserved = 0;
+    if (comm_err != 0ull && out->failed == 0) {      // a peer wait timed out somewhere in the batch
+        out->failed = 2;
+        out->done = 1;
+    }
     if (hist_t) std::memcpy(hist_t, c.hist_t, sizeof(c.hist_t));
     if (hist_dt) std::memcpy(hist_dt, c.hist_dt, sizeof(c.hist_dt));
+    return TDX_OK;
+}
+
+// ---- following a running solve from the host (dense output) -------------------------------------------------------------
+extern "C" int tdx_ctl_poll(tdx_ctx* ctx, tdx_ctl_progress* out) {
+    if (!ctx || !ctx->feed || !out) return fail(TDX_ERR_INVALID, "tdx_ctl_poll: call tdx_ctl_begin_ex with follow = 1 first");
+    out->accepted = (int64_t)ctx->feed->accepted;
+    out->attempts = (int64_t)ctx->feed->attempts;
+    return TDX_OK;
+}
+
+extern "C" int tdx_ctl_history(tdx_ctx* ctx, int64_t state_index, double* t, double* dt, int64_t* attempts) {
+    if (!ctx || !ctx->feed || state_index < 1) return fail(TDX_ERR_INVALID, "tdx_ctl_history: no feed, or state index < 1");
+    const long long slot = state_index % kCtlHistory;
+    if (t) *t = ctx->feed->hist_t[slot];
+    if (dt) *dt = ctx->feed->hist_dt[slot];
+    if (attempts) *attempts = (int64_t)ctx->feed->hist_att[slot];
+    return TDX_OK;
+}
+
+extern "C" int tdx_ctl_consume(tdx_ctx* ctx, int64_t upto) {
+    if (!ctx || !ctx->feed) return fail(TDX_ERR_INVALID, "tdx_ctl_consume: call tdx_ctl_begin_ex with follow = 1 first");
+    if (upto >= 0 && (unsigned long long)upto > ctx->feed->consumed) {
+        ctx->feed->consumed = (unsigned long long)upto;
+        __sync_synchronize();
+    }
+    return TDX_OK;
+}
+
+extern "C" int tdx_ctl_abort(tdx_ctx* ctx) {
+    if (!ctx || !ctx->feed) return fail(TDX_ERR_INVALID, "tdx_ctl_abort: call tdx_ctl_begin_ex with follow = 1 first");
+    ctx->feed->abort = 1ull;
+    __sync_synchronize();
     return TDX_OK;
 }

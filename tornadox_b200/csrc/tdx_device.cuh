@@ -39,6 +39,14 @@ struct Consts {
     unsigned int flags;          // TDX_STEP_*
 };
 
+// A load of state that another CTA of the SAME kernel may have written (multi-attempt kernels): L2 only.  The read-only path
+// (ld.global.nc) is not coherent within a kernel; single-attempt kernels keep it.
+template <bool kCoherent, typename T>
+__device__ __forceinline__ T ld_state(const T* p) {
+    if constexpr (kCoherent) return __ldcg(p);
+    else return __ldg(p);
+}
+
 template <typename T, int N>
 __device__ __forceinline__ T QL(const Consts<T, N>& c, int i, int j) {
     return c.ql[i * (i + 1) / 2 + j];
@@ -60,24 +68,78 @@ __host__ __device__ inline void nordsieck_vectors(int nu, double dt, double* p, 
 }
 
 // Device-resident step controller (odefilter.py:171-223 + step.py:28-108 in device memory): the step kernels read the
-// step to attempt and which of the two state buffers is current from this block, and the last CTA of every attempt
-// decides accept / reject, proposes the next dt and flips the buffers.  The host enqueues attempts without reading anything
-// back and looks at the block once per batch.
+// step to attempt and which state buffer is current from this block, and the last CTA of every attempt decides
+// accept / reject, proposes the next dt and advances the buffer ring.  A multi-attempt launch (tdx_*_run_attempts) loops
+// over attempts inside ONE persistent cooperative kernel: ``epoch`` is the in-kernel grid barrier that publishes every
+// decision to the other CTAs.  The host looks at the block once per launch -- or, for dense output, follows
+// ``host_feed`` (mapped pinned memory) while the kernel is running.
 constexpr int kCtlHistory = 256;
+constexpr int kMaxRing = 8;              // state buffers a controller-driven solve can rotate through
+
+// What the kernel tells the host while it is running, and what the host tells the kernel (mapped pinned memory).
+struct HostFeed {
+    volatile unsigned long long accepted;      // kernel -> host: accepted states so far (state j lives in ring slot j % nbuf)
+    volatile unsigned long long attempts;
+    volatile unsigned long long consumed;      // host -> kernel: states [0, consumed] have been copied out, their slots may be reused
+    volatile unsigned long long abort;         // host -> kernel: stop at the next attempt boundary
+    volatile double hist_t[kCtlHistory];       // time / step of accepted state j at [j % kCtlHistory]
+    volatile double hist_dt[kCtlHistory];
+    volatile long long hist_att[kCtlHistory];  // attempts made when state j was accepted
+};
+
 struct StepCtl {
     double p[kMaxN], pinv[kMaxN];        // Nordsieck vectors of the step to attempt next
     double t, dt, tmax;
     double abstol, reltol, safety_scale, min_change, max_change, constant_dt;
     int adaptive, nu;
-    int cur;                              // index of the buffer pair that holds the current state
-    int done;                             // t reached tmax (or the norm became NaN): further launches do nothing
-    int failed;                           // the error estimate became NaN
-    int pad_;
+    int cur;                              // ring slot that holds the current state
+    int done;                             // t reached tmax (or the norm became NaN): further attempts do nothing
+    int failed;                           // 1: the error estimate became NaN; 2: an in-kernel wait timed out (peer / barrier)
+    int nbuf;                             // ring size (2: plain ping-pong)
     long long attempts, accepted;
     double last_norm;
-    double hist_t[kCtlHistory];           // times of the accepted states, ring indexed by accepted % kCtlHistory
+    unsigned long long epoch;             // attempts whose decision has been published (multi-attempt kernels spin on it)
+    // time stops (odefilter.py:355-373): sorted device array, index of the stop the solve is heading for
+    const double* stops;
+    int n_stops, next_stop;
+    // dense output: wait until the host has drained a ring slot before it is written again (null: nobody follows)
+    HostFeed* feed;
+    long long wait_timeout_ns;            // in-kernel waits give up after this long and fail the solve
+    double hist_t[kCtlHistory];           // times of the accepted states, ring indexed by (accepted - 1) % kCtlHistory
     double hist_dt[kCtlHistory];          // the accepted steps
 };
+
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_gpu(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_gpu(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+constexpr unsigned long long kDefaultWaitNs = 4000000000ull;
+
+// odefilter.py:355-373 (_TimeStopper.adjust_dt_to_time_stops) on the controller's stop list
+__device__ inline double ctl_adjust_to_stops(StepCtl* ctl, double t, double dt) {
+    if (ctl->stops == nullptr) return dt;
+    if (ctl->next_stop < ctl->n_stops && t >= ctl->stops[ctl->next_stop]) ctl->next_stop += 1;
+    const double loc = ctl->next_stop < ctl->n_stops ? ctl->stops[ctl->next_stop] : INFINITY;
+    if (t + dt > loc) dt = loc - t;
+    return dt;
+}
 
 // after one attempt: ``sum`` = sum_i (dt err_i / tol_i)^2 over ALL ranks (ignored for ConstantSteps)
 __device__ inline void ctl_update(StepCtl* ctl, double sum, double d_global) {
@@ -89,7 +151,7 @@ __device__ inline void ctl_update(StepCtl* ctl, double sum, double d_global) {
         const double norm = sqrt(sum / d_global);                                   // step.py:101-104
         ctl->last_norm = norm;
         if (norm != norm) {                                                          // odefilter.py:179-219 would spin forever
-            ctl->failed = 1;
+            if (ctl->failed == 0) ctl->failed = 1;
             ctl->done = 1;
             return;
         }
@@ -98,6 +160,11 @@ __device__ inline void ctl_update(StepCtl* ctl, double sum, double d_global) {
         factor = fmax(ctl->min_change, fmin(factor, ctl->max_change));
         dt_next = fmin(factor * dt, ctl->tmax - (accepted ? t + dt : t));           // odefilter.py:214-219
     } else {
+        if (sum != sum) {                                                            // a poisoned attempt (timed-out wait)
+            if (ctl->failed == 0) ctl->failed = 2;
+            ctl->done = 1;
+            return;
+        }
         dt_next = fmin(ctl->constant_dt, ctl->tmax - (t + dt));
     }
     if (accepted) {
@@ -106,8 +173,16 @@ __device__ inline void ctl_update(StepCtl* ctl, double sum, double d_global) {
         ctl->hist_dt[slot] = dt;
         ctl->accepted += 1;
         ctl->t = t + dt;
-        ctl->cur ^= 1;
+        ctl->cur = (ctl->cur + 1) % ctl->nbuf;
         if (!(ctl->t < ctl->tmax)) ctl->done = 1;                                    // odefilter.py:111 ``while state.t < tmax``
+        dt_next = ctl_adjust_to_stops(ctl, ctl->t, dt_next);                         // odefilter.py:134-135
+        if (ctl->feed != nullptr) {
+            HostFeed* fd = ctl->feed;
+            const long long hs = ctl->accepted % kCtlHistory;                        // state j at [j % kCtlHistory]
+            fd->hist_t[hs] = t + dt;
+            fd->hist_dt[hs] = dt;
+            fd->hist_att[hs] = ctl->attempts;
+        }
     }
     if (!(dt_next > 0.0)) ctl->done = 1;
     ctl->dt = dt_next;
@@ -144,16 +219,16 @@ __device__ __forceinline__ void predict_column(const T (&raw)[N], const Consts<T
 
 // Accessor: predicted, un-preconditioned state p[0] * (A p_inv m)[0] at an arbitrary local flat index,
 // recomputed from the mean in global memory (bitwise identical to the owner thread's own value).
-template <typename T, int N>
+template <typename T, int N, bool kCoherent = false>
 struct MeanAt {
     const T* __restrict__ mean;
     long long d;
     const Consts<T, N>* c;
     __device__ __forceinline__ T operator()(long long idx) const {
-        T acc = c->pinv[0] * __ldg(mean + idx);
+        T acc = c->pinv[0] * ld_state<kCoherent>(mean + idx);
 #pragma unroll
         for (int k = 1; k < N; ++k)
-            acc = fma((T)A_entry<N>(0, k), c->pinv[k] * __ldg(mean + (long long)k * d + idx), acc);
+            acc = fma((T)A_entry<N>(0, k), c->pinv[k] * ld_state<kCoherent>(mean + (long long)k * d + idx), acc);
         return c->p[0] * acc;
     }
 };
@@ -643,11 +718,16 @@ __device__ __forceinline__ void bulk_s2g(void* gmem_dst, const void* smem_src, u
 }
 // Ampere-style asynchronous copies (SASS LDGSTS) of one element with a per-lane destination: used where the shared-memory
 // layout is padded and a linear bulk copy cannot be used
+// kCoherent (multi-attempt kernels: the source may have been written earlier in the same kernel): a synchronous L2 load
+template <bool kCoherent = false>
 __device__ __forceinline__ void cp_async_elem(double* smem_dst, const double* gmem_src) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+    if constexpr (kCoherent) *smem_dst = __ldcg(gmem_src);
+    else asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
 }
+template <bool kCoherent = false>
 __device__ __forceinline__ void cp_async_elem(float* smem_dst, const float* gmem_src) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+    if constexpr (kCoherent) *smem_dst = __ldcg(gmem_src);
+    else asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
 }
 // 16 bytes, L2 only (both addresses 16-byte aligned)
 __device__ __forceinline__ void cp_async_unit(void* smem_dst, const void* gmem_src) {
@@ -659,59 +739,73 @@ __device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.w
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// orders generic-proxy and async-proxy (TMA) accesses to global memory: a state buffer written with ordinary stores in one
+// attempt is read with cp.async.bulk in the next attempt of the same (multi-attempt) kernel, and vice versa
+__device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
+
 // Peer-memory exchange (NVLink): per-rank device block, mapped by the neighbours through CUDA IPC.
 constexpr int kMaxWorld = 16;
+constexpr int kRedChunks = 16;           // fixed global chunks of a reduction (see RedPlan)
 
 struct CommHeader {
     unsigned long long halo_flag_lo[2];              // sequence number of the halo the LOWER neighbour delivered (per parity)
     unsigned long long halo_flag_hi[2];
     unsigned long long red_flag[2][kMaxWorld];       // per parity, per source rank
-    double red_val[2][kMaxWorld][4];
+    double red_val[2][kMaxWorld][kRedChunks];        // per parity, per source rank: its chunk sums in chunk order
+    int red_cnt[2][kMaxWorld];                       // how many of them are meaningful
     unsigned long long error;                        // a flag wait timed out
     unsigned int pack_count[2];                      // CTAs of the local pack kernel that have finished (per direction)
-    unsigned long long pad[4];
+    unsigned long long wait_timeout_ns;              // how long a flag wait may take before it fails the attempt
+    unsigned long long pad[3];
 };
 static_assert(sizeof(CommHeader) % 16 == 0, "halo storage behind the header must stay 16-byte aligned");
 
-struct CommWait {                                    // what a step kernel has to wait for before it reads halos
+// What a step kernel has to wait for before it reads halos.  Flags and halo buffers exist once per parity of the halo
+// sequence number (a neighbour may already deliver the next attempt's halo while this rank still reads the current one):
+// ``flag_*`` point at element [0] of the two-element flag arrays, ``seq`` is the sequence number of the kernel's FIRST attempt.
+struct CommWait {
     const unsigned long long* flag_lo;
     const unsigned long long* flag_hi;
     unsigned long long seq;
     unsigned long long* error;
+    unsigned long long timeout_ns;
 };
 
 struct CommReduce {                                  // fused all-reduce of the kernel's scalar result (world == 0: off)
     CommHeader* local;
     CommHeader* peer[kMaxWorld];
     int rank, world;
-    unsigned long long seq;
+    unsigned long long seq;                          // of the kernel's first reduction
+    unsigned long long timeout_ns;
 };
 
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
-    unsigned long long v;
-    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long global_timer_ns() {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    return t;
-}
-// spin until *flag >= seq; gives up after ~4 s (sets *error) so that a dead peer cannot hang the GPU
-__device__ __forceinline__ void spin_until(const unsigned long long* flag, unsigned long long seq,
-                                           unsigned long long* error) {
-    if (flag == nullptr) return;
+// spin until *flag >= seq; gives up after the timeout (sets *error, returns false) so that a dead peer cannot hang the GPU.
+// The caller poisons the attempt (NaN norm) so that the failure reaches every rank's step controller / host loop.
+__device__ __forceinline__ bool spin_until(const unsigned long long* flag, unsigned long long seq,
+                                           unsigned long long* error, unsigned long long timeout_ns = kDefaultWaitNs) {
+    if (flag == nullptr) return true;
+    if (ld_acquire_sys(flag) >= seq) return true;
     const unsigned long long t0 = global_timer_ns();
     while (ld_acquire_sys(flag) < seq) {
-        if (global_timer_ns() - t0 > 4000000000ull) {
+        if (global_timer_ns() - t0 > (timeout_ns ? timeout_ns : kDefaultWaitNs)) {
             if (error) *error = 1ull;
-            break;
+            return false;
         }
-        __nanosleep(100);
+        __nanosleep(40);
     }
+    return true;
+}
+// the same at GPU scope (in-kernel grid barriers)
+__device__ __forceinline__ bool spin_until_gpu(const unsigned long long* flag, unsigned long long seq,
+                                               unsigned long long timeout_ns = kDefaultWaitNs) {
+    if (ld_acquire_gpu(flag) >= seq) return true;
+    const unsigned long long t0 = global_timer_ns();
+    while (ld_acquire_gpu(flag) < seq) {
+        if (global_timer_ns() - t0 > (timeout_ns ? timeout_ns : kDefaultWaitNs)) return false;
+        __nanosleep(20);
+    }
+    return true;
 }
 // Who takes part in a CTA-level helper: the whole CTA (barrier 0), or the first COUNT threads through a named barrier
 // (warp-specialised kernels whose producer warp must not be waited for).
@@ -725,59 +819,137 @@ struct NamedSync {
     __device__ __forceinline__ int threads() const { return COUNT; }
 };
 
-// one thread per CTA waits, the barrier releases the rest
+// One thread per CTA waits for the halos of sequence number ``seq``, the barrier releases the rest.  Returns false
+// (CTA-uniform) if a wait timed out: the halo buffers then hold stale data and the caller must poison its result.
 template <class Sync = FullSync>
-__device__ __forceinline__ void cta_wait_halos(const CommWait& w, Sync sync = Sync()) {
-    if (w.flag_lo == nullptr && w.flag_hi == nullptr) return;
+__device__ __forceinline__ bool cta_wait_halos(const CommWait& w, unsigned long long seq, int* s_ok, Sync sync = Sync()) {
+    if (w.flag_lo == nullptr && w.flag_hi == nullptr) return true;
     if (threadIdx.x == 0) {
-        spin_until(w.flag_lo, w.seq, w.error);
-        spin_until(w.flag_hi, w.seq, w.error);
+        const int par = (int)(seq & 1ull);
+        bool ok = spin_until(w.flag_lo ? w.flag_lo + par : nullptr, seq, w.error, w.timeout_ns);
+        ok = spin_until(w.flag_hi ? w.flag_hi + par : nullptr, seq, w.error, w.timeout_ns) && ok;
+        *s_ok = ok ? 1 : 0;
     }
     sync();
+    const bool ok = *s_ok != 0;
+    return ok;
 }
 
-// Sum ``v`` (held by thread 0 of ONE CTA) over all ranks in rank order through the peers' reduction slots.
-// Called by every thread of that CTA; returns the global sum in thread 0.
-template <class Sync = FullSync>
-__device__ __forceinline__ double cta_allreduce(double v, const CommReduce& cr, double* s_red, Sync sync = Sync()) {
-    const int r = threadIdx.x;
-    const int parity = (int)(cr.seq & 1ull);
-    if (r == 0) s_red[0] = v;
-    sync();
-    if (r < cr.world) {
-        CommHeader* dst = cr.peer[r];
-        dst->red_val[parity][cr.rank][0] = s_red[0];
-        __threadfence_system();
-        st_release_sys(&dst->red_flag[parity][cr.rank], cr.seq);
-    }
-    sync();
-    if (r < cr.world) spin_until(&cr.local->red_flag[parity][r], cr.seq, &cr.local->error);
-    sync();
-    double acc = 0.0;
-    if (r == 0)
-        for (int k = 0; k < cr.world; ++k) acc += *((volatile double*)&cr.local->red_val[parity][k][0]);
-    return acc;
-}
-
-// ---------------------------------------------------------------------------------------------
-// Deterministic grid-wide sum of one double per thread: warp shuffle -> smem -> per-CTA partial ->
-// last-arriving CTA adds the partials in a fixed order.
-// ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
 }
 
-// The final value is sum * mult * (*mult_sqrt_ptr)^2 (the last two default to 1).
-// With ``cr`` (world > 0) the last CTA then all-reduces the value over the ranks through peer memory.
-// Returns true in exactly one thread of the grid (thread 0 of the last CTA), after ``*out`` has been written; that thread
-// receives the final value in ``*final_value`` (the device-resident step controller runs there).
-__device__ __forceinline__ bool grid_sum(double v, double* s_red, double* partials, unsigned int* ticket,
-                                         double* out, double mult = 1.0, const double* mult_sqrt_ptr = nullptr,
-                                         const CommReduce* cr = nullptr, double* final_value = nullptr) {
+// ---------------------------------------------------------------------------------------------
+// Deterministic, sharding-independent grid-wide sums (step.py:101-104 is ONE norm over all d coordinates).
+//
+// Every kernel stores one partial per UNIT of work -- a 256-coordinate tile, or one grid row of a 256-column strip -- whose
+// value is a fixed function of the unit's coordinates (warp shuffle tree, then the CTA's warps in order), whichever CTA or
+// GPU computes it.  The global index range of the units is cut into kRedChunks equal chunks; a chunk sum adds the chunk's unit
+// partials in a fixed order (32 strided lanes, shuffle tree), and the result is the sum of the chunk sums in chunk order.
+// With several GPUs every rank sends the sums of the chunks (chunk parts) it owns to all peers and every rank adds all of
+// them in (rank, chunk) order: when the shard boundaries are chunk boundaries -- 2, 4, 8, 16 equal shards of a grid whose
+// unit count divides by 16 -- that is the SAME sequence of additions as on one GPU, so the norm, the accept / reject
+// decisions and the proposed steps are bit-identical at 1 / 2 / 4 / 8 GPUs.  Otherwise it is still deterministic and identical
+// on all ranks, just not independent of the number of ranks.
+// ---------------------------------------------------------------------------------------------
+struct RedPlan {
+    double* unit;                        // unit partials of this reduction, indexed by LOCAL unit id (null: per-CTA partials)
+    unsigned int units_local;
+    unsigned long long unit0;            // global id of local unit 0
+    unsigned long long units_global;
+};
+
+__device__ __forceinline__ unsigned long long chunk_begin(const RedPlan& rp, int c) {
+    return ((unsigned long long)c * rp.units_global) / (unsigned long long)kRedChunks;
+}
+
+// The CTA's arrival at a grid-wide rendezvous: returns (CTA-uniform) whether this CTA is the LAST of the grid to arrive.
+// Everything the CTA's threads wrote to global memory before the call is visible to the last CTA after it.
+template <class Sync = FullSync>
+__device__ __forceinline__ bool cta_arrive_last(unsigned int* ticket, int* s_flag, Sync sync = Sync()) {
+    sync();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned int t = atomicAdd(ticket, 1u);
+        const bool last = (t == gridDim.x - 1);
+        if (last) {
+            *ticket = 0u;                 // everybody has arrived; the next rendezvous starts after the last CTA's release
+            __threadfence();
+        }
+        *s_flag = last ? 1 : 0;
+    }
+    sync();
+    return *s_flag != 0;
+}
+
+// Run by all participating threads of ONE CTA (the last to arrive): chunk sums of the local unit partials, exchange with the
+// peers (cr != null && cr->world > 0, reduction sequence number ``seq``), total in (rank, chunk) order.  The total is valid in
+// thread 0; a timed-out peer wait makes it NaN.  ``s_red`` needs kRedChunks + 2 doubles.
+template <class Sync = FullSync>
+__device__ __forceinline__ double reduce_units(const RedPlan& rp, const CommReduce* cr, unsigned long long seq, double* s_red,
+                                               Sync sync = Sync()) {
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = sync.threads() >> 5;
+    const unsigned long long lo_all = rp.unit0, hi_all = rp.unit0 + rp.units_local;
+    sync();                                                      // s_red may still be read by a previous use
+    if (threadIdx.x == 0) s_red[kRedChunks + 1] = 0.0;           // "a peer wait timed out"
+    for (int c = w; c < kRedChunks; c += nw) {
+        unsigned long long b0 = chunk_begin(rp, c), b1 = chunk_begin(rp, c + 1);
+        b0 = b0 > lo_all ? b0 : lo_all;
+        b1 = b1 < hi_all ? b1 : hi_all;
+        double acc = 0.0;
+        for (unsigned long long u = b0 + lane; u < b1; u += 32) acc += __ldcg(rp.unit + (u - lo_all));
+        acc = warp_sum(acc);
+        if (lane == 0) s_red[c] = acc;
+    }
+    sync();
+    const bool comm = cr != nullptr && cr->world > 0;
+    double total = 0.0;
+    if (!comm) {
+        if (threadIdx.x == 0) {
+            for (int c = 0; c < kRedChunks; ++c) {
+                const unsigned long long b0 = chunk_begin(rp, c), b1 = chunk_begin(rp, c + 1);
+                if ((b0 > lo_all ? b0 : lo_all) < (b1 < hi_all ? b1 : hi_all)) total += s_red[c];
+            }
+        }
+        return total;
+    }
+    const int parity = (int)(seq & 1ull);
+    const int r = threadIdx.x;
+    if (r < cr->world) {
+        CommHeader* dst = cr->peer[r];
+        int cnt = 0;
+        for (int c = 0; c < kRedChunks; ++c) {
+            const unsigned long long b0 = chunk_begin(rp, c), b1 = chunk_begin(rp, c + 1);
+            if ((b0 > lo_all ? b0 : lo_all) < (b1 < hi_all ? b1 : hi_all)) dst->red_val[parity][cr->rank][cnt++] = s_red[c];
+        }
+        dst->red_cnt[parity][cr->rank] = cnt;
+        __threadfence_system();
+        st_release_sys(&dst->red_flag[parity][cr->rank], seq);
+    }
+    sync();
+    if (r < cr->world) {
+        const bool ok = spin_until(&cr->local->red_flag[parity][r], seq, &cr->local->error, cr->timeout_ns);
+        if (!ok) s_red[kRedChunks + 1] = 1.0;
+    }
+    sync();
+    if (r == 0) {
+        for (int k = 0; k < cr->world; ++k) {
+            const int cnt = *((volatile int*)&cr->local->red_cnt[parity][k]);
+            for (int j = 0; j < cnt && j < kRedChunks; ++j) total += *((volatile double*)&cr->local->red_val[parity][k][j]);
+        }
+        if (s_red[kRedChunks + 1] != 0.0) total = nan("");
+    }
+    return total;
+}
+
+// Legacy per-CTA partial sums (launches that cover only a part of the shard's tiles: TDX_STEP_TILES_INTERIOR / _RIM).
+// Returns true in thread 0 of the last CTA, after ``*out`` has been written.
+__device__ __forceinline__ bool grid_sum_cta(double v, double* s_red, double* partials, unsigned int* ticket, double* out) {
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     v = warp_sum(v);
+    __syncthreads();
     if (lane == 0) s_red[w] = v;
     __syncthreads();
     __shared__ bool s_last;
@@ -798,24 +970,12 @@ __device__ __forceinline__ bool grid_sum(double v, double* s_red, double* partia
         acc = warp_sum(acc);
         if (lane == 0) s_red[w] = acc;
         __syncthreads();
-        double b = 0.0;
         if (threadIdx.x == 0) {
+            double b = 0.0;
 #pragma unroll
             for (int i = 0; i < kWarps; ++i) b += s_red[i];
-            if (mult_sqrt_ptr) {
-                const double r = *mult_sqrt_ptr;
-                b *= r * r;
-            }
-            b *= mult;
-        }
-        if (cr != nullptr && cr->world > 0) {
-            __syncthreads();
-            b = cta_allreduce(b, *cr, s_red);
-        }
-        if (threadIdx.x == 0) {
             if (out) *out = b;
             *ticket = 0u;
-            if (final_value) *final_value = b;
             return true;
         }
     }

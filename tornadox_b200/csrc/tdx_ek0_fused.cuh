@@ -32,65 +32,64 @@ namespace tdx {
 
 template <typename T, int N, int W_>
 struct Ek0FusedCfg {
-    static constexpr int W = W_;                          // columns per strip == consumer threads per CTA (+ one producer warp)
+    static constexpr int W = W_;                          // columns per strip == consumer threads per CTA
+    static constexpr int THREADS = W_ + 64;               // + one producer warp + one service warp
     static constexpr int PADC = 16 / (int)sizeof(T);      // columns of left/right overlap (16-byte granularity of TMA)
     static constexpr int WP = W + 2 * PADC;
     static constexpr int STAGES = TDX_EK0_STAGES;
     static constexpr int STAGE_ELEMS = 2 * N * WP;        // [field][derivative][WP]
     static constexpr int AT_ROW = W + 2;                  // [left edge][W own][right edge]
     static constexpr int AT_ELEMS = 2 * 2 * AT_ROW;       // [slot][field][AT_ROW]
-    static constexpr size_t BAR_BYTES = 128, RED_BYTES = 256;
+    static constexpr size_t BAR_BYTES = 128, RED_BYTES = 512;
     __host__ __device__ static constexpr size_t at_bytes() { return ((size_t)AT_ELEMS * sizeof(T) + 127) / 128 * 128; }
     __host__ __device__ static constexpr size_t stage_bytes() { return (size_t)STAGE_ELEMS * sizeof(T); }
     __host__ __device__ static constexpr size_t total() { return BAR_BYTES + RED_BYTES + at_bytes() + STAGES * stage_bytes(); }
     static_assert((STAGE_ELEMS * sizeof(T)) % 16 == 0 && (WP * sizeof(T)) % 16 == 0, "TMA destinations stay 16-byte aligned");
+    static_assert(W_ % 32 == 0 && W_ <= 256, "one row partial per consumer warp, at most eight");
 };
+
+// Layout of the reduction scratch (doubles) behind the mbarriers of the fused kernels
+constexpr int kEk0RedScratch = 0;      // [kRedChunks + 2] final reductions
+constexpr int kEk0RowRed = 32;         // [2][8] per-unit warp sums, double-buffered
 
 template <typename T, int N>
 struct Ek0FusedArgs {
     Geo g;
     Consts<T, N> c;
     Consts<double, N> cd;            // the calibration / QR run in fp64 whatever the state dtype
-    const T* mean_in;
-    T* mean_out;
-    T* ref_out;
+    // state buffers: a ring of ``nbuf`` (mean, factor) pairs.  Without a controller: in = slot 0, out = slot 1.
+    T* mean_ring[kMaxRing];
+    T* Cl_ring[kMaxRing];
+    T* err_ring[kMaxRing];           // scalar error estimate of the state in every slot
+    T* ref_ring[kMaxRing];           // reference_state vectors (null entries: not written)
     const T* halo_lo;
     const T* halo_hi;
-    const T* Cl_in;
-    T* Cl_out;
-    T* err_out;
+    long long halo_parity_stride;
     Ek0Mid<T, N>* mid;
-    unsigned long long* mid_flag;    // raised to mid_seq once the gain is published
-    unsigned long long mid_seq;
-    double* partials;                // [2][gridDim.x]
+    unsigned long long* mid_flag;    // raised to mid_seq + attempt once the global sum of z^2 is published
+    unsigned long long mid_seq;      // of the kernel's first attempt
+    unsigned long long* cl_flag;     // raised to cl_seq + attempt + 1 once the attempt's new factor has been written
+    unsigned long long cl_seq;
+    double* partials;                // [2][gridDim.x] (unused by the unit-partial reductions; timing instrumentation)
     unsigned int* ticket;            // [2]
     double* z_sq_out;                // global sum of z^2 (diagnostic / API parity with the three-phase path)
     double* out_sum;                 // sum_i (dt err / tol_i)^2
+    RedPlan red_a, red_b;            // unit partials of the two phases
     double d_global;
     unsigned int col_blocks, chunks, total_strips;
     int use_bulk;
     float keep_frac;                 // share of a strip's rows kept in L2 across the phase turn-arounds (>= 1: no hints)
     CommWait wait;
-    CommReduce reduce_a, reduce_b;
+    CommReduce reduce_a, reduce_b;   // seq of the kernel's first attempt; an attempt uses seq + 2 * attempt
     PackPeer<T> pack;
     // device-resident step controller (kCtl instantiation)
     StepCtl* ctl;
-    T* mean_ab[2];
-    T* Cl_ab[2];
+    int max_attempts;
 };
 
 struct StripGeom {
     int c0, wlen, r0, r1, dir;
 };
-
-__device__ __forceinline__ unsigned long long ld_acquire_gpu(const unsigned long long* p) {
-    unsigned long long v;
-    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_release_gpu(unsigned long long* p, unsigned long long v) {
-    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
 
 // calibration, the single stacked QR, gain, factor update (one thread, fp64)   ek0.py:123-140,175,182
 template <typename T, int N>
@@ -107,7 +106,7 @@ __device__ __noinline__ void ek0_mid_compute(const Consts<double, N>& c, const T
     for (int j = 0; j < N; ++j) {
         double col[N];
 #pragma unroll
-        for (int k = 0; k < N; ++k) col[k] = c.pinv[k] * (double)Cl_in[k * N + j];
+        for (int k = 0; k < N; ++k) col[k] = c.pinv[k] * (double)__ldcg(Cl_in + k * N + j);
 #pragma unroll
         for (int i = 0; i < N; ++i) {
             double acc = col[i];
@@ -134,43 +133,6 @@ __device__ __noinline__ void ek0_mid_compute(const Consts<double, N>& c, const T
     mid->err = err;
 }
 
-// per-CTA partial -> global memory; returns (uniform over the participants) this CTA's arrival number 0 .. gridDim.x - 1
-template <class Sync>
-__device__ __forceinline__ unsigned publish_partial(double v, double* s_red, double* partials, unsigned int* ticket, Sync sync) {
-    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = (sync.threads() + 31) >> 5;
-    v = warp_sum(v);
-    sync();                          // s_red may still be read by a previous use
-    if (lane == 0) s_red[w] = v;
-    sync();
-    if (threadIdx.x == 0) {
-        double b = 0.0;
-        for (int i = 0; i < nw; ++i) b += s_red[i];
-        partials[blockIdx.x] = b;
-        __threadfence();
-        const unsigned int t = atomicAdd(ticket, 1u);
-        s_red[31] = (double)t;
-    }
-    sync();
-    return (unsigned)s_red[31];
-}
-
-// the participants of the last CTA: the partials in a fixed order; the result is valid in thread 0
-template <class Sync>
-__device__ __forceinline__ double sum_partials(double* s_red, const double* partials, Sync sync) {
-    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = (sync.threads() + 31) >> 5;
-    __threadfence();
-    double acc = 0.0;
-    for (unsigned int i = threadIdx.x; i < gridDim.x; i += sync.threads()) acc += __ldcg(partials + i);
-    acc = warp_sum(acc);
-    sync();
-    if (lane == 0) s_red[w] = acc;
-    sync();
-    double b = 0.0;
-    if (threadIdx.x == 0)
-        for (int i = 0; i < nw; ++i) b += s_red[i];
-    return b;
-}
-
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -192,430 +154,10 @@ __device__ __forceinline__ StripGeom strip_geom(const Geo& g, unsigned strip, un
     return s;
 }
 
-// Threads [0, W): consumers, thread t owns column c0 + t of both fields.  Threads [W, W + 32): the producer warp.
-template <typename T, int N, int W, bool kCtl = false>
-__global__ void __maxnreg__(TDX_EK0_MAXREG) ek0_fused_fhn_kernel(const __grid_constant__ Ek0FusedArgs<T, N> a) {
-    using Cfg = Ek0FusedCfg<T, N, W>;
-    using CSync = NamedSync<1, W>;                         // the consumers' barrier (the producer warp never joins)
-    constexpr int PADC = Cfg::PADC, WP = Cfg::WP, S = Cfg::STAGES, AT_ROW = Cfg::AT_ROW;
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);                                   // [S] data has landed
-    uint64_t* empty = full + S;                                                               // [S] consumers are done
-    double* s_red = reinterpret_cast<double*>(smem_raw + Cfg::BAR_BYTES);                     // [32]
-    T* s_at = reinterpret_cast<T*>(smem_raw + Cfg::BAR_BYTES + Cfg::RED_BYTES);               // [2][2][AT_ROW]
-    T* s_stage = reinterpret_cast<T*>(smem_raw + Cfg::BAR_BYTES + Cfg::RED_BYTES + Cfg::at_bytes());
-
-    const Geo& g = a.g;
-    const int tc = threadIdx.x;
-    const Consts<T, N>* cp = &a.c;
-    const Consts<double, N>* cdp = &a.cd;
-    const T* mean_in = a.mean_in;
-    T* mean_out = a.mean_out;
-    const T* Cl_in = a.Cl_in;
-    T* Cl_out = a.Cl_out;
-    if constexpr (kCtl) {
-        __shared__ Consts<T, N> s_c;
-        __shared__ Consts<double, N> s_cd;
-        __shared__ int s_cur;
-        if (tc == 0) {
-            const StepCtl* ctl = a.ctl;
-            Consts<T, N> cc = a.c;
-            Consts<double, N> ccd = a.cd;
-#pragma unroll
-            for (int k = 0; k < N; ++k) {
-                ccd.p[k] = ctl->p[k];
-                ccd.pinv[k] = ctl->pinv[k];
-                cc.p[k] = (T)ctl->p[k];
-                cc.pinv[k] = (T)ctl->pinv[k];
-            }
-            ccd.dt = ctl->dt;
-            cc.dt = (T)ctl->dt;
-            s_c = cc;
-            s_cd = ccd;
-            s_cur = ctl->done ? -1 : ctl->cur;
-        }
-        __syncthreads();
-        if (s_cur < 0) return;
-        cp = &s_c;
-        cdp = &s_cd;
-        mean_in = a.mean_ab[s_cur];
-        mean_out = a.mean_ab[s_cur ^ 1];
-        Cl_in = a.Cl_ab[s_cur];
-        Cl_out = a.Cl_ab[s_cur ^ 1];
-    }
-    const Consts<T, N>& c = *cp;
-    const Consts<double, N>& cdr = *cdp;
-    const bool has_lo = a.halo_lo != nullptr, has_hi = a.halo_hi != nullptr;
-    const bool hints = a.keep_frac < 1.0f;
-    const int ns = (int)((a.total_strips - blockIdx.x + gridDim.x - 1) / gridDim.x);   // strips of this CTA
-
-    if (tc == 0) {
-#pragma unroll
-        for (int s = 0; s < S; ++s) {
-            mbar_init(full + s, 1);
-            mbar_init(empty + s, 1);
-        }
-        fence_mbar_init();
-        fence_proxy_async();
-    }
-    __syncthreads();
-
-    if (tc >= W) {
-        // ---- producer warp: walks the same (strip, row) enumeration as the consumers, up to S rows ahead ------------
-        // Every item owns ring slot q % S (items beyond the shard simply load nothing).  The 2 n row segments of a
-        // row are issued by 2 n lanes in one instruction.
-        const int lane = tc - W;
-        const int seg_f = lane / N, seg_k = lane - seg_f * N;           // (field, derivative) of this lane's segment
-        const long long seg_src = (long long)seg_k * g.d + (long long)seg_f * g.npts;
-        const int seg_dst = (seg_f * N + seg_k) * WP;
-        unsigned q = 0;
-        const uint64_t pol_keep = l2_policy_evict_last(), pol_stream = l2_policy_evict_first();
-#pragma unroll 1
-        for (int phase = 0; phase < 2; ++phase) {
-#pragma unroll 1
-            for (int kk = 0; kk < ns; ++kk) {
-                const int k = phase ? ns - 1 - kk : kk;
-                StripGeom s = strip_geom<W>(g, blockIdx.x + (unsigned)k * gridDim.x, a.col_blocks, a.chunks, has_lo, has_hi);
-                if (phase) s.dir = -s.dir;
-                const int L = s.r1 - s.r0 + 2;
-                const int gs = max(s.c0 - PADC, 0), ge = min(s.c0 + W + PADC, g.cols);
-                const int off = gs - (s.c0 - PADC);
-                const uint32_t bytes = (uint32_t)((ge - gs) * (int)sizeof(T));
-                // L2 residency: the rows phase A reads last are the rows phase B reads first -> keep those, stream the rest
-                const int keep_from = (phase == 0 && hints) ? L - 1 - (int)ceilf(a.keep_frac * (float)(s.r1 - s.r0)) : L;
-                int rr = s.dir > 0 ? s.r0 - 1 : s.r1;
-#pragma unroll 1
-                for (int i = 0; i < L; ++i, rr += s.dir, ++q) {
-                    const unsigned stage = q % S, round = q / S;
-                    if (round > 0) mbar_wait(empty + stage, (round - 1u) & 1u);     // the slot's previous row is consumed
-                    if (rr < 0 || rr >= g.rows) continue;
-                    T* dst = s_stage + (size_t)stage * Cfg::STAGE_ELEMS;
-                    const T* src = mean_in + (long long)rr * g.cols + gs;
-                    if (a.use_bulk) {
-                        if (lane == 0) mbar_expect_tx(full + stage, 2u * N * bytes);
-                        __syncwarp();
-                        if (lane < 2 * N) {
-                            if (hints) bulk_g2s_hint(dst + seg_dst + off, src + seg_src, bytes, full + stage, i >= keep_from ? pol_keep : pol_stream);
-                            else bulk_g2s(dst + seg_dst + off, src + seg_src, bytes, full + stage);
-                        }
-                    } else {
-                        // unaligned / odd-sized grids: plain loads by the 32 lanes, then a normal arrival
-                        for (int seg = 0; seg < 2 * N; ++seg) {
-                            const int f = seg / N, kd = seg - f * N;
-                            const T* sp = src + (long long)kd * g.d + (long long)f * g.npts;
-                            for (int j = lane; j < ge - gs; j += 32) dst[seg * WP + off + j] = __ldg(sp + j);
-                        }
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(full + stage);
-                    }
-                }
-            }
-        }
-        return;
-    }
-
-    // ---- consumers ----------------------------------------------------------------------------------------------------
-    CSync csync;
-    // deliver this shard's edge rows to the neighbours before anything else (multi-GPU)
-    if (a.pack.enabled)
-        for (int part = (int)blockIdx.x; part < 2 * kPackCtas; part += (int)gridDim.x)   // a small grid takes several parts per CTA
-            pack_halo_part<T, N>(g, c, mean_in, a.pack, part, csync);
-
-    // Column 1 of the predicted covariance without the diffusion term, M1 = (B B^T)[:, 1] with B = A (p_inv * Cl).
-    // The gain K = Clp Clp^T H^T / S (ek0.py:136) only needs column 1 of Clp Clp^T = B B^T + sigma^2 Ql Ql^T, so once
-    // sigma^2 is known (after phase A) every CTA derives K in a handful of flops; the stacked QR that produces the new
-    // factor itself (ek0.py:175,138) is off the critical path (done by the first CTA to finish phase B).
-    double* s_m1 = s_red + 16;
-    if (tc == 0) {
-        const Consts<double, N>& cd = cdr;
-        double B[N][N];
-#pragma unroll
-        for (int j = 0; j < N; ++j) {
-            double colv[N];
-#pragma unroll
-            for (int kd = 0; kd < N; ++kd) colv[kd] = cd.pinv[kd] * (double)__ldg(Cl_in + kd * N + j);
-#pragma unroll
-            for (int i = 0; i < N; ++i) {
-                double accb = colv[i];
-#pragma unroll
-                for (int kd = i + 1; kd < N; ++kd) accb = fma(A_entry<N>(i, kd), colv[kd], accb);
-                B[i][j] = accb;
-            }
-        }
-#pragma unroll
-        for (int r = 0; r < N; ++r) {
-            double m = 0.0;
-#pragma unroll
-            for (int j = 0; j < N; ++j) m = fma(B[r][j], B[1][j], m);
-            s_m1[r] = m;
-        }
-    }
-    unsigned cq = 0, phase_bits = 0u;
-    bool halos_ready = false;
-    const uint64_t pol_keep = l2_policy_evict_last(), pol_stream = l2_policy_evict_first();
-    const T inv_dx2 = (T)g.prm[0], pa = (T)g.prm[1], pb = (T)g.prm[2], pk = (T)g.prm[3], inv_tau = (T)g.prm[5];
-
-    auto m_at_from = [&](const T* fld, int idx) -> T {     // predicted, un-preconditioned state of a stage column
-        T acc = c.pinv[0] * fld[idx];
-#pragma unroll
-        for (int k = 1; k < N; ++k) acc = fma((T)A_entry<N>(0, k), c.pinv[k] * fld[k * WP + idx], acc);
-        return c.p[0] * acc;
-    };
-
-    // one phase over this CTA's strips.  kUpdate = false: phase A (forward), true: phase B (backward).
-    auto run_phase = [&](auto update_tag, const T (&K)[N]) -> double {
-        constexpr bool kUpdate = decltype(update_tag)::value;
-        constexpr int NK = kUpdate ? N : 2;                 // rows of the predicted mean kept for the row being finalised
-        double acc = 0.0;
-#pragma unroll 1
-        for (int kk = 0; kk < ns; ++kk) {
-            const int k = kUpdate ? ns - 1 - kk : kk;
-            StripGeom s = strip_geom<W>(g, blockIdx.x + (unsigned)k * gridDim.x, a.col_blocks, a.chunks, has_lo, has_hi);
-            if (kUpdate) s.dir = -s.dir;
-            const int L = s.r1 - s.r0 + 2;
-            const int col = s.c0 + tc;
-            const bool valid = tc < s.wlen;
-            const bool left_inner = (tc == 0) && s.c0 > 0;                            // recompute the column left of the strip
-            const bool right_inner = (tc == s.wlen - 1) && (s.c0 + s.wlen < g.cols);  // ... right of the strip
-            const bool left_edge = (tc == 0) && s.c0 == 0;                            // grid edge: replicate own value
-            const bool right_edge = (tc == s.wlen - 1) && (s.c0 + s.wlen >= g.cols);
-            int rr = s.dir > 0 ? s.r0 - 1 : s.r1;
-            T at_m1[2] = {}, at_m2[2] = {}, hs_m1[2] = {}, mp_m1[2][NK] = {};
-            bool first_replicated = false;
-            T* out_ptr = mean_out + ((long long)(rr - s.dir) * g.cols + col);      // row being finalised, field 0
-            // the rows phase B writes last are the rows the NEXT attempt's phase A reads first -> keep those in L2
-            const int keep_from = (kUpdate && hints) ? L - (int)ceilf(a.keep_frac * (float)(s.r1 - s.r0)) : L;
-#pragma unroll 1
-            for (int i = 0; i < L; ++i, rr += s.dir, ++cq, out_ptr += (long long)s.dir * g.cols) {
-                const unsigned stage = cq % S;
-                T* at_row = s_at + (cq & 1u) * 2 * AT_ROW;
-                T at_cur[2], mp_cur[2][NK];
-                if (rr >= 0 && rr < g.rows) {
-                    mbar_wait(full + stage, (phase_bits >> stage) & 1u);
-                    phase_bits ^= (1u << stage);
-                    const T* st = s_stage + (size_t)stage * Cfg::STAGE_ELEMS;
-#pragma unroll
-                    for (int f = 0; f < 2; ++f) {
-                        T raw[N], mp[N];
-#pragma unroll
-                        for (int kd = 0; kd < N; ++kd) raw[kd] = st[(f * N + kd) * WP + PADC + tc];
-                        predict_column<T, N>(raw, c, mp);
-                        at_cur[f] = c.p[0] * mp[0];
-#pragma unroll
-                        for (int r = 0; r < NK; ++r) mp_cur[f][r] = mp[r];
-                    }
-                    // columns just outside the strip (inside the grid): recomputed from the stage's overlap columns
-                    if (left_inner) {
-#pragma unroll
-                        for (int f = 0; f < 2; ++f) at_row[f * AT_ROW] = m_at_from(st + f * N * WP, PADC - 1);
-                    }
-                    if (right_inner) {
-#pragma unroll
-                        for (int f = 0; f < 2; ++f) at_row[f * AT_ROW + s.wlen + 1] = m_at_from(st + f * N * WP, PADC + s.wlen);
-                    }
-                } else {
-                    const T* h = rr < 0 ? a.halo_lo : a.halo_hi;
-                    if (h != nullptr) {
-                        if (!halos_ready) {
-                            cta_wait_halos(a.wait, csync);
-                            halos_ready = true;
-                        }
-#pragma unroll
-                        for (int f = 0; f < 2; ++f) at_cur[f] = valid ? __ldcg(h + (long long)f * g.cols + col) : (T)0;
-                    } else {
-                        // edge replication (ivp.py:488-490): the row beyond the grid equals the grid's edge row
-#pragma unroll
-                        for (int f = 0; f < 2; ++f) at_cur[f] = at_m1[f];
-                        if (i == 0) first_replicated = true;
-                    }
-#pragma unroll
-                    for (int f = 0; f < 2; ++f)
-#pragma unroll
-                        for (int r = 0; r < NK; ++r) mp_cur[f][r] = (T)0;
-                }
-                if (i == 1 && first_replicated) {
-                    at_m1[0] = at_cur[0];
-                    at_m1[1] = at_cur[1];
-                }
-                if (valid) {
-#pragma unroll
-                    for (int f = 0; f < 2; ++f) {
-                        at_row[f * AT_ROW + tc + 1] = at_cur[f];
-                        if (left_edge) at_row[f * AT_ROW] = at_cur[f];
-                        if (right_edge) at_row[f * AT_ROW + s.wlen + 1] = at_cur[f];
-                    }
-                }
-                csync();              // publishes the row; every consumer has read the stage -> hand it back
-                if (tc == 0) mbar_arrive(empty + stage);
-                T hs_cur[2];
-#pragma unroll
-                for (int f = 0; f < 2; ++f) hs_cur[f] = at_row[f * AT_ROW + tc] + at_row[f * AT_ROW + tc + 2];
-
-                if (i >= 2 && valid) {    // the previous row now has both vertical neighbours
-                    const T u = at_m1[0], v = at_m1[1];
-#pragma unroll
-                    for (int f = 0; f < 2; ++f) {
-                        const T own = at_m1[f];
-                        const T lap = (((at_m2[f] + at_cur[f]) + hs_m1[f]) - (T)4 * own) * inv_dx2;
-                        T fx;
-                        if (f == 0) fx = pa * lap + u - u * u * u - v + pk;       // ivp.py:441
-                        else fx = (pb * lap + u - v) * inv_tau;                   // ivp.py:442
-                        const T z = c.p[1] * mp_m1[f][1] - fx;
-                        if constexpr (!kUpdate) {
-                            acc += (double)z * (double)z;
-                        } else {
-                            T* mo_ptr = out_ptr + (long long)f * g.npts;
-                            T m0 = (T)0;
-#pragma unroll
-                            for (int r = 0; r < N; ++r) {
-                                const T mo = c.p[r] * (mp_m1[f][r] - K[r] * z);
-                                if (hints) st_global_hint(mo_ptr, mo, i >= keep_from ? pol_keep : pol_stream);
-                                else *mo_ptr = mo;
-                                mo_ptr += g.d;
-                                if (r == 0) m0 = mo;
-                            }
-                            const T ref = tabs<T>(m0);
-                            if (a.ref_out) {
-                                T* rp = a.ref_out + ((out_ptr - mean_out) + (long long)f * g.npts);
-                                if (hints) st_global_hint(rp, ref, pol_stream);
-                                else *rp = ref;
-                            }
-                            if (c.want_norm) {
-                                const double tol = (double)c.abstol + (double)c.reltol * (double)ref;
-                                acc += 1.0 / (tol * tol);
-                            }
-                        }
-                    }
-                }
-#pragma unroll
-                for (int f = 0; f < 2; ++f) {
-                    at_m2[f] = at_m1[f];
-                    at_m1[f] = at_cur[f];
-                    hs_m1[f] = hs_cur[f];
-#pragma unroll
-                    for (int r = 0; r < NK; ++r) mp_m1[f][r] = mp_cur[f][r];
-                }
-            }
-        }
-        return acc;
-    };
-
-    T K[N];
-#pragma unroll
-    for (int r = 0; r < N; ++r) K[r] = (T)0;
-
-#ifdef TDX_EK0_TIMING
-    double* stamps = a.partials + 1024 + 4 * blockIdx.x;    // [t_start, t_end_A, t_gain_seen, t_end_B] in ns
-    if (tc == 0) {
-        stamps[0] = (double)global_timer_ns();
-        unsigned smid;
-        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-        a.partials[1024 + 4096 + blockIdx.x] = (double)smid;
-    }
-#endif
-    // ---- phase A ----------------------------------------------------------------------------------------------------
-    const double acc_a = run_phase(std::false_type{}, K);
-#ifdef TDX_EK0_TIMING
-    if (tc == 0) stamps[1] = (double)global_timer_ns();
-#endif
-    if (publish_partial(acc_a, s_red, a.partials, a.ticket, csync) == gridDim.x - 1) {
-        double z_sq = sum_partials(s_red, a.partials, csync);
-        if (a.reduce_a.world > 0) {
-            csync();
-            z_sq = cta_allreduce(z_sq, a.reduce_a, s_red, csync);
-        }
-        if (tc == 0) {
-            a.mid->z_sq = z_sq;
-            if (a.z_sq_out) *a.z_sq_out = z_sq;
-            *a.ticket = 0u;
-            __threadfence();
-            st_release_gpu(a.mid_flag, a.mid_seq);
-        }
-    }
-    if (tc == 0) {
-        const unsigned long long t0 = global_timer_ns();
-        s_red[30] = 0.0;
-        while (ld_acquire_gpu(a.mid_flag) < a.mid_seq) {
-            if (global_timer_ns() - t0 > 4000000000ull) {        // a dead peer must not hang the GPU ...
-                s_red[30] = 1.0;                                 // ... and must not go unnoticed: poison the attempt
-                break;
-            }
-            __nanosleep(64);
-        }
-    }
-    csync();
-#ifdef TDX_EK0_TIMING
-    if (tc == 0) stamps[2] = (double)global_timer_ns();
-#endif
-    // calibration (ek0.py:123-130) and gain (ek0.py:132-136), redundantly in every thread
-    const double z_sq_all = (s_red[30] != 0.0) ? nan("") : __ldcg(&a.mid->z_sq);   // timed out: NaN state, NaN norm, the host raises
-    double err_cal;
-    {
-        const Consts<double, N>& cd = cdr;
-        const double p1 = cd.p[1];
-        const double Q11 = QL(cd, 1, 0) * QL(cd, 1, 0) + QL(cd, 1, 1) * QL(cd, 1, 1);
-        const double HQH = p1 * p1 * Q11;
-        const double sigma_sq = z_sq_all / HQH / a.d_global;
-        err_cal = sqrt(sigma_sq * HQH);
-        const double den = p1 * fma(sigma_sq, Q11, s_m1[1]);
-#pragma unroll
-        for (int r = 0; r < N; ++r) {
-            // (Ql Ql^T)[r][1]: rows 0 and 1 of Ql have 1 and 2 nonzeros
-            const double q = (r == 0) ? QL(cd, 0, 0) * QL(cd, 1, 0) : QL(cd, r, 0) * QL(cd, 1, 0) + QL(cd, r, 1) * QL(cd, 1, 1);
-            K[r] = (T)(fma(sigma_sq, q, s_m1[r]) / den);
-        }
-    }
-
-    // ---- phase B ----------------------------------------------------------------------------------------------------
-    const double acc_b = run_phase(std::true_type{}, K);
-#ifdef TDX_EK0_TIMING
-    if (tc == 0) stamps[3] = (double)global_timer_ns();
-#endif
-    const unsigned arrival = publish_partial(acc_b, s_red, a.partials + gridDim.x, a.ticket + 1, csync);
-    if (arrival == 0u && tc == 0) {
-        // the first CTA to finish has the most slack: it runs the stacked QR for the new factor  ek0.py:175,138
-        ek0_mid_compute<T, N>(cdr, Cl_in, z_sq_all, a.d_global, Cl_out, a.err_out, a.mid);
-    }
-    if (arrival == gridDim.x - 1) {
-        if (c.want_norm) {
-            double b = sum_partials(s_red, a.partials + gridDim.x, csync);
-            if (tc == 0) {
-                b *= err_cal * err_cal;
-                b *= (double)c.dt * (double)c.dt;      // sum_i (dt err / tol_i)^2   step.py:101-104, scalar error estimate
-            }
-            if (a.reduce_b.world > 0) {
-                csync();
-                b = cta_allreduce(b, a.reduce_b, s_red, csync);
-            }
-            if (tc == 0) *a.out_sum = b;
-            if (kCtl && tc == 0) ctl_update(a.ctl, b, a.d_global);
-        } else if (kCtl && tc == 0) {
-            ctl_update(a.ctl, 0.0, a.d_global);
-        }
-        if (tc == 0) a.ticket[1] = 0u;
-    }
-}
-
-// =====================================================================================================================
-// The same one-launch attempt for the 1-d vector fields (vanderpol, lorenz96, brusselator, burgers_1d, wave_1d).
-//
-// Work unit = the 256-coordinate tile of the sweep kernels (tile_coord / ExtTile / IVP::ring_value / IVP::eval are reused as
-// they are): thread = one state coordinate.  A CTA owns a CONTIGUOUS range of tiles, walks it forwards in phase A and
-// backwards in phase B (L2 reuse), and gets every tile's raw mean columns through the same TMA ring + producer warp as the
-// fhn kernel; the few stencil neighbours outside a tile (2-3 per field) are recomputed from the mean through L2.
-// =====================================================================================================================
-template <typename T, int N>
-struct Ek0ChainCfg {
-    static constexpr int STAGES = 4;
-    static constexpr int STAGE_ELEMS = N * kThreads;                 // [derivative][thread]
-    static constexpr size_t BAR_BYTES = 128, RED_BYTES = 256;
-    __host__ __device__ static constexpr size_t at_bytes(int at_elems) { return ((size_t)at_elems * sizeof(T) + 127) / 128 * 128; }
-    __host__ __device__ static constexpr size_t total(int at_elems) {
-        return BAR_BYTES + RED_BYTES + 2 * at_bytes(at_elems) + STAGES * (size_t)STAGE_ELEMS * sizeof(T);
-    }
-};
-
-// sigma-independent part of column 1 of the predicted covariance: M1 = (B B^T)[:, 1], B = A (p_inv * Cl)   (see the fhn kernel)
+// sigma-independent part of column 1 of the predicted covariance: M1 = (B B^T)[:, 1], B = A (p_inv * Cl).
+// The gain K = Clp Clp^T H^T / S (ek0.py:136) only needs column 1 of Clp Clp^T = B B^T + sigma^2 Ql Ql^T, so once
+// sigma^2 is known (after phase A) every CTA derives K in a handful of flops; the stacked QR that produces the new
+// factor itself (ek0.py:175,138) is off the critical path (service warp of CTA 0, while phase B is streaming).
 template <typename T, int N>
 __device__ __forceinline__ void ek0_m1_column(const Consts<double, N>& cd, const T* Cl_in, double* m1) {
     double B[N][N];
@@ -623,7 +165,7 @@ __device__ __forceinline__ void ek0_m1_column(const Consts<double, N>& cd, const
     for (int j = 0; j < N; ++j) {
         double colv[N];
 #pragma unroll
-        for (int kd = 0; kd < N; ++kd) colv[kd] = cd.pinv[kd] * (double)__ldg(Cl_in + kd * N + j);
+        for (int kd = 0; kd < N; ++kd) colv[kd] = cd.pinv[kd] * (double)__ldcg(Cl_in + kd * N + j);
 #pragma unroll
         for (int i = 0; i < N; ++i) {
             double accb = colv[i];
@@ -651,11 +193,488 @@ __device__ __forceinline__ double ek0_gain(const Consts<double, N>& cd, const do
     const double den = p1 * fma(sigma_sq, Q11, m1[1]);
 #pragma unroll
     for (int r = 0; r < N; ++r) {
+        // (Ql Ql^T)[r][1]: rows 0 and 1 of Ql have 1 and 2 nonzeros
         const double q = (r == 0) ? QL(cd, 0, 0) * QL(cd, 1, 0) : QL(cd, r, 0) * QL(cd, 1, 0) + QL(cd, r, 1) * QL(cd, 1, 1);
         K[r] = (T)(fma(sigma_sq, q, m1[r]) / den);
     }
     return sqrt(sigma_sq * HQH);
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Pieces shared by the two fused kernels (fhn strips / 1-d tile ranges).  Thread roles: consumers [0, CONS), the producer
+// warp [CONS, CONS + 32), the service warp [CONS + 32, CONS + 64).
+// ---------------------------------------------------------------------------------------------------------------------
+template <typename T, int N>
+struct Ek0CtaState {
+    Consts<T, N> c;                  // kCtl: the attempt's constants rebuilt from the controller block
+    Consts<double, N> cd;
+    int cur, out;                    // ring slots of the attempt's input / output state (cur < 0: stop)
+    int flag, ok;
+    unsigned long long epoch0;
+    uint64_t m1_bar;                 // the service warp has published m1[attempt & 1]
+    double m1[2][kMaxN + 1];
+    double timed_out;                // the wait for the global sum of z^2 timed out
+};
+
+// top of an attempt, all threads of the CTA: thread 0 waits for the previous attempt's decision and reads the controller
+template <typename T, int N, bool kCtl>
+__device__ __forceinline__ bool ek0_attempt_begin(const Ek0FusedArgs<T, N>& a, Ek0CtaState<T, N>& sh, int att) {
+    if (threadIdx.x == 0) {
+        if constexpr (kCtl) {
+            StepCtl* ctl = a.ctl;
+            bool ok = true;
+            if (att == 0) sh.epoch0 = ld_acquire_gpu(&ctl->epoch);
+            else ok = spin_until_gpu(&ctl->epoch, sh.epoch0 + (unsigned long long)att, (unsigned long long)ctl->wait_timeout_ns);
+            if (!ok) {
+                ctl->failed = 2;
+                ctl->done = 1;
+            }
+            Consts<T, N> cc = a.c;
+            Consts<double, N> ccd = a.cd;
+#pragma unroll
+            for (int k = 0; k < N; ++k) {
+                ccd.p[k] = ctl->p[k];
+                ccd.pinv[k] = ctl->pinv[k];
+                cc.p[k] = (T)ctl->p[k];
+                cc.pinv[k] = (T)ctl->pinv[k];
+            }
+            ccd.dt = ctl->dt;
+            cc.dt = (T)ctl->dt;
+            sh.c = cc;
+            sh.cd = ccd;
+            const int cur = ctl->cur, nbuf = ctl->nbuf;
+            sh.cur = (ctl->done || !ok) ? -1 : cur;
+            sh.out = (cur + 1) % nbuf;
+        } else {
+            sh.cur = 0;
+            sh.out = 1;
+        }
+    }
+    __syncthreads();
+    return sh.cur >= 0;
+}
+
+// the service warp's attempt (lane 0): m1 of the attempt's input factor for every CTA; in CTA 0 additionally the stacked QR
+// for the attempt's output factor as soon as the global sum of z^2 is known
+template <typename T, int N>
+__device__ __forceinline__ void ek0_service(const Ek0FusedArgs<T, N>& a, Ek0CtaState<T, N>& sh, const Consts<double, N>& cd_shared,
+                                            int att, int lane) {
+    if (lane == 0) {
+        const unsigned long long tmo = a.wait.timeout_ns;
+        const T* Cl_in = a.Cl_ring[sh.cur];
+        const Consts<double, N> cd = cd_shared;      // thread 0 rebuilds the shared copy at the top of the next attempt
+        // the factor this attempt starts from was written by the previous attempt's QR (the first attempt's by an earlier launch)
+        bool ok = att == 0 || spin_until_gpu(a.cl_flag, a.cl_seq + (unsigned long long)att, tmo);
+        ek0_m1_column<T, N>(cd, Cl_in, sh.m1[att & 1]);
+        if (!ok) sh.m1[att & 1][1] = nan("");
+        mbar_arrive(&sh.m1_bar);
+        if (blockIdx.x == 0) {
+            ok = spin_until_gpu(a.mid_flag, a.mid_seq + (unsigned long long)att, tmo);
+            const double z_sq = ok ? __ldcg(&a.mid->z_sq) : nan("");
+            ek0_mid_compute<T, N>(cd, Cl_in, z_sq, a.d_global, a.Cl_ring[sh.out], a.err_ring[sh.out], a.mid);
+            __threadfence();
+            st_release_gpu(a.cl_flag, a.cl_seq + (unsigned long long)att + 1ull);
+        }
+    }
+    __syncwarp();
+}
+
+// consumers, after phase A: publish the CTA's arrival; the last CTA reduces the unit partials (over the ranks too) and
+// releases the global sum of z^2; everybody waits for it and derives the gain.  Returns the calibrated error estimate.
+template <typename T, int N, class CSync>
+__device__ __forceinline__ double ek0_mid_barrier(const Ek0FusedArgs<T, N>& a, Ek0CtaState<T, N>& sh, const Consts<double, N>& cd,
+                                                  int att, double* s_red, T (&K)[N], CSync csync) {
+    const int tc = threadIdx.x;
+    if (cta_arrive_last(a.ticket, &sh.flag, csync)) {
+        const double z_sq = reduce_units(a.red_a, &a.reduce_a, a.reduce_a.seq + 2ull * (unsigned long long)att,
+                                         s_red + kEk0RedScratch, csync);
+        if (tc == 0) {
+            a.mid->z_sq = z_sq;
+            if (a.z_sq_out) *a.z_sq_out = z_sq;
+            __threadfence();
+            st_release_gpu(a.mid_flag, a.mid_seq + (unsigned long long)att);
+        }
+    }
+    if (tc == 0) {
+        sh.timed_out = spin_until_gpu(a.mid_flag, a.mid_seq + (unsigned long long)att, a.wait.timeout_ns) ? 0.0 : 1.0;
+        mbar_wait(&sh.m1_bar, (unsigned)att & 1u);           // the service warp's m1 of this attempt
+    }
+    csync();
+    // a dead peer must not hang the GPU and must not go unnoticed: NaN state, NaN norm, the controller / host raises
+    const double z_sq_all = (sh.timed_out != 0.0) ? nan("") : __ldcg(&a.mid->z_sq);
+    return ek0_gain<T, N>(cd, sh.m1[att & 1], z_sq_all, a.d_global, K);
+}
+
+// consumers, after phase B: the last CTA reduces sum_i 1 / tol_i^2, scales it to sum_i (dt err / tol_i)^2 (step.py:101-104 with a
+// scalar error estimate), writes it out and -- under the controller -- decides and publishes the decision
+template <typename T, int N, bool kCtl, class CSync>
+__device__ __forceinline__ void ek0_end_barrier(const Ek0FusedArgs<T, N>& a, Ek0CtaState<T, N>& sh, const Consts<T, N>& c, int att,
+                                                double err_cal, double* s_red, CSync csync) {
+    const int tc = threadIdx.x;
+    if (!(c.want_norm || kCtl)) return;
+    if (cta_arrive_last(a.ticket + 1, &sh.flag, csync)) {
+        double b = 0.0;
+        if (c.want_norm || a.reduce_b.world > 0) {
+            b = reduce_units(a.red_b, &a.reduce_b, a.reduce_b.seq + 2ull * (unsigned long long)att, s_red + kEk0RedScratch, csync);
+            if (tc == 0) {
+                b *= err_cal * err_cal;
+                b *= (double)c.dt * (double)c.dt;
+                if (c.want_norm && a.out_sum) *a.out_sum = b;
+            }
+        }
+        if constexpr (kCtl) {
+            if (tc == 0) ctl_finish_attempt(a.ctl, b, a.d_global, sh.epoch0 + (unsigned long long)att + 1ull);
+        }
+    }
+}
+
+// Threads [0, W): consumers, thread t owns column c0 + t of both fields.  Threads [W, W + 32): the producer warp.
+// Threads [W + 32, W + 64): the service warp.
+template <typename T, int N, int W, bool kCtl = false>
+__global__ void __maxnreg__(TDX_EK0_MAXREG) ek0_fused_fhn_kernel(const __grid_constant__ Ek0FusedArgs<T, N> a) {
+    using Cfg = Ek0FusedCfg<T, N, W>;
+    using CSync = NamedSync<1, W>;                         // the consumers' barrier (producer and service warps never join)
+    constexpr int PADC = Cfg::PADC, WP = Cfg::WP, S = Cfg::STAGES, AT_ROW = Cfg::AT_ROW;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);                                   // [S] data has landed
+    uint64_t* empty = full + S;                                                               // [S] consumers are done
+    double* s_red = reinterpret_cast<double*>(smem_raw + Cfg::BAR_BYTES);                     // see kEk0Red*
+    T* s_at = reinterpret_cast<T*>(smem_raw + Cfg::BAR_BYTES + Cfg::RED_BYTES);               // [2][2][AT_ROW]
+    T* s_stage = reinterpret_cast<T*>(smem_raw + Cfg::BAR_BYTES + Cfg::RED_BYTES + Cfg::at_bytes());
+    __shared__ Ek0CtaState<T, N> sh;
+
+    const Geo& g = a.g;
+    const int tc = threadIdx.x;
+    const bool has_lo = a.halo_lo != nullptr, has_hi = a.halo_hi != nullptr;
+    const bool hints = a.keep_frac < 1.0f;
+    const int ns = (int)((a.total_strips - blockIdx.x + gridDim.x - 1) / gridDim.x);   // strips of this CTA
+
+    if (tc == 0) {
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+            mbar_init(full + s, 1);
+            mbar_init(empty + s, 1);
+        }
+        mbar_init(&sh.m1_bar, 1);
+        fence_mbar_init();
+        fence_proxy_async();
+    }
+    __syncthreads();
+
+    unsigned q = 0;                       // producer: ring position
+    unsigned cq = 0, phase_bits = 0u;     // consumers: ring position, parity of each stage's full barrier
+    const int max_attempts = kCtl ? a.max_attempts : 1;
+
+#pragma unroll 1
+    for (int att = 0; att < max_attempts; ++att) {
+        if (!ek0_attempt_begin<T, N, kCtl>(a, sh, att)) break;
+        const Consts<T, N>& c = kCtl ? sh.c : a.c;
+        const Consts<double, N>& cdr = kCtl ? sh.cd : a.cd;
+        const T* mean_in = a.mean_ring[sh.cur];
+        T* mean_out = a.mean_ring[sh.out];
+        T* ref_out = a.ref_ring[sh.out];
+        const unsigned long long hseq = a.wait.seq + (unsigned long long)att;
+        const T* halo_lo = has_lo ? a.halo_lo + (long long)(hseq & 1ull) * a.halo_parity_stride : nullptr;
+        const T* halo_hi = has_hi ? a.halo_hi + (long long)(hseq & 1ull) * a.halo_parity_stride : nullptr;
+
+        if (tc >= W + 32) {
+            ek0_service<T, N>(a, sh, cdr, att, tc - (W + 32));
+            continue;
+        }
+        if (tc >= W) {
+            // ---- producer warp: walks the same (strip, row) enumeration as the consumers, up to S rows ahead ------------
+            // Every item owns ring slot q % S (items beyond the shard simply load nothing).  The 2 n row segments of a
+            // row are issued by 2 n lanes in one instruction.
+            const int lane = tc - W;
+            const int seg_f = lane / N, seg_k = lane - seg_f * N;           // (field, derivative) of this lane's segment
+            const long long seg_src = (long long)seg_k * g.d + (long long)seg_f * g.npts;
+            const int seg_dst = (seg_f * N + seg_k) * WP;
+            const uint64_t pol_keep = l2_policy_evict_last(), pol_stream = l2_policy_evict_first();
+            if (kCtl) fence_proxy_async_global();      // the mean was written with ordinary stores by the previous attempt
+#pragma unroll 1
+            for (int phase = 0; phase < 2; ++phase) {
+#pragma unroll 1
+                for (int kk = 0; kk < ns; ++kk) {
+                    const int k = phase ? ns - 1 - kk : kk;
+                    StripGeom s = strip_geom<W>(g, blockIdx.x + (unsigned)k * gridDim.x, a.col_blocks, a.chunks, has_lo, has_hi);
+                    if (phase) s.dir = -s.dir;
+                    const int L = s.r1 - s.r0 + 2;
+                    const int gs = max(s.c0 - PADC, 0), ge = min(s.c0 + W + PADC, g.cols);
+                    const int off = gs - (s.c0 - PADC);
+                    const uint32_t bytes = (uint32_t)((ge - gs) * (int)sizeof(T));
+                    // L2 residency: the rows phase A reads last are the rows phase B reads first -> keep those, stream the rest
+                    const int keep_from = (phase == 0 && hints) ? L - 1 - (int)ceilf(a.keep_frac * (float)(s.r1 - s.r0)) : L;
+                    int rr = s.dir > 0 ? s.r0 - 1 : s.r1;
+#pragma unroll 1
+                    for (int i = 0; i < L; ++i, rr += s.dir, ++q) {
+                        const unsigned stage = q % S, round = q / S;
+                        if (round > 0) mbar_wait(empty + stage, (round - 1u) & 1u);     // the slot's previous row is consumed
+                        if (rr < 0 || rr >= g.rows) continue;
+                        T* dst = s_stage + (size_t)stage * Cfg::STAGE_ELEMS;
+                        const T* src = mean_in + (long long)rr * g.cols + gs;
+                        if (a.use_bulk) {
+                            if (lane == 0) mbar_expect_tx(full + stage, 2u * N * bytes);
+                            __syncwarp();
+                            if (lane < 2 * N) {
+                                if (hints) bulk_g2s_hint(dst + seg_dst + off, src + seg_src, bytes, full + stage, i >= keep_from ? pol_keep : pol_stream);
+                                else bulk_g2s(dst + seg_dst + off, src + seg_src, bytes, full + stage);
+                            }
+                        } else {
+                            // unaligned / odd-sized grids: plain loads by the 32 lanes, then a normal arrival
+                            for (int seg = 0; seg < 2 * N; ++seg) {
+                                const int f = seg / N, kd = seg - f * N;
+                                const T* sp = src + (long long)kd * g.d + (long long)f * g.npts;
+                                for (int j = lane; j < ge - gs; j += 32) dst[seg * WP + off + j] = ld_state<kCtl>(sp + j);
+                            }
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(full + stage);
+                        }
+                    }
+                }
+            }
+            continue;
+        }
+
+        // ---- consumers ------------------------------------------------------------------------------------------------
+        CSync csync;
+        double* s_rowred = s_red + kEk0RowRed;
+        // deliver this shard's edge rows to the neighbours before anything else (multi-GPU)
+        if (a.pack.enabled)
+            for (int part = (int)blockIdx.x; part < 2 * kPackCtas; part += (int)gridDim.x)   // a small grid takes several parts per CTA
+                pack_halo_part<T, N, CSync, kCtl>(g, c, mean_in, a.pack, a.pack.seq + (unsigned long long)att, part, csync);
+
+        bool halos_ready = false, poisoned = false;
+        int pending_unit = -1, first_unit = -1;      // thread 0: the row whose warp sums wait in s_rowred for the next barrier
+        const uint64_t pol_keep = l2_policy_evict_last(), pol_stream = l2_policy_evict_first();
+        const T inv_dx2 = (T)g.prm[0], pa = (T)g.prm[1], pb = (T)g.prm[2], pk = (T)g.prm[3], inv_tau = (T)g.prm[5];
+        const int wq = tc >> 5, lq = tc & 31;
+
+        auto m_at_from = [&](const T* fld, int idx) -> T {     // predicted, un-preconditioned state of a stage column
+            T acc = c.pinv[0] * fld[idx];
+#pragma unroll
+            for (int k = 1; k < N; ++k) acc = fma((T)A_entry<N>(0, k), c.pinv[k] * fld[k * WP + idx], acc);
+            return c.p[0] * acc;
+        };
+
+        // one phase over this CTA's strips.  kUpdate = false: phase A (forward), true: phase B (backward).
+        // Every finalised grid row leaves ONE partial sum per strip (unit = (row, column block)): the lanes' terms through the
+        // shuffle tree, the warps through shared memory in warp order -- independent of strip boundaries and walking direction.
+        auto run_phase = [&](auto update_tag, const T (&K)[N], double* unit) {
+            constexpr bool kUpdate = decltype(update_tag)::value;
+            constexpr int NK = kUpdate ? N : 2;                 // rows of the predicted mean kept for the row being finalised
+            const bool reduces = !kUpdate || c.want_norm || (kCtl && a.reduce_b.world > 0);
+            auto flush_row_partial = [&](unsigned cq_prev) {
+                if (tc == 0 && pending_unit >= 0) {
+                    const double* ws = s_rowred + (cq_prev & 1u) * 8;
+                    double b = 0.0;
+#pragma unroll
+                    for (int i = 0; i < W / 32; ++i) b += ws[i];
+                    unit[pending_unit] = b;
+                    pending_unit = -1;
+                }
+            };
+#pragma unroll 1
+            for (int kk = 0; kk < ns; ++kk) {
+                const int k = kUpdate ? ns - 1 - kk : kk;
+                const unsigned strip = blockIdx.x + (unsigned)k * gridDim.x;
+                StripGeom s = strip_geom<W>(g, strip, a.col_blocks, a.chunks, has_lo, has_hi);
+                const int cb = (int)(strip % a.col_blocks);
+                if (kUpdate) s.dir = -s.dir;
+                const int L = s.r1 - s.r0 + 2;
+                const int col = s.c0 + tc;
+                const bool valid = tc < s.wlen;
+                const bool left_inner = (tc == 0) && s.c0 > 0;                            // recompute the column left of the strip
+                const bool right_inner = (tc == s.wlen - 1) && (s.c0 + s.wlen < g.cols);  // ... right of the strip
+                const bool left_edge = (tc == 0) && s.c0 == 0;                            // grid edge: replicate own value
+                const bool right_edge = (tc == s.wlen - 1) && (s.c0 + s.wlen >= g.cols);
+                int rr = s.dir > 0 ? s.r0 - 1 : s.r1;
+                T at_m1[2] = {}, at_m2[2] = {}, hs_m1[2] = {}, mp_m1[2][NK] = {};
+                bool first_replicated = false;
+                T* out_ptr = mean_out + ((long long)(rr - s.dir) * g.cols + col);      // row being finalised, field 0
+                // the rows phase B writes last are the rows the NEXT attempt's phase A reads first -> keep those in L2
+                const int keep_from = (kUpdate && hints) ? L - (int)ceilf(a.keep_frac * (float)(s.r1 - s.r0)) : L;
+#pragma unroll 1
+                for (int i = 0; i < L; ++i, rr += s.dir, ++cq, out_ptr += (long long)s.dir * g.cols) {
+                    const unsigned stage = cq % S;
+                    T* at_row = s_at + (cq & 1u) * 2 * AT_ROW;
+                    T at_cur[2], mp_cur[2][NK];
+                    if (rr >= 0 && rr < g.rows) {
+                        mbar_wait(full + stage, (phase_bits >> stage) & 1u);
+                        phase_bits ^= (1u << stage);
+                        const T* st = s_stage + (size_t)stage * Cfg::STAGE_ELEMS;
+#pragma unroll
+                        for (int f = 0; f < 2; ++f) {
+                            T raw[N], mp[N];
+#pragma unroll
+                            for (int kd = 0; kd < N; ++kd) raw[kd] = st[(f * N + kd) * WP + PADC + tc];
+                            predict_column<T, N>(raw, c, mp);
+                            at_cur[f] = c.p[0] * mp[0];
+#pragma unroll
+                            for (int r = 0; r < NK; ++r) mp_cur[f][r] = mp[r];
+                        }
+                        // columns just outside the strip (inside the grid): recomputed from the stage's overlap columns
+                        if (left_inner) {
+#pragma unroll
+                            for (int f = 0; f < 2; ++f) at_row[f * AT_ROW] = m_at_from(st + f * N * WP, PADC - 1);
+                        }
+                        if (right_inner) {
+#pragma unroll
+                            for (int f = 0; f < 2; ++f) at_row[f * AT_ROW + s.wlen + 1] = m_at_from(st + f * N * WP, PADC + s.wlen);
+                        }
+                    } else {
+                        const T* h = rr < 0 ? halo_lo : halo_hi;
+                        if (h != nullptr) {
+                            if (!halos_ready) {
+                                if (!cta_wait_halos(a.wait, hseq, &sh.ok, csync)) poisoned = true;
+                                halos_ready = true;
+                            }
+#pragma unroll
+                            for (int f = 0; f < 2; ++f) at_cur[f] = valid ? __ldcg(h + (long long)f * g.cols + col) : (T)0;
+                        } else {
+                            // edge replication (ivp.py:488-490): the row beyond the grid equals the grid's edge row
+#pragma unroll
+                            for (int f = 0; f < 2; ++f) at_cur[f] = at_m1[f];
+                            if (i == 0) first_replicated = true;
+                        }
+#pragma unroll
+                        for (int f = 0; f < 2; ++f)
+#pragma unroll
+                            for (int r = 0; r < NK; ++r) mp_cur[f][r] = (T)0;
+                    }
+                    if (i == 1 && first_replicated) {
+                        at_m1[0] = at_cur[0];
+                        at_m1[1] = at_cur[1];
+                    }
+                    if (valid) {
+#pragma unroll
+                        for (int f = 0; f < 2; ++f) {
+                            at_row[f * AT_ROW + tc + 1] = at_cur[f];
+                            if (left_edge) at_row[f * AT_ROW] = at_cur[f];
+                            if (right_edge) at_row[f * AT_ROW + s.wlen + 1] = at_cur[f];
+                        }
+                    }
+                    csync();              // publishes the row; every consumer has read the stage -> hand it back
+                    if (tc == 0) mbar_arrive(empty + stage);
+                    if (reduces) flush_row_partial(cq - 1u);
+                    T hs_cur[2];
+#pragma unroll
+                    for (int f = 0; f < 2; ++f) hs_cur[f] = at_row[f * AT_ROW + tc] + at_row[f * AT_ROW + tc + 2];
+
+                    if (i >= 2) {         // the previous row now has both vertical neighbours
+                        double term = 0.0;
+                        if (valid) {
+                            const T u = at_m1[0], v = at_m1[1];
+#pragma unroll
+                            for (int f = 0; f < 2; ++f) {
+                                const T own = at_m1[f];
+                                const T lap = (((at_m2[f] + at_cur[f]) + hs_m1[f]) - (T)4 * own) * inv_dx2;
+                                T fx;
+                                if (f == 0) fx = pa * lap + u - u * u * u - v + pk;       // ivp.py:441
+                                else fx = (pb * lap + u - v) * inv_tau;                   // ivp.py:442
+                                const T z = c.p[1] * mp_m1[f][1] - fx;
+                                if constexpr (!kUpdate) {
+                                    term += (double)z * (double)z;
+                                } else {
+                                    T* mo_ptr = out_ptr + (long long)f * g.npts;
+                                    T m0 = (T)0;
+#pragma unroll
+                                    for (int r = 0; r < N; ++r) {
+                                        const T mo = c.p[r] * (mp_m1[f][r] - K[r] * z);
+                                        if (hints) st_global_hint(mo_ptr, mo, i >= keep_from ? pol_keep : pol_stream);
+                                        else *mo_ptr = mo;
+                                        mo_ptr += g.d;
+                                        if (r == 0) m0 = mo;
+                                    }
+                                    const T ref = tabs<T>(m0);
+                                    if (ref_out) {
+                                        T* rp = ref_out + ((out_ptr - mean_out) + (long long)f * g.npts);
+                                        if (hints) st_global_hint(rp, ref, pol_stream);
+                                        else *rp = ref;
+                                    }
+                                    if (c.want_norm) {
+                                        const double tol = (double)c.abstol + (double)c.reltol * (double)ref;
+                                        term += 1.0 / (tol * tol);
+                                    }
+                                }
+                            }
+                        }
+                        if (reduces) {
+                            const double ws = warp_sum(term);
+                            if (lq == 0) s_rowred[(cq & 1u) * 8 + wq] = ws;
+                            if (tc == 0) {
+                                pending_unit = (rr - s.dir) * (int)a.col_blocks + cb;
+                                if (first_unit < 0) first_unit = pending_unit;
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int f = 0; f < 2; ++f) {
+                        at_m2[f] = at_m1[f];
+                        at_m1[f] = at_cur[f];
+                        hs_m1[f] = hs_cur[f];
+#pragma unroll
+                        for (int r = 0; r < NK; ++r) mp_m1[f][r] = mp_cur[f][r];
+                    }
+                }
+            }
+            if (reduces) {
+                csync();
+                flush_row_partial(cq - 1u);
+                if (tc == 0 && poisoned && first_unit >= 0) unit[first_unit] = nan("");   // stale halos: fail the attempt everywhere
+            }
+        };
+
+        T K[N];
+#pragma unroll
+        for (int r = 0; r < N; ++r) K[r] = (T)0;
+
+#ifdef TDX_EK0_TIMING
+        double* stamps = a.partials + 1024 + 4 * blockIdx.x;    // [t_start, t_end_A, t_gain_seen, t_end_B] in ns
+        if (tc == 0) {
+            stamps[0] = (double)global_timer_ns();
+            unsigned smid;
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            a.partials[1024 + 4096 + blockIdx.x] = (double)smid;
+        }
+#endif
+        // ---- phase A ------------------------------------------------------------------------------------------------
+        run_phase(std::false_type{}, K, a.red_a.unit);
+#ifdef TDX_EK0_TIMING
+        if (tc == 0) stamps[1] = (double)global_timer_ns();
+#endif
+        const double err_cal = ek0_mid_barrier<T, N>(a, sh, cdr, att, s_red, K, csync);
+#ifdef TDX_EK0_TIMING
+        if (tc == 0) stamps[2] = (double)global_timer_ns();
+#endif
+        // ---- phase B ------------------------------------------------------------------------------------------------
+        run_phase(std::true_type{}, K, a.red_b.unit);
+#ifdef TDX_EK0_TIMING
+        if (tc == 0) stamps[3] = (double)global_timer_ns();
+#endif
+        if (kCtl) fence_proxy_async_global();          // the next attempt's TMA loads read what this thread just stored
+        ek0_end_barrier<T, N, kCtl>(a, sh, c, att, err_cal, s_red, csync);
+    }
+}
+
+// =====================================================================================================================
+// The same one-launch attempt for the 1-d vector fields (vanderpol, lorenz96, brusselator, burgers_1d, wave_1d, ...).
+//
+// Work unit = the 256-coordinate tile of the sweep kernels (tile_coord / ExtTile / IVP::ring_value / IVP::eval are reused as
+// they are): thread = one state coordinate.  A CTA owns a CONTIGUOUS range of tiles, walks it forwards in phase A and
+// backwards in phase B (L2 reuse), and gets every tile's raw mean columns through the same TMA ring + producer warp as the
+// fhn kernel; the few stencil neighbours outside a tile (2-3 per field) are recomputed from the mean through L2.
+// =====================================================================================================================
+template <typename T, int N>
+struct Ek0ChainCfg {
+    static constexpr int STAGES = 4;
+    static constexpr int THREADS = kThreads + 64;                     // consumers + producer warp + service warp
+    static constexpr int STAGE_ELEMS = N * kThreads;                 // [derivative][thread]
+    static constexpr size_t BAR_BYTES = 128, RED_BYTES = 512;
+    __host__ __device__ static constexpr size_t at_bytes(int at_elems) { return ((size_t)at_elems * sizeof(T) + 127) / 128 * 128; }
+    __host__ __device__ static constexpr size_t total(int at_elems) {
+        return BAR_BYTES + RED_BYTES + 2 * at_bytes(at_elems) + STAGES * (size_t)STAGE_ELEMS * sizeof(T);
+    }
+};
 
 template <class IVP, typename T, int N, bool kCtl = false>
 __global__ void __maxnreg__(72) ek0_fused_chain_kernel(const __grid_constant__ Ek0FusedArgs<T, N> a) {
@@ -671,47 +690,10 @@ __global__ void __maxnreg__(72) ek0_fused_chain_kernel(const __grid_constant__ E
     T* s_at0 = reinterpret_cast<T*>(smem_raw + Cfg::BAR_BYTES + Cfg::RED_BYTES);
     constexpr size_t AT_STRIDE = Cfg::at_bytes(E::ELEMS) / sizeof(T);
     T* s_stage = reinterpret_cast<T*>(smem_raw + Cfg::BAR_BYTES + Cfg::RED_BYTES + 2 * Cfg::at_bytes(E::ELEMS));
+    __shared__ Ek0CtaState<T, N> sh;
 
     const Geo& g = a.g;
     const int tid = threadIdx.x;
-    const Consts<T, N>* cp = &a.c;
-    const Consts<double, N>* cdp = &a.cd;
-    const T* mean_in = a.mean_in;
-    T* mean_out = a.mean_out;
-    const T* Cl_in = a.Cl_in;
-    T* Cl_out = a.Cl_out;
-    if constexpr (kCtl) {
-        __shared__ Consts<T, N> s_c;
-        __shared__ Consts<double, N> s_cd;
-        __shared__ int s_cur;
-        if (tid == 0) {
-            const StepCtl* ctl = a.ctl;
-            Consts<T, N> cc = a.c;
-            Consts<double, N> ccd = a.cd;
-#pragma unroll
-            for (int k = 0; k < N; ++k) {
-                ccd.p[k] = ctl->p[k];
-                ccd.pinv[k] = ctl->pinv[k];
-                cc.p[k] = (T)ctl->p[k];
-                cc.pinv[k] = (T)ctl->pinv[k];
-            }
-            ccd.dt = ctl->dt;
-            cc.dt = (T)ctl->dt;
-            s_c = cc;
-            s_cd = ccd;
-            s_cur = ctl->done ? -1 : ctl->cur;
-        }
-        __syncthreads();
-        if (s_cur < 0) return;
-        cp = &s_c;
-        cdp = &s_cd;
-        mean_in = a.mean_ab[s_cur];
-        mean_out = a.mean_ab[s_cur ^ 1];
-        Cl_in = a.Cl_ab[s_cur];
-        Cl_out = a.Cl_ab[s_cur ^ 1];
-    }
-    const Consts<T, N>& c = *cp;
-    const Consts<double, N>& cdr = *cdp;
 
     // this CTA's contiguous range of tiles
     const unsigned num_tiles = a.total_strips, tiles_x = a.col_blocks;
@@ -724,161 +706,159 @@ __global__ void __maxnreg__(72) ek0_fused_chain_kernel(const __grid_constant__ E
             mbar_init(full + s, 1);
             mbar_init(empty + s, 1);
         }
+        mbar_init(&sh.m1_bar, 1);
         fence_mbar_init();
         fence_proxy_async();
     }
     __syncthreads();
 
-    if (tid >= kThreads) {
-        // ---- producer warp: one tile per ring slot; per tile NF * n contiguous row segments -------------------------
-        const int lane = tid - kThreads;
-        const int seg_f = lane / N, seg_k = lane - seg_f * N;
-        unsigned q = 0;
+    unsigned q = 0, cq = 0, phase_bits = 0u;
+    const int max_attempts = kCtl ? a.max_attempts : 1;
+
 #pragma unroll 1
-        for (int phase = 0; phase < 2; ++phase) {
-#pragma unroll 1
-            for (unsigned j = 0; j < t1 - t0; ++j, ++q) {
-                const unsigned tile = phase ? (t1 - 1u - j) : (t0 + j);
-                const unsigned stage = q % S, round = q / S;
-                if (round > 0) mbar_wait(empty + stage, (round - 1u) & 1u);
-                // the tile's columns of field f: [col0, col0 + len) of a chain (one tile row)
-                const long long col0 = (long long)(tile % tiles_x) * TCOLS;
-                long long len = (long long)g.cols - col0;
-                len = len > TCOLS ? TCOLS : len;
-                T* dst = s_stage + (size_t)stage * Cfg::STAGE_ELEMS;
-                const uint32_t bytes = (uint32_t)(len * (long long)sizeof(T));
-                const bool bulk = a.use_bulk && (bytes % 16u == 0u) && (((col0 * (long long)sizeof(T)) & 15) == 0);
-                if (bulk) {
-                    if (lane == 0) mbar_expect_tx(full + stage, (uint32_t)(NF * N) * bytes);
-                    __syncwarp();
-                    if (lane < NF * N)
-                        bulk_g2s(dst + seg_k * kThreads + seg_f * TCOLS, mean_in + (long long)seg_k * g.d + (long long)seg_f * g.npts + col0,
-                                 bytes, full + stage);
-                } else {
-                    for (int seg = 0; seg < NF * N; ++seg) {
-                        const int f = seg / N, kd = seg - f * N;
-                        const T* sp = mean_in + (long long)kd * g.d + (long long)f * g.npts + col0;
-                        for (int jj = lane; jj < (int)len; jj += 32) dst[kd * kThreads + f * TCOLS + jj] = __ldg(sp + jj);
-                    }
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(full + stage);
-                }
-            }
+    for (int att = 0; att < max_attempts; ++att) {
+        if (!ek0_attempt_begin<T, N, kCtl>(a, sh, att)) break;
+        const Consts<T, N>& c = kCtl ? sh.c : a.c;
+        const Consts<double, N>& cdr = kCtl ? sh.cd : a.cd;
+        const T* mean_in = a.mean_ring[sh.cur];
+        T* mean_out = a.mean_ring[sh.out];
+        T* ref_out = a.ref_ring[sh.out];
+        const unsigned long long hseq = a.wait.seq + (unsigned long long)att;
+        const T* halo_lo = a.halo_lo ? a.halo_lo + (long long)(hseq & 1ull) * a.halo_parity_stride : nullptr;
+        const T* halo_hi = a.halo_hi ? a.halo_hi + (long long)(hseq & 1ull) * a.halo_parity_stride : nullptr;
+
+        if (tid >= kThreads + 32) {
+            ek0_service<T, N>(a, sh, cdr, att, tid - (kThreads + 32));
+            continue;
         }
-        return;
-    }
-
-    // ---- consumers ----------------------------------------------------------------------------------------------------
-    CSync csync;
-    if (a.pack.enabled)
-        for (int part = (int)blockIdx.x; part < 2 * kPackCtas; part += (int)gridDim.x)
-            pack_halo_part<T, N>(g, c, mean_in, a.pack, part, csync);
-    double* s_m1 = s_red + 16;
-    if (tid == 0) ek0_m1_column<T, N>(cdr, Cl_in, s_m1);
-    // the shard's end tiles read the neighbours' halo values: they are tiny and on their way since the peers' kernels started
-    if ((a.halo_lo != nullptr || a.halo_hi != nullptr) && (t0 == 0u || t1 == num_tiles)) cta_wait_halos(a.wait, csync);
-
-    unsigned cq = 0, phase_bits = 0u;
-    T K[N];
-#pragma unroll
-    for (int r = 0; r < N; ++r) K[r] = (T)0;
-
-    auto run_phase = [&](auto update_tag) -> double {
-        constexpr bool kUpdate = decltype(update_tag)::value;
-        double acc = 0.0;
+        if (tid >= kThreads) {
+            // ---- producer warp: one tile per ring slot; per tile NF * n contiguous row segments -------------------------
+            const int lane = tid - kThreads;
+            const int seg_f = lane / N, seg_k = lane - seg_f * N;
+            if (kCtl) fence_proxy_async_global();
 #pragma unroll 1
-        for (unsigned j = 0; j < t1 - t0; ++j, ++cq) {
-            const unsigned tile = kUpdate ? (t1 - 1u - j) : (t0 + j);
-            const unsigned stage = cq % S;
-            const Coord co = tile_coord<Shape>(g, tile, tiles_x);
-            FrontRegs<IVP, T, N> fr;
-            front_load<IVP, T, N, false>(g, c, mean_in, a.halo_lo, a.halo_hi, co, fr);     // ring / fill values only
-            mbar_wait(full + stage, (phase_bits >> stage) & 1u);
-            phase_bits ^= (1u << stage);
-            const T* st = s_stage + (size_t)stage * Cfg::STAGE_ELEMS + tid;
-#pragma unroll
-            for (int kd = 0; kd < N; ++kd) fr.raw[kd] = co.valid ? st[kd * kThreads] : (T)0;
-            T mp[N], fx, jac;
-            front_eval<IVP, T, N>(g, c, co, fr, s_at0 + (cq & 1u) * AT_STRIDE, mp, fx, jac, csync);
-            if (tid == 0) mbar_arrive(empty + stage);       // every consumer has its column in registers (barrier above)
-            if (co.valid) {
-                const T z = c.p[1] * mp[1] - fx;
-                if constexpr (!kUpdate) {
-                    acc += (double)z * (double)z;
-                } else {
-                    T m0 = (T)0;
-                    T* mo_ptr = mean_out + co.flat;
-#pragma unroll
-                    for (int r = 0; r < N; ++r) {
-                        const T mo = c.p[r] * (mp[r] - K[r] * z);
-                        *mo_ptr = mo;
-                        mo_ptr += g.d;
-                        if (r == 0) m0 = mo;
-                    }
-                    const T ref = tabs<T>(m0);
-                    if (a.ref_out) a.ref_out[co.flat] = ref;
-                    if (c.want_norm) {
-                        const double tol = (double)c.abstol + (double)c.reltol * (double)ref;
-                        acc += 1.0 / (tol * tol);
+            for (int phase = 0; phase < 2; ++phase) {
+#pragma unroll 1
+                for (unsigned j = 0; j < t1 - t0; ++j, ++q) {
+                    const unsigned tile = phase ? (t1 - 1u - j) : (t0 + j);
+                    const unsigned stage = q % S, round = q / S;
+                    if (round > 0) mbar_wait(empty + stage, (round - 1u) & 1u);
+                    // the tile's columns of field f: [col0, col0 + len) of a chain (one tile row)
+                    const long long col0 = (long long)(tile % tiles_x) * TCOLS;
+                    long long len = (long long)g.cols - col0;
+                    len = len > TCOLS ? TCOLS : len;
+                    T* dst = s_stage + (size_t)stage * Cfg::STAGE_ELEMS;
+                    const uint32_t bytes = (uint32_t)(len * (long long)sizeof(T));
+                    const bool bulk = a.use_bulk && (bytes % 16u == 0u) && (((col0 * (long long)sizeof(T)) & 15) == 0);
+                    if (bulk) {
+                        if (lane == 0) mbar_expect_tx(full + stage, (uint32_t)(NF * N) * bytes);
+                        __syncwarp();
+                        if (lane < NF * N)
+                            bulk_g2s(dst + seg_k * kThreads + seg_f * TCOLS, mean_in + (long long)seg_k * g.d + (long long)seg_f * g.npts + col0,
+                                     bytes, full + stage);
+                    } else {
+                        for (int seg = 0; seg < NF * N; ++seg) {
+                            const int f = seg / N, kd = seg - f * N;
+                            const T* sp = mean_in + (long long)kd * g.d + (long long)f * g.npts + col0;
+                            for (int jj = lane; jj < (int)len; jj += 32) dst[kd * kThreads + f * TCOLS + jj] = ld_state<kCtl>(sp + jj);
+                        }
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(full + stage);
                     }
                 }
             }
+            continue;
         }
-        return acc;
-    };
 
-    // ---- phase A, barrier, gain ---------------------------------------------------------------------------------------
-    const double acc_a = run_phase(std::false_type{});
-    if (publish_partial(acc_a, s_red, a.partials, a.ticket, csync) == gridDim.x - 1) {
-        double z_sq = sum_partials(s_red, a.partials, csync);
-        if (a.reduce_a.world > 0) {
-            csync();
-            z_sq = cta_allreduce(z_sq, a.reduce_a, s_red, csync);
-        }
-        if (tid == 0) {
-            a.mid->z_sq = z_sq;
-            if (a.z_sq_out) *a.z_sq_out = z_sq;
-            *a.ticket = 0u;
-            __threadfence();
-            st_release_gpu(a.mid_flag, a.mid_seq);
-        }
-    }
-    if (tid == 0) {
-        const unsigned long long ts = global_timer_ns();
-        s_red[30] = 0.0;
-        while (ld_acquire_gpu(a.mid_flag) < a.mid_seq) {
-            if (global_timer_ns() - ts > 4000000000ull) {
-                s_red[30] = 1.0;
-                break;
-            }
-            __nanosleep(64);
-        }
-    }
-    csync();
-    const double z_sq_all = (s_red[30] != 0.0) ? nan("") : __ldcg(&a.mid->z_sq);
-    const double err_cal = ek0_gain<T, N>(cdr, s_m1, z_sq_all, a.d_global, K);
+        // ---- consumers ------------------------------------------------------------------------------------------------
+        CSync csync;
+        double* s_tilered = s_red + kEk0RowRed;
+        const int wq = tid >> 5, lq = tid & 31;
+        if (a.pack.enabled)
+            for (int part = (int)blockIdx.x; part < 2 * kPackCtas; part += (int)gridDim.x)
+                pack_halo_part<T, N, CSync, kCtl>(g, c, mean_in, a.pack, a.pack.seq + (unsigned long long)att, part, csync);
+        // the shard's end tiles read the neighbours' halo values: they are tiny and on their way since the peers' kernels started
+        bool poisoned = false;
+        if ((a.halo_lo != nullptr || a.halo_hi != nullptr) && (t0 == 0u || t1 == num_tiles))
+            poisoned = !cta_wait_halos(a.wait, hseq, &sh.ok, csync);
 
-    // ---- phase B ----------------------------------------------------------------------------------------------------
-    const double acc_b = run_phase(std::true_type{});
-    const unsigned arrival = publish_partial(acc_b, s_red, a.partials + gridDim.x, a.ticket + 1, csync);
-    if (arrival == 0u && tid == 0) ek0_mid_compute<T, N>(cdr, Cl_in, z_sq_all, a.d_global, Cl_out, a.err_out, a.mid);
-    if (arrival == gridDim.x - 1) {
-        if (c.want_norm) {
-            double b = sum_partials(s_red, a.partials + gridDim.x, csync);
-            if (tid == 0) {
-                b *= err_cal * err_cal;
-                b *= (double)c.dt * (double)c.dt;
+        T K[N];
+#pragma unroll
+        for (int r = 0; r < N; ++r) K[r] = (T)0;
+        int pending_unit = -1;
+
+        auto run_phase = [&](auto update_tag, double* unit) {
+            constexpr bool kUpdate = decltype(update_tag)::value;
+            const bool reduces = !kUpdate || c.want_norm || (kCtl && a.reduce_b.world > 0);
+            auto flush_tile_partial = [&](unsigned cq_prev) {
+                if (tid == 0 && pending_unit >= 0) {
+                    const double* ws = s_tilered + (cq_prev & 1u) * 8;
+                    double b = 0.0;
+#pragma unroll
+                    for (int i = 0; i < kWarps; ++i) b += ws[i];
+                    unit[pending_unit] = b;
+                    pending_unit = -1;
+                }
+            };
+#pragma unroll 1
+            for (unsigned j = 0; j < t1 - t0; ++j, ++cq) {
+                const unsigned tile = kUpdate ? (t1 - 1u - j) : (t0 + j);
+                const unsigned stage = cq % S;
+                const Coord co = tile_coord<Shape>(g, tile, tiles_x);
+                FrontRegs<IVP, T, N> fr;
+                front_load<IVP, T, N, false, kCtl>(g, c, mean_in, halo_lo, halo_hi, co, fr);     // ring / fill values only
+                mbar_wait(full + stage, (phase_bits >> stage) & 1u);
+                phase_bits ^= (1u << stage);
+                const T* st = s_stage + (size_t)stage * Cfg::STAGE_ELEMS + tid;
+#pragma unroll
+                for (int kd = 0; kd < N; ++kd) fr.raw[kd] = co.valid ? st[kd * kThreads] : (T)0;
+                T mp[N], fx, jac;
+                front_eval<IVP, T, N>(g, c, co, fr, s_at0 + (cq & 1u) * AT_STRIDE, mp, fx, jac, csync);
+                if (tid == 0) mbar_arrive(empty + stage);       // every consumer has its column in registers (barrier above)
+                if (reduces) flush_tile_partial(cq - 1u);
+                double term = 0.0;
+                if (co.valid) {
+                    const T z = c.p[1] * mp[1] - fx;
+                    if constexpr (!kUpdate) {
+                        term = (double)z * (double)z;
+                    } else {
+                        T m0 = (T)0;
+                        T* mo_ptr = mean_out + co.flat;
+#pragma unroll
+                        for (int r = 0; r < N; ++r) {
+                            const T mo = c.p[r] * (mp[r] - K[r] * z);
+                            *mo_ptr = mo;
+                            mo_ptr += g.d;
+                            if (r == 0) m0 = mo;
+                        }
+                        const T ref = tabs<T>(m0);
+                        if (ref_out) ref_out[co.flat] = ref;
+                        if (c.want_norm) {
+                            const double tol = (double)c.abstol + (double)c.reltol * (double)ref;
+                            term = 1.0 / (tol * tol);
+                        }
+                    }
+                }
+                if (reduces) {
+                    const double ws = warp_sum(term);
+                    if (lq == 0) s_tilered[(cq & 1u) * 8 + wq] = ws;
+                    if (tid == 0) pending_unit = (int)tile;
+                }
             }
-            if (a.reduce_b.world > 0) {
+            if (reduces) {
                 csync();
-                b = cta_allreduce(b, a.reduce_b, s_red, csync);
+                flush_tile_partial(cq - 1u);
+                if (tid == 0 && poisoned && t1 > t0) unit[t0] = nan("");
             }
-            if (tid == 0) *a.out_sum = b;
-            if (kCtl && tid == 0) ctl_update(a.ctl, b, a.d_global);
-        } else if (kCtl && tid == 0) {
-            ctl_update(a.ctl, 0.0, a.d_global);
-        }
-        if (tid == 0) a.ticket[1] = 0u;
+        };
+
+        // ---- phase A, barrier, gain -----------------------------------------------------------------------------------
+        run_phase(std::false_type{}, a.red_a.unit);
+        const double err_cal = ek0_mid_barrier<T, N>(a, sh, cdr, att, s_red, K, csync);
+        // ---- phase B --------------------------------------------------------------------------------------------------
+        run_phase(std::true_type{}, a.red_b.unit);
+        if (kCtl) fence_proxy_async_global();
+        ek0_end_barrier<T, N, kCtl>(a, sh, c, att, err_cal, s_red, csync);
     }
 }
 

@@ -53,7 +53,7 @@ struct SmemLayout {
     static constexpr int STRIDE = VEC ? ((UNITS | 1) * PER_UNIT) : ((NN % 2 == 1) ? NN : NN + 1);
     static constexpr int SC_ELEMS = kWarps * 32 * STRIDE;
     static constexpr size_t BAR_BYTES = 128;                       // kWarps mbarriers, padded
-    static constexpr size_t RED_BYTES = 128;                       // kWarps doubles, padded
+    static constexpr size_t RED_BYTES = 256;                       // 2 x kWarps per-tile warp sums / the chunk sums of the final reduction
     __host__ __device__ static constexpr size_t sc_bytes() { return ((size_t)SC_ELEMS * sizeof(T) + 127) / 128 * 128; }
     __host__ __device__ static constexpr size_t at_bytes(int at_elems) { return ((size_t)at_elems * sizeof(T) + 127) / 128 * 128; }
     __host__ __device__ static constexpr size_t total(int at_elems, bool with_sc) {
@@ -132,7 +132,8 @@ __device__ __forceinline__ int tile_row0(const Coord& c) { return c.row - c.tr; 
 __device__ __forceinline__ int tile_col0(const Coord& c) { return c.col - c.tcol; }
 
 // kOwn = false: only the ring / fill values (the caller gets the thread's own column from somewhere else, e.g. a TMA stage)
-template <class IVP, typename T, int N, bool kOwn = true>
+// kCoherent: the mean may have been written earlier in the same kernel (multi-attempt kernels): no read-only-path loads
+template <class IVP, typename T, int N, bool kOwn = true, bool kCoherent = false>
 __device__ __forceinline__ void front_load(const Geo& g, const Consts<T, N>& c, const T* __restrict__ mean_in,
                                            const T* halo_lo, const T* halo_hi, const Coord& co,
                                            FrontRegs<IVP, T, N>& fr) {
@@ -141,13 +142,13 @@ __device__ __forceinline__ void front_load(const Geo& g, const Consts<T, N>& c, 
         const T* src = mean_in + co.flat;
 #pragma unroll
         for (int k = 0; k < N; ++k) {
-            fr.raw[k] = co.valid ? __ldg(src) : (T)0;
+            fr.raw[k] = co.valid ? ld_state<kCoherent>(src) : (T)0;
             src += g.d;
         }
     }
     fr.ring = (T)0;
     fr.fill = (T)0;
-    MeanAt<T, N> at{mean_in, g.d, &c};
+    MeanAt<T, N, kCoherent> at{mean_in, g.d, &c};
     if (E::NRING > 0 && (int)threadIdx.x < IVP::Shape::NF * E::NRING) {
         const int field = threadIdx.x / (E::NRING > 0 ? E::NRING : 1);
         int er, ec;
@@ -190,24 +191,28 @@ constexpr int kPackCtas = 4;
 
 template <typename T>
 struct PackPeer {
-    T* dst_lower;                    // lower neighbour's halo_hi[parity] (mapped), or null
-    T* dst_upper;                    // upper neighbour's halo_lo[parity] (mapped), or null
-    unsigned long long* flag_lower;  // lower neighbour's halo_flag_hi[parity]
-    unsigned long long* flag_upper;  // upper neighbour's halo_flag_lo[parity]
+    T* dst_lower;                    // lower neighbour's halo_hi buffer of parity 0 (mapped), or null
+    T* dst_upper;                    // upper neighbour's halo_lo buffer of parity 0 (mapped), or null
+    unsigned long long* flag_lower;  // lower neighbour's halo_flag_hi[0]
+    unsigned long long* flag_upper;  // upper neighbour's halo_flag_lo[0]
     unsigned int* done_count;        // local CommHeader::pack_count
-    unsigned long long seq;
+    unsigned long long seq;          // halo sequence number of the kernel's first attempt
+    long long parity_stride;         // elements between the parity-0 and the parity-1 halo buffer
     int n_first, n_last;
     int enabled;
 };
 
-template <typename T, int N, class Sync = FullSync>
+template <typename T, int N, class Sync = FullSync, bool kCoherent = false>
 __device__ __forceinline__ void pack_halo_part(const Geo& g, const Consts<T, N>& c, const T* mean_in,
-                                               const PackPeer<T>& pk, int part_index, Sync sync = Sync()) {
-    MeanAt<T, N> at{mean_in, g.d, &c};
+                                               const PackPeer<T>& pk, unsigned long long seq, int part_index,
+                                               Sync sync = Sync()) {
+    MeanAt<T, N, kCoherent> at{mean_in, g.d, &c};
     const bool lower = part_index < kPackCtas;
     const int part = lower ? part_index : part_index - kPackCtas;
+    const int par = (int)(seq & 1ull);
     T* dst = lower ? pk.dst_lower : pk.dst_upper;
     if (dst == nullptr) return;      // CTA-uniform
+    dst += (long long)par * pk.parity_stride;
     const int per_field = lower ? pk.n_first : pk.n_last;
     const long long start = lower ? 0 : (g.npts - pk.n_last);
     const int total = g.nf * per_field;
@@ -225,7 +230,7 @@ __device__ __forceinline__ void pack_halo_part(const Geo& g, const Consts<T, N>&
         if (prev == kPackCtas - 1) {
             *cnt = 0u;
             __threadfence();   // the other CTAs' fences happened before their atomicAdd; order our read of the count
-            st_release_sys(lower ? pk.flag_lower : pk.flag_upper, pk.seq);
+            st_release_sys((lower ? pk.flag_lower : pk.flag_upper) + par, seq);
         }
     }
 }
@@ -240,7 +245,7 @@ struct PackPeerArgs {
 
 template <typename T, int N>
 __global__ void __launch_bounds__(1024) pack_halo_peer_kernel(const __grid_constant__ PackPeerArgs<T, N> a) {
-    pack_halo_part<T, N>(a.g, a.c, a.mean_in, a.pk, (int)blockIdx.x);
+    pack_halo_part<T, N>(a.g, a.c, a.mean_in, a.pk, a.pk.seq, (int)blockIdx.x);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -258,20 +263,26 @@ struct DekArgs {
     T* sc_out;
     T* err_out;
     T* ref_out;
-    const T* halo_lo;
+    const T* halo_lo;                  // the caller's halo buffers, or the parity-0 buffers of the context's peer-written ones
     const T* halo_hi;
-    double* partials;
+    long long halo_parity_stride;      // elements between the parity-0 and parity-1 buffers (0: caller-provided halos)
+    double* partials;                  // per-CTA partial sums (launches over a part of the tiles only)
     unsigned int* ticket;
     double* out_sum;
-    unsigned int num_tiles, tiles_x;   // num_tiles = number of tiles THIS launch processes (both ranges)
+    RedPlan red;                       // per-tile partials + the sharding-independent summation order (unit == null: per-CTA partials)
+    unsigned int num_tiles, tiles_x;   // num_tiles = number of tiles THIS launch processes (all ranges)
     TileRanges ranges;
     CommWait wait;                     // peer-memory halos: flags to wait for (null: nothing to wait for)
     CommReduce reduce;                 // fused all-reduce of the norm sum (world == 0: off)
     PackPeer<T> pack;                  // fused halo delivery (enabled == 0: off)
-    // device-resident step controller (kCtl instantiation): dt, Nordsieck vectors and the current buffer come from ``ctl``
+    // device-resident step controller (kCtl instantiation): dt, Nordsieck vectors and the current ring slot come from ``ctl``;
+    // the kernel runs up to ``max_attempts`` attempts, the last CTA of each publishing the decision to the others
     StepCtl* ctl;
-    T* mean_ab[2];
-    T* sc_ab[2];
+    T* mean_ring[kMaxRing];
+    T* sc_ring[kMaxRing];
+    T* err_ring[kMaxRing];             // per-slot error_estimate / reference_state vectors (null entries: not written)
+    T* ref_ring[kMaxRing];
+    int max_attempts;
     double d_global;
 };
 
@@ -285,16 +296,46 @@ struct DekSmem {
     // registers for a third and fourth CTA, which is what hides the front end's load latency when there are few factor bytes
     // per coordinate to wait for (8.4 M dimensions, fp64: nu = 1 39 -> 53 %, nu = 2 63 -> 81 %, nu = 3 78 -> 85 % of the roofline)
     static constexpr int MIN_BLOCKS = (N <= 2) ? TDX_MIN_BLOCKS_N2 : (N == 3) ? TDX_MIN_BLOCKS_N3 : (N == 4) ? TDX_MIN_BLOCKS_N4 : TDX_MIN_BLOCKS;
-    static constexpr int SC_SLOTS = (MIN_BLOCKS * (L::BAR_BYTES + L::RED_BYTES + 2 * 4096 + 2 * L::sc_bytes()) <= 225 * 1024) ? 2 : 1;
+    static constexpr int SC_SLOTS = (MIN_BLOCKS * (L::BAR_BYTES + L::RED_BYTES + 2 * 4096 + 2 * L::sc_bytes() + 1024) <= 225 * 1024) ? 2 : 1;
     __host__ __device__ static constexpr size_t total(int at_elems) {
         return L::BAR_BYTES + L::RED_BYTES + SLOTS * L::at_bytes(at_elems) + SC_SLOTS * L::sc_bytes();
     }
 };
 
+// What the last CTA of a controller-driven attempt does once the global norm sum is known: decide (ctl_update), tell the
+// host feed, wait for the ring slot the next attempt writes to, publish the decision (epoch) to the other CTAs.
+__device__ inline void ctl_finish_attempt(StepCtl* ctl, double total, double d_global, unsigned long long epoch_next) {
+    ctl_update(ctl, total, d_global);
+    HostFeed* fd = ctl->feed;
+    if (fd != nullptr) {
+        __threadfence_system();
+        fd->attempts = (unsigned long long)ctl->attempts;
+        fd->accepted = (unsigned long long)ctl->accepted;
+        __threadfence_system();
+        if (fd->abort != 0ull) ctl->done = 1;
+        if (!ctl->done) {
+            // the next attempt writes ring slot (cur + 1) % nbuf, which holds accepted state number accepted + 1 - nbuf
+            const long long need = ctl->accepted + 1 - (long long)ctl->nbuf;
+            const unsigned long long t0 = global_timer_ns();
+            while (need >= 0 && (long long)fd->consumed < need) {
+                if (fd->abort != 0ull || global_timer_ns() - t0 > (unsigned long long)(ctl->wait_timeout_ns > 0 ? 16 * ctl->wait_timeout_ns : 64000000000ll)) {
+                    ctl->done = 1;
+                    if (fd->abort == 0ull && ctl->failed == 0) ctl->failed = 2;
+                    break;
+                }
+                __nanosleep(500);
+            }
+        }
+    }
+    __threadfence();
+    st_release_gpu(&ctl->epoch, epoch_next);
+}
+
 // kComm = false: single-GPU instantiation without any of the peer-memory code paths (halo delivery, flag waits,
 // fused all-reduce); the register allocation of this kernel sits at the 128-register cap and is sensitive to them.
-// kCtl = true: the step to attempt and the in / out buffers are read from the device-resident controller block, and the
-// last CTA updates it (accept / reject, next dt) -- no host involvement between attempts.
+// kCtl = true: the step to attempt and the in / out buffers are read from the device-resident controller block, the
+// last CTA updates it (accept / reject, next dt), and the kernel goes on with the next attempt (up to max_attempts; launched
+// cooperatively so that all CTAs are resident) -- no host involvement between attempts.
 template <class IVP, typename T, int N, bool kComm, bool kCtl = false>
 __global__ void __launch_bounds__(kThreads, DekSmem<T, N>::MIN_BLOCKS) dek1_kernel(const __grid_constant__ DekArgs<T, N> a) {
     using Shape = typename IVP::Shape;
@@ -302,11 +343,15 @@ __global__ void __launch_bounds__(kThreads, DekSmem<T, N>::MIN_BLOCKS) dek1_kern
     constexpr int NN = L::NN, STRIDE = L::STRIDE;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);                       // [2][kWarps]
-    double* s_red = reinterpret_cast<double*>(smem_raw + L::BAR_BYTES);
+    double* s_red = reinterpret_cast<double*>(smem_raw + L::BAR_BYTES);          // [2][kWarps] per-tile warp sums; final reduction
     T* s_at0 = reinterpret_cast<T*>(smem_raw + L::BAR_BYTES + L::RED_BYTES);      // [2][AT_ELEMS]
     T* s_sc0 = reinterpret_cast<T*>(smem_raw + L::BAR_BYTES + L::RED_BYTES + 2 * L::at_bytes(ExtTile<IVP>::ELEMS));
     constexpr size_t AT_STRIDE = L::at_bytes(ExtTile<IVP>::ELEMS) / sizeof(T);
     constexpr size_t SC_STRIDE = L::sc_bytes() / sizeof(T);
+    __shared__ int s_flag, s_ok;
+    __shared__ Consts<T, N> s_c;                  // kCtl: the attempt's constants, rebuilt from the controller block
+    __shared__ int s_cur, s_out;
+    __shared__ unsigned long long s_epoch0;
 
     const Geo& g = a.g;
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -315,30 +360,8 @@ __global__ void __launch_bounds__(kThreads, DekSmem<T, N>::MIN_BLOCKS) dek1_kern
     const T* sc_in = a.sc_in;
     T* mean_out = a.mean_out;
     T* sc_out = a.sc_out;
-    if constexpr (kCtl) {
-        __shared__ Consts<T, N> s_c;
-        __shared__ int s_cur;
-        if (threadIdx.x == 0) {
-            const StepCtl* ctl = a.ctl;
-            Consts<T, N> cc = a.c;            // Ql, tolerances and flags come with the launch, the step with the controller
-#pragma unroll
-            for (int k = 0; k < N; ++k) {
-                cc.p[k] = (T)ctl->p[k];
-                cc.pinv[k] = (T)ctl->pinv[k];
-            }
-            cc.dt = (T)ctl->dt;
-            s_c = cc;
-            s_cur = ctl->done ? -1 : ctl->cur;
-        }
-        __syncthreads();
-        if (s_cur < 0) return;                // the solve is over: the remaining launches of the batch do nothing
-        cp = &s_c;
-        mean_in = a.mean_ab[s_cur];
-        sc_in = a.sc_ab[s_cur];
-        mean_out = a.mean_ab[s_cur ^ 1];
-        sc_out = a.sc_ab[s_cur ^ 1];
-    }
-    const Consts<T, N>& c = *cp;
+    T* err_out = a.err_out;
+    T* ref_out = a.ref_out;
 
     if (lane == 0) {
         mbar_init(bars + w, 1);
@@ -348,212 +371,299 @@ __global__ void __launch_bounds__(kThreads, DekSmem<T, N>::MIN_BLOCKS) dek1_kern
     }
     __syncwarp();
 
-    // issue the streaming load of one tile's 32 factor blocks of this warp into a slot; returns whether the
-    // bulk (TMA) path was used (warp-uniform), in which case the data lands on the slot's mbarrier
-    auto stage_in = [&](const Coord& co, int slot) -> bool {
-        T* dst = s_sc0 + slot * SC_STRIDE + w * 32 * STRIDE;
-        const long long off = co.seg_base * NN;
-        const bool bulk = (STRIDE == NN) && (co.seg_len == 32) && ((reinterpret_cast<uintptr_t>(sc_in + off) & 15) == 0);
-        if (bulk) {
-            if (lane == 0) {
-                uint64_t* bar = bars + slot * kWarps + w;
-                mbar_expect_tx(bar, (uint32_t)(32 * NN * sizeof(T)));
-                bulk_g2s(dst, sc_in + off, (uint32_t)(32 * NN * sizeof(T)), bar);
-            }
-        } else {
-            // padded layout: element-wise asynchronous copies (LDGSTS), one group per tile; they land while the current
-            // tile is being factorised
-            if (L::VEC && (reinterpret_cast<uintptr_t>(sc_in) & 15) == 0) {      // 16-byte units, L1 bypassed
-                const int total = co.seg_len * L::UNITS;
-                for (int u = lane; u < total; u += 32) {
-                    const int blk = u / L::UNITS;
-                    cp_async_unit(dst + blk * STRIDE + (u - blk * L::UNITS) * L::PER_UNIT, sc_in + off + (long long)u * L::PER_UNIT);
-                }
-            } else {
-                const int total = co.seg_len * NN;
-                for (int e = lane; e < total; e += 32) {
-                    const int blk = e / NN;
-                    cp_async_elem(dst + blk * STRIDE + (e - blk * NN), sc_in + off + e);
-                }
-            }
-            cp_async_commit();
-        }
-        return bulk;
-    };
-
-    // CTA b walks the virtual tiles (G-1-b), (G-1-b)+G, ...: the lowest block indices (scheduled first, always resident)
-    // have the shortest lists when tiles % G != 0, and they deliver this shard's halos before they start on them
-    if (kComm && a.pack.enabled)
-        for (int part = (int)blockIdx.x; part < 2 * kPackCtas; part += (int)gridDim.x)   // a small grid takes several parts per CTA
-            pack_halo_part<T, N>(g, c, mean_in, a.pack, part);
-    bool halos_ready = false;          // CTA-uniform: the arrival flags have been seen
-    unsigned tile = kComm ? (gridDim.x - 1u - blockIdx.x) : blockIdx.x;
     unsigned phase_bits = 0u;          // parity of each slot's mbarrier
-    double ratio_sq_acc = 0.0;
-    bool cur_bulk = false;
-    if (tile < a.num_tiles) cur_bulk = stage_in(tile_coord<Shape>(g, a.ranges.tile(tile), a.tiles_x), 0);
-
     constexpr int SC_SLOTS = DekSmem<T, N>::SC_SLOTS;
-    for (unsigned it = 0; tile < a.num_tiles; ++it) {
-        const int slot = (SC_SLOTS == 2) ? (int)(it & 1u) : 0;
-        T* my_sc = s_sc0 + slot * SC_STRIDE + w * 32 * STRIDE;
-        T* s_at = s_at0 + (it & 1u) * AT_STRIDE;
-        if (kComm && !halos_ready && tile >= a.ranges.wait_from) {
-            cta_wait_halos(a.wait);
-            halos_ready = true;
-        }
+    const int max_attempts = kCtl ? a.max_attempts : 1;
 
-        // (1) mean column, prediction and vector field of the current tile
-        const Coord cur = tile_coord<Shape>(g, a.ranges.tile(tile), a.tiles_x);
-        T mp[N], fx, jac, raw0;
-        {
-            FrontRegs<IVP, T, N> fr;
-            front_load<IVP, T, N>(g, c, mean_in, a.halo_lo, a.halo_hi, cur, fr);
-            front_eval<IVP, T, N>(g, c, cur, fr, s_at, mp, fx, jac);
-            raw0 = fr.raw[0];
-        }
-
-        // (2) start streaming the next tile's factor blocks into the other slot
-        const unsigned next = tile + gridDim.x;
-        bool next_bulk = false;
-        if (SC_SLOTS == 2 && next < a.num_tiles) {
-            if (lane == 0) bulk_wait_read0();      // the other slot's previous results have left shared memory
-            __syncwarp();
-            next_bulk = stage_in(tile_coord<Shape>(g, a.ranges.tile(next), a.tiles_x), slot ^ 1);
-        }
-
-        // (3) wait for the current tile's blocks
-        if (cur_bulk) {
-            mbar_wait(bars + slot * kWarps + w, (phase_bits >> slot) & 1u);
-            phase_bits ^= (1u << slot);
-        } else if (SC_SLOTS == 2 && next < a.num_tiles && !next_bulk) {
-            cp_async_wait_group<1>();  // everything but the next tile's group, which was committed just above
-        } else {
-            cp_async_wait_group<0>();
-        }
-        __syncwarp();
-
-        const long long sc_off = cur.seg_base * NN;
-        const bool bulk_out = (STRIDE == NN) && (cur.seg_len == 32) &&
-                              ((reinterpret_cast<uintptr_t>(sc_out + sc_off) & 15) == 0);
-        if (cur.valid) {
-            const T z = c.p[1] * mp[1] - fx;
-
-            // estimate_error / local diffusion  ek1.py:314-331.  Ql rows 0 and 1 have 1 and 2 nonzeros.
-            const T h0 = c.p[1] * QL(c, 1, 0) - jac * (c.p[0] * QL(c, 0, 0));
-            const T h1 = c.p[1] * QL(c, 1, 1);
-            const T s = h0 * h0 + h1 * h1;
-            const T sqs = tsqrt<T>(s);
-            const T sigma = tabs<T>(z / sqs);
-            const T err = sigma * sqs;
-
-            // B = A (p_inv * sc)   ek1.py:233,269
-            T B[N][N];
-            T* blk = my_sc + lane * STRIDE;
-            T blkv[L::VEC ? NN : 1];           // even n: the block travels through registers, 128 bits per access
-            if constexpr (L::VEC) block_load_vec<T, NN>(blk, blkv);
-#pragma unroll
-            for (int j = 0; j < N; ++j) {
-                T col[N];
-#pragma unroll
-                for (int k = 0; k < N; ++k) col[k] = c.pinv[k] * (L::VEC ? blkv[L::VEC ? k * N + j : 0] : blk[k * N + j]);
-#pragma unroll
-                for (int i = 0; i < N; ++i) {
-                    T acc = col[i];
-#pragma unroll
-                    for (int k = i + 1; k < N; ++k) acc = fma((T)A_entry<N>(i, k), col[k], acc);
-                    B[i][j] = acc;
+#pragma unroll 1
+    for (int att = 0; att < max_attempts; ++att) {
+        if constexpr (kCtl) {
+            if (threadIdx.x == 0) {
+                StepCtl* ctl = a.ctl;
+                bool ok = true;
+                if (att == 0) s_epoch0 = ld_acquire_gpu(&ctl->epoch);
+                else ok = spin_until_gpu(&ctl->epoch, s_epoch0 + (unsigned long long)att, (unsigned long long)ctl->wait_timeout_ns);
+                if (!ok) {                        // the grid barrier timed out (a CTA or a peer rank is gone): fail the solve
+                    ctl->failed = 2;
+                    ctl->done = 1;
                 }
-            }
-
-            // predict_cov_sqrtm: QR of [(A sc)^T ; (sigma Ql)^T]   ek1.py:267-270, sqrt.py:8-30
-            stacked_qr<T, N>(B, sigma, c);
-
-            // observe_cov_sqrtm  ek1.py:333-349 (L = lower(B); rows 0,1 have 1 and 2 nonzeros)
-            const T g0 = c.p[1] * B[1][0] - jac * (c.p[0] * B[0][0]);
-            const T g1 = c.p[1] * B[1][1];
-            const T s2 = (g0 * g0 + g1 * g1) + (T)1e-16;
-            const T inv_s2 = (T)1 / s2;
-
-            // correct_cov_sqrtm / correct_mean  ek1.py:351-369, un-precondition ek1.py:246-247
-            T new_m0 = (T)0;
-            T* mo_ptr = mean_out + cur.flat;
+                Consts<T, N> cc = a.c;            // Ql, tolerances and flags come with the launch, the step with the controller
 #pragma unroll
-            for (int r = 0; r < N; ++r) {
-                const T l0 = B[r][0];
-                const T l1 = (r >= 1) ? B[r][1] : (T)0;
-                const T kg = (l0 * g0 + l1 * g1) * inv_s2;
-                const T pr = c.p[r];
-                T* row = L::VEC ? (blkv + (L::VEC ? r * N : 0)) : (blk + r * N);
-                row[0] = pr * (l0 - kg * g0);
-                row[1] = pr * (l1 - kg * g1);
-#pragma unroll
-                for (int cc = 2; cc < N; ++cc) row[cc] = (r >= cc) ? pr * B[r][cc] : (T)0;
-                const T mo = pr * (mp[r] - kg * z);
-                *mo_ptr = mo;
-                mo_ptr += g.d;
-                if (r == 0) new_m0 = mo;
+                for (int k = 0; k < N; ++k) {
+                    cc.p[k] = (T)ctl->p[k];
+                    cc.pinv[k] = (T)ctl->pinv[k];
+                }
+                cc.dt = (T)ctl->dt;
+                s_c = cc;
+                const int cur = ctl->cur, nbuf = ctl->nbuf;
+                s_cur = (ctl->done || !ok) ? -1 : cur;
+                s_out = (cur + 1) % nbuf;
             }
-            if constexpr (L::VEC) block_store_vec<T, NN>(blk, blkv);
-            const T ref = nanmax<T>(tabs<T>(raw0), tabs<T>(new_m0));   // ek1.py:249-251
-            if (a.err_out) a.err_out[cur.flat] = err;
-            if (a.ref_out) a.ref_out[cur.flat] = ref;
-            if (c.want_norm) {
-                const double ratio = ((double)c.dt * (double)err) / ((double)c.abstol + (double)c.reltol * (double)ref);
-                ratio_sq_acc += ratio * ratio;                         // step.py:101-104
-            }
+            __syncthreads();
+            if (s_cur < 0) break;                 // the solve is over (or a barrier timed out): nothing left to do
+            if (att > 0) fence_proxy_async_global();   // TMA loads below read what other CTAs stored in the previous attempt
+            cp = &s_c;
+            mean_in = a.mean_ring[s_cur];
+            sc_in = a.sc_ring[s_cur];
+            mean_out = a.mean_ring[s_out];
+            sc_out = a.sc_ring[s_out];
+            err_out = a.err_ring[s_out];
+            ref_out = a.ref_ring[s_out];
         }
+        const Consts<T, N>& c = *cp;
+        const unsigned long long hseq = a.wait.seq + (unsigned long long)att;          // halo sequence number of this attempt
+        const T* halo_lo = a.halo_lo ? a.halo_lo + (long long)(hseq & 1ull) * a.halo_parity_stride : nullptr;
+        const T* halo_hi = a.halo_hi ? a.halo_hi + (long long)(hseq & 1ull) * a.halo_parity_stride : nullptr;
 
-        // (4) stream the updated blocks back
-        if (bulk_out) {
-            fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) {
-                bulk_s2g(sc_out + sc_off, my_sc, (uint32_t)(32 * NN * sizeof(T)));
-                bulk_commit();
-            }
-        } else {
-            __syncwarp();
-            if (L::VEC && (reinterpret_cast<uintptr_t>(sc_out) & 15) == 0) {
-                const int total = cur.seg_len * L::UNITS;
-                uint4* out_units = reinterpret_cast<uint4*>(sc_out + sc_off);
-                for (int u = lane; u < total; u += 32) {
-                    const int b = u / L::UNITS;
-                    out_units[u] = *reinterpret_cast<const uint4*>(my_sc + b * STRIDE + (u - b * L::UNITS) * L::PER_UNIT);
+        // issue the streaming load of one tile's 32 factor blocks of this warp into a slot; returns whether the
+        // bulk (TMA) path was used (warp-uniform), in which case the data lands on the slot's mbarrier
+        auto stage_in = [&](const Coord& co, int slot) -> bool {
+            T* dst = s_sc0 + slot * SC_STRIDE + w * 32 * STRIDE;
+            const long long off = co.seg_base * NN;
+            const bool bulk = (STRIDE == NN) && (co.seg_len == 32) && ((reinterpret_cast<uintptr_t>(sc_in + off) & 15) == 0);
+            if (bulk) {
+                if (lane == 0) {
+                    uint64_t* bar = bars + slot * kWarps + w;
+                    mbar_expect_tx(bar, (uint32_t)(32 * NN * sizeof(T)));
+                    bulk_g2s(dst, sc_in + off, (uint32_t)(32 * NN * sizeof(T)), bar);
                 }
             } else {
-                const int total = cur.seg_len * NN;
-                for (int e = lane; e < total; e += 32) {
-                    const int b = e / NN;
-                    sc_out[sc_off + e] = my_sc[b * STRIDE + (e - b * NN)];
+                // padded layout: element-wise asynchronous copies (LDGSTS), one group per tile; they land while the current
+                // tile is being factorised
+                if (L::VEC && (reinterpret_cast<uintptr_t>(sc_in) & 15) == 0) {      // 16-byte units, L1 bypassed
+                    const int total = co.seg_len * L::UNITS;
+                    for (int u = lane; u < total; u += 32) {
+                        const int blk = u / L::UNITS;
+                        cp_async_unit(dst + blk * STRIDE + (u - blk * L::UNITS) * L::PER_UNIT, sc_in + off + (long long)u * L::PER_UNIT);
+                    }
+                } else {
+                    const int total = co.seg_len * NN;
+                    for (int e = lane; e < total; e += 32) {
+                        const int blk = e / NN;
+                        cp_async_elem<kCtl>(dst + blk * STRIDE + (e - blk * NN), sc_in + off + e);
+                    }
+                }
+                cp_async_commit();
+            }
+            return bulk;
+        };
+
+        // CTA b walks the virtual tiles (G-1-b), (G-1-b)+G, ...: the lowest block indices (scheduled first, always resident)
+        // have the shortest lists when tiles % G != 0, and they deliver this shard's halos before they start on them
+        if (kComm && a.pack.enabled)
+            for (int part = (int)blockIdx.x; part < 2 * kPackCtas; part += (int)gridDim.x)   // a small grid takes several parts per CTA
+                pack_halo_part<T, N, FullSync, kCtl>(g, c, mean_in, a.pack, a.pack.seq + (unsigned long long)att, part);
+        bool halos_ready = false;          // CTA-uniform: the arrival flags have been seen
+        bool poisoned = false;             // CTA-uniform: a halo wait timed out
+        unsigned tile = kComm ? (gridDim.x - 1u - blockIdx.x) : blockIdx.x;
+        double cta_acc = 0.0;              // thread 0, per-CTA partial sums only (no unit partials)
+        int pending_unit = -1;             // thread 0: the tile whose warp sums wait in s_red for the next barrier
+        bool cur_bulk = false;
+        if (tile < a.num_tiles) cur_bulk = stage_in(tile_coord<Shape>(g, a.ranges.tile(tile), a.tiles_x), 0);
+
+        // thread 0, after a barrier that follows the tile's warp sums: the tile's partial = the 8 warp sums in warp order
+        auto flush_tile_partial = [&](unsigned it_prev) {
+            if (threadIdx.x == 0 && pending_unit >= 0) {
+                const double* ws = s_red + (it_prev & 1u) * kWarps;
+                double b = 0.0;
+#pragma unroll
+                for (int i = 0; i < kWarps; ++i) b += ws[i];
+                if (a.red.unit) a.red.unit[pending_unit] = b;
+                else cta_acc += b;
+                pending_unit = -1;
+            }
+        };
+
+        unsigned it = 0;
+        for (; tile < a.num_tiles; ++it) {
+            const int slot = (SC_SLOTS == 2) ? (int)(it & 1u) : 0;
+            T* my_sc = s_sc0 + slot * SC_STRIDE + w * 32 * STRIDE;
+            T* s_at = s_at0 + (it & 1u) * AT_STRIDE;
+            if (kComm && !halos_ready && tile >= a.ranges.wait_from) {
+                if (!cta_wait_halos(a.wait, hseq, &s_ok)) poisoned = true;
+                halos_ready = true;
+            }
+
+            // (1) mean column, prediction and vector field of the current tile
+            const unsigned tile_id = a.ranges.tile(tile);
+            const Coord cur = tile_coord<Shape>(g, tile_id, a.tiles_x);
+            T mp[N], fx, jac, raw0;
+            {
+                FrontRegs<IVP, T, N> fr;
+                front_load<IVP, T, N, true, kCtl>(g, c, mean_in, halo_lo, halo_hi, cur, fr);
+                front_eval<IVP, T, N>(g, c, cur, fr, s_at, mp, fx, jac);
+                raw0 = fr.raw[0];
+            }
+            flush_tile_partial(it - 1u);       // the barrier inside front_eval ordered the previous tile's warp sums
+
+            // (2) start streaming the next tile's factor blocks into the other slot
+            const unsigned next = tile + gridDim.x;
+            bool next_bulk = false;
+            if (SC_SLOTS == 2 && next < a.num_tiles) {
+                if (lane == 0) bulk_wait_read0();      // the other slot's previous results have left shared memory
+                __syncwarp();
+                next_bulk = stage_in(tile_coord<Shape>(g, a.ranges.tile(next), a.tiles_x), slot ^ 1);
+            }
+
+            // (3) wait for the current tile's blocks
+            if (cur_bulk) {
+                mbar_wait(bars + slot * kWarps + w, (phase_bits >> slot) & 1u);
+                phase_bits ^= (1u << slot);
+            } else if (SC_SLOTS == 2 && next < a.num_tiles && !next_bulk) {
+                cp_async_wait_group<1>();  // everything but the next tile's group, which was committed just above
+            } else {
+                cp_async_wait_group<0>();
+            }
+            __syncwarp();
+
+            const long long sc_off = cur.seg_base * NN;
+            const bool bulk_out = (STRIDE == NN) && (cur.seg_len == 32) &&
+                                  ((reinterpret_cast<uintptr_t>(sc_out + sc_off) & 15) == 0);
+            double ratio_sq = 0.0;
+            if (cur.valid) {
+                const T z = c.p[1] * mp[1] - fx;
+
+                // estimate_error / local diffusion  ek1.py:314-331.  Ql rows 0 and 1 have 1 and 2 nonzeros.
+                const T h0 = c.p[1] * QL(c, 1, 0) - jac * (c.p[0] * QL(c, 0, 0));
+                const T h1 = c.p[1] * QL(c, 1, 1);
+                const T s = h0 * h0 + h1 * h1;
+                const T sqs = tsqrt<T>(s);
+                const T sigma = tabs<T>(z / sqs);
+                const T err = sigma * sqs;
+
+                // B = A (p_inv * sc)   ek1.py:233,269
+                T B[N][N];
+                T* blk = my_sc + lane * STRIDE;
+                T blkv[L::VEC ? NN : 1];           // even n: the block travels through registers, 128 bits per access
+                if constexpr (L::VEC) block_load_vec<T, NN>(blk, blkv);
+#pragma unroll
+                for (int j = 0; j < N; ++j) {
+                    T col[N];
+#pragma unroll
+                    for (int k = 0; k < N; ++k) col[k] = c.pinv[k] * (L::VEC ? blkv[L::VEC ? k * N + j : 0] : blk[k * N + j]);
+#pragma unroll
+                    for (int i = 0; i < N; ++i) {
+                        T acc = col[i];
+#pragma unroll
+                        for (int k = i + 1; k < N; ++k) acc = fma((T)A_entry<N>(i, k), col[k], acc);
+                        B[i][j] = acc;
+                    }
+                }
+
+                // predict_cov_sqrtm: QR of [(A sc)^T ; (sigma Ql)^T]   ek1.py:267-270, sqrt.py:8-30
+                stacked_qr<T, N>(B, sigma, c);
+
+                // observe_cov_sqrtm  ek1.py:333-349 (L = lower(B); rows 0,1 have 1 and 2 nonzeros)
+                const T g0 = c.p[1] * B[1][0] - jac * (c.p[0] * B[0][0]);
+                const T g1 = c.p[1] * B[1][1];
+                const T s2 = (g0 * g0 + g1 * g1) + (T)1e-16;
+                const T inv_s2 = (T)1 / s2;
+
+                // correct_cov_sqrtm / correct_mean  ek1.py:351-369, un-precondition ek1.py:246-247
+                T new_m0 = (T)0;
+                T* mo_ptr = mean_out + cur.flat;
+#pragma unroll
+                for (int r = 0; r < N; ++r) {
+                    const T l0 = B[r][0];
+                    const T l1 = (r >= 1) ? B[r][1] : (T)0;
+                    const T kg = (l0 * g0 + l1 * g1) * inv_s2;
+                    const T pr = c.p[r];
+                    T* row = L::VEC ? (blkv + (L::VEC ? r * N : 0)) : (blk + r * N);
+                    row[0] = pr * (l0 - kg * g0);
+                    row[1] = pr * (l1 - kg * g1);
+#pragma unroll
+                    for (int cc = 2; cc < N; ++cc) row[cc] = (r >= cc) ? pr * B[r][cc] : (T)0;
+                    const T mo = pr * (mp[r] - kg * z);
+                    *mo_ptr = mo;
+                    mo_ptr += g.d;
+                    if (r == 0) new_m0 = mo;
+                }
+                if constexpr (L::VEC) block_store_vec<T, NN>(blk, blkv);
+                const T ref = nanmax<T>(tabs<T>(raw0), tabs<T>(new_m0));   // ek1.py:249-251
+                if (err_out) err_out[cur.flat] = err;
+                if (ref_out) ref_out[cur.flat] = ref;
+                if (c.want_norm) {
+                    const double ratio = ((double)c.dt * (double)err) / ((double)c.abstol + (double)c.reltol * (double)ref);
+                    ratio_sq = ratio * ratio;                              // step.py:101-104
                 }
             }
+            if (c.want_norm || kCtl) {
+                // the tile's share of the norm: lanes through the shuffle tree, the warps through shared memory (next barrier)
+                const double ws = warp_sum(ratio_sq);
+                if (lane == 0) s_red[(it & 1u) * kWarps + w] = ws;
+                if (threadIdx.x == 0) pending_unit = (int)tile_id;
+            }
+
+            // (4) stream the updated blocks back
+            if (bulk_out) {
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) {
+                    bulk_s2g(sc_out + sc_off, my_sc, (uint32_t)(32 * NN * sizeof(T)));
+                    bulk_commit();
+                }
+            } else {
+                __syncwarp();
+                if (L::VEC && (reinterpret_cast<uintptr_t>(sc_out) & 15) == 0) {
+                    const int total = cur.seg_len * L::UNITS;
+                    uint4* out_units = reinterpret_cast<uint4*>(sc_out + sc_off);
+                    for (int u = lane; u < total; u += 32) {
+                        const int b = u / L::UNITS;
+                        out_units[u] = *reinterpret_cast<const uint4*>(my_sc + b * STRIDE + (u - b * L::UNITS) * L::PER_UNIT);
+                    }
+                } else {
+                    const int total = cur.seg_len * NN;
+                    for (int e = lane; e < total; e += 32) {
+                        const int b = e / NN;
+                        sc_out[sc_off + e] = my_sc[b * STRIDE + (e - b * NN)];
+                    }
+                }
+            }
+            if (SC_SLOTS == 1 && next < a.num_tiles) {
+                // single slot: refill it as soon as this tile's results have left (the other resident CTA covers the gap)
+                if (lane == 0) bulk_wait_read0();
+                __syncwarp();
+                next_bulk = stage_in(tile_coord<Shape>(g, a.ranges.tile(next), a.tiles_x), 0);
+            }
+            tile = next;
+            cur_bulk = next_bulk;
         }
-        if (SC_SLOTS == 1 && next < a.num_tiles) {
-            // single slot: refill it as soon as this tile's results have left (the other resident CTA covers the gap)
-            if (lane == 0) bulk_wait_read0();
-            __syncwarp();
-            next_bulk = stage_in(tile_coord<Shape>(g, a.ranges.tile(next), a.tiles_x), 0);
-        }
-        tile = next;
-        cur_bulk = next_bulk;
-    }
 
 #ifdef TDX_DEK1_TIMING
-    if (threadIdx.x == 0) {      // development aid: when did this CTA run out of tiles? (scripts/dek1_timeline.py)
-        a.partials[1024 + 2 * blockIdx.x] = (double)global_timer_ns();
-        unsigned smid;
-        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-        a.partials[1024 + 2 * blockIdx.x + 1] = (double)smid;
-    }
+        if (threadIdx.x == 0) {      // development aid: when did this CTA run out of tiles? (scripts/dek1_timeline.py)
+            a.partials[1024 + 2 * blockIdx.x] = (double)global_timer_ns();
+            unsigned smid;
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            a.partials[1024 + 2 * blockIdx.x + 1] = (double)smid;
+        }
 #endif
-    if constexpr (kCtl) {
+        if (!(c.want_norm || kCtl)) break;            // ConstantSteps without a controller: nothing to reduce
+
+        // ---- end of the attempt: everything this CTA wrote must be visible before it reports in ------------------------
+        if constexpr (kCtl) {
+            if (lane == 0) bulk_wait0();              // the factor blocks have LANDED in global memory (not just left shared memory)
+            fence_proxy_async_global();               // ... and ordinary stores are ordered before the next attempt's TMA loads
+        }
+        __syncthreads();
+        flush_tile_partial(it - 1u);
+        if (threadIdx.x == 0 && poisoned) {           // stale halos: the attempt must not be accepted anywhere
+            if (a.red.unit) a.red.unit[a.ranges.tile(kComm ? (gridDim.x - 1u - blockIdx.x) : blockIdx.x)] = nan("");
+            else cta_acc = nan("");
+        }
         double total = 0.0;
-        const bool fin = grid_sum(ratio_sq_acc, s_red, a.partials, a.ticket, c.want_norm ? a.out_sum : nullptr, 1.0, nullptr,
-                                  (kComm && c.want_norm) ? &a.reduce : nullptr, &total);
-        if (fin) ctl_update(a.ctl, total, a.d_global);
-    } else {
-        if (c.want_norm) grid_sum(ratio_sq_acc, s_red, a.partials, a.ticket, a.out_sum, 1.0, nullptr, kComm ? &a.reduce : nullptr);
+        bool fin = false;                             // thread 0 of the last CTA
+        if (a.red.unit != nullptr) {
+            if (cta_arrive_last(a.ticket, &s_flag)) {
+                total = reduce_units(a.red, kComm ? &a.reduce : nullptr, a.reduce.seq + (unsigned long long)att, s_red);
+                fin = threadIdx.x == 0;
+                if (fin && c.want_norm && a.out_sum) *a.out_sum = total;
+            }
+        } else {
+            fin = grid_sum_cta(cta_acc, s_red, a.partials, a.ticket, c.want_norm ? a.out_sum : nullptr);
+        }
+        if constexpr (kCtl) {
+            if (fin) ctl_finish_attempt(a.ctl, total, a.d_global, s_epoch0 + (unsigned long long)att + 1ull);
+        }
     }
     if (lane == 0) bulk_wait_read0();
 }
@@ -577,10 +687,12 @@ struct Ek0Args {
     T* ref_out;
     const T* halo_lo;
     const T* halo_hi;
+    long long halo_parity_stride;
     const Ek0Mid<T, N>* mid;
     double* partials;
     unsigned int* ticket;
     double* out_sum;
+    RedPlan red;
     unsigned int num_tiles, tiles_x;
     TileRanges ranges;
     CommWait wait;
@@ -600,8 +712,13 @@ __global__ void __launch_bounds__(kThreads, 3) ek0_sweep_kernel(const __grid_con
     double* s_red = reinterpret_cast<double*>(smem_raw + L::BAR_BYTES);
     T* s_at0 = reinterpret_cast<T*>(smem_raw + L::BAR_BYTES + L::RED_BYTES);
     constexpr size_t AT_STRIDE = L::at_bytes(ExtTile<IVP>::ELEMS) / sizeof(T);
+    __shared__ int s_flag, s_ok;
     const Geo& g = a.g;
     const Consts<T, N>& c = a.c;
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const unsigned long long hseq = a.wait.seq;
+    const T* halo_lo = a.halo_lo ? a.halo_lo + (long long)(hseq & 1ull) * a.halo_parity_stride : nullptr;
+    const T* halo_hi = a.halo_hi ? a.halo_hi + (long long)(hseq & 1ull) * a.halo_parity_stride : nullptr;
 
     T K[N];
     if (kUpdate) {
@@ -612,40 +729,61 @@ __global__ void __launch_bounds__(kThreads, 3) ek0_sweep_kernel(const __grid_con
 
     // virtual index of the i-th tile this launch walks (reversed for sweep B) and whether it reads halos
     auto vidx = [&](unsigned i) { return a.reverse ? (a.num_tiles - 1u - i) : i; };
-    bool halos_ready = false;
+    bool halos_ready = false, poisoned = false;
     auto wait_if_needed = [&](unsigned i) {
         if (!halos_ready && vidx(i) >= a.ranges.wait_from) {
-            cta_wait_halos(a.wait);
+            if (!cta_wait_halos(a.wait, hseq, &s_ok)) poisoned = true;
             halos_ready = true;
         }
     };
 
     if (a.pack.enabled)
         for (int part = (int)blockIdx.x; part < 2 * kPackCtas; part += (int)gridDim.x)
-            pack_halo_part<T, N>(g, c, a.mean_in, a.pack, part);
+            pack_halo_part<T, N>(g, c, a.mean_in, a.pack, a.pack.seq, part);
     unsigned i = gridDim.x - 1u - blockIdx.x;
-    double acc = 0.0;
+    const unsigned first_tile = i < a.num_tiles ? tile_of(i) : 0u;
+    double cta_acc = 0.0;
+    int pending_unit = -1;
+    const bool reduces = !kUpdate || c.want_norm;
     Coord co{};
+    unsigned co_tile = 0u;
     FrontRegs<IVP, T, N> fr;
     if (i < a.num_tiles) {
         wait_if_needed(i);
-        co = tile_coord<Shape>(g, tile_of(i), a.tiles_x);
-        front_load<IVP, T, N>(g, c, a.mean_in, a.halo_lo, a.halo_hi, co, fr);
+        co_tile = tile_of(i);
+        co = tile_coord<Shape>(g, co_tile, a.tiles_x);
+        front_load<IVP, T, N>(g, c, a.mean_in, halo_lo, halo_hi, co, fr);
     }
-    for (unsigned it = 0; i < a.num_tiles; ++it) {
+    auto flush_tile_partial = [&](unsigned it_prev) {
+        if (threadIdx.x == 0 && pending_unit >= 0) {
+            const double* ws = s_red + (it_prev & 1u) * kWarps;
+            double b = 0.0;
+#pragma unroll
+            for (int k = 0; k < kWarps; ++k) b += ws[k];
+            if (a.red.unit) a.red.unit[pending_unit] = b;
+            else cta_acc += b;
+            pending_unit = -1;
+        }
+    };
+    unsigned it = 0;
+    for (; i < a.num_tiles; ++it) {
         T mp[N], fx, jac;
         front_eval<IVP, T, N>(g, c, co, fr, s_at0 + (it & 1) * AT_STRIDE, mp, fx, jac);
+        flush_tile_partial(it - 1u);
         const Coord cur = co;
+        const unsigned cur_tile = co_tile;
         i += gridDim.x;
         if (i < a.num_tiles) {
             wait_if_needed(i);
-            co = tile_coord<Shape>(g, tile_of(i), a.tiles_x);
-            front_load<IVP, T, N>(g, c, a.mean_in, a.halo_lo, a.halo_hi, co, fr);
+            co_tile = tile_of(i);
+            co = tile_coord<Shape>(g, co_tile, a.tiles_x);
+            front_load<IVP, T, N>(g, c, a.mean_in, halo_lo, halo_hi, co, fr);
         }
+        double term = 0.0;
         if (cur.valid) {
             const T z = c.p[1] * mp[1] - fx;
             if (!kUpdate) {
-                acc += (double)z * (double)z;
+                term = (double)z * (double)z;
             } else {
                 T m0 = (T)0;
                 T* mo_ptr = a.mean_out + cur.flat;
@@ -660,16 +798,45 @@ __global__ void __launch_bounds__(kThreads, 3) ek0_sweep_kernel(const __grid_con
                 if (a.ref_out) a.ref_out[cur.flat] = ref;
                 if (c.want_norm) {
                     const double tol = (double)c.abstol + (double)c.reltol * (double)ref;
-                    acc += 1.0 / (tol * tol);
+                    term = 1.0 / (tol * tol);
                 }
             }
         }
+        if (reduces) {
+            const double ws = warp_sum(term);
+            if (lane == 0) s_red[(it & 1u) * kWarps + w] = ws;
+            if (threadIdx.x == 0) pending_unit = (int)cur_tile;
+        }
     }
-    if (!kUpdate) {
-        grid_sum(acc, s_red, a.partials, a.ticket, a.out_sum, 1.0, nullptr, &a.reduce);
-    } else if (c.want_norm) {
-        // sum_i (dt err / tol_i)^2 = (dt err)^2 sum_i 1 / tol_i^2     step.py:101-104 with a scalar error estimate
-        grid_sum(acc, s_red, a.partials, a.ticket, a.out_sum, (double)c.dt * (double)c.dt, &a.mid->err, &a.reduce);
+    if (!reduces) return;
+    __syncthreads();
+    flush_tile_partial(it - 1u);
+    if (threadIdx.x == 0 && poisoned) {
+        if (a.red.unit) a.red.unit[first_tile] = nan("");
+        else cta_acc = nan("");
+    }
+    // sweep B:  sum_i (dt err / tol_i)^2 = (dt err)^2 sum_i 1 / tol_i^2     step.py:101-104 with a scalar error estimate
+    const double scale = kUpdate ? ((double)c.dt * (double)c.dt) : 1.0;
+    if (a.red.unit != nullptr) {
+        if (cta_arrive_last(a.ticket, &s_flag)) {
+            double total = reduce_units(a.red, &a.reduce, a.reduce.seq, s_red);
+            if (threadIdx.x == 0) {
+                if (kUpdate) {
+                    const double r = a.mid->err;
+                    total *= r * r;
+                    total *= scale;
+                }
+                *a.out_sum = total;
+            }
+        }
+    } else {
+        // a launch over a part of the tiles (interior / rim): per-CTA partials; the caller adds the launches' sums
+        if (kUpdate && threadIdx.x == 0) {
+            const double r = a.mid->err;
+            cta_acc *= r * r;
+            cta_acc *= scale;
+        }
+        grid_sum_cta(cta_acc, s_red, a.partials, a.ticket, a.out_sum);
     }
 }
 

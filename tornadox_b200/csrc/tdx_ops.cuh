@@ -29,7 +29,31 @@ struct Workspace {
     CommWait wait;           // peer-memory halos: flags the kernel must see before it reads them (null otherwise)
     CommReduce reduce;       // fused all-reduce of the scalar result (world == 0: off)
     PackPeer<double> pack;   // fused halo delivery (pointers are dtype-agnostic; enabled == 0: off)
+    long long halo_parity_stride_bytes;   // between the parity-0 and parity-1 halo buffers of the context (0: the caller's halos)
+    double* unit_a;          // unit partials of the launch's (first) reduction, >= unit_cap doubles
+    double* unit_b;          // ... of the second one (fused KroneckerEK0: phase B)
+    long long unit_cap;
+    unsigned long long* cl_flag;   // fused KroneckerEK0: "the attempt's new factor has been written"
+    unsigned long long cl_seq;
 };
+
+// unit partials of a tile-based launch (one unit per tile, numbered row-major over the global tile grid)
+template <class Shape>
+inline RedPlan tile_red_plan(const Geo& g, double* unit, unsigned tiles_x, unsigned tiles_y) {
+    RedPlan rp{};
+    rp.unit = unit;
+    rp.units_local = tiles_x * tiles_y;
+    if (g.kind == IVP_FHN2D) {
+        rp.unit0 = (unsigned long long)(g.grow0 / Shape::TR) * tiles_x;
+        rp.units_global = (unsigned long long)((g.grows + Shape::TR - 1) / Shape::TR) * tiles_x;
+    } else {
+        rp.unit0 = (unsigned long long)(g.gcol0 / Shape::TC);
+        rp.units_global = (unsigned long long)((g.gcols + Shape::TC - 1) / Shape::TC);
+    }
+    // a shard that does not start on a tile boundary of the global tiling: still a valid (rank-dependent) order
+    if (rp.unit0 + rp.units_local > rp.units_global) rp.units_global = rp.unit0 + rp.units_local;
+    return rp;
+}
 
 // Which tiles does a launch process?  all / interior (no halo reads) / rim (TDX_STEP_TILES_*).
 // Rim = the first / last tile row (2-d grids) or the first / last tile (chains) on sides that have a neighbour.
@@ -60,14 +84,15 @@ struct Ops {
                    void* err_out, const Workspace&, cudaStream_t);
     int (*ek0_b)(const Geo&, const StepHost&, const void* mean_in, void* mean_out, void* ref_out, const void* halo_lo,
                  const void* halo_hi, const Workspace&, double* out_sum, cudaStream_t);
-    // the same attempts driven by the device-resident step controller: in/out = pair[ctl->cur] / pair[ctl->cur ^ 1]
-    int (*dek1_ctl)(const Geo&, const StepHost&, void* const mean_ab[2], void* const sc_ab[2], void* err_out, void* ref_out,
-                    const void* halo_lo, const void* halo_hi, const Workspace&, StepCtl* ctl, double d_global,
-                    double* out_sum, cudaStream_t);
-    int (*ek0_ctl)(const Geo&, const StepHost&, void* const mean_ab[2], void* const Cl_ab[2], void* err_out, void* ref_out,
-                   const void* halo_lo, const void* halo_hi, const Workspace&, const CommReduce& reduce_b,
-                   unsigned long long* mid_flag, unsigned long long mid_seq, StepCtl* ctl, double d_global, double* z_sq_out,
-                   double* out_sum, cudaStream_t);
+    // the same attempts driven by the device-resident step controller, up to ``max_attempts`` of them in ONE cooperative
+    // launch: in / out = ring[ctl->cur] / ring[(ctl->cur + 1) % nbuf]
+    int (*dek1_ctl)(const Geo&, const StepHost&, void* const* mean_ring, void* const* sc_ring, int nbuf, int max_attempts,
+                    void* const* err_ring, void* const* ref_ring, const void* halo_lo, const void* halo_hi, const Workspace&, StepCtl* ctl,
+                    double d_global, double* out_sum, cudaStream_t);
+    int (*ek0_ctl)(const Geo&, const StepHost&, void* const* mean_ring, void* const* Cl_ring, int nbuf, int max_attempts,
+                   void* const* err_ring, void* const* ref_ring, const void* halo_lo, const void* halo_hi, const Workspace&,
+                   const CommReduce& reduce_b, unsigned long long* mid_flag, unsigned long long mid_seq, StepCtl* ctl,
+                   double d_global, double* z_sq_out, double* out_sum, cudaStream_t);
     // whole KroneckerEK0 attempt in one cooperative launch (fhn_2d only; returns kNoFusedKernel otherwise)
     int (*ek0_fused)(const Geo&, const StepHost&, const void* mean_in, const void* Cl_in, void* mean_out, void* Cl_out,
                      void* err_out, void* ref_out, const void* halo_lo, const void* halo_hi, const Workspace&,
@@ -133,6 +158,10 @@ inline cudaError_t persistent_grid(size_t smem, long long tiles, int reserve, un
         if (dev >= 0 && dev < kMaxDevices) resident_cache[dev] = resident;
     }
     if (reserve > 0 && resident - reserve >= 1) resident -= reserve;
+    if (const char* cap = std::getenv("TDX_MAX_CTAS")) {     // tests: the sums must not depend on the number of CTAs
+        const int m = std::atoi(cap);
+        if (m >= 1 && m < resident) resident = m;
+    }
     grid = (unsigned)(tiles < resident ? tiles : resident);
     return cudaSuccess;
 }
@@ -160,30 +189,34 @@ template <typename T, int N>
 struct Launch {
     using L = SmemLayout<T, N>;
 
-    static int dek1_ctl(const Geo& g, const StepHost& h, void* const mean_ab[2], void* const sc_ab[2], void* err_out,
-                        void* ref_out, const void* halo_lo, const void* halo_hi, const Workspace& ws, StepCtl* ctl,
-                        double d_global, double* out_sum, cudaStream_t st) {
-        return dek1_impl(g, h, nullptr, nullptr, nullptr, nullptr, err_out, ref_out, halo_lo, halo_hi, ws, out_sum, st, ctl,
-                         mean_ab, sc_ab, d_global);
+    static int dek1_ctl(const Geo& g, const StepHost& h, void* const* mean_ring, void* const* sc_ring, int nbuf, int max_attempts,
+                        void* const* err_ring, void* const* ref_ring, const void* halo_lo, const void* halo_hi, const Workspace& ws,
+                        StepCtl* ctl, double d_global, double* out_sum, cudaStream_t st) {
+        return dek1_impl(g, h, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, halo_lo, halo_hi, ws, out_sum, st, ctl,
+                         mean_ring, sc_ring, err_ring, ref_ring, nbuf, max_attempts, d_global);
     }
 
     static int dek1(const Geo& g, const StepHost& h, const void* mean_in, const void* sc_in, void* mean_out,
                     void* sc_out, void* err_out, void* ref_out, const void* halo_lo, const void* halo_hi,
                     const Workspace& ws, double* out_sum, cudaStream_t st) {
         return dek1_impl(g, h, mean_in, sc_in, mean_out, sc_out, err_out, ref_out, halo_lo, halo_hi, ws, out_sum, st, nullptr,
-                         nullptr, nullptr, 0.0);
+                         nullptr, nullptr, nullptr, nullptr, 0, 1, 0.0);
     }
 
     static int dek1_impl(const Geo& g, const StepHost& h, const void* mean_in, const void* sc_in, void* mean_out,
                          void* sc_out, void* err_out, void* ref_out, const void* halo_lo, const void* halo_hi,
-                         const Workspace& ws, double* out_sum, cudaStream_t st, StepCtl* ctl, void* const mean_ab[2],
-                         void* const sc_ab[2], double d_global) {
+                         const Workspace& ws, double* out_sum, cudaStream_t st, StepCtl* ctl, void* const* mean_ring,
+                         void* const* sc_ring, void* const* err_ring, void* const* ref_ring, int nbuf, int max_attempts,
+                         double d_global) {
         DekArgs<T, N> a;
         a.ctl = ctl;
         a.d_global = d_global;
-        for (int i = 0; i < 2; ++i) {
-            a.mean_ab[i] = ctl ? (T*)mean_ab[i] : nullptr;
-            a.sc_ab[i] = ctl ? (T*)sc_ab[i] : nullptr;
+        a.max_attempts = max_attempts;
+        for (int i = 0; i < kMaxRing; ++i) {
+            a.mean_ring[i] = (ctl && i < nbuf) ? (T*)mean_ring[i] : nullptr;
+            a.sc_ring[i] = (ctl && i < nbuf) ? (T*)sc_ring[i] : nullptr;
+            a.err_ring[i] = (ctl && i < nbuf && err_ring) ? (T*)err_ring[i] : nullptr;
+            a.ref_ring[i] = (ctl && i < nbuf && ref_ring) ? (T*)ref_ring[i] : nullptr;
         }
         a.g = g;
         a.c = make_consts<T, N>(h);
@@ -195,6 +228,7 @@ struct Launch {
         a.ref_out = (T*)ref_out;
         a.halo_lo = (const T*)halo_lo;
         a.halo_hi = (const T*)halo_hi;
+        a.halo_parity_stride = ws.halo_parity_stride_bytes / (long long)sizeof(T);
         a.partials = ws.partials;
         a.ticket = ws.ticket;
         a.out_sum = out_sum;
@@ -209,6 +243,10 @@ struct Launch {
             a.num_tiles = a.ranges.n0 + a.ranges.n1 + a.ranges.n2;
             a.wait = ws.wait;
             a.reduce = ws.reduce;
+            // a launch over all tiles leaves one partial per tile (sharding-independent summation); a launch over a part of
+            // them (interior / rim) falls back to per-CTA partials
+            const bool whole = a.num_tiles == a.tiles_x * tiles_y && (long long)a.num_tiles <= ws.unit_cap;
+            a.red = whole ? tile_red_plan<Shape>(g, ws.unit_a, a.tiles_x, tiles_y) : RedPlan{};
             if (a.num_tiles == 0u) {
                 if (h.want_norm) TDX_CUDA_TRY(cudaMemsetAsync(out_sum, 0, sizeof(double), st));
                 return 0;
@@ -216,9 +254,12 @@ struct Launch {
             a.pack = typed_pack(ws.pack);
             unsigned grid = 0;
             if (ctl) {
+                if (!whole) return (int)cudaErrorInvalidValue;
                 constexpr auto kern = dek1_kernel<IVP, T, N, true, true>;
                 TDX_CUDA_TRY(persistent_grid<kern>(smem, a.num_tiles, ws.reserve_ctas, grid));
-                kern<<<grid, kThreads, smem, st>>>(a);
+                // all CTAs wait for one another between the attempts: a cooperative launch guarantees that they are resident
+                void* params[] = {(void*)&a};
+                TDX_CUDA_TRY(cudaLaunchCooperativeKernel((const void*)kern, dim3(grid), dim3(kThreads), params, smem, st));
             } else if (comm) {
                 constexpr auto kern = dek1_kernel<IVP, T, N, true>;
                 TDX_CUDA_TRY(persistent_grid<kern>(smem, a.num_tiles, ws.reserve_ctas, grid));
@@ -242,6 +283,7 @@ struct Launch {
         a.ref_out = (T*)ref_out;
         a.halo_lo = (const T*)halo_lo;
         a.halo_hi = (const T*)halo_hi;
+        a.halo_parity_stride = ws.halo_parity_stride_bytes / (long long)sizeof(T);
         a.mid = (const Ek0Mid<T, N>*)ws.mid;
         a.partials = ws.partials;
         a.ticket = ws.ticket;
@@ -263,6 +305,8 @@ struct Launch {
             a.wait = ws.wait;
             a.reduce = ws.reduce;
             a.reverse = kUpdate ? 1 : 0;
+            const bool whole = a.num_tiles == a.tiles_x * tiles_y && (long long)a.num_tiles <= ws.unit_cap;
+            a.red = whole ? tile_red_plan<Shape>(g, kUpdate ? ws.unit_b : ws.unit_a, a.tiles_x, tiles_y) : RedPlan{};
             if (a.num_tiles == 0u) {
                 if (a.out_sum && (!kUpdate || a.c.want_norm)) TDX_CUDA_TRY(cudaMemsetAsync(a.out_sum, 0, sizeof(double), st));
                 return 0;
@@ -276,12 +320,12 @@ struct Launch {
         return (int)cudaGetLastError();
     }
 
-    static int ek0_ctl(const Geo& g, const StepHost& h, void* const mean_ab[2], void* const Cl_ab[2], void* err_out,
-                       void* ref_out, const void* halo_lo, const void* halo_hi, const Workspace& ws,
+    static int ek0_ctl(const Geo& g, const StepHost& h, void* const* mean_ring, void* const* Cl_ring, int nbuf, int max_attempts,
+                       void* const* err_ring, void* const* ref_ring, const void* halo_lo, const void* halo_hi, const Workspace& ws,
                        const CommReduce& reduce_b, unsigned long long* mid_flag, unsigned long long mid_seq, StepCtl* ctl,
                        double d_global, double* z_sq_out, double* out_sum, cudaStream_t st) {
-        return ek0_fused_impl<true>(g, h, mean_ab[0], nullptr, nullptr, nullptr, err_out, ref_out, halo_lo, halo_hi, ws, reduce_b,
-                                    mid_flag, mid_seq, d_global, z_sq_out, out_sum, st, ctl, mean_ab, Cl_ab);
+        return ek0_fused_impl<true>(g, h, mean_ring, Cl_ring, nbuf, max_attempts, err_ring, ref_ring, halo_lo, halo_hi, ws, reduce_b,
+                                    mid_flag, mid_seq, d_global, z_sq_out, out_sum, st, ctl);
     }
 
     static int ek0_fused(const Geo& g, const StepHost& h, const void* mean_in, const void* Cl_in, void* mean_out,
@@ -289,95 +333,64 @@ struct Launch {
                          const Workspace& ws, const CommReduce& reduce_b, unsigned long long* mid_flag,
                          unsigned long long mid_seq, double d_global, double* z_sq_out, double* out_sum,
                          cudaStream_t st) {
-        return ek0_fused_impl<false>(g, h, mean_in, Cl_in, mean_out, Cl_out, err_out, ref_out, halo_lo, halo_hi, ws, reduce_b,
-                                     mid_flag, mid_seq, d_global, z_sq_out, out_sum, st, nullptr, nullptr, nullptr);
+        void* mean_ring[2] = {const_cast<void*>(mean_in), mean_out};
+        void* Cl_ring[2] = {const_cast<void*>(Cl_in), Cl_out};
+        void* err_ring[2] = {nullptr, err_out};
+        void* ref_ring[2] = {nullptr, ref_out};
+        return ek0_fused_impl<false>(g, h, mean_ring, Cl_ring, 2, 1, err_ring, ref_ring, halo_lo, halo_hi, ws, reduce_b,
+                                     mid_flag, mid_seq, d_global, z_sq_out, out_sum, st, nullptr);
     }
 
     template <class IVP, bool kCtl>
-    static int launch_chain(const Geo& g, Ek0FusedArgs<T, N>& a, cudaStream_t st) {
+    static int launch_chain(const Geo& g, Ek0FusedArgs<T, N>& a, const Workspace& ws, cudaStream_t st) {
         using Shape = typename IVP::Shape;
         using CCfg = Ek0ChainCfg<T, N>;
         constexpr auto kern = ek0_fused_chain_kernel<IVP, T, N, kCtl>;
         const size_t smem = CCfg::total(ExtTile<IVP>::ELEMS);
         a.col_blocks = (unsigned)((g.cols + Shape::TC - 1) / Shape::TC);                       // tiles per tile row
-        a.total_strips = a.col_blocks * (unsigned)((g.rows + Shape::TR - 1) / Shape::TR);     // tiles
+        const unsigned tiles_y = (unsigned)((g.rows + Shape::TR - 1) / Shape::TR);
+        a.total_strips = a.col_blocks * tiles_y;                                               // tiles
+        if ((long long)a.total_strips > ws.unit_cap) return (int)cudaErrorInvalidValue;
+        a.red_a = tile_red_plan<Shape>(g, ws.unit_a, a.col_blocks, tiles_y);
+        a.red_b = tile_red_plan<Shape>(g, ws.unit_b, a.col_blocks, tiles_y);
         unsigned grid = 0;
-        TDX_CUDA_TRY(persistent_grid<kern>(smem, (long long)a.total_strips, 0, grid, kThreads + 32));
+        TDX_CUDA_TRY(persistent_grid<kern>(smem, (long long)a.total_strips, 0, grid, CCfg::THREADS));
         void* params[] = {(void*)&a};
-        TDX_CUDA_TRY(cudaLaunchCooperativeKernel((const void*)kern, dim3(grid), dim3(kThreads + 32), params, smem, st));
+        TDX_CUDA_TRY(cudaLaunchCooperativeKernel((const void*)kern, dim3(grid), dim3(CCfg::THREADS), params, smem, st));
         return (int)cudaGetLastError();
     }
 
     template <bool kCtl>
-    static int ek0_fused_impl(const Geo& g, const StepHost& h, const void* mean_in, const void* Cl_in, void* mean_out,
-                              void* Cl_out, void* err_out, void* ref_out, const void* halo_lo, const void* halo_hi,
+    static int ek0_fused_impl(const Geo& g, const StepHost& h, void* const* mean_ring, void* const* Cl_ring, int nbuf,
+                              int max_attempts, void* const* err_ring, void* const* ref_ring, const void* halo_lo, const void* halo_hi,
                               const Workspace& ws, const CommReduce& reduce_b, unsigned long long* mid_flag,
                               unsigned long long mid_seq, double d_global, double* z_sq_out, double* out_sum,
-                              cudaStream_t st, StepCtl* ctl, void* const mean_ab[2], void* const Cl_ab[2]) {
+                              cudaStream_t st, StepCtl* ctl) {
         constexpr int W = TDX_EK0_W;
         using Cfg = Ek0FusedCfg<T, N, W>;
         constexpr auto kern = ek0_fused_fhn_kernel<T, N, W, kCtl>;
         Ek0FusedArgs<T, N> a;
         a.ctl = ctl;
-        for (int i = 0; i < 2; ++i) {
-            a.mean_ab[i] = ctl ? (T*)mean_ab[i] : nullptr;
-            a.Cl_ab[i] = ctl ? (T*)Cl_ab[i] : nullptr;
-        }
-        if (g.kind != IVP_FHN2D) {
-            // 1-d vector fields: the tile-based one-launch kernel
-            a.g = g;
-            a.c = make_consts<T, N>(h);
-            a.cd = make_consts<double, N>(h);
-            a.mean_in = (const T*)mean_in;
-            a.mean_out = (T*)mean_out;
-            a.ref_out = (T*)ref_out;
-            a.halo_lo = (const T*)halo_lo;
-            a.halo_hi = (const T*)halo_hi;
-            a.Cl_in = (const T*)Cl_in;
-            a.Cl_out = (T*)Cl_out;
-            a.err_out = (T*)err_out;
-            a.mid = (Ek0Mid<T, N>*)ws.mid;
-            a.mid_flag = mid_flag;
-            a.mid_seq = mid_seq;
-            a.partials = ws.partials;
-            a.ticket = ws.ticket;
-            a.z_sq_out = z_sq_out;
-            a.out_sum = out_sum;
-            a.d_global = d_global;
-            a.wait = ws.wait;
-            a.reduce_a = ws.reduce;
-            a.reduce_b = reduce_b;
-            a.pack = typed_pack(ws.pack);
-            a.chunks = 0;
-            a.keep_frac = 2.0f;
-            a.use_bulk = (g.cols % (16 / (int)sizeof(T)) == 0) && ((reinterpret_cast<uintptr_t>(ctl ? mean_ab[0] : mean_in) & 15) == 0) &&
-                                 (!ctl || (reinterpret_cast<uintptr_t>(mean_ab[1]) & 15) == 0)
-                             ? 1 : 0;
-            switch (g.kind) {
-                case IVP_VDP: return launch_chain<VanderPol<T>, kCtl>(g, a, st);
-                case IVP_LORENZ96: return launch_chain<Lorenz96<T>, kCtl>(g, a, st);
-                case IVP_BRUSS: return launch_chain<Brusselator<T>, kCtl>(g, a, st);
-                case IVP_BURGERS1D: return launch_chain<Burgers1d<T>, kCtl>(g, a, st);
-                case IVP_WAVE1D: return launch_chain<Wave1d<T>, kCtl>(g, a, st);
-                case IVP_THREEBODY: return launch_chain<ThreeBody<T>, kCtl>(g, a, st);
-                case IVP_PLEIADES: return launch_chain<Pleiades<T>, kCtl>(g, a, st);
-                default: return kNoFusedKernel;
-            }
+        a.max_attempts = max_attempts;
+        bool aligned16 = true;
+        for (int i = 0; i < kMaxRing; ++i) {
+            a.mean_ring[i] = i < nbuf ? (T*)mean_ring[i] : nullptr;
+            a.Cl_ring[i] = i < nbuf ? (T*)Cl_ring[i] : nullptr;
+            a.err_ring[i] = (i < nbuf && err_ring) ? (T*)err_ring[i] : nullptr;
+            a.ref_ring[i] = (i < nbuf && ref_ring) ? (T*)ref_ring[i] : nullptr;
+            if (i < nbuf && (reinterpret_cast<uintptr_t>(mean_ring[i]) & 15) != 0) aligned16 = false;
         }
         a.g = g;
         a.c = make_consts<T, N>(h);
         a.cd = make_consts<double, N>(h);
-        a.mean_in = (const T*)mean_in;
-        a.mean_out = (T*)mean_out;
-        a.ref_out = (T*)ref_out;
         a.halo_lo = (const T*)halo_lo;
         a.halo_hi = (const T*)halo_hi;
-        a.Cl_in = (const T*)Cl_in;
-        a.Cl_out = (T*)Cl_out;
-        a.err_out = (T*)err_out;
+        a.halo_parity_stride = ws.halo_parity_stride_bytes / (long long)sizeof(T);
         a.mid = (Ek0Mid<T, N>*)ws.mid;
         a.mid_flag = mid_flag;
         a.mid_seq = mid_seq;
+        a.cl_flag = ws.cl_flag;
+        a.cl_seq = ws.cl_seq;
         a.partials = ws.partials;
         a.ticket = ws.ticket;
         a.z_sq_out = z_sq_out;
@@ -387,10 +400,26 @@ struct Launch {
         a.reduce_a = ws.reduce;
         a.reduce_b = reduce_b;
         a.pack = typed_pack(ws.pack);
+        if (g.kind != IVP_FHN2D) {
+            // 1-d vector fields: the tile-based one-launch kernel
+            a.chunks = 0;
+            a.keep_frac = 2.0f;
+            a.use_bulk = (g.cols % (16 / (int)sizeof(T)) == 0) && aligned16 ? 1 : 0;
+            switch (g.kind) {
+                case IVP_VDP: return launch_chain<VanderPol<T>, kCtl>(g, a, ws, st);
+                case IVP_LORENZ96: return launch_chain<Lorenz96<T>, kCtl>(g, a, ws, st);
+                case IVP_BRUSS: return launch_chain<Brusselator<T>, kCtl>(g, a, ws, st);
+                case IVP_BURGERS1D: return launch_chain<Burgers1d<T>, kCtl>(g, a, ws, st);
+                case IVP_WAVE1D: return launch_chain<Wave1d<T>, kCtl>(g, a, ws, st);
+                case IVP_THREEBODY: return launch_chain<ThreeBody<T>, kCtl>(g, a, ws, st);
+                case IVP_PLEIADES: return launch_chain<Pleiades<T>, kCtl>(g, a, ws, st);
+                default: return kNoFusedKernel;
+            }
+        }
         constexpr int PADC = Cfg::PADC;
-        a.use_bulk = (g.cols % PADC == 0) && ((reinterpret_cast<uintptr_t>(mean_in) & 15) == 0) ? 1 : 0;
+        a.use_bulk = (g.cols % PADC == 0) && aligned16 ? 1 : 0;
         unsigned resident = 0;
-        TDX_CUDA_TRY(persistent_grid<kern>(Cfg::total(), 1LL << 40, 0, resident, W + 32));
+        TDX_CUDA_TRY(persistent_grid<kern>(Cfg::total(), 1LL << 40, 0, resident, Cfg::THREADS));
         a.col_blocks = (unsigned)((g.cols + W - 1) / W);
         unsigned chunks = resident / a.col_blocks;
         if (chunks < 1u) chunks = 1u;
@@ -398,16 +427,22 @@ struct Launch {
         a.chunks = chunks;
         a.total_strips = a.col_blocks * chunks;
         const unsigned grid = a.total_strips < resident ? a.total_strips : resident;
+        // one unit partial per (grid row, column block) and phase
+        const long long units = (long long)g.rows * a.col_blocks;
+        if (units > ws.unit_cap) return (int)cudaErrorInvalidValue;
+        a.red_a = RedPlan{ws.unit_a, (unsigned)units, (unsigned long long)g.grow0 * a.col_blocks, (unsigned long long)g.grows * a.col_blocks};
+        a.red_b = a.red_a;
+        a.red_b.unit = ws.unit_b;
         // L2 residency hints: keep as many rows of every strip as fit the budget; everything fits -> no hints at all
         {
             static const double budget_mb = std::getenv("TDX_EK0_L2_KEEP_MB") ? std::atof(std::getenv("TDX_EK0_L2_KEEP_MB")) : 80.0;
             const double mean_mb = (double)g.d * N * sizeof(T) / 1.0e6;
             a.keep_frac = (budget_mb <= 0.0) ? 2.0f : (float)(budget_mb / mean_mb);
         }
-        // the CTAs wait for one another at the in-kernel barrier: a cooperative launch guarantees that all of them are resident
+        // the CTAs wait for one another at the in-kernel barriers: a cooperative launch guarantees that all of them are resident
         // (measured: no launch-latency penalty against a plain launch of the same grid)
         void* params[] = {(void*)&a};
-        TDX_CUDA_TRY(cudaLaunchCooperativeKernel((const void*)kern, dim3(grid), dim3(W + 32), params, Cfg::total(), st));
+        TDX_CUDA_TRY(cudaLaunchCooperativeKernel((const void*)kern, dim3(grid), dim3(Cfg::THREADS), params, Cfg::total(), st));
         return (int)cudaGetLastError();
     }
 
@@ -472,6 +507,7 @@ struct Launch {
         out.flag_upper = pk.flag_upper;
         out.done_count = pk.done_count;
         out.seq = pk.seq;
+        out.parity_stride = pk.parity_stride / (long long)sizeof(T);   // the host sets it in bytes
         out.n_first = pk.n_first;
         out.n_last = pk.n_last;
         out.enabled = pk.enabled;

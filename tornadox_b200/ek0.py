@@ -2,7 +2,9 @@
 ``DiagonalEK0`` (:196-280, = the DiagonalEK1 kernel with the Jacobian diagonal forced to zero).
 
 KroneckerEK0 keeps ONE (n, n) factor for all coordinates; an attempt is two d-wide sweeps over the mean
-with the global calibration scalar in between (``tdx_ek0_sweep_a`` -> ``tdx_ek0_mid`` -> ``tdx_ek0_sweep_b``).
+with the global calibration scalar in between, fused into ONE cooperative launch (``tdx_ek0_attempt_step``;
+the three phases ``tdx_ek0_sweep_a`` -> ``tdx_ek0_mid`` -> ``tdx_ek0_sweep_b`` remain for callers that all-reduce
+between them themselves).
 The dense ``ReferenceEK0`` (:13-82) is O(d^3) and out of scope.
 """
 
@@ -23,6 +25,7 @@ class KroneckerEK0(odefilter.ODEFilter):
     #: when False (default), reference_state = |mean[0]| is not written by the kernel every attempt: it is implied by the
     #: new mean and is computed on first access of ``state.reference_state`` (``odefilter.DeferredAbsRow``)
     materialize_reference_state = False
+    _has_controller = True
 
     def initialize(self, f, t0, tmax, y0, df, df_diagonal):
         """ek0.py:94-121: single (n, n) factor, scalar NaN error estimate."""
@@ -40,7 +43,7 @@ class KroneckerEK0(odefilter.ODEFilter):
         return odefilter.ODEFilterState(t=t0, error_estimate=float("nan"), reference_state=nan, y=y)
 
     def attempt_step(self, state, dt, f, t0, tmax, y0, df, df_diagonal):
-        """ek0.py:152-193 as three launches."""
+        """ek0.py:152-193 as one cooperative launch."""
         if self.engine is None:
             raise RuntimeError("call initialize() first")
         abstol, reltol = self.steprule.kernel_tolerances
@@ -77,44 +80,32 @@ class KroneckerEK0(odefilter.ODEFilter):
 
     perform_full_step_compiled = perform_full_step
 
-    def _device_loop_final_state(self, ivp):
-        """The whole solve under the device-resident step controller (``tdx_ek0_enqueue_attempts``)."""
-        state = self.initialize(*ivp)
-        eng = self.engine
-        rule = eng.native_steprule(self.steprule)
-        if rule is None or state.y.mean.device.type != "cuda" or not eng.can_run_full_steps():
-            return None
-        if not state.t < ivp.tmax:
-            return state, dict(num_f_evaluations=0, num_df_evaluations=0, num_df_diagonal_evaluations=0, num_steps=0,
-                               num_attempted_steps=0)
-        return self.run_device_loop(state, self.steprule.first_dt(*ivp), ivp.tmax)
+    # ---- device-resident controller hooks (odefilter.ODEFilter.run_device_loop / _Follower) --------------------------------
+    def _ctl_ring(self, state, nbuf, clone_first=False):
+        mean0, Cl0 = state.y.mean, state.y.cov_sqrtm_2
+        if clone_first:
+            mean0, Cl0 = mean0.clone(), Cl0.clone()
+        means = [mean0] + [torch.empty_like(mean0) for _ in range(nbuf - 1)]
+        factors = [Cl0] + [torch.empty_like(Cl0) for _ in range(nbuf - 1)]
+        err = torch.full((nbuf,), float("nan"), dtype=mean0.dtype, device=mean0.device)
+        errs = [err[i] for i in range(nbuf)]
+        refs = None
+        if self.materialize_reference_state:
+            refs = [torch.full((mean0.shape[1],), float("nan"), dtype=mean0.dtype, device=mean0.device) for _ in range(nbuf)]
+        return dict(means=means, factors=factors, errs=errs, refs=refs)
 
-    def run_device_loop(self, state, dt0, tmax):
-        """Advance ``state`` to ``tmax`` under the device-resident step controller, starting with step ``dt0``; the input
-        state's buffers become one of the two buffer pairs.  Returns (final state, info)."""
-        eng = self.engine
-        rule = eng.native_steprule(self.steprule)
-        info = dict(num_f_evaluations=0, num_df_evaluations=0, num_df_diagonal_evaluations=0, num_steps=0,
-                    num_attempted_steps=0)
-        pair_a = (state.y.mean, state.y.cov_sqrtm_2)
-        pair_b = (torch.empty_like(pair_a[0]), torch.empty_like(pair_a[1]))
-        err = torch.empty((), dtype=self.dtype, device=pair_a[0].device)
-        ref = torch.empty(pair_a[0].shape[1], dtype=self.dtype, device=err.device) if self.materialize_reference_state else None
-        eng.ctl_begin(rule, state.t, dt0, tmax)
-        while True:
-            eng.ek0_enqueue_attempts(self.device_loop_batch, pair_a, pair_b, err, ref)
-            ctl = eng.ctl_read()
-            if ctl.failed:
-                raise FloatingPointError(f"error estimate is NaN at t={ctl.t}, dt={ctl.dt}")
-            if ctl.done:
-                break
-        mean, Cl = pair_b if ctl.cur else pair_a
-        final = odefilter.ODEFilterState(t=ctl.t, error_estimate=err,
-                                         reference_state=ref if ref is not None else odefilter.DeferredAbsRow(mean),
-                                         y=rv.LeftIsotropicMatrixNormal(mean, state.y.d, Cl))
-        n_att = int(ctl.attempts)
-        info.update(num_f_evaluations=n_att, num_steps=int(ctl.accepted), num_attempted_steps=n_att)
-        return final, info
+    def _ctl_launch(self, k, ring, stream=None):
+        self.engine.ek0_run_attempts(k, ring["means"], ring["factors"], ring["errs"], ring["refs"], stream=stream)
+
+    def _ctl_state(self, ring, slot, t):
+        mean = ring["means"][slot]
+        ref = ring["refs"][slot] if ring["refs"] is not None else odefilter.DeferredAbsRow(mean)
+        return odefilter.ODEFilterState(t=t, error_estimate=ring["errs"][slot], reference_state=ref,
+                                        y=rv.LeftIsotropicMatrixNormal(mean, mean.shape[1], ring["factors"][slot]))
+
+    def _ctl_info(self, attempts, accepted):
+        return dict(num_f_evaluations=attempts, num_df_evaluations=0, num_df_diagonal_evaluations=0, num_steps=accepted,
+                    num_attempted_steps=attempts)
 
 
 class DiagonalEK0(BatchedEK1):

@@ -22,6 +22,7 @@ class BatchedEK1(odefilter.ODEFilter):
     #: when False the per-coordinate error_estimate / reference_state vectors are not written to HBM
     #: (the scaled error norm is fused regardless); state.error_estimate / reference_state are then None
     materialize_error_vectors = True
+    _has_controller = True
 
     def __init__(self, *args, **kwargs):
         super().__init__(*args, **kwargs)
@@ -117,45 +118,34 @@ class BatchedEK1(odefilter.ODEFilter):
 
     perform_full_step_compiled = perform_full_step
 
-    def _device_loop_final_state(self, ivp):
-        """The whole solve under the device-resident step controller (``tdx_dek1_enqueue_attempts``)."""
-        state = self.initialize(*ivp)
-        eng = self.engine
-        rule = eng.native_steprule(self.steprule)
-        if rule is None or state.y.mean.device.type != "cuda" or not eng.can_run_full_steps():
-            return None
-        if not state.t < ivp.tmax:
-            return state, dict(num_f_evaluations=0, num_df_evaluations=0, num_df_diagonal_evaluations=0, num_steps=0,
-                               num_attempted_steps=0)
-        return self.run_device_loop(state, self.steprule.first_dt(*ivp), ivp.tmax)
+    # ---- device-resident controller hooks (odefilter.ODEFilter.run_device_loop / _Follower) --------------------------------
+    def _ctl_ring(self, state, nbuf, clone_first=False):
+        mean0, sc0 = state.y.mean, state.y.cov_sqrtm
+        if clone_first:
+            mean0, sc0 = mean0.clone(), sc0.clone()
+        means = [mean0] + [torch.empty_like(mean0) for _ in range(nbuf - 1)]
+        factors = [sc0] + [torch.empty_like(sc0) for _ in range(nbuf - 1)]
+        errs = refs = None
+        if self.materialize_error_vectors:
+            d = mean0.shape[1]
+            errs = [torch.full((d,), float("nan"), dtype=mean0.dtype, device=mean0.device) for _ in range(nbuf)]
+            refs = [torch.full((d,), float("nan"), dtype=mean0.dtype, device=mean0.device) for _ in range(nbuf)]
+        return dict(means=means, factors=factors, errs=errs, refs=refs)
 
-    def run_device_loop(self, state, dt0, tmax):
-        """Advance ``state`` to ``tmax`` under the device-resident step controller, starting with step ``dt0``; the input
-        state's buffers become one of the two buffer pairs.  Returns (final state, info)."""
-        eng = self.engine
-        rule = eng.native_steprule(self.steprule)
-        info = dict(num_f_evaluations=0, num_df_evaluations=0, num_df_diagonal_evaluations=0, num_steps=0,
-                    num_attempted_steps=0)
-        pair_a = (state.y.mean, state.y.cov_sqrtm)
-        pair_b = (torch.empty_like(pair_a[0]), torch.empty_like(pair_a[1]))
-        d = pair_a[0].shape[1]
-        err = torch.empty(d, dtype=self.dtype, device=pair_a[0].device) if self.materialize_error_vectors else None
-        ref = torch.empty_like(err) if err is not None else None
-        eng.ctl_begin(rule, state.t, dt0, tmax)
-        while True:
-            eng.dek1_enqueue_attempts(self.device_loop_batch, pair_a, pair_b, err, ref, jacobian=self._uses_jacobian)
-            ctl = eng.ctl_read()
-            if ctl.failed:
-                raise FloatingPointError(f"error estimate is NaN at t={ctl.t}, dt={ctl.dt}")
-            if ctl.done:
-                break
-        mean, sc = pair_b if ctl.cur else pair_a
-        final = odefilter.ODEFilterState(t=ctl.t, y=rv.BatchedMultivariateNormal(mean, sc), error_estimate=err,
-                                         reference_state=ref)
-        n_att = int(ctl.attempts)
-        info.update(num_f_evaluations=n_att, num_df_diagonal_evaluations=n_att if self._uses_jacobian else 0,
-                    num_steps=int(ctl.accepted), num_attempted_steps=n_att)
-        return final, info
+    def _ctl_launch(self, k, ring, stream=None):
+        self.engine.dek1_run_attempts(k, ring["means"], ring["factors"], ring["errs"], ring["refs"],
+                                      jacobian=self._uses_jacobian, stream=stream)
+
+    def _ctl_state(self, ring, slot, t):
+        err = ring["errs"][slot] if ring["errs"] is not None else None
+        ref = ring["refs"][slot] if ring["refs"] is not None else None
+        return odefilter.ODEFilterState(t=t, y=rv.BatchedMultivariateNormal(ring["means"][slot], ring["factors"][slot]),
+                                        error_estimate=err, reference_state=ref)
+
+    def _ctl_info(self, attempts, accepted):
+        return dict(num_f_evaluations=attempts, num_df_evaluations=0,
+                    num_df_diagonal_evaluations=attempts if self._uses_jacobian else 0, num_steps=accepted,
+                    num_attempted_steps=attempts)
 
     def _attempt_step_host(self, state, dt, abstol, reltol):
         """``attempt_step`` for a state held in host memory (CPU tensors): chunked H2D | kernel | D2H pipeline inside the

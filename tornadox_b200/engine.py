@@ -1,9 +1,12 @@
 """Step engine: owns one ``tdx_ctx`` (one GPU, one shard) and launches the fused kernels on torch buffers.
 
 Multi-GPU: one process per GPU; the state dimension is sharded by grid rows (fhn_2d) or chain ranges
-(lorenz96, brusselator) of BOTH fields.  Per attempt the only communication is the stencil halo
-(``HaloExchanger``: NCCL send/recv over NVLink) and the all-reduce of one or two fp64 scalars, so every
-rank takes the identical accept/reject decision (reference: no counterpart, single device).
+(lorenz96, brusselator) of BOTH fields.  Per attempt the only communication is the stencil halo and the
+all-reduce of one or two fp64 sums; by default both travel through NVLink peer memory written and read by the
+step kernels themselves (``_connect_peers``: CUDA-IPC mapped exchange blocks, ``tdx_comm_*``), so every rank
+takes the identical accept/reject decision without a single NCCL call between kernels.  ``HaloExchanger``
+(torch.distributed send/recv, any backend) remains for callers without peer access and for the CPU tests
+(reference: no counterpart, single device).
 """
 
 import ctypes
@@ -18,8 +21,37 @@ KernelSpec = namedtuple("KernelSpec", "kind params grid_rows grid_cols n_fields 
 """Which in-kernel vector field an ``InitialValueProblem`` maps to (global geometry)."""
 
 
+_RED_CHUNKS = 16      # kRedChunks in csrc/tdx_device.cuh
+
+
+def _chunk_aligned_bounds(spec, world):
+    """Shard boundaries on the chunk grid of the kernels' reductions (see ``reduction_is_sharding_independent``), or None
+    if the problem's size does not allow it.  The shards then differ in size by at most one chunk's rounding."""
+    if _RED_CHUNKS % world:
+        return None
+    per = _RED_CHUNKS // world
+    if spec.kind == _lib.TDX_IVP_FHN2D:
+        rows = spec.grid_rows
+        bounds = [((r * per) * rows) // _RED_CHUNKS for r in range(world + 1)]
+        tiles_x = -(-spec.grid_cols // 32)
+        tiles_y = -(-rows // 4)
+        for r, b in enumerate(bounds[1:-1], start=1):
+            if b % 4 or (b // 4) * tiles_x != ((r * per) * tiles_y * tiles_x) // _RED_CHUNKS:
+                return None
+    else:
+        tile = 256 if spec.n_fields == 1 else 128
+        units = -(-spec.grid_cols // tile)
+        bounds = [min((((r * per) * units) // _RED_CHUNKS) * tile, spec.grid_cols) for r in range(world + 1)]
+        bounds[-1] = spec.grid_cols
+    if any(b1 - b0 < 2 for b0, b1 in zip(bounds[:-1], bounds[1:])):
+        return None
+    return bounds
+
+
 def shard_range(spec, rank, world):
-    """Contiguous balanced split of the sharded axis (grid rows for fhn_2d, points for 1-d chains)."""
+    """Contiguous split of the sharded axis (grid rows for fhn_2d, points for 1-d chains).  Where the size allows it the
+    boundaries are put on the chunk grid of the kernels' reductions, which makes the error norm (and with it the accepted-step
+    sequence) bit-identical to a single-GPU run; otherwise the split is balanced to within one row / point."""
     extent = spec.grid_rows if spec.kind == _lib.TDX_IVP_FHN2D else spec.grid_cols
     if world == 1:
         return 0, extent
@@ -31,9 +63,41 @@ def shard_range(spec, rank, world):
         raise ValueError(f"{spec.name} (d = {spec.grid_cols}) cannot be sharded across GPUs")
     if extent < 2 * world:
         raise ValueError(f"cannot shard an axis of {extent} across {world} ranks")
+    aligned = _chunk_aligned_bounds(spec, world)
+    if aligned is not None:
+        return aligned[rank], aligned[rank + 1]
     base, rem = divmod(extent, world)
     begin = rank * base + min(rank, rem)
     return begin, begin + base + (1 if rank < rem else 0)
+
+
+def reduction_is_sharding_independent(spec, world, chunks=16):
+    """True if the kernels' norm sums are bit-identical to a single-GPU run for this problem and number of ranks: every
+    shard boundary has to fall on a boundary of the ``chunks`` equal parts of the reduction's global unit range (``RedPlan``
+    in csrc/tdx_device.cuh).  Units: 256-coordinate tiles (fhn_2d: 4 grid rows x 32 columns of both fields; chains: 128
+    points of both fields, or 256 points) for DiagonalEK1 and the 1-d KroneckerEK0 kernels, (grid row, 256-column block)
+    pairs for the fused fhn_2d KroneckerEK0 kernel.  E.g. 2 / 4 / 8 / 16 equal shards of a 2048 x 2048 grid qualify."""
+    if world == 1:
+        return True
+
+    def on_chunk_boundary(unit_index, units):
+        return any((c * units) // chunks == unit_index for c in range(chunks + 1))
+
+    bounds = [shard_range(spec, r, world)[0] for r in range(1, world)]
+    if spec.kind == _lib.TDX_IVP_FHN2D:
+        tile_rows, tile_cols, strip_cols = 4, 32, 256
+        tiles_x = -(-spec.grid_cols // tile_cols)
+        tiles_y = -(-spec.grid_rows // tile_rows)
+        col_blocks = -(-spec.grid_cols // strip_cols)
+        for b in bounds:
+            if b % tile_rows or not on_chunk_boundary((b // tile_rows) * tiles_x, tiles_y * tiles_x):
+                return False
+            if not on_chunk_boundary(b * col_blocks, spec.grid_rows * col_blocks):
+                return False
+        return True
+    tile = 256 if spec.n_fields == 1 else 128
+    units = -(-spec.grid_cols // tile)
+    return all(b % tile == 0 and on_chunk_boundary(b // tile, units) for b in bounds)
 
 
 def local_slices(spec, begin, end):
@@ -435,8 +499,18 @@ class StepEngine:
         return mean_out, Cl_out, err, ref, res
 
     # ---- device-resident step controller (no host involvement between attempts) -------------------------------------
-    def ctl_begin(self, rule, t0, dt0, tmax):
-        _lib.check(self.lib.tdx_ctl_begin(self.handle, ctypes.byref(rule), float(t0), float(dt0), float(tmax), self._stream()))
+    def ctl_begin(self, rule, t0, dt0, tmax, nbuf=2, stop_at=None, follow=False):
+        """Reset the device-resident controller.  ``nbuf``: size of the state ring; ``stop_at``: time stops
+        (odefilter.py:355-373); ``follow``: the host follows the running solve (``ctl_poll`` / ``ctl_consume``)."""
+        opt = _lib.CtlOptions()
+        opt.nbuf, opt.follow = int(nbuf), 1 if follow else 0
+        stops = None
+        if stop_at is not None:
+            stops = np.ascontiguousarray(np.asarray(list(stop_at), dtype=np.float64))
+            opt.stop_at = stops.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+            opt.n_stops = int(stops.shape[0])
+        _lib.check(self.lib.tdx_ctl_begin_ex(self.handle, ctypes.byref(rule), float(t0), float(dt0), float(tmax),
+                                             ctypes.byref(opt), self._stream()))
 
     def ctl_read(self, history=False):
         st = _lib.CtlState()
@@ -449,6 +523,39 @@ class StepEngine:
         _lib.check(self.lib.tdx_ctl_read(self.handle, ctypes.byref(st), None, None, self._stream()))
         return st
 
+    def ctl_poll(self):
+        """(accepted, attempts) of the running solve from the mapped pinned feed; no synchronisation."""
+        pr = _lib.CtlProgress()
+        _lib.check(self.lib.tdx_ctl_poll(self.handle, ctypes.byref(pr)))
+        return int(pr.accepted), int(pr.attempts)
+
+    def ctl_history(self, state_index):
+        """(t, dt, attempts so far) of accepted state ``state_index`` >= 1 from the feed."""
+        t, dt, att = ctypes.c_double(), ctypes.c_double(), ctypes.c_int64()
+        _lib.check(self.lib.tdx_ctl_history(self.handle, int(state_index), ctypes.byref(t), ctypes.byref(dt), ctypes.byref(att)))
+        return t.value, dt.value, int(att.value)
+
+    def ctl_consume(self, upto):
+        _lib.check(self.lib.tdx_ctl_consume(self.handle, int(upto)))
+
+    def ctl_abort(self):
+        _lib.check(self.lib.tdx_ctl_abort(self.handle))
+
+    def raise_if_failed(self, ctl):
+        """Map the controller's failure codes to the exceptions of the host-driven loops."""
+        if ctl.failed == 1:
+            raise FloatingPointError(f"error estimate is NaN at t={ctl.t}, dt={ctl.dt}")
+        if ctl.failed:
+            raise _lib.TornadoxB200Error(
+                "a wait inside the step kernels timed out (a neighbouring rank did not deliver its halo / its share of a "
+                "reduction, or a grid barrier was abandoned); the state is not valid")
+
+    @staticmethod
+    def _ring(tensors):
+        if tensors is None:
+            return None
+        return (ctypes.c_void_p * len(tensors))(*[(t.data_ptr() if t is not None else None) for t in tensors])
+
     def dek1_enqueue_attempts(self, k, pair_a, pair_b, err=None, ref=None, jacobian=True):
         flags = self._full_step_flags(0 if jacobian else _lib.TDX_STEP_ZERO_JACOBIAN)
         _lib.check(self.lib.tdx_dek1_enqueue_attempts(self.handle, int(k), flags, _ptr(pair_a[0]), _ptr(pair_a[1]), _ptr(pair_b[0]),
@@ -457,6 +564,19 @@ class StepEngine:
     def ek0_enqueue_attempts(self, k, pair_a, pair_b, err, ref=None):
         _lib.check(self.lib.tdx_ek0_enqueue_attempts(self.handle, int(k), self._full_step_flags(), _ptr(pair_a[0]), _ptr(pair_a[1]),
                                                      _ptr(pair_b[0]), _ptr(pair_b[1]), _ptr(err), _ptr(ref), self._stream()))
+
+    def dek1_run_attempts(self, k, means, factors, errs=None, refs=None, jacobian=True, stream=None):
+        """Up to ``k`` DiagonalEK1 attempts in ONE persistent launch over the state ring ``means`` / ``factors`` (lists of
+        tensors; ``errs`` / ``refs``: per-slot error_estimate / reference_state vectors or None)."""
+        flags = self._full_step_flags(0 if jacobian else _lib.TDX_STEP_ZERO_JACOBIAN)
+        _lib.check(self.lib.tdx_dek1_run_attempts(self.handle, int(k), flags, self._ring(means), self._ring(factors), len(means),
+                                                  self._ring(errs), self._ring(refs), stream if stream is not None else self._stream()))
+
+    def ek0_run_attempts(self, k, means, factors, errs, refs=None, stream=None):
+        """Up to ``k`` KroneckerEK0 attempts in ONE persistent launch (``errs``: one device scalar per ring slot)."""
+        _lib.check(self.lib.tdx_ek0_run_attempts(self.handle, int(k), self._full_step_flags(), self._ring(means), self._ring(factors),
+                                                 len(means), self._ring(errs), self._ring(refs),
+                                                 stream if stream is not None else self._stream()))
 
     # ---- KroneckerEK0 -----------------------------------------------------------------------------
     def ek0_attempt(self, t, dt, mean, Cl, abstol=0.0, reltol=0.0, mean_out=None, want_ref=True):

@@ -1,15 +1,20 @@
-"""Solver driver: the host loop around the fused ``attempt_step`` kernels.
+"""Solver driver around the fused ``attempt_step`` kernels.
 
 Mirrors the public interface of tornadox/odefilter.py -- ``ODEFilterState`` (:17-20), ``ODESolution``
 (:23-28), ``ODEFilter`` with ``solve`` (:51-71), ``simulate_final_state`` (:73-78),
 ``solution_generator`` (:80-159), ``perform_full_step`` (:171-223) and the ``stop_at`` time stopper
-(:355-373).  The reference's jitted ``perform_full_step_compiled`` (:225-344) is the same
-accept/reject logic inside ``lax.while_loop``; here the loop runs on the host and reads ONE fp64 scalar
-per attempt (the error norm the kernel epilogue reduced), so ``compile_step`` is accepted and ignored.
+(:355-373).  The reference's jitted ``perform_full_step_compiled`` (:225-344) compiles the accept/reject
+loop into ``lax.while_loop``; the counterpart here is the device-resident step controller: ONE persistent
+cooperative kernel runs attempt after attempt (``tdx_*_run_attempts``), deciding accept / reject, the next
+step and the time stops on the device.  ``simulate_final_state`` runs whole batches of attempts per launch;
+``solve`` / ``solution_generator`` follow the running kernel from the host through a ring of state buffers
+(dense output without a host round trip per step).  A host-driven loop (one scalar read per attempt) remains
+for user-defined step rules and for states held in host memory.
 """
 
 import dataclasses
 import math
+import time
 from abc import ABC, abstractmethod
 from collections import namedtuple
 from typing import Dict, Iterable
@@ -102,10 +107,23 @@ class ODEFilter(ABC):
             host.copy_(x, non_blocking=True)
             return host
 
+        ivp = args[0] if args else kwargs.get("ivp")
+        stop_at = kwargs.get("stop_at", args[1] if len(args) > 1 else None)
+        if self.device_loop and ivp is not None and len(args) <= 2 and not kwargs.get("progressbar"):
+            out = self._solve_following(ivp, stop_at, offload)
+            if out is not None:
+                return out
+
+        def host_keep(x):
+            # states of the host-buffer path alias the solver's two alternating pinned output sets: keep a copy
+            if isinstance(x, torch.Tensor) and x.device.type == "cpu" and x.is_pinned():
+                return x.clone()
+            return keep(x)
+
         times, means, cov_sqrtms, info = [], [], [], dict()
-        for state, info in self.solution_generator(*args, **kwargs):
+        for state, info in self.solution_generator(*args, **dict(kwargs, device_loop=False)):
             times.append(float(state.t))
-            means.append(keep(state.y.mean))
+            means.append(host_keep(state.y.mean))
             if isinstance(self, ek0.KroneckerEK0):
                 n, d = state.y.mean.shape
                 if (n * d) ** 2 <= self.dense_output_limit:
@@ -113,7 +131,7 @@ class ODEFilter(ABC):
                 else:
                     cov_sqrtms.append(keep(state.y.cov_sqrtm_2))
             else:
-                cov_sqrtms.append(keep(state.y.cov_sqrtm))
+                cov_sqrtms.append(host_keep(state.y.cov_sqrtm))
         if offload and torch.cuda.is_available():
             torch.cuda.synchronize()
         return ODESolution(
@@ -123,41 +141,151 @@ class ODEFilter(ABC):
             info=info,
         )
 
+    def _solve_following(self, ivp, stop_at, offload):
+        """``solve`` on top of the device-resident controller: the persistent kernel runs the whole solve on its own stream,
+        the host follows its progress through mapped pinned memory and copies every accepted state out of the state ring
+        (copy engine, behind the kernel) before releasing the slot.  None: not available for this configuration."""
+        from . import ek0
+
+        state = self.initialize(*ivp)
+        if not self._controller_available(state):
+            return None
+        kron = isinstance(self, ek0.KroneckerEK0)
+        dense = kron and (state.y.mean.shape[0] * state.y.mean.shape[1]) ** 2 <= self.dense_output_limit
+        times, means, factors = [float(state.t)], [], []
+
+        def store(dst_list, src, stream):
+            if offload:
+                dst = torch.empty(src.shape, dtype=src.dtype, pin_memory=True)
+            else:
+                dst = torch.empty_like(src)
+            with torch.cuda.stream(stream):
+                dst.copy_(src, non_blocking=True)
+            dst_list.append(dst)
+
+        info = self._ctl_info(0, 0)
+        if state.t < ivp.tmax:
+            follower = _Follower(self, state, self.steprule.first_dt(*ivp), ivp.tmax, stop_at)
+            try:
+                store(means, follower.ring["means"][0], follower.copy_stream)
+                store(factors, follower.ring["factors"][0], follower.copy_stream)
+                for j, t, attempts, slot in follower.states():
+                    times.append(t)
+                    store(means, follower.ring["means"][slot], follower.copy_stream)
+                    store(factors, follower.ring["factors"][slot], follower.copy_stream)
+                    follower.release_when_copied(j)
+                    info = self._ctl_info(attempts, j)
+            finally:
+                follower.close()
+        else:
+            means.append(state.y.mean.clone())
+            factors.append((state.y.cov_sqrtm_2 if kron else state.y.cov_sqrtm).clone())
+        if dense:       # as upstream: the dense kron(I_d, C) factor of every state, small problems only
+            d = state.y.mean.shape[1]
+            factors = [torch.kron(torch.eye(d, dtype=f.dtype, device=f.device), f) for f in factors]
+        return ODESolution(t=torch.tensor(times, dtype=torch.float64), mean=torch.stack(means), cov_sqrtm=torch.stack(factors),
+                           info=info)
+
     #: attempts enqueued per look at the device-resident controller (``simulate_final_state`` fast path)
     device_loop_batch = 64
     #: set False to force the host-driven loop everywhere
     device_loop = True
 
-    def _device_loop_final_state(self, ivp):
-        """Solvers with a device-resident step controller override this; None = not available for this configuration."""
-        return None
+    #: state buffers the controller rotates through when the host follows the solve (``solve``, ``solution_generator``)
+    ring_size = 4
+
+    # ---- device-resident controller: hooks of the fused solvers ---------------------------------------------------------
+    engine = None
+    _has_controller = False
+
+    def _controller_available(self, state):
+        eng = self.engine
+        return (eng is not None and eng.native_steprule(self.steprule) is not None and state.y.mean.device.type == "cuda"
+                and eng.can_run_full_steps())
+
+    def _ctl_ring(self, state, nbuf, clone_first=False):
+        raise NotImplementedError
+
+    def _ctl_launch(self, k, ring, stream=None):
+        raise NotImplementedError
+
+    def _ctl_state(self, ring, slot, t):
+        raise NotImplementedError
+
+    def _ctl_info(self, attempts, accepted):
+        raise NotImplementedError
+
+    def _device_loop_final_state(self, ivp, stop_at=None):
+        """The whole solve under the device-resident step controller; None = not available for this configuration."""
+        if not self._has_controller:
+            return None
+        state = self.initialize(*ivp)
+        if not self._controller_available(state):
+            return None
+        if not state.t < ivp.tmax:
+            return state, self._ctl_info(0, 0)
+        return self.run_device_loop(state, self.steprule.first_dt(*ivp), ivp.tmax, stop_at=stop_at)
+
+    def run_device_loop(self, state, dt0, tmax, stop_at=None):
+        """Advance ``state`` to ``tmax`` under the device-resident step controller, starting with step ``dt0``: launches of
+        ``device_loop_batch`` attempts each, ONE persistent kernel per launch, one look at the controller per launch.  The
+        input state's buffers become slot 0 of the state ring.  Returns (final state, info)."""
+        eng = self.engine
+        rule = eng.native_steprule(self.steprule)
+        ring = self._ctl_ring(state, 2)
+        eng.ctl_begin(rule, state.t, dt0, tmax, nbuf=2, stop_at=stop_at)
+        while True:
+            self._ctl_launch(self.device_loop_batch, ring)
+            ctl = eng.ctl_read()
+            eng.raise_if_failed(ctl)
+            if ctl.done:
+                break
+        return self._ctl_state(ring, ctl.cur, ctl.t), self._ctl_info(int(ctl.attempts), int(ctl.accepted))
 
     def simulate_final_state(self, *args, **kwargs):
         """Drain the generator, return the last (state, info) (odefilter.py:73-78).
 
         Nobody looks at the intermediate states here, so when the solver has a device-resident step controller the
-        whole solve runs without the host in the loop (batches of attempts, one look at the controller per batch)."""
+        whole solve runs without the host in the loop (batches of attempts per launch, one look at the controller per
+        launch); ``stop_at`` becomes the controller's list of time stops."""
         ivp = args[0] if args else kwargs.get("ivp")
-        plain = len(args) <= 1 and not kwargs.get("stop_at") and not kwargs.get("progressbar")
+        stop_at = kwargs.get("stop_at", args[1] if len(args) > 1 else None)
+        plain = len(args) <= 2 and not kwargs.get("progressbar")
         if self.device_loop and plain and ivp is not None:
-            out = self._device_loop_final_state(ivp)
+            out = self._device_loop_final_state(ivp, stop_at=stop_at)
             if out is not None:
                 return out
         state, info = None, None
-        for state, info in self.solution_generator(*args, **kwargs):
+        for state, info in self.solution_generator(*args, **dict(kwargs, device_loop=False)):
             pass
         return state, info
 
-    def solution_generator(self, ivp, stop_at=None, progressbar=False, compile_step=True, compile_init=False):
-        """Yield (state, info) after initialisation and after every accepted step (odefilter.py:80-159)."""
+    def solution_generator(self, ivp, stop_at=None, progressbar=False, compile_step=True, compile_init=False, device_loop=None):
+        """Yield (state, info) after initialisation and after every accepted step (odefilter.py:80-159).
+
+        With a device-resident controller (``device_loop``; default: the solver's ``device_loop`` attribute) the persistent
+        kernel runs ahead on its own stream and the states that are yielded are copies taken out of the state ring;
+        otherwise the host drives one full step at a time and yields the step's own output buffers."""
         del compile_step, compile_init  # no tracing compiler here; the step is a CUDA kernel either way
-        stopper = _TimeStopper(stop_at) if stop_at is not None else None
+        use_ctl = self.device_loop if device_loop is None else device_loop
         state = self.initialize(*ivp)
         info = dict(num_f_evaluations=0, num_df_evaluations=0, num_df_diagonal_evaluations=0, num_steps=0,
                     num_attempted_steps=0)
         yield state, info
 
         dt = self.steprule.first_dt(*ivp)
+        if use_ctl and not progressbar and state.t < ivp.tmax and self._controller_available(state):
+            follower = _Follower(self, state, dt, ivp.tmax, stop_at, clone_first=True)
+            try:
+                for j, t, attempts, slot in follower.states():
+                    copy = follower.clone_state(slot, t)
+                    follower.release_when_copied(j, wait=True)
+                    yield copy, self._ctl_info(attempts, j)
+            finally:
+                follower.close()
+            return
+
+        stopper = _TimeStopper(stop_at) if stop_at is not None else None
         bar = _ProgressBar(ivp.tmax) if progressbar else None
         while state.t < ivp.tmax:
             if bar is not None:
@@ -209,7 +337,10 @@ class ODEFilter(ABC):
         if isinstance(self.steprule, step.ConstantSteps):
             return None
         sq_sum = getattr(proposed, "scaled_error_norm_sq_sum", None)
-        if sq_sum is not None:
+        # the kernel-reduced sum implements exactly AdaptiveSteps.scale_error_estimate: a subclass that overrides it (or the
+        # tolerances' meaning) must see its own method
+        fused_ok = type(self.steprule).scale_error_estimate is step.AdaptiveSteps.scale_error_estimate
+        if sq_sum is not None and fused_ok:
             return step.norm_from_sq_sum(sq_sum, proposed.scaled_error_norm_dim)
         if proposed.error_estimate is None:
             return self.steprule.scale_error_estimate(None, proposed.reference_state)
@@ -222,6 +353,87 @@ class ODEFilter(ABC):
     @abstractmethod
     def attempt_step(self, state, dt, f, t0, tmax, y0, df, df_diagonal):
         raise NotImplementedError
+
+
+class _Follower:
+    """Host side of a solve that runs as ONE persistent kernel on its own stream (``tdx_*_run_attempts`` with ``follow``):
+    reads the kernel's progress from mapped pinned memory, hands out the ring slots of newly accepted states and tells the
+    kernel which slots may be reused."""
+
+    def __init__(self, solver, state, dt0, tmax, stop_at, clone_first=False):
+        eng = solver.engine
+        self.solver, self.eng = solver, eng
+        self.nbuf = max(3, min(int(solver.ring_size), 8))
+        self.ring = solver._ctl_ring(state, self.nbuf, clone_first=clone_first)
+        dev = state.y.mean.device
+        self.loop_stream = torch.cuda.Stream(device=dev)
+        self.copy_stream = torch.cuda.Stream(device=dev)
+        current = torch.cuda.current_stream(dev)
+        self.loop_stream.wait_stream(current)
+        self.copy_stream.wait_stream(current)
+        eng.ctl_begin(eng.native_steprule(solver.steprule), state.t, dt0, tmax, nbuf=self.nbuf, stop_at=stop_at, follow=True)
+        import ctypes
+
+        solver._ctl_launch(2 ** 30, self.ring, stream=ctypes.c_void_p(self.loop_stream.cuda_stream))
+        self.finished = torch.cuda.Event()
+        self.finished.record(self.loop_stream)
+        self.seen = 0
+        self.pending = []          # (state index, event): copies in flight
+        self.closed = False
+
+    def states(self):
+        """Yield (j, t_j, attempts so far, ring slot) for every accepted state, in order, while the kernel is running."""
+        eng = self.eng
+        while True:
+            ended = self.finished.query()            # read BEFORE the progress counters: nothing can follow a finished kernel
+            accepted, _ = eng.ctl_poll()
+            while self.seen < accepted:
+                self.seen += 1
+                t, _, attempts = eng.ctl_history(self.seen)
+                yield self.seen, t, attempts, self.seen % self.nbuf
+            self._release_finished_copies()
+            if ended:
+                break
+            time.sleep(0)
+
+    def clone_state(self, slot, t):
+        """A copy of the state in ``slot``, made on the copy stream."""
+        with torch.cuda.stream(self.copy_stream):
+            copy = {k: (None if v is None else [None if v[slot] is None else v[slot].clone()]) for k, v in self.ring.items()}
+        return self.solver._ctl_state(copy, 0, t)
+
+    def release_when_copied(self, j, wait=False):
+        ev = torch.cuda.Event()
+        ev.record(self.copy_stream)
+        if wait:
+            ev.synchronize()
+            torch.cuda.current_stream(self.copy_stream.device).wait_event(ev)
+            self.eng.ctl_consume(j)
+        else:
+            self.pending.append((j, ev))
+            self._release_finished_copies()
+
+    def _release_finished_copies(self):
+        done = -1
+        while self.pending and self.pending[0][1].query():
+            done = self.pending.pop(0)[0]
+        if done >= 0:
+            self.eng.ctl_consume(done)
+
+    def close(self):
+        if self.closed:
+            return
+        self.closed = True
+        if not self.finished.query():
+            # the consumer stopped early, or an exception is on its way: let the kernel drain and stop
+            if self.pending:
+                self.copy_stream.synchronize()
+            self.eng.ctl_abort()
+        self.loop_stream.synchronize()
+        self.copy_stream.synchronize()
+        torch.cuda.current_stream(self.copy_stream.device).wait_stream(self.copy_stream)
+        ctl = self.eng.ctl_read()
+        self.eng.raise_if_failed(ctl)
 
 
 class _TimeStopper:
