@@ -60,6 +60,9 @@ extern "C" {
 #define TDX_IVP_WAVE1D 5      /* params: [dx, diffusion_param]       ivp.py:110-140 (one GPU only) */
 #define TDX_IVP_THREEBODY 6   /* params: []   grid_cols = 4          ivp.py:188-216 (one GPU only) */
 #define TDX_IVP_PLEIADES 7    /* params: []   grid_cols = 28         ivp.py:344-406 (one GPU only) */
+/* any other vector field: the caller evaluates f (and the Jacobian diagonal) itself, see tdx_predict_state / tdx_set_external.
+ * grid_rows = 1, grid_cols = d, one GPU. */
+#define TDX_IVP_EXTERNAL 8
 
 typedef struct tdx_ctx tdx_ctx;
 
@@ -143,6 +146,17 @@ int tdx_eval_f(tdx_ctx* ctx, double t, const void* y, void* fy, void* jdiag_or_n
  * edge_first has halo_hi-of-lower-neighbour layout, edge_last has halo_lo-of-upper-neighbour layout. */
 int tdx_pack_halo(tdx_ctx* ctx, double dt, const void* mean_in, void* edge_first, void* edge_last,
                   void* stream);
+
+/* ---- vector fields the library does not know (the reference takes any Python callable f / df_diagonal, odefilter.py:346-352)
+ * The filter step needs f and diag(df) at ONE point per attempt, the predicted state m_at = E0 P A P^-1 m (ek1.py:304-306,
+ * ek0.py:146-147).  For a TDX_IVP_EXTERNAL context every attempt is
+ *     tdx_predict_state(ctx, dt, mean, m_at)          m_at (d) on the device
+ *     fx = f(t + dt, m_at), jd = df_diagonal(t + dt, m_at)   the caller's own code on device arrays
+ *     tdx_set_external(ctx, fx, jd)                   jd may be NULL (DiagonalEK0 / KroneckerEK0)
+ *     tdx_dek1_attempt_step / tdx_ek0_attempt_step    the same fused kernels, reading fx / jd instead of evaluating a stencil
+ * The arrays must stay valid until the step has run.  tdx_predict_state works for every context (all fields, local shard). */
+int tdx_predict_state(tdx_ctx* ctx, double dt, const void* mean_in, void* y_out, void* stream);
+int tdx_set_external(tdx_ctx* ctx, const void* fx, const void* jdiag_or_null);
 
 /* DiagonalEK1.attempt_step (ek1.py:228-260 + 274-369), fused with
  * sum_i (dt * err_i / (abstol + reltol * ref_i))^2 over the local shard (step.py:101-104),

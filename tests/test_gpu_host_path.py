@@ -101,7 +101,7 @@ def test_native_full_step_loop_equals_the_python_loop(cuda_device, solver_name, 
     for rule in (step.AdaptiveSteps(), PyLoopSteps()):
         sol = cls(num_derivatives=3, steprule=rule)
         ts, final, info = [], None, None
-        for st, info in sol.solution_generator(p):
+        for st, info in sol.solution_generator(p, device_loop=False):
             ts.append(st.t)
             final = st
         runs.append((ts, final, dict(info)))

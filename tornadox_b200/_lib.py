@@ -23,7 +23,7 @@ TDX_STEP_COMM_REDUCE = 32
 TDX_STEP_COMM_PACK = 64
 TDX_COMM_HANDLE_BYTES = 64
 TDX_IVP_VANDERPOL, TDX_IVP_LORENZ96, TDX_IVP_BRUSSELATOR, TDX_IVP_FHN2D, TDX_IVP_BURGERS1D, TDX_IVP_WAVE1D = 0, 1, 2, 3, 4, 5
-TDX_IVP_THREEBODY, TDX_IVP_PLEIADES = 6, 7
+TDX_IVP_THREEBODY, TDX_IVP_PLEIADES, TDX_IVP_EXTERNAL = 6, 7, 8
 
 EXPORTED_SYMBOLS = (
     "tdx_last_error", "tdx_abi_version", "tdx_create", "tdx_destroy", "tdx_set_problem", "tdx_local_dim",
@@ -32,6 +32,7 @@ EXPORTED_SYMBOLS = (
     "tdx_debug_read_workspace", "tdx_dek1_attempt_step_host", "tdx_dek1_attempt_step_host_sharded", "tdx_dek1_full_step", "tdx_ek0_full_step", "tdx_propagate_cholesky_factor",
     "tdx_ctl_begin", "tdx_dek1_enqueue_attempts", "tdx_ek0_enqueue_attempts", "tdx_ctl_read",
     "tdx_ctl_begin_ex", "tdx_dek1_run_attempts", "tdx_ek0_run_attempts", "tdx_ctl_poll", "tdx_ctl_history", "tdx_ctl_consume", "tdx_ctl_abort",
+    "tdx_predict_state", "tdx_set_external",
     "tdx_comm_init", "tdx_comm_connect", "tdx_comm_pack_halo", "tdx_comm_allreduce", "tdx_comm_error",
 )
 
@@ -150,6 +151,8 @@ def load():
     lib.tdx_nordsieck.argtypes = [cint, dbl, pd, pd]
     lib.tdx_eval_f.argtypes = [vp, dbl, vp, vp, vp, vp, vp, vp]
     lib.tdx_pack_halo.argtypes = [vp, dbl, vp, vp, vp, vp]
+    lib.tdx_predict_state.argtypes = [vp, dbl, vp, vp, vp]
+    lib.tdx_set_external.argtypes = [vp, vp, vp]
     lib.tdx_dek1_attempt_step.argtypes = [vp, ctypes.POINTER(StepArgs)] + [vp] * 10
     lib.tdx_dek1_attempt_step_host.argtypes = [vp, ctypes.POINTER(StepArgs)] + [vp] * 6 + [pd, cint]
     full = [vp, ctypes.POINTER(StepRule), dbl, dbl, dbl, ctypes.c_uint32] + [vp] * 6 + [ctypes.POINTER(FullStepResult), vp]

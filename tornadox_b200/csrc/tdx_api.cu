@@ -56,6 +56,7 @@ long long grid_for(const Geo& g) {
         case IVP_WAVE1D: return num_tiles<Wave1d<double>::Shape>(g.rows, g.cols);
         case IVP_THREEBODY: return num_tiles<ThreeBody<double>::Shape>(g.rows, g.cols);
         case IVP_PLEIADES: return num_tiles<Pleiades<double>::Shape>(g.rows, g.cols);
+        case IVP_EXTERNAL: return num_tiles<External<double>::Shape>(g.rows, g.cols);
     }
     return 0;
 }
@@ -331,6 +332,14 @@ int tdx_set_problem(tdx_ctx* ctx, const tdx_problem_desc* d) {
             g.rows = 1; g.cols = (int)dim; g.grow0 = 0; g.gcol0 = 0;
             break;
         }
+        case TDX_IVP_EXTERNAL:
+            if (d->grid_rows != 1 || d->grid_cols < 1 || d->shard_begin != 0 || d->shard_end != d->grid_cols)
+                return fail(TDX_ERR_INVALID, "tdx_set_problem: an external vector field is laid out as one field of d points "
+                                             "(grid_rows = 1, grid_cols = d) and runs on one GPU");
+            if (d->grid_cols > 2147483647LL) return fail(TDX_ERR_INVALID, "tdx_set_problem: state too large");
+            g.nf = 1;
+            g.rows = 1; g.cols = (int)d->grid_cols; g.grow0 = 0; g.gcol0 = 0;
+            break;
         case TDX_IVP_LORENZ96:
             if (d->grid_rows != 1) return fail(TDX_ERR_INVALID, "tdx_set_problem: lorenz96 is one-dimensional (grid_rows = 1)");
             if (d->shard_end > d->grid_cols) return fail(TDX_ERR_INVALID, "tdx_set_problem: shard exceeds the chain");
@@ -384,8 +393,8 @@ int tdx_set_problem(tdx_ctx* ctx, const tdx_problem_desc* d) {
             break;
         default:
             return fail(TDX_ERR_UNSUPPORTED,
-                        "tdx_set_problem: unknown vector field kind; only vanderpol, lorenz96, brusselator, fhn_2d, "
-                        "burgers_1d, wave_1d, threebody and pleiades are evaluated in-kernel (there is no CPU fallback)");
+                        "tdx_set_problem: unknown vector field kind; vanderpol, lorenz96, brusselator, fhn_2d, burgers_1d, wave_1d, "
+                        "threebody and pleiades are evaluated in-kernel, TDX_IVP_EXTERNAL takes the caller's f / diag J arrays");
     }
     g.npts = (long long)g.rows * g.cols;
     g.d = (long long)g.nf * g.npts;
@@ -463,6 +472,15 @@ int tdx_halo_sizes(const tdx_ctx* ctx, int64_t* lo, int64_t* hi) {
     return TDX_OK;
 }
 
+int tdx_set_external(tdx_ctx* ctx, const void* fx, const void* jdiag) {
+    if (!ctx || !ctx->has_problem) return fail(TDX_ERR_INVALID, "tdx_set_external: no problem set");
+    if (ctx->geo.kind != IVP_EXTERNAL) return fail(TDX_ERR_INVALID, "tdx_set_external: the context's vector field is evaluated in-kernel");
+    if (!fx) return fail(TDX_ERR_INVALID, "tdx_set_external: null f array");
+    ctx->geo.ext_f = fx;
+    ctx->geo.ext_j = jdiag;
+    return TDX_OK;
+}
+
 int64_t tdx_launch_count(const tdx_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
 int tdx_debug_read_workspace(tdx_ctx* ctx, double* host_out, int64_t offset, int64_t count) {
@@ -479,6 +497,14 @@ int tdx_debug_read_workspace(tdx_ctx* ctx, double* host_out, int64_t offset, int
 static int check_ready(const tdx_ctx* ctx, const char* where) {
     if (!ctx) return fail(TDX_ERR_INVALID, std::string(where) + ": null context");
     if (!ctx->has_problem) return fail(TDX_ERR_INVALID, std::string(where) + ": tdx_set_problem has not been called");
+    return TDX_OK;
+}
+
+// step calls on an external vector field need the caller's f array first
+static int check_external(const tdx_ctx* ctx, const char* where) {
+    if (ctx->geo.kind == IVP_EXTERNAL && !ctx->geo.ext_f)
+        return fail(TDX_ERR_INVALID, std::string(where) + ": external vector field: call tdx_predict_state, evaluate f there and "
+                                                          "hand it in with tdx_set_external before every attempt");
     return TDX_OK;
 }
 
@@ -637,6 +663,7 @@ int tdx_eval_f(tdx_ctx* ctx, double t, const void* y, void* fy, void* jdiag, con
     int rc = check_ready(ctx, "tdx_eval_f");
     if (rc) return rc;
     if (!y || !fy) return fail(TDX_ERR_INVALID, "tdx_eval_f: null buffer");
+    if (ctx->geo.kind == IVP_EXTERNAL) return fail(TDX_ERR_UNSUPPORTED, "tdx_eval_f: an external vector field is evaluated by the caller");
     if ((rc = check_halos(ctx, halo_lo, halo_hi, "tdx_eval_f"))) return rc;
     DeviceGuard guard(ctx->device);
     ctx->launches += 1;
@@ -669,12 +696,28 @@ int tdx_pack_halo(tdx_ctx* ctx, double dt, const void* mean_in, void* edge_first
                      "tdx_pack_halo");
 }
 
+int tdx_predict_state(tdx_ctx* ctx, double dt, const void* mean_in, void* y_out, void* stream) {
+    int rc = check_ready(ctx, "tdx_predict_state");
+    if (rc) return rc;
+    tdx_step_args a{0.0, dt, 0.0, 0.0, 0u, 0u};
+    if ((rc = check_dt(&a, "tdx_predict_state"))) return rc;
+    if (!mean_in || !y_out) return fail(TDX_ERR_INVALID, "tdx_predict_state: null buffer");
+    const Geo& g = ctx->geo;
+    if (g.npts > 2147483647LL / 2) return fail(TDX_ERR_INVALID, "tdx_predict_state: shard too large");
+    StepHost h = make_step(ctx, &a);
+    DeviceGuard guard(ctx->device);
+    ctx->launches += 1;
+    // the "first n points of every field" of the halo packer, with n = all of them, is the predicted state of the shard
+    return cuda_fail(ctx->ops->pack(g, h, mean_in, y_out, nullptr, (int)g.npts, 0, (cudaStream_t)stream), "tdx_predict_state");
+}
+
 int tdx_dek1_attempt_step(tdx_ctx* ctx, const tdx_step_args* args, const void* mean_in, const void* sc_in,
                           void* mean_out, void* sc_out, void* err_out, void* ref_out, const void* halo_lo,
                           const void* halo_hi, double* sq_norm_sum, void* stream) {
     int rc = check_ready(ctx, "tdx_dek1_attempt_step");
     if (rc) return rc;
     if ((rc = check_dt(args, "tdx_dek1_attempt_step"))) return rc;
+    if ((rc = check_external(ctx, "tdx_dek1_attempt_step"))) return rc;
     if ((rc = comm_pack_check(ctx, args->flags, "tdx_dek1_attempt_step"))) return rc;
     resolve_halos(ctx, args->flags, halo_lo, halo_hi);
     if (!mean_in || !sc_in || !mean_out || !sc_out) return fail(TDX_ERR_INVALID, "tdx_dek1_attempt_step: null state buffer");
@@ -853,6 +896,7 @@ int tdx_ek0_attempt_step(tdx_ctx* ctx, const tdx_step_args* args, const void* me
     int rc = check_ready(ctx, "tdx_ek0_attempt_step");
     if (rc) return rc;
     if ((rc = check_dt(args, "tdx_ek0_attempt_step"))) return rc;
+    if ((rc = check_external(ctx, "tdx_ek0_attempt_step"))) return rc;
     const bool sharded = ctx->halo_lo > 0 || ctx->halo_hi > 0;
     const unsigned comm_flags = TDX_STEP_COMM_PACK | TDX_STEP_COMM_REDUCE;
     if (sharded && (args->flags & comm_flags) != comm_flags)
@@ -1539,8 +1583,8 @@ extern "C" int tdx_ctl_history(tdx_ctx* ctx, int64_t state_index, double* t, dou
 
 extern "C" int tdx_ctl_consume(tdx_ctx* ctx, int64_t upto) {
     if (!ctx || !ctx->feed) return fail(TDX_ERR_INVALID, "tdx_ctl_consume: call tdx_ctl_begin_ex with follow = 1 first");
-    if (upto >= 0 && (unsigned long long)upto > ctx->feed->consumed) {
-        ctx->feed->consumed = (unsigned long long)upto;
+    if (upto >= 0 && (unsigned long long)upto + 1ull > ctx->feed->consumed) {
+        ctx->feed->consumed = (unsigned long long)upto + 1ull;
         __sync_synchronize();
     }
     return TDX_OK;

@@ -16,7 +16,8 @@ constexpr int kMaxN = 7;       // n = nu + 1 <= 7
 constexpr int kWarps = 8;      // warps per CTA; every warp owns one 32-wide segment of one field
 constexpr int kThreads = kWarps * 32;
 
-enum : int { IVP_VDP = 0, IVP_LORENZ96 = 1, IVP_BRUSS = 2, IVP_FHN2D = 3, IVP_BURGERS1D = 4, IVP_WAVE1D = 5, IVP_THREEBODY = 6, IVP_PLEIADES = 7 };
+enum : int { IVP_VDP = 0, IVP_LORENZ96 = 1, IVP_BRUSS = 2, IVP_FHN2D = 3, IVP_BURGERS1D = 4, IVP_WAVE1D = 5, IVP_THREEBODY = 6, IVP_PLEIADES = 7,
+              IVP_EXTERNAL = 8 };
 
 // Local shard geometry.  Flat local state index = field * npts + row * cols + col.
 struct Geo {
@@ -26,6 +27,8 @@ struct Geo {
     long long grow0, gcol0;     // global coordinates of the local (0, 0)
     long long grows, gcols;     // global extent
     double prm[8];
+    const void* ext_f;          // IVP_EXTERNAL: f(t, y) and diag J at the predicted state, evaluated by the caller (device arrays)
+    const void* ext_j;          // (null: zero Jacobian diagonal)
 };
 
 // Per-attempt constants, passed by value (lands in the constant bank).
@@ -80,7 +83,7 @@ constexpr int kMaxRing = 8;              // state buffers a controller-driven so
 struct HostFeed {
     volatile unsigned long long accepted;      // kernel -> host: accepted states so far (state j lives in ring slot j % nbuf)
     volatile unsigned long long attempts;
-    volatile unsigned long long consumed;      // host -> kernel: states [0, consumed] have been copied out, their slots may be reused
+    volatile unsigned long long consumed;      // host -> kernel: NUMBER of states released, i.e. states [0, consumed) have been copied out
     volatile unsigned long long abort;         // host -> kernel: stop at the next attempt boundary
     volatile double hist_t[kCtlHistory];       // time / step of accepted state j at [j % kCtlHistory]
     volatile double hist_dt[kCtlHistory];
@@ -131,6 +134,16 @@ __device__ __forceinline__ unsigned long long global_timer_ns() {
     return t;
 }
 constexpr unsigned long long kDefaultWaitNs = 4000000000ull;
+
+// development aid (-DTDX_TIMELINE): CTA 0 records when it passes the stations of an attempt (scripts/attempt_timeline.py)
+#ifdef TDX_TIMELINE
+#define TDX_STAMP(buf, att, k)                                                                                   \
+    do {                                                                                                         \
+        if (blockIdx.x == 0) (buf)[2048 + ((att) & 63) * 8 + (k)] = (double)global_timer_ns();                   \
+    } while (0)
+#else
+#define TDX_STAMP(buf, att, k) do { } while (0)
+#endif
 
 // odefilter.py:355-373 (_TimeStopper.adjust_dt_to_time_stops) on the controller's stop list
 __device__ inline double ctl_adjust_to_stops(StepCtl* ctl, double t, double dt) {
@@ -550,6 +563,25 @@ struct Pleiades {
             acc += (j == i) ? (T)0 : term;
         }
         fx = acc;
+    }
+};
+
+// --- a vector field the library does not know: the caller evaluated f (and optionally the Jacobian diagonal) at the predicted
+//     state E0 P A P^-1 m (tdx_predict_state) with its own code and hands the arrays in (tdx_set_external).  Everything else
+//     of the attempt -- prediction, the batched QR, update, error estimate, norm -- is the same fused kernel.
+template <typename T>
+struct External {
+    using Shape = TileShape<1, 1, 8>;
+    static constexpr int HL = 0, HR = 0, HV = 0;
+    static __host__ void halo_sizes(const Geo&, long long& lo, long long& hi) { lo = hi = 0; }
+    template <class At>
+    __device__ static __forceinline__ T ring_value(const Geo&, int, int, int, int, int, const At&, const T*, const T*) {
+        return (T)0;
+    }
+    __device__ static __forceinline__ void eval(const Geo& g, const Coord& c, const T*, T own, T& fx, T& jac) {
+        (void)own;
+        fx = __ldg(reinterpret_cast<const T*>(g.ext_f) + c.flat);
+        jac = g.ext_j ? __ldg(reinterpret_cast<const T*>(g.ext_j) + c.flat) : (T)0;
     }
 };
 

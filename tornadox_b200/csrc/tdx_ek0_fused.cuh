@@ -33,7 +33,7 @@ namespace tdx {
 template <typename T, int N, int W_>
 struct Ek0FusedCfg {
     static constexpr int W = W_;                          // columns per strip == consumer threads per CTA
-    static constexpr int THREADS = W_ + 64;               // + one producer warp + one service warp
+    static constexpr int THREADS = W_ + 32;               // + one producer warp (which also does the n x n algebra)
     static constexpr int PADC = 16 / (int)sizeof(T);      // columns of left/right overlap (16-byte granularity of TMA)
     static constexpr int WP = W + 2 * PADC;
     static constexpr int STAGES = TDX_EK0_STAGES;
@@ -41,9 +41,10 @@ struct Ek0FusedCfg {
     static constexpr int AT_ROW = W + 2;                  // [left edge][W own][right edge]
     static constexpr int AT_ELEMS = 2 * 2 * AT_ROW;       // [slot][field][AT_ROW]
     static constexpr size_t BAR_BYTES = 128, RED_BYTES = 512;
+    static constexpr size_t TREE_BYTES = 3 * (size_t)W_ * sizeof(double);    // RowTree levels
     __host__ __device__ static constexpr size_t at_bytes() { return ((size_t)AT_ELEMS * sizeof(T) + 127) / 128 * 128; }
     __host__ __device__ static constexpr size_t stage_bytes() { return (size_t)STAGE_ELEMS * sizeof(T); }
-    __host__ __device__ static constexpr size_t total() { return BAR_BYTES + RED_BYTES + at_bytes() + STAGES * stage_bytes(); }
+    __host__ __device__ static constexpr size_t total() { return BAR_BYTES + RED_BYTES + TREE_BYTES + at_bytes() + STAGES * stage_bytes(); }
     static_assert((STAGE_ELEMS * sizeof(T)) % 16 == 0 && (WP * sizeof(T)) % 16 == 0, "TMA destinations stay 16-byte aligned");
     static_assert(W_ % 32 == 0 && W_ <= 256, "one row partial per consumer warp, at most eight");
 };
@@ -77,6 +78,7 @@ struct Ek0FusedArgs {
     RedPlan red_a, red_b;            // unit partials of the two phases
     double d_global;
     unsigned int col_blocks, chunks, total_strips;
+    int block0, nblocks, row_block;  // fhn: first global row block that touches the shard, number of row blocks of the shard, R
     int use_bulk;
     float keep_frac;                 // share of a strip's rows kept in L2 across the phase turn-arounds (>= 1: no hints)
     CommWait wait;
@@ -89,7 +91,56 @@ struct Ek0FusedArgs {
 
 struct StripGeom {
     int c0, wlen, r0, r1, dir;
+    int b0;                  // local index of the strip's first row block
 };
+
+// The error-norm and z^T z sums of the fhn kernel are formed per ROW BLOCK of R grid rows (aligned in GLOBAL row numbers)
+// and 256-column strip: every thread adds its column's terms of the block's rows in a balanced binary tree -- the same
+// additions whether the strip walks the rows upwards or downwards -- then the lanes go through the shuffle tree and the
+// warps through shared memory.  Strips are whole numbers of row blocks, so a block's partial is a fixed function of the
+// block's coordinates: independent of how many strips, CTAs or GPUs the grid is cut into.  R = 8 for large grids (one shuffle
+// tree per 8 rows costs nothing); small grids take R = 4, 2, 1 so that there are still enough strips to fill the device
+// (ek0_row_block: a function of the GLOBAL grid only, i.e. the same on every rank count).
+constexpr int kMaxRowBlock = 8;
+
+__host__ __device__ inline int ek0_row_block(long long global_rows, int col_blocks) {
+    for (int r = kMaxRowBlock; r > 1; r >>= 1)
+        if (((global_rows + r - 1) / r) * col_blocks >= 512) return r;
+    return 1;
+}
+
+// Streaming balanced tree over the kRowBlock leaves of a block (binary counter).  The three pending partial sums of a thread
+// live in shared memory ([level][thread]; registers are the scarce resource of the kernel), the leaf position comes from the row.
+// Missing leaves (grid / shard ends inside a block) count as +0.0, which is exact.
+template <int W>
+struct RowTree {
+    double* lv;              // this thread's level-0 slot; levels are W doubles apart
+    __device__ __forceinline__ void reset() { lv[0] = lv[W] = lv[2 * W] = 0.0; }
+    // leaf number ``c`` (0 .. R - 1 in walking order, R = 1, 2, 4 or 8) with value v; returns true when the block is complete,
+    // ``v`` then holds the block's sum
+    __device__ __forceinline__ bool push(int c, double& v, int R) {
+        if (R == 1) return true;
+        if (!(c & 1)) {
+            lv[0] = v;
+            return false;
+        }
+        v += lv[0];
+        if (R == 2) return true;
+        if (!(c & 2)) {
+            lv[W] = v;
+            return false;
+        }
+        v += lv[W];
+        if (R == 4) return true;
+        if (!(c & 4)) {
+            lv[2 * W] = v;
+            return false;
+        }
+        v += lv[2 * W];
+        return true;
+    }
+};
+static_assert(kMaxRowBlock == 8, "RowTree has three levels");
 
 // calibration, the single stacked QR, gain, factor update (one thread, fp64)   ek0.py:123-140,175,182
 template <typename T, int N>
@@ -138,14 +189,17 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 }
 
 template <int W>
-__device__ __forceinline__ StripGeom strip_geom(const Geo& g, unsigned strip, unsigned col_blocks, unsigned chunks,
-                                                bool has_lo, bool has_hi) {
+__device__ __forceinline__ StripGeom strip_geom(const Geo& g, unsigned strip, unsigned col_blocks, unsigned chunks, int block0,
+                                                int nblocks, int kRowBlock, bool has_lo, bool has_hi) {
     StripGeom s;
     const unsigned chunk = strip / col_blocks, cb = strip - chunk * col_blocks;
     s.c0 = (int)cb * W;
     s.wlen = min(W, g.cols - s.c0);
-    s.r0 = (int)(((long long)chunk * g.rows) / chunks);
-    s.r1 = (int)(((long long)(chunk + 1) * g.rows) / chunks);
+    // whole row blocks (aligned in global rows), clipped to the shard
+    const int bl = (int)(((long long)chunk * nblocks) / chunks), bh = (int)(((long long)(chunk + 1) * nblocks) / chunks);
+    s.b0 = bl;
+    s.r0 = max(0, (int)((long long)(block0 + bl) * kRowBlock - g.grow0));
+    s.r1 = min(g.rows, (int)((long long)(block0 + bh) * kRowBlock - g.grow0));
     // Vertically adjacent strips walk in opposite directions: they read the row they share (one's halo row is the
     // other's edge row) at about the same time, so the second read is an L2 hit.  A strip under the shard's lower /
     // upper edge walks towards that edge in phase A so that the neighbour GPU's halo row is needed LAST.
@@ -202,7 +256,7 @@ __device__ __forceinline__ double ek0_gain(const Consts<double, N>& cd, const do
 
 // ---------------------------------------------------------------------------------------------------------------------
 // Pieces shared by the two fused kernels (fhn strips / 1-d tile ranges).  Thread roles: consumers [0, CONS), the producer
-// warp [CONS, CONS + 32), the service warp [CONS + 32, CONS + 64).
+// warp [CONS, CONS + 32).
 // ---------------------------------------------------------------------------------------------------------------------
 template <typename T, int N>
 struct Ek0CtaState {
@@ -211,7 +265,7 @@ struct Ek0CtaState {
     int cur, out;                    // ring slots of the attempt's input / output state (cur < 0: stop)
     int flag, ok;
     unsigned long long epoch0;
-    uint64_t m1_bar;                 // the service warp has published m1[attempt & 1]
+    uint64_t m1_bar;                 // the producer warp has published m1[attempt & 1]
     double m1[2][kMaxN + 1];
     double timed_out;                // the wait for the global sum of z^2 timed out
 };
@@ -254,27 +308,35 @@ __device__ __forceinline__ bool ek0_attempt_begin(const Ek0FusedArgs<T, N>& a, E
     return sh.cur >= 0;
 }
 
-// the service warp's attempt (lane 0): m1 of the attempt's input factor for every CTA; in CTA 0 additionally the stacked QR
-// for the attempt's output factor as soon as the global sum of z^2 is known
+// The n x n algebra of an attempt is done by lane 0 of the PRODUCER warp while it has nothing to issue:
+//  * after the phase A loads are on their way: M1 of the attempt's input factor (every CTA; the consumers need it for the gain
+//    right after the barrier in the middle of the attempt);
+//  * after the phase B loads are on their way, in CTA 0 only: the ONE stacked QR for the attempt's output factor
+//    (ek0.py:175,138), as soon as the global sum of z^2 is known.  It overlaps the consumers' last rows and the end barrier.
 template <typename T, int N>
-__device__ __forceinline__ void ek0_service(const Ek0FusedArgs<T, N>& a, Ek0CtaState<T, N>& sh, const Consts<double, N>& cd_shared,
-                                            int att, int lane) {
+__device__ __forceinline__ void ek0_service_m1(const Ek0FusedArgs<T, N>& a, Ek0CtaState<T, N>& sh, const Consts<double, N>& cd,
+                                               int att, int lane) {
     if (lane == 0) {
-        const unsigned long long tmo = a.wait.timeout_ns;
-        const T* Cl_in = a.Cl_ring[sh.cur];
-        const Consts<double, N> cd = cd_shared;      // thread 0 rebuilds the shared copy at the top of the next attempt
         // the factor this attempt starts from was written by the previous attempt's QR (the first attempt's by an earlier launch)
-        bool ok = att == 0 || spin_until_gpu(a.cl_flag, a.cl_seq + (unsigned long long)att, tmo);
-        ek0_m1_column<T, N>(cd, Cl_in, sh.m1[att & 1]);
+        const bool ok = att == 0 || spin_until_gpu(a.cl_flag, a.cl_seq + (unsigned long long)att, a.wait.timeout_ns);
+        ek0_m1_column<T, N>(cd, a.Cl_ring[sh.cur], sh.m1[att & 1]);
         if (!ok) sh.m1[att & 1][1] = nan("");
         mbar_arrive(&sh.m1_bar);
-        if (blockIdx.x == 0) {
-            ok = spin_until_gpu(a.mid_flag, a.mid_seq + (unsigned long long)att, tmo);
-            const double z_sq = ok ? __ldcg(&a.mid->z_sq) : nan("");
-            ek0_mid_compute<T, N>(cd, Cl_in, z_sq, a.d_global, a.Cl_ring[sh.out], a.err_ring[sh.out], a.mid);
-            __threadfence();
-            st_release_gpu(a.cl_flag, a.cl_seq + (unsigned long long)att + 1ull);
-        }
+    }
+    __syncwarp();
+}
+
+template <typename T, int N>
+__device__ __forceinline__ void ek0_service_qr(const Ek0FusedArgs<T, N>& a, Ek0CtaState<T, N>& sh, const Consts<double, N>& cd,
+                                               int att, int lane) {
+    if (lane == 0 && blockIdx.x == 0) {
+        const bool ok = spin_until_gpu(a.mid_flag, a.mid_seq + (unsigned long long)att, a.wait.timeout_ns);
+        const double z_sq = ok ? __ldcg(&a.mid->z_sq) : nan("");
+        TDX_STAMP(a.partials, att, 5);
+        ek0_mid_compute<T, N>(cd, a.Cl_ring[sh.cur], z_sq, a.d_global, a.Cl_ring[sh.out], a.err_ring[sh.out], a.mid);
+        TDX_STAMP(a.partials, att, 6);
+        __threadfence();
+        st_release_gpu(a.cl_flag, a.cl_seq + (unsigned long long)att + 1ull);
     }
     __syncwarp();
 }
@@ -297,7 +359,7 @@ __device__ __forceinline__ double ek0_mid_barrier(const Ek0FusedArgs<T, N>& a, E
     }
     if (tc == 0) {
         sh.timed_out = spin_until_gpu(a.mid_flag, a.mid_seq + (unsigned long long)att, a.wait.timeout_ns) ? 0.0 : 1.0;
-        mbar_wait(&sh.m1_bar, (unsigned)att & 1u);           // the service warp's m1 of this attempt
+        mbar_wait(&sh.m1_bar, (unsigned)att & 1u);           // the producer warp's m1 of this attempt
     }
     csync();
     // a dead peer must not hang the GPU and must not go unnoticed: NaN state, NaN norm, the controller / host raises
@@ -329,18 +391,18 @@ __device__ __forceinline__ void ek0_end_barrier(const Ek0FusedArgs<T, N>& a, Ek0
 }
 
 // Threads [0, W): consumers, thread t owns column c0 + t of both fields.  Threads [W, W + 32): the producer warp.
-// Threads [W + 32, W + 64): the service warp.
 template <typename T, int N, int W, bool kCtl = false>
 __global__ void __maxnreg__(TDX_EK0_MAXREG) ek0_fused_fhn_kernel(const __grid_constant__ Ek0FusedArgs<T, N> a) {
     using Cfg = Ek0FusedCfg<T, N, W>;
-    using CSync = NamedSync<1, W>;                         // the consumers' barrier (producer and service warps never join)
+    using CSync = NamedSync<1, W>;                         // the consumers' barrier (the producer warp never joins)
     constexpr int PADC = Cfg::PADC, WP = Cfg::WP, S = Cfg::STAGES, AT_ROW = Cfg::AT_ROW;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);                                   // [S] data has landed
     uint64_t* empty = full + S;                                                               // [S] consumers are done
     double* s_red = reinterpret_cast<double*>(smem_raw + Cfg::BAR_BYTES);                     // see kEk0Red*
-    T* s_at = reinterpret_cast<T*>(smem_raw + Cfg::BAR_BYTES + Cfg::RED_BYTES);               // [2][2][AT_ROW]
-    T* s_stage = reinterpret_cast<T*>(smem_raw + Cfg::BAR_BYTES + Cfg::RED_BYTES + Cfg::at_bytes());
+    double* s_tree = reinterpret_cast<double*>(smem_raw + Cfg::BAR_BYTES + Cfg::RED_BYTES);   // [3][W]
+    T* s_at = reinterpret_cast<T*>(smem_raw + Cfg::BAR_BYTES + Cfg::RED_BYTES + Cfg::TREE_BYTES);               // [2][2][AT_ROW]
+    T* s_stage = reinterpret_cast<T*>(smem_raw + Cfg::BAR_BYTES + Cfg::RED_BYTES + Cfg::TREE_BYTES + Cfg::at_bytes());
     __shared__ Ek0CtaState<T, N> sh;
 
     const Geo& g = a.g;
@@ -377,10 +439,6 @@ __global__ void __maxnreg__(TDX_EK0_MAXREG) ek0_fused_fhn_kernel(const __grid_co
         const T* halo_lo = has_lo ? a.halo_lo + (long long)(hseq & 1ull) * a.halo_parity_stride : nullptr;
         const T* halo_hi = has_hi ? a.halo_hi + (long long)(hseq & 1ull) * a.halo_parity_stride : nullptr;
 
-        if (tc >= W + 32) {
-            ek0_service<T, N>(a, sh, cdr, att, tc - (W + 32));
-            continue;
-        }
         if (tc >= W) {
             // ---- producer warp: walks the same (strip, row) enumeration as the consumers, up to S rows ahead ------------
             // Every item owns ring slot q % S (items beyond the shard simply load nothing).  The 2 n row segments of a
@@ -396,7 +454,7 @@ __global__ void __maxnreg__(TDX_EK0_MAXREG) ek0_fused_fhn_kernel(const __grid_co
 #pragma unroll 1
                 for (int kk = 0; kk < ns; ++kk) {
                     const int k = phase ? ns - 1 - kk : kk;
-                    StripGeom s = strip_geom<W>(g, blockIdx.x + (unsigned)k * gridDim.x, a.col_blocks, a.chunks, has_lo, has_hi);
+                    StripGeom s = strip_geom<W>(g, blockIdx.x + (unsigned)k * gridDim.x, a.col_blocks, a.chunks, a.block0, a.nblocks, a.row_block, has_lo, has_hi);
                     if (phase) s.dir = -s.dir;
                     const int L = s.r1 - s.r0 + 2;
                     const int gs = max(s.c0 - PADC, 0), ge = min(s.c0 + W + PADC, g.cols);
@@ -431,7 +489,9 @@ __global__ void __maxnreg__(TDX_EK0_MAXREG) ek0_fused_fhn_kernel(const __grid_co
                         }
                     }
                 }
+                if (phase == 0) ek0_service_m1<T, N>(a, sh, cdr, att, lane);
             }
+            ek0_service_qr<T, N>(a, sh, cdr, att, lane);
             continue;
         }
 
@@ -444,7 +504,8 @@ __global__ void __maxnreg__(TDX_EK0_MAXREG) ek0_fused_fhn_kernel(const __grid_co
                 pack_halo_part<T, N, CSync, kCtl>(g, c, mean_in, a.pack, a.pack.seq + (unsigned long long)att, part, csync);
 
         bool halos_ready = false, poisoned = false;
-        int pending_unit = -1, first_unit = -1;      // thread 0: the row whose warp sums wait in s_rowred for the next barrier
+        int pending_unit = -1, first_unit = -1;      // CTA-uniform: the row block whose warp sums wait in s_rowred for the next barrier
+        int pending_slot = 0;
         const uint64_t pol_keep = l2_policy_evict_last(), pol_stream = l2_policy_evict_first();
         const T inv_dx2 = (T)g.prm[0], pa = (T)g.prm[1], pb = (T)g.prm[2], pk = (T)g.prm[3], inv_tau = (T)g.prm[5];
         const int wq = tc >> 5, lq = tc & 31;
@@ -463,21 +524,26 @@ __global__ void __maxnreg__(TDX_EK0_MAXREG) ek0_fused_fhn_kernel(const __grid_co
             constexpr bool kUpdate = decltype(update_tag)::value;
             constexpr int NK = kUpdate ? N : 2;                 // rows of the predicted mean kept for the row being finalised
             const bool reduces = !kUpdate || c.want_norm || (kCtl && a.reduce_b.world > 0);
-            auto flush_row_partial = [&](unsigned cq_prev) {
-                if (tc == 0 && pending_unit >= 0) {
-                    const double* ws = s_rowred + (cq_prev & 1u) * 8;
-                    double b = 0.0;
+            // after a barrier that follows a block's warp sums: the block's partial = the warp sums in warp order
+            auto flush_block_partial = [&]() {
+                if (pending_unit >= 0) {
+                    if (tc == 0) {
+                        const double* ws = s_rowred + (pending_slot & 1) * 8;
+                        double b = 0.0;
 #pragma unroll
-                    for (int i = 0; i < W / 32; ++i) b += ws[i];
-                    unit[pending_unit] = b;
+                        for (int i = 0; i < W / 32; ++i) b += ws[i];
+                        unit[pending_unit] = b;
+                    }
                     pending_unit = -1;
                 }
             };
+            RowTree<W> tree{s_tree + tc};
+            const int kRowBlock = a.row_block;
 #pragma unroll 1
             for (int kk = 0; kk < ns; ++kk) {
                 const int k = kUpdate ? ns - 1 - kk : kk;
                 const unsigned strip = blockIdx.x + (unsigned)k * gridDim.x;
-                StripGeom s = strip_geom<W>(g, strip, a.col_blocks, a.chunks, has_lo, has_hi);
+                StripGeom s = strip_geom<W>(g, strip, a.col_blocks, a.chunks, a.block0, a.nblocks, a.row_block, has_lo, has_hi);
                 const int cb = (int)(strip % a.col_blocks);
                 if (kUpdate) s.dir = -s.dir;
                 const int L = s.r1 - s.r0 + 2;
@@ -491,6 +557,9 @@ __global__ void __maxnreg__(TDX_EK0_MAXREG) ek0_fused_fhn_kernel(const __grid_co
                 T at_m1[2] = {}, at_m2[2] = {}, hs_m1[2] = {}, mp_m1[2][NK] = {};
                 bool first_replicated = false;
                 T* out_ptr = mean_out + ((long long)(rr - s.dir) * g.cols + col);      // row being finalised, field 0
+                if (reduces) tree.reset();
+                // local index of the row block the first finalised row belongs to
+                int blk = (int)((g.grow0 + (s.dir > 0 ? s.r0 : s.r1 - 1)) / kRowBlock) - a.block0;
                 // the rows phase B writes last are the rows the NEXT attempt's phase A reads first -> keep those in L2
                 const int keep_from = (kUpdate && hints) ? L - (int)ceilf(a.keep_frac * (float)(s.r1 - s.r0)) : L;
 #pragma unroll 1
@@ -555,7 +624,7 @@ __global__ void __maxnreg__(TDX_EK0_MAXREG) ek0_fused_fhn_kernel(const __grid_co
                     }
                     csync();              // publishes the row; every consumer has read the stage -> hand it back
                     if (tc == 0) mbar_arrive(empty + stage);
-                    if (reduces) flush_row_partial(cq - 1u);
+                    if (reduces) flush_block_partial();
                     T hs_cur[2];
 #pragma unroll
                     for (int f = 0; f < 2; ++f) hs_cur[f] = at_row[f * AT_ROW + tc] + at_row[f * AT_ROW + tc + 2];
@@ -599,11 +668,23 @@ __global__ void __maxnreg__(TDX_EK0_MAXREG) ek0_fused_fhn_kernel(const __grid_co
                             }
                         }
                         if (reduces) {
-                            const double ws = warp_sum(term);
-                            if (lq == 0) s_rowred[(cq & 1u) * 8 + wq] = ws;
-                            if (tc == 0) {
-                                pending_unit = (rr - s.dir) * (int)a.col_blocks + cb;
+                            // leaf number of the finalised row in walking order inside its (global) row block
+                            const int pos = (int)((g.grow0 + (rr - s.dir)) & (kRowBlock - 1));
+                            int leaf = s.dir > 0 ? pos : (kRowBlock - 1 - pos);
+                            bool done = tree.push(leaf, term, kRowBlock);
+                            // the strip's last row ends inside a block (grid / shard end): the missing leaves are zeros
+                            if (i == L - 1)
+                                while (!done) {
+                                    term = 0.0;
+                                    done = tree.push(++leaf, term, kRowBlock);
+                                }
+                            if (done) {
+                                const double ws = warp_sum(term);
+                                pending_slot ^= 1;
+                                if (lq == 0) s_rowred[(pending_slot & 1) * 8 + wq] = ws;
+                                pending_unit = blk * (int)a.col_blocks + cb;
                                 if (first_unit < 0) first_unit = pending_unit;
+                                blk += s.dir;
                             }
                         }
                     }
@@ -619,7 +700,8 @@ __global__ void __maxnreg__(TDX_EK0_MAXREG) ek0_fused_fhn_kernel(const __grid_co
             }
             if (reduces) {
                 csync();
-                flush_row_partial(cq - 1u);
+                flush_block_partial();
+                csync();
                 if (tc == 0 && poisoned && first_unit >= 0) unit[first_unit] = nan("");   // stale halos: fail the attempt everywhere
             }
         };
@@ -638,11 +720,14 @@ __global__ void __maxnreg__(TDX_EK0_MAXREG) ek0_fused_fhn_kernel(const __grid_co
         }
 #endif
         // ---- phase A ------------------------------------------------------------------------------------------------
+        if (tc == 0) TDX_STAMP(a.partials, att, 0);
         run_phase(std::false_type{}, K, a.red_a.unit);
 #ifdef TDX_EK0_TIMING
         if (tc == 0) stamps[1] = (double)global_timer_ns();
 #endif
+        if (tc == 0) TDX_STAMP(a.partials, att, 1);
         const double err_cal = ek0_mid_barrier<T, N>(a, sh, cdr, att, s_red, K, csync);
+        if (tc == 0) TDX_STAMP(a.partials, att, 2);
 #ifdef TDX_EK0_TIMING
         if (tc == 0) stamps[2] = (double)global_timer_ns();
 #endif
@@ -651,8 +736,10 @@ __global__ void __maxnreg__(TDX_EK0_MAXREG) ek0_fused_fhn_kernel(const __grid_co
 #ifdef TDX_EK0_TIMING
         if (tc == 0) stamps[3] = (double)global_timer_ns();
 #endif
+        if (tc == 0) TDX_STAMP(a.partials, att, 3);
         if (kCtl) fence_proxy_async_global();          // the next attempt's TMA loads read what this thread just stored
         ek0_end_barrier<T, N, kCtl>(a, sh, c, att, err_cal, s_red, csync);
+        if (tc == 0) TDX_STAMP(a.partials, att, 4);
     }
 }
 
@@ -667,7 +754,7 @@ __global__ void __maxnreg__(TDX_EK0_MAXREG) ek0_fused_fhn_kernel(const __grid_co
 template <typename T, int N>
 struct Ek0ChainCfg {
     static constexpr int STAGES = 4;
-    static constexpr int THREADS = kThreads + 64;                     // consumers + producer warp + service warp
+    static constexpr int THREADS = kThreads + 32;                     // consumers + producer warp (which also does the n x n algebra)
     static constexpr int STAGE_ELEMS = N * kThreads;                 // [derivative][thread]
     static constexpr size_t BAR_BYTES = 128, RED_BYTES = 512;
     __host__ __device__ static constexpr size_t at_bytes(int at_elems) { return ((size_t)at_elems * sizeof(T) + 127) / 128 * 128; }
@@ -727,10 +814,6 @@ __global__ void __maxnreg__(72) ek0_fused_chain_kernel(const __grid_constant__ E
         const T* halo_lo = a.halo_lo ? a.halo_lo + (long long)(hseq & 1ull) * a.halo_parity_stride : nullptr;
         const T* halo_hi = a.halo_hi ? a.halo_hi + (long long)(hseq & 1ull) * a.halo_parity_stride : nullptr;
 
-        if (tid >= kThreads + 32) {
-            ek0_service<T, N>(a, sh, cdr, att, tid - (kThreads + 32));
-            continue;
-        }
         if (tid >= kThreads) {
             // ---- producer warp: one tile per ring slot; per tile NF * n contiguous row segments -------------------------
             const int lane = tid - kThreads;
@@ -766,7 +849,9 @@ __global__ void __maxnreg__(72) ek0_fused_chain_kernel(const __grid_constant__ E
                         if (lane == 0) mbar_arrive(full + stage);
                     }
                 }
+                if (phase == 0) ek0_service_m1<T, N>(a, sh, cdr, att, lane);
             }
+            ek0_service_qr<T, N>(a, sh, cdr, att, lane);
             continue;
         }
 

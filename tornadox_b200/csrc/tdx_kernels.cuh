@@ -317,7 +317,7 @@ __device__ inline void ctl_finish_attempt(StepCtl* ctl, double total, double d_g
             // the next attempt writes ring slot (cur + 1) % nbuf, which holds accepted state number accepted + 1 - nbuf
             const long long need = ctl->accepted + 1 - (long long)ctl->nbuf;
             const unsigned long long t0 = global_timer_ns();
-            while (need >= 0 && (long long)fd->consumed < need) {
+            while (need >= 0 && (long long)fd->consumed <= need) {
                 if (fd->abort != 0ull || global_timer_ns() - t0 > (unsigned long long)(ctl->wait_timeout_ns > 0 ? 16 * ctl->wait_timeout_ns : 64000000000ll)) {
                     ctl->done = 1;
                     if (fd->abort == 0ull && ctl->failed == 0) ctl->failed = 2;
@@ -453,26 +453,28 @@ __global__ void __launch_bounds__(kThreads, DekSmem<T, N>::MIN_BLOCKS) dek1_kern
         if (kComm && a.pack.enabled)
             for (int part = (int)blockIdx.x; part < 2 * kPackCtas; part += (int)gridDim.x)   // a small grid takes several parts per CTA
                 pack_halo_part<T, N, FullSync, kCtl>(g, c, mean_in, a.pack, a.pack.seq + (unsigned long long)att, part);
+        if (threadIdx.x == 0) TDX_STAMP(a.partials, att, 0);
         bool halos_ready = false;          // CTA-uniform: the arrival flags have been seen
         bool poisoned = false;             // CTA-uniform: a halo wait timed out
         unsigned tile = kComm ? (gridDim.x - 1u - blockIdx.x) : blockIdx.x;
-        double cta_acc = 0.0;              // thread 0, per-CTA partial sums only (no unit partials)
-        int pending_unit = -1;             // thread 0: the tile whose warp sums wait in s_red for the next barrier
+        const bool unit_mode = a.red.unit != nullptr;
+        double legacy_acc = 0.0;           // per-thread running sum (launches over a part of the tiles: per-CTA partials)
+        int pending_unit = -1;             // CTA-uniform: the tile whose warp sums wait in s_red for the next barrier
         bool cur_bulk = false;
         if (tile < a.num_tiles) cur_bulk = stage_in(tile_coord<Shape>(g, a.ranges.tile(tile), a.tiles_x), 0);
 
-        // thread 0, after a barrier that follows the tile's warp sums: the tile's partial = the 8 warp sums in warp order
+        // after a barrier that follows the tile's warp sums: the tile's partial = the 8 warp sums in a fixed tree; one lane of
+        // a warp that changes from tile to tile does it (no warp is always the one the next barrier waits for)
         auto flush_tile_partial = [&](unsigned it_prev) {
-            if (threadIdx.x == 0 && pending_unit >= 0) {
-                const double* ws = s_red + (it_prev & 1u) * kWarps;
-                double b = 0.0;
-#pragma unroll
-                for (int i = 0; i < kWarps; ++i) b += ws[i];
-                if (a.red.unit) a.red.unit[pending_unit] = b;
-                else cta_acc += b;
+            if (pending_unit >= 0) {
+                if (threadIdx.x == ((it_prev & (unsigned)(kWarps - 1)) << 5)) {
+                    const double* ws = s_red + (it_prev & 1u) * kWarps;
+                    a.red.unit[pending_unit] = ((ws[0] + ws[1]) + (ws[2] + ws[3])) + ((ws[4] + ws[5]) + (ws[6] + ws[7]));
+                }
                 pending_unit = -1;
             }
         };
+        static_assert(kWarps == 8, "the tile partial adds eight warp sums");
 
         unsigned it = 0;
         for (; tile < a.num_tiles; ++it) {
@@ -494,7 +496,7 @@ __global__ void __launch_bounds__(kThreads, DekSmem<T, N>::MIN_BLOCKS) dek1_kern
                 front_eval<IVP, T, N>(g, c, cur, fr, s_at, mp, fx, jac);
                 raw0 = fr.raw[0];
             }
-            flush_tile_partial(it - 1u);       // the barrier inside front_eval ordered the previous tile's warp sums
+            if (unit_mode) flush_tile_partial(it - 1u);   // the barrier inside front_eval ordered the previous tile's warp sums
 
             // (2) start streaming the next tile's factor blocks into the other slot
             const unsigned next = tile + gridDim.x;
@@ -587,12 +589,7 @@ __global__ void __launch_bounds__(kThreads, DekSmem<T, N>::MIN_BLOCKS) dek1_kern
                     ratio_sq = ratio * ratio;                              // step.py:101-104
                 }
             }
-            if (c.want_norm || kCtl) {
-                // the tile's share of the norm: lanes through the shuffle tree, the warps through shared memory (next barrier)
-                const double ws = warp_sum(ratio_sq);
-                if (lane == 0) s_red[(it & 1u) * kWarps + w] = ws;
-                if (threadIdx.x == 0) pending_unit = (int)tile_id;
-            }
+            if (!unit_mode) legacy_acc += ratio_sq;
 
             // (4) stream the updated blocks back
             if (bulk_out) {
@@ -625,6 +622,13 @@ __global__ void __launch_bounds__(kThreads, DekSmem<T, N>::MIN_BLOCKS) dek1_kern
                 __syncwarp();
                 next_bulk = stage_in(tile_coord<Shape>(g, a.ranges.tile(next), a.tiles_x), 0);
             }
+            if (unit_mode && (c.want_norm || kCtl)) {
+                // the tile's share of the norm (after the stores are on their way): lanes through the shuffle tree, the warps
+                // through shared memory after the next barrier
+                const double ws = warp_sum(ratio_sq);
+                if (lane == 0) s_red[(it & 1u) * kWarps + w] = ws;
+                pending_unit = (int)tile_id;
+            }
             tile = next;
             cur_bulk = next_bulk;
         }
@@ -637,6 +641,7 @@ __global__ void __launch_bounds__(kThreads, DekSmem<T, N>::MIN_BLOCKS) dek1_kern
             a.partials[1024 + 2 * blockIdx.x + 1] = (double)smid;
         }
 #endif
+        if (threadIdx.x == 0) TDX_STAMP(a.partials, att, 1);
         if (!(c.want_norm || kCtl)) break;            // ConstantSteps without a controller: nothing to reduce
 
         // ---- end of the attempt: everything this CTA wrote must be visible before it reports in ------------------------
@@ -645,25 +650,27 @@ __global__ void __launch_bounds__(kThreads, DekSmem<T, N>::MIN_BLOCKS) dek1_kern
             fence_proxy_async_global();               // ... and ordinary stores are ordered before the next attempt's TMA loads
         }
         __syncthreads();
-        flush_tile_partial(it - 1u);
+        if (unit_mode) flush_tile_partial(it - 1u);
+        __syncthreads();
         if (threadIdx.x == 0 && poisoned) {           // stale halos: the attempt must not be accepted anywhere
-            if (a.red.unit) a.red.unit[a.ranges.tile(kComm ? (gridDim.x - 1u - blockIdx.x) : blockIdx.x)] = nan("");
-            else cta_acc = nan("");
+            if (unit_mode) a.red.unit[a.ranges.tile(kComm ? (gridDim.x - 1u - blockIdx.x) : blockIdx.x)] = nan("");
+            else legacy_acc = nan("");
         }
         double total = 0.0;
         bool fin = false;                             // thread 0 of the last CTA
-        if (a.red.unit != nullptr) {
+        if (unit_mode) {
             if (cta_arrive_last(a.ticket, &s_flag)) {
                 total = reduce_units(a.red, kComm ? &a.reduce : nullptr, a.reduce.seq + (unsigned long long)att, s_red);
                 fin = threadIdx.x == 0;
                 if (fin && c.want_norm && a.out_sum) *a.out_sum = total;
             }
         } else {
-            fin = grid_sum_cta(cta_acc, s_red, a.partials, a.ticket, c.want_norm ? a.out_sum : nullptr);
+            fin = grid_sum_cta(legacy_acc, s_red, a.partials, a.ticket, c.want_norm ? a.out_sum : nullptr);
         }
         if constexpr (kCtl) {
             if (fin) ctl_finish_attempt(a.ctl, total, a.d_global, s_epoch0 + (unsigned long long)att + 1ull);
         }
+        if (threadIdx.x == 0) TDX_STAMP(a.partials, att, 2);
     }
     if (lane == 0) bulk_wait_read0();
 }

@@ -177,11 +177,16 @@ inline cudaError_t persistent_grid(size_t smem, long long tiles, int reserve, un
         case IVP_WAVE1D: { using IVP = Wave1d<T>; __VA_ARGS__ } break;           \
         case IVP_THREEBODY: { using IVP = ThreeBody<T>; __VA_ARGS__ } break;     \
         case IVP_PLEIADES: { using IVP = Pleiades<T>; __VA_ARGS__ } break;       \
+        case IVP_EXTERNAL: { using IVP = External<T>; __VA_ARGS__ } break;       \
         default: return -1;                                                      \
     }
 
 inline bool force_comm_kernel() {
     static const bool on = std::getenv("TDX_FORCE_COMM_KERNEL") != nullptr;   // experiments only
+    return on;
+}
+inline bool force_cta_partials() {
+    static const bool on = std::getenv("TDX_CTA_PARTIALS") != nullptr;        // A/B: per-CTA partial sums instead of per-tile ones
     return on;
 }
 
@@ -245,7 +250,8 @@ struct Launch {
             a.reduce = ws.reduce;
             // a launch over all tiles leaves one partial per tile (sharding-independent summation); a launch over a part of
             // them (interior / rim) falls back to per-CTA partials
-            const bool whole = a.num_tiles == a.tiles_x * tiles_y && (long long)a.num_tiles <= ws.unit_cap;
+            const bool whole = a.num_tiles == a.tiles_x * tiles_y && (long long)a.num_tiles <= ws.unit_cap &&
+                               !(force_cta_partials() && !ctl && ws.reduce.world == 0);
             a.red = whole ? tile_red_plan<Shape>(g, ws.unit_a, a.tiles_x, tiles_y) : RedPlan{};
             if (a.num_tiles == 0u) {
                 if (h.want_norm) TDX_CUDA_TRY(cudaMemsetAsync(out_sum, 0, sizeof(double), st));
@@ -413,6 +419,7 @@ struct Launch {
                 case IVP_WAVE1D: return launch_chain<Wave1d<T>, kCtl>(g, a, ws, st);
                 case IVP_THREEBODY: return launch_chain<ThreeBody<T>, kCtl>(g, a, ws, st);
                 case IVP_PLEIADES: return launch_chain<Pleiades<T>, kCtl>(g, a, ws, st);
+                case IVP_EXTERNAL: return launch_chain<External<T>, kCtl>(g, a, ws, st);
                 default: return kNoFusedKernel;
             }
         }
@@ -421,16 +428,22 @@ struct Launch {
         unsigned resident = 0;
         TDX_CUDA_TRY(persistent_grid<kern>(Cfg::total(), 1LL << 40, 0, resident, Cfg::THREADS));
         a.col_blocks = (unsigned)((g.cols + W - 1) / W);
+        // strips are whole row blocks (R grid rows, aligned in global row numbers): see RowTree
+        const int kRowBlock = ek0_row_block(g.grows, (int)a.col_blocks);
+        a.row_block = kRowBlock;
+        a.block0 = (int)(g.grow0 / kRowBlock);
+        a.nblocks = (int)((g.grow0 + g.rows + kRowBlock - 1) / kRowBlock) - a.block0;
         unsigned chunks = resident / a.col_blocks;
         if (chunks < 1u) chunks = 1u;
-        if (chunks > (unsigned)g.rows) chunks = (unsigned)g.rows;
+        if (chunks > (unsigned)a.nblocks) chunks = (unsigned)a.nblocks;
         a.chunks = chunks;
         a.total_strips = a.col_blocks * chunks;
         const unsigned grid = a.total_strips < resident ? a.total_strips : resident;
-        // one unit partial per (grid row, column block) and phase
-        const long long units = (long long)g.rows * a.col_blocks;
+        // one unit partial per (row block, column block) and phase
+        const long long units = (long long)a.nblocks * a.col_blocks;
         if (units > ws.unit_cap) return (int)cudaErrorInvalidValue;
-        a.red_a = RedPlan{ws.unit_a, (unsigned)units, (unsigned long long)g.grow0 * a.col_blocks, (unsigned long long)g.grows * a.col_blocks};
+        a.red_a = RedPlan{ws.unit_a, (unsigned)units, (unsigned long long)a.block0 * a.col_blocks,
+                          (unsigned long long)((g.grows + kRowBlock - 1) / kRowBlock) * a.col_blocks};
         a.red_b = a.red_a;
         a.red_b.unit = ws.unit_b;
         // L2 residency hints: keep as many rows of every strip as fit the budget; everything fits -> no hints at all

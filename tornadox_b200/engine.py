@@ -24,6 +24,16 @@ KernelSpec = namedtuple("KernelSpec", "kind params grid_rows grid_cols n_fields 
 _RED_CHUNKS = 16      # kRedChunks in csrc/tdx_device.cuh
 
 
+def _ek0_row_block(global_rows, col_blocks):
+    """Row-block height of the fused fhn_2d KroneckerEK0 kernel's sums (ek0_row_block in csrc/tdx_ek0_fused.cuh)."""
+    r = 8
+    while r > 1:
+        if -(-global_rows // r) * col_blocks >= 512:
+            return r
+        r //= 2
+    return 1
+
+
 def _chunk_aligned_bounds(spec, world):
     """Shard boundaries on the chunk grid of the kernels' reductions (see ``reduction_is_sharding_independent``), or None
     if the problem's size does not allow it.  The shards then differ in size by at most one chunk's rounding."""
@@ -35,8 +45,13 @@ def _chunk_aligned_bounds(spec, world):
         bounds = [((r * per) * rows) // _RED_CHUNKS for r in range(world + 1)]
         tiles_x = -(-spec.grid_cols // 32)
         tiles_y = -(-rows // 4)
+        col_blocks = -(-spec.grid_cols // 256)
+        rb = _ek0_row_block(rows, col_blocks)
+        blocks_y = -(-rows // rb)
         for r, b in enumerate(bounds[1:-1], start=1):
             if b % 4 or (b // 4) * tiles_x != ((r * per) * tiles_y * tiles_x) // _RED_CHUNKS:
+                return None
+            if b % rb or (b // rb) * col_blocks != ((r * per) * blocks_y * col_blocks) // _RED_CHUNKS:
                 return None
     else:
         tile = 256 if spec.n_fields == 1 else 128
@@ -89,10 +104,12 @@ def reduction_is_sharding_independent(spec, world, chunks=16):
         tiles_x = -(-spec.grid_cols // tile_cols)
         tiles_y = -(-spec.grid_rows // tile_rows)
         col_blocks = -(-spec.grid_cols // strip_cols)
+        row_block = _ek0_row_block(spec.grid_rows, col_blocks)
+        blocks_y = -(-spec.grid_rows // row_block)
         for b in bounds:
             if b % tile_rows or not on_chunk_boundary((b // tile_rows) * tiles_x, tiles_y * tiles_x):
                 return False
-            if not on_chunk_boundary(b * col_blocks, spec.grid_rows * col_blocks):
+            if b % row_block or not on_chunk_boundary((b // row_block) * col_blocks, blocks_y * col_blocks):
                 return False
         return True
     tile = 256 if spec.n_fields == 1 else 128

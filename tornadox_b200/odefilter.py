@@ -169,6 +169,7 @@ class ODEFilter(ABC):
             try:
                 store(means, follower.ring["means"][0], follower.copy_stream)
                 store(factors, follower.ring["factors"][0], follower.copy_stream)
+                follower.release_when_copied(0)
                 for j, t, attempts, slot in follower.states():
                     times.append(t)
                     store(means, follower.ring["means"][slot], follower.copy_stream)
@@ -380,6 +381,8 @@ class _Follower:
         self.seen = 0
         self.pending = []          # (state index, event): copies in flight
         self.closed = False
+        if clone_first:            # slot 0 is a private copy of the initial state: nobody needs it
+            eng.ctl_consume(0)
 
     def states(self):
         """Yield (j, t_j, attempts so far, ring slot) for every accepted state, in order, while the kernel is running."""
