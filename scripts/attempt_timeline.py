@@ -61,6 +61,8 @@ run("config3 fhn 256^2 KroneckerEK0 nu=4 adaptive", ek0.KroneckerEK0, ivp.fhn_2d
 run("        fhn 256^2 DiagonalEK1 nu=4 adaptive", ek1.DiagonalEK1, ivp.fhn_2d(dx=1 / 256, y0=y3), step.AdaptiveSteps(), 4)
 run("config2 lorenz96 100k DiagonalEK1 nu=3 constant", ek1.DiagonalEK1, ivp.lorenz96(num_variables=100_000), step.ConstantSteps(0.01), 3)
 run("        lorenz96 100k KroneckerEK0 nu=3 adaptive", ek0.KroneckerEK0, ivp.lorenz96(num_variables=100_000), step.AdaptiveSteps(), 3)
+if len(sys.argv) > 1 and sys.argv[1] == "small":
+    sys.exit(0)
 y5 = np.random.default_rng(2).uniform(size=2 * 2048 * 2048)
 run("config5 fhn 2048^2 KroneckerEK0 nu=4 adaptive", ek0.KroneckerEK0, ivp.fhn_2d(dx=1 / 2048, y0=y5), step.AdaptiveSteps(), 4, k=16)
 run("config5 fhn 2048^2 DiagonalEK1 nu=4 adaptive", ek1.DiagonalEK1, ivp.fhn_2d(dx=1 / 2048, y0=y5), step.AdaptiveSteps(), 4, k=8)

@@ -88,7 +88,7 @@ def test_solve_follows_the_running_kernel(cuda_device, solver_name, kind, size, 
         out = sol.solve(p, offload=offload)
         assert out.info == ref.info, (out.info, ref.info)
         assert out.t.shape == ref.t.shape
-        np.testing.assert_allclose(out.t.numpy(), ref.t.numpy(), rtol=1e-12, atol=0)
+        np.testing.assert_allclose(out.t.numpy(), ref.t.numpy(), rtol=1e-9, atol=0)
         assert out.mean.shape == ref.mean.shape and out.cov_sqrtm.shape == ref.cov_sqrtm.shape
         assert (out.mean.device.type == "cpu") == offload
         # device pow() in the dt proposal is within an ulp or two of the host's: equal to rounding, not bit for bit
@@ -109,7 +109,7 @@ def test_solution_generator_yields_copies_from_the_ring(cuda_device, solver_name
     got = [(st.t, st.y.mean, dict(info)) for st, info in sol.solution_generator(p)]
     assert len(got) == len(ref)
     for (t1, m1, i1), (t2, m2, i2) in zip(got, ref):
-        assert abs(t1 - t2) <= 1e-12 * max(abs(t2), 1e-300) and i1 == i2
+        assert abs(t1 - t2) <= 1e-9 * max(abs(t2), 1e-300) and i1 == i2
         assert_close(m1.cpu().numpy(), m2.cpu().numpy(), 1e-9, "yielded mean")
     # abandon a running solve
     sol2 = _solver(solver_name, step.AdaptiveSteps())
@@ -141,11 +141,11 @@ def test_time_stops_on_the_device(cuda_device, solver_name, kind, size, tmax):
         ts_dev.append(st.t)
         infos.append(dict(info))
     assert len(ts_dev) == len(ts_host)
-    np.testing.assert_allclose(ts_dev, ts_host, rtol=1e-12, atol=0)
+    np.testing.assert_allclose(ts_dev, ts_host, rtol=1e-9, atol=0)
     for s in stops:
         assert any(t == s for t in ts_dev), (s, ts_dev)
     fin, info = _solver(solver_name, step.AdaptiveSteps()).simulate_final_state(p, stop_at=stops)
-    assert info == infos[-1] and abs(fin.t - ts_host[-1]) <= 1e-12 * abs(ts_host[-1])
+    assert info == infos[-1] and abs(fin.t - ts_host[-1]) <= 1e-9 * abs(ts_host[-1])
     # the oracle's driver (op-for-op restatement of the reference's loop) takes the same steps
     m0, c0 = odriver.taylor_init(series_f, o.y0, o.t0, 3)
     solve = odriver.solve_kronecker_ek0 if solver_name == "ek0" else odriver.solve_diagonal_ek1

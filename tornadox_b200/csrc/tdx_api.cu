@@ -1437,8 +1437,9 @@ static int dek1_launch_attempts(tdx_ctx* ctx, int k, uint32_t flags, void* const
     comm_pack_advance(ctx, f, (unsigned long long)(k - 1));          // attempt i of the launch uses base + i
     comm_reduce_advance(ctx, f, true, (unsigned long long)(k - 1));
     ctx->launches += 1;
+    // the norm sum goes to device scratch: a store to mapped host memory would sit in front of the controller's fence
     const int code = ctx->ops->dek1_ctl(ctx->geo, h, mean_ring, sc_ring, nbuf, k, err_ring, ref_ring, halo_lo, halo_hi, ws, ctx->ctl,
-                                        d_global, ctx->host_norm_dev, (cudaStream_t)stream);
+                                        d_global, ctx->zsq_scratch + 1, (cudaStream_t)stream);
     return cuda_fail(code, where);
 }
 
@@ -1469,7 +1470,7 @@ static int ek0_launch_attempts(tdx_ctx* ctx, int k, uint32_t flags, void* const*
     ctx->launches += 1;
     unsigned long long* mid_flag = reinterpret_cast<unsigned long long*>(static_cast<unsigned char*>(ctx->mid) + 128);
     const int code = ctx->ops->ek0_ctl(ctx->geo, h, mean_ring, Cl_ring, nbuf, k, err_ring, ref_ring, halo_lo, halo_hi, ws, reduce_b,
-                                       mid_flag, mid_base, ctx->ctl, d_global, ctx->zsq_scratch, ctx->host_norm_dev,
+                                       mid_flag, mid_base, ctx->ctl, d_global, ctx->zsq_scratch, ctx->zsq_scratch + 1,
                                        (cudaStream_t)stream);
     return cuda_fail(code, where);
 }

@@ -60,13 +60,18 @@ __device__ __forceinline__ T QL(const Consts<T, N>& c, int i, int j) {
 // evaluates the same vectors with libm's pow like NumPy does -- the two agree to a few ulp).
 __host__ __device__ inline void nordsieck_vectors(int nu, double dt, double* p, double* pinv) {
     const double adt = dt < 0.0 ? -dt : dt;
-    double pw = sqrt(adt), fact = 1.0;
+    const double radt = 1.0 / adt;
+    double pw = sqrt(adt), ipw = 1.0 / pw, fact = 1.0, ifact = 1.0;
     for (int q = 0; q <= nu; ++q) {       // q = nu - k
-        if (q > 1) fact *= (double)q;
+        if (q > 1) {
+            fact *= (double)q;
+            ifact = 1.0 / fact;           // q! <= 720: the reciprocals are loop-invariant constants after unrolling
+        }
         const int k = nu - q;
-        if (p) p[k] = pw / fact;
-        if (pinv) pinv[k] = fact / pw;
+        if (p) p[k] = pw * ifact;
+        if (pinv) pinv[k] = fact * ipw;
         pw *= adt;
+        ipw *= radt;
     }
 }
 
@@ -712,6 +717,32 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "r"(parity)
         : "memory");
 }
+#ifdef TDX_DEBUG_WAITS
+// development aid: an mbarrier wait that gives up after 2 s and leaves a note (code, CTA, attempt) in the debug buffer
+__device__ __forceinline__ void mbar_wait_dbg(uint64_t* bar, uint32_t parity, double* dbg, int code, int att) {
+    const unsigned long long t0 = global_timer_ns();
+    for (;;) {
+        uint32_t ok;
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+        if (ok) return;
+        if (global_timer_ns() - t0 > 2000000000ull) {
+            dbg[3000 + code] = (double)(1 + blockIdx.x) + 1e-3 * att;
+            return;
+        }
+    }
+}
+#define TDX_MBAR_WAIT(bar, parity, dbg, code, att) mbar_wait_dbg(bar, parity, dbg, code, att)
+#else
+#define TDX_MBAR_WAIT(bar, parity, dbg, code, att) mbar_wait(bar, parity)
+#endif
 __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                      smem_u32(smem_dst)),
@@ -833,9 +864,13 @@ __device__ __forceinline__ bool spin_until_gpu(const unsigned long long* flag, u
                                                unsigned long long timeout_ns = kDefaultWaitNs) {
     if (ld_acquire_gpu(flag) >= seq) return true;
     const unsigned long long t0 = global_timer_ns();
+    unsigned int spins = 0;
     while (ld_acquire_gpu(flag) < seq) {
-        if (global_timer_ns() - t0 > (timeout_ns ? timeout_ns : kDefaultWaitNs)) return false;
-        __nanosleep(20);
+        // the release is at most a few microseconds away in the common case: poll back to back first
+        if (++spins > 64u) {
+            if (global_timer_ns() - t0 > (timeout_ns ? timeout_ns : kDefaultWaitNs)) return false;
+            __nanosleep(32);
+        }
     }
     return true;
 }
@@ -926,14 +961,46 @@ __device__ __forceinline__ double reduce_units(const RedPlan& rp, const CommRedu
     const unsigned long long lo_all = rp.unit0, hi_all = rp.unit0 + rp.units_local;
     sync();                                                      // s_red may still be read by a previous use
     if (threadIdx.x == 0) s_red[kRedChunks + 1] = 0.0;           // "a peer wait timed out"
-    for (int c = w; c < kRedChunks; c += nw) {
-        unsigned long long b0 = chunk_begin(rp, c), b1 = chunk_begin(rp, c + 1);
-        b0 = b0 > lo_all ? b0 : lo_all;
-        b1 = b1 < hi_all ? b1 : hi_all;
-        double acc = 0.0;
-        for (unsigned long long u = b0 + lane; u < b1; u += 32) acc += __ldcg(rp.unit + (u - lo_all));
-        acc = warp_sum(acc);
-        if (lane == 0) s_red[c] = acc;
+    if (nw * 2 >= kRedChunks) {
+        // two chunks per warp: issue the loads of both before the first shuffle tree (one L2 latency instead of two)
+        double acc[2] = {0.0, 0.0};
+        unsigned long long b0[2], b1[2];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int c = w + j * nw;
+            b0[j] = b1[j] = 0ull;
+            if (c < kRedChunks) {
+                b0[j] = chunk_begin(rp, c);
+                b1[j] = chunk_begin(rp, c + 1);
+                b0[j] = b0[j] > lo_all ? b0[j] : lo_all;
+                b1[j] = b1[j] < hi_all ? b1[j] : hi_all;
+            }
+        }
+        double first[2] = {0.0, 0.0};
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+            if (b0[j] + lane < b1[j]) first[j] = __ldcg(rp.unit + (b0[j] + lane - lo_all));
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            acc[j] = first[j];
+            for (unsigned long long u = b0[j] + lane + 32; u < b1[j]; u += 32) acc[j] += __ldcg(rp.unit + (u - lo_all));
+        }
+        acc[0] = warp_sum(acc[0]);
+        acc[1] = warp_sum(acc[1]);
+        if (lane == 0) {
+            if (w < kRedChunks) s_red[w] = acc[0];
+            if (w + nw < kRedChunks) s_red[w + nw] = acc[1];
+        }
+    } else {
+        for (int c = w; c < kRedChunks; c += nw) {
+            unsigned long long b0 = chunk_begin(rp, c), b1 = chunk_begin(rp, c + 1);
+            b0 = b0 > lo_all ? b0 : lo_all;
+            b1 = b1 < hi_all ? b1 : hi_all;
+            double acc = 0.0;
+            for (unsigned long long u = b0 + lane; u < b1; u += 32) acc += __ldcg(rp.unit + (u - lo_all));
+            acc = warp_sum(acc);
+            if (lane == 0) s_red[c] = acc;
+        }
     }
     sync();
     const bool comm = cr != nullptr && cr->world > 0;

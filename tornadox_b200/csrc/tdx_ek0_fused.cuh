@@ -359,7 +359,10 @@ __device__ __forceinline__ double ek0_mid_barrier(const Ek0FusedArgs<T, N>& a, E
     }
     if (tc == 0) {
         sh.timed_out = spin_until_gpu(a.mid_flag, a.mid_seq + (unsigned long long)att, a.wait.timeout_ns) ? 0.0 : 1.0;
-        mbar_wait(&sh.m1_bar, (unsigned)att & 1u);           // the producer warp's m1 of this attempt
+#ifdef TDX_DEBUG_WAITS
+        if (sh.timed_out != 0.0) a.partials[3004] = (double)(1 + blockIdx.x) + 1e-3 * att;
+#endif
+        TDX_MBAR_WAIT(&sh.m1_bar, (unsigned)att & 1u, a.partials, 3, att);           // the producer warp's m1 of this attempt
     }
     csync();
     // a dead peer must not hang the GPU and must not go unnoticed: NaN state, NaN norm, the controller / host raises
@@ -466,7 +469,7 @@ __global__ void __maxnreg__(TDX_EK0_MAXREG) ek0_fused_fhn_kernel(const __grid_co
 #pragma unroll 1
                     for (int i = 0; i < L; ++i, rr += s.dir, ++q) {
                         const unsigned stage = q % S, round = q / S;
-                        if (round > 0) mbar_wait(empty + stage, (round - 1u) & 1u);     // the slot's previous row is consumed
+                        if (round > 0) TDX_MBAR_WAIT(empty + stage, (round - 1u) & 1u, a.partials, 2, att);     // the slot's previous row is consumed
                         if (rr < 0 || rr >= g.rows) continue;
                         T* dst = s_stage + (size_t)stage * Cfg::STAGE_ELEMS;
                         const T* src = mean_in + (long long)rr * g.cols + gs;
@@ -568,7 +571,7 @@ __global__ void __maxnreg__(TDX_EK0_MAXREG) ek0_fused_fhn_kernel(const __grid_co
                     T* at_row = s_at + (cq & 1u) * 2 * AT_ROW;
                     T at_cur[2], mp_cur[2][NK];
                     if (rr >= 0 && rr < g.rows) {
-                        mbar_wait(full + stage, (phase_bits >> stage) & 1u);
+                        TDX_MBAR_WAIT(full + stage, (phase_bits >> stage) & 1u, a.partials, 1, att);
                         phase_bits ^= (1u << stage);
                         const T* st = s_stage + (size_t)stage * Cfg::STAGE_ELEMS;
 #pragma unroll

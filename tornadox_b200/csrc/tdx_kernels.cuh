@@ -622,7 +622,7 @@ __global__ void __launch_bounds__(kThreads, DekSmem<T, N>::MIN_BLOCKS) dek1_kern
                 __syncwarp();
                 next_bulk = stage_in(tile_coord<Shape>(g, a.ranges.tile(next), a.tiles_x), 0);
             }
-            if (unit_mode && (c.want_norm || kCtl)) {
+            if (unit_mode && (c.want_norm || (kCtl && kComm && a.reduce.world > 0))) {
                 // the tile's share of the norm (after the stores are on their way): lanes through the shuffle tree, the warps
                 // through shared memory after the next barrier
                 const double ws = warp_sum(ratio_sq);
@@ -660,7 +660,9 @@ __global__ void __launch_bounds__(kThreads, DekSmem<T, N>::MIN_BLOCKS) dek1_kern
         bool fin = false;                             // thread 0 of the last CTA
         if (unit_mode) {
             if (cta_arrive_last(a.ticket, &s_flag)) {
-                total = reduce_units(a.red, kComm ? &a.reduce : nullptr, a.reduce.seq + (unsigned long long)att, s_red);
+                // ConstantSteps on one GPU: nothing to add up, the rendezvous alone orders the attempts
+                if (c.want_norm || (kComm && a.reduce.world > 0))
+                    total = reduce_units(a.red, kComm ? &a.reduce : nullptr, a.reduce.seq + (unsigned long long)att, s_red);
                 fin = threadIdx.x == 0;
                 if (fin && c.want_norm && a.out_sum) *a.out_sum = total;
             }

@@ -30,7 +30,7 @@ class KroneckerEK0(odefilter.ODEFilter):
     def initialize(self, f, t0, tmax, y0, df, df_diagonal):
         """ek0.py:94-121: single (n, n) factor, scalar NaN error estimate."""
         y0 = as_device_tensor(y0, dtype=self.dtype)
-        self.engine = BatchedEK1._make_engine(self, f, y0.device)
+        self.engine = BatchedEK1._make_engine(self, f, y0.device, y0)
         A, _ = _lib.prior(self.num_derivatives)
         Ql = self.engine.Ql
         self.A = torch.as_tensor(A, dtype=self.dtype, device=y0.device)
@@ -47,6 +47,8 @@ class KroneckerEK0(odefilter.ODEFilter):
         if self.engine is None:
             raise RuntimeError("call initialize() first")
         abstol, reltol = self.steprule.kernel_tolerances
+        if self.engine.external:      # a user-defined f: evaluated by the caller's torch code at the predicted state
+            self.engine.evaluate_external(f, None, state.t, dt, state.y.mean, False)
         mean, Cl, err, ref, itol = self.engine.ek0_attempt(
             state.t, dt, state.y.mean, state.y.cov_sqrtm_2, abstol=abstol, reltol=reltol,
             want_ref=self.materialize_reference_state)

@@ -30,8 +30,8 @@ class BatchedEK1(odefilter.ODEFilter):
         self.sq_1d = None
         self.engine = None
 
-    def _make_engine(self, f, device):
-        spec = _spec_of(f)
+    def _make_engine(self, f, device, y0=None):
+        spec = _spec_of(f, y0)
         group = self.process_group
         rank = world = None
         if group is not None:
@@ -44,7 +44,7 @@ class BatchedEK1(odefilter.ODEFilter):
     def initialize(self, f, t0, tmax, y0, df, df_diagonal):
         """ek1.py:190-205.  ``y0`` is the GLOBAL initial value; a sharded solver keeps its own slice."""
         y0 = as_device_tensor(y0, dtype=self.dtype)
-        self.engine = self._make_engine(f, y0.device)
+        self.engine = self._make_engine(f, y0.device, y0)
         A, _ = _lib.prior(self.num_derivatives)
         Ql = self.engine.Ql
         self.phi_1d = torch.as_tensor(A, dtype=self.dtype, device=y0.device)
@@ -81,6 +81,8 @@ class BatchedEK1(odefilter.ODEFilter):
         abstol, reltol = self.steprule.kernel_tolerances
         if state.y.mean.device.type == "cpu":
             return self._attempt_step_host(state, dt, abstol, reltol)
+        if self.engine.external:      # a user-defined f: evaluated by the caller's torch code at the predicted state
+            self.engine.evaluate_external(f, df_diagonal, state.t, dt, state.y.mean, self._uses_jacobian)
         mean, sc, err, ref, sq = self.engine.dek1_attempt(
             state.t, dt, state.y.mean, state.y.cov_sqrtm, abstol=abstol, reltol=reltol,
             want_err_ref=self.materialize_error_vectors, jacobian=self._uses_jacobian)

@@ -480,8 +480,40 @@ class StepEngine:
             return _lib.StepRule(0, 0, 0.0, 0.0, 0.0, 0.0, 0.0, float(steprule.dt))
         return None
 
+    @property
+    def external(self):
+        """The vector field is the caller's own code (``TDX_IVP_EXTERNAL``): every attempt needs f at the predicted state."""
+        return self.spec.kind == _lib.TDX_IVP_EXTERNAL
+
     def can_run_full_steps(self):
-        return self.world == 1 or self.peer
+        # the library's own accept / reject loops cannot call back into the caller's f
+        return (self.world == 1 or self.peer) and not self.external
+
+    def predict_state(self, dt, mean):
+        """E0 P A P^-1 m: the point where the attempt with step ``dt`` from ``mean`` evaluates f (ek1.py:304-306, ek0.py:146-147)."""
+        self._check(mean, (self.n, self.d_local), "mean")
+        out = torch.empty(self.d_local, dtype=self.dtype, device=self.device)
+        _lib.check(self.lib.tdx_predict_state(self.handle, float(dt), _ptr(mean), _ptr(out), self._stream()))
+        return out
+
+    def set_external(self, fx, jac=None):
+        """Hand the caller's f(t + dt, m_at) (and diag df) to the next attempt of an EXTERNAL vector field."""
+        self._check(fx, (self.d_local,), "f(t, y)")
+        if jac is not None:
+            self._check(jac, (self.d_local,), "df_diagonal(t, y)")
+        self._external_arrays = (fx, jac)            # keep them alive until the step has run
+        _lib.check(self.lib.tdx_set_external(self.handle, _ptr(fx), _ptr(jac)))
+
+    def evaluate_external(self, f, df_diagonal, t, dt, mean, jacobian):
+        """predict -> the caller's f / df_diagonal on device tensors -> hand the arrays in."""
+        m_at = self.predict_state(dt, mean)
+        fx = torch.as_tensor(f(t + dt, m_at), dtype=self.dtype, device=self.device).reshape(-1).contiguous()
+        jac = None
+        if jacobian:
+            if df_diagonal is None:
+                raise ValueError("DiagonalEK1 needs df_diagonal(t, y) for a user-defined vector field")
+            jac = torch.as_tensor(df_diagonal(t + dt, m_at), dtype=self.dtype, device=self.device).reshape(-1).contiguous()
+        self.set_external(fx, jac)
 
     def _full_step_flags(self, base=0):
         return base | ((_lib.TDX_STEP_COMM_PACK | _lib.TDX_STEP_COMM_REDUCE) if self.world > 1 else 0)

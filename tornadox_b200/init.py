@@ -25,14 +25,25 @@ class InitializationRoutine(abc.ABC):
         raise NotImplementedError
 
 
-def _spec_of(f):
+def _spec_of(f, y0=None):
+    """The in-kernel vector field a callable stands for, or -- for any other callable -- the EXTERNAL field: the fused
+    kernels then read f (and the Jacobian diagonal) from arrays the caller's own torch code produces at the predicted state
+    (``StepEngine.predict_state`` / ``set_external``), which is how the reference treats every f (odefilter.py:346-352)."""
     spec = getattr(f, "spec", None)
-    if spec is None:
-        raise ValueError(
-            "tornadox_b200 only integrates the vector fields of tornadox_b200.ivp (evaluated in-kernel); "
-            "an arbitrary Python callable has no fused kernel and there is no CPU fallback"
-        )
-    return spec
+    if spec is not None:
+        return spec
+    if not callable(f):
+        raise ValueError("the vector field must be callable: f(t, y) -> dy/dt on device tensors")
+    if y0 is None:
+        raise ValueError("a user-defined vector field needs y0 to size the state")
+    from .engine import KernelSpec
+
+    d = int(as_device_tensor(y0).reshape(-1).shape[0])
+    return KernelSpec(_lib.TDX_IVP_EXTERNAL, (), 1, d, 1, getattr(f, "__name__", "user-defined f"))
+
+
+def is_external(f):
+    return getattr(f, "spec", None) is None
 
 
 class _PowerSeries:
@@ -247,6 +258,8 @@ class TaylorMode(InitializationRoutine):
     @staticmethod
     def taylor_mode(fun, y0, t0, num_derivatives):
         """With y(t0 + h) = sum_k Y_k h^k and y' = f(y):  (k + 1) Y_{k+1} = [h^k] f(y(t0 + h))."""
+        if is_external(fun):
+            return TaylorMode.taylor_mode_autodiff(fun, y0, t0, num_derivatives)
         spec = _spec_of(fun)
         rhs = _series_rhs(spec)
         y0 = as_device_tensor(y0).reshape(-1)
@@ -258,14 +271,36 @@ class TaylorMode(InitializationRoutine):
         return torch.stack([math.factorial(k) * c for k, c in enumerate(coeffs)])
 
 
+    @staticmethod
+    def taylor_mode_autodiff(fun, y0, t0, num_derivatives):
+        """Taylor-mode initialisation of a user-defined vector field written in differentiable torch operations (the
+        reference pushes any f through ``jax.experimental.jet``, init.py:63-103).  With the autonomous extension
+        z = [y, t], z' = F(z) = [f(t, y), 1]:  z^(k+1) = d/dt z^(k) = J_{z^(k)}(z) F(z), i.e. one forward-mode
+        derivative (``torch.func.jvp``) per order, nested.  Cost grows like 2^nu evaluations of f: fine for nu <= 6."""
+        y0 = as_device_tensor(y0).reshape(-1)
+        d = y0.shape[0]
+        z0 = torch.cat([y0, torch.as_tensor([float(t0)], dtype=y0.dtype, device=y0.device)])
+
+        def F(z):
+            return torch.cat([fun(z[d], z[:d]).reshape(-1), torch.ones(1, dtype=z.dtype, device=z.device)])
+
+        def derivative(k):
+            if k == 0:
+                return lambda z: z
+            prev = derivative(k - 1)
+            return lambda z: torch.func.jvp(prev, (z,), (F(z),))[1]
+
+        rows = [derivative(k)(z0)[:d] for k in range(num_derivatives + 1)]
+        return torch.stack(rows).contiguous()
+
+
 class Stack(InitializationRoutine):
-    """[y0, f(t0, y0), 0, ...] with large uncertainty on the unknown derivatives (init.py:359-391)."""
+    """[y0, f(t0, y0), 0, ...] with large uncertainty on the unknown derivatives (init.py:359-391).
+    ``use_df=True`` also fills y'' = df(t0, y0) @ f(t0, y0) from the caller's DENSE Jacobian (init.py:377-385; O(d^2), small
+    problems -- the in-kernel vector fields carry no dense Jacobian)."""
 
     def __init__(self, use_df=False):
-        if use_df:
-            raise NotImplementedError(
-                "Stack(use_df=True) multiplies with the dense Jacobian (O(d^2)); use Stack(use_df=False) or TaylorMode()"
-            )
+        self.use_df = bool(use_df)
 
     def __call__(self, f, df, y0, t0, num_derivatives):
         y0 = as_device_tensor(y0).reshape(-1)
@@ -273,11 +308,20 @@ class Stack(InitializationRoutine):
         fy = f(t0, y0)
         m = torch.zeros((n, y0.shape[0]), dtype=y0.dtype, device=y0.device)
         m[0], m[1] = y0, fy
-        diag = torch.tensor([0.0, 0.0] + [1e3] * (n - 2), dtype=y0.dtype, device=y0.device)
+        known = 2
+        if self.use_df:
+            if df is None:
+                raise NotImplementedError(
+                    "Stack(use_df=True) needs the dense Jacobian df(t, y) (O(d^2)); the vector fields of tornadox_b200.ivp do not "
+                    "provide one -- use Stack(use_df=False) or TaylorMode()")
+            if n > 2:
+                m[2] = torch.as_tensor(df(t0, y0), dtype=y0.dtype, device=y0.device) @ fy
+                known = 3
+        diag = torch.tensor([0.0] * min(known, n) + [1e3] * max(n - known, 0), dtype=y0.dtype, device=y0.device)
         return m, torch.diag(diag)
 
     def __repr__(self):
-        return f"{self.__class__.__name__}(use_df=False)"
+        return f"{self.__class__.__name__}(use_df={self.use_df})"
 
 
 class RungeKutta(InitializationRoutine):

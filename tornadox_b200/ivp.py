@@ -7,7 +7,9 @@ Mirrors the factory functions of the reference (tornadox/ivp.py): ``vanderpol`` 
 ``InitialValueProblem(f, t0, tmax, y0, df, df_diagonal)`` (:10-25); ``f`` and ``df_diagonal`` are callables
 on device tensors (they launch ``tdx_eval_f``) that additionally carry the ``KernelSpec`` the solvers
 dispatch on.  ``df`` (dense Jacobian) is ``None``: the O(d^2) dense solvers are out of scope.
-A user-supplied Python ``f`` has no fused kernel and is rejected by the solvers (no CPU fallback).
+A user-supplied ``f`` (any callable on device tensors, optionally with ``df_diagonal``) is integrated too: the solvers then
+evaluate it with the caller's own torch code at the predicted state of every attempt and run the same fused kernels on the
+result (``TDX_IVP_EXTERNAL``); only the device-resident step controller needs an in-kernel vector field.
 """
 
 from collections import namedtuple
