@@ -268,19 +268,22 @@ int tdx_ctl_read(tdx_ctx* ctx, tdx_ctl_state* out, double* hist_t, double* hist_
  * The reference compiles the whole accept / reject loop into one ``lax.while_loop`` (odefilter.py:225-344).  Here
  * tdx_*_run_attempts is ONE persistent cooperative kernel that runs up to ``k`` attempts: after every attempt the last CTA
  * reduces the norm (over the ranks too), updates the controller and releases an in-kernel grid barrier; halo delivery and both
- * all-reduces of a sharded run happen inside the same launch.  The launch ends early when the solve reaches tmax.
+ * all-reduces of a sharded run happen inside the same launch.  The launch ends early when the solve reaches tmax, or after
+ * ``max_accepted`` newly accepted steps (0: no limit).
  * State buffers form a RING of ``nbuf`` (mean, factor) pairs (2 <= nbuf <= TDX_CTL_MAX_RING; the same ring must be passed to
  * every launch of a solve): attempt output goes to slot (cur + 1) % nbuf, an accepted attempt advances ``cur``, so accepted
  * state number j (0 = the initial state, in slot 0) lives in slot j % nbuf until nbuf - 1 further steps have been accepted.
+ * Dense output without a host round trip per step: launch with max_accepted = nbuf - 1 on one stream and copy the states out
+ * of the ring on another stream while the kernel goes on with the next attempts; within one launch no slot is written twice.
  *   tdx_ctl_begin_ex   tdx_ctl_begin with options: ring size, time stops (odefilter.py:355-373: the solve lands exactly on
- *                      every stop), and ``follow``: the kernel publishes its progress to mapped pinned memory and does not
- *                      rewrite a ring slot before the host has released the state it holds
+ *                      every stop), and ``follow``: the kernel publishes its progress to mapped pinned memory
  *   tdx_ctl_poll       (follow) accepted / attempted steps so far, without synchronising anything
- *   tdx_ctl_history    (follow) time and step of accepted state ``state_index`` >= 1 (kept for the last TDX_CTL_HISTORY states)
- *   tdx_ctl_consume    (follow) states [0, upto] have been copied out of the ring
+ *   tdx_ctl_history    (follow) time, step and attempt count of accepted state ``state_index`` >= 1 (kept for the last
+ *                      TDX_CTL_HISTORY states)
  *   tdx_ctl_abort      (follow) stop the running launch at the next attempt boundary
  * A wait inside the kernels (peer halos, reductions, grid barriers) that exceeds TDX_WAIT_TIMEOUT_MS (environment, default
- * 4000) poisons the attempt's norm with NaN and stops the solve with ``failed`` = 2 on every rank. */
+ * 4000) poisons the attempt's norm with NaN and stops the solve on every rank with ``failed`` = 2 (poisoned attempt), 3 (the
+ * grid barrier between two attempts), 4 (reserved) or 5 (a peer); 1 = NaN error estimate. */
 #define TDX_CTL_MAX_RING 8
 typedef struct {
     int32_t nbuf;          /* ring size                                                                            */
@@ -295,13 +298,12 @@ int tdx_ctl_begin_ex(tdx_ctx* ctx, const tdx_steprule* rule, double t0, double d
                      const tdx_ctl_options* options, void* stream);
 /* err_ring / ref_ring: per-slot error_estimate (DiagonalEK1: (d) vectors or NULL; KroneckerEK0: scalars, required) and
  * reference_state vectors (NULL, or NULL entries: not written), so that they belong to the state in the same slot */
-int tdx_dek1_run_attempts(tdx_ctx* ctx, int k, uint32_t flags, void* const* mean_ring, void* const* sc_ring, int nbuf,
-                          void* const* err_ring, void* const* ref_ring, void* stream);
-int tdx_ek0_run_attempts(tdx_ctx* ctx, int k, uint32_t flags, void* const* mean_ring, void* const* Cl_ring, int nbuf,
-                         void* const* err_ring, void* const* ref_ring, void* stream);
+int tdx_dek1_run_attempts(tdx_ctx* ctx, int k, int64_t max_accepted, uint32_t flags, void* const* mean_ring,
+                          void* const* sc_ring, int nbuf, void* const* err_ring, void* const* ref_ring, void* stream);
+int tdx_ek0_run_attempts(tdx_ctx* ctx, int k, int64_t max_accepted, uint32_t flags, void* const* mean_ring,
+                         void* const* Cl_ring, int nbuf, void* const* err_ring, void* const* ref_ring, void* stream);
 int tdx_ctl_poll(tdx_ctx* ctx, tdx_ctl_progress* out);
 int tdx_ctl_history(tdx_ctx* ctx, int64_t state_index, double* t, double* dt, int64_t* attempts);
-int tdx_ctl_consume(tdx_ctx* ctx, int64_t upto);
 int tdx_ctl_abort(tdx_ctx* ctx);
 
 /* ---- peer-memory exchange over NVLink (multi-GPU, one process per GPU on one node) -------------------------

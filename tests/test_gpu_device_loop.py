@@ -93,7 +93,9 @@ def test_solve_follows_the_running_kernel(cuda_device, solver_name, kind, size, 
         assert (out.mean.device.type == "cpu") == offload
         # device pow() in the dt proposal is within an ulp or two of the host's: equal to rounding, not bit for bit
         assert_close(out.mean.cpu().numpy(), ref.mean.cpu().numpy(), 1e-9, "means of all accepted states")
-        assert_close(out.cov_sqrtm.cpu().numpy(), ref.cov_sqrtm.cpu().numpy(), 1e-7, "factors of all accepted states")
+        # factors are unique up to column signs (LAPACK's beta = -sign(alpha) |x| flips with the last bit of alpha): compare S S^T
+        S, R = out.cov_sqrtm.cpu().numpy(), ref.cov_sqrtm.cpu().numpy()
+        assert_close(S @ np.swapaxes(S, -1, -2), R @ np.swapaxes(R, -1, -2), 1e-7, "covariances of all accepted states")
 
 
 @pytest.mark.parametrize("solver_name", ["ek0", "ek1"])
@@ -120,7 +122,7 @@ def test_solution_generator_yields_copies_from_the_ring(cuda_device, solver_name
     gen.close()
     torch.cuda.synchronize()
     ctl = sol2.engine.ctl_read()
-    assert ctl.done and not ctl.failed and ctl.t < 1.0
+    assert not ctl.failed and ctl.t < 1.0          # stopped: by the abort flag, or at the end of its bounded launch
 
 
 @pytest.mark.parametrize("solver_name", ["ek0", "ek1"])

@@ -168,11 +168,23 @@ def test_taylor_mode_series_algebra_on_cpu_tensors(name, size):
         assert_close(m0.numpy(), ref, 1e-13, "taylor mode")
 
 
-def test_untagged_vector_field_is_rejected():
-    from tornadox_b200 import init
+def test_user_defined_vector_field_maps_to_the_external_kernel_tag():
+    """A callable without a kernel tag is not rejected: it becomes the EXTERNAL vector field (the caller's torch code evaluates
+    f at the predicted state, the fused kernels do the rest), and Taylor mode differentiates it with nested forward mode."""
+    from tornadox_b200 import _lib, init
 
-    with pytest.raises(ValueError, match="no CPU fallback"):
-        init.TaylorMode()(lambda t, y: y, None, np.ones(3), 0.0, 2)
+    y0 = torch.tensor([1.0, 2.0, 3.0], dtype=torch.float64)
+    spec = init._spec_of(lambda t, y: y, y0)
+    assert spec.kind == _lib.TDX_IVP_EXTERNAL and (spec.grid_rows, spec.grid_cols, spec.n_fields) == (1, 3, 1)
+    # dy/dt = t y: second derivative y + t dy/dt, third derivative 2 dy/dt + t d2y/dt2
+    m, c = init.TaylorMode()(lambda t, y: t * y, None, y0, 0.5, 3)
+    expect = torch.stack([y0, 0.5 * y0, 1.25 * y0, 1.625 * y0])
+    assert torch.allclose(m, expect, rtol=1e-14, atol=0) and float(c.abs().max()) == 0.0
+    with pytest.raises(ValueError):
+        init._spec_of(None, y0)
+    # Stack(use_df=True) with the caller's dense Jacobian (init.py:377-385)
+    m, c = init.Stack(use_df=True)(lambda t, y: -y, lambda t, y: -torch.eye(3, dtype=torch.float64), y0, 0.0, 3)
+    assert torch.equal(m[2], y0) and torch.equal(torch.diagonal(c), torch.tensor([0.0, 0.0, 0.0, 1e3], dtype=torch.float64))
 
 
 def test_rv_containers():
@@ -221,3 +233,15 @@ def test_native_steprule_mirror_and_shard_ranges():
         with pytest.raises(ValueError):
             engine.shard_range(small.spec, 0, 2)
     assert engine.shard_range(ivp.lorenz96(num_variables=10).spec, 1, 2) == (5, 10)
+
+
+def test_scripts_compile():
+    """scripts/ holds development aids that no test runs on the CPU: at least keep them syntactically valid."""
+    import pathlib
+    import py_compile
+
+    root = pathlib.Path(__file__).resolve().parent.parent / "scripts"
+    names = sorted(root.glob("*.py"))
+    assert len(names) >= 8
+    for path in names:
+        py_compile.compile(str(path), doraise=True)

@@ -31,7 +31,7 @@ EXPORTED_SYMBOLS = (
     "tdx_ek0_sweep_a", "tdx_ek0_mid", "tdx_ek0_sweep_b", "tdx_ek0_attempt_step", "tdx_launch_count",
     "tdx_debug_read_workspace", "tdx_dek1_attempt_step_host", "tdx_dek1_attempt_step_host_sharded", "tdx_dek1_full_step", "tdx_ek0_full_step", "tdx_propagate_cholesky_factor",
     "tdx_ctl_begin", "tdx_dek1_enqueue_attempts", "tdx_ek0_enqueue_attempts", "tdx_ctl_read",
-    "tdx_ctl_begin_ex", "tdx_dek1_run_attempts", "tdx_ek0_run_attempts", "tdx_ctl_poll", "tdx_ctl_history", "tdx_ctl_consume", "tdx_ctl_abort",
+    "tdx_ctl_begin_ex", "tdx_dek1_run_attempts", "tdx_ek0_run_attempts", "tdx_ctl_poll", "tdx_ctl_history", "tdx_ctl_abort",
     "tdx_predict_state", "tdx_set_external",
     "tdx_comm_init", "tdx_comm_connect", "tdx_comm_pack_halo", "tdx_comm_allreduce", "tdx_comm_error",
 )
@@ -165,11 +165,10 @@ def load():
     lib.tdx_ctl_read.argtypes = [vp, ctypes.POINTER(CtlState), pd, pd, vp]
     lib.tdx_ctl_begin_ex.argtypes = [vp, ctypes.POINTER(StepRule), dbl, dbl, dbl, ctypes.POINTER(CtlOptions), vp]
     ring = ctypes.POINTER(vp)
-    lib.tdx_dek1_run_attempts.argtypes = [vp, cint, ctypes.c_uint32, ring, ring, cint, ring, ring, vp]
-    lib.tdx_ek0_run_attempts.argtypes = [vp, cint, ctypes.c_uint32, ring, ring, cint, ring, ring, vp]
+    lib.tdx_dek1_run_attempts.argtypes = [vp, cint, i64, ctypes.c_uint32, ring, ring, cint, ring, ring, vp]
+    lib.tdx_ek0_run_attempts.argtypes = [vp, cint, i64, ctypes.c_uint32, ring, ring, cint, ring, ring, vp]
     lib.tdx_ctl_poll.argtypes = [vp, ctypes.POINTER(CtlProgress)]
     lib.tdx_ctl_history.argtypes = [vp, i64, pd, pd, ctypes.POINTER(i64)]
-    lib.tdx_ctl_consume.argtypes = [vp, i64]
     lib.tdx_ctl_abort.argtypes = [vp]
     lib.tdx_dek1_attempt_step_host_sharded.argtypes = [vp, ctypes.POINTER(StepArgs)] + [vp] * 8 + [pd, cint]
     lib.tdx_ek0_sweep_a.argtypes = [vp, ctypes.POINTER(StepArgs), vp, vp, vp, vp, vp]

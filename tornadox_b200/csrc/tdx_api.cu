@@ -1419,8 +1419,8 @@ static int check_ring(const tdx_ctx* ctx, void* const* a, void* const* b, int nb
 }
 
 // one cooperative launch that runs up to ``k`` attempts
-static int dek1_launch_attempts(tdx_ctx* ctx, int k, uint32_t flags, void* const* mean_ring, void* const* sc_ring, int nbuf,
-                                void* const* err_ring, void* const* ref_ring, void* stream, const char* where) {
+static int dek1_launch_attempts(tdx_ctx* ctx, int k, int64_t max_accepted, uint32_t flags, void* const* mean_ring, void* const* sc_ring,
+                                int nbuf, void* const* err_ring, void* const* ref_ring, void* stream, const char* where) {
     const bool sharded = ctx->halo_lo > 0 || ctx->halo_hi > 0;
     const uint32_t f = sharded ? flags : (flags & TDX_STEP_ZERO_JACOBIAN);
     const double d_global = (double)ctx->geo.nf * (double)ctx->geo.grows * (double)ctx->geo.gcols;
@@ -1434,6 +1434,7 @@ static int dek1_launch_attempts(tdx_ctx* ctx, int k, uint32_t flags, void* const
     comm_pack_advance(ctx, f);
     comm_reduce_advance(ctx, f, true);             // under the controller every attempt ends with a reduction over the ranks
     Workspace ws = make_ws(ctx, f);
+    ws.max_accepted = max_accepted;
     comm_pack_advance(ctx, f, (unsigned long long)(k - 1));          // attempt i of the launch uses base + i
     comm_reduce_advance(ctx, f, true, (unsigned long long)(k - 1));
     ctx->launches += 1;
@@ -1443,8 +1444,8 @@ static int dek1_launch_attempts(tdx_ctx* ctx, int k, uint32_t flags, void* const
     return cuda_fail(code, where);
 }
 
-static int ek0_launch_attempts(tdx_ctx* ctx, int k, uint32_t flags, void* const* mean_ring, void* const* Cl_ring, int nbuf,
-                               void* const* err_ring, void* const* ref_ring, void* stream, const char* where) {
+static int ek0_launch_attempts(tdx_ctx* ctx, int k, int64_t max_accepted, uint32_t flags, void* const* mean_ring, void* const* Cl_ring,
+                               int nbuf, void* const* err_ring, void* const* ref_ring, void* stream, const char* where) {
     const bool sharded = ctx->halo_lo > 0 || ctx->halo_hi > 0;
     const uint32_t f = sharded ? flags : 0u;
     const double d_global = (double)ctx->geo.nf * (double)ctx->geo.grows * (double)ctx->geo.gcols;
@@ -1458,6 +1459,7 @@ static int ek0_launch_attempts(tdx_ctx* ctx, int k, uint32_t flags, void* const*
     comm_pack_advance(ctx, f);
     comm_reduce_advance(ctx, f, true);
     Workspace ws = make_ws(ctx, f);                 // reduce_a: base sequence number, cl_seq: base
+    ws.max_accepted = max_accepted;
     comm_reduce_advance(ctx, f, true);
     CommReduce reduce_b = ws.reduce;
     reduce_b.seq = ctx->red_seq;
@@ -1475,20 +1477,21 @@ static int ek0_launch_attempts(tdx_ctx* ctx, int k, uint32_t flags, void* const*
     return cuda_fail(code, where);
 }
 
-extern "C" int tdx_dek1_run_attempts(tdx_ctx* ctx, int k, uint32_t flags, void* const* mean_ring, void* const* sc_ring, int nbuf,
-                                     void* const* err_ring, void* const* ref_ring, void* stream) {
+extern "C" int tdx_dek1_run_attempts(tdx_ctx* ctx, int k, int64_t max_accepted, uint32_t flags, void* const* mean_ring,
+                                     void* const* sc_ring, int nbuf, void* const* err_ring, void* const* ref_ring, void* stream) {
     int rc = check_ready(ctx, "tdx_dek1_run_attempts");
     if (rc) return rc;
     if (!ctx->ctl) return fail(TDX_ERR_INVALID, "tdx_dek1_run_attempts: call tdx_ctl_begin first");
     if ((rc = check_full_step_flags(ctx, flags, "tdx_dek1_run_attempts"))) return rc;
     if ((rc = check_ring(ctx, mean_ring, sc_ring, nbuf, "tdx_dek1_run_attempts"))) return rc;
     if (k < 1) return fail(TDX_ERR_INVALID, "tdx_dek1_run_attempts: k must be positive");
+    if (max_accepted < 0) return fail(TDX_ERR_INVALID, "tdx_dek1_run_attempts: max_accepted must not be negative");
     DeviceGuard guard(ctx->device);
-    return dek1_launch_attempts(ctx, k, flags, mean_ring, sc_ring, nbuf, err_ring, ref_ring, stream, "tdx_dek1_run_attempts");
+    return dek1_launch_attempts(ctx, k, max_accepted, flags, mean_ring, sc_ring, nbuf, err_ring, ref_ring, stream, "tdx_dek1_run_attempts");
 }
 
-extern "C" int tdx_ek0_run_attempts(tdx_ctx* ctx, int k, uint32_t flags, void* const* mean_ring, void* const* Cl_ring, int nbuf,
-                                    void* const* err_ring, void* const* ref_ring, void* stream) {
+extern "C" int tdx_ek0_run_attempts(tdx_ctx* ctx, int k, int64_t max_accepted, uint32_t flags, void* const* mean_ring,
+                                    void* const* Cl_ring, int nbuf, void* const* err_ring, void* const* ref_ring, void* stream) {
     int rc = check_ready(ctx, "tdx_ek0_run_attempts");
     if (rc) return rc;
     if (!ctx->ctl) return fail(TDX_ERR_INVALID, "tdx_ek0_run_attempts: call tdx_ctl_begin first");
@@ -1498,8 +1501,9 @@ extern "C" int tdx_ek0_run_attempts(tdx_ctx* ctx, int k, uint32_t flags, void* c
     for (int i = 0; i < nbuf; ++i)
         if (!err_ring[i]) return fail(TDX_ERR_INVALID, "tdx_ek0_run_attempts: null entry in err_ring");
     if (k < 1) return fail(TDX_ERR_INVALID, "tdx_ek0_run_attempts: k must be positive");
+    if (max_accepted < 0) return fail(TDX_ERR_INVALID, "tdx_ek0_run_attempts: max_accepted must not be negative");
     DeviceGuard guard(ctx->device);
-    return ek0_launch_attempts(ctx, k, flags, mean_ring, Cl_ring, nbuf, err_ring, ref_ring, stream, "tdx_ek0_run_attempts");
+    return ek0_launch_attempts(ctx, k, max_accepted, flags, mean_ring, Cl_ring, nbuf, err_ring, ref_ring, stream, "tdx_ek0_run_attempts");
 }
 
 // the same attempts as k separate launches of one attempt each (the first design of the controller; kept as the A/B partner
@@ -1519,7 +1523,7 @@ extern "C" int tdx_dek1_enqueue_attempts(tdx_ctx* ctx, int k, uint32_t flags, vo
     void* err_ab[2] = {err_out, err_out};
     void* ref_ab[2] = {ref_out, ref_out};
     for (int i = 0; i < k; ++i)
-        if ((rc = dek1_launch_attempts(ctx, 1, flags, mean_ab, sc_ab, 2, err_ab, ref_ab, stream, "tdx_dek1_enqueue_attempts"))) return rc;
+        if ((rc = dek1_launch_attempts(ctx, 1, 0, flags, mean_ab, sc_ab, 2, err_ab, ref_ab, stream, "tdx_dek1_enqueue_attempts"))) return rc;
     return TDX_OK;
 }
 
@@ -1538,7 +1542,7 @@ extern "C" int tdx_ek0_enqueue_attempts(tdx_ctx* ctx, int k, uint32_t flags, voi
     void* err_ab[2] = {err_out, err_out};
     void* ref_ab[2] = {ref_out, ref_out};
     for (int i = 0; i < k; ++i)
-        if ((rc = ek0_launch_attempts(ctx, 1, flags, mean_ab, Cl_ab, 2, err_ab, ref_ab, stream, "tdx_ek0_enqueue_attempts"))) return rc;
+        if ((rc = ek0_launch_attempts(ctx, 1, 0, flags, mean_ab, Cl_ab, 2, err_ab, ref_ab, stream, "tdx_ek0_enqueue_attempts"))) return rc;
     return TDX_OK;
 }
 
@@ -1557,7 +1561,7 @@ extern "C" int tdx_ctl_read(tdx_ctx* ctx, tdx_ctl_state* out, double* hist_t, do
     out->attempts = c.attempts; out->accepted = c.accepted;
     out->cur = c.cur; out->done = c.done; out->failed = c.failed; out->reserved = 0;
     if (comm_err != 0ull && out->failed == 0) {      // a peer wait timed out somewhere in the batch
-        out->failed = 2;
+        out->failed = TDX_FAIL_PEER;
         out->done = 1;
     }
     if (hist_t) std::memcpy(hist_t, c.hist_t, sizeof(c.hist_t));
@@ -1579,15 +1583,6 @@ extern "C" int tdx_ctl_history(tdx_ctx* ctx, int64_t state_index, double* t, dou
     if (t) *t = ctx->feed->hist_t[slot];
     if (dt) *dt = ctx->feed->hist_dt[slot];
     if (attempts) *attempts = (int64_t)ctx->feed->hist_att[slot];
-    return TDX_OK;
-}
-
-extern "C" int tdx_ctl_consume(tdx_ctx* ctx, int64_t upto) {
-    if (!ctx || !ctx->feed) return fail(TDX_ERR_INVALID, "tdx_ctl_consume: call tdx_ctl_begin_ex with follow = 1 first");
-    if (upto >= 0 && (unsigned long long)upto + 1ull > ctx->feed->consumed) {
-        ctx->feed->consumed = (unsigned long long)upto + 1ull;
-        __sync_synchronize();
-    }
     return TDX_OK;
 }
 

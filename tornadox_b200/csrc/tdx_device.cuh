@@ -88,7 +88,7 @@ constexpr int kMaxRing = 8;              // state buffers a controller-driven so
 struct HostFeed {
     volatile unsigned long long accepted;      // kernel -> host: accepted states so far (state j lives in ring slot j % nbuf)
     volatile unsigned long long attempts;
-    volatile unsigned long long consumed;      // host -> kernel: NUMBER of states released, i.e. states [0, consumed) have been copied out
+    volatile unsigned long long reserved;
     volatile unsigned long long abort;         // host -> kernel: stop at the next attempt boundary
     volatile double hist_t[kCtlHistory];       // time / step of accepted state j at [j % kCtlHistory]
     volatile double hist_dt[kCtlHistory];
@@ -102,7 +102,7 @@ struct StepCtl {
     int adaptive, nu;
     int cur;                              // ring slot that holds the current state
     int done;                             // t reached tmax (or the norm became NaN): further attempts do nothing
-    int failed;                           // 1: the error estimate became NaN; 2: an in-kernel wait timed out (peer / barrier)
+    int failed;                           // 1: the error estimate became NaN; >= 2: an in-kernel wait timed out (TDX_FAIL_*)
     int nbuf;                             // ring size (2: plain ping-pong)
     long long attempts, accepted;
     double last_norm;
@@ -110,7 +110,7 @@ struct StepCtl {
     // time stops (odefilter.py:355-373): sorted device array, index of the stop the solve is heading for
     const double* stops;
     int n_stops, next_stop;
-    // dense output: wait until the host has drained a ring slot before it is written again (null: nobody follows)
+    // dense output: progress reports for a host that follows the solve (null: nobody follows)
     HostFeed* feed;
     long long wait_timeout_ns;            // in-kernel waits give up after this long and fail the solve
     double hist_t[kCtlHistory];           // times of the accepted states, ring indexed by (accepted - 1) % kCtlHistory
@@ -139,6 +139,8 @@ __device__ __forceinline__ unsigned long long global_timer_ns() {
     return t;
 }
 constexpr unsigned long long kDefaultWaitNs = 4000000000ull;
+// why a controller-driven solve stopped (StepCtl::failed / tdx_ctl_state::failed)
+enum : int { TDX_FAIL_NAN = 1, TDX_FAIL_POISONED = 2, TDX_FAIL_GRID_BARRIER = 3, TDX_FAIL_HOST_FEED = 4, TDX_FAIL_PEER = 5 };
 
 // development aid (-DTDX_TIMELINE): CTA 0 records when it passes the stations of an attempt (scripts/attempt_timeline.py)
 #ifdef TDX_TIMELINE
@@ -179,7 +181,7 @@ __device__ inline void ctl_update(StepCtl* ctl, double sum, double d_global) {
         dt_next = fmin(factor * dt, ctl->tmax - (accepted ? t + dt : t));           // odefilter.py:214-219
     } else {
         if (sum != sum) {                                                            // a poisoned attempt (timed-out wait)
-            if (ctl->failed == 0) ctl->failed = 2;
+            if (ctl->failed == 0) ctl->failed = TDX_FAIL_POISONED;
             ctl->done = 1;
             return;
         }

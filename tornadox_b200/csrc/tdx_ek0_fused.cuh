@@ -41,7 +41,7 @@ struct Ek0FusedCfg {
     static constexpr int AT_ROW = W + 2;                  // [left edge][W own][right edge]
     static constexpr int AT_ELEMS = 2 * 2 * AT_ROW;       // [slot][field][AT_ROW]
     static constexpr size_t BAR_BYTES = 128, RED_BYTES = 512;
-    static constexpr size_t TREE_BYTES = 3 * (size_t)W_ * sizeof(double);    // RowTree levels
+    static constexpr size_t TREE_BYTES = 2 * (size_t)W_ * sizeof(double);    // levels 1 and 2 of the row-block trees
     __host__ __device__ static constexpr size_t at_bytes() { return ((size_t)AT_ELEMS * sizeof(T) + 127) / 128 * 128; }
     __host__ __device__ static constexpr size_t stage_bytes() { return (size_t)STAGE_ELEMS * sizeof(T); }
     __host__ __device__ static constexpr size_t total() { return BAR_BYTES + RED_BYTES + TREE_BYTES + at_bytes() + STAGES * stage_bytes(); }
@@ -87,6 +87,7 @@ struct Ek0FusedArgs {
     // device-resident step controller (kCtl instantiation)
     StepCtl* ctl;
     int max_attempts;
+    long long max_accepted;          // stop the launch after this many newly accepted steps (0: no limit)
 };
 
 struct StripGeom {
@@ -94,53 +95,17 @@ struct StripGeom {
     int b0;                  // local index of the strip's first row block
 };
 
-// The error-norm and z^T z sums of the fhn kernel are formed per ROW BLOCK of R grid rows (aligned in GLOBAL row numbers)
-// and 256-column strip: every thread adds its column's terms of the block's rows in a balanced binary tree -- the same
-// additions whether the strip walks the rows upwards or downwards -- then the lanes go through the shuffle tree and the
-// warps through shared memory.  Strips are whole numbers of row blocks, so a block's partial is a fixed function of the
-// block's coordinates: independent of how many strips, CTAs or GPUs the grid is cut into.  R = 8 for large grids (one shuffle
-// tree per 8 rows costs nothing); small grids take R = 4, 2, 1 so that there are still enough strips to fill the device
-// (ek0_row_block: a function of the GLOBAL grid only, i.e. the same on every rank count).
-constexpr int kMaxRowBlock = 8;
-
+// The error-norm and z^T z sums of the fhn kernel are formed per ROW BLOCK of RB grid rows (aligned in GLOBAL row numbers)
+// and 256-column strip.  RB = 8 (template parameter) for large grids: every thread adds its column's terms of the block's
+// rows in a balanced binary tree -- the same additions whether the strip walks the rows upwards or downwards; a row that is
+// missing because the grid / shard ends inside a block counts as +0.0, which is exact -- then the lanes go through the
+// shuffle tree and the warps through shared memory, once per 8 rows.  Strips are whole numbers of row blocks, so a block's
+// partial is a fixed function of the block's coordinates: independent of how many strips, CTAs or GPUs the grid is cut into.
+// Small grids take RB = 1 (one shuffle tree per row) so that there are still enough strips to fill the device
+// (ek0_row_block: a function of the GLOBAL grid only, i.e. the same for every number of ranks).
 __host__ __device__ inline int ek0_row_block(long long global_rows, int col_blocks) {
-    for (int r = kMaxRowBlock; r > 1; r >>= 1)
-        if (((global_rows + r - 1) / r) * col_blocks >= 512) return r;
-    return 1;
+    return ((global_rows + 7) / 8) * col_blocks >= 256 ? 8 : 1;
 }
-
-// Streaming balanced tree over the kRowBlock leaves of a block (binary counter).  The three pending partial sums of a thread
-// live in shared memory ([level][thread]; registers are the scarce resource of the kernel), the leaf position comes from the row.
-// Missing leaves (grid / shard ends inside a block) count as +0.0, which is exact.
-template <int W>
-struct RowTree {
-    double* lv;              // this thread's level-0 slot; levels are W doubles apart
-    __device__ __forceinline__ void reset() { lv[0] = lv[W] = lv[2 * W] = 0.0; }
-    // leaf number ``c`` (0 .. R - 1 in walking order, R = 1, 2, 4 or 8) with value v; returns true when the block is complete,
-    // ``v`` then holds the block's sum
-    __device__ __forceinline__ bool push(int c, double& v, int R) {
-        if (R == 1) return true;
-        if (!(c & 1)) {
-            lv[0] = v;
-            return false;
-        }
-        v += lv[0];
-        if (R == 2) return true;
-        if (!(c & 2)) {
-            lv[W] = v;
-            return false;
-        }
-        v += lv[W];
-        if (R == 4) return true;
-        if (!(c & 4)) {
-            lv[2 * W] = v;
-            return false;
-        }
-        v += lv[2 * W];
-        return true;
-    }
-};
-static_assert(kMaxRowBlock == 8, "RowTree has three levels");
 
 // calibration, the single stacked QR, gain, factor update (one thread, fp64)   ek0.py:123-140,175,182
 template <typename T, int N>
@@ -265,6 +230,7 @@ struct Ek0CtaState {
     int cur, out;                    // ring slots of the attempt's input / output state (cur < 0: stop)
     int flag, ok;
     unsigned long long epoch0;
+    long long pause_at;
     uint64_t m1_bar;                 // the producer warp has published m1[attempt & 1]
     double m1[2][kMaxN + 1];
     double timed_out;                // the wait for the global sum of z^2 timed out
@@ -277,10 +243,14 @@ __device__ __forceinline__ bool ek0_attempt_begin(const Ek0FusedArgs<T, N>& a, E
         if constexpr (kCtl) {
             StepCtl* ctl = a.ctl;
             bool ok = true;
-            if (att == 0) sh.epoch0 = ld_acquire_gpu(&ctl->epoch);
-            else ok = spin_until_gpu(&ctl->epoch, sh.epoch0 + (unsigned long long)att, (unsigned long long)ctl->wait_timeout_ns);
+            if (att == 0) {
+                sh.epoch0 = ld_acquire_gpu(&ctl->epoch);
+                sh.pause_at = a.max_accepted > 0 ? ctl->accepted + a.max_accepted : (long long)0x7fffffffffffffffLL;
+            } else {
+                ok = spin_until_gpu(&ctl->epoch, sh.epoch0 + (unsigned long long)att, (unsigned long long)ctl->wait_timeout_ns);
+            }
             if (!ok) {
-                ctl->failed = 2;
+                ctl->failed = TDX_FAIL_GRID_BARRIER;
                 ctl->done = 1;
             }
             Consts<T, N> cc = a.c;
@@ -297,7 +267,7 @@ __device__ __forceinline__ bool ek0_attempt_begin(const Ek0FusedArgs<T, N>& a, E
             sh.c = cc;
             sh.cd = ccd;
             const int cur = ctl->cur, nbuf = ctl->nbuf;
-            sh.cur = (ctl->done || !ok) ? -1 : cur;
+            sh.cur = (ctl->done || !ok || ctl->accepted >= sh.pause_at) ? -1 : cur;
             sh.out = (cur + 1) % nbuf;
         } else {
             sh.cur = 0;
@@ -394,8 +364,9 @@ __device__ __forceinline__ void ek0_end_barrier(const Ek0FusedArgs<T, N>& a, Ek0
 }
 
 // Threads [0, W): consumers, thread t owns column c0 + t of both fields.  Threads [W, W + 32): the producer warp.
-template <typename T, int N, int W, bool kCtl = false>
+template <typename T, int N, int W, bool kCtl = false, int RB = 8>
 __global__ void __maxnreg__(TDX_EK0_MAXREG) ek0_fused_fhn_kernel(const __grid_constant__ Ek0FusedArgs<T, N> a) {
+    static_assert(RB == 1 || RB == 8, "row blocks of 1 or 8 grid rows");
     using Cfg = Ek0FusedCfg<T, N, W>;
     using CSync = NamedSync<1, W>;                         // the consumers' barrier (the producer warp never joins)
     constexpr int PADC = Cfg::PADC, WP = Cfg::WP, S = Cfg::STAGES, AT_ROW = Cfg::AT_ROW;
@@ -403,7 +374,7 @@ __global__ void __maxnreg__(TDX_EK0_MAXREG) ek0_fused_fhn_kernel(const __grid_co
     uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);                                   // [S] data has landed
     uint64_t* empty = full + S;                                                               // [S] consumers are done
     double* s_red = reinterpret_cast<double*>(smem_raw + Cfg::BAR_BYTES);                     // see kEk0Red*
-    double* s_tree = reinterpret_cast<double*>(smem_raw + Cfg::BAR_BYTES + Cfg::RED_BYTES);   // [3][W]
+    double* s_tree = reinterpret_cast<double*>(smem_raw + Cfg::BAR_BYTES + Cfg::RED_BYTES);   // [2][W]
     T* s_at = reinterpret_cast<T*>(smem_raw + Cfg::BAR_BYTES + Cfg::RED_BYTES + Cfg::TREE_BYTES);               // [2][2][AT_ROW]
     T* s_stage = reinterpret_cast<T*>(smem_raw + Cfg::BAR_BYTES + Cfg::RED_BYTES + Cfg::TREE_BYTES + Cfg::at_bytes());
     __shared__ Ek0CtaState<T, N> sh;
@@ -457,7 +428,7 @@ __global__ void __maxnreg__(TDX_EK0_MAXREG) ek0_fused_fhn_kernel(const __grid_co
 #pragma unroll 1
                 for (int kk = 0; kk < ns; ++kk) {
                     const int k = phase ? ns - 1 - kk : kk;
-                    StripGeom s = strip_geom<W>(g, blockIdx.x + (unsigned)k * gridDim.x, a.col_blocks, a.chunks, a.block0, a.nblocks, a.row_block, has_lo, has_hi);
+                    StripGeom s = strip_geom<W>(g, blockIdx.x + (unsigned)k * gridDim.x, a.col_blocks, a.chunks, a.block0, a.nblocks, RB, has_lo, has_hi);
                     if (phase) s.dir = -s.dir;
                     const int L = s.r1 - s.r0 + 2;
                     const int gs = max(s.c0 - PADC, 0), ge = min(s.c0 + W + PADC, g.cols);
@@ -507,7 +478,7 @@ __global__ void __maxnreg__(TDX_EK0_MAXREG) ek0_fused_fhn_kernel(const __grid_co
                 pack_halo_part<T, N, CSync, kCtl>(g, c, mean_in, a.pack, a.pack.seq + (unsigned long long)att, part, csync);
 
         bool halos_ready = false, poisoned = false;
-        int pending_unit = -1, first_unit = -1;      // CTA-uniform: the row block whose warp sums wait in s_rowred for the next barrier
+        int pending_unit = -1;                       // CTA-uniform: the row block whose warp sums wait in s_rowred for the next barrier
         int pending_slot = 0;
         const uint64_t pol_keep = l2_policy_evict_last(), pol_stream = l2_policy_evict_first();
         const T inv_dx2 = (T)g.prm[0], pa = (T)g.prm[1], pb = (T)g.prm[2], pk = (T)g.prm[3], inv_tau = (T)g.prm[5];
@@ -540,13 +511,24 @@ __global__ void __maxnreg__(TDX_EK0_MAXREG) ek0_fused_fhn_kernel(const __grid_co
                     pending_unit = -1;
                 }
             };
-            RowTree<W> tree{s_tree + tc};
-            const int kRowBlock = a.row_block;
+            constexpr int kRowBlock = RB;
+            double* lv1 = s_tree + tc;                          // this thread's pending pair / quad sums (RB = 8)
+            double* lv2 = s_tree + W + tc;
+            double t0 = 0.0;                                    // ... and its pending single row
+            int blk = 0;                                        // local index of the row block being summed
+            // a finished block: lanes through the shuffle tree, warps through shared memory (added up after the next barrier)
+            auto emit_block = [&](double v, int cb_, int dir_) {
+                const double ws = warp_sum(v);
+                pending_slot ^= 1;
+                if (lq == 0) s_rowred[(pending_slot & 1) * 8 + wq] = ws;
+                pending_unit = blk * (int)a.col_blocks + cb_;
+                blk += dir_;
+            };
 #pragma unroll 1
             for (int kk = 0; kk < ns; ++kk) {
                 const int k = kUpdate ? ns - 1 - kk : kk;
                 const unsigned strip = blockIdx.x + (unsigned)k * gridDim.x;
-                StripGeom s = strip_geom<W>(g, strip, a.col_blocks, a.chunks, a.block0, a.nblocks, a.row_block, has_lo, has_hi);
+                StripGeom s = strip_geom<W>(g, strip, a.col_blocks, a.chunks, a.block0, a.nblocks, RB, has_lo, has_hi);
                 const int cb = (int)(strip % a.col_blocks);
                 if (kUpdate) s.dir = -s.dir;
                 const int L = s.r1 - s.r0 + 2;
@@ -560,9 +542,18 @@ __global__ void __maxnreg__(TDX_EK0_MAXREG) ek0_fused_fhn_kernel(const __grid_co
                 T at_m1[2] = {}, at_m2[2] = {}, hs_m1[2] = {}, mp_m1[2][NK] = {};
                 bool first_replicated = false;
                 T* out_ptr = mean_out + ((long long)(rr - s.dir) * g.cols + col);      // row being finalised, field 0
-                if (reduces) tree.reset();
-                // local index of the row block the first finalised row belongs to
-                int blk = (int)((g.grow0 + (s.dir > 0 ? s.r0 : s.r1 - 1)) / kRowBlock) - a.block0;
+                // the row block of the strip's first finalised row, and that row's leaf number inside it (in walking order)
+                int leaf = 0;
+                {
+                    const long long first = g.grow0 + (s.dir > 0 ? s.r0 : s.r1 - 1);
+                    blk = (int)(first / kRowBlock) - a.block0;
+                    if (RB == 8) {
+                        const int pos = (int)(first & 7);
+                        leaf = s.dir > 0 ? pos : 7 - pos;
+                        t0 = 0.0;
+                        if (reduces) lv1[0] = lv2[0] = 0.0;
+                    }
+                }
                 // the rows phase B writes last are the rows the NEXT attempt's phase A reads first -> keep those in L2
                 const int keep_from = (kUpdate && hints) ? L - (int)ceilf(a.keep_frac * (float)(s.r1 - s.r0)) : L;
 #pragma unroll 1
@@ -671,23 +662,27 @@ __global__ void __maxnreg__(TDX_EK0_MAXREG) ek0_fused_fhn_kernel(const __grid_co
                             }
                         }
                         if (reduces) {
-                            // leaf number of the finalised row in walking order inside its (global) row block
-                            const int pos = (int)((g.grow0 + (rr - s.dir)) & (kRowBlock - 1));
-                            int leaf = s.dir > 0 ? pos : (kRowBlock - 1 - pos);
-                            bool done = tree.push(leaf, term, kRowBlock);
-                            // the strip's last row ends inside a block (grid / shard end): the missing leaves are zeros
-                            if (i == L - 1)
-                                while (!done) {
-                                    term = 0.0;
-                                    done = tree.push(++leaf, term, kRowBlock);
+                            if (RB == 1) {
+                                emit_block(term, cb, s.dir);
+                            } else {
+                                const int lf = leaf;
+                                leaf = (leaf + 1) & 7;
+                                if (!(lf & 1)) {
+                                    t0 = term;
+                                } else {
+                                    term += t0;
+                                    if (!(lf & 2)) {
+                                        lv1[0] = term;
+                                    } else {
+                                        term += lv1[0];
+                                        if (!(lf & 4)) {
+                                            lv2[0] = term;
+                                        } else {
+                                            term += lv2[0];
+                                            emit_block(term, cb, s.dir);
+                                        }
+                                    }
                                 }
-                            if (done) {
-                                const double ws = warp_sum(term);
-                                pending_slot ^= 1;
-                                if (lq == 0) s_rowred[(pending_slot & 1) * 8 + wq] = ws;
-                                pending_unit = blk * (int)a.col_blocks + cb;
-                                if (first_unit < 0) first_unit = pending_unit;
-                                blk += s.dir;
                             }
                         }
                     }
@@ -700,12 +695,45 @@ __global__ void __maxnreg__(TDX_EK0_MAXREG) ek0_fused_fhn_kernel(const __grid_co
                         for (int r = 0; r < NK; ++r) mp_m1[f][r] = mp_cur[f][r];
                     }
                 }
+                if (RB == 8 && reduces && leaf != 0) {
+                    // the strip ends inside a row block (grid / shard end): the missing rows are zeros
+                    double v = 0.0;
+                    bool have = false;            // v holds a carried partial sum
+                    for (int lf = leaf; lf < 8; ++lf) {
+                        // push a zero leaf: only the carries matter
+                        if (!(lf & 1)) {
+                            t0 = 0.0;
+                            continue;
+                        }
+                        v = 0.0 + t0;
+                        if (!(lf & 2)) {
+                            lv1[0] = v;
+                            continue;
+                        }
+                        v += lv1[0];
+                        if (!(lf & 4)) {
+                            lv2[0] = v;
+                            continue;
+                        }
+                        v += lv2[0];
+                        have = true;
+                    }
+                    if (have) {
+                        csync();                  // a block finished in the strip's last row may still wait for its flush
+                        flush_block_partial();
+                        emit_block(v, cb, s.dir);
+                    }
+                    leaf = 0;
+                }
             }
             if (reduces) {
                 csync();
                 flush_block_partial();
                 csync();
-                if (tc == 0 && poisoned && first_unit >= 0) unit[first_unit] = nan("");   // stale halos: fail the attempt everywhere
+                if (tc == 0 && poisoned && ns > 0) {     // stale halos: fail the attempt everywhere
+                    const StripGeom s0 = strip_geom<W>(g, blockIdx.x, a.col_blocks, a.chunks, a.block0, a.nblocks, RB, has_lo, has_hi);
+                    unit[s0.b0 * (int)a.col_blocks + (int)(blockIdx.x % a.col_blocks)] = nan("");
+                }
             }
         };
 
@@ -760,9 +788,10 @@ struct Ek0ChainCfg {
     static constexpr int THREADS = kThreads + 32;                     // consumers + producer warp (which also does the n x n algebra)
     static constexpr int STAGE_ELEMS = N * kThreads;                 // [derivative][thread]
     static constexpr size_t BAR_BYTES = 128, RED_BYTES = 512;
+    static constexpr size_t TERM_BYTES = 2 * kThreads * sizeof(double);   // a tile's per-coordinate terms, double-buffered
     __host__ __device__ static constexpr size_t at_bytes(int at_elems) { return ((size_t)at_elems * sizeof(T) + 127) / 128 * 128; }
     __host__ __device__ static constexpr size_t total(int at_elems) {
-        return BAR_BYTES + RED_BYTES + 2 * at_bytes(at_elems) + STAGES * (size_t)STAGE_ELEMS * sizeof(T);
+        return BAR_BYTES + RED_BYTES + TERM_BYTES + 2 * at_bytes(at_elems) + STAGES * (size_t)STAGE_ELEMS * sizeof(T);
     }
 };
 
@@ -777,9 +806,10 @@ __global__ void __maxnreg__(72) ek0_fused_chain_kernel(const __grid_constant__ E
     uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);
     uint64_t* empty = full + S;
     double* s_red = reinterpret_cast<double*>(smem_raw + Cfg::BAR_BYTES);
-    T* s_at0 = reinterpret_cast<T*>(smem_raw + Cfg::BAR_BYTES + Cfg::RED_BYTES);
+    double* s_term = reinterpret_cast<double*>(smem_raw + Cfg::BAR_BYTES + Cfg::RED_BYTES);    // [2][kThreads]
+    T* s_at0 = reinterpret_cast<T*>(smem_raw + Cfg::BAR_BYTES + Cfg::RED_BYTES + Cfg::TERM_BYTES);
     constexpr size_t AT_STRIDE = Cfg::at_bytes(E::ELEMS) / sizeof(T);
-    T* s_stage = reinterpret_cast<T*>(smem_raw + Cfg::BAR_BYTES + Cfg::RED_BYTES + 2 * Cfg::at_bytes(E::ELEMS));
+    T* s_stage = reinterpret_cast<T*>(smem_raw + Cfg::BAR_BYTES + Cfg::RED_BYTES + Cfg::TERM_BYTES + 2 * Cfg::at_bytes(E::ELEMS));
     __shared__ Ek0CtaState<T, N> sh;
 
     const Geo& g = a.g;
@@ -860,7 +890,6 @@ __global__ void __maxnreg__(72) ek0_fused_chain_kernel(const __grid_constant__ E
 
         // ---- consumers ------------------------------------------------------------------------------------------------
         CSync csync;
-        double* s_tilered = s_red + kEk0RowRed;
         const int wq = tid >> 5, lq = tid & 31;
         if (a.pack.enabled)
             for (int part = (int)blockIdx.x; part < 2 * kPackCtas; part += (int)gridDim.x)
@@ -878,13 +907,15 @@ __global__ void __maxnreg__(72) ek0_fused_chain_kernel(const __grid_constant__ E
         auto run_phase = [&](auto update_tag, double* unit) {
             constexpr bool kUpdate = decltype(update_tag)::value;
             const bool reduces = !kUpdate || c.want_norm || (kCtl && a.reduce_b.world > 0);
+            // one warp (rotating) adds the tile's 256 terms in a fixed order, see dek1_kernel
             auto flush_tile_partial = [&](unsigned cq_prev) {
-                if (tid == 0 && pending_unit >= 0) {
-                    const double* ws = s_tilered + (cq_prev & 1u) * 8;
-                    double b = 0.0;
-#pragma unroll
-                    for (int i = 0; i < kWarps; ++i) b += ws[i];
-                    unit[pending_unit] = b;
+                if (pending_unit >= 0) {
+                    if (wq == (int)(cq_prev & (unsigned)(kWarps - 1))) {
+                        const double* v = s_term + (cq_prev & 1u) * kThreads + lq;
+                        double x = ((v[0] + v[32]) + (v[64] + v[96])) + ((v[128] + v[160]) + (v[192] + v[224]));
+                        x = warp_sum(x);
+                        if (lq == 0) unit[pending_unit] = x;
+                    }
                     pending_unit = -1;
                 }
             };
@@ -928,9 +959,8 @@ __global__ void __maxnreg__(72) ek0_fused_chain_kernel(const __grid_constant__ E
                     }
                 }
                 if (reduces) {
-                    const double ws = warp_sum(term);
-                    if (lq == 0) s_tilered[(cq & 1u) * 8 + wq] = ws;
-                    if (tid == 0) pending_unit = (int)tile;
+                    s_term[(cq & 1u) * kThreads + tid] = term;
+                    pending_unit = (int)tile;
                 }
             }
             if (reduces) {

@@ -283,6 +283,7 @@ struct DekArgs {
     T* err_ring[kMaxRing];             // per-slot error_estimate / reference_state vectors (null entries: not written)
     T* ref_ring[kMaxRing];
     int max_attempts;
+    long long max_accepted;            // stop the launch after this many newly accepted steps (0: no limit)
     double d_global;
 };
 
@@ -296,36 +297,25 @@ struct DekSmem {
     // registers for a third and fourth CTA, which is what hides the front end's load latency when there are few factor bytes
     // per coordinate to wait for (8.4 M dimensions, fp64: nu = 1 39 -> 53 %, nu = 2 63 -> 81 %, nu = 3 78 -> 85 % of the roofline)
     static constexpr int MIN_BLOCKS = (N <= 2) ? TDX_MIN_BLOCKS_N2 : (N == 3) ? TDX_MIN_BLOCKS_N3 : (N == 4) ? TDX_MIN_BLOCKS_N4 : TDX_MIN_BLOCKS;
-    static constexpr int SC_SLOTS = (MIN_BLOCKS * (L::BAR_BYTES + L::RED_BYTES + 2 * 4096 + 2 * L::sc_bytes() + 1024) <= 225 * 1024) ? 2 : 1;
+    static constexpr size_t TERM_BYTES = 2 * kThreads * sizeof(double);   // the tile's per-coordinate norm terms, double-buffered
+    static constexpr int SC_SLOTS = (MIN_BLOCKS * (L::BAR_BYTES + L::RED_BYTES + TERM_BYTES + 2 * 3328 + 2 * L::sc_bytes() + 1024) <= 225 * 1024) ? 2 : 1;
     __host__ __device__ static constexpr size_t total(int at_elems) {
-        return L::BAR_BYTES + L::RED_BYTES + SLOTS * L::at_bytes(at_elems) + SC_SLOTS * L::sc_bytes();
+        return L::BAR_BYTES + L::RED_BYTES + TERM_BYTES + SLOTS * L::at_bytes(at_elems) + SC_SLOTS * L::sc_bytes();
     }
 };
 
 // What the last CTA of a controller-driven attempt does once the global norm sum is known: decide (ctl_update), tell the
-// host feed, wait for the ring slot the next attempt writes to, publish the decision (epoch) to the other CTAs.
+// host feed, publish the decision (epoch) to the other CTAs.
 __device__ inline void ctl_finish_attempt(StepCtl* ctl, double total, double d_global, unsigned long long epoch_next) {
     ctl_update(ctl, total, d_global);
     HostFeed* fd = ctl->feed;
     if (fd != nullptr) {
+        // a host that follows the solve: progress goes to mapped pinned memory (the launch itself is bounded by max_accepted,
+        // so the ring never wraps onto a state the host has not copied yet)
         __threadfence_system();
         fd->attempts = (unsigned long long)ctl->attempts;
         fd->accepted = (unsigned long long)ctl->accepted;
-        __threadfence_system();
         if (fd->abort != 0ull) ctl->done = 1;
-        if (!ctl->done) {
-            // the next attempt writes ring slot (cur + 1) % nbuf, which holds accepted state number accepted + 1 - nbuf
-            const long long need = ctl->accepted + 1 - (long long)ctl->nbuf;
-            const unsigned long long t0 = global_timer_ns();
-            while (need >= 0 && (long long)fd->consumed <= need) {
-                if (fd->abort != 0ull || global_timer_ns() - t0 > (unsigned long long)(ctl->wait_timeout_ns > 0 ? 16 * ctl->wait_timeout_ns : 64000000000ll)) {
-                    ctl->done = 1;
-                    if (fd->abort == 0ull && ctl->failed == 0) ctl->failed = 2;
-                    break;
-                }
-                __nanosleep(500);
-            }
-        }
     }
     __threadfence();
     st_release_gpu(&ctl->epoch, epoch_next);
@@ -343,15 +333,18 @@ __global__ void __launch_bounds__(kThreads, DekSmem<T, N>::MIN_BLOCKS) dek1_kern
     constexpr int NN = L::NN, STRIDE = L::STRIDE;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);                       // [2][kWarps]
-    double* s_red = reinterpret_cast<double*>(smem_raw + L::BAR_BYTES);          // [2][kWarps] per-tile warp sums; final reduction
-    T* s_at0 = reinterpret_cast<T*>(smem_raw + L::BAR_BYTES + L::RED_BYTES);      // [2][AT_ELEMS]
-    T* s_sc0 = reinterpret_cast<T*>(smem_raw + L::BAR_BYTES + L::RED_BYTES + 2 * L::at_bytes(ExtTile<IVP>::ELEMS));
+    double* s_red = reinterpret_cast<double*>(smem_raw + L::BAR_BYTES);          // final reduction scratch
+    double* s_term = reinterpret_cast<double*>(smem_raw + L::BAR_BYTES + L::RED_BYTES);   // [2][kThreads] norm terms of a tile
+    constexpr size_t kHead = L::BAR_BYTES + L::RED_BYTES + DekSmem<T, N>::TERM_BYTES;
+    T* s_at0 = reinterpret_cast<T*>(smem_raw + kHead);                            // [2][AT_ELEMS]
+    T* s_sc0 = reinterpret_cast<T*>(smem_raw + kHead + 2 * L::at_bytes(ExtTile<IVP>::ELEMS));
     constexpr size_t AT_STRIDE = L::at_bytes(ExtTile<IVP>::ELEMS) / sizeof(T);
     constexpr size_t SC_STRIDE = L::sc_bytes() / sizeof(T);
     __shared__ int s_flag, s_ok;
     __shared__ Consts<T, N> s_c;                  // kCtl: the attempt's constants, rebuilt from the controller block
     __shared__ int s_cur, s_out;
     __shared__ unsigned long long s_epoch0;
+    __shared__ long long s_pause_at;
 
     const Geo& g = a.g;
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -381,10 +374,14 @@ __global__ void __launch_bounds__(kThreads, DekSmem<T, N>::MIN_BLOCKS) dek1_kern
             if (threadIdx.x == 0) {
                 StepCtl* ctl = a.ctl;
                 bool ok = true;
-                if (att == 0) s_epoch0 = ld_acquire_gpu(&ctl->epoch);
-                else ok = spin_until_gpu(&ctl->epoch, s_epoch0 + (unsigned long long)att, (unsigned long long)ctl->wait_timeout_ns);
+                if (att == 0) {
+                    s_epoch0 = ld_acquire_gpu(&ctl->epoch);
+                    s_pause_at = a.max_accepted > 0 ? ctl->accepted + a.max_accepted : (long long)0x7fffffffffffffffLL;
+                } else {
+                    ok = spin_until_gpu(&ctl->epoch, s_epoch0 + (unsigned long long)att, (unsigned long long)ctl->wait_timeout_ns);
+                }
                 if (!ok) {                        // the grid barrier timed out (a CTA or a peer rank is gone): fail the solve
-                    ctl->failed = 2;
+                    ctl->failed = TDX_FAIL_GRID_BARRIER;
                     ctl->done = 1;
                 }
                 Consts<T, N> cc = a.c;            // Ql, tolerances and flags come with the launch, the step with the controller
@@ -396,7 +393,7 @@ __global__ void __launch_bounds__(kThreads, DekSmem<T, N>::MIN_BLOCKS) dek1_kern
                 cc.dt = (T)ctl->dt;
                 s_c = cc;
                 const int cur = ctl->cur, nbuf = ctl->nbuf;
-                s_cur = (ctl->done || !ok) ? -1 : cur;
+                s_cur = (ctl->done || !ok || ctl->accepted >= s_pause_at) ? -1 : cur;
                 s_out = (cur + 1) % nbuf;
             }
             __syncthreads();
@@ -463,18 +460,21 @@ __global__ void __launch_bounds__(kThreads, DekSmem<T, N>::MIN_BLOCKS) dek1_kern
         bool cur_bulk = false;
         if (tile < a.num_tiles) cur_bulk = stage_in(tile_coord<Shape>(g, a.ranges.tile(tile), a.tiles_x), 0);
 
-        // after a barrier that follows the tile's warp sums: the tile's partial = the 8 warp sums in a fixed tree; one lane of
-        // a warp that changes from tile to tile does it (no warp is always the one the next barrier waits for)
+        // After a barrier that follows the tile's terms: ONE warp (a different one from tile to tile, so that no warp is always
+        // the one the next barrier waits for) adds the 256 terms in a fixed order -- lane l the eight warps' terms of lane l in a
+        // tree, then the shuffle tree over the lanes.  A fixed function of the tile's coordinates, whoever computes it.
         auto flush_tile_partial = [&](unsigned it_prev) {
             if (pending_unit >= 0) {
-                if (threadIdx.x == ((it_prev & (unsigned)(kWarps - 1)) << 5)) {
-                    const double* ws = s_red + (it_prev & 1u) * kWarps;
-                    a.red.unit[pending_unit] = ((ws[0] + ws[1]) + (ws[2] + ws[3])) + ((ws[4] + ws[5]) + (ws[6] + ws[7]));
+                if (w == (int)(it_prev & (unsigned)(kWarps - 1))) {
+                    const double* v = s_term + (it_prev & 1u) * kThreads + lane;
+                    double x = ((v[0] + v[32]) + (v[64] + v[96])) + ((v[128] + v[160]) + (v[192] + v[224]));
+                    x = warp_sum(x);
+                    if (lane == 0) a.red.unit[pending_unit] = x;
                 }
                 pending_unit = -1;
             }
         };
-        static_assert(kWarps == 8, "the tile partial adds eight warp sums");
+        static_assert(kWarps == 8, "the tile partial adds eight warps' terms");
 
         unsigned it = 0;
         for (; tile < a.num_tiles; ++it) {
@@ -623,10 +623,8 @@ __global__ void __launch_bounds__(kThreads, DekSmem<T, N>::MIN_BLOCKS) dek1_kern
                 next_bulk = stage_in(tile_coord<Shape>(g, a.ranges.tile(next), a.tiles_x), 0);
             }
             if (unit_mode && (c.want_norm || (kCtl && kComm && a.reduce.world > 0))) {
-                // the tile's share of the norm (after the stores are on their way): lanes through the shuffle tree, the warps
-                // through shared memory after the next barrier
-                const double ws = warp_sum(ratio_sq);
-                if (lane == 0) s_red[(it & 1u) * kWarps + w] = ws;
+                // the coordinate's share of the norm: one shared-memory store now, the tile's sum after the next barrier
+                s_term[(it & 1u) * kThreads + threadIdx.x] = ratio_sq;
                 pending_unit = (int)tile_id;
             }
             tile = next;

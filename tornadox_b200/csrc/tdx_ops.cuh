@@ -35,6 +35,7 @@ struct Workspace {
     long long unit_cap;
     unsigned long long* cl_flag;   // fused KroneckerEK0: "the attempt's new factor has been written"
     unsigned long long cl_seq;
+    long long max_accepted;        // controller launches: stop after this many newly accepted steps (0: no limit)
 };
 
 // unit partials of a tile-based launch (one unit per tile, numbered row-major over the global tile grid)
@@ -217,6 +218,7 @@ struct Launch {
         a.ctl = ctl;
         a.d_global = d_global;
         a.max_attempts = max_attempts;
+        a.max_accepted = ws.max_accepted;
         for (int i = 0; i < kMaxRing; ++i) {
             a.mean_ring[i] = (ctl && i < nbuf) ? (T*)mean_ring[i] : nullptr;
             a.sc_ring[i] = (ctl && i < nbuf) ? (T*)sc_ring[i] : nullptr;
@@ -374,10 +376,10 @@ struct Launch {
                               cudaStream_t st, StepCtl* ctl) {
         constexpr int W = TDX_EK0_W;
         using Cfg = Ek0FusedCfg<T, N, W>;
-        constexpr auto kern = ek0_fused_fhn_kernel<T, N, W, kCtl>;
         Ek0FusedArgs<T, N> a;
         a.ctl = ctl;
         a.max_attempts = max_attempts;
+        a.max_accepted = ws.max_accepted;
         bool aligned16 = true;
         for (int i = 0; i < kMaxRing; ++i) {
             a.mean_ring[i] = i < nbuf ? (T*)mean_ring[i] : nullptr;
@@ -425,14 +427,22 @@ struct Launch {
         }
         constexpr int PADC = Cfg::PADC;
         a.use_bulk = (g.cols % PADC == 0) && aligned16 ? 1 : 0;
+        a.col_blocks = (unsigned)((g.cols + W - 1) / W);
+        // strips are whole row blocks (8 grid rows, or single rows on small grids; aligned in global row numbers)
+        if (ek0_row_block(g.grows, (int)a.col_blocks) == 8) return launch_fhn<kCtl, 8>(g, a, ws, st);
+        return launch_fhn<kCtl, 1>(g, a, ws, st);
+    }
+
+    template <bool kCtl, int RB>
+    static int launch_fhn(const Geo& g, Ek0FusedArgs<T, N>& a, const Workspace& ws, cudaStream_t st) {
+        constexpr int W = TDX_EK0_W;
+        using Cfg = Ek0FusedCfg<T, N, W>;
+        constexpr auto kern = ek0_fused_fhn_kernel<T, N, W, kCtl, RB>;
         unsigned resident = 0;
         TDX_CUDA_TRY(persistent_grid<kern>(Cfg::total(), 1LL << 40, 0, resident, Cfg::THREADS));
-        a.col_blocks = (unsigned)((g.cols + W - 1) / W);
-        // strips are whole row blocks (R grid rows, aligned in global row numbers): see RowTree
-        const int kRowBlock = ek0_row_block(g.grows, (int)a.col_blocks);
-        a.row_block = kRowBlock;
-        a.block0 = (int)(g.grow0 / kRowBlock);
-        a.nblocks = (int)((g.grow0 + g.rows + kRowBlock - 1) / kRowBlock) - a.block0;
+        a.row_block = RB;
+        a.block0 = (int)(g.grow0 / RB);
+        a.nblocks = (int)((g.grow0 + g.rows + RB - 1) / RB) - a.block0;
         unsigned chunks = resident / a.col_blocks;
         if (chunks < 1u) chunks = 1u;
         if (chunks > (unsigned)a.nblocks) chunks = (unsigned)a.nblocks;
@@ -443,7 +453,7 @@ struct Launch {
         const long long units = (long long)a.nblocks * a.col_blocks;
         if (units > ws.unit_cap) return (int)cudaErrorInvalidValue;
         a.red_a = RedPlan{ws.unit_a, (unsigned)units, (unsigned long long)a.block0 * a.col_blocks,
-                          (unsigned long long)((g.grows + kRowBlock - 1) / kRowBlock) * a.col_blocks};
+                          (unsigned long long)((g.grows + RB - 1) / RB) * a.col_blocks};
         a.red_b = a.red_a;
         a.red_b.unit = ws.unit_b;
         // L2 residency hints: keep as many rows of every strip as fit the budget; everything fits -> no hints at all

@@ -96,8 +96,9 @@ class KroneckerEK0(odefilter.ODEFilter):
             refs = [torch.full((mean0.shape[1],), float("nan"), dtype=mean0.dtype, device=mean0.device) for _ in range(nbuf)]
         return dict(means=means, factors=factors, errs=errs, refs=refs)
 
-    def _ctl_launch(self, k, ring, stream=None):
-        self.engine.ek0_run_attempts(k, ring["means"], ring["factors"], ring["errs"], ring["refs"], stream=stream)
+    def _ctl_launch(self, k, ring, stream=None, max_accepted=0):
+        self.engine.ek0_run_attempts(k, ring["means"], ring["factors"], ring["errs"], ring["refs"], stream=stream,
+                                     max_accepted=max_accepted)
 
     def _ctl_state(self, ring, slot, t):
         mean = ring["means"][slot]

@@ -134,9 +134,9 @@ class BatchedEK1(odefilter.ODEFilter):
             refs = [torch.full((d,), float("nan"), dtype=mean0.dtype, device=mean0.device) for _ in range(nbuf)]
         return dict(means=means, factors=factors, errs=errs, refs=refs)
 
-    def _ctl_launch(self, k, ring, stream=None):
+    def _ctl_launch(self, k, ring, stream=None, max_accepted=0):
         self.engine.dek1_run_attempts(k, ring["means"], ring["factors"], ring["errs"], ring["refs"],
-                                      jacobian=self._uses_jacobian, stream=stream)
+                                      jacobian=self._uses_jacobian, stream=stream, max_accepted=max_accepted)
 
     def _ctl_state(self, ring, slot, t):
         err = ring["errs"][slot] if ring["errs"] is not None else None

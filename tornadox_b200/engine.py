@@ -26,12 +26,7 @@ _RED_CHUNKS = 16      # kRedChunks in csrc/tdx_device.cuh
 
 def _ek0_row_block(global_rows, col_blocks):
     """Row-block height of the fused fhn_2d KroneckerEK0 kernel's sums (ek0_row_block in csrc/tdx_ek0_fused.cuh)."""
-    r = 8
-    while r > 1:
-        if -(-global_rows // r) * col_blocks >= 512:
-            return r
-        r //= 2
-    return 1
+    return 8 if -(-global_rows // 8) * col_blocks >= 256 else 1
 
 
 def _chunk_aligned_bounds(spec, world):
@@ -584,9 +579,6 @@ class StepEngine:
         _lib.check(self.lib.tdx_ctl_history(self.handle, int(state_index), ctypes.byref(t), ctypes.byref(dt), ctypes.byref(att)))
         return t.value, dt.value, int(att.value)
 
-    def ctl_consume(self, upto):
-        _lib.check(self.lib.tdx_ctl_consume(self.handle, int(upto)))
-
     def ctl_abort(self):
         _lib.check(self.lib.tdx_ctl_abort(self.handle))
 
@@ -595,9 +587,12 @@ class StepEngine:
         if ctl.failed == 1:
             raise FloatingPointError(f"error estimate is NaN at t={ctl.t}, dt={ctl.dt}")
         if ctl.failed:
-            raise _lib.TornadoxB200Error(
-                "a wait inside the step kernels timed out (a neighbouring rank did not deliver its halo / its share of a "
-                "reduction, or a grid barrier was abandoned); the state is not valid")
+            why = {2: "an attempt was poisoned (a peer's halo or share of a reduction did not arrive in time)",
+                   3: "the grid barrier between two attempts was abandoned",
+                   4: "host feed",
+                   5: "a wait for a neighbouring rank timed out"}.get(int(ctl.failed), f"code {ctl.failed}")
+            raise _lib.TornadoxB200Error(f"a wait inside the step kernels timed out: {why}; the state is not valid "
+                                         f"(t={ctl.t}, attempts={ctl.attempts})")
 
     @staticmethod
     def _ring(tensors):
@@ -614,17 +609,19 @@ class StepEngine:
         _lib.check(self.lib.tdx_ek0_enqueue_attempts(self.handle, int(k), self._full_step_flags(), _ptr(pair_a[0]), _ptr(pair_a[1]),
                                                      _ptr(pair_b[0]), _ptr(pair_b[1]), _ptr(err), _ptr(ref), self._stream()))
 
-    def dek1_run_attempts(self, k, means, factors, errs=None, refs=None, jacobian=True, stream=None):
+    def dek1_run_attempts(self, k, means, factors, errs=None, refs=None, jacobian=True, stream=None, max_accepted=0):
         """Up to ``k`` DiagonalEK1 attempts in ONE persistent launch over the state ring ``means`` / ``factors`` (lists of
-        tensors; ``errs`` / ``refs``: per-slot error_estimate / reference_state vectors or None)."""
+        tensors; ``errs`` / ``refs``: per-slot error_estimate / reference_state vectors or None).  ``max_accepted`` > 0 ends
+        the launch after that many newly accepted steps."""
         flags = self._full_step_flags(0 if jacobian else _lib.TDX_STEP_ZERO_JACOBIAN)
-        _lib.check(self.lib.tdx_dek1_run_attempts(self.handle, int(k), flags, self._ring(means), self._ring(factors), len(means),
-                                                  self._ring(errs), self._ring(refs), stream if stream is not None else self._stream()))
+        _lib.check(self.lib.tdx_dek1_run_attempts(self.handle, int(k), int(max_accepted), flags, self._ring(means), self._ring(factors),
+                                                  len(means), self._ring(errs), self._ring(refs),
+                                                  stream if stream is not None else self._stream()))
 
-    def ek0_run_attempts(self, k, means, factors, errs, refs=None, stream=None):
+    def ek0_run_attempts(self, k, means, factors, errs, refs=None, stream=None, max_accepted=0):
         """Up to ``k`` KroneckerEK0 attempts in ONE persistent launch (``errs``: one device scalar per ring slot)."""
-        _lib.check(self.lib.tdx_ek0_run_attempts(self.handle, int(k), self._full_step_flags(), self._ring(means), self._ring(factors),
-                                                 len(means), self._ring(errs), self._ring(refs),
+        _lib.check(self.lib.tdx_ek0_run_attempts(self.handle, int(k), int(max_accepted), self._full_step_flags(), self._ring(means),
+                                                 self._ring(factors), len(means), self._ring(errs), self._ring(refs),
                                                  stream if stream is not None else self._stream()))
 
     # ---- KroneckerEK0 -----------------------------------------------------------------------------

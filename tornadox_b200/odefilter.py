@@ -142,9 +142,10 @@ class ODEFilter(ABC):
         )
 
     def _solve_following(self, ivp, stop_at, offload):
-        """``solve`` on top of the device-resident controller: the persistent kernel runs the whole solve on its own stream,
-        the host follows its progress through mapped pinned memory and copies every accepted state out of the state ring
-        (copy engine, behind the kernel) before releasing the slot.  None: not available for this configuration."""
+        """``solve`` on top of the device-resident controller: persistent launches on their own stream, each running until
+        ``ring_size - 1`` further steps have been accepted; the host follows the kernel's progress through mapped pinned memory
+        and copies every accepted state out of the state ring (copy engine) while the kernel is already working on the next
+        attempts.  None: not available for this configuration."""
         from . import ek0
 
         state = self.initialize(*ivp)
@@ -152,35 +153,32 @@ class ODEFilter(ABC):
             return None
         kron = isinstance(self, ek0.KroneckerEK0)
         dense = kron and (state.y.mean.shape[0] * state.y.mean.shape[1]) ** 2 <= self.dense_output_limit
-        times, means, factors = [float(state.t)], [], []
+        factor0 = state.y.cov_sqrtm_2 if kron else state.y.cov_sqrtm
 
-        def store(dst_list, src, stream):
+        def like(src):
             if offload:
-                dst = torch.empty(src.shape, dtype=src.dtype, pin_memory=True)
-            else:
-                dst = torch.empty_like(src)
-            with torch.cuda.stream(stream):
-                dst.copy_(src, non_blocking=True)
-            dst_list.append(dst)
+                return torch.empty(src.shape, dtype=src.dtype, pin_memory=True)
+            return torch.empty_like(src)
 
+        def grab(src):
+            dst = like(src)
+            dst.copy_(src, non_blocking=True)
+            return dst
+
+        times, means, factors = [float(state.t)], [grab(state.y.mean)], [grab(factor0)]
         info = self._ctl_info(0, 0)
         if state.t < ivp.tmax:
             follower = _Follower(self, state, self.steprule.first_dt(*ivp), ivp.tmax, stop_at)
             try:
-                store(means, follower.ring["means"][0], follower.copy_stream)
-                store(factors, follower.ring["factors"][0], follower.copy_stream)
-                follower.release_when_copied(0)
-                for j, t, attempts, slot in follower.states():
+                for j, t, attempts, dst in follower.states(lambda: (like(state.y.mean), like(factor0))):
                     times.append(t)
-                    store(means, follower.ring["means"][slot], follower.copy_stream)
-                    store(factors, follower.ring["factors"][slot], follower.copy_stream)
-                    follower.release_when_copied(j)
+                    means.append(dst[0])
+                    factors.append(dst[1])
                     info = self._ctl_info(attempts, j)
             finally:
                 follower.close()
-        else:
-            means.append(state.y.mean.clone())
-            factors.append((state.y.cov_sqrtm_2 if kron else state.y.cov_sqrtm).clone())
+        if torch.cuda.is_available():
+            torch.cuda.current_stream(state.y.mean.device).synchronize()
         if dense:       # as upstream: the dense kron(I_d, C) factor of every state, small problems only
             d = state.y.mean.shape[1]
             factors = [torch.kron(torch.eye(d, dtype=f.dtype, device=f.device), f) for f in factors]
@@ -278,10 +276,8 @@ class ODEFilter(ABC):
         if use_ctl and not progressbar and state.t < ivp.tmax and self._controller_available(state):
             follower = _Follower(self, state, dt, ivp.tmax, stop_at, clone_first=True)
             try:
-                for j, t, attempts, slot in follower.states():
-                    copy = follower.clone_state(slot, t)
-                    follower.release_when_copied(j, wait=True)
-                    yield copy, self._ctl_info(attempts, j)
+                for j, t, attempts, copy in follower.states(None):
+                    yield self._ctl_state(copy, 0, t), self._ctl_info(attempts, j)
             finally:
                 follower.close()
             return
@@ -357,9 +353,11 @@ class ODEFilter(ABC):
 
 
 class _Follower:
-    """Host side of a solve that runs as ONE persistent kernel on its own stream (``tdx_*_run_attempts`` with ``follow``):
-    reads the kernel's progress from mapped pinned memory, hands out the ring slots of newly accepted states and tells the
-    kernel which slots may be reused."""
+    """Host side of a solve whose attempts run in persistent kernels on their own stream (``tdx_*_run_attempts`` with
+    ``follow``).  Every launch goes on until ``nbuf - 1`` further steps have been accepted (or the solve is over), so no ring
+    slot is written twice within a launch; the host reads the kernel's progress from mapped pinned memory and copies newly
+    accepted states out of the ring on a second stream while the kernel is already working on the next attempts.  Everything
+    that may synchronise the device (memory allocation, the controller read) happens BETWEEN launches."""
 
     def __init__(self, solver, state, dt0, tmax, stop_at, clone_first=False):
         eng = solver.engine
@@ -373,70 +371,83 @@ class _Follower:
         self.loop_stream.wait_stream(current)
         self.copy_stream.wait_stream(current)
         eng.ctl_begin(eng.native_steprule(solver.steprule), state.t, dt0, tmax, nbuf=self.nbuf, stop_at=stop_at, follow=True)
+        self.seen = 0
+        self.running = None        # event behind the launch in flight
+        self.closed = False
+
+    def _launch(self):
         import ctypes
 
-        solver._ctl_launch(2 ** 30, self.ring, stream=ctypes.c_void_p(self.loop_stream.cuda_stream))
-        self.finished = torch.cuda.Event()
-        self.finished.record(self.loop_stream)
-        self.seen = 0
-        self.pending = []          # (state index, event): copies in flight
-        self.closed = False
-        if clone_first:            # slot 0 is a private copy of the initial state: nobody needs it
-            eng.ctl_consume(0)
+        self.solver._ctl_launch(2 ** 30, self.ring, stream=ctypes.c_void_p(self.loop_stream.cuda_stream),
+                                max_accepted=self.nbuf - 1)
+        self.running = torch.cuda.Event()
+        self.running.record(self.loop_stream)
 
-    def states(self):
-        """Yield (j, t_j, attempts so far, ring slot) for every accepted state, in order, while the kernel is running."""
-        eng = self.eng
+    def states(self, make_dst):
+        """Yield (j, t_j, attempts so far, copy) for every accepted state, in order.  ``make_dst()`` returns the (mean, factor)
+        tensors a state is copied into; None: copies of every ring array of the slot (a dict like the ring, one-element lists)."""
+        eng, m = self.eng, self.nbuf - 1
+        current = torch.cuda.current_stream(self.copy_stream.device)
         while True:
-            ended = self.finished.query()            # read BEFORE the progress counters: nothing can follow a finished kernel
-            accepted, _ = eng.ctl_poll()
-            while self.seen < accepted:
-                self.seen += 1
-                t, _, attempts = eng.ctl_history(self.seen)
-                yield self.seen, t, attempts, self.seen % self.nbuf
-            self._release_finished_copies()
-            if ended:
+            # destinations first: allocating device / pinned memory may synchronise with a running kernel
+            if make_dst is None:
+                dsts = [{k: (None if v is None else [None if v[0] is None else torch.empty_like(v[0])]) for k, v in self.ring.items()}
+                        for _ in range(m)]
+            else:
+                dsts = [make_dst() for _ in range(m)]
+            self._launch()
+            got, events = 0, []
+            while True:
+                ended = self.running.query()             # read BEFORE the counters: nothing follows a finished launch
+                accepted, _ = eng.ctl_poll()
+                while self.seen < accepted and got < m:
+                    self.seen += 1
+                    slot = self.seen % self.nbuf
+                    t, _, attempts = eng.ctl_history(self.seen)
+                    dst = dsts[got]
+                    got += 1
+                    with torch.cuda.stream(self.copy_stream):
+                        if make_dst is None:
+                            for key, arrs in self.ring.items():
+                                if arrs is not None and arrs[slot] is not None:
+                                    dst[key][0].copy_(arrs[slot], non_blocking=True)
+                        else:
+                            dst[0].copy_(self.ring["means"][slot], non_blocking=True)
+                            dst[1].copy_(self.ring["factors"][slot], non_blocking=True)
+                        ev = torch.cuda.Event()
+                        ev.record(self.copy_stream)
+                    events.append((self.seen, t, attempts, dst, ev))
+                # hand over what has been copied completely, in order
+                while events and events[0][4].query():
+                    j, t, attempts, dst, ev = events.pop(0)
+                    current.wait_event(ev)
+                    yield j, t, attempts, dst
+                if ended and self.seen >= eng.ctl_poll()[0]:
+                    break
+                time.sleep(0)
+            for j, t, attempts, dst, ev in events:
+                ev.synchronize()
+                current.wait_event(ev)
+                yield j, t, attempts, dst
+            self.loop_stream.synchronize()
+            self.running = None
+            ctl = eng.ctl_read()
+            eng.raise_if_failed(ctl)
+            if ctl.done:
                 break
-            time.sleep(0)
-
-    def clone_state(self, slot, t):
-        """A copy of the state in ``slot``, made on the copy stream."""
-        with torch.cuda.stream(self.copy_stream):
-            copy = {k: (None if v is None else [None if v[slot] is None else v[slot].clone()]) for k, v in self.ring.items()}
-        return self.solver._ctl_state(copy, 0, t)
-
-    def release_when_copied(self, j, wait=False):
-        ev = torch.cuda.Event()
-        ev.record(self.copy_stream)
-        if wait:
-            ev.synchronize()
-            torch.cuda.current_stream(self.copy_stream.device).wait_event(ev)
-            self.eng.ctl_consume(j)
-        else:
-            self.pending.append((j, ev))
-            self._release_finished_copies()
-
-    def _release_finished_copies(self):
-        done = -1
-        while self.pending and self.pending[0][1].query():
-            done = self.pending.pop(0)[0]
-        if done >= 0:
-            self.eng.ctl_consume(done)
 
     def close(self):
         if self.closed:
             return
         self.closed = True
-        if not self.finished.query():
-            # the consumer stopped early, or an exception is on its way: let the kernel drain and stop
-            if self.pending:
-                self.copy_stream.synchronize()
-            self.eng.ctl_abort()
-        self.loop_stream.synchronize()
+        if self.running is not None:
+            # the consumer stopped early, or an exception is on its way: stop the launch at its next attempt boundary
+            if not self.running.query():
+                self.eng.ctl_abort()
+            self.loop_stream.synchronize()
+            self.running = None
         self.copy_stream.synchronize()
         torch.cuda.current_stream(self.copy_stream.device).wait_stream(self.copy_stream)
-        ctl = self.eng.ctl_read()
-        self.eng.raise_if_failed(ctl)
 
 
 class _TimeStopper:
