@@ -54,6 +54,10 @@ def run(name, cls, prob, rule, nu, k=48):
         print(f"    tiles                  {np.mean(gaps[1:, 0]) * 1e-3:7.2f} us")
         print(f"    end barrier(+ctl)      {np.mean(gaps[1:, 1]) * 1e-3:7.2f} us")
         print(f"    next attempt's top     {np.mean(top) * 1e-3:7.2f} us")
+        last = s[1:-1]
+        print(f"    (last CTA: arrives {np.mean(last[:, 3] - last[:, 1]) * 1e-3:.2f} us after CTA 0 ran out of tiles; reduction "
+              f"{np.mean(last[:, 4] - last[:, 3]) * 1e-3:.2f} us; controller + release {np.mean(last[:, 5] - last[:, 4]) * 1e-3:.2f} us; "
+              f"CTA 0 starts the next attempt {np.mean(s[2:, 0] - s[1:-1, 5]) * 1e-3:.2f} us after the release)")
 
 
 y3 = np.random.default_rng(2).uniform(size=2 * 256 * 256)

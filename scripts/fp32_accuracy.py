@@ -20,7 +20,10 @@ def state(n, d, seed, blocks=True):
     return mean, sc
 
 def rel(a, b):
-    return float(np.max(np.abs(np.asarray(a, dtype=np.float64) - b)) / max(np.max(np.abs(b)), 1e-300))
+    a = np.asarray(a, dtype=np.float64)
+    assert a.shape == b.shape and a.size > 0, (a.shape, b.shape)
+    assert np.all(np.isfinite(a)) and np.all(np.isfinite(b)), "non-finite values"
+    return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300))
 
 def fhn_dek1(side, dt):
     nu, n, d, npts = 4, 5, 2 * side * side, side * side

@@ -60,18 +60,24 @@ __device__ __forceinline__ T QL(const Consts<T, N>& c, int i, int j) {
 // evaluates the same vectors with libm's pow like NumPy does -- the two agree to a few ulp).
 __host__ __device__ inline void nordsieck_vectors(int nu, double dt, double* p, double* pinv) {
     const double adt = dt < 0.0 ? -dt : dt;
-    const double radt = 1.0 / adt;
-    double pw = sqrt(adt), ipw = 1.0 / pw, fact = 1.0, ifact = 1.0;
-    for (int q = 0; q <= nu; ++q) {       // q = nu - k
-        if (q > 1) {
-            fact *= (double)q;
-            ifact = 1.0 / fact;           // q! <= 720: the reciprocals are loop-invariant constants after unrolling
+    // powers and factorials first (a short chain of multiplications), then all the divisions: they are independent of one
+    // another, so the controller's single thread overlaps them instead of waiting for one after the other
+    double pw[kMaxN], fact[kMaxN];
+    double w = sqrt(adt), f = 1.0;
+#pragma unroll
+    for (int q = 0; q < kMaxN; ++q) {     // q = nu - k
+        if (q > 1) f *= (double)q;
+        pw[q] = w;
+        fact[q] = f;
+        w *= adt;
+    }
+#pragma unroll
+    for (int q = 0; q < kMaxN; ++q) {
+        if (q <= nu) {
+            const int k = nu - q;
+            if (p) p[k] = pw[q] / fact[q];
+            if (pinv) pinv[k] = fact[q] / pw[q];
         }
-        const int k = nu - q;
-        if (p) p[k] = pw * ifact;
-        if (pinv) pinv[k] = fact * ipw;
-        pw *= adt;
-        ipw *= radt;
     }
 }
 
@@ -148,8 +154,10 @@ enum : int { TDX_FAIL_NAN = 1, TDX_FAIL_POISONED = 2, TDX_FAIL_GRID_BARRIER = 3,
     do {                                                                                                         \
         if (blockIdx.x == 0) (buf)[2048 + ((att) & 63) * 8 + (k)] = (double)global_timer_ns();                   \
     } while (0)
+#define TDX_STAMP_ANY(buf, att, k) (buf)[2048 + ((att) & 63) * 8 + (k)] = (double)global_timer_ns()
 #else
 #define TDX_STAMP(buf, att, k) do { } while (0)
+#define TDX_STAMP_ANY(buf, att, k) do { } while (0)
 #endif
 
 // odefilter.py:355-373 (_TimeStopper.adjust_dt_to_time_stops) on the controller's stop list

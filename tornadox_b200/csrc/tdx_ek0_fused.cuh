@@ -398,7 +398,7 @@ __global__ void __maxnreg__(TDX_EK0_MAXREG) ek0_fused_fhn_kernel(const __grid_co
     __syncthreads();
 
     unsigned q = 0;                       // producer: ring position
-    unsigned cq = 0, phase_bits = 0u;     // consumers: ring position, parity of each stage's full barrier
+    unsigned cq = 0, cr = 0, phase_bits = 0u;     // consumers: row counter, ring position, parity of each stage's full barrier
     const int max_attempts = kCtl ? a.max_attempts : 1;
 
 #pragma unroll 1
@@ -415,7 +415,7 @@ __global__ void __maxnreg__(TDX_EK0_MAXREG) ek0_fused_fhn_kernel(const __grid_co
 
         if (tc >= W) {
             // ---- producer warp: walks the same (strip, row) enumeration as the consumers, up to S rows ahead ------------
-            // Every item owns ring slot q % S (items beyond the shard simply load nothing).  The 2 n row segments of a
+            // Every row inside the shard owns ring slot q % S.  The 2 n row segments of a
             // row are issued by 2 n lanes in one instruction.
             const int lane = tc - W;
             const int seg_f = lane / N, seg_k = lane - seg_f * N;           // (field, derivative) of this lane's segment
@@ -438,10 +438,14 @@ __global__ void __maxnreg__(TDX_EK0_MAXREG) ek0_fused_fhn_kernel(const __grid_co
                     const int keep_from = (phase == 0 && hints) ? L - 1 - (int)ceilf(a.keep_frac * (float)(s.r1 - s.r0)) : L;
                     int rr = s.dir > 0 ? s.r0 - 1 : s.r1;
 #pragma unroll 1
-                    for (int i = 0; i < L; ++i, rr += s.dir, ++q) {
-                        const unsigned stage = q % S, round = q / S;
-                        if (round > 0) TDX_MBAR_WAIT(empty + stage, (round - 1u) & 1u, a.partials, 2, att);     // the slot's previous row is consumed
+                    for (int i = 0; i < L; ++i, rr += s.dir) {
+                        // Rows beyond the shard take no ring slot: a consumer can get through such a row without waiting for
+                        // anything, i.e. ahead of the producer, and two completions of an "empty" barrier in a row would make the
+                        // producer's parity wait miss its turn.
                         if (rr < 0 || rr >= g.rows) continue;
+                        const unsigned stage = q % S, round = q / S;
+                        ++q;
+                        if (round > 0) TDX_MBAR_WAIT(empty + stage, (round - 1u) & 1u, a.partials, 2, att);     // the slot's previous row is consumed
                         T* dst = s_stage + (size_t)stage * Cfg::STAGE_ELEMS;
                         const T* src = mean_in + (long long)rr * g.cols + gs;
                         if (a.use_bulk) {
@@ -558,10 +562,12 @@ __global__ void __maxnreg__(TDX_EK0_MAXREG) ek0_fused_fhn_kernel(const __grid_co
                 const int keep_from = (kUpdate && hints) ? L - (int)ceilf(a.keep_frac * (float)(s.r1 - s.r0)) : L;
 #pragma unroll 1
                 for (int i = 0; i < L; ++i, rr += s.dir, ++cq, out_ptr += (long long)s.dir * g.cols) {
-                    const unsigned stage = cq % S;
+                    const unsigned stage = cr % S;
+                    const bool in_shard = rr >= 0 && rr < g.rows;
                     T* at_row = s_at + (cq & 1u) * 2 * AT_ROW;
                     T at_cur[2], mp_cur[2][NK];
-                    if (rr >= 0 && rr < g.rows) {
+                    if (in_shard) {
+                        ++cr;
                         TDX_MBAR_WAIT(full + stage, (phase_bits >> stage) & 1u, a.partials, 1, att);
                         phase_bits ^= (1u << stage);
                         const T* st = s_stage + (size_t)stage * Cfg::STAGE_ELEMS;
@@ -617,7 +623,7 @@ __global__ void __maxnreg__(TDX_EK0_MAXREG) ek0_fused_fhn_kernel(const __grid_co
                         }
                     }
                     csync();              // publishes the row; every consumer has read the stage -> hand it back
-                    if (tc == 0) mbar_arrive(empty + stage);
+                    if (tc == 0 && in_shard) mbar_arrive(empty + stage);
                     if (reduces) flush_block_partial();
                     T hs_cur[2];
 #pragma unroll
@@ -661,6 +667,7 @@ __global__ void __maxnreg__(TDX_EK0_MAXREG) ek0_fused_fhn_kernel(const __grid_co
                                 }
                             }
                         }
+#ifndef TDX_EK0_NO_SUMS
                         if (reduces) {
                             if (RB == 1) {
                                 emit_block(term, cb, s.dir);
@@ -685,6 +692,7 @@ __global__ void __maxnreg__(TDX_EK0_MAXREG) ek0_fused_fhn_kernel(const __grid_co
                                 }
                             }
                         }
+#endif
                     }
 #pragma unroll
                     for (int f = 0; f < 2; ++f) {

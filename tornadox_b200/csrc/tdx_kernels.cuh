@@ -658,17 +658,22 @@ __global__ void __launch_bounds__(kThreads, DekSmem<T, N>::MIN_BLOCKS) dek1_kern
         bool fin = false;                             // thread 0 of the last CTA
         if (unit_mode) {
             if (cta_arrive_last(a.ticket, &s_flag)) {
+                if (threadIdx.x == 0) TDX_STAMP_ANY(a.partials, att, 3);
                 // ConstantSteps on one GPU: nothing to add up, the rendezvous alone orders the attempts
                 if (c.want_norm || (kComm && a.reduce.world > 0))
                     total = reduce_units(a.red, kComm ? &a.reduce : nullptr, a.reduce.seq + (unsigned long long)att, s_red);
                 fin = threadIdx.x == 0;
+                if (fin) TDX_STAMP_ANY(a.partials, att, 4);
                 if (fin && c.want_norm && a.out_sum) *a.out_sum = total;
             }
         } else {
             fin = grid_sum_cta(legacy_acc, s_red, a.partials, a.ticket, c.want_norm ? a.out_sum : nullptr);
         }
         if constexpr (kCtl) {
-            if (fin) ctl_finish_attempt(a.ctl, total, a.d_global, s_epoch0 + (unsigned long long)att + 1ull);
+            if (fin) {
+                ctl_finish_attempt(a.ctl, total, a.d_global, s_epoch0 + (unsigned long long)att + 1ull);
+                TDX_STAMP_ANY(a.partials, att, 5);
+            }
         }
         if (threadIdx.x == 0) TDX_STAMP(a.partials, att, 2);
     }

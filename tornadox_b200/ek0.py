@@ -40,6 +40,7 @@ class KroneckerEK0(odefilter.ODEFilter):
         d = mean.shape[1]
         y = rv.LeftIsotropicMatrixNormal(mean=mean, d=d, cov_sqrtm_2=cov_sqrtm.to(self.dtype).contiguous())
         nan = torch.full((d,), float("nan"), dtype=self.dtype, device=mean.device)
+        self.engine.barrier()      # sharded: nobody starts stepping before every rank has its initial state
         return odefilter.ODEFilterState(t=t0, error_estimate=float("nan"), reference_state=nan, y=y)
 
     def attempt_step(self, state, dt, f, t0, tmax, y0, df, df_diagonal):

@@ -51,7 +51,9 @@ class BatchedEK1(odefilter.ODEFilter):
         self.sq_1d = torch.as_tensor(Ql, dtype=self.dtype, device=y0.device)
         extended_dy0, cov_sqrtm = self.init(f=f, df=df, y0=y0, t0=t0, num_derivatives=self.num_derivatives)
         extended_dy0 = self._own_slice(extended_dy0.to(self.dtype))
-        return BatchedEK1.y0_to_initial_state(extended_dy0, cov_sqrtm.to(self.dtype), d=extended_dy0.shape[1], t0=t0)
+        state = BatchedEK1.y0_to_initial_state(extended_dy0, cov_sqrtm.to(self.dtype), d=extended_dy0.shape[1], t0=t0)
+        self.engine.barrier()      # sharded: nobody starts stepping before every rank has its initial state
+        return state
 
     def _own_slice(self, mean_global):
         eng = self.engine

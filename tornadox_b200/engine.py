@@ -262,6 +262,13 @@ class StepEngine:
         dist.barrier(group=self.group)
         self.peer = True
 
+    def barrier(self):
+        """All ranks of a sharded solver meet here (after the initialisation, whose duration differs from rank to rank): the
+        in-kernel waits for a neighbour's halo / share of a reduction give up after TDX_WAIT_TIMEOUT_MS."""
+        if self.world > 1:
+            torch.cuda.current_stream(self.device).synchronize()
+            self.exchanger.dist.barrier(group=self.group)
+
     def check_peers(self):
         """Raise if a flag wait timed out (a neighbouring rank died or diverged)."""
         if not self.peer:
