@@ -572,9 +572,24 @@ def parity_check(torch, args, sol, state, dt, problem, world, rank, dev):
     from oracle.ref_np import filters, problems
     from tornadox_b200 import ek1
 
+    from tornadox_b200 import odefilter, rv
+    from tornadox_b200.engine import local_slices
+
     eng = sol.engine
     is_dek1 = isinstance(sol, ek1.DiagonalEK1)
     n = NU + 1
+    # The benchmark's state is a few tiny steps away from the exact Taylor initialisation: the residual z = p1 mp[1] - f cancels
+    # to ~8 digits there, and any two correct implementations differ by ~1e-9 in everything that is scaled by z.  The check
+    # therefore moves the mean off the solution manifold by 1e-3 (relative; a fixed function of the GLOBAL coordinate index, so
+    # that every rank perturbs its shard consistently) -- z is then O(1e-3) of its terms and the 1e-10 bar applies.
+    gidx = torch.cat([torch.arange(sl.start, sl.stop, device=dev, dtype=torch.float64) for sl in local_slices(eng.spec, eng.begin, eng.end)])
+    krow = torch.arange(n, device=dev, dtype=torch.float64)[:, None]
+    mean_p = (state.y.mean.double() * (1.0 + 1e-3 * torch.sin(0.37 * gidx[None, :] + krow))).to(state.y.mean.dtype).contiguous()
+    if is_dek1:
+        y_p = rv.BatchedMultivariateNormal(mean_p, state.y.cov_sqrtm)
+    else:
+        y_p = rv.LeftIsotropicMatrixNormal(mean_p, state.y.d, state.y.cov_sqrtm_2)
+    state = odefilter.ODEFilterState(state.t, y_p, None, None)
     new, _ = sol.attempt_step(state, dt, *problem)
     torch.cuda.synchronize()
     out = {}
@@ -676,8 +691,6 @@ def parity_check(torch, args, sol, state, dt, problem, world, rank, dev):
         out["ok"] = bool(out["max_rel_err_mean"] < 1e-10 and out["max_rel_err_cov_sqrtm"] < 1e-10 and out.get("norm_rel_diff", 0.0) < 1e-10)
     else:
         # the whole KroneckerEK0 attempt on rank 0
-        from tornadox_b200.engine import local_slices
-
         def gather_full(t):
             if world == 1:
                 return t.cpu().numpy()

@@ -26,5 +26,23 @@ if which in ("both", "ek0"):
     Cl = 1e-3*torch.randn((n, n), generator=g, device="cuda", dtype=dtype)
     for _ in range(iters):
         eng.ek0_attempt(0.0, 1e-4, mean, Cl, 1e-4, 1e-2, mean_out=mo, want_ref=True)
+if which in ("ek1ctl", "ek0ctl"):
+    # the controller-driven (multi-attempt) instantiations: one launch of 2 attempts per iteration
+    from tornadox_b200 import step
+    rule = eng.native_steprule(step.AdaptiveSteps())
+    means = [mean, mo]
+    if which == "ek1ctl":
+        sc = 1e-3*torch.randn((d, n, n), generator=g, device="cuda", dtype=dtype)
+        facs = [sc, torch.empty_like(sc)]
+    else:
+        Cl = 1e-3*torch.randn((n, n), generator=g, device="cuda", dtype=dtype)
+        facs = [Cl, torch.empty_like(Cl)]
+        errs = [torch.zeros((), device="cuda", dtype=dtype) for _ in range(2)]
+    for _ in range(iters):
+        eng.ctl_begin(rule, 0.0, 1e-4, 1.0, nbuf=2)
+        if which == "ek1ctl":
+            eng.dek1_run_attempts(2, means, facs)
+        else:
+            eng.ek0_run_attempts(2, means, facs, errs)
 torch.cuda.synchronize()
 print("ok")

@@ -50,8 +50,22 @@ __device__ __forceinline__ T ld_state(const T* p) {
     else return __ldg(p);
 }
 
+// The constants of one attempt as a multi-attempt (controller-driven) kernel sees them: what comes with the launch (Ql,
+// tolerances, flags) stays in the constant bank, where every use is an instruction operand; only the step's own vectors
+// (rebuilt by thread 0 from the controller block before each attempt) live in shared memory.  A whole Consts in shared
+// memory costs the tile loop a load per use, re-issued after every store that might alias it.
 template <typename T, int N>
-__device__ __forceinline__ T QL(const Consts<T, N>& c, int i, int j) {
+struct StepView {
+    const T* p;
+    const T* pinv;
+    const T* ql;
+    T dt, abstol, reltol;
+    int want_norm;
+    unsigned int flags;
+};
+
+template <class C>
+__device__ __forceinline__ auto QL(const C& c, int i, int j) {
     return c.ql[i * (i + 1) / 2 + j];
 }
 
@@ -231,8 +245,8 @@ __host__ __device__ constexpr double A_entry(int i, int j) {
 // ---------------------------------------------------------------------------------------------
 // mean prediction for one state coordinate:  mp = A (p_inv * raw)      ek1.py:232,262-265 / ek0.py:162-166
 // ---------------------------------------------------------------------------------------------
-template <typename T, int N>
-__device__ __forceinline__ void predict_column(const T (&raw)[N], const Consts<T, N>& c, T (&mp)[N]) {
+template <typename T, int N, class C = Consts<T, N>>
+__device__ __forceinline__ void predict_column(const T (&raw)[N], const C& c, T (&mp)[N]) {
     T m[N];
 #pragma unroll
     for (int k = 0; k < N; ++k) m[k] = c.pinv[k] * raw[k];
@@ -247,11 +261,11 @@ __device__ __forceinline__ void predict_column(const T (&raw)[N], const Consts<T
 
 // Accessor: predicted, un-preconditioned state p[0] * (A p_inv m)[0] at an arbitrary local flat index,
 // recomputed from the mean in global memory (bitwise identical to the owner thread's own value).
-template <typename T, int N, bool kCoherent = false>
+template <typename T, int N, bool kCoherent = false, class C = Consts<T, N>>
 struct MeanAt {
     const T* __restrict__ mean;
     long long d;
-    const Consts<T, N>* c;
+    const C* c;
     __device__ __forceinline__ T operator()(long long idx) const {
         T acc = c->pinv[0] * ld_state<kCoherent>(mean + idx);
 #pragma unroll
@@ -660,8 +674,8 @@ __device__ __forceinline__ double tsqrt<double>(double x) { return sqrt(x); }
 template <>
 __device__ __forceinline__ float tsqrt<float>(float x) { return sqrtf(x); }
 
-template <typename T, int N>
-__device__ __forceinline__ void stacked_qr(T (&B)[N][N], T sigma, const Consts<T, N>& c) {
+template <typename T, int N, class C = Consts<T, N>>
+__device__ __forceinline__ void stacked_qr(T (&B)[N][N], T sigma, const C& c) {
     T G[N][N];   // only j <= i used; materialised lazily (row k of the bottom block is first touched at step k)
 #pragma unroll
     for (int k = 0; k < N; ++k) {
@@ -986,14 +1000,41 @@ __device__ __forceinline__ double reduce_units(const RedPlan& rp, const CommRedu
                 b1[j] = b1[j] < hi_all ? b1[j] : hi_all;
             }
         }
-        double first[2] = {0.0, 0.0};
+        // lane l adds units l, l + 32, l + 64, ... of the chunk IN THAT ORDER; the loads of kBatch of them (per chunk) are issued
+        // before the first addition, so that a chunk of thousands of units costs a few L2 round trips, not one per unit
+        constexpr int kBatch = 16;
+        const double* base = rp.unit - lo_all;
+        unsigned long long u0 = b0[0] + lane, u1 = b0[1] + lane;
+        while (u0 + 32ull * (kBatch - 1) < b1[0] && u1 + 32ull * (kBatch - 1) < b1[1]) {
+            double v0[kBatch], v1[kBatch];
 #pragma unroll
-        for (int j = 0; j < 2; ++j)
-            if (b0[j] + lane < b1[j]) first[j] = __ldcg(rp.unit + (b0[j] + lane - lo_all));
+            for (int i = 0; i < kBatch; ++i) {
+                v0[i] = __ldcg(base + u0 + 32 * i);
+                v1[i] = __ldcg(base + u1 + 32 * i);
+            }
+#pragma unroll
+            for (int i = 0; i < kBatch; ++i) {
+                acc[0] += v0[i];
+                acc[1] += v1[i];
+            }
+            u0 += 32ull * kBatch;
+            u1 += 32ull * kBatch;
+        }
+        constexpr int kTail = 4;
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
-            acc[j] = first[j];
-            for (unsigned long long u = b0[j] + lane + 32; u < b1[j]; u += 32) acc[j] += __ldcg(rp.unit + (u - lo_all));
+            unsigned long long u = j == 0 ? u0 : u1;
+            double x = acc[j];
+            while (u + 32ull * (kTail - 1) < b1[j]) {
+                double v[kTail];
+#pragma unroll
+                for (int i = 0; i < kTail; ++i) v[i] = __ldcg(base + u + 32 * i);
+#pragma unroll
+                for (int i = 0; i < kTail; ++i) x += v[i];
+                u += 32ull * kTail;
+            }
+            for (; u < b1[j]; u += 32) x += __ldcg(base + u);
+            acc[j] = x;
         }
         acc[0] = warp_sum(acc[0]);
         acc[1] = warp_sum(acc[1]);

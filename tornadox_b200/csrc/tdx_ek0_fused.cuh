@@ -41,10 +41,9 @@ struct Ek0FusedCfg {
     static constexpr int AT_ROW = W + 2;                  // [left edge][W own][right edge]
     static constexpr int AT_ELEMS = 2 * 2 * AT_ROW;       // [slot][field][AT_ROW]
     static constexpr size_t BAR_BYTES = 128, RED_BYTES = 512;
-    static constexpr size_t TREE_BYTES = 2 * (size_t)W_ * sizeof(double);    // levels 1 and 2 of the row-block trees
     __host__ __device__ static constexpr size_t at_bytes() { return ((size_t)AT_ELEMS * sizeof(T) + 127) / 128 * 128; }
     __host__ __device__ static constexpr size_t stage_bytes() { return (size_t)STAGE_ELEMS * sizeof(T); }
-    __host__ __device__ static constexpr size_t total() { return BAR_BYTES + RED_BYTES + TREE_BYTES + at_bytes() + STAGES * stage_bytes(); }
+    __host__ __device__ static constexpr size_t total() { return BAR_BYTES + RED_BYTES + at_bytes() + STAGES * stage_bytes(); }
     static_assert((STAGE_ELEMS * sizeof(T)) % 16 == 0 && (WP * sizeof(T)) % 16 == 0, "TMA destinations stay 16-byte aligned");
     static_assert(W_ % 32 == 0 && W_ <= 256, "one row partial per consumer warp, at most eight");
 };
@@ -97,12 +96,11 @@ struct StripGeom {
 
 // The error-norm and z^T z sums of the fhn kernel are formed per ROW BLOCK of RB grid rows (aligned in GLOBAL row numbers)
 // and 256-column strip.  RB = 8 (template parameter) for large grids: every thread adds its column's terms of the block's
-// rows in a balanced binary tree -- the same additions whether the strip walks the rows upwards or downwards; a row that is
-// missing because the grid / shard ends inside a block counts as +0.0, which is exact -- then the lanes go through the
-// shuffle tree and the warps through shared memory, once per 8 rows.  Strips are whole numbers of row blocks, so a block's
-// partial is a fixed function of the block's coordinates: independent of how many strips, CTAs or GPUs the grid is cut into.
-// Small grids take RB = 1 (one shuffle tree per row) so that there are still enough strips to fill the device
-// (ek0_row_block: a function of the GLOBAL grid only, i.e. the same for every number of ranks).
+// rows in walking order -- up in phase A, down in phase B, the same for every strip -- then the lanes go through the shuffle
+// tree and the warps through shared memory, once per 8 rows.  A row the grid / shard does not have is simply absent.  Strips
+// are whole numbers of row blocks, so a block's partial is a fixed function of the block's coordinates: independent of how
+// many strips, CTAs or GPUs the grid is cut into.  Small grids take RB = 1 (one shuffle tree per row) so that there are still
+// enough strips to fill the device (ek0_row_block: a function of the GLOBAL grid only, i.e. the same for every number of ranks).
 __host__ __device__ inline int ek0_row_block(long long global_rows, int col_blocks) {
     return ((global_rows + 7) / 8) * col_blocks >= 256 ? 8 : 1;
 }
@@ -155,7 +153,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 
 template <int W>
 __device__ __forceinline__ StripGeom strip_geom(const Geo& g, unsigned strip, unsigned col_blocks, unsigned chunks, int block0,
-                                                int nblocks, int kRowBlock, bool has_lo, bool has_hi) {
+                                                int nblocks, int kRowBlock) {
     StripGeom s;
     const unsigned chunk = strip / col_blocks, cb = strip - chunk * col_blocks;
     s.c0 = (int)cb * W;
@@ -165,11 +163,11 @@ __device__ __forceinline__ StripGeom strip_geom(const Geo& g, unsigned strip, un
     s.b0 = bl;
     s.r0 = max(0, (int)((long long)(block0 + bl) * kRowBlock - g.grow0));
     s.r1 = min(g.rows, (int)((long long)(block0 + bh) * kRowBlock - g.grow0));
-    // Vertically adjacent strips walk in opposite directions: they read the row they share (one's halo row is the
-    // other's edge row) at about the same time, so the second read is an L2 hit.  A strip under the shard's lower /
-    // upper edge walks towards that edge in phase A so that the neighbour GPU's halo row is needed LAST.
-    s.dir = (((chunk & 1u) != 0u) != has_lo) ? -1 : 1;
-    if (chunk + 1 == chunks && has_hi && !(chunk == 0 && has_lo)) s.dir = 1;
+    // Every strip walks UP in phase A and DOWN in phase B (the rows phase A read last are the rows phase B reads first: L2
+    // reuse across the turn-around).  One direction for all strips makes the order in which a thread adds the rows of a row
+    // block a function of the phase only -- not of which strip, CTA or GPU the block landed in -- at the price of reading the
+    // row two vertically adjacent strips share at different times (2 extra rows of DRAM reads per strip, < 4 % of a strip).
+    s.dir = 1;
     return s;
 }
 
@@ -225,7 +223,7 @@ __device__ __forceinline__ double ek0_gain(const Consts<double, N>& cd, const do
 // ---------------------------------------------------------------------------------------------------------------------
 template <typename T, int N>
 struct Ek0CtaState {
-    Consts<T, N> c;                  // kCtl: the attempt's constants rebuilt from the controller block
+    T p[N], pinv[N], dt;             // kCtl: the step's vectors rebuilt from the controller block (see StepView)
     Consts<double, N> cd;
     int cur, out;                    // ring slots of the attempt's input / output state (cur < 0: stop)
     int flag, ok;
@@ -253,18 +251,16 @@ __device__ __forceinline__ bool ek0_attempt_begin(const Ek0FusedArgs<T, N>& a, E
                 ctl->failed = TDX_FAIL_GRID_BARRIER;
                 ctl->done = 1;
             }
-            Consts<T, N> cc = a.c;
             Consts<double, N> ccd = a.cd;
 #pragma unroll
             for (int k = 0; k < N; ++k) {
                 ccd.p[k] = ctl->p[k];
                 ccd.pinv[k] = ctl->pinv[k];
-                cc.p[k] = (T)ctl->p[k];
-                cc.pinv[k] = (T)ctl->pinv[k];
+                sh.p[k] = (T)ctl->p[k];
+                sh.pinv[k] = (T)ctl->pinv[k];
             }
             ccd.dt = ctl->dt;
-            cc.dt = (T)ctl->dt;
-            sh.c = cc;
+            sh.dt = (T)ctl->dt;
             sh.cd = ccd;
             const int cur = ctl->cur, nbuf = ctl->nbuf;
             sh.cur = (ctl->done || !ok || ctl->accepted >= sh.pause_at) ? -1 : cur;
@@ -342,8 +338,8 @@ __device__ __forceinline__ double ek0_mid_barrier(const Ek0FusedArgs<T, N>& a, E
 
 // consumers, after phase B: the last CTA reduces sum_i 1 / tol_i^2, scales it to sum_i (dt err / tol_i)^2 (step.py:101-104 with a
 // scalar error estimate), writes it out and -- under the controller -- decides and publishes the decision
-template <typename T, int N, bool kCtl, class CSync>
-__device__ __forceinline__ void ek0_end_barrier(const Ek0FusedArgs<T, N>& a, Ek0CtaState<T, N>& sh, const Consts<T, N>& c, int att,
+template <typename T, int N, bool kCtl, class CSync, class C>
+__device__ __forceinline__ void ek0_end_barrier(const Ek0FusedArgs<T, N>& a, Ek0CtaState<T, N>& sh, const C& c, int att,
                                                 double err_cal, double* s_red, CSync csync) {
     const int tc = threadIdx.x;
     if (!(c.want_norm || kCtl)) return;
@@ -374,9 +370,8 @@ __global__ void __maxnreg__(TDX_EK0_MAXREG) ek0_fused_fhn_kernel(const __grid_co
     uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);                                   // [S] data has landed
     uint64_t* empty = full + S;                                                               // [S] consumers are done
     double* s_red = reinterpret_cast<double*>(smem_raw + Cfg::BAR_BYTES);                     // see kEk0Red*
-    double* s_tree = reinterpret_cast<double*>(smem_raw + Cfg::BAR_BYTES + Cfg::RED_BYTES);   // [2][W]
-    T* s_at = reinterpret_cast<T*>(smem_raw + Cfg::BAR_BYTES + Cfg::RED_BYTES + Cfg::TREE_BYTES);               // [2][2][AT_ROW]
-    T* s_stage = reinterpret_cast<T*>(smem_raw + Cfg::BAR_BYTES + Cfg::RED_BYTES + Cfg::TREE_BYTES + Cfg::at_bytes());
+    T* s_at = reinterpret_cast<T*>(smem_raw + Cfg::BAR_BYTES + Cfg::RED_BYTES);               // [2][2][AT_ROW]
+    T* s_stage = reinterpret_cast<T*>(smem_raw + Cfg::BAR_BYTES + Cfg::RED_BYTES + Cfg::at_bytes());
     __shared__ Ek0CtaState<T, N> sh;
 
     const Geo& g = a.g;
@@ -404,7 +399,10 @@ __global__ void __maxnreg__(TDX_EK0_MAXREG) ek0_fused_fhn_kernel(const __grid_co
 #pragma unroll 1
     for (int att = 0; att < max_attempts; ++att) {
         if (!ek0_attempt_begin<T, N, kCtl>(a, sh, att)) break;
-        const Consts<T, N>& c = kCtl ? sh.c : a.c;
+        decltype(auto) c = [&]() -> decltype(auto) {
+            if constexpr (kCtl) return StepView<T, N>{sh.p, sh.pinv, a.c.ql, sh.dt, a.c.abstol, a.c.reltol, a.c.want_norm, a.c.flags};
+            else return (a.c);
+        }();
         const Consts<double, N>& cdr = kCtl ? sh.cd : a.cd;
         const T* mean_in = a.mean_ring[sh.cur];
         T* mean_out = a.mean_ring[sh.out];
@@ -428,7 +426,7 @@ __global__ void __maxnreg__(TDX_EK0_MAXREG) ek0_fused_fhn_kernel(const __grid_co
 #pragma unroll 1
                 for (int kk = 0; kk < ns; ++kk) {
                     const int k = phase ? ns - 1 - kk : kk;
-                    StripGeom s = strip_geom<W>(g, blockIdx.x + (unsigned)k * gridDim.x, a.col_blocks, a.chunks, a.block0, a.nblocks, RB, has_lo, has_hi);
+                    StripGeom s = strip_geom<W>(g, blockIdx.x + (unsigned)k * gridDim.x, a.col_blocks, a.chunks, a.block0, a.nblocks, RB);
                     if (phase) s.dir = -s.dir;
                     const int L = s.r1 - s.r0 + 2;
                     const int gs = max(s.c0 - PADC, 0), ge = min(s.c0 + W + PADC, g.cols);
@@ -516,12 +514,12 @@ __global__ void __maxnreg__(TDX_EK0_MAXREG) ek0_fused_fhn_kernel(const __grid_co
                 }
             };
             constexpr int kRowBlock = RB;
-            double* lv1 = s_tree + tc;                          // this thread's pending pair / quad sums (RB = 8)
-            double* lv2 = s_tree + W + tc;
-            double t0 = 0.0;                                    // ... and its pending single row
+            double t0 = 0.0;                                    // RB = 8: this thread's sum over the rows of the block so far
             int blk = 0;                                        // local index of the row block being summed
-            // a finished block: lanes through the shuffle tree, warps through shared memory (added up after the next barrier)
+            // a finished block: lanes through the shuffle tree, warps through shared memory; the warp sums of the block before
+            // (stored at least one row, i.e. one barrier, ago) are added up first
             auto emit_block = [&](double v, int cb_, int dir_) {
+                flush_block_partial();
                 const double ws = warp_sum(v);
                 pending_slot ^= 1;
                 if (lq == 0) s_rowred[(pending_slot & 1) * 8 + wq] = ws;
@@ -532,7 +530,7 @@ __global__ void __maxnreg__(TDX_EK0_MAXREG) ek0_fused_fhn_kernel(const __grid_co
             for (int kk = 0; kk < ns; ++kk) {
                 const int k = kUpdate ? ns - 1 - kk : kk;
                 const unsigned strip = blockIdx.x + (unsigned)k * gridDim.x;
-                StripGeom s = strip_geom<W>(g, strip, a.col_blocks, a.chunks, a.block0, a.nblocks, RB, has_lo, has_hi);
+                StripGeom s = strip_geom<W>(g, strip, a.col_blocks, a.chunks, a.block0, a.nblocks, RB);
                 const int cb = (int)(strip % a.col_blocks);
                 if (kUpdate) s.dir = -s.dir;
                 const int L = s.r1 - s.r0 + 2;
@@ -555,7 +553,6 @@ __global__ void __maxnreg__(TDX_EK0_MAXREG) ek0_fused_fhn_kernel(const __grid_co
                         const int pos = (int)(first & 7);
                         leaf = s.dir > 0 ? pos : 7 - pos;
                         t0 = 0.0;
-                        if (reduces) lv1[0] = lv2[0] = 0.0;
                     }
                 }
                 // the rows phase B writes last are the rows the NEXT attempt's phase A reads first -> keep those in L2
@@ -624,7 +621,6 @@ __global__ void __maxnreg__(TDX_EK0_MAXREG) ek0_fused_fhn_kernel(const __grid_co
                     }
                     csync();              // publishes the row; every consumer has read the stage -> hand it back
                     if (tc == 0 && in_shard) mbar_arrive(empty + stage);
-                    if (reduces) flush_block_partial();
                     T hs_cur[2];
 #pragma unroll
                     for (int f = 0; f < 2; ++f) hs_cur[f] = at_row[f * AT_ROW + tc] + at_row[f * AT_ROW + tc + 2];
@@ -672,23 +668,11 @@ __global__ void __maxnreg__(TDX_EK0_MAXREG) ek0_fused_fhn_kernel(const __grid_co
                             if (RB == 1) {
                                 emit_block(term, cb, s.dir);
                             } else {
-                                const int lf = leaf;
+                                t0 += term;                   // rows of a block in walking order: up in phase A, down in phase B
                                 leaf = (leaf + 1) & 7;
-                                if (!(lf & 1)) {
-                                    t0 = term;
-                                } else {
-                                    term += t0;
-                                    if (!(lf & 2)) {
-                                        lv1[0] = term;
-                                    } else {
-                                        term += lv1[0];
-                                        if (!(lf & 4)) {
-                                            lv2[0] = term;
-                                        } else {
-                                            term += lv2[0];
-                                            emit_block(term, cb, s.dir);
-                                        }
-                                    }
+                                if (leaf == 0) {
+                                    emit_block(t0, cb, s.dir);
+                                    t0 = 0.0;
                                 }
                             }
                         }
@@ -704,33 +688,10 @@ __global__ void __maxnreg__(TDX_EK0_MAXREG) ek0_fused_fhn_kernel(const __grid_co
                     }
                 }
                 if (RB == 8 && reduces && leaf != 0) {
-                    // the strip ends inside a row block (grid / shard end): the missing rows are zeros
-                    double v = 0.0;
-                    bool have = false;            // v holds a carried partial sum
-                    for (int lf = leaf; lf < 8; ++lf) {
-                        // push a zero leaf: only the carries matter
-                        if (!(lf & 1)) {
-                            t0 = 0.0;
-                            continue;
-                        }
-                        v = 0.0 + t0;
-                        if (!(lf & 2)) {
-                            lv1[0] = v;
-                            continue;
-                        }
-                        v += lv1[0];
-                        if (!(lf & 4)) {
-                            lv2[0] = v;
-                            continue;
-                        }
-                        v += lv2[0];
-                        have = true;
-                    }
-                    if (have) {
-                        csync();                  // a block finished in the strip's last row may still wait for its flush
-                        flush_block_partial();
-                        emit_block(v, cb, s.dir);
-                    }
+                    // the strip ends inside a row block (the grid / the shard ends there): the block's partial is the sum of the
+                    // rows there are.  The previous block was emitted at least one row (one barrier) ago.
+                    emit_block(t0, cb, s.dir);
+                    t0 = 0.0;
                     leaf = 0;
                 }
             }
@@ -739,7 +700,7 @@ __global__ void __maxnreg__(TDX_EK0_MAXREG) ek0_fused_fhn_kernel(const __grid_co
                 flush_block_partial();
                 csync();
                 if (tc == 0 && poisoned && ns > 0) {     // stale halos: fail the attempt everywhere
-                    const StripGeom s0 = strip_geom<W>(g, blockIdx.x, a.col_blocks, a.chunks, a.block0, a.nblocks, RB, has_lo, has_hi);
+                    const StripGeom s0 = strip_geom<W>(g, blockIdx.x, a.col_blocks, a.chunks, a.block0, a.nblocks, RB);
                     unit[s0.b0 * (int)a.col_blocks + (int)(blockIdx.x % a.col_blocks)] = nan("");
                 }
             }
@@ -846,7 +807,10 @@ __global__ void __maxnreg__(72) ek0_fused_chain_kernel(const __grid_constant__ E
 #pragma unroll 1
     for (int att = 0; att < max_attempts; ++att) {
         if (!ek0_attempt_begin<T, N, kCtl>(a, sh, att)) break;
-        const Consts<T, N>& c = kCtl ? sh.c : a.c;
+        decltype(auto) c = [&]() -> decltype(auto) {
+            if constexpr (kCtl) return StepView<T, N>{sh.p, sh.pinv, a.c.ql, sh.dt, a.c.abstol, a.c.reltol, a.c.want_norm, a.c.flags};
+            else return (a.c);
+        }();
         const Consts<double, N>& cdr = kCtl ? sh.cd : a.cd;
         const T* mean_in = a.mean_ring[sh.cur];
         T* mean_out = a.mean_ring[sh.out];

@@ -133,8 +133,8 @@ __device__ __forceinline__ int tile_col0(const Coord& c) { return c.col - c.tcol
 
 // kOwn = false: only the ring / fill values (the caller gets the thread's own column from somewhere else, e.g. a TMA stage)
 // kCoherent: the mean may have been written earlier in the same kernel (multi-attempt kernels): no read-only-path loads
-template <class IVP, typename T, int N, bool kOwn = true, bool kCoherent = false>
-__device__ __forceinline__ void front_load(const Geo& g, const Consts<T, N>& c, const T* __restrict__ mean_in,
+template <class IVP, typename T, int N, bool kOwn = true, bool kCoherent = false, class C = Consts<T, N>>
+__device__ __forceinline__ void front_load(const Geo& g, const C& c, const T* __restrict__ mean_in,
                                            const T* halo_lo, const T* halo_hi, const Coord& co,
                                            FrontRegs<IVP, T, N>& fr) {
     using E = ExtTile<IVP>;
@@ -148,7 +148,7 @@ __device__ __forceinline__ void front_load(const Geo& g, const Consts<T, N>& c, 
     }
     fr.ring = (T)0;
     fr.fill = (T)0;
-    MeanAt<T, N, kCoherent> at{mean_in, g.d, &c};
+    MeanAt<T, N, kCoherent, C> at{mean_in, g.d, &c};
     if (E::NRING > 0 && (int)threadIdx.x < IVP::Shape::NF * E::NRING) {
         const int field = threadIdx.x / (E::NRING > 0 ? E::NRING : 1);
         int er, ec;
@@ -160,12 +160,12 @@ __device__ __forceinline__ void front_load(const Geo& g, const Consts<T, N>& c, 
                                   halo_hi);
 }
 
-template <class IVP, typename T, int N, class Sync = FullSync>
-__device__ __forceinline__ void front_eval(const Geo& g, const Consts<T, N>& c, const Coord& co,
+template <class IVP, typename T, int N, class Sync = FullSync, class C = Consts<T, N>>
+__device__ __forceinline__ void front_eval(const Geo& g, const C& c, const Coord& co,
                                            const FrontRegs<IVP, T, N>& fr, T* s_ext, T (&mp)[N], T& fx, T& jac,
                                            Sync sync = Sync()) {
     using E = ExtTile<IVP>;
-    predict_column<T, N>(fr.raw, c, mp);
+    predict_column<T, N, C>(fr.raw, c, mp);
     const T own = co.valid ? c.p[0] * mp[0] : fr.fill;
     s_ext[E::own(co)] = own;
     if (E::NRING > 0 && (int)threadIdx.x < IVP::Shape::NF * E::NRING) {
@@ -202,11 +202,11 @@ struct PackPeer {
     int enabled;
 };
 
-template <typename T, int N, class Sync = FullSync, bool kCoherent = false>
-__device__ __forceinline__ void pack_halo_part(const Geo& g, const Consts<T, N>& c, const T* mean_in,
+template <typename T, int N, class Sync = FullSync, bool kCoherent = false, class C = Consts<T, N>>
+__device__ __forceinline__ void pack_halo_part(const Geo& g, const C& c, const T* mean_in,
                                                const PackPeer<T>& pk, unsigned long long seq, int part_index,
                                                Sync sync = Sync()) {
-    MeanAt<T, N, kCoherent> at{mean_in, g.d, &c};
+    MeanAt<T, N, kCoherent, C> at{mean_in, g.d, &c};
     const bool lower = part_index < kPackCtas;
     const int part = lower ? part_index : part_index - kPackCtas;
     const int par = (int)(seq & 1ull);
@@ -341,14 +341,13 @@ __global__ void __launch_bounds__(kThreads, DekSmem<T, N>::MIN_BLOCKS) dek1_kern
     constexpr size_t AT_STRIDE = L::at_bytes(ExtTile<IVP>::ELEMS) / sizeof(T);
     constexpr size_t SC_STRIDE = L::sc_bytes() / sizeof(T);
     __shared__ int s_flag, s_ok;
-    __shared__ Consts<T, N> s_c;                  // kCtl: the attempt's constants, rebuilt from the controller block
+    __shared__ T s_p[N], s_pinv[N], s_dt;         // kCtl: the step's vectors, rebuilt from the controller block before each attempt
     __shared__ int s_cur, s_out;
     __shared__ unsigned long long s_epoch0;
     __shared__ long long s_pause_at;
 
     const Geo& g = a.g;
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const Consts<T, N>* cp = &a.c;
     const T* mean_in = a.mean_in;
     const T* sc_in = a.sc_in;
     T* mean_out = a.mean_out;
@@ -384,14 +383,12 @@ __global__ void __launch_bounds__(kThreads, DekSmem<T, N>::MIN_BLOCKS) dek1_kern
                     ctl->failed = TDX_FAIL_GRID_BARRIER;
                     ctl->done = 1;
                 }
-                Consts<T, N> cc = a.c;            // Ql, tolerances and flags come with the launch, the step with the controller
 #pragma unroll
-                for (int k = 0; k < N; ++k) {
-                    cc.p[k] = (T)ctl->p[k];
-                    cc.pinv[k] = (T)ctl->pinv[k];
+                for (int k = 0; k < N; ++k) {     // Ql, tolerances and flags come with the launch, the step with the controller
+                    s_p[k] = (T)ctl->p[k];
+                    s_pinv[k] = (T)ctl->pinv[k];
                 }
-                cc.dt = (T)ctl->dt;
-                s_c = cc;
+                s_dt = (T)ctl->dt;
                 const int cur = ctl->cur, nbuf = ctl->nbuf;
                 s_cur = (ctl->done || !ok || ctl->accepted >= s_pause_at) ? -1 : cur;
                 s_out = (cur + 1) % nbuf;
@@ -399,7 +396,6 @@ __global__ void __launch_bounds__(kThreads, DekSmem<T, N>::MIN_BLOCKS) dek1_kern
             __syncthreads();
             if (s_cur < 0) break;                 // the solve is over (or a barrier timed out): nothing left to do
             if (att > 0) fence_proxy_async_global();   // TMA loads below read what other CTAs stored in the previous attempt
-            cp = &s_c;
             mean_in = a.mean_ring[s_cur];
             sc_in = a.sc_ring[s_cur];
             mean_out = a.mean_ring[s_out];
@@ -407,7 +403,10 @@ __global__ void __launch_bounds__(kThreads, DekSmem<T, N>::MIN_BLOCKS) dek1_kern
             err_out = a.err_ring[s_out];
             ref_out = a.ref_ring[s_out];
         }
-        const Consts<T, N>& c = *cp;
+        decltype(auto) c = [&]() -> decltype(auto) {
+            if constexpr (kCtl) return StepView<T, N>{s_p, s_pinv, a.c.ql, s_dt, a.c.abstol, a.c.reltol, a.c.want_norm, a.c.flags};
+            else return (a.c);
+        }();
         const unsigned long long hseq = a.wait.seq + (unsigned long long)att;          // halo sequence number of this attempt
         const T* halo_lo = a.halo_lo ? a.halo_lo + (long long)(hseq & 1ull) * a.halo_parity_stride : nullptr;
         const T* halo_hi = a.halo_hi ? a.halo_hi + (long long)(hseq & 1ull) * a.halo_parity_stride : nullptr;
