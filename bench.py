@@ -490,7 +490,7 @@ def run_mine(args):
         }
         # the controller-driven path: K attempts inside ONE persistent cooperative launch (halos + all-reduces in-kernel)
         results[name]["device_loop"] = device_loop_timed(torch, sol, state, dt, d, args.steps, max_over_ranks, barrier)
-        if not args.no_parity and args.dtype == "f64":
+        if not args.no_parity:
             parity[name] = parity_check(torch, args, sol, state, dt, problem, world, rank, dev)
         if not args.no_e2e:
             if name == args.solver:
@@ -578,6 +578,7 @@ def parity_check(torch, args, sol, state, dt, problem, world, rank, dev):
     eng = sol.engine
     is_dek1 = isinstance(sol, ek1.DiagonalEK1)
     n = NU + 1
+    tol_par = 1e-10 if args.dtype == "f64" else 1e-5     # north_star: 1e-10 in fp64, 1e-5 in fp32 (against the fp64 oracle)
     # The benchmark's state is a few tiny steps away from the exact Taylor initialisation: the residual z = p1 mp[1] - f cancels
     # to ~8 digits there, and any two correct implementations differ by ~1e-9 in everything that is scaled by z.  The check
     # therefore moves the mean off the solution manifold by 1e-3 (relative; a fixed function of the GLOBAL coordinate index, so
@@ -617,11 +618,11 @@ def parity_check(torch, args, sol, state, dt, problem, world, rank, dev):
             bufs = [torch.empty_like(last) for _ in range(world)]
             dist.all_gather(bufs, last)
             above = bufs[rank - 1] if rank > 0 else None
-        wm = gather_rows(state.y.mean, 0, take).cpu().numpy().reshape(n, nf, take * width)
-        wsc = gather_rows(state.y.cov_sqrtm, 0, take).cpu().numpy()
+        wm = gather_rows(state.y.mean, 0, take).double().cpu().numpy().reshape(n, nf, take * width)
+        wsc = gather_rows(state.y.cov_sqrtm, 0, take).double().cpu().numpy()
         halo = 0
         if above is not None:
-            ab = above.cpu().numpy().reshape(n, nf, width)
+            ab = above.double().cpu().numpy().reshape(n, nf, width)
             wm = np.concatenate((ab, wm), axis=2)
             halo = 1
             # the neighbour's factor blocks do not enter this shard's results: any block will do for the halo row
@@ -668,8 +669,8 @@ def parity_check(torch, args, sol, state, dt, problem, world, rank, dev):
         # keep what the window computes exactly: drop the halo row on top and the last row (its lower neighbour is outside)
         keep_lo, keep_hi = halo, rows - 1
         keep = np.concatenate([np.arange(fl * rows * width + keep_lo * width, fl * rows * width + keep_hi * width) for fl in range(nf)])
-        got_m = gather_rows(new.y.mean, 0, take - 1).cpu().numpy()
-        got_s = gather_rows(new.y.cov_sqrtm, 0, take - 1).cpu().numpy()
+        got_m = gather_rows(new.y.mean, 0, take - 1).double().cpu().numpy()
+        got_s = gather_rows(new.y.cov_sqrtm, 0, take - 1).double().cpu().numpy()
 
         def rel(x, y):
             return float(np.max(np.abs(x - y)) / max(np.max(np.abs(y)), 1e-300))
@@ -688,16 +689,17 @@ def parity_check(torch, args, sol, state, dt, problem, world, rank, dev):
             fused = float(new.scaled_error_norm_sq_sum.sum())
             out["norm_sq_sum_fused"], out["norm_sq_sum_recomputed"] = fused, float(tot)
             out["norm_rel_diff"] = abs(fused - float(tot)) / max(abs(float(tot)), 1e-300)
-        out["ok"] = bool(out["max_rel_err_mean"] < 1e-10 and out["max_rel_err_cov_sqrtm"] < 1e-10 and out.get("norm_rel_diff", 0.0) < 1e-10)
+        out["tolerance"] = tol_par
+        out["ok"] = bool(out["max_rel_err_mean"] < tol_par and out["max_rel_err_cov_sqrtm"] < tol_par and out.get("norm_rel_diff", 0.0) < tol_par)
     else:
         # the whole KroneckerEK0 attempt on rank 0
         def gather_full(t):
             if world == 1:
-                return t.cpu().numpy()
+                return t.double().cpu().numpy()
             import torch.distributed as dist
 
             parts = [None] * world
-            dist.all_gather_object(parts, (eng.begin, eng.end, t.cpu().numpy()))
+            dist.all_gather_object(parts, (eng.begin, eng.end, t.double().cpu().numpy()))
             if rank != 0:
                 return None
             full = np.empty((n, eng.d_global))
@@ -711,10 +713,10 @@ def parity_check(torch, args, sol, state, dt, problem, world, rank, dev):
         m_in, m_out = gather_full(state.y.mean), gather_full(new.y.mean)
         if rank == 0:
             _, oprob, _ = initial_condition(args)
-            ost, _ = filters.kronecker_ek0_attempt(filters.FilterState(float(state.t), m_in, state.y.cov_sqrtm_2.cpu().numpy(), None, None),
+            ost, _ = filters.kronecker_ek0_attempt(filters.FilterState(float(state.t), m_in, state.y.cov_sqrtm_2.double().cpu().numpy(), None, None),
                                                    dt, oprob.f, NU)
             e_mean = float(np.max(np.abs(m_out - ost.mean)) / np.max(np.abs(ost.mean)))
-            e_cl = float(np.max(np.abs(new.y.cov_sqrtm_2.cpu().numpy() - ost.cov_sqrtm)) / np.max(np.abs(ost.cov_sqrtm)))
+            e_cl = float(np.max(np.abs(new.y.cov_sqrtm_2.double().cpu().numpy() - ost.cov_sqrtm)) / np.max(np.abs(ost.cov_sqrtm)))
             e_err = abs(float(new.error_estimate) - ost.error_estimate) / abs(ost.error_estimate)
             tol = 1e-4 + 1e-2 * ost.reference_state
             ref_sum = float(np.sum((dt * ost.error_estimate / tol) ** 2))
@@ -722,7 +724,8 @@ def parity_check(torch, args, sol, state, dt, problem, world, rank, dev):
             out = {"window": "the whole attempt vs the NumPy oracle (state gathered on rank 0)", "max_rel_err_mean": e_mean,
                    "max_rel_err_cov_sqrtm": e_cl, "rel_err_error_estimate": e_err, "norm_sq_sum_fused": fused,
                    "norm_sq_sum_oracle": ref_sum, "norm_rel_diff": abs(fused - ref_sum) / abs(ref_sum)}
-            out["ok"] = bool(e_mean < 1e-10 and e_cl < 1e-10 and e_err < 1e-10 and out["norm_rel_diff"] < 1e-10)
+            out["tolerance"] = tol_par
+            out["ok"] = bool(e_mean < tol_par and e_cl < tol_par and e_err < tol_par and out["norm_rel_diff"] < tol_par)
     if world > 1:
         torch.distributed.barrier()
     return out

@@ -46,8 +46,12 @@ struct Consts {
 // (ld.global.nc) is not coherent within a kernel; single-attempt kernels keep it.
 template <bool kCoherent, typename T>
 __device__ __forceinline__ T ld_state(const T* p) {
+#ifdef TDX_EXP_CTL_LDG      // timing experiment only (NOT coherent across the attempts of a multi-attempt kernel)
+    return __ldg(p);
+#else
     if constexpr (kCoherent) return __ldcg(p);
     else return __ldg(p);
+#endif
 }
 
 // The constants of one attempt as a multi-attempt (controller-driven) kernel sees them: what comes with the launch (Ql,

@@ -630,8 +630,8 @@ __global__ void __launch_bounds__(kThreads, DekSmem<T, N>::MIN_BLOCKS) dek1_kern
             cur_bulk = next_bulk;
         }
 
-#ifdef TDX_DEK1_TIMING
-        if (threadIdx.x == 0) {      // development aid: when did this CTA run out of tiles? (scripts/dek1_timeline.py)
+#if defined(TDX_DEK1_TIMING) || defined(TDX_TIMELINE)
+        if (threadIdx.x == 0) {      // development aid: when did this CTA run out of tiles? (scripts/dek1_cta_spread.py)
             a.partials[1024 + 2 * blockIdx.x] = (double)global_timer_ns();
             unsigned smid;
             asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));

@@ -263,11 +263,17 @@ struct Launch {
             unsigned grid = 0;
             if (ctl) {
                 if (!whole) return (int)cudaErrorInvalidValue;
-                constexpr auto kern = dek1_kernel<IVP, T, N, true, true>;
-                TDX_CUDA_TRY(persistent_grid<kern>(smem, a.num_tiles, ws.reserve_ctas, grid));
                 // all CTAs wait for one another between the attempts: a cooperative launch guarantees that they are resident
                 void* params[] = {(void*)&a};
-                TDX_CUDA_TRY(cudaLaunchCooperativeKernel((const void*)kern, dim3(grid), dim3(kThreads), params, smem, st));
+                if (comm) {
+                    constexpr auto kern = dek1_kernel<IVP, T, N, true, true>;
+                    TDX_CUDA_TRY(persistent_grid<kern>(smem, a.num_tiles, ws.reserve_ctas, grid));
+                    TDX_CUDA_TRY(cudaLaunchCooperativeKernel((const void*)kern, dim3(grid), dim3(kThreads), params, smem, st));
+                } else {
+                    constexpr auto kern = dek1_kernel<IVP, T, N, false, true>;      // one GPU: none of the peer-memory code paths
+                    TDX_CUDA_TRY(persistent_grid<kern>(smem, a.num_tiles, ws.reserve_ctas, grid));
+                    TDX_CUDA_TRY(cudaLaunchCooperativeKernel((const void*)kern, dim3(grid), dim3(kThreads), params, smem, st));
+                }
             } else if (comm) {
                 constexpr auto kern = dek1_kernel<IVP, T, N, true>;
                 TDX_CUDA_TRY(persistent_grid<kern>(smem, a.num_tiles, ws.reserve_ctas, grid));
@@ -429,7 +435,9 @@ struct Launch {
         a.use_bulk = (g.cols % PADC == 0) && aligned16 ? 1 : 0;
         a.col_blocks = (unsigned)((g.cols + W - 1) / W);
         // strips are whole row blocks (8 grid rows, or single rows on small grids; aligned in global row numbers)
-        if (ek0_row_block(g.grows, (int)a.col_blocks) == 8) return launch_fhn<kCtl, 8>(g, a, ws, st);
+        static const int forced_rb = std::getenv("TDX_EK0_RB") ? std::atoi(std::getenv("TDX_EK0_RB")) : 0;   // experiments only
+        const int rb = forced_rb ? forced_rb : ek0_row_block(g.grows, (int)a.col_blocks);
+        if (rb == 8) return launch_fhn<kCtl, 8>(g, a, ws, st);
         return launch_fhn<kCtl, 1>(g, a, ws, st);
     }
 
