@@ -476,7 +476,9 @@ def run_mine(args):
         if name == args.solver and rank == 0:
             sampler.start()
         ms, state, launches, host_ms = timed_steps(sol, state, dt, args.steps, args.warmup)
-        clocks = sampler.stop() if (name == args.solver and rank == 0) else None
+        # the controller-driven path: K attempts inside ONE persistent cooperative launch (halos + all-reduces in-kernel)
+        dl = device_loop_timed(torch, sol, state, dt, d, args.steps, max_over_ranks, barrier)
+        clocks = sampler.stop() if (name == args.solver and rank == 0) else None      # sampled over both timed regions
         kms = ms / args.steps                                    # one launch per step, back to back: the kernel's average duration
         alg = ALG_BYTES[name](n, w) * (d / world)                # per launch, per GPU
         traffic, traffic_src = recorded_traffic(args, name) if world == 1 else (None, "single-GPU captures only")
@@ -488,8 +490,20 @@ def run_mine(args):
                          "peak_source": peak_src, "kernel_ms": kms, "algorithmic_bytes_per_launch": alg,
                          "kernel": "dek1_kernel" if name == "dek1" else ("ek0_fused_fhn_kernel" if args.workload == "fhn_2d" else "ek0_fused_chain_kernel")},
         }
-        # the controller-driven path: K attempts inside ONE persistent cooperative launch (halos + all-reduces in-kernel)
-        results[name]["device_loop"] = device_loop_timed(torch, sol, state, dt, d, args.steps, max_over_ranks, barrier)
+        results[name]["device_loop"] = dl
+        results[name]["per_launch"] = {"value": results[name]["value"], "ms_per_step": results[name]["ms_per_step"], "launches": launches}
+        # Headline = the faster of the library's two ways of running the same K attempts (both resident in HBM, both through the
+        # public solver API: attempt_step per attempt, or simulate_final_state's device-resident loop); the other one stays
+        # in the line.  On one GPU they are within a few per cent; sharded, the device loop has no host or launch in it.
+        if not dl["failed"] and dl["attempts"] == args.steps and dl["value"] > results[name]["value"]:
+            r = results[name]
+            r["path"] = "device_loop"
+            r["value"], r["ms_per_step"], r["launches"] = dl["value"], dl["ms_per_attempt"], 1
+            kms = dl["ms_per_attempt"]
+            r["roofline"].update({"achieved": alg / (kms * 1e-3) / 1e9, "frac": alg / (kms * 1e-3) / 1e9 / peak, "kernel_ms": kms,
+                                  "kernel_ms_note": "ONE launch runs all --steps attempts: launch duration / attempts"})
+        else:
+            results[name]["path"] = "per_launch"
         if not args.no_parity:
             parity[name] = parity_check(torch, args, sol, state, dt, problem, world, rank, dev)
         if not args.no_e2e:
@@ -520,21 +534,24 @@ def run_mine(args):
                 "l2": "the state streamed per attempt (mean+factors: 2.0 GB for DiagonalEK1, mean: 0.34 GB for KroneckerEK0 at "
                       "d = 8.4M fp64, divided by the number of GPUs) is larger than the 126 MB L2 on 1-2 GPUs; no flush (every attempt "
                       "reads the buffer the previous one wrote)",
-                "value": "attempt_step through the public API, one launch per attempt, state resident in HBM",
+                "value": "the faster of per_launch and device_loop (named in value_path), state resident in HBM",
+                "per_launch": "attempt_step through the public API, one launch per attempt",
                 "device_loop": "the same attempts under the device-resident controller: ONE persistent cooperative launch for all "
                                "--steps attempts (tdx_*_run_attempts), accept / reject and next dt decided on the device",
             },
             "clocks": main["clocks"],
             "e2e": main.get("e2e"),
             "e2e_resident": main.get("e2e_resident"),
+            "value_path": main["path"],
+            "per_launch": main.get("per_launch"),
             "device_loop": main.get("device_loop"),
             "gpu_launches": main["launches"],
             "roofline": main["roofline"],
             "cpu_baseline": cpu,
             "parity": parity or None,
             "host_enqueue_ms_per_step": main["host_enqueue_ms_per_step"],
-            "also": {other: {k: results[other].get(k) for k in ("value", "ms_per_step", "roofline", "launches", "host_enqueue_ms_per_step",
-                                                                "device_loop", "e2e")}},
+            "also": {other: {k: results[other].get(k) for k in ("value", "ms_per_step", "path", "roofline", "launches", "host_enqueue_ms_per_step",
+                                                                "per_launch", "device_loop", "e2e")}},
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -172,7 +172,7 @@ struct tdx_ctx {
     // workspace
     double* partials = nullptr;
     long long partials_cap = 0;
-    unsigned int* ticket = nullptr;   // [2]: the rim launch of an interior/rim pair uses the second workspace
+    unsigned int* ticket = nullptr;   // [8]: [0..1] arrival tickets (the rim launch of an interior/rim pair uses the second), [4..5] tile counters
     void* mid = nullptr;
     long long halo_lo = 0, halo_hi = 0;
     int64_t launches = 0;
@@ -260,8 +260,8 @@ int tdx_create(tdx_ctx** out, int device, int dtype) {
     int prev = 0;
     cudaGetDevice(&prev);
     cudaSetDevice(device);
-    e = cudaMalloc(&ctx->ticket, 2 * sizeof(unsigned int));
-    if (e == cudaSuccess) e = cudaMemset(ctx->ticket, 0, 2 * sizeof(unsigned int));
+    e = cudaMalloc(&ctx->ticket, 8 * sizeof(unsigned int));
+    if (e == cudaSuccess) e = cudaMemset(ctx->ticket, 0, 8 * sizeof(unsigned int));
     if (e == cudaSuccess) e = cudaMalloc(&ctx->mid, 256);
     if (e == cudaSuccess) e = cudaMemset(ctx->mid, 0, 256);
     cudaSetDevice(prev);
@@ -567,6 +567,7 @@ static Workspace make_ws(const tdx_ctx* ctx, unsigned flags = 0u) {
     Workspace ws{};
     ws.partials = ctx->partials + (second ? ctx->partials_cap : 0);
     ws.ticket = ctx->ticket + (second ? 1 : 0);
+    ws.tile_counter = ctx->ticket + 4 + (second ? 1 : 0);
     ws.mid = ctx->mid;
     ws.reserve_ctas = 0;
     ws.has_lo = ctx->halo_lo > 0;

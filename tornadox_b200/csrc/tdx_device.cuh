@@ -146,6 +146,12 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
     asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
+__device__ __forceinline__ unsigned long long ld_relaxed_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void fence_acq_rel_sys() { asm volatile("fence.acq_rel.sys;" ::: "memory"); }
 __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
@@ -154,6 +160,12 @@ __device__ __forceinline__ unsigned long long ld_acquire_gpu(const unsigned long
     asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
+__device__ __forceinline__ unsigned long long ld_relaxed_gpu(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
 __device__ __forceinline__ void st_release_gpu(unsigned long long* p, unsigned long long v) {
     asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
@@ -876,30 +888,44 @@ struct CommReduce {                                  // fused all-reduce of the 
 __device__ __forceinline__ bool spin_until(const unsigned long long* flag, unsigned long long seq,
                                            unsigned long long* error, unsigned long long timeout_ns = kDefaultWaitNs) {
     if (flag == nullptr) return true;
-    if (ld_acquire_sys(flag) >= seq) return true;
-    const unsigned long long t0 = global_timer_ns();
-    while (ld_acquire_sys(flag) < seq) {
-        if (global_timer_ns() - t0 > (timeout_ns ? timeout_ns : kDefaultWaitNs)) {
-            if (error) *error = 1ull;
-            return false;
+    // relaxed polls, ONE acquire fence once the value is there (see spin_until_gpu)
+    if (ld_relaxed_sys(flag) < seq) {
+        const unsigned long long t0 = global_timer_ns();
+        while (ld_relaxed_sys(flag) < seq) {
+            if (global_timer_ns() - t0 > (timeout_ns ? timeout_ns : kDefaultWaitNs)) {
+                if (error) *error = 1ull;
+                return false;
+            }
+            __nanosleep(40);
         }
-        __nanosleep(40);
     }
+    fence_acq_rel_sys();
     return true;
 }
 // the same at GPU scope (in-kernel grid barriers)
 __device__ __forceinline__ bool spin_until_gpu(const unsigned long long* flag, unsigned long long seq,
                                                unsigned long long timeout_ns = kDefaultWaitNs) {
-    if (ld_acquire_gpu(flag) >= seq) return true;
+    // Poll with RELAXED loads and fence once the value is there: an acquire load per poll makes the SM invalidate its L1 and
+    // order its memory pipeline every time, which the other CTA of the SM (still working on its tiles) pays for.
+    if (ld_relaxed_gpu(flag) >= seq) {
+        fence_acq_rel_gpu();
+        return true;
+    }
     const unsigned long long t0 = global_timer_ns();
     unsigned int spins = 0;
-    while (ld_acquire_gpu(flag) < seq) {
+    while (ld_relaxed_gpu(flag) < seq) {
+#ifdef TDX_POLL_SLOW            // experiment: never poll back to back
+        __nanosleep(400);
+        if ((++spins & 255u) == 0u && global_timer_ns() - t0 > (timeout_ns ? timeout_ns : kDefaultWaitNs)) return false;
+#else
         // the release is at most a few microseconds away in the common case: poll back to back first
         if (++spins > 64u) {
             if (global_timer_ns() - t0 > (timeout_ns ? timeout_ns : kDefaultWaitNs)) return false;
             __nanosleep(32);
         }
+#endif
     }
+    fence_acq_rel_gpu();
     return true;
 }
 // Who takes part in a CTA-level helper: the whole CTA (barrier 0), or the first COUNT threads through a named barrier

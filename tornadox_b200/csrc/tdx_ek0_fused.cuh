@@ -167,7 +167,11 @@ __device__ __forceinline__ StripGeom strip_geom(const Geo& g, unsigned strip, un
     // reuse across the turn-around).  One direction for all strips makes the order in which a thread adds the rows of a row
     // block a function of the phase only -- not of which strip, CTA or GPU the block landed in -- at the price of reading the
     // row two vertically adjacent strips share at different times (2 extra rows of DRAM reads per strip, < 4 % of a strip).
+#ifdef TDX_EXP_ALT_DIR      // timing experiment: vertically adjacent strips walk in opposite directions (sums then depend on the cut)
+    s.dir = (chunk & 1u) ? -1 : 1;
+#else
     s.dir = 1;
+#endif
     return s;
 }
 
@@ -231,6 +235,7 @@ struct Ek0CtaState {
     long long pause_at;
     uint64_t m1_bar;                 // the producer warp has published m1[attempt & 1]
     double m1[2][kMaxN + 1];
+    T gain[kMaxN];                   // the attempt's gain K (ek0.py:136): phase B reads it from here (broadcast), not from registers
     double timed_out;                // the wait for the global sum of z^2 timed out
 };
 
@@ -640,21 +645,23 @@ __global__ void __maxnreg__(TDX_EK0_MAXREG) ek0_fused_fhn_kernel(const __grid_co
                                 if constexpr (!kUpdate) {
                                     term += (double)z * (double)z;
                                 } else {
-                                    T* mo_ptr = out_ptr + (long long)f * g.npts;
-                                    T m0 = (T)0;
+                                    // all n values first, then the stores: the stores are opaque to the compiler (asm with a
+                                    // memory clobber), and loads of p / K between them would be serialised behind each one
+                                    T mo[N];
 #pragma unroll
-                                    for (int r = 0; r < N; ++r) {
-                                        const T mo = c.p[r] * (mp_m1[f][r] - K[r] * z);
-                                        if (hints) st_global_hint(mo_ptr, mo, i >= keep_from ? pol_keep : pol_stream);
-                                        else *mo_ptr = mo;
-                                        mo_ptr += g.d;
-                                        if (r == 0) m0 = mo;
-                                    }
-                                    const T ref = tabs<T>(m0);
-                                    if (ref_out) {
-                                        T* rp = ref_out + ((out_ptr - mean_out) + (long long)f * g.npts);
-                                        if (hints) st_global_hint(rp, ref, pol_stream);
-                                        else *rp = ref;
+                                    for (int r = 0; r < N; ++r) mo[r] = c.p[r] * (mp_m1[f][r] - sh.gain[r] * z);
+                                    T* mo_ptr = out_ptr + (long long)f * g.npts;
+                                    const T ref = tabs<T>(mo[0]);
+                                    T* rp = ref_out ? ref_out + ((out_ptr - mean_out) + (long long)f * g.npts) : nullptr;
+                                    if (hints) {
+                                        const uint64_t pol_row = i >= keep_from ? pol_keep : pol_stream;
+#pragma unroll
+                                        for (int r = 0; r < N; ++r) st_global_hint(mo_ptr + (long long)r * g.d, mo[r], pol_row);
+                                        if (rp) st_global_hint(rp, ref, pol_stream);
+                                    } else {
+#pragma unroll
+                                        for (int r = 0; r < N; ++r) mo_ptr[(long long)r * g.d] = mo[r];
+                                        if (rp) *rp = ref;
                                     }
                                     if (c.want_norm) {
                                         const double tol = (double)c.abstol + (double)c.reltol * (double)ref;
@@ -710,34 +717,43 @@ __global__ void __maxnreg__(TDX_EK0_MAXREG) ek0_fused_fhn_kernel(const __grid_co
 #pragma unroll
         for (int r = 0; r < N; ++r) K[r] = (T)0;
 
-#ifdef TDX_EK0_TIMING
-        double* stamps = a.partials + 1024 + 4 * blockIdx.x;    // [t_start, t_end_A, t_gain_seen, t_end_B] in ns
+#ifdef TDX_TIMELINE
+        // development aid (scripts/ek0_cta_spread.py): per CTA [t_start, t_end_A, t_gain_seen, t_end_B, t_fenced] in ns, and its SM
+        double* stamps = a.partials + 4096 + 8 * blockIdx.x;
         if (tc == 0) {
             stamps[0] = (double)global_timer_ns();
             unsigned smid;
             asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-            a.partials[1024 + 4096 + blockIdx.x] = (double)smid;
+            stamps[5] = (double)smid;
         }
 #endif
         // ---- phase A ------------------------------------------------------------------------------------------------
         if (tc == 0) TDX_STAMP(a.partials, att, 0);
         run_phase(std::false_type{}, K, a.red_a.unit);
-#ifdef TDX_EK0_TIMING
+#ifdef TDX_TIMELINE
         if (tc == 0) stamps[1] = (double)global_timer_ns();
 #endif
         if (tc == 0) TDX_STAMP(a.partials, att, 1);
         const double err_cal = ek0_mid_barrier<T, N>(a, sh, cdr, att, s_red, K, csync);
+        if (tc == 0) {
+#pragma unroll
+            for (int r = 0; r < N; ++r) sh.gain[r] = K[r];
+        }
+        csync();
         if (tc == 0) TDX_STAMP(a.partials, att, 2);
-#ifdef TDX_EK0_TIMING
+#ifdef TDX_TIMELINE
         if (tc == 0) stamps[2] = (double)global_timer_ns();
 #endif
         // ---- phase B ------------------------------------------------------------------------------------------------
         run_phase(std::true_type{}, K, a.red_b.unit);
-#ifdef TDX_EK0_TIMING
+#ifdef TDX_TIMELINE
         if (tc == 0) stamps[3] = (double)global_timer_ns();
 #endif
         if (tc == 0) TDX_STAMP(a.partials, att, 3);
         if (kCtl) fence_proxy_async_global();          // the next attempt's TMA loads read what this thread just stored
+#ifdef TDX_TIMELINE
+        if (tc == 0) stamps[4] = (double)global_timer_ns();
+#endif
         ek0_end_barrier<T, N, kCtl>(a, sh, c, att, err_cal, s_red, csync);
         if (tc == 0) TDX_STAMP(a.partials, att, 4);
     }

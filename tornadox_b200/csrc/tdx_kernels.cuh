@@ -268,6 +268,7 @@ struct DekArgs {
     long long halo_parity_stride;      // elements between the parity-0 and parity-1 buffers (0: caller-provided halos)
     double* partials;                  // per-CTA partial sums (launches over a part of the tiles only)
     unsigned int* ticket;
+    unsigned int* tile_counter;        // non-null: a CTA's third, fourth, ... tile come from this counter (zero at launch, reset by the last CTA)
     double* out_sum;
     RedPlan red;                       // per-tile partials + the sharding-independent summation order (unit == null: per-CTA partials)
     unsigned int num_tiles, tiles_x;   // num_tiles = number of tiles THIS launch processes (all ranges)
@@ -341,6 +342,7 @@ __global__ void __launch_bounds__(kThreads, DekSmem<T, N>::MIN_BLOCKS) dek1_kern
     constexpr size_t AT_STRIDE = L::at_bytes(ExtTile<IVP>::ELEMS) / sizeof(T);
     constexpr size_t SC_STRIDE = L::sc_bytes() / sizeof(T);
     __shared__ int s_flag, s_ok;
+    __shared__ unsigned int s_next[2];            // dynamic tile hand-out: the tile after next, fetched one iteration ahead
     __shared__ T s_p[N], s_pinv[N], s_dt;         // kCtl: the step's vectors, rebuilt from the controller block before each attempt
     __shared__ int s_cur, s_out;
     __shared__ unsigned long long s_epoch0;
@@ -450,10 +452,14 @@ __global__ void __launch_bounds__(kThreads, DekSmem<T, N>::MIN_BLOCKS) dek1_kern
             for (int part = (int)blockIdx.x; part < 2 * kPackCtas; part += (int)gridDim.x)   // a small grid takes several parts per CTA
                 pack_halo_part<T, N, FullSync, kCtl>(g, c, mean_in, a.pack, a.pack.seq + (unsigned long long)att, part);
         if (threadIdx.x == 0) TDX_STAMP(a.partials, att, 0);
+#ifdef TDX_TIMELINE
+        if (threadIdx.x == 0) a.partials[5000 + 2 * blockIdx.x] = (double)global_timer_ns();     // this CTA starts on its tiles
+#endif
         bool halos_ready = false;          // CTA-uniform: the arrival flags have been seen
         bool poisoned = false;             // CTA-uniform: a halo wait timed out
         unsigned tile = kComm ? (gridDim.x - 1u - blockIdx.x) : blockIdx.x;
         const bool unit_mode = a.red.unit != nullptr;
+        const bool dyn_tiles = a.tile_counter != nullptr;
         double legacy_acc = 0.0;           // per-thread running sum (launches over a part of the tiles: per-CTA partials)
         int pending_unit = -1;             // CTA-uniform: the tile whose warp sums wait in s_red for the next barrier
         bool cur_bulk = false;
@@ -478,6 +484,12 @@ __global__ void __launch_bounds__(kThreads, DekSmem<T, N>::MIN_BLOCKS) dek1_kern
         unsigned it = 0;
         for (; tile < a.num_tiles; ++it) {
             const int slot = (SC_SLOTS == 2) ? (int)(it & 1u) : 0;
+            unsigned fetched = 0u;         // thread 0: the ticket for the tile after next (in flight while this tile is computed)
+            if (dyn_tiles && threadIdx.x == 0) fetched = 2u * gridDim.x + atomicAdd(a.tile_counter, 1u);
+#ifdef TDX_TIMELINE
+            if (threadIdx.x == 0 && (it == 28u || it == 56u || it == 84u))
+                a.partials[5600 + 4 * blockIdx.x + (it / 28u - 1u)] = (double)global_timer_ns();
+#endif
             T* my_sc = s_sc0 + slot * SC_STRIDE + w * 32 * STRIDE;
             T* s_at = s_at0 + (it & 1u) * AT_STRIDE;
             if (kComm && !halos_ready && tile >= a.ranges.wait_from) {
@@ -497,8 +509,9 @@ __global__ void __launch_bounds__(kThreads, DekSmem<T, N>::MIN_BLOCKS) dek1_kern
             }
             if (unit_mode) flush_tile_partial(it - 1u);   // the barrier inside front_eval ordered the previous tile's warp sums
 
-            // (2) start streaming the next tile's factor blocks into the other slot
-            const unsigned next = tile + gridDim.x;
+            // (2) start streaming the next tile's factor blocks into the other slot.  The first two tiles of a CTA are fixed;
+            // the others were fetched from the counter by thread 0 one iteration ago (published by the barrier above).
+            const unsigned next = (!dyn_tiles || it == 0u) ? tile + gridDim.x : s_next[it & 1u];
             bool next_bulk = false;
             if (SC_SLOTS == 2 && next < a.num_tiles) {
                 if (lane == 0) bulk_wait_read0();      // the other slot's previous results have left shared memory
@@ -626,6 +639,7 @@ __global__ void __launch_bounds__(kThreads, DekSmem<T, N>::MIN_BLOCKS) dek1_kern
                 s_term[(it & 1u) * kThreads + threadIdx.x] = ratio_sq;
                 pending_unit = (int)tile_id;
             }
+            if (dyn_tiles && threadIdx.x == 0) s_next[(it + 1u) & 1u] = fetched;
             tile = next;
             cur_bulk = next_bulk;
         }
@@ -633,6 +647,9 @@ __global__ void __launch_bounds__(kThreads, DekSmem<T, N>::MIN_BLOCKS) dek1_kern
 #if defined(TDX_DEK1_TIMING) || defined(TDX_TIMELINE)
         if (threadIdx.x == 0) {      // development aid: when did this CTA run out of tiles? (scripts/dek1_cta_spread.py)
             a.partials[1024 + 2 * blockIdx.x] = (double)global_timer_ns();
+#ifdef TDX_TIMELINE
+            a.partials[5000 + 2 * blockIdx.x + 1] = (double)it;
+#endif
             unsigned smid;
             asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
             a.partials[1024 + 2 * blockIdx.x + 1] = (double)smid;
@@ -644,11 +661,20 @@ __global__ void __launch_bounds__(kThreads, DekSmem<T, N>::MIN_BLOCKS) dek1_kern
         // ---- end of the attempt: everything this CTA wrote must be visible before it reports in ------------------------
         if constexpr (kCtl) {
             if (lane == 0) bulk_wait0();              // the factor blocks have LANDED in global memory (not just left shared memory)
+#ifdef TDX_TIMELINE
+            if (threadIdx.x == 0) a.partials[3072 + 4 * blockIdx.x + 0] = (double)global_timer_ns();
+#endif
             fence_proxy_async_global();               // ... and ordinary stores are ordered before the next attempt's TMA loads
+#ifdef TDX_TIMELINE
+            if (threadIdx.x == 0) a.partials[3072 + 4 * blockIdx.x + 1] = (double)global_timer_ns();
+#endif
         }
         __syncthreads();
         if (unit_mode) flush_tile_partial(it - 1u);
         __syncthreads();
+#ifdef TDX_TIMELINE
+        if (threadIdx.x == 0) a.partials[3072 + 4 * blockIdx.x + 2] = (double)global_timer_ns();
+#endif
         if (threadIdx.x == 0 && poisoned) {           // stale halos: the attempt must not be accepted anywhere
             if (unit_mode) a.red.unit[a.ranges.tile(kComm ? (gridDim.x - 1u - blockIdx.x) : blockIdx.x)] = nan("");
             else legacy_acc = nan("");
@@ -656,7 +682,12 @@ __global__ void __launch_bounds__(kThreads, DekSmem<T, N>::MIN_BLOCKS) dek1_kern
         double total = 0.0;
         bool fin = false;                             // thread 0 of the last CTA
         if (unit_mode) {
-            if (cta_arrive_last(a.ticket, &s_flag)) {
+            const bool last_cta = cta_arrive_last(a.ticket, &s_flag);
+#ifdef TDX_TIMELINE
+            if (kCtl && threadIdx.x == 0) a.partials[3072 + 4 * blockIdx.x + 3] = (double)global_timer_ns();
+#endif
+            if (last_cta) {
+                if (threadIdx.x == 0 && dyn_tiles) *a.tile_counter = 0u;      // everybody is past its last fetch
                 if (threadIdx.x == 0) TDX_STAMP_ANY(a.partials, att, 3);
                 // ConstantSteps on one GPU: nothing to add up, the rendezvous alone orders the attempts
                 if (c.want_norm || (kComm && a.reduce.world > 0))

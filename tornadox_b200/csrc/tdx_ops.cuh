@@ -23,6 +23,7 @@ struct StepHost {
 struct Workspace {
     double* partials;        // >= grid doubles
     unsigned int* ticket;
+    unsigned int* tile_counter;        // dynamic hand-out of the DiagonalEK1 tiles (zero between launches)
     void* mid;               // Ek0Mid<T, N>
     int reserve_ctas;        // CTAs left free on the device (room for a concurrent NCCL kernel)
     bool has_lo, has_hi;     // the shard has a lower / upper neighbour (halo buffers exist)
@@ -255,6 +256,10 @@ struct Launch {
             const bool whole = a.num_tiles == a.tiles_x * tiles_y && (long long)a.num_tiles <= ws.unit_cap &&
                                !(force_cta_partials() && !ctl && ws.reduce.world == 0);
             a.red = whole ? tile_red_plan<Shape>(g, ws.unit_a, a.tiles_x, tiles_y) : RedPlan{};
+            // tiles beyond a CTA's first two are handed out through a counter (the last CTA of the attempt's rendezvous resets
+            // it): a CTA that falls behind its SM mate simply takes fewer tiles.  Needs the rendezvous, i.e. a norm or a controller.
+            static const bool static_tiles = std::getenv("TDX_STATIC_TILES") != nullptr;      // A/B experiments
+            a.tile_counter = (whole && a.red.unit != nullptr && (h.want_norm || ctl) && !static_tiles) ? ws.tile_counter : nullptr;
             if (a.num_tiles == 0u) {
                 if (h.want_norm) TDX_CUDA_TRY(cudaMemsetAsync(out_sum, 0, sizeof(double), st));
                 return 0;
@@ -272,7 +277,9 @@ struct Launch {
                 } else {
                     constexpr auto kern = dek1_kernel<IVP, T, N, false, true>;      // one GPU: none of the peer-memory code paths
                     TDX_CUDA_TRY(persistent_grid<kern>(smem, a.num_tiles, ws.reserve_ctas, grid));
-                    TDX_CUDA_TRY(cudaLaunchCooperativeKernel((const void*)kern, dim3(grid), dim3(kThreads), params, smem, st));
+                    static const bool plain = std::getenv("TDX_EXP_PLAIN_CTL_LAUNCH") != nullptr;    // experiments only
+                    if (plain) kern<<<grid, kThreads, smem, st>>>(a);
+                    else TDX_CUDA_TRY(cudaLaunchCooperativeKernel((const void*)kern, dim3(grid), dim3(kThreads), params, smem, st));
                 }
             } else if (comm) {
                 constexpr auto kern = dek1_kernel<IVP, T, N, true>;
