@@ -1105,7 +1105,8 @@ __device__ __forceinline__ double reduce_units(const RedPlan& rp, const CommRedu
             if ((b0 > lo_all ? b0 : lo_all) < (b1 < hi_all ? b1 : hi_all)) dst->red_val[parity][cr->rank][cnt++] = s_red[c];
         }
         dst->red_cnt[parity][cr->rank] = cnt;
-        __threadfence_system();
+        // the chunk sums, the count and the flag are written by THIS thread: the release store alone orders them (a separate
+        // system-scope fence in front of it costs one more NVLink round trip per exchange)
         st_release_sys(&dst->red_flag[parity][cr->rank], seq);
     }
     sync();
