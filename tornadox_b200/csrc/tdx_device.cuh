@@ -1110,17 +1110,33 @@ __device__ __forceinline__ double reduce_units(const RedPlan& rp, const CommRedu
         st_release_sys(&dst->red_flag[parity][cr->rank], seq);
     }
     sync();
-    if (r < cr->world) {
-        const bool ok = spin_until(&cr->local->red_flag[parity][r], seq, &cr->local->error, cr->timeout_ns);
-        if (!ok) s_red[kRedChunks + 1] = 1.0;
-    }
-    sync();
-    if (r == 0) {
-        for (int k = 0; k < cr->world; ++k) {
-            const int cnt = *((volatile int*)&cr->local->red_cnt[parity][k]);
-            for (int j = 0; j < cnt && j < kRedChunks; ++j) total += *((volatile double*)&cr->local->red_val[parity][k][j]);
+    // Warp 0 gathers: lane k waits for rank k's flag and loads rank k's count and ALL its value slots with independent loads (one
+    // memory latency per lane instead of one per value: the slots were written by a peer and miss every cache); the sum itself
+    // is formed by every lane of the warp in (rank, chunk) order from the other lanes' registers.
+    static_assert(kMaxWorld <= 32, "one lane per rank");
+    if ((threadIdx.x >> 5) == 0) {
+        const int lane = threadIdx.x & 31;
+        bool ok = true;
+        int cnt = 0;
+        double v[kRedChunks];
+#pragma unroll
+        for (int j = 0; j < kRedChunks; ++j) v[j] = 0.0;
+        if (lane < cr->world) {
+            ok = spin_until(&cr->local->red_flag[parity][lane], seq, &cr->local->error, cr->timeout_ns);
+            cnt = *((volatile int*)&cr->local->red_cnt[parity][lane]);
+#pragma unroll
+            for (int j = 0; j < kRedChunks; ++j) v[j] = *((volatile double*)&cr->local->red_val[parity][lane][j]);
         }
-        if (s_red[kRedChunks + 1] != 0.0) total = nan("");
+        const bool failed = __any_sync(0xffffffffu, !ok);
+        for (int k = 0; k < cr->world; ++k) {
+            const int ck = __shfl_sync(0xffffffffu, cnt, k);
+#pragma unroll
+            for (int j = 0; j < kRedChunks; ++j) {
+                const double x = __shfl_sync(0xffffffffu, v[j], k);
+                if (j < ck) total += x;
+            }
+        }
+        if (failed) total = nan("");
     }
     return total;
 }
