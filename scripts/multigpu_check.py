@@ -33,17 +33,25 @@ def main():
     from helpers import random_state
     from tornadox_b200 import odefilter, rv
 
-    for kind, size in (("fhn_2d", 64), ("fhn_2d", 50), ("brusselator", 1000), ("lorenz96", 4099)):
+    # fhn_2d 1024: the fused KroneckerEK0 kernel's row-block sums (8 grid rows per unit, large grids only) incl. the strips under a
+    # shard's lower edge, which walk against the summation order
+    for kind, size, solvers in (("fhn_2d", 64, ("dek1", "ek0")), ("fhn_2d", 50, ("dek1", "ek0")), ("brusselator", 1000, ("dek1", "ek0")),
+                                ("lorenz96", 4099, ("dek1", "ek0")), ("fhn_2d", 1024, ("ek0",))):
         o, p, _ = make_pair(kind, size)
         nu = 4
         n, d = nu + 1, o.y0.shape[0]
         # a mid-solve looking state (right after an exact Taylor init the residual is rounding noise)
         rng = np.random.default_rng(size)
-        mean, blocks = random_state(rng, n, d, "dense")
+        if "dek1" in solvers:
+            mean, blocks = random_state(rng, n, d, "dense")
+        else:
+            mean, blocks = rng.standard_normal((n, d)), None
         mean[0] = o.y0 + 0.05 * rng.standard_normal(d)
         single = 1e-2 * rng.standard_normal((n, n))
         dt = 1e-4 if kind == "fhn_2d" else 1e-3
-        for name in ("dek1", "ek0"):
+        if size >= 1024:
+            dt = 1e-6
+        for name in solvers:
             cls = ek1.DiagonalEK1 if name == "dek1" else ek0.KroneckerEK0
             sol = cls(num_derivatives=nu, steprule=step.AdaptiveSteps(), process_group=group)
             sol.initialize(*p)
@@ -103,7 +111,8 @@ def main():
             assert e_f < 1e-13, (kind, e_f)
     # whole adaptive solves, sharded: the native accept / reject loop and the device-resident step controller must both
     # reproduce the unsharded oracle's accepted-step count and final state on every rank
-    for kind, size, tmax in (("fhn_2d", 32, 2e-3), ("brusselator", 400, 3e-3), ("lorenz96", 600, 0.5)):
+    # (brusselator 4096: 16 tiles per field, so that 2, 4 and 8 equal shards are all cuts of the global summation grid)
+    for kind, size, tmax in (("fhn_2d", 32, 2e-3), ("brusselator", 400, 3e-3), ("lorenz96", 600, 0.5), ("brusselator", 4096, 4e-5)):
         o, p, series_f = make_pair(kind, size)
         o, p = o._replace(tmax=tmax), p._replace(tmax=tmax)
         nu = 3

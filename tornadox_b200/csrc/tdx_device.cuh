@@ -1055,6 +1055,15 @@ __device__ __forceinline__ double reduce_units(const RedPlan& rp, const CommRedu
         for (int j = 0; j < 2; ++j) {
             unsigned long long u = j == 0 ? u0 : u1;
             double x = acc[j];
+            // a warp whose other chunk is empty (sharded runs: a rank owns 16 / G chunks) or shorter still takes deep batches
+            while (u + 32ull * (kBatch - 1) < b1[j]) {
+                double v[kBatch];
+#pragma unroll
+                for (int i = 0; i < kBatch; ++i) v[i] = __ldcg(base + u + 32 * i);
+#pragma unroll
+                for (int i = 0; i < kBatch; ++i) x += v[i];
+                u += 32ull * kBatch;
+            }
             while (u + 32ull * (kTail - 1) < b1[j]) {
                 double v[kTail];
 #pragma unroll

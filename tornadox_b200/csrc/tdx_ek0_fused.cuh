@@ -41,9 +41,10 @@ struct Ek0FusedCfg {
     static constexpr int AT_ROW = W + 2;                  // [left edge][W own][right edge]
     static constexpr int AT_ELEMS = 2 * 2 * AT_ROW;       // [slot][field][AT_ROW]
     static constexpr size_t BAR_BYTES = 128, RED_BYTES = 512;
+    static constexpr size_t BUF_BYTES = 8 * (size_t)W_ * sizeof(double);     // a row block's terms per thread (strips that walk against the summation order)
     __host__ __device__ static constexpr size_t at_bytes() { return ((size_t)AT_ELEMS * sizeof(T) + 127) / 128 * 128; }
     __host__ __device__ static constexpr size_t stage_bytes() { return (size_t)STAGE_ELEMS * sizeof(T); }
-    __host__ __device__ static constexpr size_t total() { return BAR_BYTES + RED_BYTES + at_bytes() + STAGES * stage_bytes(); }
+    __host__ __device__ static constexpr size_t total() { return BAR_BYTES + RED_BYTES + BUF_BYTES + at_bytes() + STAGES * stage_bytes(); }
     static_assert((STAGE_ELEMS * sizeof(T)) % 16 == 0 && (WP * sizeof(T)) % 16 == 0, "TMA destinations stay 16-byte aligned");
     static_assert(W_ % 32 == 0 && W_ <= 256, "one row partial per consumer warp, at most eight");
 };
@@ -153,7 +154,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 
 template <int W>
 __device__ __forceinline__ StripGeom strip_geom(const Geo& g, unsigned strip, unsigned col_blocks, unsigned chunks, int block0,
-                                                int nblocks, int kRowBlock) {
+                                                int nblocks, int kRowBlock, bool has_lo) {
     StripGeom s;
     const unsigned chunk = strip / col_blocks, cb = strip - chunk * col_blocks;
     s.c0 = (int)cb * W;
@@ -163,15 +164,12 @@ __device__ __forceinline__ StripGeom strip_geom(const Geo& g, unsigned strip, un
     s.b0 = bl;
     s.r0 = max(0, (int)((long long)(block0 + bl) * kRowBlock - g.grow0));
     s.r1 = min(g.rows, (int)((long long)(block0 + bh) * kRowBlock - g.grow0));
-    // Every strip walks UP in phase A and DOWN in phase B (the rows phase A read last are the rows phase B reads first: L2
-    // reuse across the turn-around).  One direction for all strips makes the order in which a thread adds the rows of a row
-    // block a function of the phase only -- not of which strip, CTA or GPU the block landed in -- at the price of reading the
-    // row two vertically adjacent strips share at different times (2 extra rows of DRAM reads per strip, < 4 % of a strip).
-#ifdef TDX_EXP_ALT_DIR      // timing experiment: vertically adjacent strips walk in opposite directions (sums then depend on the cut)
-    s.dir = (chunk & 1u) ? -1 : 1;
-#else
-    s.dir = 1;
-#endif
+    // Strips walk UP in phase A and DOWN in phase B (the rows phase A read last are the rows phase B reads first: L2 reuse
+    // across the turn-around), and that is also the order in which a thread adds the rows of a row block -- a function of the
+    // phase only, not of which strip, CTA or GPU the block landed in.  ONE exception to the walk, not to the order of the sums:
+    // the strips under the shard's lower edge walk DOWN in phase A so that the neighbour GPU's halo row is needed last, not
+    // first (its delivery takes ~10 us from the start of the attempt); they buffer a block's terms and add them in the usual order.
+    s.dir = (has_lo && chunk == 0u && chunks > 1u) ? -1 : 1;
     return s;
 }
 
@@ -375,8 +373,9 @@ __global__ void __maxnreg__(TDX_EK0_MAXREG) ek0_fused_fhn_kernel(const __grid_co
     uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);                                   // [S] data has landed
     uint64_t* empty = full + S;                                                               // [S] consumers are done
     double* s_red = reinterpret_cast<double*>(smem_raw + Cfg::BAR_BYTES);                     // see kEk0Red*
-    T* s_at = reinterpret_cast<T*>(smem_raw + Cfg::BAR_BYTES + Cfg::RED_BYTES);               // [2][2][AT_ROW]
-    T* s_stage = reinterpret_cast<T*>(smem_raw + Cfg::BAR_BYTES + Cfg::RED_BYTES + Cfg::at_bytes());
+    double* s_buf = reinterpret_cast<double*>(smem_raw + Cfg::BAR_BYTES + Cfg::RED_BYTES);                    // [8][W]
+    T* s_at = reinterpret_cast<T*>(smem_raw + Cfg::BAR_BYTES + Cfg::RED_BYTES + Cfg::BUF_BYTES);               // [2][2][AT_ROW]
+    T* s_stage = reinterpret_cast<T*>(smem_raw + Cfg::BAR_BYTES + Cfg::RED_BYTES + Cfg::BUF_BYTES + Cfg::at_bytes());
     __shared__ Ek0CtaState<T, N> sh;
 
     const Geo& g = a.g;
@@ -431,7 +430,7 @@ __global__ void __maxnreg__(TDX_EK0_MAXREG) ek0_fused_fhn_kernel(const __grid_co
 #pragma unroll 1
                 for (int kk = 0; kk < ns; ++kk) {
                     const int k = phase ? ns - 1 - kk : kk;
-                    StripGeom s = strip_geom<W>(g, blockIdx.x + (unsigned)k * gridDim.x, a.col_blocks, a.chunks, a.block0, a.nblocks, RB);
+                    StripGeom s = strip_geom<W>(g, blockIdx.x + (unsigned)k * gridDim.x, a.col_blocks, a.chunks, a.block0, a.nblocks, RB, has_lo);
                     if (phase) s.dir = -s.dir;
                     const int L = s.r1 - s.r0 + 2;
                     const int gs = max(s.c0 - PADC, 0), ge = min(s.c0 + W + PADC, g.cols);
@@ -535,7 +534,7 @@ __global__ void __maxnreg__(TDX_EK0_MAXREG) ek0_fused_fhn_kernel(const __grid_co
             for (int kk = 0; kk < ns; ++kk) {
                 const int k = kUpdate ? ns - 1 - kk : kk;
                 const unsigned strip = blockIdx.x + (unsigned)k * gridDim.x;
-                StripGeom s = strip_geom<W>(g, strip, a.col_blocks, a.chunks, a.block0, a.nblocks, RB);
+                StripGeom s = strip_geom<W>(g, strip, a.col_blocks, a.chunks, a.block0, a.nblocks, RB, has_lo);
                 const int cb = (int)(strip % a.col_blocks);
                 if (kUpdate) s.dir = -s.dir;
                 const int L = s.r1 - s.r0 + 2;
@@ -559,6 +558,11 @@ __global__ void __maxnreg__(TDX_EK0_MAXREG) ek0_fused_fhn_kernel(const __grid_co
                         leaf = s.dir > 0 ? pos : 7 - pos;
                         t0 = 0.0;
                     }
+                }
+                const bool buffered = RB == 8 && reduces && s.dir != (kUpdate ? -1 : 1);
+                if (buffered) {
+#pragma unroll
+                    for (int j8 = 0; j8 < 8; ++j8) s_buf[j8 * W + tc] = 0.0;
                 }
                 // the rows phase B writes last are the rows the NEXT attempt's phase A reads first -> keep those in L2
                 const int keep_from = (kUpdate && hints) ? L - (int)ceilf(a.keep_frac * (float)(s.r1 - s.r0)) : L;
@@ -675,11 +679,26 @@ __global__ void __maxnreg__(TDX_EK0_MAXREG) ek0_fused_fhn_kernel(const __grid_co
                             if (RB == 1) {
                                 emit_block(term, cb, s.dir);
                             } else {
-                                t0 += term;                   // rows of a block in walking order: up in phase A, down in phase B
-                                leaf = (leaf + 1) & 7;
-                                if (leaf == 0) {
-                                    emit_block(t0, cb, s.dir);
-                                    t0 = 0.0;
+                                if (!buffered) {
+                                    t0 += term;               // rows of a block in walking order: up in phase A, down in phase B
+                                    leaf = (leaf + 1) & 7;
+                                    if (leaf == 0) {
+                                        emit_block(t0, cb, s.dir);
+                                        t0 = 0.0;
+                                    }
+                                } else {
+                                    // this strip walks against the summation order: park the term, add at the end of the block
+                                    s_buf[(7 - leaf) * W + tc] = term;
+                                    leaf = (leaf + 1) & 7;
+                                    if (leaf == 0) {
+                                        double x = 0.0;
+#pragma unroll
+                                        for (int j8 = 0; j8 < 8; ++j8) {
+                                            x += s_buf[j8 * W + tc];
+                                            s_buf[j8 * W + tc] = 0.0;
+                                        }
+                                        emit_block(x, cb, s.dir);
+                                    }
                                 }
                             }
                         }
@@ -697,7 +716,13 @@ __global__ void __maxnreg__(TDX_EK0_MAXREG) ek0_fused_fhn_kernel(const __grid_co
                 if (RB == 8 && reduces && leaf != 0) {
                     // the strip ends inside a row block (the grid / the shard ends there): the block's partial is the sum of the
                     // rows there are.  The previous block was emitted at least one row (one barrier) ago.
-                    emit_block(t0, cb, s.dir);
+                    double x = t0;
+                    if (buffered) {
+                        x = 0.0;
+#pragma unroll
+                        for (int j8 = 0; j8 < 8; ++j8) x += s_buf[j8 * W + tc];      // rows the block does not have are +0.0
+                    }
+                    emit_block(x, cb, s.dir);
                     t0 = 0.0;
                     leaf = 0;
                 }
@@ -707,7 +732,7 @@ __global__ void __maxnreg__(TDX_EK0_MAXREG) ek0_fused_fhn_kernel(const __grid_co
                 flush_block_partial();
                 csync();
                 if (tc == 0 && poisoned && ns > 0) {     // stale halos: fail the attempt everywhere
-                    const StripGeom s0 = strip_geom<W>(g, blockIdx.x, a.col_blocks, a.chunks, a.block0, a.nblocks, RB);
+                    const StripGeom s0 = strip_geom<W>(g, blockIdx.x, a.col_blocks, a.chunks, a.block0, a.nblocks, RB, has_lo);
                     unit[s0.b0 * (int)a.col_blocks + (int)(blockIdx.x % a.col_blocks)] = nan("");
                 }
             }
