@@ -10,11 +10,11 @@ S=gpurun_out/r2p_summary_${N}gpu.txt
 : > $S
 timeout 500 $TR --master-port 29581 scripts/multigpu_check.py > gpurun_out/r2p_multigpu_check_$N.log 2>&1; echo "multigpu_check $N rc=$?" | tee -a $S
 grep MULTIGPU gpurun_out/r2p_multigpu_check_$N.log
-timeout 300 $TR --master-port 29582 scripts/comm_microbench.py > gpurun_out/r2p_comm_microbench_$N.log 2>&1; echo "comm_microbench $N rc=$?" | tee -a $S
+[ -n "$SKIP_MICRO" ] || timeout 300 $TR --master-port 29582 scripts/comm_microbench.py > gpurun_out/r2p_comm_microbench_$N.log 2>&1; echo "comm_microbench $N rc=$?" | tee -a $S
 grep -E "^(Diagonal|Kronecker)" gpurun_out/r2p_comm_microbench_$N.log
 timeout 500 $TR --master-port 29583 bench.py --gpus $N --steps 10 --warmup 3 > gpurun_out/r2p_bench_${N}gpu.json 2> gpurun_out/r2p_bench_${N}gpu.err; echo "bench fhn $N rc=$?" | tee -a $S
 timeout 500 $TR --master-port 29584 bench.py --gpus $N --steps 10 --warmup 3 --workload brusselator > gpurun_out/r2p_bench_${N}gpu_brusselator.json 2> gpurun_out/r2p_bench_${N}gpu_brusselator.err; echo "bench brusselator $N rc=$?" | tee -a $S
-timeout 500 $TR --master-port 29585 bench.py --gpus $N --steps 10 --warmup 3 --dtype f32 --no-e2e > gpurun_out/r2p_bench_${N}gpu_f32.json 2> gpurun_out/r2p_bench_${N}gpu_f32.err; echo "bench f32 $N rc=$?" | tee -a $S
+[ -n "$SKIP_F32" ] || timeout 500 $TR --master-port 29585 bench.py --gpus $N --steps 10 --warmup 3 --dtype f32 --no-e2e > gpurun_out/r2p_bench_${N}gpu_f32.json 2> gpurun_out/r2p_bench_${N}gpu_f32.err; echo "bench f32 $N rc=$?" | tee -a $S
 python - <<PY
 import json
 for f in ("r2p_bench_${N}gpu.json", "r2p_bench_${N}gpu_brusselator.json", "r2p_bench_${N}gpu_f32.json"):

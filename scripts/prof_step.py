@@ -10,7 +10,7 @@ size = int(sys.argv[1]) if len(sys.argv) > 1 else 2048
 which = sys.argv[2] if len(sys.argv) > 2 else "both"
 iters = int(sys.argv[3]) if len(sys.argv) > 3 else 3
 dtype = {"f64": torch.float64, "f32": torch.float32}[sys.argv[4] if len(sys.argv) > 4 else "f64"]
-nu = 4; n = nu + 1
+nu = int(sys.argv[5]) if len(sys.argv) > 5 else 4; n = nu + 1
 prob = ivp.fhn_2d(dx=1.0/size, y0=np.zeros(2))
 d = 2*size*size
 g = torch.Generator(device="cuda").manual_seed(0)
@@ -22,10 +22,12 @@ if which in ("both", "dek1"):
     so = torch.empty_like(sc)
     for _ in range(iters):
         eng.dek1_attempt(0.0, 1e-4, mean, sc, 1e-4, 1e-2, mean_out=mo, sc_out=so, want_err_ref=True)
-if which in ("both", "ek0"):
+if which in ("both", "ek0", "ek0noref"):
+    # ek0noref: without the materialised reference_state vector (the solver's default: |mean[0]| is deferred), which is what
+    # bench.py's timed launches do -- the capture profiles/traffic.json records
     Cl = 1e-3*torch.randn((n, n), generator=g, device="cuda", dtype=dtype)
     for _ in range(iters):
-        eng.ek0_attempt(0.0, 1e-4, mean, Cl, 1e-4, 1e-2, mean_out=mo, want_ref=True)
+        eng.ek0_attempt(0.0, 1e-4, mean, Cl, 1e-4, 1e-2, mean_out=mo, want_ref=(which != "ek0noref"))
 if which in ("ek1ctl", "ek0ctl"):
     # the controller-driven (multi-attempt) instantiations: one launch of 2 attempts per iteration
     from tornadox_b200 import step
