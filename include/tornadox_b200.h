@@ -9,8 +9,9 @@
  *
  * as implemented by ``ek1.DiagonalEK1`` (tornadox/ek1.py:228-369) and ``ek0.KroneckerEK0``
  * (tornadox/ek0.py:152-193), plus the d-wide reduction of ``AdaptiveSteps.scale_error_estimate``
- * (tornadox/step.py:93-104) and the vector fields ``ivp.vanderpol / brusselator / lorenz96 / fhn_2d``
- * (tornadox/ivp.py:28-49, 219-265, 268-294, 409-505), which are evaluated inside the step kernels.
+ * (tornadox/step.py:93-104) and the vector fields of ``ivp.py`` (vanderpol, brusselator, lorenz96,
+ * fhn_2d, burgers_1d, wave_1d, threebody, pleiades: tornadox/ivp.py:28-505), which are evaluated inside the step kernels
+ * (any other vector field: TDX_IVP_EXTERNAL).
  *
  * Conventions
  *  - plain pointers and sizes only; every array pointer is a DEVICE pointer owned by the caller;
@@ -26,7 +27,7 @@
  *    kernels themselves (tdx_comm_*, flags TDX_STEP_COMM_PACK | TDX_STEP_COMM_REDUCE); a caller without peer access can
  *    still exchange the halo buffers and all-reduce the scalars itself (tdx_pack_halo + the three-phase entry points).
  *  - sums over the state dimension (error norm, sum of z^2) are formed from one partial per 256-coordinate tile (or per
- *    grid row of a 256-column strip) in a fixed order over 16 global chunks, so their bits do not depend on how many CTAs ran
+ *    block of 8 grid rows x 256 columns in the fused fhn_2d KroneckerEK0 kernel) in a fixed order over 16 global chunks, so their bits do not depend on how many CTAs ran
  *    and -- when the shard boundaries fall on chunk boundaries, e.g. 2 / 4 / 8 equal shards of a 2048 x 2048 grid -- not
  *    on the number of GPUs either: the accepted-step sequence is identical at 1 / 2 / 4 / 8 GPUs.
  */

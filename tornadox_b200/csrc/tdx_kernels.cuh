@@ -14,7 +14,7 @@ namespace tdx {
 #define TDX_MIN_BLOCKS_N3 4
 #endif
 #ifndef TDX_MIN_BLOCKS_N4
-#define TDX_MIN_BLOCKS_N4 3
+#define TDX_MIN_BLOCKS_N4 2
 #endif
 #ifndef TDX_MIN_BLOCKS
 #define TDX_MIN_BLOCKS 2
@@ -343,6 +343,7 @@ __global__ void __launch_bounds__(kThreads, DekSmem<T, N>::MIN_BLOCKS) dek1_kern
     constexpr size_t SC_STRIDE = L::sc_bytes() / sizeof(T);
     __shared__ int s_flag, s_ok;
     __shared__ unsigned int s_next[2];            // dynamic tile hand-out: the tile after next, fetched one iteration ahead
+    __shared__ int s_pending[2];                  // the tile whose 256 terms wait in s_term[slot] for the next barrier (-1: none)
     __shared__ T s_p[N], s_pinv[N], s_dt;         // kCtl: the step's vectors, rebuilt from the controller block before each attempt
     __shared__ int s_cur, s_out;
     __shared__ unsigned long long s_epoch0;
@@ -410,8 +411,9 @@ __global__ void __launch_bounds__(kThreads, DekSmem<T, N>::MIN_BLOCKS) dek1_kern
             else return (a.c);
         }();
         const unsigned long long hseq = a.wait.seq + (unsigned long long)att;          // halo sequence number of this attempt
-        const T* halo_lo = a.halo_lo ? a.halo_lo + (long long)(hseq & 1ull) * a.halo_parity_stride : nullptr;
-        const T* halo_hi = a.halo_hi ? a.halo_hi + (long long)(hseq & 1ull) * a.halo_parity_stride : nullptr;
+        // halo buffers of this attempt's parity: formed where they are used (two long-lived pointers less in a kernel that sits
+        // at its register cap at every order)
+        const bool halo_odd = (hseq & 1ull) != 0ull;
 
         // issue the streaming load of one tile's 32 factor blocks of this warp into a slot; returns whether the
         // bulk (TMA) path was used (warp-uniform), in which case the data lands on the slot's mbarrier
@@ -460,8 +462,10 @@ __global__ void __launch_bounds__(kThreads, DekSmem<T, N>::MIN_BLOCKS) dek1_kern
         unsigned tile = kComm ? (gridDim.x - 1u - blockIdx.x) : blockIdx.x;
         const bool unit_mode = a.red.unit != nullptr;
         const bool dyn_tiles = a.tile_counter != nullptr;
-        double legacy_acc = 0.0;           // per-thread running sum (launches over a part of the tiles: per-CTA partials)
-        int pending_unit = -1;             // CTA-uniform: the tile whose warp sums wait in s_red for the next barrier
+        // launches over a part of the tiles (interior / rim pairs) keep per-CTA partials: the per-thread running sum lives in
+        // this thread's own s_term slot, not in two registers of every instantiation
+        if (!unit_mode) s_term[threadIdx.x] = 0.0;
+        if (threadIdx.x == 0) s_pending[0] = s_pending[1] = -1;      // (read only after a later barrier)
         bool cur_bulk = false;
         if (tile < a.num_tiles) cur_bulk = stage_in(tile_coord<Shape>(g, a.ranges.tile(tile), a.tiles_x), 0);
 
@@ -469,14 +473,17 @@ __global__ void __launch_bounds__(kThreads, DekSmem<T, N>::MIN_BLOCKS) dek1_kern
         // the one the next barrier waits for) adds the 256 terms in a fixed order -- lane l the eight warps' terms of lane l in a
         // tree, then the shuffle tree over the lanes.  A fixed function of the tile's coordinates, whoever computes it.
         auto flush_tile_partial = [&](unsigned it_prev) {
-            if (pending_unit >= 0) {
-                if (w == (int)(it_prev & (unsigned)(kWarps - 1))) {
+            if (w == (int)(it_prev & (unsigned)(kWarps - 1))) {
+                const int pending = s_pending[it_prev & 1u];
+                if (pending >= 0) {
                     const double* v = s_term + (it_prev & 1u) * kThreads + lane;
                     double x = ((v[0] + v[32]) + (v[64] + v[96])) + ((v[128] + v[160]) + (v[192] + v[224]));
                     x = warp_sum(x);
-                    if (lane == 0) a.red.unit[pending_unit] = x;
+                    if (lane == 0) {
+                        a.red.unit[pending] = x;
+                        s_pending[it_prev & 1u] = -1;
+                    }
                 }
-                pending_unit = -1;
             }
         };
         static_assert(kWarps == 8, "the tile partial adds eight warps' terms");
@@ -503,7 +510,9 @@ __global__ void __launch_bounds__(kThreads, DekSmem<T, N>::MIN_BLOCKS) dek1_kern
             T mp[N], fx, jac, raw0;
             {
                 FrontRegs<IVP, T, N> fr;
-                front_load<IVP, T, N, true, kCtl>(g, c, mean_in, halo_lo, halo_hi, cur, fr);
+                const long long hoff = halo_odd ? a.halo_parity_stride : 0ll;
+                front_load<IVP, T, N, true, kCtl>(g, c, mean_in, a.halo_lo ? a.halo_lo + hoff : nullptr,
+                                                  a.halo_hi ? a.halo_hi + hoff : nullptr, cur, fr);
                 front_eval<IVP, T, N>(g, c, cur, fr, s_at, mp, fx, jac);
                 raw0 = fr.raw[0];
             }
@@ -601,7 +610,7 @@ __global__ void __launch_bounds__(kThreads, DekSmem<T, N>::MIN_BLOCKS) dek1_kern
                     ratio_sq = ratio * ratio;                              // step.py:101-104
                 }
             }
-            if (!unit_mode) legacy_acc += ratio_sq;
+            if (!unit_mode) s_term[threadIdx.x] += ratio_sq;
 
             // (4) stream the updated blocks back
             if (bulk_out) {
@@ -637,7 +646,7 @@ __global__ void __launch_bounds__(kThreads, DekSmem<T, N>::MIN_BLOCKS) dek1_kern
             if (unit_mode && (c.want_norm || (kCtl && kComm && a.reduce.world > 0))) {
                 // the coordinate's share of the norm: one shared-memory store now, the tile's sum after the next barrier
                 s_term[(it & 1u) * kThreads + threadIdx.x] = ratio_sq;
-                pending_unit = (int)tile_id;
+                if (threadIdx.x == 0) s_pending[it & 1u] = (int)tile_id;
             }
             if (dyn_tiles && threadIdx.x == 0) s_next[(it + 1u) & 1u] = fetched;
             tile = next;
@@ -677,7 +686,7 @@ __global__ void __launch_bounds__(kThreads, DekSmem<T, N>::MIN_BLOCKS) dek1_kern
 #endif
         if (threadIdx.x == 0 && poisoned) {           // stale halos: the attempt must not be accepted anywhere
             if (unit_mode) a.red.unit[a.ranges.tile(kComm ? (gridDim.x - 1u - blockIdx.x) : blockIdx.x)] = nan("");
-            else legacy_acc = nan("");
+            else s_term[threadIdx.x] = nan("");
         }
         double total = 0.0;
         bool fin = false;                             // thread 0 of the last CTA
@@ -697,7 +706,7 @@ __global__ void __launch_bounds__(kThreads, DekSmem<T, N>::MIN_BLOCKS) dek1_kern
                 if (fin && c.want_norm && a.out_sum) *a.out_sum = total;
             }
         } else {
-            fin = grid_sum_cta(legacy_acc, s_red, a.partials, a.ticket, c.want_norm ? a.out_sum : nullptr);
+            fin = grid_sum_cta(s_term[threadIdx.x], s_red, a.partials, a.ticket, c.want_norm ? a.out_sum : nullptr);
         }
         if constexpr (kCtl) {
             if (fin) {
