@@ -245,3 +245,66 @@ def test_scripts_compile():
     assert len(names) >= 8
     for path in names:
         py_compile.compile(str(path), doraise=True)
+
+
+def test_shard_boundaries_sit_on_the_summation_grid_where_the_size_allows():
+    """engine.shard_range / reduction_is_sharding_independent (step.py:93-104 is ONE norm over all coordinates; the kernels add
+    one partial per work unit in 16 global chunks, csrc/tdx_device.cuh RedPlan): BASELINE's large grids cut into 2 / 4 / 8 equal
+    shards are aligned, sizes that cannot be cut that way are reported as such, and every split still covers the axis."""
+    from tornadox_b200 import engine, ivp
+
+    big = ivp.fhn_2d(dx=1.0 / 2048, y0=np.zeros(2)).spec
+    for world in (1, 2, 4, 8, 16):
+        assert engine.reduction_is_sharding_independent(big, world)
+        bounds = [engine.shard_range(big, r, world) for r in range(world)]
+        assert bounds[0][0] == 0 and bounds[-1][1] == 2048
+        assert all(b[1] == c[0] for b, c in zip(bounds, bounds[1:]))
+        assert all(e - b == 2048 // world for b, e in bounds)
+    chain = ivp.brusselator(N=4096).spec
+    assert all(engine.reduction_is_sharding_independent(chain, w) for w in (2, 4, 8))
+    assert not engine.reduction_is_sharding_independent(ivp.brusselator(N=400).spec, 8)
+    assert not engine.reduction_is_sharding_independent(ivp.fhn_2d(dx=1.0 / 50, y0=np.zeros(2)).spec, 2)
+    # small / odd sizes: balanced to within one row, still a partition
+    odd = ivp.fhn_2d(dx=1.0 / 50, y0=np.zeros(2)).spec
+    bounds = [engine.shard_range(odd, r, 3) for r in range(3)]
+    assert bounds[0][0] == 0 and bounds[-1][1] == 50 and all(b[1] == c[0] for b, c in zip(bounds, bounds[1:]))
+    # the fused fhn KroneckerEK0 kernel sums per 8-row block on large grids only (a function of the GLOBAL grid)
+    assert engine._ek0_row_block(2048, 8) == 8 and engine._ek0_row_block(256, 1) == 1 and engine._ek0_row_block(1024, 4) == 8
+
+
+def test_chunk_ordered_sum_is_independent_of_the_number_of_ranks():
+    """A NumPy model of the kernels' summation order (reduce_units in csrc/tdx_device.cuh): unit partials -> 16 chunk sums (32
+    lane-strided sequential sums, xor-shuffle tree) -> total in (rank, chunk) order.  With shard boundaries on chunk boundaries
+    the total has the same bits for 1, 2, 4, 8 ranks; the plain left-to-right sum of the same numbers does not."""
+    rng = np.random.default_rng(0)
+    units = 4096
+    part = rng.uniform(size=units) * 10.0 ** rng.integers(-6, 6, size=units)
+
+    def chunk_sum(v):
+        lanes = np.zeros(32)
+        for lane in range(32):
+            acc = 0.0
+            for x in v[lane::32]:
+                acc += x
+            lanes[lane] = acc
+        o = 16
+        while o:
+            lanes = lanes + lanes[np.arange(32) ^ o]
+            o >>= 1
+        return float(lanes[0])
+
+    def total(world):
+        out = 0.0
+        for r in range(world):                       # every rank sends the sums of the chunks it owns ...
+            lo, hi = r * units // world, (r + 1) * units // world
+            for c in range(16):
+                b0, b1 = c * units // 16, (c + 1) * units // 16
+                b0, b1 = max(b0, lo), min(b1, hi)
+                if b0 < b1:
+                    out += chunk_sum(part[b0:b1])     # ... and everybody adds them in (rank, chunk) order
+        return out
+
+    ref = total(1)
+    assert all(total(w) == ref for w in (2, 4, 8, 16))
+    # 3 ranks do not sit on the chunk grid: deterministic, but not the single-GPU bits in general
+    assert abs(total(3) - ref) <= 1e-12 * abs(ref)
