@@ -533,7 +533,12 @@ def run_mine(args):
             parity[name] = parity_check(torch, args, sol, state0, dt, problem, world, rank, dev)
         if not args.no_e2e:
             if name == args.solver:
-                results[name]["e2e_resident"] = e2e_resident_solve(torch, sol, state, dt, problem, world, dev, d, args.steps)
+                try:
+                    results[name]["e2e_resident"] = e2e_resident_solve(torch, sol, state, dt, problem, world, dev, d, args.steps)
+                except FloatingPointError as exc:
+                    # fp32 at this problem's first steps: the error estimate leaves fp32's exponent range and
+                    # the accept / reject loop refuses to go on, as it should
+                    results[name]["e2e_resident"] = {"failed": str(exc)}
             torch.cuda.empty_cache()
             results[name]["e2e"] = e2e_host_buffers(torch, sol, state, dt, problem, world, dev, d, args.steps)
         del sol, state
