@@ -46,12 +46,8 @@ struct Consts {
 // (ld.global.nc) is not coherent within a kernel; single-attempt kernels keep it.
 template <bool kCoherent, typename T>
 __device__ __forceinline__ T ld_state(const T* p) {
-#ifdef TDX_EXP_CTL_LDG      // timing experiment only (NOT coherent across the attempts of a multi-attempt kernel)
-    return __ldg(p);
-#else
     if constexpr (kCoherent) return __ldcg(p);
     else return __ldg(p);
-#endif
 }
 
 // The constants of one attempt as a multi-attempt (controller-driven) kernel sees them: what comes with the launch (Ql,
@@ -905,8 +901,8 @@ __device__ __forceinline__ bool spin_until(const unsigned long long* flag, unsig
 // the same at GPU scope (in-kernel grid barriers)
 __device__ __forceinline__ bool spin_until_gpu(const unsigned long long* flag, unsigned long long seq,
                                                unsigned long long timeout_ns = kDefaultWaitNs) {
-    // Poll with RELAXED loads and fence once the value is there: an acquire load per poll makes the SM invalidate its L1 and
-    // order its memory pipeline every time, which the other CTA of the SM (still working on its tiles) pays for.
+    // Poll with RELAXED loads and fence once the value is there (an acquire load per poll makes the SM invalidate its L1 every
+    // time; measured: no difference for the CTA that shares the SM, kept because it is the cheaper protocol).
     if (ld_relaxed_gpu(flag) >= seq) {
         fence_acq_rel_gpu();
         return true;
@@ -914,16 +910,11 @@ __device__ __forceinline__ bool spin_until_gpu(const unsigned long long* flag, u
     const unsigned long long t0 = global_timer_ns();
     unsigned int spins = 0;
     while (ld_relaxed_gpu(flag) < seq) {
-#ifdef TDX_POLL_SLOW            // experiment: never poll back to back
-        __nanosleep(400);
-        if ((++spins & 255u) == 0u && global_timer_ns() - t0 > (timeout_ns ? timeout_ns : kDefaultWaitNs)) return false;
-#else
         // the release is at most a few microseconds away in the common case: poll back to back first
         if (++spins > 64u) {
             if (global_timer_ns() - t0 > (timeout_ns ? timeout_ns : kDefaultWaitNs)) return false;
             __nanosleep(32);
         }
-#endif
     }
     fence_acq_rel_gpu();
     return true;

@@ -498,8 +498,9 @@ __global__ void __maxnreg__(TDX_EK0_MAXREG) ek0_fused_fhn_kernel(const __grid_co
         };
 
         // one phase over this CTA's strips.  kUpdate = false: phase A (forward), true: phase B (backward).
-        // Every finalised grid row leaves ONE partial sum per strip (unit = (row, column block)): the lanes' terms through the
-        // shuffle tree, the warps through shared memory in warp order -- independent of strip boundaries and walking direction.
+        // Every finished row block (RB = 8: eight grid rows; RB = 1: every row) leaves ONE partial sum per column block: the
+        // threads' block sums through the shuffle tree, the warps through shared memory in warp order (see the note on row blocks
+        // above ek0_row_block) -- independent of strip boundaries, CTAs and GPUs.
         auto run_phase = [&](auto update_tag, const T (&K)[N], double* unit) {
             constexpr bool kUpdate = decltype(update_tag)::value;
             constexpr int NK = kUpdate ? N : 2;                 // rows of the predicted mean kept for the row being finalised

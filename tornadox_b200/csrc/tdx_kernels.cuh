@@ -448,8 +448,9 @@ __global__ void __launch_bounds__(kThreads, DekSmem<T, N>::MIN_BLOCKS) dek1_kern
             return bulk;
         };
 
-        // CTA b walks the virtual tiles (G-1-b), (G-1-b)+G, ...: the lowest block indices (scheduled first, always resident)
-        // have the shortest lists when tiles % G != 0, and they deliver this shard's halos before they start on them
+        // The lowest block indices deliver this shard's halos before they start on their tiles.  A CTA's first two tiles are
+        // fixed ((G-1-b) and (G-1-b)+G in the sharded instantiations, so that the halo-delivering CTAs start with the tiles
+        // handed out last); the others come from the tile counter, i.e. a CTA that starts late simply takes fewer of them.
         if (kComm && a.pack.enabled)
             for (int part = (int)blockIdx.x; part < 2 * kPackCtas; part += (int)gridDim.x)   // a small grid takes several parts per CTA
                 pack_halo_part<T, N, FullSync, kCtl>(g, c, mean_in, a.pack, a.pack.seq + (unsigned long long)att, part);

@@ -277,9 +277,7 @@ struct Launch {
                 } else {
                     constexpr auto kern = dek1_kernel<IVP, T, N, false, true>;      // one GPU: none of the peer-memory code paths
                     TDX_CUDA_TRY(persistent_grid<kern>(smem, a.num_tiles, ws.reserve_ctas, grid));
-                    static const bool plain = std::getenv("TDX_EXP_PLAIN_CTL_LAUNCH") != nullptr;    // experiments only
-                    if (plain) kern<<<grid, kThreads, smem, st>>>(a);
-                    else TDX_CUDA_TRY(cudaLaunchCooperativeKernel((const void*)kern, dim3(grid), dim3(kThreads), params, smem, st));
+                    TDX_CUDA_TRY(cudaLaunchCooperativeKernel((const void*)kern, dim3(grid), dim3(kThreads), params, smem, st));
                 }
             } else if (comm) {
                 constexpr auto kern = dek1_kernel<IVP, T, N, true>;
@@ -442,7 +440,7 @@ struct Launch {
         a.use_bulk = (g.cols % PADC == 0) && aligned16 ? 1 : 0;
         a.col_blocks = (unsigned)((g.cols + W - 1) / W);
         // strips are whole row blocks (8 grid rows, or single rows on small grids; aligned in global row numbers)
-        static const int forced_rb = std::getenv("TDX_EK0_RB") ? std::atoi(std::getenv("TDX_EK0_RB")) : 0;   // experiments only
+        static const int forced_rb = std::getenv("TDX_EK0_RB") ? std::atoi(std::getenv("TDX_EK0_RB")) : 0;   // A/B of the unit size (one GPU)
         const int rb = forced_rb ? forced_rb : ek0_row_block(g.grows, (int)a.col_blocks);
         if (rb == 8) return launch_fhn<kCtl, 8>(g, a, ws, st);
         return launch_fhn<kCtl, 1>(g, a, ws, st);
