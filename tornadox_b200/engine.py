@@ -552,7 +552,7 @@ class StepEngine:
     # ---- device-resident step controller (no host involvement between attempts) -------------------------------------
     def ctl_begin(self, rule, t0, dt0, tmax, nbuf=2, stop_at=None, follow=False):
         """Reset the device-resident controller.  ``nbuf``: size of the state ring; ``stop_at``: time stops
-        (odefilter.py:355-373); ``follow``: the host follows the running solve (``ctl_poll`` / ``ctl_consume``)."""
+        (odefilter.py:355-373); ``follow``: the host follows the running solve (``ctl_poll`` / ``ctl_history`` / ``ctl_abort``)."""
         opt = _lib.CtlOptions()
         opt.nbuf, opt.follow = int(nbuf), 1 if follow else 0
         stops = None
