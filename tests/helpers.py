@@ -110,7 +110,8 @@ GOLDEN_PATH = pathlib.Path(__file__).resolve().parent / "golden" / "reference_ve
 @functools.lru_cache(maxsize=1)
 def golden():
     out = {}
-    for path in (GOLDEN_PATH, GOLDEN_PATH.with_name("reference_vectors_small.npz")):   # disjoint keys (different problems)
+    # disjoint keys: different problems / (oracle/make_golden_ek0_const.py) ConstantSteps solves of the reference's KroneckerEK0
+    for path in (GOLDEN_PATH, GOLDEN_PATH.with_name("reference_vectors_small.npz"), GOLDEN_PATH.with_name("reference_vectors_ek0_const.npz")):
         with np.load(path) as data:
             out.update({k: data[k] for k in data.files})
     return out

@@ -226,3 +226,4 @@ def test_fp32_attempt_within_1e5(cuda_device, name):
     Rc = g[f"dense/{name}/ek0/cov_sqrtm"]
     assert_close(C @ C.T, Rc @ Rc.T, 5 * FP32_RTOL, "fp32 ek0 covariance")
     assert_close(float(new0.error_estimate), g[f"dense/{name}/ek0/error_estimate"], 5 * FP32_RTOL, "fp32 ek0 error estimate")
+

@@ -58,13 +58,17 @@ def test_golden_file_is_reproducible(tornadox, tmp_path, monkeypatch):
     monkeypatch.setattr(mg, "OUT_SMALL", tmp_path / "regen_small.npz")
     mg.main()
     mg.main(small=True)
+    import oracle.make_golden_ek0_const as mgc
+
+    monkeypatch.setattr(mgc, "OUT", tmp_path / "regen_ek0_const.npz")
+    mgc.main()
     from helpers import golden
 
     old = golden()
     seen = set()
-    for path in (tmp_path / "regen.npz", tmp_path / "regen_small.npz"):
+    for path in (tmp_path / "regen.npz", tmp_path / "regen_small.npz", tmp_path / "regen_ek0_const.npz"):
         with np.load(path) as new:
-            assert not (seen & set(new.files)), "the two fixture files must not share keys"
+            assert not (seen & set(new.files)), "the fixture files must not share keys"
             seen |= set(new.files)
             for k in new.files:
                 np.testing.assert_array_equal(new[k], old[k], err_msg=k)
