@@ -227,3 +227,30 @@ def test_fp32_attempt_within_1e5(cuda_device, name):
     assert_close(C @ C.T, Rc @ Rc.T, 5 * FP32_RTOL, "fp32 ek0 covariance")
     assert_close(float(new0.error_estimate), g[f"dense/{name}/ek0/error_estimate"], 5 * FP32_RTOL, "fp32 ek0 error estimate")
 
+
+@pytest.mark.parametrize("name", ["vanderpol", "lorenz96", "brusselator", "fhn_2d", "burgers_1d", "wave_1d"])
+@pytest.mark.parametrize("device_loop", [False, True])
+def test_kronecker_ek0_constant_steps_solve(cuda_device, name, device_loop):
+    """Five ConstantSteps steps of KroneckerEK0 against the reference's own solve (reference_vectors_ek0_const.npz): under the
+    host loop and with all five attempts inside persistent launches of the device-resident controller.  The first calibration
+    after an exact Taylor init is rounding noise, so the bounds carry the reference's own change under a 1-ulp change of y0
+    (stored next to the outputs; brusselator: 6e-8 for the mean, 9e-4 for the covariance)."""
+    from tornadox_b200 import ek0, step
+
+    g = golden()
+    key = f"solve/{name}/ek0_const"
+    dt = float(g[key + "/dt"])
+    p = product_problem(name)
+    p5 = p._replace(tmax=p.t0 + 5.0 * dt - 1e-12 * dt)
+    sol = ek0.KroneckerEK0(num_derivatives=3, steprule=step.ConstantSteps(dt))
+    ts, last, info = [], None, None
+    for state, info in sol.solution_generator(p5, device_loop=device_loop):
+        ts.append(float(state.t))
+        last = state
+    np.testing.assert_allclose(ts, g[key + "/ts"], rtol=1e-12, atol=0)
+    counters = [info[k] for k in ("num_f_evaluations", "num_df_evaluations", "num_df_diagonal_evaluations", "num_steps",
+                                  "num_attempted_steps")]
+    np.testing.assert_array_equal(counters, g[key + "/info"])
+    assert_close(_np(last.y.mean), g[key + "/final_mean"], max(1e-8, 100.0 * float(g[key + "/mean_noise"])), "final mean")
+    S, R = _np(last.y.cov_sqrtm_2), g[key + "/final_cov_sqrtm"]
+    assert_close(S @ S.T, R @ R.T, max(1e-7, 100.0 * float(g[key + "/cov_noise"])), "final covariance factor (as S S^T)")
